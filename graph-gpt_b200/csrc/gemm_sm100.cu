@@ -1,0 +1,491 @@
+// tcgen05 GEMM for the GraphGPT hot path (sm_100a).
+//
+//   C[M,N] = A[M,K] * B[N,K]^T      bf16 operands, fp32 accumulation in TMEM
+//
+// One persistent CTA per SM, 6 warps: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) and TMEM
+// owner, warps 2..5 = epilogue (TMEM -> registers -> fused epilogue -> HBM).  Tiles are 128 x BN x 64 with a
+// multi-stage smem ring (TMA SWIZZLE_128B) and two TMEM accumulator buffers so the epilogue of tile i overlaps
+// the MMAs of tile i+1.
+//
+// Operand majors cover the three GEMMs of a linear layer y = x W^T (W is nn.Linear's [out,in]):
+//   forward  y  = x  W^T : A = x  [T,in]  K-major,  B = W [out,in] K-major
+//   dgrad    dx = dy W   : A = dy [T,out] K-major,  B = W [out,in] read MN-major (K = out rows)
+//   wgrad    dW = dy^T x : A = dy [T,out] MN-major, B = x [T,in]   MN-major      (K = T rows)
+// so no transposed copies of weights or activations are ever made.
+//
+// Replaces (reference, all via torch/cuBLAS): q/k/v/o_proj HF modeling_llama.py:262-264,288; gate/up/down_proj
+// HF:182-184; n_token_proj modeling_pretrain.py:89-93; lm_head modeling_pretrain.py:218; and their autograd.
+#include "common.cuh"
+#include "../../include/ggpt_b200.h"
+
+namespace ggpt {
+
+enum : int { EPI_BF16 = 0, EPI_F32 = 1, EPI_RESID = 2, EPI_GEGLU = 3, EPI_QKV_ROPE = 4 };
+
+struct GemmParams {
+  int M, N, K;
+  int num_m_blocks, num_n_blocks, num_k_blocks;
+  int b_half_rows;      // GEGLU: row offset of the `up` half inside B (= N/2)
+  // epilogue
+  void* C;              // bf16 (EPI_BF16/GEGLU/QKV_ROPE) or f32 (EPI_F32/RESID) output
+  long long ldc;
+  void* C2;             // GEGLU: act = gelu(gate)*up, bf16 [M, N/2]
+  long long ldc2;
+  const float* resid;   // RESID: fp32 [M,N]
+  long long ldr;
+  const float* colscale;  // RESID: optional per-column scale (LayerScale lambda), fp32 [N]
+  const float* rowscale;  // RESID: optional per-row scale (DropPath keep/p), fp32 [M]
+  int accumulate;         // F32: C += acc
+  const int* pos;         // QKV_ROPE: position per row
+  const float* cos_tab;   // QKV_ROPE: [max_pos, 32]
+  const float* sin_tab;
+  int rope_cols;          // QKV_ROPE: rotate columns [0, rope_cols) in heads of 64
+};
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kGemmThreads = 192;
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int kABytes = BM * BK * 2;  // 16 KB
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kBarBytes = 256;
+  static constexpr int kTotal = kStages * kStageBytes + kBarBytes + 1024;  // +1024 alignment slack
+};
+
+__device__ __forceinline__ void store8_bf16(__nv_bfloat16* dst, const float* v) {
+  uint4 o;
+  o.x = pack_bf16(v[0], v[1]);
+  o.y = pack_bf16(v[2], v[3]);
+  o.z = pack_bf16(v[4], v[5]);
+  o.w = pack_bf16(v[6], v[7]);
+  *reinterpret_cast<uint4*>(dst) = o;
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using S = GemmSmem<BN>;
+  constexpr int kStages = S::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* bar_base = smem + kStages * S::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tfull_bar[0], 1);
+    mbar_init(&tfull_bar[1], 1);
+    mbar_init(&tempty_bar[0], 4);
+    mbar_init(&tempty_bar[1], 4);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 2 * BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.num_n_blocks) * BM;
+        const int nb = tile % p.num_n_blocks;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * S::kStageBytes;
+          uint8_t* sb = sa + S::kABytes;
+          mbar_expect_tx(&full_bar[stage], S::kStageBytes);
+          const int k0 = kb * BK;
+          if (!A_MN) {
+            tma_load_2d(sa, &tmA, &full_bar[stage], k0, m0);
+          } else {
+            tma_load_2d(sa, &tmA, &full_bar[stage], m0, k0);
+            tma_load_2d(sa + 8192, &tmA, &full_bar[stage], m0 + 64, k0);
+          }
+          if (EPI == EPI_GEGLU) {
+            // B rows: [gate tile | up tile], each BN/2 rows, from the two halves of the fused weight
+            const int nh = nb * (BN / 2);
+            tma_load_2d(sb, &tmB, &full_bar[stage], k0, nh);
+            tma_load_2d(sb + (BN / 2) * 128, &tmB, &full_bar[stage], k0, p.b_half_rows + nh);
+          } else if (!B_MN) {
+            tma_load_2d(sb, &tmB, &full_bar[stage], k0, nb * BN);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i)
+              tma_load_2d(sb + i * 8192, &tmB, &full_bar[stage], nb * BN + i * 64, k0);
+          }
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
+          const uint32_t sb = sa + S::kABytes;
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t adesc = A_MN ? umma_desc_sw128(sa + kk * 2048, 8192, 1024)
+                                        : umma_desc_sw128(sa + kk * 32, 16, 1024);
+            const uint64_t bdesc = B_MN ? umma_desc_sw128(sb + kk * 2048, 8192, 1024)
+                                        : umma_desc_sw128(sb + kk * 32, 16, 1024);
+            tc_mma_bf16(d_tmem, adesc, bdesc, idesc, (kb | kk) != 0 ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tc_commit(&tfull_bar[acc]);  // accumulator complete
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================== Epilogue warps (2..5) =====================
+    const int quad = warp & 3;            // TMEM lane quadrant this warp may access
+    const int row_in_tile = quad * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / p.num_n_blocks) * BM;
+      const int nb = tile % p.num_n_blocks;
+      const int row = m0 + row_in_tile;
+      const bool row_ok = row < p.M;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
+
+      if constexpr (EPI == EPI_BF16) {
+        const int n0 = nb * BN;
+        __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<long long>(row) * p.ldc + n0;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c, r);
+          tmem_ld_wait();
+          if (row_ok) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if (n0 + c + g * 8 < p.N) {
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
+                store8_bf16(crow + c + g * 8, v);
+              }
+            }
+          }
+        }
+      } else if constexpr (EPI == EPI_F32) {
+        const int n0 = nb * BN;
+        float* crow = reinterpret_cast<float*>(p.C) + static_cast<long long>(row) * p.ldc + n0;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c, r);
+          tmem_ld_wait();
+          if (row_ok) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              if (n0 + c + g * 4 < p.N) {
+                float4 o = make_float4(__uint_as_float(r[g * 4 + 0]), __uint_as_float(r[g * 4 + 1]),
+                                       __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3]));
+                float4* dst = reinterpret_cast<float4*>(crow + c + g * 4);
+                if (p.accumulate) {
+                  float4 old = *dst;
+                  o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                }
+                *dst = o;
+              }
+            }
+          }
+        }
+      } else if constexpr (EPI == EPI_RESID) {
+        const int n0 = nb * BN;
+        float* crow = reinterpret_cast<float*>(p.C) + static_cast<long long>(row) * p.ldc + n0;
+        const float* rrow = p.resid + static_cast<long long>(row) * p.ldr + n0;
+        const float rs = (p.rowscale != nullptr && row_ok) ? p.rowscale[row] : 1.0f;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c, r);
+          tmem_ld_wait();
+          if (row_ok) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              if (n0 + c + g * 4 < p.N) {
+                float4 res = *reinterpret_cast<const float4*>(rrow + c + g * 4);
+                float4 sc = make_float4(rs, rs, rs, rs);
+                if (p.colscale != nullptr) {
+                  float4 cs = *reinterpret_cast<const float4*>(p.colscale + n0 + c + g * 4);
+                  sc.x *= cs.x; sc.y *= cs.y; sc.z *= cs.z; sc.w *= cs.w;
+                }
+                float4 o;
+                o.x = fmaf(__uint_as_float(r[g * 4 + 0]), sc.x, res.x);
+                o.y = fmaf(__uint_as_float(r[g * 4 + 1]), sc.y, res.y);
+                o.z = fmaf(__uint_as_float(r[g * 4 + 2]), sc.z, res.z);
+                o.w = fmaf(__uint_as_float(r[g * 4 + 3]), sc.w, res.w);
+                *reinterpret_cast<float4*>(crow + c + g * 4) = o;
+              }
+            }
+          }
+        }
+      } else if constexpr (EPI == EPI_GEGLU) {
+        // tile columns [0,BN/2) = gate for fused columns nh.., [BN/2,BN) = matching up columns
+        const int nh = nb * (BN / 2);
+        __nv_bfloat16* gu = reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<long long>(row) * p.ldc;
+        __nv_bfloat16* act = reinterpret_cast<__nv_bfloat16*>(p.C2) + static_cast<long long>(row) * p.ldc2;
+        const int half_n = p.N / 2;
+#pragma unroll 1
+        for (int c = 0; c < BN / 2; c += 32) {
+          uint32_t rg[32], ru[32];
+          tmem_ld32(taddr + c, rg);
+          tmem_ld32(taddr + BN / 2 + c, ru);
+          tmem_ld_wait();
+          if (row_ok) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if (nh + c + g * 8 < half_n) {
+                float vg[8], vu[8], va[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  vg[j] = __uint_as_float(rg[g * 8 + j]);
+                  vu[j] = __uint_as_float(ru[g * 8 + j]);
+                  va[j] = gelu_erf(vg[j]) * vu[j];
+                }
+                if (p.C != nullptr) {
+                  store8_bf16(gu + nh + c + g * 8, vg);
+                  store8_bf16(gu + half_n + nh + c + g * 8, vu);
+                }
+                store8_bf16(act + nh + c + g * 8, va);
+              }
+            }
+          }
+        }
+      } else if constexpr (EPI == EPI_QKV_ROPE) {
+        const int n0 = nb * BN;
+        __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<long long>(row) * p.ldc + n0;
+        const int pos = row_ok ? p.pos[row] : 0;
+        const float* cs = p.cos_tab + static_cast<long long>(pos) * 32;
+        const float* sn = p.sin_tab + static_cast<long long>(pos) * 32;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 64) {
+          uint32_t r1[32], r2[32];
+          tmem_ld32(taddr + c, r1);
+          tmem_ld32(taddr + c + 32, r2);
+          tmem_ld_wait();
+          if (row_ok && n0 + c < p.N) {
+            const bool rot = (n0 + c) < p.rope_cols;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float o1[8], o2[8];
+              if (rot) {
+                const float4 c0 = *reinterpret_cast<const float4*>(cs + g * 8);
+                const float4 c1 = *reinterpret_cast<const float4*>(cs + g * 8 + 4);
+                const float4 s0 = *reinterpret_cast<const float4*>(sn + g * 8);
+                const float4 s1 = *reinterpret_cast<const float4*>(sn + g * 8 + 4);
+                const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float x1 = __uint_as_float(r1[g * 8 + j]);
+                  const float x2 = __uint_as_float(r2[g * 8 + j]);
+                  o1[j] = x1 * cc[j] - x2 * ss[j];   // q*cos + rotate_half(q)*sin, first half
+                  o2[j] = x2 * cc[j] + x1 * ss[j];   // second half
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  o1[j] = __uint_as_float(r1[g * 8 + j]);
+                  o2[j] = __uint_as_float(r2[g * 8 + j]);
+                }
+              }
+              store8_bf16(crow + c + g * 8, o1);
+              store8_bf16(crow + c + 32 + g * 8, o2);
+            }
+          }
+        }
+      }
+
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host launcher
+// ---------------------------------------------------------------------------------------------
+template <int BN, bool A_MN, bool B_MN, int EPI>
+static int launch_gemm(const void* A, long long lda, const void* B, long long ldb, GemmParams p, cudaStream_t stream) {
+  using S = GemmSmem<BN>;
+  CUtensorMap tmA, tmB;
+  int rc;
+  // A: K-major -> global [M rows, K cols], box 128 x 64.  MN-major -> global [K rows, M cols], box 64 x 64.
+  if (!A_MN) rc = make_tmap_2d_bf16(&tmA, A, p.M, p.K, lda, BM, 64);
+  else rc = make_tmap_2d_bf16(&tmA, A, p.K, p.M, lda, 64, 64);
+  if (rc) return rc;
+  const uint64_t b_rows_total = static_cast<uint64_t>(p.N);
+  if (EPI == EPI_GEGLU) rc = make_tmap_2d_bf16(&tmB, B, b_rows_total, p.K, ldb, BN / 2, 64);
+  else if (!B_MN) rc = make_tmap_2d_bf16(&tmB, B, b_rows_total, p.K, ldb, BN, 64);
+  else rc = make_tmap_2d_bf16(&tmB, B, p.K, b_rows_total, ldb, 64, 64);
+  if (rc) return rc;
+
+  p.num_m_blocks = (p.M + BM - 1) / BM;
+  if (EPI == EPI_GEGLU) p.num_n_blocks = (p.N / 2 + BN / 2 - 1) / (BN / 2);
+  else p.num_n_blocks = (p.N + BN - 1) / BN;
+  p.num_k_blocks = (p.K + BK - 1) / BK;
+  p.b_half_rows = p.N / 2;
+  const int tiles = p.num_m_blocks * p.num_n_blocks;
+  int grid = num_sms();
+  if (grid > tiles) grid = tiles;
+
+  auto kern = gemm_kernel<BN, A_MN, B_MN, EPI>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+    if (e != cudaSuccess) {
+      set_error("gemm: cudaFuncSetAttribute(%d B smem) failed: %s", S::kTotal, cudaGetErrorString(e));
+      return -2;
+    }
+    attr_set = true;
+  }
+  kern<<<grid, kGemmThreads, S::kTotal, stream>>>(tmA, tmB, p);
+  return check_launch("gemm_kernel");
+}
+
+template <int BN, int EPI>
+static int dispatch_major(int a_mn, int b_mn, const void* A, long long lda, const void* B, long long ldb,
+                          const GemmParams& p, cudaStream_t s) {
+  if (!a_mn && !b_mn) return launch_gemm<BN, false, false, EPI>(A, lda, B, ldb, p, s);
+  if (!a_mn && b_mn) return launch_gemm<BN, false, true, EPI>(A, lda, B, ldb, p, s);
+  if (a_mn && b_mn) return launch_gemm<BN, true, true, EPI>(A, lda, B, ldb, p, s);
+  set_error("gemm: operand majors (A MN-major, B K-major) are not instantiated");
+  return -1;
+}
+
+static int check_common(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K) {
+  GGPT_REQUIRE(A && B, "gemm: null operand");
+  GGPT_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  GGPT_REQUIRE((lda % 8) == 0 && (ldb % 8) == 0, "gemm: lda/ldb must be multiples of 8 elements (TMA 16 B stride), got %lld %lld", lda, ldb);
+  GGPT_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
+               "gemm: operands must be 16-byte aligned");
+  return 0;
+}
+
+}  // namespace ggpt
+
+using namespace ggpt;
+
+extern "C" {
+
+int ggpt_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major,
+                   void* C, long long ldc, int out_f32, int accumulate, int M, int N, int K, void* stream) {
+  if (int rc = check_common(A, lda, B, ldb, M, N, K)) return rc;
+  GGPT_REQUIRE(C != nullptr, "gemm: null output");
+  GGPT_REQUIRE(ldc % 8 == 0 && ldc >= ((N + 7) / 8) * 8, "gemm: ldc=%lld must be a multiple of 8 and >= N rounded up to 8", ldc);
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.accumulate = accumulate;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool wide = N > 128;
+  if (out_f32) {
+    return wide ? dispatch_major<256, EPI_F32>(a_mn_major, b_mn_major, A, lda, B, ldb, p, s)
+                : dispatch_major<128, EPI_F32>(a_mn_major, b_mn_major, A, lda, B, ldb, p, s);
+  }
+  GGPT_REQUIRE(!accumulate, "gemm: accumulate needs an fp32 output");
+  return wide ? dispatch_major<256, EPI_BF16>(a_mn_major, b_mn_major, A, lda, B, ldb, p, s)
+              : dispatch_major<128, EPI_BF16>(a_mn_major, b_mn_major, A, lda, B, ldb, p, s);
+}
+
+int ggpt_gemm_bf16_resid(const void* A, long long lda, const void* B, long long ldb, const float* resid,
+                         long long ldr, const float* colscale, const float* rowscale, float* out, long long ldo,
+                         int M, int N, int K, void* stream) {
+  if (int rc = check_common(A, lda, B, ldb, M, N, K)) return rc;
+  GGPT_REQUIRE(resid && out, "gemm_resid: null residual/output");
+  GGPT_REQUIRE(N % 4 == 0 && ldr % 4 == 0 && ldo % 4 == 0, "gemm_resid: N, ldr, ldo must be multiples of 4");
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K; p.C = out; p.ldc = ldo; p.resid = resid; p.ldr = ldr;
+  p.colscale = colscale; p.rowscale = rowscale;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return N > 128 ? launch_gemm<256, false, false, EPI_RESID>(A, lda, B, ldb, p, s)
+                 : launch_gemm<128, false, false, EPI_RESID>(A, lda, B, ldb, p, s);
+}
+
+int ggpt_gemm_bf16_geglu(const void* A, long long lda, const void* Wgu, long long ldb, void* gu, long long ldgu,
+                         void* act, long long ldact, int M, int N2, int K, void* stream) {
+  if (int rc = check_common(A, lda, Wgu, ldb, M, N2, K)) return rc;
+  GGPT_REQUIRE(act != nullptr, "gemm_geglu: null act output");
+  GGPT_REQUIRE(N2 % 16 == 0, "gemm_geglu: fused width must be a multiple of 16, got %d", N2);
+  GGPT_REQUIRE(ldact % 8 == 0 && (gu == nullptr || ldgu % 8 == 0), "gemm_geglu: ld must be a multiple of 8");
+  GemmParams p{};
+  p.M = M; p.N = N2; p.K = K; p.C = gu; p.ldc = ldgu; p.C2 = act; p.ldc2 = ldact;
+  return launch_gemm<256, false, false, EPI_GEGLU>(A, lda, Wgu, ldb, p, static_cast<cudaStream_t>(stream));
+}
+
+int ggpt_gemm_bf16_qkv_rope(const void* A, long long lda, const void* Wqkv, long long ldb, void* qkv, long long ldc,
+                            const int* pos, const float* cos_tab, const float* sin_tab, int rope_cols, int M, int N,
+                            int K, void* stream) {
+  if (int rc = check_common(A, lda, Wqkv, ldb, M, N, K)) return rc;
+  GGPT_REQUIRE(qkv && pos && cos_tab && sin_tab, "gemm_qkv_rope: null pointer");
+  GGPT_REQUIRE(N % 64 == 0 && rope_cols % 64 == 0 && ldc % 8 == 0, "gemm_qkv_rope: N and rope_cols must be multiples of 64 (head_dim)");
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K; p.C = qkv; p.ldc = ldc; p.pos = pos; p.cos_tab = cos_tab; p.sin_tab = sin_tab;
+  p.rope_cols = rope_cols;
+  return launch_gemm<256, false, false, EPI_QKV_ROPE>(A, lda, Wqkv, ldb, p, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

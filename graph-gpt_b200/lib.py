@@ -1,0 +1,87 @@
+"""ctypes binding of libggpt_b200.so — the only way the Python host code reaches the CUDA kernels.
+
+There is deliberately no fallback: if the library is missing or a call fails, a RuntimeError is raised.
+Function prototypes are parsed from include/ggpt_b200.h so the header stays the single source of truth.
+"""
+import ctypes
+import os
+import re
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libggpt_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "ggpt_b200.h")
+
+_CTYPES = {
+    "int": ctypes.c_int,
+    "long long": ctypes.c_longlong,
+    "float": ctypes.c_float,
+    "double": ctypes.c_double,
+    "uint64_t": ctypes.c_uint64,
+    "unsigned long long": ctypes.c_uint64,
+}
+
+
+def parse_header(path=HEADER_PATH):
+    """Return {name: (restype, [argtypes], [argnames])} for every function declared in the header."""
+    text = open(path).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"//.*", "", text)
+    protos = {}
+    for m in re.finditer(r"(const char\*|int|void)\s+(ggpt_\w+)\s*\(([^)]*)\)\s*;", text, flags=re.S):
+        ret, name, args = m.group(1), m.group(2), m.group(3)
+        restype = {"int": ctypes.c_int, "void": None, "const char*": ctypes.c_char_p}[ret]
+        argtypes, argnames = [], []
+        args = " ".join(args.split())
+        if args and args != "void":
+            for a in args.split(","):
+                a = a.strip()
+                if "*" in a:
+                    argtypes.append(ctypes.c_void_p)
+                    argnames.append(a.split("*")[-1].strip())
+                else:
+                    parts = a.replace("const ", "").split()
+                    ty = " ".join(parts[:-1])
+                    argtypes.append(_CTYPES[ty])
+                    argnames.append(parts[-1])
+        protos[name] = (restype, argtypes, argnames)
+    return protos
+
+
+class _Lib:
+    def __init__(self):
+        self._dll = None
+        self._protos = None
+
+    def load(self):
+        if self._dll is not None:
+            return self._dll
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python graph-gpt_b200/build.py` "
+                "(there is no CPU / PyTorch fallback for the GraphGPT hot path)"
+            )
+        dll = ctypes.CDLL(LIB_PATH)
+        self._protos = parse_header()
+        for name, (restype, argtypes, _) in self._protos.items():
+            fn = getattr(dll, name)  # AttributeError if the .so lacks a declared symbol
+            fn.restype = restype
+            fn.argtypes = argtypes
+        self._dll = dll
+        return dll
+
+    def last_error(self):
+        return self.load().ggpt_last_error().decode(errors="replace")
+
+    def call(self, name, *args):
+        dll = self.load()
+        rc = getattr(dll, name)(*args)
+        if rc != 0:
+            raise RuntimeError(f"{name} failed (rc={rc}): {self.last_error()}")
+
+    def __getattr__(self, name):
+        if name.startswith("ggpt_"):
+            return lambda *args: self.call(name, *args)
+        raise AttributeError(name)
+
+
+lib = _Lib()
