@@ -1,0 +1,202 @@
+"""Generate the golden fixtures that pin oracle/graphgpt_oracle.py to the REFERENCE's own outputs.
+
+Runs only in the build container (needs /root/reference): imports the unmodified reference model classes through
+ref_shim.py, instantiates them on CPU in fp32/eval with seeded weights, feeds seeded synthetic batches and stores
+{config, inputs, state_dict, outputs, gradients} as tests/golden/<case>.pt.   Re-run:  python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+from ref_shim import load_reference  # noqa: E402
+
+from graphgpt_b200 import synth  # noqa: E402
+
+GRAD_KEYS = [
+    "model.embed_tokens.weight", "model.layers.0.self_attn.q_proj.weight", "model.layers.0.self_attn.v_proj.weight",
+    "model.layers.0.mlp.gate_proj.weight", "model.layers.1.mlp.down_proj.weight",
+    "model.layers.1.input_layernorm.weight", "model.norm.weight", "lm_head.weight", "n_token_proj.weight",
+    "score.weight", "stacked_feat_agg.weight", "model.layers.0.lambda_1",
+]
+
+
+def base_cfg(**kw):
+    cfg = dict(vocab_size=300, hidden_size=64, intermediate_size=256, num_hidden_layers=2, num_attention_heads=1,
+               num_key_value_heads=1, head_dim=64, hidden_act="gelu", max_position_embeddings=256, rms_norm_eps=1e-6,
+               rope_theta=10000.0, attention_bias=False, mlp_bias=False, tie_word_embeddings=False, use_cache=False,
+               pad_token_id=0, bos_token_id=20, eos_token_id=19, causal_attention=False, stacked_feat=1,
+               stack_method="short", stacked_feat_agg_method="sum", next_n_token=1, attention_dropout=0.1)
+    cfg.update(kw)
+    if "num_attention_heads" not in kw:
+        cfg["num_attention_heads"] = cfg["num_key_value_heads"] = cfg["hidden_size"] // 64
+    return cfg
+
+
+def t(x):
+    return torch.from_numpy(np.ascontiguousarray(x))
+
+
+CASES = {}
+
+
+def case(name):
+    def deco(fn):
+        CASES[name] = fn
+        return fn
+    return deco
+
+
+@case("c1_toy_smtp_2d")
+def _c1():
+    """C1: toy 2L/64d, F=1, right-padded 2-D mask, bidirectional SMTP."""
+    cfg = base_cfg()
+    b = synth.make_batch(4, 64, layout="unpacked", vocab=synth.TOY_VOCAB, seed=11)
+    return "pretrain", cfg, dict(input_ids=t(b["input_ids"]), attention_mask=t(b["attention_mask"]), labels=t(b["labels"]))
+
+
+@case("c2_smtp_stacked_2d")
+def _c2():
+    """C2-shaped: 2L/128d, F=13, V=756, unpacked right-padded."""
+    cfg = base_cfg(vocab_size=756, hidden_size=128, intermediate_size=512, stacked_feat=13, next_n_token=13)
+    b = synth.make_batch(3, 64, layout="unpacked", seed=12)
+    return "pretrain", cfg, dict(input_ids=t(b["input_ids"]), attention_mask=t(b["attention_mask"]), labels=t(b["labels"]))
+
+
+@case("c2_smtp_stacked_packed3d")
+def _c2p():
+    """C2 packed: block-diagonal [N,S,S] mask (tokenizer_utils.py:351-355)."""
+    cfg = base_cfg(vocab_size=756, hidden_size=128, intermediate_size=512, stacked_feat=13, next_n_token=13)
+    b = synth.make_batch(2, 96, layout="packed", seed=13)
+    return "pretrain", cfg, dict(input_ids=t(b["input_ids"]), attention_mask=t(b["attention_mask"]), labels=t(b["labels"]))
+
+
+@case("c5_ntp_causal")
+def _c5():
+    """C5-shaped: causal NTP, 2 heads, 2-D padding mask combined with causal inside the backbone."""
+    cfg = base_cfg(vocab_size=756, hidden_size=128, intermediate_size=512, stacked_feat=13, next_n_token=13,
+                   causal_attention=True)
+    b = synth.make_batch(3, 64, layout="unpacked", task="ntp", seed=14)
+    lab = b["labels"].copy()
+    lab[b["attention_mask"] == 0] = -100
+    return "pretrain", cfg, dict(input_ids=t(b["input_ids"]), attention_mask=t(b["attention_mask"]), labels=t(lab))
+
+
+@case("c2_dlm_weighted")
+def _dlm():
+    """dLM-weighted SMTP loss (sample_wgt given -> per-feat lvl head + sum/(N*S*F), modeling_pretrain.py:229-236)."""
+    cfg = base_cfg(vocab_size=756, hidden_size=128, intermediate_size=512, stacked_feat=13, next_n_token=13)
+    b = synth.make_batch(3, 64, layout="unpacked", seed=15)
+    wgt = torch.tensor([1.7, 0.4, 3.1])
+    return "pretrain", cfg, dict(input_ids=t(b["input_ids"]), attention_mask=t(b["attention_mask"]), labels=t(b["labels"]),
+                                 sample_wgt=wgt)
+
+
+@case("c2_gated_agg")
+def _gated():
+    """gated stacked-feature aggregation (modeling_common.py:128-129)."""
+    cfg = base_cfg(vocab_size=756, hidden_size=64, intermediate_size=256, stacked_feat=13, next_n_token=13,
+                   stacked_feat_agg_method="gated")
+    b = synth.make_batch(2, 48, layout="unpacked", seed=16)
+    return "pretrain", cfg, dict(input_ids=t(b["input_ids"]), attention_mask=t(b["attention_mask"]), labels=t(b["labels"]))
+
+
+@case("c2_infer_all_entries")
+def _infer():
+    """labels=None: the head runs on every (n,s,f) entry (generation path, modeling_helpers.py:284-292)."""
+    cfg = base_cfg(vocab_size=756, hidden_size=64, intermediate_size=256, stacked_feat=13, next_n_token=13)
+    b = synth.make_batch(2, 32, layout="unpacked", seed=17)
+    return "pretrain", cfg, dict(input_ids=t(b["input_ids"]), attention_mask=t(b["attention_mask"]))
+
+
+@case("c3_ft_edge_cls")
+def _ft():
+    """C3-shaped fine-tune: F=4, 2 labels, last-token pooling, position_ids passed (training_utils.py:136-145)."""
+    cfg = base_cfg(vocab_size=1200, hidden_size=128, intermediate_size=512, stacked_feat=4, next_n_token=4,
+                   num_labels=2, problem_type="single_label_classification", pooling_method="last")
+    vocab = synth.VocabLayout(vocab_size=1200, scope=512, n_node_attr=2, n_edge_attr=1)
+    b = synth.make_batch(4, 64, layout="unpacked", task="ntp", vocab=vocab, seed=18)
+    labels = torch.tensor([1, 0, 1, 1])
+    return "finetune", cfg, dict(input_ids=t(b["input_ids"]), attention_mask=t(b["attention_mask"]),
+                                 position_ids=t(b["position_ids"]), task_labels=labels)
+
+
+@case("c3_ft_layerscale")
+def _ft_ls():
+    """ppa fine-tune variant with LayerScale (lsi=1, examples/edge_lvl/ppa_supervised.sh:22-25), eval mode so
+    DropPath is the identity.  Needs the dropout backbone utils_graphgpt.LlamaModel."""
+    cfg = base_cfg(vocab_size=1200, hidden_size=128, intermediate_size=512, stacked_feat=4, next_n_token=4,
+                   num_labels=2, problem_type="single_label_classification", pooling_method="last",
+                   layer_scale_init_value=1.0, path_pdrop=0.2)
+    vocab = synth.VocabLayout(vocab_size=1200, scope=512, n_node_attr=2, n_edge_attr=1)
+    b = synth.make_batch(3, 64, layout="unpacked", task="ntp", vocab=vocab, seed=19)
+    labels = torch.tensor([0, 1, 1])
+    return "finetune", cfg, dict(input_ids=t(b["input_ids"]), attention_mask=t(b["attention_mask"]),
+                                 position_ids=t(b["position_ids"]), task_labels=labels)
+
+
+def _patch_dropout_backbone():
+    """transformers 5.5.0's LlamaModel loop expects decoder layers to return a tensor; the reference's dropout
+    layer (utils_graphgpt.py:168-173) returns the 4.53-style tuple.  Unwrap it (SURVEY §8c caveat)."""
+    from src.models.graphgpt import utils_graphgpt
+    if getattr(utils_graphgpt.LlamaDecoderLayer, "_ggpt_patched", False):
+        return
+    orig = utils_graphgpt.LlamaDecoderLayer.forward
+
+    def fwd(self, hidden_states, *a, **k):
+        k.pop("past_key_values", None)
+        out = orig(self, hidden_states, *a, **k)
+        return out[0] if isinstance(out, tuple) else out
+
+    utils_graphgpt.LlamaDecoderLayer.forward = fwd
+    utils_graphgpt.LlamaDecoderLayer._ggpt_patched = True
+
+
+def main():
+    mp, mf, GraphGPTConfig = load_reference()
+    _patch_dropout_backbone()
+    only = set(sys.argv[1:])
+    for name, fn in CASES.items():
+        if only and name not in only:
+            continue
+        kind, cfgd, inputs = fn()
+        cfg = GraphGPTConfig(**cfgd)
+        cfg._attn_implementation = "eager"
+        torch.manual_seed(1000 + len(name))
+        model = (mp.GraphGPTPretrainBase if kind == "pretrain" else mf.GraphGPTTaskModel)(cfg).eval().float()
+        with torch.no_grad():  # make norm weights / lambdas non-trivial so their gradients and scaling are exercised
+            for n_, p in model.named_parameters():
+                if "layernorm" in n_ or n_.endswith("norm.weight"):
+                    p.add_(0.1 * torch.randn_like(p))
+                if "lambda_" in n_:
+                    p.mul_(1.0 + 0.2 * torch.randn_like(p))
+        out = model(**inputs)
+        rec = {"kind": kind, "config": cfgd, "inputs": inputs,
+               "state_dict": {k: v.detach().clone() for k, v in model.state_dict().items()}}
+        if kind == "pretrain":
+            rec["logits"] = out.head1_logits.detach().clone()
+            loss = out.head1_loss
+        else:
+            rec["task_logits"] = out.task_logits.detach().clone()
+            rec["hidden"] = out.hidden_states.detach().clone()
+            rec["task_hidden"] = out.task_hidden_states.detach().clone()
+            loss = out.task_loss
+        if loss is not None:
+            rec["loss"] = loss.detach().clone()
+            loss.backward()
+            named = dict(model.named_parameters())
+            rec["grads"] = {k: named[k].grad.detach().clone() for k in GRAD_KEYS if k in named and named[k].grad is not None}
+        path = os.path.join(HERE, name + ".pt")
+        torch.save(rec, path)
+        print(f"{name}: loss={None if loss is None else float(loss):.6f}" if loss is not None else f"{name}: no loss",
+              {k: tuple(v.shape) for k, v in rec.items() if torch.is_tensor(v)}, f"{os.path.getsize(path) / 1e6:.2f} MB")
+
+
+if __name__ == "__main__":
+    main()
