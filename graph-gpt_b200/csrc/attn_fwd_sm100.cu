@@ -1,0 +1,379 @@
+// Flash-style softmax attention forward on tcgen05 (sm_100a) for GraphGPT's padded / packed / causal sequences.
+//
+//   O[n, q, h, :] = softmax_k( Q[n,q,h,:] . K[n,k,h,:] / sqrt(64) + mask[n,q,k] ) V[n,k,h,:]
+//
+// The reference materialises an additive [N,1,S,S] mask (0 / finfo.min) and runs matmul-softmax-matmul
+// (HF:199-221 eager_attention_forward; mask from modeling_helpers.py:38-64).  Here the mask is a bit matrix
+// (1 bit per (q,k), built once per step by ggpt_attn_mask_build) plus a per-128x128-tile class
+// (0 = all masked -> tile skipped, 1 = all visible -> no mask loads, 2 = mixed), which covers right-padding,
+// block-diagonal packing, causal and any other 2-D/3-D mask the reference accepts without an O(S^2) fp tensor.
+//
+// One CTA per (128-query tile, head, sequence); 6 warps: TMA producer, MMA issuer, 4 softmax warps (one query row
+// per thread).  QK^T and PV run on tcgen05 with accumulators in TMEM; P goes through shared memory (bf16, 128B
+// swizzle) as the A operand of the PV MMA; V is consumed in place as an MN-major B operand.  Two CTAs fit per SM
+// (112 KB smem, 256 TMEM columns each) so one CTA's softmax overlaps the other's MMAs.
+#include "common.cuh"
+#include "../../include/ggpt_b200.h"
+
+namespace ggpt {
+
+constexpr int kAttThreads = 192;
+constexpr int kTileQ = 128;
+constexpr int kTileK = 128;
+constexpr int kHeadDim = 64;
+constexpr int kAttSmem = 16384 /*Q*/ + 2 * 16384 /*K*/ + 2 * 16384 /*V*/ + 32768 /*P*/ + 256 /*barriers*/;
+
+struct AttnFwdParams {
+  int N, S, H;
+  int n_qt, n_kt;
+  int mask_words;             // uint32 words per mask row (multiple of 4)
+  const uint32_t* mask_bits;  // [N, S, mask_words]
+  const uint8_t* tile_cls;    // [N, n_qt, n_kt]
+  __nv_bfloat16* out;         // [N*S, H*64]
+  long long ldo;
+  float* lse;                 // [N, H, S]  natural-log logsumexp of the scaled scores (for backward)
+  int q_col0, k_col0, v_col0; // column offsets of q/k/v inside the fused qkv row
+  float scale_log2;           // (1/sqrt(64)) * log2(e)
+};
+
+__global__ void __launch_bounds__(kAttThreads, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + 16384;
+  uint8_t* sV = smem + 16384 + 32768;
+  uint8_t* sP = smem + 16384 + 65536;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 16384 + 65536 + 32768);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;    // [2]
+  uint64_t* kv_empty = bars + 3;   // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* o_full = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
+  const uint8_t* cls_row = p.tile_cls + (static_cast<size_t>(n) * p.n_qt + qt) * p.n_kt;
+
+  if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) {
+      printf("ggpt attn_fwd: dynamic smem base not 1024-aligned\n");
+      __trap();
+    }
+    tma_prefetch_desc(&tmQKV);
+    mbar_init(q_full, 1);
+    mbar_init(&kv_full[0], 1);
+    mbar_init(&kv_full[1], 1);
+    mbar_init(&kv_empty[0], 1);
+    mbar_init(&kv_empty[1], 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 4);
+    mbar_init(o_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base;         // 128 columns
+  const uint32_t tmem_O = tmem_base + 128;   // 64 columns
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(q_full, 16384);
+      tma_load_3d(sQ, &tmQKV, q_full, p.q_col0 + h * kHeadDim, qt * kTileQ, n);
+      int it = 0;
+      for (int kt = 0; kt < p.n_kt; ++kt) {
+        if (cls_row[kt] == 0) continue;
+        const int st = it & 1;
+        mbar_wait(&kv_empty[st], ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[st], 32768);
+        tma_load_3d(sK + st * 16384, &tmQKV, &kv_full[st], p.k_col0 + h * kHeadDim, kt * kTileK, n);
+        tma_load_3d(sV + st * 16384, &tmQKV, &kv_full[st], p.v_col0 + h * kHeadDim, kt * kTileK, n);
+        ++it;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, false, true);
+      const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
+      auto issue_S = [&](int st) {
+        const uint32_t aK = smem_u32(sK + st * 16384);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          tc_mma_bf16(tmem_S, umma_desc_sw128(aQ + kk * 32, 16, 1024), umma_desc_sw128(aK + kk * 32, 16, 1024),
+                      idesc_s, kk != 0);
+        tc_commit(s_full);
+      };
+      int n_active = 0;
+      for (int kt = 0; kt < p.n_kt; ++kt) n_active += (cls_row[kt] != 0);
+      if (n_active > 0) {
+        mbar_wait(q_full, 0);
+        mbar_wait(&kv_full[0], 0);
+        tc_fence_after();
+        issue_S(0);
+        for (int it = 0; it < n_active; ++it) {
+          const int st = it & 1;
+          mbar_wait(p_full, it & 1);   // P(it) in smem, S(it) and O(it-1) drained from TMEM
+          tc_fence_after();
+          const uint32_t aV = smem_u32(sV + st * 16384);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            tc_mma_bf16(tmem_O, umma_desc_sw128(aP + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                        umma_desc_sw128(aV + kk * 2048, 8192, 1024), idesc_o, kk != 0);
+          tc_commit(o_full);
+          tc_commit(&kv_empty[st]);
+          if (it + 1 < n_active) {
+            const int st2 = (it + 1) & 1;
+            mbar_wait(&kv_full[st2], ((it + 1) >> 1) & 1);
+            tc_fence_after();
+            issue_S(st2);
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== softmax / epilogue warps: one query row per thread =====================
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;              // row inside the tile
+    const int q_row = qt * kTileQ + r;
+    const bool row_ok = q_row < p.S;
+    const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t* mrow = p.mask_bits + (static_cast<size_t>(n) * p.S + (row_ok ? q_row : 0)) * p.mask_words;
+
+    float o_acc[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) o_acc[i] = 0.f;
+    float m_run = -INFINITY;   // running max of scaled (log2-domain) scores
+    float l_run = 0.f;
+
+    int it = 0;
+    for (int kt = 0; kt < p.n_kt; ++kt) {
+      const int cls = cls_row[kt];
+      if (cls == 0) continue;
+      uint32_t mw[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+      if (cls == 2) {
+        if (row_ok) {
+          const uint4 v = *reinterpret_cast<const uint4*>(mrow + kt * 4);
+          mw[0] = v.x; mw[1] = v.y; mw[2] = v.z; mw[3] = v.w;
+        } else {
+          mw[0] = mw[1] = mw[2] = mw[3] = 0u;
+        }
+      }
+      mbar_wait(s_full, it & 1);
+      tc_fence_after();
+      // pass 1: row max
+      float m_tile = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t s[32];
+        tmem_ld32(tmem_S + lane_addr + c * 32, s);
+        tmem_ld_wait();
+        const uint32_t w = (c == 0) ? mw[0] : (c == 1) ? mw[1] : (c == 2) ? mw[2] : mw[3];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float v = __uint_as_float(s[j]) * p.scale_log2;
+          m_tile = fmaxf(m_tile, ((w >> j) & 1u) ? v : -INFINITY);
+        }
+      }
+      const float m_new = fmaxf(m_run, m_tile);
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+      const float alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run - m_use);
+      // pass 2: probabilities -> smem (bf16, swizzled K-major A operand), row sum
+      float l_tile = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t s[32];
+        tmem_ld32(tmem_S + lane_addr + c * 32, s);
+        tmem_ld_wait();
+        const uint32_t w = (c == 0) ? mw[0] : (c == 1) ? mw[1] : (c == 2) ? mw[2] : mw[3];
+        // columns c*32 .. c*32+31 of P: half = c/2 (64-col K block), 16-byte chunks (c&1)*4 .. +3
+        uint8_t* pbase = sP + (c >> 1) * 16384 + r * 128;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float pv[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float e = exp2f(__uint_as_float(s[g * 8 + j]) * p.scale_log2 - m_use);
+            pv[j] = ((w >> (g * 8 + j)) & 1u) ? e : 0.f;
+            l_tile += pv[j];
+          }
+          uint4 o;
+          o.x = pack_bf16(pv[0], pv[1]);
+          o.y = pack_bf16(pv[2], pv[3]);
+          o.z = pack_bf16(pv[4], pv[5]);
+          o.w = pack_bf16(pv[6], pv[7]);
+          const int chunk = ((c & 1) * 4 + g) ^ (r & 7);
+          *reinterpret_cast<uint4*>(pbase + chunk * 16) = o;
+        }
+      }
+      l_run = l_run * alpha + l_tile;
+      m_run = m_new;
+      fence_proxy_async_smem();   // make P visible to the tensor-core (async) proxy
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      // accumulate O = O * alpha + P V
+      mbar_wait(o_full, it & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t o[32];
+        tmem_ld32(tmem_O + lane_addr + c * 32, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o_acc[c * 32 + j] = fmaf(o_acc[c * 32 + j], alpha, __uint_as_float(o[j]));
+      }
+      ++it;
+    }
+
+    if (row_ok) {
+      const float inv = (l_run > 0.f) ? 1.0f / l_run : 0.f;
+      __nv_bfloat16* orow = p.out + (static_cast<long long>(n) * p.S + q_row) * p.ldo + h * kHeadDim;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        uint4 o;
+        o.x = pack_bf16(o_acc[g * 8 + 0] * inv, o_acc[g * 8 + 1] * inv);
+        o.y = pack_bf16(o_acc[g * 8 + 2] * inv, o_acc[g * 8 + 3] * inv);
+        o.z = pack_bf16(o_acc[g * 8 + 4] * inv, o_acc[g * 8 + 5] * inv);
+        o.w = pack_bf16(o_acc[g * 8 + 6] * inv, o_acc[g * 8 + 7] * inv);
+        *reinterpret_cast<uint4*>(orow + g * 8) = o;
+      }
+      if (p.lse != nullptr) {
+        const float lse = (l_run > 0.f) ? (m_run * 0.6931471805599453f + logf(l_run)) : 0.f;
+        p.lse[(static_cast<size_t>(n) * p.H + h) * p.S + q_row] = lse;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Mask preparation: int64 attention_mask ([N,S] key mask or [N,S,S]) (+ causal) -> bit matrix + tile classes
+// ref: modeling_helpers.py:38-64 (_update_causal_mask / _expand_mask_from_3d_mask), HF:398-405 (causal)
+// ---------------------------------------------------------------------------------------------
+__global__ void attn_mask_bits_kernel(const long long* __restrict__ am, int am_dims, int N, int S, int causal,
+                                      int mask_words, uint32_t* __restrict__ bits) {
+  // one warp per (n, q, word)
+  const long long gw = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long total = static_cast<long long>(N) * S * mask_words;
+  if (gw >= total) return;
+  const int w = static_cast<int>(gw % mask_words);
+  const long long nq = gw / mask_words;
+  const int q = static_cast<int>(nq % S);
+  const int n = static_cast<int>(nq / S);
+  const int k = w * 32 + lane;
+  bool keep = false;
+  if (k < S) {
+    if (am == nullptr) keep = true;
+    else if (am_dims == 2) keep = am[static_cast<long long>(n) * S + k] != 0;
+    else keep = am[(static_cast<long long>(n) * S + q) * S + k] != 0;
+    if (causal && k > q) keep = false;
+  }
+  const uint32_t word = __ballot_sync(0xffffffffu, keep);
+  if (lane == 0) bits[gw] = word;
+}
+
+__global__ void attn_tile_cls_kernel(const uint32_t* __restrict__ bits, int N, int S, int mask_words, int n_qt, int n_kt,
+                                     uint8_t* __restrict__ cls) {
+  // one warp per (n, qt, kt): lane handles rows lane, lane+32, ...
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gw >= N * n_qt * n_kt) return;
+  const int kt = gw % n_kt;
+  const int qt = (gw / n_kt) % n_qt;
+  const int n = gw / (n_kt * n_qt);
+  uint32_t any = 0, all = 0xffffffffu;
+  for (int r = lane; r < 128; r += 32) {
+    const int q = qt * 128 + r;
+    if (q < S) {
+      const uint4 v = *reinterpret_cast<const uint4*>(bits + (static_cast<size_t>(n) * S + q) * mask_words + kt * 4);
+      any |= v.x | v.y | v.z | v.w;
+      all &= v.x & v.y & v.z & v.w;
+    } else {
+      all = 0;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    any |= __shfl_xor_sync(0xffffffffu, any, o);
+    all &= __shfl_xor_sync(0xffffffffu, all, o);
+  }
+  if (lane == 0) cls[gw] = (any == 0) ? 0 : ((all == 0xffffffffu) ? 1 : 2);
+}
+
+}  // namespace ggpt
+
+using namespace ggpt;
+
+extern "C" {
+
+int ggpt_attn_mask_words(int S) { return ((S + 127) / 128) * 4; }
+
+int ggpt_attn_mask_build(const long long* attention_mask, int mask_dims, int N, int S, int causal, uint32_t* mask_bits,
+                         uint8_t* tile_cls, void* stream) {
+  GGPT_REQUIRE(N > 0 && S > 0, "attn_mask_build: empty batch");
+  GGPT_REQUIRE(attention_mask == nullptr || mask_dims == 2 || mask_dims == 3,
+               "attention_mask of %d dims is not implemented (expected [N,S] or [N,S,S])", mask_dims);
+  GGPT_REQUIRE(mask_bits && tile_cls, "attn_mask_build: null output");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int words = ggpt_attn_mask_words(S);
+  const int nt = (S + 127) / 128;
+  const long long warps = static_cast<long long>(N) * S * words;
+  const long long blocks = (warps * 32 + 255) / 256;
+  attn_mask_bits_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(attention_mask, mask_dims, N, S, causal, words,
+                                                                       mask_bits);
+  if (int rc = check_launch("attn_mask_bits_kernel")) return rc;
+  const int warps2 = N * nt * nt;
+  attn_tile_cls_kernel<<<(warps2 * 32 + 255) / 256, 256, 0, s>>>(mask_bits, N, S, words, nt, nt, tile_cls);
+  return check_launch("attn_tile_cls_kernel");
+}
+
+int ggpt_attn_fwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int v_col0, const uint32_t* mask_bits,
+                  const uint8_t* tile_cls, void* out, long long ldo, float* lse, int N, int S, int H, void* stream) {
+  GGPT_REQUIRE(qkv && mask_bits && tile_cls && out, "attn_fwd: null pointer");
+  GGPT_REQUIRE(N > 0 && S > 0 && H > 0, "attn_fwd: empty problem");
+  GGPT_REQUIRE(ld_qkv % 8 == 0 && ldo % 8 == 0 && q_col0 % 8 == 0 && k_col0 % 8 == 0 && v_col0 % 8 == 0,
+               "attn_fwd: leading dimensions / column offsets must be multiples of 8");
+  CUtensorMap tm;
+  if (int rc = make_tmap_3d_bf16(&tm, qkv, N, S, ld_qkv, static_cast<uint64_t>(S) * ld_qkv, ld_qkv, 128, 64)) return rc;
+  AttnFwdParams p{};
+  p.N = N; p.S = S; p.H = H;
+  p.n_qt = (S + 127) / 128;
+  p.n_kt = p.n_qt;
+  p.mask_words = ggpt_attn_mask_words(S);
+  p.mask_bits = mask_bits; p.tile_cls = tile_cls;
+  p.out = static_cast<__nv_bfloat16*>(out); p.ldo = ldo; p.lse = lse;
+  p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
+  p.scale_log2 = 0.125f * 1.4426950408889634f;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem);
+    if (e != cudaSuccess) {
+      set_error("attn_fwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return -2;
+    }
+    attr_set = true;
+  }
+  dim3 grid(p.n_qt, H, N);
+  attn_fwd_kernel<<<grid, kAttThreads, kAttSmem, static_cast<cudaStream_t>(stream)>>>(tm, p);
+  return check_launch("attn_fwd_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,707 @@
+// HBM-bound kernels of the GraphGPT hot path: stacked-token embedding gather-sum, RMSNorm, GeGLU backward,
+// loss-head compaction / gathers, fp32 cross-entropy, fused AdamW.  All are one-pass, vectorised (16-byte
+// accesses), warp-shuffle reductions, grid sized from the SM count.
+#include "common.cuh"
+#include "../../include/ggpt_b200.h"
+
+namespace ggpt {
+
+static inline int grid_for_rows(long long rows, int rows_per_block, int max_waves = 8) {
+  long long blocks = (rows + rows_per_block - 1) / rows_per_block;
+  long long cap = static_cast<long long>(num_sms()) * max_waves;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+// =============================================================================================
+// Stacked-token embedding: x[t,:] = sum_f gate[f,:] * E[ids[t,f],:]   (gate == NULL -> plain sum)
+// ref: modeling_helpers.py:89-114 (_get_stacked_inputs_embeds), modeling_common.py:127-135
+// =============================================================================================
+__global__ void embed_fwd_kernel(const long long* __restrict__ ids, const float* __restrict__ table,
+                                 const float* __restrict__ gate, float* __restrict__ out, long long T, int F, int d,
+                                 int V, int long_scale, int* __restrict__ err) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  for (long long t = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); t < T;
+       t += static_cast<long long>(gridDim.x) * warps_per_block) {
+    const long long* idrow = ids + t * F;
+    int nnz = 0;
+    for (int c = lane * 4; c < d; c += 128) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int f = 0; f < F; ++f) {
+        long long id = idrow[f];
+        if (id < 0 || id >= V) {
+          if (err) atomicExch(err, 1);
+          id = 0;
+        }
+        if (c == lane * 4) nnz += (id != 0);
+        float4 e = *reinterpret_cast<const float4*>(table + id * d + c);
+        if (gate != nullptr) {
+          const float4 g = *reinterpret_cast<const float4*>(gate + static_cast<long long>(f) * d + c);
+          e.x *= g.x; e.y *= g.y; e.z *= g.z; e.w *= g.w;
+        }
+        acc.x += e.x; acc.y += e.y; acc.z += e.z; acc.w += e.w;
+      }
+      if (long_scale) {  // stack_method == "long": scale by 1/clamp(#non-pad features) (modeling_helpers.py:106-110)
+        const float ratio = fminf(1.0f / (static_cast<float>(nnz) + 1e-7f), 1.0f);
+        acc.x *= ratio; acc.y *= ratio; acc.z *= ratio; acc.w *= ratio;
+      }
+      *reinterpret_cast<float4*>(out + t * d + c) = acc;
+    }
+  }
+}
+
+// dE[id,:] += gate[f,:] * dx[t,:] for id != padding_idx;  dgate[f,:] += E[id,:] * dx[t,:]
+__global__ void embed_bwd_kernel(const long long* __restrict__ ids, const float* __restrict__ dx,
+                                 const float* __restrict__ table, const float* __restrict__ gate,
+                                 float* __restrict__ dtable, float* __restrict__ dgate, long long T, int F, int d, int V,
+                                 int padding_idx, int long_scale) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  for (long long t = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); t < T;
+       t += static_cast<long long>(gridDim.x) * warps_per_block) {
+    const long long* idrow = ids + t * F;
+    float ratio = 1.f;
+    if (long_scale) {
+      int nnz = 0;
+      for (int f = 0; f < F; ++f) nnz += (idrow[f] != 0);
+      ratio = fminf(1.0f / (static_cast<float>(nnz) + 1e-7f), 1.0f);
+    }
+    for (int c = lane * 4; c < d; c += 128) {
+      float4 g = *reinterpret_cast<const float4*>(dx + t * d + c);
+      g.x *= ratio; g.y *= ratio; g.z *= ratio; g.w *= ratio;
+      for (int f = 0; f < F; ++f) {
+        long long id = idrow[f];
+        if (id < 0 || id >= V) continue;
+        float4 v = g;
+        if (gate != nullptr) {
+          const float4 gt = *reinterpret_cast<const float4*>(gate + static_cast<long long>(f) * d + c);
+          const float4 e = *reinterpret_cast<const float4*>(table + id * d + c);
+          float* dg = dgate + static_cast<long long>(f) * d + c;
+          atomicAdd(dg + 0, e.x * g.x); atomicAdd(dg + 1, e.y * g.y);
+          atomicAdd(dg + 2, e.z * g.z); atomicAdd(dg + 3, e.w * g.w);
+          v.x *= gt.x; v.y *= gt.y; v.z *= gt.z; v.w *= gt.w;
+        }
+        if (id == padding_idx) continue;  // nn.Embedding(padding_idx): row never receives gradient (HF:361)
+        float* dst = dtable + id * d + c;
+        atomicAdd(dst + 0, v.x); atomicAdd(dst + 1, v.y); atomicAdd(dst + 2, v.z); atomicAdd(dst + 3, v.w);
+      }
+    }
+  }
+}
+
+// =============================================================================================
+// RMSNorm  y = bf16( w * x * rsqrt(mean(x^2) + eps) ), fp32 statistics.   ref: HF:59-64
+// =============================================================================================
+__global__ void rmsnorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                   __nv_bfloat16* __restrict__ y, long long ldy, float* __restrict__ rstd_out,
+                                   long long T, int d, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  for (long long t = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); t < T;
+       t += static_cast<long long>(gridDim.x) * warps_per_block) {
+    const float* xr = x + t * d;
+    float ss = 0.f;
+    for (int c = lane * 4; c < d; c += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(xr + c);
+      ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    ss = warp_sum(ss);
+    const float rstd = rsqrtf(ss / static_cast<float>(d) + eps);
+    if (lane == 0 && rstd_out != nullptr) rstd_out[t] = rstd;
+    __nv_bfloat16* yr = y + t * ldy;
+    for (int c = lane * 4; c < d; c += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(xr + c);
+      const float4 ww = *reinterpret_cast<const float4*>(w + c);
+      uint2 o;
+      o.x = pack_bf16(ww.x * (v.x * rstd), ww.y * (v.y * rstd));
+      o.y = pack_bf16(ww.z * (v.z * rstd), ww.w * (v.w * rstd));
+      *reinterpret_cast<uint2*>(yr + c) = o;
+    }
+  }
+}
+
+// dx_out = dresid + rstd * (g - xhat * mean(g * xhat)),  g = dy * w,  xhat = x * rstd;  dw += sum_t dy * xhat
+// Also emits a bf16 copy of dx_out (the A operand of the next dgrad GEMMs).
+// Each lane owns the same columns (lane*4 + k*128) for every row its warp visits, so the row is held in registers
+// (one HBM pass) and the dw partial sums stay in registers until one smem + global reduction per block.
+template <int NV>
+__global__ void rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const float* __restrict__ x,
+                                   const float* __restrict__ rstd_in, const float* __restrict__ w,
+                                   const float* __restrict__ dresid, float* __restrict__ dx_out,
+                                   __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dw, long long T, int d) {
+  extern __shared__ float s_dw[];  // [d]
+  for (int c = threadIdx.x; c < d; c += blockDim.x) s_dw[c] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const float inv_d = 1.0f / static_cast<float>(d);
+  float4 wv[NV], dwacc[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = lane * 4 + k * 128;
+    wv[k] = (c < d) ? *reinterpret_cast<const float4*>(w + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    dwacc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (long long t = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); t < T;
+       t += static_cast<long long>(gridDim.x) * warps_per_block) {
+    const float* xr = x + t * d;
+    const __nv_bfloat16* dyr = dy + t * lddy;
+    const float rstd = rstd_in[t];
+    float4 xs[NV], gv[NV];   // xhat and dy (then g = dy*w)
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = lane * 4 + k * 128;
+      if (c < d) {
+        const float4 xv = *reinterpret_cast<const float4*>(xr + c);
+        const uint2 dv = *reinterpret_cast<const uint2*>(dyr + c);
+        const float2 d01 = unpack_bf16(dv.x), d23 = unpack_bf16(dv.y);
+        xs[k] = make_float4(xv.x * rstd, xv.y * rstd, xv.z * rstd, xv.w * rstd);
+        gv[k] = make_float4(d01.x, d01.y, d23.x, d23.y);
+        dwacc[k].x += gv[k].x * xs[k].x; dwacc[k].y += gv[k].y * xs[k].y;
+        dwacc[k].z += gv[k].z * xs[k].z; dwacc[k].w += gv[k].w * xs[k].w;
+        gv[k].x *= wv[k].x; gv[k].y *= wv[k].y; gv[k].z *= wv[k].z; gv[k].w *= wv[k].w;
+        dot += gv[k].x * xs[k].x + gv[k].y * xs[k].y + gv[k].z * xs[k].z + gv[k].w * xs[k].w;
+      }
+    }
+    dot = warp_sum(dot) * inv_d;  // mean(g * xhat)
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = lane * 4 + k * 128;
+      if (c < d) {
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (dresid != nullptr) r = *reinterpret_cast<const float4*>(dresid + t * d + c);
+        float4 o;
+        o.x = r.x + rstd * (gv[k].x - xs[k].x * dot);
+        o.y = r.y + rstd * (gv[k].y - xs[k].y * dot);
+        o.z = r.z + rstd * (gv[k].z - xs[k].z * dot);
+        o.w = r.w + rstd * (gv[k].w - xs[k].w * dot);
+        *reinterpret_cast<float4*>(dx_out + t * d + c) = o;
+        if (dx_bf16 != nullptr) {
+          uint2 ob;
+          ob.x = pack_bf16(o.x, o.y);
+          ob.y = pack_bf16(o.z, o.w);
+          *reinterpret_cast<uint2*>(dx_bf16 + t * d + c) = ob;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = lane * 4 + k * 128;
+    if (c < d) {
+      atomicAdd(&s_dw[c + 0], dwacc[k].x); atomicAdd(&s_dw[c + 1], dwacc[k].y);
+      atomicAdd(&s_dw[c + 2], dwacc[k].z); atomicAdd(&s_dw[c + 3], dwacc[k].w);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < d; c += blockDim.x) atomicAdd(dw + c, s_dw[c]);
+}
+
+// =============================================================================================
+// GeGLU backward: dg = dact * u * gelu'(g), du = dact * gelu(g)      (gu = [g | u], bf16)
+// =============================================================================================
+__global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ dact, const __nv_bfloat16* __restrict__ gu,
+                                 __nv_bfloat16* __restrict__ dgu, long long T, int I) {
+  const long long groups_per_row = I / 8;
+  const long long total = T * groups_per_row;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long t = i / groups_per_row;
+    const int c = static_cast<int>(i % groups_per_row) * 8;
+    const uint4 da = *reinterpret_cast<const uint4*>(dact + t * I + c);
+    const uint4 gv = *reinterpret_cast<const uint4*>(gu + t * 2 * I + c);
+    const uint4 uv = *reinterpret_cast<const uint4*>(gu + t * 2 * I + I + c);
+    const uint32_t dau[4] = {da.x, da.y, da.z, da.w}, gvu[4] = {gv.x, gv.y, gv.z, gv.w}, uvu[4] = {uv.x, uv.y, uv.z, uv.w};
+    uint32_t og[4], ou[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 a = unpack_bf16(dau[j]), g = unpack_bf16(gvu[j]), u = unpack_bf16(uvu[j]);
+      og[j] = pack_bf16(a.x * u.x * gelu_erf_grad(g.x), a.y * u.y * gelu_erf_grad(g.y));
+      ou[j] = pack_bf16(a.x * gelu_erf(g.x), a.y * gelu_erf(g.y));
+    }
+    *reinterpret_cast<uint4*>(dgu + t * 2 * I + c) = make_uint4(og[0], og[1], og[2], og[3]);
+    *reinterpret_cast<uint4*>(dgu + t * 2 * I + I + c) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+  }
+}
+
+// =============================================================================================
+// Loss-head compaction (no host-side boolean indexing):
+//   rows with >= 1 label, in (n,s) order -> sel_rows[M];  labelled (row, f) entries in row-major order ->
+//   ent_src[L] = m*F + f (row of the [M*F, d] projected matrix), ent_label[L], ent_tok[L] = token index t.
+// ref: modeling_helpers.py:263-301 (_prepare_for_stacked_feat_labels_per_mix_lvl)
+// Three phases: per-block counts -> single-block scan of block totals -> write.
+// =============================================================================================
+constexpr int kScanBlock = 256;
+
+__global__ void head_count_kernel(const long long* __restrict__ labels, long long T, int F, int* __restrict__ blk_rows,
+                                  int* __restrict__ blk_ents) {
+  const long long t = static_cast<long long>(blockIdx.x) * kScanBlock + threadIdx.x;
+  int ents = 0;
+  if (t < T) {
+    for (int f = 0; f < F; ++f) ents += (labels[t * F + f] != -100);
+  }
+  int rows = ents > 0;
+  __shared__ int s_r[kScanBlock / 32], s_e[kScanBlock / 32];
+  int r = rows, e = ents;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    r += __shfl_xor_sync(0xffffffffu, r, o);
+    e += __shfl_xor_sync(0xffffffffu, e, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_r[threadIdx.x >> 5] = r;
+    s_e[threadIdx.x >> 5] = e;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tr = 0, te = 0;
+    for (int i = 0; i < kScanBlock / 32; ++i) {
+      tr += s_r[i];
+      te += s_e[i];
+    }
+    blk_rows[blockIdx.x] = tr;
+    blk_ents[blockIdx.x] = te;
+  }
+}
+
+__global__ void head_scan_blocks_kernel(int* __restrict__ blk_rows, int* __restrict__ blk_ents, int nblk,
+                                        int* __restrict__ counts) {
+  // single block; exclusive scan in place (nblk is small: T / 256)
+  __shared__ int carry_r, carry_e;
+  if (threadIdx.x == 0) {
+    carry_r = 0;
+    carry_e = 0;
+  }
+  __syncthreads();
+  for (int base = 0; base < nblk; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    int r = (i < nblk) ? blk_rows[i] : 0;
+    int e = (i < nblk) ? blk_ents[i] : 0;
+    // block-wide inclusive scan (Hillis-Steele in smem)
+    __shared__ int sr[1024], se[1024];
+    sr[threadIdx.x] = r;
+    se[threadIdx.x] = e;
+    __syncthreads();
+    for (int o = 1; o < blockDim.x; o <<= 1) {
+      int ar = 0, ae = 0;
+      if (threadIdx.x >= o) {
+        ar = sr[threadIdx.x - o];
+        ae = se[threadIdx.x - o];
+      }
+      __syncthreads();
+      sr[threadIdx.x] += ar;
+      se[threadIdx.x] += ae;
+      __syncthreads();
+    }
+    if (i < nblk) {
+      blk_rows[i] = carry_r + sr[threadIdx.x] - r;
+      blk_ents[i] = carry_e + se[threadIdx.x] - e;
+    }
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) {
+      carry_r += sr[threadIdx.x];
+      carry_e += se[threadIdx.x];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    counts[0] = carry_r;
+    counts[1] = carry_e;
+  }
+}
+
+__global__ void head_write_kernel(const long long* __restrict__ labels, long long T, int F,
+                                  const int* __restrict__ blk_rows, const int* __restrict__ blk_ents,
+                                  int* __restrict__ sel_rows, int* __restrict__ ent_src, int* __restrict__ ent_label,
+                                  int* __restrict__ ent_tok) {
+  const long long t = static_cast<long long>(blockIdx.x) * kScanBlock + threadIdx.x;
+  int ents = 0;
+  if (t < T) {
+    for (int f = 0; f < F; ++f) ents += (labels[t * F + f] != -100);
+  }
+  const int rows = ents > 0;
+  __shared__ int sr[kScanBlock], se[kScanBlock];
+  sr[threadIdx.x] = rows;
+  se[threadIdx.x] = ents;
+  __syncthreads();
+  for (int o = 1; o < kScanBlock; o <<= 1) {
+    int ar = 0, ae = 0;
+    if (threadIdx.x >= o) {
+      ar = sr[threadIdx.x - o];
+      ae = se[threadIdx.x - o];
+    }
+    __syncthreads();
+    sr[threadIdx.x] += ar;
+    se[threadIdx.x] += ae;
+    __syncthreads();
+  }
+  if (t < T && rows) {
+    const int m = blk_rows[blockIdx.x] + sr[threadIdx.x] - 1;
+    int e = blk_ents[blockIdx.x] + se[threadIdx.x] - ents;
+    sel_rows[m] = static_cast<int>(t);
+    for (int f = 0; f < F; ++f) {
+      const long long lab = labels[t * F + f];
+      if (lab != -100) {
+        ent_src[e] = m * F + f;
+        ent_label[e] = static_cast<int>(lab);
+        ent_tok[e] = static_cast<int>(t);
+        ++e;
+      }
+    }
+  }
+}
+
+// out[i,:] = src[idx[i],:]  (bf16 rows, 16-byte vectors); count read from device (*n_ptr) so no host sync is needed
+__global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ src, long long lds, const int* __restrict__ idx,
+                                   __nv_bfloat16* __restrict__ out, long long ldo, const int* __restrict__ n_ptr,
+                                   int n_max, int d) {
+  const int n = n_ptr ? min(*n_ptr, n_max) : n_max;
+  const int vec_per_row = d / 8;
+  const long long total = static_cast<long long>(n) * vec_per_row;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / vec_per_row;
+    const int c = static_cast<int>(i % vec_per_row) * 8;
+    const long long s = idx ? idx[r] : r;
+    *reinterpret_cast<uint4*>(out + r * ldo + c) = *reinterpret_cast<const uint4*>(src + s * lds + c);
+  }
+}
+
+// out[idx[i],:] = src[i,:]   (distinct idx -> plain stores; `out` must be pre-zeroed by the caller)
+__global__ void scatter_rows_kernel(const __nv_bfloat16* __restrict__ src, long long lds, const int* __restrict__ idx,
+                                    __nv_bfloat16* __restrict__ out, long long ldo, const int* __restrict__ n_ptr,
+                                    int n_max, int d) {
+  const int n = n_ptr ? min(*n_ptr, n_max) : n_max;
+  const int vec_per_row = d / 8;
+  const long long total = static_cast<long long>(n) * vec_per_row;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / vec_per_row;
+    const int c = static_cast<int>(i % vec_per_row) * 8;
+    const long long s = idx[r];
+    *reinterpret_cast<uint4*>(out + s * ldo + c) = *reinterpret_cast<const uint4*>(src + r * lds + c);
+  }
+}
+
+// =============================================================================================
+// Cross-entropy over fp32 logits [L, ldl] (first V columns valid).  One warp per row.
+//   row_lse[e] = logsumexp(logits[e,:V]);  loss_sum += wgt[e] * (row_lse[e] - logits[e, label[e]])
+// ref: modeling_helpers.py:145-198 (_get_ce_loss / _get_dlm_ce_loss on logits.float())
+// =============================================================================================
+__global__ void ce_fwd_kernel(const float* __restrict__ logits, long long ldl, const int* __restrict__ labels,
+                              const float* __restrict__ wgt, float* __restrict__ row_lse, float* __restrict__ row_loss,
+                              double* __restrict__ loss_sum, double* __restrict__ wgt_sum, int L, int V,
+                              int* __restrict__ err) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  double local = 0.0, local_w = 0.0;
+  for (int e = blockIdx.x * warps_per_block + (threadIdx.x >> 5); e < L; e += gridDim.x * warps_per_block) {
+    const float* row = logits + static_cast<long long>(e) * ldl;
+    float m = -INFINITY;
+    for (int c = lane; c < V; c += 32) m = fmaxf(m, row[c]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int c = lane; c < V; c += 32) s += __expf(row[c] - m);
+    s = warp_sum(s);
+    const float lse = m + logf(s);
+    if (lane == 0) {
+      int lab = labels[e];
+      if (lab < 0 || lab >= V) {
+        if (err) atomicExch(err, 2);
+        lab = 0;
+      }
+      const float w = wgt ? wgt[e] : 1.0f;
+      const float l = lse - row[lab];
+      row_lse[e] = lse;
+      if (row_loss) row_loss[e] = l;
+      local += static_cast<double>(l) * w;
+      local_w += w;
+    }
+  }
+  // block reduce of lane-0 partials
+  __shared__ double s_l[32], s_w[32];
+  if (lane == 0) {
+    s_l[threadIdx.x >> 5] = local;
+    s_w[threadIdx.x >> 5] = local_w;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < warps_per_block; ++i) {
+      a += s_l[i];
+      b += s_w[i];
+    }
+    atomicAdd(loss_sum, a);
+    if (wgt_sum) atomicAdd(wgt_sum, b);
+  }
+}
+
+// dlogits[e,c] = (softmax(logits[e])[c] - [c == label[e]]) * wgt[e] * scale[0] * gout[0]   (bf16, pad columns = 0)
+__global__ void ce_bwd_kernel(const float* __restrict__ logits, long long ldl, const int* __restrict__ labels,
+                              const float* __restrict__ wgt, const float* __restrict__ row_lse,
+                              const float* __restrict__ scale, const float* __restrict__ gout,
+                              __nv_bfloat16* __restrict__ dlogits, long long ldd, int L, int V, int Vpad) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const float g = scale[0] * (gout ? gout[0] : 1.0f);
+  for (int e = blockIdx.x * warps_per_block + (threadIdx.x >> 5); e < L; e += gridDim.x * warps_per_block) {
+    const float* row = logits + static_cast<long long>(e) * ldl;
+    __nv_bfloat16* drow = dlogits + static_cast<long long>(e) * ldd;
+    const float lse = row_lse[e];
+    const int lab = labels[e];
+    const float w = (wgt ? wgt[e] : 1.0f) * g;
+    for (int c = lane * 2; c < Vpad; c += 64) {
+      float v0 = 0.f, v1 = 0.f;
+      if (c < V) v0 = (__expf(row[c] - lse) - (c == lab ? 1.f : 0.f)) * w;
+      if (c + 1 < V) v1 = (__expf(row[c + 1] - lse) - (c + 1 == lab ? 1.f : 0.f)) * w;
+      *reinterpret_cast<uint32_t*>(drow + c) = pack_bf16(v0, v1);
+    }
+  }
+}
+
+// loss = loss_sum / denom  where denom = L (mean), wgt_sum + 1e-7, or a fixed divisor; also writes scale = 1/denom
+__global__ void ce_finalize_kernel(const double* __restrict__ loss_sum, const double* __restrict__ wgt_sum,
+                                   const int* __restrict__ count, int mode, float fixed_denom, float* __restrict__ loss,
+                                   float* __restrict__ scale) {
+  double denom;
+  if (mode == 0) denom = static_cast<double>(*count);              // mean over L labelled entries
+  else if (mode == 1) denom = *wgt_sum + 1e-7;                    // weighted mean
+  else denom = static_cast<double>(fixed_denom);                  // dLM: N*S*F
+  if (denom <= 0.0) {
+    *loss = nanf("");  // CrossEntropyLoss over zero targets is NaN in torch
+    *scale = 0.f;
+  } else {
+    *loss = static_cast<float>(*loss_sum / denom);
+    *scale = static_cast<float>(1.0 / denom);
+  }
+}
+
+// =============================================================================================
+// Optimiser: squared-norm of the flat gradient, then fused AdamW with optional clipping, writing the fp32 master
+// and its bf16 compute copy in one pass.  ref: training_utils.py:71-86 (clip_grad_norm_ + AdamW),
+// configs/training/base.yaml:35-44 (betas 0.9/0.95, wd 0.1, clip 1.0)
+// =============================================================================================
+__global__ void sumsq_kernel(const float* __restrict__ g, long long n, double* __restrict__ out) {
+  double acc = 0.0;
+  const long long n4 = n / 4;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(g)[i];
+    acc += static_cast<double>(v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (long long i = n4 * 4; i < n; ++i) acc += static_cast<double>(g[i]) * g[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ double s[32];
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) t += s[i];
+    atomicAdd(out, t);
+  }
+}
+
+__global__ void adamw_kernel(float* __restrict__ p, __nv_bfloat16* __restrict__ p_bf16, const float* __restrict__ g,
+                             float* __restrict__ m, float* __restrict__ v, long long n, float lr, float beta1,
+                             float beta2, float eps, float wd, float bc1, float bc2, const double* __restrict__ gnorm_sq,
+                             float max_norm, float grad_scale) {
+  float clip = grad_scale;
+  if (gnorm_sq != nullptr && max_norm > 0.f) {
+    const float norm = sqrtf(static_cast<float>(*gnorm_sq)) * grad_scale;
+    clip = grad_scale * fminf(1.0f, max_norm / (norm + 1e-6f));
+  }
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float gi = g[i] * clip;
+    float pi = p[i];
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    pi -= lr * wd * pi;                                   // decoupled weight decay (torch.optim.AdamW)
+    pi -= lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
+    p[i] = pi;
+    if (p_bf16 != nullptr) p_bf16[i] = __float2bfloat16_rn(pi);
+  }
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  const long long n4 = n / 4;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    uint2 o;
+    o.x = pack_bf16(v.x, v.y);
+    o.y = pack_bf16(v.z, v.w);
+    reinterpret_cast<uint2*>(dst)[i] = o;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (long long i = n4 * 4; i < n; ++i) dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+}  // namespace ggpt
+
+using namespace ggpt;
+
+extern "C" {
+
+int ggpt_embed_fwd(const long long* ids, const float* table, const float* gate, float* out, long long T, int F, int d,
+                   int V, int long_scale, int* err_flag, void* stream) {
+  GGPT_REQUIRE(ids && table && out, "embed_fwd: null pointer");
+  GGPT_REQUIRE(T > 0 && F > 0 && d > 0 && d % 4 == 0, "embed_fwd: bad sizes T=%lld F=%d d=%d", T, F, d);
+  embed_fwd_kernel<<<grid_for_rows(T, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(ids, table, gate, out, T, F, d,
+                                                                                       V, long_scale, err_flag);
+  return check_launch("embed_fwd_kernel");
+}
+
+int ggpt_embed_bwd(const long long* ids, const float* dx, const float* table, const float* gate, float* dtable,
+                   float* dgate, long long T, int F, int d, int V, int padding_idx, int long_scale, void* stream) {
+  GGPT_REQUIRE(ids && dx && dtable, "embed_bwd: null pointer");
+  GGPT_REQUIRE(gate == nullptr || (table && dgate), "embed_bwd: gated aggregation needs table and dgate");
+  embed_bwd_kernel<<<grid_for_rows(T, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      ids, dx, table, gate, dtable, dgate, T, F, d, V, padding_idx, long_scale);
+  return check_launch("embed_bwd_kernel");
+}
+
+int ggpt_rmsnorm_fwd(const float* x, const float* w, void* y, long long ldy, float* rstd, long long T, int d, float eps,
+                     void* stream) {
+  GGPT_REQUIRE(x && w && y, "rmsnorm_fwd: null pointer");
+  GGPT_REQUIRE(T > 0 && d % 4 == 0 && ldy % 4 == 0, "rmsnorm_fwd: bad sizes");
+  rmsnorm_fwd_kernel<<<grid_for_rows(T, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, w, static_cast<__nv_bfloat16*>(y), ldy, rstd, T, d, eps);
+  return check_launch("rmsnorm_fwd_kernel");
+}
+
+int ggpt_rmsnorm_bwd(const void* dy, long long lddy, const float* x, const float* rstd, const float* w,
+                     const float* dresid, float* dx_out, void* dx_bf16, float* dw, long long T, int d, void* stream) {
+  GGPT_REQUIRE(dy && x && rstd && w && dx_out && dw, "rmsnorm_bwd: null pointer");
+  GGPT_REQUIRE(T > 0 && d % 4 == 0 && lddy % 4 == 0, "rmsnorm_bwd: bad sizes");
+  GGPT_REQUIRE(d <= 2048, "rmsnorm_bwd: hidden size %d > 2048 is not instantiated", d);
+  const int grid = grid_for_rows(T, 8, 2);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const __nv_bfloat16* dyb = static_cast<const __nv_bfloat16*>(dy);
+  __nv_bfloat16* dxb = static_cast<__nv_bfloat16*>(dx_bf16);
+  const size_t sm = d * sizeof(float);
+  const int nv = (d + 127) / 128;
+  if (nv <= 1) rmsnorm_bwd_kernel<1><<<grid, 256, sm, s>>>(dyb, lddy, x, rstd, w, dresid, dx_out, dxb, dw, T, d);
+  else if (nv <= 2) rmsnorm_bwd_kernel<2><<<grid, 256, sm, s>>>(dyb, lddy, x, rstd, w, dresid, dx_out, dxb, dw, T, d);
+  else if (nv <= 4) rmsnorm_bwd_kernel<4><<<grid, 256, sm, s>>>(dyb, lddy, x, rstd, w, dresid, dx_out, dxb, dw, T, d);
+  else if (nv <= 6) rmsnorm_bwd_kernel<6><<<grid, 256, sm, s>>>(dyb, lddy, x, rstd, w, dresid, dx_out, dxb, dw, T, d);
+  else if (nv <= 8) rmsnorm_bwd_kernel<8><<<grid, 256, sm, s>>>(dyb, lddy, x, rstd, w, dresid, dx_out, dxb, dw, T, d);
+  else rmsnorm_bwd_kernel<16><<<grid, 256, sm, s>>>(dyb, lddy, x, rstd, w, dresid, dx_out, dxb, dw, T, d);
+  return check_launch("rmsnorm_bwd_kernel");
+}
+
+int ggpt_geglu_bwd(const void* dact, const void* gu, void* dgu, long long T, int I, void* stream) {
+  GGPT_REQUIRE(dact && gu && dgu, "geglu_bwd: null pointer");
+  GGPT_REQUIRE(T > 0 && I % 8 == 0, "geglu_bwd: bad sizes");
+  const long long total = T * (I / 8);
+  geglu_bwd_kernel<<<grid_for_rows(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dact), static_cast<const __nv_bfloat16*>(gu), static_cast<__nv_bfloat16*>(dgu), T,
+      I);
+  return check_launch("geglu_bwd_kernel");
+}
+
+long long ggpt_head_scratch_ints(long long T) { return 2 * ((T + kScanBlock - 1) / kScanBlock); }
+
+int ggpt_head_compact(const long long* labels, long long T, int F, int* scratch, int* counts, int* sel_rows,
+                      int* ent_src, int* ent_label, int* ent_tok, void* stream) {
+  GGPT_REQUIRE(labels && scratch && counts && sel_rows && ent_src && ent_label && ent_tok, "head_compact: null pointer");
+  GGPT_REQUIRE(T > 0 && F > 0 && T * F < (1ll << 31), "head_compact: bad sizes");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int nblk = static_cast<int>((T + kScanBlock - 1) / kScanBlock);
+  int* blk_rows = scratch;
+  int* blk_ents = scratch + nblk;
+  head_count_kernel<<<nblk, kScanBlock, 0, s>>>(labels, T, F, blk_rows, blk_ents);
+  if (int rc = check_launch("head_count_kernel")) return rc;
+  head_scan_blocks_kernel<<<1, 1024, 0, s>>>(blk_rows, blk_ents, nblk, counts);
+  if (int rc = check_launch("head_scan_blocks_kernel")) return rc;
+  head_write_kernel<<<nblk, kScanBlock, 0, s>>>(labels, T, F, blk_rows, blk_ents, sel_rows, ent_src, ent_label, ent_tok);
+  return check_launch("head_write_kernel");
+}
+
+int ggpt_gather_rows(const void* src, long long lds, const int* idx, void* out, long long ldo, const int* n_ptr,
+                     int n_max, int d, void* stream) {
+  GGPT_REQUIRE(src && out, "gather_rows: null pointer");
+  GGPT_REQUIRE(d % 8 == 0 && lds % 8 == 0 && ldo % 8 == 0, "gather_rows: d/ld must be multiples of 8");
+  if (n_max <= 0) return 0;
+  const long long total = static_cast<long long>(n_max) * (d / 8);
+  gather_rows_kernel<<<grid_for_rows(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(src), lds, idx, static_cast<__nv_bfloat16*>(out), ldo, n_ptr, n_max, d);
+  return check_launch("gather_rows_kernel");
+}
+
+int ggpt_scatter_rows(const void* src, long long lds, const int* idx, void* out, long long ldo, const int* n_ptr,
+                      int n_max, int d, void* stream) {
+  GGPT_REQUIRE(src && out && idx, "scatter_rows: null pointer");
+  GGPT_REQUIRE(d % 8 == 0 && lds % 8 == 0 && ldo % 8 == 0, "scatter_rows: d/ld must be multiples of 8");
+  if (n_max <= 0) return 0;
+  const long long total = static_cast<long long>(n_max) * (d / 8);
+  scatter_rows_kernel<<<grid_for_rows(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(src), lds, idx, static_cast<__nv_bfloat16*>(out), ldo, n_ptr, n_max, d);
+  return check_launch("scatter_rows_kernel");
+}
+
+int ggpt_ce_fwd(const float* logits, long long ldl, const int* labels, const float* wgt, float* row_lse, float* row_loss,
+                double* loss_sum, double* wgt_sum, int L, int V, int* err_flag, void* stream) {
+  GGPT_REQUIRE(logits && labels && row_lse && loss_sum, "ce_fwd: null pointer");
+  if (L <= 0) return 0;
+  ce_fwd_kernel<<<grid_for_rows(L, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, ldl, labels, wgt, row_lse,
+                                                                                    row_loss, loss_sum, wgt_sum, L, V,
+                                                                                    err_flag);
+  return check_launch("ce_fwd_kernel");
+}
+
+int ggpt_ce_finalize(const double* loss_sum, const double* wgt_sum, const int* count, int mode, float fixed_denom,
+                     float* loss, float* scale, void* stream) {
+  GGPT_REQUIRE(loss_sum && loss && scale, "ce_finalize: null pointer");
+  GGPT_REQUIRE(mode == 2 || (mode == 0 && count) || (mode == 1 && wgt_sum), "ce_finalize: bad mode %d", mode);
+  ce_finalize_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(loss_sum, wgt_sum, count, mode, fixed_denom, loss,
+                                                                     scale);
+  return check_launch("ce_finalize_kernel");
+}
+
+int ggpt_ce_bwd(const float* logits, long long ldl, const int* labels, const float* wgt, const float* row_lse,
+                const float* scale, const float* gout, void* dlogits, long long ldd, int L, int V, void* stream) {
+  GGPT_REQUIRE(logits && labels && row_lse && scale && dlogits, "ce_bwd: null pointer");
+  GGPT_REQUIRE(ldd % 8 == 0 && ldd >= ((V + 7) / 8) * 8, "ce_bwd: ldd must be a multiple of 8 covering V");
+  if (L <= 0) return 0;
+  ce_bwd_kernel<<<grid_for_rows(L, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      logits, ldl, labels, wgt, row_lse, scale, gout, static_cast<__nv_bfloat16*>(dlogits), ldd, L, V, ((V + 7) / 8) * 8);
+  return check_launch("ce_bwd_kernel");
+}
+
+int ggpt_sumsq(const float* g, long long n, double* out, void* stream) {
+  GGPT_REQUIRE(g && out && n > 0, "sumsq: bad arguments");
+  GGPT_REQUIRE((reinterpret_cast<uintptr_t>(g) & 15) == 0, "sumsq: pointer must be 16-byte aligned");
+  sumsq_kernel<<<grid_for_rows(n / 4 + 1, 256, 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(g, n, out);
+  return check_launch("sumsq_kernel");
+}
+
+int ggpt_adamw(float* p, void* p_bf16, const float* g, float* m, float* v, long long n, float lr, float beta1,
+               float beta2, float eps, float weight_decay, int step, const double* gnorm_sq, float max_norm,
+               float grad_scale, void* stream) {
+  GGPT_REQUIRE(p && g && m && v && n > 0 && step >= 1, "adamw: bad arguments");
+  const float bc1 = 1.0f - powf(beta1, static_cast<float>(step));
+  const float bc2 = 1.0f - powf(beta2, static_cast<float>(step));
+  adamw_kernel<<<grid_for_rows(n, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      p, static_cast<__nv_bfloat16*>(p_bf16), g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2, gnorm_sq,
+      max_norm, grad_scale);
+  return check_launch("adamw_kernel");
+}
+
+int ggpt_cast_f32_bf16(const float* src, void* dst, long long n, void* stream) {
+  GGPT_REQUIRE(src && dst && n > 0, "cast: bad arguments");
+  GGPT_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0,
+               "cast: pointers must be 16/8-byte aligned");
+  cast_f32_bf16_kernel<<<grid_for_rows(n / 4 + 1, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, static_cast<__nv_bfloat16*>(dst), n);
+  return check_launch("cast_f32_bf16_kernel");
+}
+
+}  // extern "C"

@@ -27,9 +27,9 @@ def parse_header(path=HEADER_PATH):
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     text = re.sub(r"//.*", "", text)
     protos = {}
-    for m in re.finditer(r"(const char\*|int|void)\s+(ggpt_\w+)\s*\(([^)]*)\)\s*;", text, flags=re.S):
+    for m in re.finditer(r"(const char\*|long long|int|void)\s+(ggpt_\w+)\s*\(([^)]*)\)\s*;", text, flags=re.S):
         ret, name, args = m.group(1), m.group(2), m.group(3)
-        restype = {"int": ctypes.c_int, "void": None, "const char*": ctypes.c_char_p}[ret]
+        restype = {"int": ctypes.c_int, "void": None, "const char*": ctypes.c_char_p, "long long": ctypes.c_longlong}[ret]
         argtypes, argnames = [], []
         args = " ".join(args.split())
         if args and args != "void":
@@ -45,6 +45,10 @@ def parse_header(path=HEADER_PATH):
                     argnames.append(parts[-1])
         protos[name] = (restype, argtypes, argnames)
     return protos
+
+
+# functions whose int return is a value, not a status code
+_VALUE_FUNCS = {"ggpt_abi_version", "ggpt_attn_mask_words"}
 
 
 class _Lib:
@@ -75,8 +79,11 @@ class _Lib:
     def call(self, name, *args):
         dll = self.load()
         rc = getattr(dll, name)(*args)
-        if rc != 0:
-            raise RuntimeError(f"{name} failed (rc={rc}): {self.last_error()}")
+        if self._protos[name][0] is ctypes.c_int and name not in _VALUE_FUNCS:
+            if rc != 0:
+                raise RuntimeError(f"{name} failed (rc={rc}): {self.last_error()}")
+            return None
+        return rc
 
     def __getattr__(self, name):
         if name.startswith("ggpt_"):

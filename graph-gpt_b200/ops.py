@@ -102,3 +102,191 @@ def gemm_qkv_rope(a, wqkv, pos, cos_tab, sin_tab, rope_cols):
     lib.ggpt_gemm_bf16_qkv_rope(a.data_ptr(), a.stride(0), wqkv.data_ptr(), wqkv.stride(0), out.data_ptr(), N,
                                 pos.data_ptr(), cos_tab.data_ptr(), sin_tab.data_ptr(), rope_cols, M, N, K, _stream())
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Attention
+# ------------------------------------------------------------------------------------------------
+class AttnMask:
+    """Bit-matrix form of the reference's additive attention mask (built once per step, shared by all layers)."""
+
+    def __init__(self, bits, cls, N, S):
+        self.bits, self.cls, self.N, self.S = bits, cls, N, S
+
+
+def attn_mask_build(attention_mask, N, S, causal, device):
+    """attention_mask: None, int64 [N,S] or int64 [N,S,S] (modeling_helpers.py:38-64)."""
+    words = lib.ggpt_attn_mask_words(S)
+    nt = (S + 127) // 128
+    bits = torch.empty((N, S, words), device=device, dtype=torch.int32)
+    cls = torch.empty((N, nt, nt), device=device, dtype=torch.uint8)
+    dims = 0
+    if attention_mask is not None:
+        if attention_mask.dim() not in (2, 3):
+            raise NotImplementedError(f"attention_mask of shape {tuple(attention_mask.shape)} is not Implemented")
+        if attention_mask.dtype != torch.int64:
+            attention_mask = attention_mask.to(torch.int64)
+        attention_mask = attention_mask.contiguous()
+        _check(attention_mask, torch.int64, "attention_mask")
+        dims = attention_mask.dim()
+        if attention_mask.shape[0] != N or attention_mask.shape[-1] != S:
+            raise RuntimeError(f"attention_mask shape {tuple(attention_mask.shape)} does not match N={N}, S={S}")
+    lib.ggpt_attn_mask_build(_ptr(attention_mask), dims, N, S, int(bool(causal)), bits.data_ptr(), cls.data_ptr(), _stream())
+    return AttnMask(bits, cls, N, S)
+
+
+def attn_fwd(qkv, mask: AttnMask, H, *, want_lse=True):
+    """qkv bf16 [N*S, 3*H*64] (q | k | v).  Returns (out bf16 [N*S, H*64], lse f32 [N,H,S] or None)."""
+    _check(qkv, BF16, "attn_fwd qkv", 2)
+    N, S = mask.N, mask.S
+    d = H * 64
+    if qkv.shape[0] != N * S or qkv.shape[1] != 3 * d:
+        raise RuntimeError(f"attn_fwd: qkv shape {tuple(qkv.shape)} does not match N={N} S={S} H={H}")
+    out = torch.empty((N * S, d), device=qkv.device, dtype=BF16)
+    lse = torch.empty((N, H, S), device=qkv.device, dtype=F32) if want_lse else None
+    lib.ggpt_attn_fwd(qkv.data_ptr(), qkv.stride(0), 0, d, 2 * d, mask.bits.data_ptr(), mask.cls.data_ptr(),
+                      out.data_ptr(), out.stride(0), _ptr(lse), N, S, H, _stream())
+    return out, lse
+
+
+# ------------------------------------------------------------------------------------------------
+# HBM-bound kernels
+# ------------------------------------------------------------------------------------------------
+def embed_fwd(ids, table, gate=None, long_scale=False, err_flag=None):
+    """ids int64 [T,F]; table f32 [V,d] -> x f32 [T,d]."""
+    _check(ids, torch.int64, "embed ids", 2)
+    _check(table, F32, "embed table", 2)
+    T, F_ = ids.shape
+    V, d = table.shape
+    out = torch.empty((T, d), device=table.device, dtype=F32)
+    lib.ggpt_embed_fwd(ids.data_ptr(), table.data_ptr(), _ptr(gate), out.data_ptr(), T, F_, d, V, int(long_scale),
+                       _ptr(err_flag), _stream())
+    return out
+
+
+def embed_bwd(ids, dx, table, gate, dtable, dgate, padding_idx=0, long_scale=False):
+    _check(ids, torch.int64, "embed ids", 2)
+    _check(dx, F32, "embed dx", 2)
+    T, F_ = ids.shape
+    V, d = dtable.shape
+    lib.ggpt_embed_bwd(ids.data_ptr(), dx.data_ptr(), _ptr(table), _ptr(gate), dtable.data_ptr(), _ptr(dgate), T, F_, d, V,
+                       padding_idx, int(long_scale), _stream())
+
+
+def rmsnorm_fwd(x, w, eps, *, want_rstd=True):
+    _check(x, F32, "rmsnorm x", 2)
+    _check(w, F32, "rmsnorm w", 1)
+    T, d = x.shape
+    y = torch.empty((T, d), device=x.device, dtype=BF16)
+    rstd = torch.empty((T,), device=x.device, dtype=F32) if want_rstd else None
+    lib.ggpt_rmsnorm_fwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), d, _ptr(rstd), T, d, float(eps), _stream())
+    return y, rstd
+
+
+def rmsnorm_bwd(dy, x, rstd, w, dresid, dw, *, want_bf16=True):
+    """Returns (dx f32 [T,d], dx bf16 or None); accumulates into dw."""
+    _check(dy, BF16, "rmsnorm_bwd dy", 2)
+    _check(x, F32, "rmsnorm_bwd x", 2)
+    T, d = x.shape
+    dx = torch.empty((T, d), device=x.device, dtype=F32)
+    dxb = torch.empty((T, d), device=x.device, dtype=BF16) if want_bf16 else None
+    lib.ggpt_rmsnorm_bwd(dy.data_ptr(), dy.stride(0), x.data_ptr(), rstd.data_ptr(), w.data_ptr(), _ptr(dresid),
+                         dx.data_ptr(), _ptr(dxb), dw.data_ptr(), T, d, _stream())
+    return dx, dxb
+
+
+def geglu_bwd(dact, gu):
+    _check(dact, BF16, "geglu_bwd dact", 2)
+    _check(gu, BF16, "geglu_bwd gu", 2)
+    T, I = dact.shape
+    dgu = torch.empty_like(gu)
+    lib.ggpt_geglu_bwd(dact.data_ptr(), gu.data_ptr(), dgu.data_ptr(), T, I, _stream())
+    return dgu
+
+
+class HeadIndex:
+    """Device-side compaction of the labelled rows / entries (modeling_helpers.py:263-301)."""
+
+    def __init__(self, counts, sel_rows, ent_src, ent_label, ent_tok):
+        self.counts, self.sel_rows, self.ent_src, self.ent_label, self.ent_tok = counts, sel_rows, ent_src, ent_label, ent_tok
+        self.M = self.L = None
+
+    def sync_counts(self):
+        if self.M is None:
+            self.M, self.L = (int(v) for v in self.counts.tolist())  # the one D2H read of the step
+        return self.M, self.L
+
+
+def head_compact(labels):
+    """labels int64 [T,F]."""
+    _check(labels, torch.int64, "labels", 2)
+    T, F_ = labels.shape
+    dev = labels.device
+    scratch = torch.empty((lib.ggpt_head_scratch_ints(T),), device=dev, dtype=torch.int32)
+    counts = torch.empty((2,), device=dev, dtype=torch.int32)
+    sel_rows = torch.empty((T,), device=dev, dtype=torch.int32)
+    ent_src = torch.empty((T * F_,), device=dev, dtype=torch.int32)
+    ent_label = torch.empty((T * F_,), device=dev, dtype=torch.int32)
+    ent_tok = torch.empty((T * F_,), device=dev, dtype=torch.int32)
+    lib.ggpt_head_compact(labels.data_ptr(), T, F_, scratch.data_ptr(), counts.data_ptr(), sel_rows.data_ptr(),
+                          ent_src.data_ptr(), ent_label.data_ptr(), ent_tok.data_ptr(), _stream())
+    return HeadIndex(counts, sel_rows, ent_src, ent_label, ent_tok)
+
+
+def gather_rows(src, idx, n, *, n_ptr=None):
+    _check(src, BF16, "gather_rows src", 2)
+    d = src.shape[1]
+    out = torch.empty((n, d), device=src.device, dtype=BF16)
+    lib.ggpt_gather_rows(src.data_ptr(), src.stride(0), _ptr(idx), out.data_ptr(), d, _ptr(n_ptr), n, d, _stream())
+    return out
+
+
+def scatter_rows(src, idx, out, n, *, n_ptr=None):
+    _check(src, BF16, "scatter_rows src", 2)
+    _check(out, BF16, "scatter_rows out", 2)
+    lib.ggpt_scatter_rows(src.data_ptr(), src.stride(0), idx.data_ptr(), out.data_ptr(), out.stride(0), _ptr(n_ptr), n,
+                          src.shape[1], _stream())
+    return out
+
+
+def ce_fwd(logits, labels, V, wgt=None, *, want_row_loss=False, err_flag=None):
+    """logits f32 [L, ld>=V]; labels int32 [>=L].  Returns (row_lse, row_loss|None, loss_sum f64[1], wgt_sum f64[1])."""
+    _check(logits, F32, "ce logits", 2)
+    L = logits.shape[0]
+    dev = logits.device
+    row_lse = torch.empty((L,), device=dev, dtype=F32)
+    row_loss = torch.empty((L,), device=dev, dtype=F32) if want_row_loss else None
+    sums = torch.zeros((2,), device=dev, dtype=torch.float64)
+    lib.ggpt_ce_fwd(logits.data_ptr(), logits.stride(0), labels.data_ptr(), _ptr(wgt), row_lse.data_ptr(), _ptr(row_loss),
+                    sums.data_ptr(), sums.data_ptr() + 8, L, V, _ptr(err_flag), _stream())
+    return row_lse, row_loss, sums
+
+
+def ce_finalize(sums, count_ptr, mode, fixed_denom=1.0):
+    out = torch.empty((2,), device=sums.device, dtype=F32)  # [loss, scale]
+    lib.ggpt_ce_finalize(sums.data_ptr(), sums.data_ptr() + 8, count_ptr, mode, float(fixed_denom), out.data_ptr(),
+                         out.data_ptr() + 4, _stream())
+    return out
+
+
+def ce_bwd(logits, labels, V, row_lse, scale_ptr, gout, wgt=None):
+    L = logits.shape[0]
+    ldd = (V + 7) // 8 * 8
+    dlogits = torch.empty((L, ldd), device=logits.device, dtype=BF16)
+    lib.ggpt_ce_bwd(logits.data_ptr(), logits.stride(0), labels.data_ptr(), _ptr(wgt), row_lse.data_ptr(), scale_ptr,
+                    _ptr(gout), dlogits.data_ptr(), ldd, L, V, _stream())
+    return dlogits
+
+
+def sumsq(g, out):
+    lib.ggpt_sumsq(g.data_ptr(), g.numel(), out.data_ptr(), _stream())
+
+
+def adamw(p, p_bf16, g, m, v, *, lr, betas, eps, weight_decay, step, gnorm_sq=None, max_norm=0.0, grad_scale=1.0):
+    lib.ggpt_adamw(p.data_ptr(), _ptr(p_bf16), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), float(lr),
+                   float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step), _ptr(gnorm_sq),
+                   float(max_norm), float(grad_scale), _stream())
+
+
+def cast_f32_bf16(src, dst):
+    lib.ggpt_cast_f32_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), _stream())

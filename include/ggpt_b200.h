@@ -62,6 +62,86 @@ int ggpt_gemm_bf16_qkv_rope(const void* A, long long lda, const void* Wqkv, long
                             const int* pos, const float* cos_tab, const float* sin_tab, int rope_cols, int M, int N,
                             int K, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Attention.  qkv is the fused projection output [N*S, ld_qkv] (bf16); q/k/v of head h live at columns
+ * {q,k,v}_col0 + 64*h.  The mask is a bit matrix built once per step.
+ * ------------------------------------------------------------------------------------------- */
+/* uint32 words per mask row for sequence length S (multiple of 4 = one 128-key tile per uint4). */
+int ggpt_attn_mask_words(int S);
+
+/* attention_mask: int64 [N,S] (key padding mask) if mask_dims == 2, [N,S,S] if 3, or NULL (all visible);
+ * causal != 0 additionally hides keys k > q.  Outputs mask_bits [N,S,words] and tile_cls [N,nT,nT]
+ * (nT = ceil(S/128); 0 = tile fully masked, 1 = fully visible, 2 = mixed).
+ * ref: modeling_helpers.py:38-64 (_update_causal_mask, _expand_mask_from_3d_mask: additive 0/finfo.min mask),
+ *      HF:398-405 (causal mask when config.causal_attention).  Fully masked query rows yield 0 here (the
+ *      reference yields a uniform average; such rows are padding and never consumed). */
+int ggpt_attn_mask_build(const long long* attention_mask, int mask_dims, int N, int S, int causal, uint32_t* mask_bits,
+                         uint8_t* tile_cls, void* stream);
+
+/* out[N*S, H*64] = softmax(q k^T / 8 + mask) v per head; lse[N,H,S] (may be NULL) = log-sum-exp of the scaled
+ * scores, kept for the backward pass.   ref: HF:199-221 (eager_attention_forward), fp32 softmax. */
+int ggpt_attn_fwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int v_col0, const uint32_t* mask_bits,
+                  const uint8_t* tile_cls, void* out, long long ldo, float* lse, int N, int S, int H, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * HBM-bound kernels
+ * ------------------------------------------------------------------------------------------- */
+/* x[t,:] = sum_f gate[f,:] * table[ids[t,f],:] (gate NULL -> plain sum); long_scale applies the
+ * stack_method=="long" 1/nnz rescale.  err_flag (may be NULL) is set to 1 on an out-of-range id.
+ * ref: modeling_helpers.py:89-114, modeling_common.py:127-135. */
+int ggpt_embed_fwd(const long long* ids, const float* table, const float* gate, float* out, long long T, int F, int d,
+                   int V, int long_scale, int* err_flag, void* stream);
+/* dtable[id,:] += gate[f,:]*dx[t,:] for id != padding_idx (dtable pre-zeroed / accumulating), dgate likewise.
+ * ref: autograd of the above; nn.Embedding(padding_idx=0) HF:361. */
+int ggpt_embed_bwd(const long long* ids, const float* dx, const float* table, const float* gate, float* dtable,
+                   float* dgate, long long T, int F, int d, int V, int padding_idx, int long_scale, void* stream);
+
+/* y = bf16(w * x * rsqrt(mean(x^2)+eps)), rstd[T] saved for backward (may be NULL).   ref: HF:59-64 */
+int ggpt_rmsnorm_fwd(const float* x, const float* w, void* y, long long ldy, float* rstd, long long T, int d, float eps,
+                     void* stream);
+/* dx_out = dresid (may be NULL) + dRMSNorm(dy); dx_bf16 (may be NULL) = bf16 copy; dw += sum_t dy * xhat. */
+int ggpt_rmsnorm_bwd(const void* dy, long long lddy, const float* x, const float* rstd, const float* w,
+                     const float* dresid, float* dx_out, void* dx_bf16, float* dw, long long T, int d, void* stream);
+
+/* dgu = [dact*u*gelu'(g) | dact*gelu(g)] for gu = [g | u].   ref: autograd of HF:182-184 with erf GELU */
+int ggpt_geglu_bwd(const void* dact, const void* gu, void* dgu, long long T, int I, void* stream);
+
+/* Loss-head compaction without host-side boolean indexing.  labels int64 [T,F] (-100 = ignore).
+ * counts[0] = M rows with >= 1 label, counts[1] = L labelled entries; sel_rows[M] token index per selected row;
+ * ent_src[L] = m*F+f, ent_label[L], ent_tok[L] in the reference's row-major order.
+ * scratch needs ggpt_head_scratch_ints(T) ints.   ref: modeling_helpers.py:263-301. */
+long long ggpt_head_scratch_ints(long long T);
+int ggpt_head_compact(const long long* labels, long long T, int F, int* scratch, int* counts, int* sel_rows,
+                      int* ent_src, int* ent_label, int* ent_tok, void* stream);
+/* out[i,:] = src[idx[i],:] (idx NULL -> identity) / out[idx[i],:] = src[i,:]; bf16 rows of d elements;
+ * the row count is min(*n_ptr, n_max) when n_ptr != NULL (device-side count, no host sync). */
+int ggpt_gather_rows(const void* src, long long lds, const int* idx, void* out, long long ldo, const int* n_ptr,
+                     int n_max, int d, void* stream);
+int ggpt_scatter_rows(const void* src, long long lds, const int* idx, void* out, long long ldo, const int* n_ptr,
+                      int n_max, int d, void* stream);
+
+/* fp32 cross-entropy over logits [L, ldl] (V valid columns): row_lse, optional row_loss, and
+ * loss_sum += wgt[e]*(lse - logit[label]) (wgt NULL -> 1), wgt_sum += wgt[e] (may be NULL).
+ * ref: modeling_helpers.py:145-198 (CrossEntropyLoss on logits.float()). */
+int ggpt_ce_fwd(const float* logits, long long ldl, const int* labels, const float* wgt, float* row_lse, float* row_loss,
+                double* loss_sum, double* wgt_sum, int L, int V, int* err_flag, void* stream);
+/* loss = loss_sum / denom, scale = 1/denom; mode 0: denom = *count (mean), 1: *wgt_sum + 1e-7, 2: fixed_denom. */
+int ggpt_ce_finalize(const double* loss_sum, const double* wgt_sum, const int* count, int mode, float fixed_denom,
+                     float* loss, float* scale, void* stream);
+/* dlogits (bf16 [L, ldd], pad columns zeroed) = (softmax - onehot) * wgt[e] * scale[0] * gout[0] (gout NULL -> 1). */
+int ggpt_ce_bwd(const float* logits, long long ldl, const int* labels, const float* wgt, const float* row_lse,
+                const float* scale, const float* gout, void* dlogits, long long ldd, int L, int V, void* stream);
+
+/* out += sum(g^2) (double accumulator, pre-zeroed by the caller). */
+int ggpt_sumsq(const float* g, long long n, double* out, void* stream);
+/* Fused AdamW (torch.optim.AdamW semantics) over a flat fp32 parameter buffer, with optional global-norm clipping
+ * (gnorm_sq = device pointer to sum of squared grads, max_norm > 0) and grad_scale (1/loss-scale or 1/world).
+ * Also writes the bf16 compute copy p_bf16 (may be NULL).   ref: training_utils.py:71-86, opt_utils.py:18-24. */
+int ggpt_adamw(float* p, void* p_bf16, const float* g, float* m, float* v, long long n, float lr, float beta1,
+               float beta2, float eps, float weight_decay, int step, const double* gnorm_sq, float max_norm,
+               float grad_scale, void* stream);
+int ggpt_cast_f32_bf16(const float* src, void* dst, long long n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,226 @@
+"""GPU parity of the attention forward kernel and the HBM-bound kernels against plain torch fp32 references of
+the same op (the oracle's formulas).  Tolerances are stated per test."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_attention(qkv, am, causal, N, S, H):
+    """oracle.attention on bf16-rounded q,k,v (fp32 math); returns out [N*S, H*64], lse [N,H,S] and the keep mask."""
+    d = H * 64
+    x = qkv.float().view(N, S, 3, H, 64)
+    q, k, v = (x[:, :, i].transpose(1, 2) for i in range(3))
+    if am is None:
+        keep = torch.ones((N, 1, S, S), dtype=torch.bool, device=qkv.device)
+    elif am.dim() == 2:
+        keep = am[:, None, None, :].bool().expand(N, 1, S, S)
+    else:
+        keep = am[:, None].bool()
+    if causal:
+        keep = keep & torch.ones((S, S), dtype=torch.bool, device=qkv.device).tril()[None, None]
+    s = (q @ k.transpose(2, 3)) * 0.125
+    s = s.masked_fill(~keep, float("-inf"))
+    lse = torch.logsumexp(s, -1)
+    p = torch.exp(s - lse[..., None])
+    p = torch.nan_to_num(p, nan=0.0)
+    o = (p @ v).transpose(1, 2).reshape(N * S, d)
+    return o, lse, keep
+
+
+CASES = [
+    # N, S, H, mask kind, causal
+    (2, 128, 1, "none", False),
+    (2, 256, 2, "none", False),
+    (3, 40, 2, "pad", False),
+    (2, 200, 3, "pad", False),
+    (2, 384, 2, "packed", False),
+    (2, 1024, 2, "packed", False),
+    (2, 300, 2, "pad", True),
+    (1, 1024, 12, "none", False),
+    (2, 512, 2, "random", False),
+]
+
+
+@pytest.mark.parametrize("N,S,H,kind,causal", CASES)
+def test_attn_fwd(N, S, H, kind, causal):
+    from graphgpt_b200 import ops
+    g = torch.Generator().manual_seed(S * 7 + H)
+    d = H * 64
+    qkv = (torch.randn((N * S, 3 * d), generator=g) * 1.5).to(torch.bfloat16).cuda()
+    if kind == "none":
+        am = None
+    elif kind == "pad":
+        lens = torch.randint(S // 3, S + 1, (N,), generator=g)
+        am = (torch.arange(S)[None, :] < lens[:, None]).long().cuda()
+    elif kind == "packed":
+        am = torch.zeros((N, S, S), dtype=torch.long)
+        for n in range(N):
+            o = 0
+            while o < S:
+                L = int(torch.randint(8, 40, (1,), generator=g))
+                L = min(L, S - o)
+                am[n, o:o + L, o:o + L] = 1
+                o += L
+        am = am.cuda()
+    else:
+        am = (torch.rand((N, S, S), generator=g) < 0.3).long()
+        am[:, torch.arange(S), torch.arange(S)] = 1
+        am = am.cuda()
+    mask = ops.attn_mask_build(am, N, S, causal, qkv.device)
+    out, lse = ops.attn_fwd(qkv, mask, H)
+    torch.cuda.synchronize()
+    ref_o, ref_lse, keep = _ref_attention(qkv, am, causal, N, S, H)
+    valid = keep.any(-1)[:, 0]                                    # [N,S] rows with at least one visible key
+    vrow = valid.reshape(N * S)
+    err = (out.float() - ref_o)[vrow].abs().max().item()
+    scale = ref_o[vrow].abs().max().item()
+    # P is rounded to bf16 before PV (2^-9 relative per term) and the output is bf16: 1e-2 of the output scale
+    assert err <= 1e-2 * scale, f"attn out err {err} scale {scale}"
+    lerr = (lse - ref_lse)[valid[:, None, :].expand(N, H, S)].abs().max().item()
+    assert lerr <= 2e-3, f"lse err {lerr}"
+    # fully masked rows produce exact zeros
+    if (~vrow).any():
+        assert out[~vrow].abs().max().item() == 0.0
+
+
+def test_embed_fwd_bwd():
+    from graphgpt_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    T, F_, d, V = 1000, 13, 768, 756
+    ids = torch.randint(0, V, (T, F_), generator=g).cuda()
+    ids[::7] = 0
+    table = torch.randn((V, d), generator=g).cuda()
+    gate = torch.randn((F_, d), generator=g).cuda()
+    x = ops.embed_fwd(ids, table)
+    ref = table[ids].sum(1)
+    assert (x - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()     # fp32 sum order only
+    xg = ops.embed_fwd(ids, table, gate)
+    refg = torch.einsum("tfd,fd->td", table[ids], gate)
+    assert (xg - refg).abs().max().item() <= 1e-5 * refg.abs().max().item()
+    dx = torch.randn((T, d), generator=g).cuda()
+    dtable = torch.zeros_like(table)
+    ops.embed_bwd(ids, dx, None, None, dtable, None)
+    t2 = table.clone().requires_grad_(True)
+    torch.nn.functional.embedding(ids, t2, padding_idx=0).sum(1).backward(dx)
+    assert (dtable - t2.grad).abs().max().item() <= 2e-4 * t2.grad.abs().max().item()   # atomic fp32 sum order
+    assert dtable[0].abs().max().item() == 0.0
+    dtable.zero_()
+    dgate = torch.zeros_like(gate)
+    ops.embed_bwd(ids, dx, table, gate, dtable, dgate)
+    t3 = table.clone().requires_grad_(True)
+    g3 = gate.clone().requires_grad_(True)
+    torch.einsum("tfd,fd->td", torch.nn.functional.embedding(ids, t3, padding_idx=0), g3).backward(dx)
+    assert (dtable - t3.grad).abs().max().item() <= 2e-4 * t3.grad.abs().max().item()
+    assert (dgate - g3.grad).abs().max().item() <= 2e-4 * g3.grad.abs().max().item()
+
+
+@pytest.mark.parametrize("T,d", [(1000, 768), (300, 64), (200, 128), (100, 1024)])
+def test_rmsnorm_fwd_bwd(T, d):
+    from graphgpt_b200 import ops
+    g = torch.Generator().manual_seed(d)
+    x = torch.randn((T, d), generator=g).cuda() * 2
+    w = (1 + 0.1 * torch.randn((d,), generator=g)).cuda()
+    y, rstd = ops.rmsnorm_fwd(x, w, 1e-6)
+    xr = x.clone().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    ref = wr * (xr * torch.rsqrt(xr.pow(2).mean(-1, keepdim=True) + 1e-6))
+    assert (y.float() - ref).abs().max().item() <= 5e-3 * ref.abs().max().item()        # one bf16 rounding
+    dy = torch.randn((T, d), generator=g).to(torch.bfloat16).cuda()
+    dres = torch.randn((T, d), generator=g).cuda()
+    ref.backward(dy.float())
+    dw = torch.zeros_like(w)
+    dx, dxb = ops.rmsnorm_bwd(dy, x, rstd, w, dres, dw)
+    torch.cuda.synchronize()
+    assert (dx - (dres + xr.grad)).abs().max().item() <= 1e-4 * (dres + xr.grad).abs().max().item()
+    assert (dw - wr.grad).abs().max().item() <= 1e-4 * wr.grad.abs().max().item()
+    assert (dxb.float() - dx).abs().max().item() <= 5e-3 * dx.abs().max().item()
+
+
+def test_geglu_bwd():
+    from graphgpt_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    T, I = 500, 3072
+    gu = torch.randn((T, 2 * I), generator=g).to(torch.bfloat16).cuda()
+    dact = torch.randn((T, I), generator=g).to(torch.bfloat16).cuda()
+    gg = gu.float().clone().requires_grad_(True)
+    (torch.nn.functional.gelu(gg[:, :I]) * gg[:, I:]).backward(dact.float())
+    dgu = ops.geglu_bwd(dact, gu)
+    assert (dgu.float() - gg.grad).abs().max().item() <= 5e-3 * gg.grad.abs().max().item()
+
+
+@pytest.mark.parametrize("T,F_", [(1000, 13), (70000, 13), (513, 1), (256, 4)])
+def test_head_compact_and_gather(T, F_):
+    from graphgpt_b200 import ops
+    g = torch.Generator().manual_seed(T)
+    labels = torch.where(torch.rand((T, F_), generator=g) < 0.3, torch.randint(0, 700, (T, F_), generator=g), -100)
+    labels[T // 3: T // 2] = -100
+    labels = labels.cuda()
+    hi = ops.head_compact(labels)
+    M, L = hi.sync_counts()
+    mask = labels != -100
+    mask_m = mask.any(-1)
+    assert M == int(mask_m.sum()) and L == int(mask.sum())
+    assert torch.equal(hi.sel_rows[:M].long(), mask_m.nonzero()[:, 0])
+    assert torch.equal(hi.ent_label[:L].long(), labels[mask_m][mask[mask_m]])
+    src_ref = mask[mask_m].reshape(-1).nonzero()[:, 0]
+    assert torch.equal(hi.ent_src[:L].long(), src_ref)
+    assert torch.equal(hi.ent_tok[:L].long(), mask.nonzero()[:, 0])
+    h = torch.randn((T, 64), generator=g).to(torch.bfloat16).cuda()
+    sel = ops.gather_rows(h, hi.sel_rows, M)
+    assert torch.equal(sel, h[mask_m])
+    back = torch.zeros_like(h)
+    ops.scatter_rows(sel, hi.sel_rows, back, M)
+    assert torch.equal(back[mask_m], h[mask_m]) and back[~mask_m].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("L,V", [(1000, 756), (333, 300), (64, 41244)])
+def test_ce_fwd_bwd(L, V):
+    from graphgpt_b200 import ops
+    g = torch.Generator().manual_seed(V)
+    ld = (V + 7) // 8 * 8
+    logits = (torch.randn((L, ld), generator=g) * 3).cuda()
+    labels = torch.randint(0, V, (L,), generator=g, dtype=torch.int32).cuda()
+    wgt = torch.rand((L,), generator=g).cuda()
+    lg = logits[:, :V].clone().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(lg, labels.long())
+    row_lse, row_loss, sums = ops.ce_fwd(logits, labels, V, want_row_loss=True)
+    cnt = torch.tensor([L], dtype=torch.int32).cuda()
+    ls = ops.ce_finalize(sums, cnt.data_ptr(), 0)
+    assert abs(ls[0].item() - ref.item()) <= 1e-5 * abs(ref.item())
+    ref.backward()
+    gout = torch.tensor([1.0]).cuda()
+    dl = ops.ce_bwd(logits, labels, V, row_lse, ls.data_ptr() + 4, gout)
+    assert (dl[:, :V].float() - lg.grad).abs().max().item() <= 5e-3 * lg.grad.abs().max().item()
+    assert dl[:, V:].abs().max().item() == 0 if ld > V else True
+    # weighted (dLM): sum(ce * w) / fixed
+    row_lse, _, sums = ops.ce_fwd(logits, labels, V, wgt)
+    ls = ops.ce_finalize(sums, 0, 2, 1234.0)
+    refw = (torch.nn.functional.cross_entropy(logits[:, :V], labels.long(), reduction="none") * wgt).sum() / 1234.0
+    assert abs(ls[0].item() - refw.item()) <= 1e-5 * abs(refw.item())
+
+
+def test_adamw_and_sumsq():
+    from graphgpt_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    n = 100003
+    p = torch.randn((n,), generator=g).cuda()
+    gr = torch.randn((n,), generator=g).cuda() * 3
+    pr = p.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([pr], lr=1e-3, betas=(0.9, 0.95), eps=1e-6, weight_decay=0.1)
+    m = torch.zeros_like(p)
+    v = torch.zeros_like(p)
+    pb = torch.empty((n,), dtype=torch.bfloat16).cuda()
+    for step in range(1, 4):
+        pr.grad = gr.clone()
+        torch.nn.utils.clip_grad_norm_([pr], 1.0)
+        opt.step()
+        ss = torch.zeros((1,), dtype=torch.float64).cuda()
+        ops.sumsq(gr, ss)
+        assert abs(ss.item() - gr.double().pow(2).sum().item()) <= 1e-6 * ss.item()
+        ops.adamw(p, pb, gr, m, v, lr=1e-3, betas=(0.9, 0.95), eps=1e-6, weight_decay=0.1, step=step, gnorm_sq=ss,
+                  max_norm=1.0)
+        assert (p - pr.detach()).abs().max().item() <= 2e-6
+    assert (pb.float() - p).abs().max().item() <= 4e-3 * p.abs().max().item()
