@@ -1,0 +1,418 @@
+// Attention backward on tcgen05 (sm_100a): dQ, dK, dV of softmax(Q K^T / 8 + mask) V with recomputation of the
+// probabilities from the saved log-sum-exp (no [N,H,S,S] tensor is ever stored).  autograd of HF:199-221.
+//
+// Two deterministic passes of one templated kernel (no atomics):
+//   DKV : one CTA per (key tile, head, sequence), streams the query tiles:   dV += P^T dO,  dK += dS^T Q
+//   DQ  : one CTA per (query tile, head, sequence), streams the key tiles:   dQ += dS K
+// with  S = Q K^T,  P = exp(S/8 - lse),  dP = dO V^T,  dS = P * (dP - D) / 8,  D = rowsum(dO * O).
+// All five products run on tcgen05 with TMEM accumulators; P / dS are written by the softmax warps to shared
+// memory in the 128-byte-swizzled layout and consumed either as a K-major A operand (dS K) or, through the
+// MN-major descriptor, as the transposed A operand (P^T dO, dS^T Q) — no explicit transposes.  The epilogue
+// un-rotates dQ / dK (inverse RoPE) so the result is the gradient of the fused q|k|v projection output.
+#include "common.cuh"
+#include "../../include/ggpt_b200.h"
+
+namespace ggpt {
+
+constexpr int kBwdThreads = 192;
+
+struct AttnBwdParams {
+  int N, S, H;
+  int n_t;                    // tiles per side
+  int mask_words;
+  const uint32_t* mask_bits;  // [N,S,words]
+  const uint8_t* tile_cls;    // [N,n_t,n_t]  (query tile major)
+  const float* lse;           // [N,H,S]
+  const float* dsum;          // [N,H,S]   D = rowsum(dO*O)
+  __nv_bfloat16* dqkv;        // [N*S, ld]
+  long long ld;
+  int q_col0, k_col0, v_col0;
+  const int* pos;             // [N*S]
+  const float* cos_tab;
+  const float* sin_tab;
+  float scale;                // 1/8
+  float scale_log2;           // scale * log2(e)
+};
+
+// smem: fixed pair 2x16K | streamed pair 2 stages x 2 x 16K | P 32K (DKV only) | dS 32K | barriers
+template <bool DKV>
+struct BwdSmem {
+  static constexpr int kFixed = 0;
+  static constexpr int kStream = 32768;
+  static constexpr int kP = kStream + 65536;
+  static constexpr int kDS = kP + (DKV ? 32768 : 0);
+  static constexpr int kBars = kDS + 32768;
+  static constexpr int kTotal = kBars + 256;
+};
+
+template <bool DKV>
+__global__ void __launch_bounds__(kBwdThreads, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                const AttnBwdParams p) {
+  using L = BwdSmem<DKV>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sFix0 = smem + L::kFixed;            // DKV: K_j      DQ: Q_i
+  uint8_t* sFix1 = smem + L::kFixed + 16384;    // DKV: V_j      DQ: dO_i
+  uint8_t* sStr = smem + L::kStream;            // stage s: [s*32768] = (DKV ? Q_i : K_j), [+16384] = (DKV ? dO_i : V_j)
+  uint8_t* sP = smem + L::kP;
+  uint8_t* sDS = smem + L::kDS;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBars);
+  uint64_t* fix_full = bars + 0;
+  uint64_t* str_full = bars + 1;    // [2]
+  uint64_t* str_empty = bars + 3;   // [2]
+  uint64_t* sdp_full = bars + 5;    // S and dP accumulators ready
+  uint64_t* pds_full = bars + 6;    // P / dS written to smem, S / dP drained        (count 4)
+  uint64_t* pds_empty = bars + 7;   // MMAs that read P / dS have retired
+  uint64_t* acc_full = bars + 8;    // final accumulators ready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tile = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
+  const uint8_t* cls_n = p.tile_cls + static_cast<size_t>(n) * p.n_t * p.n_t;
+  // class of (query tile, key tile) for streamed index t
+  auto cls_of = [&](int t) -> int { return DKV ? cls_n[t * p.n_t + tile] : cls_n[tile * p.n_t + t]; };
+
+  if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) {
+      printf("ggpt attn_bwd: dynamic smem base not 1024-aligned\n");
+      __trap();
+    }
+    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmDO);
+    mbar_init(fix_full, 1);
+    mbar_init(&str_full[0], 1);
+    mbar_init(&str_full[1], 1);
+    mbar_init(&str_empty[0], 1);
+    mbar_init(&str_empty[1], 1);
+    mbar_init(sdp_full, 1);
+    mbar_init(pds_full, 4);
+    mbar_init(pds_empty, 1);
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base;           // [0,128)
+  const uint32_t tmem_dP = tmem_base + 128;    // [128,256)
+  const uint32_t tmem_A0 = tmem_base + 256;    // DKV: dV   DQ: dQ      (64 columns)
+  const uint32_t tmem_A1 = tmem_base + 320;    // DKV: dK
+
+  int n_active = 0;
+  for (int t = 0; t < p.n_t; ++t) n_active += (cls_of(t) != 0);
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0 && n_active > 0) {
+      mbar_expect_tx(fix_full, 32768);
+      if (DKV) {
+        tma_load_3d(sFix0, &tmQKV, fix_full, p.k_col0 + h * 64, tile * 128, n);
+        tma_load_3d(sFix1, &tmQKV, fix_full, p.v_col0 + h * 64, tile * 128, n);
+      } else {
+        tma_load_3d(sFix0, &tmQKV, fix_full, p.q_col0 + h * 64, tile * 128, n);
+        tma_load_3d(sFix1, &tmDO, fix_full, h * 64, tile * 128, n);
+      }
+      int it = 0;
+      for (int t = 0; t < p.n_t; ++t) {
+        if (cls_of(t) == 0) continue;
+        const int st = it & 1;
+        mbar_wait(&str_empty[st], ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(&str_full[st], 32768);
+        if (DKV) {
+          tma_load_3d(sStr + st * 32768, &tmQKV, &str_full[st], p.q_col0 + h * 64, t * 128, n);
+          tma_load_3d(sStr + st * 32768 + 16384, &tmDO, &str_full[st], h * 64, t * 128, n);
+        } else {
+          tma_load_3d(sStr + st * 32768, &tmQKV, &str_full[st], p.k_col0 + h * 64, t * 128, n);
+          tma_load_3d(sStr + st * 32768 + 16384, &tmQKV, &str_full[st], p.v_col0 + h * 64, t * 128, n);
+        }
+        ++it;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0 && n_active > 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);     // S, dP : K-major x K-major
+      constexpr uint32_t idesc_t = umma_idesc_bf16(128, 64, true, true);        // P^T dO, dS^T Q : MN x MN
+      constexpr uint32_t idesc_q = umma_idesc_bf16(128, 64, false, true);       // dS K : K-major x MN-major
+      const uint32_t aFix0 = smem_u32(sFix0), aFix1 = smem_u32(sFix1), aP = smem_u32(sP), aDS = smem_u32(sDS);
+      auto issue_scores = [&](int st) {
+        const uint32_t a0 = smem_u32(sStr + st * 32768), a1 = a0 + 16384;
+        const uint32_t aQ = DKV ? a0 : aFix0, aK = DKV ? aFix0 : a0;
+        const uint32_t aDO = DKV ? a1 : aFix1, aV = DKV ? aFix1 : a1;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          tc_mma_bf16(tmem_S, umma_desc_sw128(aQ + kk * 32, 16, 1024), umma_desc_sw128(aK + kk * 32, 16, 1024),
+                      idesc_s, kk != 0);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          tc_mma_bf16(tmem_dP, umma_desc_sw128(aDO + kk * 32, 16, 1024), umma_desc_sw128(aV + kk * 32, 16, 1024),
+                      idesc_s, kk != 0);
+        tc_commit(sdp_full);
+      };
+      mbar_wait(fix_full, 0);
+      mbar_wait(&str_full[0], 0);
+      tc_fence_after();
+      issue_scores(0);
+      for (int it = 0; it < n_active; ++it) {
+        const int st = it & 1;
+        mbar_wait(pds_full, it & 1);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(sStr + st * 32768), a1 = a0 + 16384;
+        if (DKV) {
+          // dV += P^T dO_i ; dK += dS^T Q_i      (A = P / dS read MN-major: M = keys, K = query rows)
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            tc_mma_bf16(tmem_A0, umma_desc_sw128(aP + kk * 2048, 16384, 1024),
+                        umma_desc_sw128(a1 + kk * 2048, 8192, 1024), idesc_t, (it | kk) != 0);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            tc_mma_bf16(tmem_A1, umma_desc_sw128(aDS + kk * 2048, 16384, 1024),
+                        umma_desc_sw128(a0 + kk * 2048, 8192, 1024), idesc_t, (it | kk) != 0);
+        } else {
+          // dQ += dS K_j      (A = dS K-major: M = query rows, K = keys; B = K_j MN-major)
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            tc_mma_bf16(tmem_A0, umma_desc_sw128(aDS + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                        umma_desc_sw128(a0 + kk * 2048, 8192, 1024), idesc_q, (it | kk) != 0);
+        }
+        tc_commit(pds_empty);
+        tc_commit(&str_empty[st]);
+        if (it + 1 < n_active) {
+          const int st2 = (it + 1) & 1;
+          mbar_wait(&str_full[st2], ((it + 1) >> 1) & 1);
+          tc_fence_after();
+          issue_scores(st2);
+        } else {
+          tc_commit(acc_full);
+        }
+      }
+    }
+  } else {
+    // ===================== softmax-gradient warps: one query row per thread =====================
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+    int it = 0;
+    for (int t = 0; t < p.n_t; ++t) {
+      const int cls = cls_of(t);
+      if (cls == 0) continue;
+      const int qt = DKV ? t : tile;
+      const int kt = DKV ? tile : t;
+      const int q_row = qt * 128 + r;
+      const bool row_ok = q_row < p.S;
+      float lse2 = 0.f, dsum = 0.f;
+      uint32_t mw[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+      if (row_ok) {
+        const size_t li = (static_cast<size_t>(n) * p.H + h) * p.S + q_row;
+        lse2 = p.lse[li] * 1.4426950408889634f;
+        dsum = p.dsum[li];
+        if (cls == 2) {
+          const uint4 v = *reinterpret_cast<const uint4*>(
+              p.mask_bits + (static_cast<size_t>(n) * p.S + q_row) * p.mask_words + kt * 4);
+          mw[0] = v.x; mw[1] = v.y; mw[2] = v.z; mw[3] = v.w;
+        }
+      } else {
+        mw[0] = mw[1] = mw[2] = mw[3] = 0u;
+      }
+      mbar_wait(sdp_full, it & 1);
+      tc_fence_after();
+      if (it > 0) mbar_wait(pds_empty, (it - 1) & 1);   // previous P / dS consumed by the tensor core
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t s[32], dp[32];
+        tmem_ld32(tmem_S + lane_addr + c * 32, s);
+        tmem_ld32(tmem_dP + lane_addr + c * 32, dp);
+        tmem_ld_wait();
+        const uint32_t w = (c == 0) ? mw[0] : (c == 1) ? mw[1] : (c == 2) ? mw[2] : mw[3];
+        uint8_t* pbase = sP + (c >> 1) * 16384 + r * 128;
+        uint8_t* dbase = sDS + (c >> 1) * 16384 + r * 128;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float pv[8], dv[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float e = exp2f(__uint_as_float(s[g * 8 + j]) * p.scale_log2 - lse2);
+            pv[j] = ((w >> (g * 8 + j)) & 1u) ? e : 0.f;
+            dv[j] = pv[j] * (__uint_as_float(dp[g * 8 + j]) - dsum) * p.scale;
+          }
+          const int chunk = ((c & 1) * 4 + g) ^ (r & 7);
+          if (DKV) {
+            uint4 o;
+            o.x = pack_bf16(pv[0], pv[1]); o.y = pack_bf16(pv[2], pv[3]);
+            o.z = pack_bf16(pv[4], pv[5]); o.w = pack_bf16(pv[6], pv[7]);
+            *reinterpret_cast<uint4*>(pbase + chunk * 16) = o;
+          }
+          uint4 o2;
+          o2.x = pack_bf16(dv[0], dv[1]); o2.y = pack_bf16(dv[2], dv[3]);
+          o2.z = pack_bf16(dv[4], dv[5]); o2.w = pack_bf16(dv[6], dv[7]);
+          *reinterpret_cast<uint4*>(dbase + chunk * 16) = o2;
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_full);
+      ++it;
+    }
+
+    // ---- epilogue: this thread owns output row `tile*128 + r`
+    const int out_row = tile * 128 + r;
+    if (n_active > 0) {
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+    }
+    const bool ok = out_row < p.S;
+    const long long grow = static_cast<long long>(n) * p.S + out_row;
+    const int pos = ok ? p.pos[grow] : 0;
+    const float* cs = p.cos_tab + static_cast<long long>(pos) * 32;
+    const float* sn = p.sin_tab + static_cast<long long>(pos) * 32;
+    constexpr int kNumAcc = DKV ? 2 : 1;
+#pragma unroll
+    for (int a = 0; a < kNumAcc; ++a) {
+      // a == 0: dV (DKV, no rotation) or dQ (DQ, rotated);  a == 1: dK (rotated)
+      const bool rot = DKV ? (a == 1) : true;
+      const int col0 = (DKV ? (a == 0 ? p.v_col0 : p.k_col0) : p.q_col0) + h * 64;
+      uint32_t x1[32], x2[32];
+      if (n_active > 0) {
+        tmem_ld32((a == 0 ? tmem_A0 : tmem_A1) + lane_addr, x1);
+        tmem_ld32((a == 0 ? tmem_A0 : tmem_A1) + lane_addr + 32, x2);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x1[j] = x2[j] = 0u;
+      }
+      if (ok) {
+        __nv_bfloat16* orow = p.dqkv + grow * p.ld + col0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float o1[8], o2[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float d1 = __uint_as_float(x1[g * 8 + j]);
+            const float d2 = __uint_as_float(x2[g * 8 + j]);
+            if (rot) {
+              const float c = cs[g * 8 + j], s = sn[g * 8 + j];
+              o1[j] = d1 * c + d2 * s;     // transpose of the forward rotation
+              o2[j] = d2 * c - d1 * s;
+            } else {
+              o1[j] = d1;
+              o2[j] = d2;
+            }
+          }
+          uint4 v1, v2;
+          v1.x = pack_bf16(o1[0], o1[1]); v1.y = pack_bf16(o1[2], o1[3]);
+          v1.z = pack_bf16(o1[4], o1[5]); v1.w = pack_bf16(o1[6], o1[7]);
+          v2.x = pack_bf16(o2[0], o2[1]); v2.y = pack_bf16(o2[2], o2[3]);
+          v2.z = pack_bf16(o2[4], o2[5]); v2.w = pack_bf16(o2[6], o2[7]);
+          *reinterpret_cast<uint4*>(orow + g * 8) = v1;
+          *reinterpret_cast<uint4*>(orow + 32 + g * 8) = v2;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// D[n,h,s] = sum_d dO[n,s,h,d] * O[n,s,h,d]     (one warp per row; 8 lanes per head)
+__global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dO,
+                                     long long ldo, long long lddo, float* __restrict__ dsum, int N, int S, int H) {
+  const int lane = threadIdx.x & 31;
+  const long long T = static_cast<long long>(N) * S;
+  const int warps_per_block = blockDim.x >> 5;
+  for (long long t = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); t < T;
+       t += static_cast<long long>(gridDim.x) * warps_per_block) {
+    const int n = static_cast<int>(t / S), s = static_cast<int>(t % S);
+    for (int h0 = 0; h0 < H; h0 += 4) {
+      const int hh = h0 + (lane >> 3);
+      float acc = 0.f;
+      if (hh < H) {
+        const int c = hh * 64 + (lane & 7) * 8;
+        const uint4 a = *reinterpret_cast<const uint4*>(o + t * ldo + c);
+        const uint4 b = *reinterpret_cast<const uint4*>(dO + t * lddo + c);
+        const uint32_t au[4] = {a.x, a.y, a.z, a.w}, bu[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 x = unpack_bf16(au[j]), y = unpack_bf16(bu[j]);
+          acc += x.x * y.x + x.y * y.y;
+        }
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      if (hh < H && (lane & 7) == 0) dsum[(static_cast<size_t>(n) * H + hh) * S + s] = acc;
+    }
+  }
+}
+
+template <bool DKV>
+static int launch_bwd(const CUtensorMap& tmQKV, const CUtensorMap& tmDO, const AttnBwdParams& p, cudaStream_t s) {
+  using L = BwdSmem<DKV>;
+  auto kern = attn_bwd_kernel<DKV>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    if (e != cudaSuccess) {
+      set_error("attn_bwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return -2;
+    }
+    attr_set = true;
+  }
+  dim3 grid(p.n_t, p.H, p.N);
+  kern<<<grid, kBwdThreads, L::kTotal, s>>>(tmQKV, tmDO, p);
+  return check_launch(DKV ? "attn_bwd_kernel<dkv>" : "attn_bwd_kernel<dq>");
+}
+
+}  // namespace ggpt
+
+using namespace ggpt;
+
+extern "C" {
+
+int ggpt_attn_bwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int v_col0, const void* out, long long ldo,
+                  const void* dout, long long lddo, const float* lse, const uint32_t* mask_bits, const uint8_t* tile_cls,
+                  const int* pos, const float* cos_tab, const float* sin_tab, float* dsum_scratch, void* dqkv,
+                  long long ld_dqkv, int N, int S, int H, void* stream) {
+  GGPT_REQUIRE(qkv && out && dout && lse && mask_bits && tile_cls && pos && cos_tab && sin_tab && dsum_scratch && dqkv,
+               "attn_bwd: null pointer");
+  GGPT_REQUIRE(N > 0 && S > 0 && H > 0, "attn_bwd: empty problem");
+  GGPT_REQUIRE(ld_qkv % 8 == 0 && ldo % 8 == 0 && lddo % 8 == 0 && ld_dqkv % 8 == 0, "attn_bwd: ld must be multiples of 8");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long long T = static_cast<long long>(N) * S;
+  long long blocks = (T + 7) / 8;
+  const long long cap = static_cast<long long>(num_sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  attn_bwd_prep_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(out),
+                                                                     static_cast<const __nv_bfloat16*>(dout), ldo, lddo,
+                                                                     dsum_scratch, N, S, H);
+  if (int rc = check_launch("attn_bwd_prep_kernel")) return rc;
+  CUtensorMap tmQKV, tmDO;
+  if (int rc = make_tmap_3d_bf16(&tmQKV, qkv, N, S, ld_qkv, static_cast<uint64_t>(S) * ld_qkv, ld_qkv, 128, 64)) return rc;
+  if (int rc = make_tmap_3d_bf16(&tmDO, dout, N, S, static_cast<uint64_t>(H) * 64, static_cast<uint64_t>(S) * lddo, lddo, 128, 64))
+    return rc;
+  AttnBwdParams p{};
+  p.N = N; p.S = S; p.H = H;
+  p.n_t = (S + 127) / 128;
+  p.mask_words = ggpt_attn_mask_words(S);
+  p.mask_bits = mask_bits; p.tile_cls = tile_cls; p.lse = lse; p.dsum = dsum_scratch;
+  p.dqkv = static_cast<__nv_bfloat16*>(dqkv); p.ld = ld_dqkv;
+  p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
+  p.pos = pos; p.cos_tab = cos_tab; p.sin_tab = sin_tab;
+  p.scale = 0.125f;
+  p.scale_log2 = 0.125f * 1.4426950408889634f;
+  if (int rc = launch_bwd<true>(tmQKV, tmDO, p, s)) return rc;
+  return launch_bwd<false>(tmQKV, tmDO, p, s);
+}
+
+}  // extern "C"

@@ -1,0 +1,417 @@
+"""Host-side orchestration of the GraphGPT hot path: which kernel runs when, over which buffers.
+
+`HotPath` owns three flat device buffers that alias every model parameter — fp32 master weights (the storage of
+the nn.Parameters themselves), their bf16 compute copy (tensor-core operands) and the fp32 gradient buffer (the
+storage of every `param.grad`) — plus the per-step activation stash.  `BackboneFn` / `PretrainHeadFn` are the
+autograd entry points; their backward passes write parameter gradients straight into the flat gradient buffer
+(returning None to autograd for parameter inputs) so that data-parallel all-reduce and the fused AdamW work on
+contiguous segments.
+
+Reference call sites reproduced (kernel-level citations are in include/ggpt_b200.h):
+  LlamaModel.forward HF:375-425, LlamaDecoderLayer.forward HF:313-332 (+ utils_graphgpt.py:137-166 LayerScale /
+  DropPath), prepare_for_stacked_feat_labels modeling_helpers.py:362-393, lm_head + CE modeling_pretrain.py:213-237.
+"""
+import math
+
+import torch
+
+from . import ops
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def _align(n, a=128):
+    return (n + a - 1) // a * a
+
+
+class FlatParams:
+    """Lays every parameter of `module` out in one flat fp32 buffer (each segment 128-element aligned so bf16
+    views stay 16-byte aligned for TMA) and keeps `param.data` / `param.grad` aliased to it."""
+
+    def __init__(self, module, order):
+        self.module = module
+        self.order = order            # list of (name, param) in layout order
+        self.offsets = {}
+        off = 0
+        for name, p in order:
+            self.offsets[name] = (off, tuple(p.shape))
+            off += _align(p.numel())
+        self.numel = off
+        self.flat = None
+        self.flat_bf16 = None
+        self.flat_grad = None
+        self._bf16_key = None
+
+    def _views(self, buf, name):
+        off, shape = self.offsets[name]
+        n = 1
+        for s in shape:
+            n *= s
+        return buf[off:off + n].view(shape)
+
+    def ensure(self):
+        """(Re)build the flat buffers when parameters moved (e.g. after .cuda()) and refresh the bf16 copy when any
+        parameter changed in place (optimizer step, load_state_dict, manual edit)."""
+        p0 = self.order[0][1]
+        dev = p0.device
+        if dev.type != "cuda":
+            raise RuntimeError("graphgpt_b200: the model must live on a CUDA device (sm_100a); there is no CPU path")
+        aliased = self.flat is not None and self.flat.device == dev
+        if aliased:
+            base = self.flat.data_ptr()
+            for name, p in self.order:
+                if p.dtype != F32 or p.data_ptr() != base + 4 * self.offsets[name][0]:
+                    aliased = False
+                    break
+        if not aliased:
+            for name, p in self.order:
+                if p.dtype != F32:
+                    raise RuntimeError(f"graphgpt_b200: parameter {name} has dtype {p.dtype}; fp32 master weights are "
+                                       "required (bf16 compute copies are kept internally)")
+            flat = torch.zeros((self.numel,), device=dev, dtype=F32)
+            for name, p in self.order:
+                v = self._views(flat, name)
+                v.copy_(p.data)
+                p.data = v
+            self.flat = flat
+            self.flat_bf16 = torch.empty((self.numel,), device=dev, dtype=BF16)
+            self.flat_grad = torch.zeros((self.numel,), device=dev, dtype=F32)
+            for name, p in self.order:
+                p.grad = None
+            self._bf16_key = None
+        key = sum(p._version for _, p in self.order)
+        if key != self._bf16_key:
+            ops.cast_f32_bf16(self.flat, self.flat_bf16)
+            self._bf16_key = key
+
+    def mark_bf16_fresh(self):
+        """Called by the fused optimizer, which updates fp32 and bf16 copies together through raw pointers."""
+        self._bf16_key = sum(p._version for _, p in self.order)
+
+    def w(self, name):
+        return self._views(self.flat, name)
+
+    def wb(self, name):
+        return self._views(self.flat_bf16, name)
+
+    def g(self, name):
+        return self._views(self.flat_grad, name)
+
+    def span(self, first, last):
+        """[start, end) element range covering parameters first..last (inclusive) in layout order."""
+        a = self.offsets[first][0]
+        off, shape = self.offsets[last]
+        n = 1
+        for s in shape:
+            n *= s
+        return a, off + _align(n)
+
+    def prepare_grads(self):
+        """Before a backward pass: if no parameter has a gradient yet, zero the flat gradient buffer; then alias
+        every `param.grad` to its flat segment.  Existing aliased gradients are accumulated into."""
+        fresh = all(p.grad is None for _, p in self.order)
+        if fresh:
+            self.flat_grad.zero_()
+        base = self.flat_grad.data_ptr()
+        for name, p in self.order:
+            if not p.requires_grad:
+                continue
+            if p.grad is None:
+                gv = self.g(name)
+                if not fresh:
+                    gv.zero_()
+                p.grad = gv
+            elif p.grad.data_ptr() != base + 4 * self.offsets[name][0]:
+                gv = self.g(name)          # a foreign gradient tensor: fold it into the flat buffer
+                gv.copy_(p.grad)
+                p.grad = gv
+
+
+class HotPath:
+    """Executes the transformer path of one GraphGPT model through the C-ABI kernels."""
+
+    def __init__(self, module, config):
+        self.cfg = config
+        self.module = module
+        d = config.hidden_size
+        self.d = d
+        self.H = config.num_attention_heads
+        self.I = config.intermediate_size
+        self.L = config.num_hidden_layers
+        self.F = max(1, int(config.stacked_feat)) if getattr(config, "stack_method", None) in ("short", "long") else 1
+        self.V = config.vocab_size
+        hd = getattr(config, "head_dim", None) or d // self.H
+        if hd != 64 or self.H * 64 != d:
+            raise NotImplementedError(f"graphgpt_b200 kernels are built for head_dim 64 (got head_dim={hd}, heads={self.H}, "
+                                      f"hidden={d}); GraphGPT always derives heads = hidden/64 (modules_utils.py:37-42)")
+        kv = getattr(config, "num_key_value_heads", self.H)
+        if kv != self.H:
+            raise NotImplementedError("grouped-query attention is not used by GraphGPT (num_key_value_heads == heads)")
+        if getattr(config, "hidden_act", "gelu") != "gelu":
+            raise NotImplementedError(f"hidden_act={config.hidden_act!r}: GraphGPT uses exact GELU (configs/model/base.yaml:21)")
+        if getattr(config, "attention_bias", False) or getattr(config, "mlp_bias", False):
+            raise NotImplementedError("attention_bias / mlp_bias are not used by GraphGPT (configs/model/base.yaml:18-19)")
+        self.layer_scale = getattr(config, "layer_scale_init_value", 0) > 0
+        self.eps = config.rms_norm_eps
+        self.flat = FlatParams(module, module._flat_param_order())
+        self._rope_tab = None
+        self.grad_ready_hook = None   # callable(first_name, last_name) fired as gradient segments complete
+
+    # ------------------------------------------------------------------ helpers
+    def rope_tables(self, max_pos, device):
+        if self._rope_tab is None or self._rope_tab[0].shape[0] < max_pos or self._rope_tab[0].device != device:
+            n = max(max_pos, self.cfg.max_position_embeddings)
+            theta = getattr(self.cfg, "rope_theta", None)
+            if theta is None:
+                theta = self.cfg.rope_parameters["rope_theta"]
+            # HF:117-135 in fp32: inv_freq = theta^(-2i/64); freqs = pos * inv_freq
+            inv_freq = 1.0 / (theta ** (torch.arange(0, 64, 2, dtype=torch.int64).float() / 64))
+            freqs = torch.arange(n, dtype=torch.float32)[:, None] * inv_freq[None, :]
+            self._rope_tab = (freqs.cos().to(device).contiguous(), freqs.sin().to(device).contiguous())
+        return self._rope_tab
+
+    def _rope_inputs(self, position_ids, N, S, device):
+        """Returns (pos int32 [T], cos_tab, sin_tab)."""
+        rope_range = getattr(self.cfg, "rope_range", 0)
+        if position_ids is None:
+            pos = torch.arange(S, device=device, dtype=torch.int32).repeat(N)      # HF:394-397
+            cos, sin = self.rope_tables(S, device)
+            return pos, cos, sin
+        position_ids = position_ids.to(device)
+        if rope_range > 0:
+            # utils_graphgpt.py:574-581: fractional positions -> per-token cos/sin table, indexed by row
+            mx = position_ids.max(dim=-1, keepdim=True)[0] + 1
+            fpos = (position_ids.float() * rope_range / mx.float()).reshape(-1)
+            inv_freq = 1.0 / (self.cfg.rope_theta ** (torch.arange(0, 64, 2, dtype=torch.int64, device=device).float() / 64))
+            freqs = fpos[:, None] * inv_freq[None, :]
+            return torch.arange(N * S, device=device, dtype=torch.int32), freqs.cos().contiguous(), freqs.sin().contiguous()
+        pos = position_ids.reshape(-1).to(torch.int32)
+        max_pos = max(S, self.cfg.max_position_embeddings)
+        cos, sin = self.rope_tables(max_pos, device)
+        return pos.contiguous(), cos, sin
+
+    def _layer_names(self, i):
+        p = f"model.layers.{i}."
+        return p
+
+    # ------------------------------------------------------------------ backbone
+    def backbone_forward(self, ids2d, N, S, attention_mask, position_ids, stash, droppath_scales=None):
+        """ids2d int64 [T,F].  Returns final-norm hidden states bf16 [T,d]; fills `stash` (a dict) when not None."""
+        fp = self.flat
+        cfg = self.cfg
+        dev = ids2d.device
+        d, H = self.d, self.H
+        gate = fp.w("stacked_feat_agg.weight") if "stacked_feat_agg.weight" in fp.offsets else None
+        long_scale = getattr(cfg, "stack_method", None) == "long" and ids2d.shape[1] > 1
+        err = torch.zeros((1,), device=dev, dtype=torch.int32)
+        x = ops.embed_fwd(ids2d, fp.w("model.embed_tokens.weight"), gate, long_scale, err)
+        pos, cos, sin = self._rope_inputs(position_ids, N, S, dev)
+        mask = ops.attn_mask_build(attention_mask, N, S, cfg.causal_attention, dev)
+        keep = stash is not None
+        if keep:
+            stash.update(ids=ids2d, N=N, S=S, mask=mask, pos=pos, cos=cos, sin=sin, layers=[], err=err,
+                         long_scale=long_scale)
+        for i in range(self.L):
+            p = f"model.layers.{i}."
+            rs = None if droppath_scales is None else droppath_scales[i]
+            h1, rstd1 = ops.rmsnorm_fwd(x, fp.w(p + "input_layernorm.weight"), self.eps, want_rstd=keep)
+            qkv = ops.gemm_qkv_rope(h1, self._wqkv(i), pos, cos, sin, 2 * d)
+            a, lse = ops.attn_fwd(qkv, mask, H, want_lse=keep)
+            lam1 = fp.w(p + "lambda_1") if self.layer_scale else None
+            x2 = ops.gemm_resid(a, fp.wb(p + "self_attn.o_proj.weight"), x, colscale=lam1, rowscale=rs)
+            h2, rstd2 = ops.rmsnorm_fwd(x2, fp.w(p + "post_attention_layernorm.weight"), self.eps, want_rstd=keep)
+            gu, act = ops.gemm_geglu(h2, self._wgu(i), want_gu=keep)
+            lam2 = fp.w(p + "lambda_2") if self.layer_scale else None
+            x3 = ops.gemm_resid(act, fp.wb(p + "mlp.down_proj.weight"), x2, colscale=lam2, rowscale=rs)
+            if keep:
+                stash["layers"].append(dict(x=x, rstd1=rstd1, h1=h1, qkv=qkv, a=a, lse=lse, x2=x2, rstd2=rstd2, h2=h2,
+                                            gu=gu, act=act, x3=x3 if self.layer_scale else None, rs=rs))
+            x = x3
+        hf, rstdf = ops.rmsnorm_fwd(x, fp.w("model.norm.weight"), self.eps, want_rstd=keep)
+        if keep:
+            stash.update(x_final=x, rstdf=rstdf)
+        return hf
+
+    def _wqkv(self, i):
+        """bf16 [3d, d] view: q_proj, k_proj, v_proj weights are adjacent in the flat layout."""
+        fp = self.flat
+        off, _ = fp.offsets[f"model.layers.{i}.self_attn.q_proj.weight"]
+        return fp.flat_bf16[off:off + 3 * self.d * self.d].view(3 * self.d, self.d)
+
+    def _wgu(self, i):
+        fp = self.flat
+        off, _ = fp.offsets[f"model.layers.{i}.mlp.gate_proj.weight"]
+        return fp.flat_bf16[off:off + 2 * self.I * self.d].view(2 * self.I, self.d)
+
+    def _gqkv(self, i):
+        fp = self.flat
+        off, _ = fp.offsets[f"model.layers.{i}.self_attn.q_proj.weight"]
+        return fp.flat_grad[off:off + 3 * self.d * self.d].view(3 * self.d, self.d)
+
+    def _ggu(self, i):
+        fp = self.flat
+        off, _ = fp.offsets[f"model.layers.{i}.mlp.gate_proj.weight"]
+        return fp.flat_grad[off:off + 2 * self.I * self.d].view(2 * self.I, self.d)
+
+    def backbone_backward(self, dhf, stash):
+        """dhf: bf16 [T,d] gradient w.r.t. the final-norm hidden states.  Accumulates all parameter gradients."""
+        fp = self.flat
+        d, H = self.d, self.H
+        wgrad = dict(a_mn_major=True, b_mn_major=True, out_dtype=F32, accumulate=True)
+        dx, dxb = ops.rmsnorm_bwd(dhf, stash["x_final"], stash["rstdf"], fp.w("model.norm.weight"), None,
+                                  fp.g("model.norm.weight"))
+        if self.grad_ready_hook:
+            self.grad_ready_hook("model.norm.weight", self.flat.order[-1][0])
+        for i in reversed(range(self.L)):
+            p = f"model.layers.{i}."
+            st = stash["layers"][i]
+            # ---- MLP block:  x3 = x2 + rs * lam2 * (act @ Wd^T)
+            dyb = dxb
+            if self.layer_scale or st["rs"] is not None:
+                dyb = self._scaled_copy(dx, fp.w(p + "lambda_2") if self.layer_scale else None, st["rs"])
+                if self.layer_scale:
+                    self._lambda_grad(fp.g(p + "lambda_2"), dx, st["x3"], st["x2"], fp.w(p + "lambda_2"))
+            dact = ops.gemm(dyb, fp.wb(p + "mlp.down_proj.weight"), b_mn_major=True)
+            ops.gemm(dyb, st["act"], out=fp.g(p + "mlp.down_proj.weight"), **wgrad)
+            dgu = ops.geglu_bwd(dact, st["gu"])
+            ops.gemm(dgu, st["h2"], out=self._ggu(i), **wgrad)
+            dh2 = ops.gemm(dgu, self._wgu(i), b_mn_major=True)
+            dx2, dx2b = ops.rmsnorm_bwd(dh2, st["x2"], st["rstd2"], fp.w(p + "post_attention_layernorm.weight"), dx,
+                                        fp.g(p + "post_attention_layernorm.weight"))
+            # ---- attention block:  x2 = x + rs * lam1 * (a @ Wo^T)
+            dyb = dx2b
+            if self.layer_scale or st["rs"] is not None:
+                dyb = self._scaled_copy(dx2, fp.w(p + "lambda_1") if self.layer_scale else None, st["rs"])
+                if self.layer_scale:
+                    self._lambda_grad(fp.g(p + "lambda_1"), dx2, st["x2"], st["x"], fp.w(p + "lambda_1"))
+            da = ops.gemm(dyb, fp.wb(p + "self_attn.o_proj.weight"), b_mn_major=True)
+            ops.gemm(dyb, st["a"], out=fp.g(p + "self_attn.o_proj.weight"), **wgrad)
+            dqkv = ops.attn_bwd(da, st["qkv"], st["a"], st["lse"], stash["mask"], H, stash["pos"], stash["cos"],
+                                stash["sin"])
+            ops.gemm(dqkv, st["h1"], out=self._gqkv(i), **wgrad)
+            dh1 = ops.gemm(dqkv, self._wqkv(i), b_mn_major=True)
+            dx, dxb = ops.rmsnorm_bwd(dh1, st["x"], st["rstd1"], fp.w(p + "input_layernorm.weight"), dx2,
+                                      fp.g(p + "input_layernorm.weight"), want_bf16=(i > 0))
+            stash["layers"][i] = None   # free activations as we go
+            if self.grad_ready_hook:
+                names = [n for n, _ in self.flat.order if n.startswith(p)]
+                self.grad_ready_hook(names[0], names[-1])
+        gate = fp.w("stacked_feat_agg.weight") if "stacked_feat_agg.weight" in fp.offsets else None
+        emb_p = dict(self.flat.order)["model.embed_tokens.weight"]
+        if emb_p.requires_grad:
+            ops.embed_bwd(stash["ids"], dx, fp.w("model.embed_tokens.weight") if gate is not None else None, gate,
+                          fp.g("model.embed_tokens.weight"),
+                          fp.g("stacked_feat_agg.weight") if gate is not None else None,
+                          padding_idx=self.cfg.pad_token_id if self.cfg.pad_token_id is not None else -1,
+                          long_scale=stash["long_scale"])
+        if self.grad_ready_hook:
+            self.grad_ready_hook(self.flat.order[0][0],
+                                 "model.embed_tokens.weight" if gate is None else "stacked_feat_agg.weight")
+
+    # LayerScale / DropPath are fine-tuning-only options (ppa: lsi=1, path_dropout=0.2); their few elementwise
+    # gradient terms are formed with torch ops on device — not on the pre-training hot path.
+    @staticmethod
+    def _scaled_copy(dx, lam, rs):
+        y = dx
+        if lam is not None:
+            y = y * lam[None, :]
+        if rs is not None:
+            y = y * rs[:, None]
+        return y.to(BF16)
+
+    @staticmethod
+    def _lambda_grad(glam, dx, x_out, x_in, lam):
+        # x_out = x_in + rs*lam*y  =>  dlam = sum_t dx * rs*y = sum_t dx * (x_out - x_in) / lam
+        glam.add_((dx * (x_out - x_in)).sum(0) / lam)
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd entry points
+# ------------------------------------------------------------------------------------------------
+class BackboneFn(torch.autograd.Function):
+    """ids -> final-norm hidden states (bf16 [T,d]).  Parameter gradients are written into the flat gradient
+    buffer by backward(); autograd only carries the activation gradient."""
+
+    @staticmethod
+    def forward(ctx, hot, ids2d, N, S, attention_mask, position_ids, droppath_scales, *params):
+        stash = {}
+        hf = hot.backbone_forward(ids2d, N, S, attention_mask, position_ids, stash, droppath_scales)
+        ctx.hot, ctx.stash = hot, stash
+        return hf
+
+    @staticmethod
+    def backward(ctx, dhf):
+        hot, stash = ctx.hot, ctx.stash
+        if stash is None:
+            raise RuntimeError("graphgpt_b200: backward called twice on the same forward (activations were freed)")
+        hot.flat.prepare_grads()
+        if dhf.dtype != BF16:
+            dhf = dhf.to(BF16)
+        hot.backbone_backward(dhf.contiguous(), stash)
+        ctx.stash = None
+        return (None,) * 7 + (None,) * (len(ctx.needs_input_grad) - 7)
+
+
+class PretrainHeadFn(torch.autograd.Function):
+    """hidden (bf16 [T,d]) + labels -> (loss, logits[L,V]).  ref: modeling_pretrain.py:213-237."""
+
+    @staticmethod
+    def forward(ctx, hot, hf, labels2d, N, S, ent_wgt_fn, loss_mode, *params):
+        fp = hot.flat
+        d, F_, V = hot.d, labels2d.shape[1], hot.V
+        hi = ops.head_compact(labels2d)
+        M, L = hi.sync_counts()
+        has_proj = "n_token_proj.weight" in fp.offsets
+        if M == 0:
+            loss = torch.full((), float("nan"), device=hf.device, dtype=F32)
+            ctx.empty = True
+            ctx.mark_non_differentiable()
+            return loss, torch.empty((0, V), device=hf.device, dtype=F32)
+        hsel = ops.gather_rows(hf, hi.sel_rows, M)
+        if has_proj:
+            proj = ops.gemm(hsel, fp.wb("n_token_proj.weight"))                      # [M, F*d]
+            hl = ops.gather_rows(proj.view(M * F_, d), hi.ent_src, L)
+        else:
+            hl = hsel                                                               # F == 1: entries == rows
+        logits = ops.gemm(hl, fp.wb("lm_head.weight"), out_dtype=F32)              # [L, V] (ld padded to 8)
+        wgt = ent_wgt_fn(hi, L) if ent_wgt_fn is not None else None
+        row_lse, _, sums = ops.ce_fwd(logits, hi.ent_label, V, wgt, err_flag=None)
+        if loss_mode == "mean":
+            ls = ops.ce_finalize(sums, hi.counts.data_ptr() + 4, 0)
+        else:                                                                       # dLM: sum / (N*S*F)
+            ls = ops.ce_finalize(sums, 0, 2, float(N * S * hot.cfg.next_n_token))
+        ctx.hot, ctx.hi, ctx.M, ctx.L, ctx.T = hot, hi, M, L, hf.shape[0]
+        ctx.saved = (hsel, hl, logits, row_lse, wgt, ls)
+        ctx.has_proj, ctx.empty = has_proj, False
+        ctx.mark_non_differentiable(logits)
+        return ls[0], logits
+
+    @staticmethod
+    def backward(ctx, gloss, _glogits):
+        n_in = len(ctx.needs_input_grad)
+        if ctx.empty:
+            return (None,) * n_in
+        hot, hi, M, L = ctx.hot, ctx.hi, ctx.M, ctx.L
+        fp = hot.flat
+        d, V = hot.d, hot.V
+        hsel, hl, logits, row_lse, wgt, ls = ctx.saved
+        ctx.saved = None
+        fp.prepare_grads()
+        wgrad = dict(a_mn_major=True, b_mn_major=True, out_dtype=F32, accumulate=True)
+        gout = gloss.reshape(1).to(F32).contiguous()
+        dlog = ops.ce_bwd(logits, hi.ent_label, V, row_lse, ls.data_ptr() + 4, gout, wgt)   # bf16 [L, ld]
+        dlv = dlog[:, :V]
+        ops.gemm(dlv, hl, out=fp.g("lm_head.weight"), **wgrad)
+        dhl = ops.gemm(dlv, fp.wb("lm_head.weight"), b_mn_major=True)                        # [L, d]
+        if ctx.has_proj:
+            F_ = hot.cfg.next_n_token
+            dproj = torch.zeros((M * F_, d), device=dhl.device, dtype=BF16)
+            ops.scatter_rows(dhl, hi.ent_src, dproj, L)
+            dproj = dproj.view(M, F_ * d)
+            ops.gemm(dproj, hsel, out=fp.g("n_token_proj.weight"), **wgrad)
+            dhsel = ops.gemm(dproj, fp.wb("n_token_proj.weight"), b_mn_major=True)           # [M, d]
+        else:
+            dhsel = dhl
+        dhf = torch.zeros((ctx.T, d), device=dhl.device, dtype=BF16)
+        ops.scatter_rows(dhsel, hi.sel_rows, dhf, M)
+        return (None, dhf) + (None,) * (n_in - 2)

@@ -149,6 +149,22 @@ def attn_fwd(qkv, mask: AttnMask, H, *, want_lse=True):
     return out, lse
 
 
+def attn_bwd(dout, qkv, out, lse, mask: AttnMask, H, pos, cos_tab, sin_tab):
+    """Returns dqkv bf16 [N*S, 3*H*64] (gradient of the fused projection output, RoPE already undone)."""
+    _check(dout, BF16, "attn_bwd dout", 2)
+    _check(qkv, BF16, "attn_bwd qkv", 2)
+    _check(out, BF16, "attn_bwd out", 2)
+    N, S = mask.N, mask.S
+    d = H * 64
+    dqkv = torch.empty_like(qkv)
+    dsum = torch.empty((N, H, S), device=qkv.device, dtype=F32)
+    lib.ggpt_attn_bwd(qkv.data_ptr(), qkv.stride(0), 0, d, 2 * d, out.data_ptr(), out.stride(0), dout.data_ptr(),
+                      dout.stride(0), lse.data_ptr(), mask.bits.data_ptr(), mask.cls.data_ptr(), pos.data_ptr(),
+                      cos_tab.data_ptr(), sin_tab.data_ptr(), dsum.data_ptr(), dqkv.data_ptr(), dqkv.stride(0), N, S, H,
+                      _stream())
+    return dqkv
+
+
 # ------------------------------------------------------------------------------------------------
 # HBM-bound kernels
 # ------------------------------------------------------------------------------------------------

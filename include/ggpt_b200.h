@@ -83,6 +83,15 @@ int ggpt_attn_mask_build(const long long* attention_mask, int mask_dims, int N, 
 int ggpt_attn_fwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int v_col0, const uint32_t* mask_bits,
                   const uint8_t* tile_cls, void* out, long long ldo, float* lse, int N, int S, int H, void* stream);
 
+/* dqkv[N*S, ld_dqkv] (bf16) = gradient of the fused q|k|v projection output given dout = dL/d(attention output).
+ * Recomputes P from lse; two deterministic tcgen05 passes (dK,dV then dQ); dQ/dK are un-rotated (inverse RoPE)
+ * with the same pos / cos / sin tables as ggpt_gemm_bf16_qkv_rope.  dsum_scratch: fp32 [N,H,S].
+ * ref: autograd of HF:199-221 and HF:146-168. */
+int ggpt_attn_bwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int v_col0, const void* out, long long ldo,
+                  const void* dout, long long lddo, const float* lse, const uint32_t* mask_bits, const uint8_t* tile_cls,
+                  const int* pos, const float* cos_tab, const float* sin_tab, float* dsum_scratch, void* dqkv,
+                  long long ld_dqkv, int N, int S, int H, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * HBM-bound kernels
  * ------------------------------------------------------------------------------------------- */

@@ -224,3 +224,86 @@ def test_adamw_and_sumsq():
                   max_norm=1.0)
         assert (p - pr.detach()).abs().max().item() <= 2e-6
     assert (pb.float() - p).abs().max().item() <= 4e-3 * p.abs().max().item()
+
+
+BWD_CASES = [
+    (2, 128, 1, "none", False, False),
+    (2, 256, 2, "none", False, True),
+    (3, 40, 2, "pad", False, True),
+    (2, 200, 3, "pad", True, True),
+    (2, 384, 2, "packed", False, True),
+    (1, 1024, 4, "none", False, False),
+    (2, 512, 2, "random", False, True),
+]
+
+
+@pytest.mark.parametrize("N,S,H,kind,causal,rope", BWD_CASES)
+def test_attn_bwd(N, S, H, kind, causal, rope):
+    """dq/dk/dv against torch autograd through (RoPE ->) masked softmax attention in fp32."""
+    from graphgpt_b200 import ops
+    g = torch.Generator().manual_seed(S * 3 + H)
+    d = H * 64
+    dev = torch.device("cuda")
+    pre = (torch.randn((N * S, 3 * d), generator=g) * 1.2).to(torch.bfloat16).float().to(dev).requires_grad_(True)
+    if kind == "none":
+        am = None
+    elif kind == "pad":
+        lens = torch.randint(S // 3, S + 1, (N,), generator=g)
+        am = (torch.arange(S)[None, :] < lens[:, None]).long().to(dev)
+    elif kind == "packed":
+        am = torch.zeros((N, S, S), dtype=torch.long)
+        for n in range(N):
+            o = 0
+            while o < S:
+                L = min(int(torch.randint(8, 40, (1,), generator=g)), S - o)
+                am[n, o:o + L, o:o + L] = 1
+                o += L
+        am = am.to(dev)
+    else:
+        am = (torch.rand((N, S, S), generator=g) < 0.3).long()
+        am[:, torch.arange(S), torch.arange(S)] = 1
+        am = am.to(dev)
+    max_pos = 2048
+    inv_freq = 1.0 / (10000.0 ** (torch.arange(0, 64, 2, dtype=torch.int64).float() / 64))
+    freqs = torch.arange(max_pos).float()[:, None] * inv_freq[None, :]
+    cos_tab, sin_tab = freqs.cos().to(dev), freqs.sin().to(dev)
+    if rope:
+        pos = torch.randint(0, max_pos, (N * S,), generator=g, dtype=torch.int32).to(dev)
+    else:
+        pos = torch.zeros((N * S,), dtype=torch.int32, device=dev)
+    # reference: rope(q,k) then attention, all fp32, autograd
+    x = pre.view(N * S, 3, H, 64)
+    cos = torch.cat([cos_tab, cos_tab], -1)[pos.long()][:, None, :]
+    sin = torch.cat([sin_tab, sin_tab], -1)[pos.long()][:, None, :]
+
+    def rot(t):
+        return t * cos + torch.cat([-t[..., 32:], t[..., :32]], -1) * sin
+
+    q, k, v = rot(x[:, 0]), rot(x[:, 1]), x[:, 2]
+    qkv_rot = torch.stack([q, k, v], 1).reshape(N * S, 3 * d)
+    qkv_b = qkv_rot.detach().to(torch.bfloat16)
+    qkv_ref = qkv_b.float().requires_grad_(True)       # reference differentiates at the bf16-rounded rotated point
+    o_ref, lse_ref, keep = _ref_attention(qkv_ref, am, causal, N, S, H)
+    valid = keep.any(-1)[:, 0].reshape(N * S)
+    dout = (torch.randn((N * S, d), generator=g)).to(torch.bfloat16).to(dev)
+    dout = dout * valid[:, None]                       # padded query rows carry no gradient in the model
+    o_ref.backward(dout.float())
+    # chain through the rotation: d pre = rot^T(d rotated)
+    gr = qkv_ref.grad.view(N * S, 3, H, 64)
+
+    def unrot(t):
+        return t * cos + torch.cat([t[..., 32:], -t[..., :32]], -1) * sin
+
+    ref = torch.stack([unrot(gr[:, 0]), unrot(gr[:, 1]), gr[:, 2]], 1).reshape(N * S, 3 * d)
+
+    mask = ops.attn_mask_build(am, N, S, causal, dev)
+    out, lse = ops.attn_fwd(qkv_b, mask, H)
+    dqkv = ops.attn_bwd(dout, qkv_b, out, lse, mask, H, pos, cos_tab, sin_tab)
+    torch.cuda.synchronize()
+    for name, sl in (("dq", slice(0, d)), ("dk", slice(d, 2 * d)), ("dv", slice(2 * d, 3 * d))):
+        a, b = dqkv[:, sl].float(), ref[:, sl]
+        err = (a - b).abs().max().item()
+        scale = b.abs().max().item()
+        rel_f = ((a - b).norm() / (b.norm() + 1e-20)).item()
+        # P and dS are rounded to bf16 before the gradient MMAs and outputs are bf16
+        assert err <= 2e-2 * scale and rel_f <= 1e-2, f"{name}: max err {err} (scale {scale}), relF {rel_f}"
