@@ -9,6 +9,12 @@
 // memory in the 128-byte-swizzled layout and consumed either as a K-major A operand (dS K) or, through the
 // MN-major descriptor, as the transposed A operand (P^T dO, dS^T Q) — no explicit transposes.  The epilogue
 // un-rotates dQ / dK (inverse RoPE) so the result is the gradient of the fused q|k|v projection output.
+//
+// Row-sum consistency: D is formed from the bf16 forward output, so sum_k dS[q,k] = -eps_q is not exactly zero and
+// dQ would carry the common-mode error -eps_q * (sum_k P[q,k] K[k]) — visible when keys share a large common
+// component (rows of identical <mask> tokens).  The DQ pass therefore also accumulates PK = P K (one extra
+// 128x64x128 MMA per tile) and eps_q = sum_k P (dP - D) in registers, and emits dQ = dS K - eps_q/8 * PK, which is
+// the gradient for the exact D = sum_k P dP.  dK and dV have no such common-mode term (eps varies per query row).
 #include "common.cuh"
 #include "../../include/ggpt_b200.h"
 
@@ -34,13 +40,13 @@ struct AttnBwdParams {
   float scale_log2;           // scale * log2(e)
 };
 
-// smem: fixed pair 2x16K | streamed pair 2 stages x 2 x 16K | P 32K (DKV only) | dS 32K | barriers
+// smem: fixed pair 2x16K | streamed pair 2 stages x 2 x 16K | P 32K | dS 32K | barriers
 template <bool DKV>
 struct BwdSmem {
   static constexpr int kFixed = 0;
   static constexpr int kStream = 32768;
   static constexpr int kP = kStream + 65536;
-  static constexpr int kDS = kP + (DKV ? 32768 : 0);
+  static constexpr int kDS = kP + 32768;
   static constexpr int kBars = kDS + 32768;
   static constexpr int kTotal = kBars + 256;
 };
@@ -102,7 +108,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const uint32_t tmem_S = tmem_base;           // [0,128)
   const uint32_t tmem_dP = tmem_base + 128;    // [128,256)
   const uint32_t tmem_A0 = tmem_base + 256;    // DKV: dV   DQ: dQ      (64 columns)
-  const uint32_t tmem_A1 = tmem_base + 320;    // DKV: dK
+  const uint32_t tmem_A1 = tmem_base + 320;    // DKV: dK   DQ: PK = P K (row-sum correction)
 
   int n_active = 0;
   for (int t = 0; t < p.n_t; ++t) n_active += (cls_of(t) != 0);
@@ -175,10 +181,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             tc_mma_bf16(tmem_A1, umma_desc_sw128(aDS + kk * 2048, 16384, 1024),
                         umma_desc_sw128(a0 + kk * 2048, 8192, 1024), idesc_t, (it | kk) != 0);
         } else {
-          // dQ += dS K_j      (A = dS K-major: M = query rows, K = keys; B = K_j MN-major)
+          // dQ += dS K_j ; PK += P K_j      (A = dS / P K-major: M = query rows, K = keys; B = K_j MN-major)
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
             tc_mma_bf16(tmem_A0, umma_desc_sw128(aDS + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                        umma_desc_sw128(a0 + kk * 2048, 8192, 1024), idesc_q, (it | kk) != 0);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            tc_mma_bf16(tmem_A1, umma_desc_sw128(aP + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
                         umma_desc_sw128(a0 + kk * 2048, 8192, 1024), idesc_q, (it | kk) != 0);
         }
         tc_commit(pds_empty);
@@ -198,6 +208,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+    float eps_run = 0.f;   // DQ: sum_k P (dP - D) of this thread's query row
     int it = 0;
     for (int t = 0; t < p.n_t; ++t) {
       const int cls = cls_of(t);
@@ -239,10 +250,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           for (int j = 0; j < 8; ++j) {
             const float e = exp2f(__uint_as_float(s[g * 8 + j]) * p.scale_log2 - lse2);
             pv[j] = ((w >> (g * 8 + j)) & 1u) ? e : 0.f;
-            dv[j] = pv[j] * (__uint_as_float(dp[g * 8 + j]) - dsum) * p.scale;
+            const float t0 = pv[j] * (__uint_as_float(dp[g * 8 + j]) - dsum);
+            if (!DKV) eps_run += t0;
+            dv[j] = t0 * p.scale;
           }
           const int chunk = ((c & 1) * 4 + g) ^ (r & 7);
-          if (DKV) {
+          {
             uint4 o;
             o.x = pack_bf16(pv[0], pv[1]); o.y = pack_bf16(pv[2], pv[3]);
             o.z = pack_bf16(pv[4], pv[5]); o.w = pack_bf16(pv[6], pv[7]);
@@ -283,6 +296,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         tmem_ld32((a == 0 ? tmem_A0 : tmem_A1) + lane_addr, x1);
         tmem_ld32((a == 0 ? tmem_A0 : tmem_A1) + lane_addr + 32, x2);
         tmem_ld_wait();
+        if (!DKV) {   // dQ = dS K - eps/8 * (P K)
+          const float ce = eps_run * p.scale;
+          uint32_t y[32];
+          tmem_ld32(tmem_A1 + lane_addr, y);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x1[j] = __float_as_uint(__uint_as_float(x1[j]) - ce * __uint_as_float(y[j]));
+          tmem_ld32(tmem_A1 + lane_addr + 32, y);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x2[j] = __float_as_uint(__uint_as_float(x2[j]) - ce * __uint_as_float(y[j]));
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) x1[j] = x2[j] = 0u;

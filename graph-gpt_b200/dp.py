@@ -1,0 +1,174 @@
+"""Data-parallel training engine: NCCL gradient all-reduce over NVLink + fused AdamW on the flat buffers.
+
+Replaces, for the GraphGPT hot path, the reference's two wrappers:
+  * DeepSpeed ZeRO-2 engine  (`deepspeed.initialize`, pretrain_mode.py:271-287; ds_config2_pt_bf16.json:24-27:
+    grad reduce-scatter + sharded Adam + param all-gather), and
+  * torch DDP + AdamW + clip (opt_utils.py:7-37, training_utils.py:66-86).
+The model is 122-417 M parameters, i.e. <= 7 GB of fp32 master + Adam state per GPU, so nothing needs sharding on
+180 GB parts: every rank keeps the full state, gradients are summed with ONE all-reduce per contiguous segment
+of the flat gradient buffer (head | layer L-1 | ... | layer 0 | embedding), launched from inside backward as soon
+as the segment is final so NCCL overlaps the remaining backward kernels, and the 1/world factor is folded into
+the AdamW kernel.  The object mimics the DeepSpeed engine surface the reference's loop uses:
+`engine(**batch)`, `engine.backward(loss)`, `engine.step()`, `engine.module`, `engine.global_steps`.
+"""
+import math
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+class GradReducer:
+    """Launches async all-reduces over [start,end) spans of one flat tensor and waits for them later.
+    Device-agnostic (NCCL on GPUs, gloo in the CPU tests)."""
+
+    def __init__(self, flat_grad, group=None):
+        self.flat = flat_grad
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.pending = []
+        self.spans = []
+
+    def reduce_span(self, start, end):
+        self.spans.append((start, end))
+        if self.world == 1:
+            return
+        self.pending.append(dist.all_reduce(self.flat[start:end], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def wait(self):
+        for w in self.pending:
+            w.wait()
+        self.pending = []
+        spans, self.spans = self.spans, []
+        return spans
+
+
+def warmup_decay_lr(step, *, max_lr, min_lr=0.0, warmup_steps=0, total_steps=1):
+    """DeepSpeed WarmupDecayLR (ds_config2_pt_bf16.json:17-25): linear warm-up then linear decay to min_lr."""
+    if warmup_steps > 0 and step < warmup_steps:
+        return min_lr + (max_lr - min_lr) * step / warmup_steps
+    frac = max(0.0, (total_steps - step) / max(1, total_steps - warmup_steps))
+    return min_lr + (max_lr - min_lr) * frac
+
+
+class GraphGPTEngine:
+    def __init__(self, model, *, lr=3e-4, betas=(0.9, 0.95), eps=1e-6, weight_decay=0.1, max_grad_norm=1.0,
+                 lr_schedule=None, process_group=None, overlap_comm=True):
+        self.module = model
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.max_grad_norm = max_grad_norm
+        self.lr_schedule = lr_schedule
+        self.global_steps = 0
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.overlap_comm = overlap_comm
+        hot = model.hot                       # builds / validates the flat buffers (raises without CUDA)
+        self.flat = hot.flat
+        n = self.flat.numel
+        dev = self.flat.flat.device
+        self.exp_avg = torch.zeros((n,), device=dev, dtype=torch.float32)
+        self.exp_avg_sq = torch.zeros((n,), device=dev, dtype=torch.float32)
+        self.gnorm_sq = torch.zeros((1,), device=dev, dtype=torch.float64)
+        flat_ids = {id(p) for _, p in self.flat.order}
+        self.extra = [p for p in model.parameters() if id(p) not in flat_ids and p.requires_grad]
+        self.extra_opt = (torch.optim.AdamW(self.extra, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+                          if self.extra else None)
+        self.reducer = GradReducer(self.flat.flat_grad, process_group)
+        if self.world > 1:
+            self._broadcast_params()
+
+    def _broadcast_params(self):
+        dist.broadcast(self.flat.flat, src=0, group=self.group)
+        for p in self.extra:
+            dist.broadcast(p.data, src=0, group=self.group)
+        self.flat._bf16_key = None            # force a re-cast of the bf16 copy
+        self.flat.ensure()
+
+    # ---- DeepSpeed-engine-like surface -----------------------------------------------------------
+    def __call__(self, *a, **k):
+        return self.module(*a, **k)
+
+    def train(self, mode=True):
+        self.module.train(mode)
+        return self
+
+    def eval(self):
+        self.module.eval()
+        return self
+
+    def parameters(self):
+        return self.module.parameters()
+
+    def backward(self, loss):
+        hot = self.module._hot
+        self.reducer = GradReducer(self.flat.flat_grad, self.group)
+        if self.world > 1 and self.overlap_comm:
+            hot.grad_ready_hook = lambda first, last: self.reducer.reduce_span(*self.flat.span(first, last))
+        else:
+            hot.grad_ready_hook = None
+        try:
+            loss.backward()
+        finally:
+            hot.grad_ready_hook = None
+        if self.world > 1 and not self.overlap_comm:
+            self.reducer.reduce_span(0, self.flat.numel)
+
+    def step(self):
+        self.global_steps += 1
+        fp = self.flat
+        self.reducer.wait()
+        inv_world = 1.0 / self.world
+        if self.world > 1:
+            for p in self.extra:
+                if p.grad is not None:
+                    dist.all_reduce(p.grad, group=self.group)
+                    p.grad.mul_(inv_world)
+        lr = self.lr_schedule(self.global_steps) if self.lr_schedule is not None else self.lr
+        gn = None
+        if self.max_grad_norm and self.max_grad_norm > 0:
+            self.gnorm_sq.zero_()
+            ops.sumsq(fp.flat_grad, self.gnorm_sq)
+            for p in self.extra:
+                if p.grad is not None:       # extra grads are already averaged; flat ones are scaled in-kernel
+                    self.gnorm_sq += (p.grad.double().pow(2).sum() * (self.world ** 2))
+            gn = self.gnorm_sq
+        ops.adamw(fp.flat, fp.flat_bf16, fp.flat_grad, self.exp_avg, self.exp_avg_sq, lr=lr, betas=self.betas,
+                  eps=self.eps, weight_decay=self.weight_decay, step=self.global_steps, gnorm_sq=gn,
+                  max_norm=self.max_grad_norm or 0.0, grad_scale=inv_world)
+        fp.mark_bf16_fresh()
+        if self.extra_opt is not None:
+            if gn is not None:
+                coef = torch.clamp(self.max_grad_norm / (gn.sqrt().float() * inv_world + 1e-6), max=1.0)
+                for p in self.extra:
+                    if p.grad is not None:
+                        p.grad.mul_(coef)
+            for grp in self.extra_opt.param_groups:
+                grp["lr"] = lr
+            self.extra_opt.step()
+        self.zero_grad()
+
+    def zero_grad(self):
+        for _, p in self.flat.order:
+            p.grad = None                    # the flat buffer is zeroed lazily by the next backward
+        for p in self.extra:
+            p.grad = None
+
+    def grad_norm(self):
+        """Global gradient norm of the last step (after averaging), as a python float (syncs)."""
+        return math.sqrt(float(self.gnorm_sq.item())) / self.world
+
+    # ---- checkpoint surface (DDP-style files; misc_utils.py:105-121) -------------------------------
+    def state_dict(self):
+        return {"model": self.module.state_dict(), "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq,
+                "global_steps": self.global_steps,
+                "extra_opt": self.extra_opt.state_dict() if self.extra_opt is not None else None}
+
+    def load_state_dict(self, sd):
+        self.module.load_state_dict(sd["model"])
+        self.flat.ensure()
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.global_steps = int(sd["global_steps"])
+        if self.extra_opt is not None and sd.get("extra_opt") is not None:
+            self.extra_opt.load_state_dict(sd["extra_opt"])

@@ -49,12 +49,37 @@ def parse_header(path=HEADER_PATH):
 
 # functions whose int return is a value, not a status code
 _VALUE_FUNCS = {"ggpt_abi_version", "ggpt_attn_mask_words"}
+# kernels launched per entry point (default 1; 0 = host-only helper) — feeds bench.py's `gpu_launches`
+_LAUNCHES = {"ggpt_last_error": 0, "ggpt_abi_version": 0, "ggpt_device_info": 0, "ggpt_attn_mask_words": 0,
+             "ggpt_head_scratch_ints": 0, "ggpt_attn_mask_build": 2, "ggpt_head_compact": 3, "ggpt_attn_bwd": 3}
+_GEMM_FUNCS = {"ggpt_gemm_bf16", "ggpt_gemm_bf16_resid", "ggpt_gemm_bf16_geglu", "ggpt_gemm_bf16_qkv_rope"}
+
+
+class KernelTimer:
+    """CUDA-event timing of C-ABI calls on the launching stream (used by bench.py inside the timed region).
+    Collects, per entry point (GEMMs are keyed by operand majors too): calls, device ms, FLOPs."""
+
+    def __init__(self):
+        self.events = []   # (key, start, end, flops)
+
+    def summary(self):
+        import torch
+        torch.cuda.synchronize()
+        out = {}
+        for key, a, b, fl in self.events:
+            d = out.setdefault(key, {"calls": 0, "ms": 0.0, "flops": 0.0})
+            d["calls"] += 1
+            d["ms"] += a.elapsed_time(b)
+            d["flops"] += fl
+        return out
 
 
 class _Lib:
     def __init__(self):
         self._dll = None
         self._protos = None
+        self.launch_count = 0
+        self.timer = None
 
     def load(self):
         if self._dll is not None:
@@ -78,7 +103,23 @@ class _Lib:
 
     def call(self, name, *args):
         dll = self.load()
-        rc = getattr(dll, name)(*args)
+        self.launch_count += _LAUNCHES.get(name, 1)
+        timer = self.timer
+        if timer is not None and _LAUNCHES.get(name, 1) > 0:
+            import torch
+            key, flops = name, 0.0
+            if name in _GEMM_FUNCS:
+                M, N, K = args[-4], args[-3], args[-2]
+                flops = 2.0 * M * N * K
+                if name == "ggpt_gemm_bf16":
+                    key = f"{name}[a_mn={args[2]},b_mn={args[5]}]"
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            rc = getattr(dll, name)(*args)
+            b.record()
+            timer.events.append((key, a, b, flops))
+        else:
+            rc = getattr(dll, name)(*args)
         if self._protos[name][0] is ctypes.c_int and name not in _VALUE_FUNCS:
             if rc != 0:
                 raise RuntimeError(f"{name} failed (rc={rc}): {self.last_error()}")

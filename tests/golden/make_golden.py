@@ -201,6 +201,33 @@ def main():
                     g = named[k].grad.detach()
                     rec["grad_norms"][k] = float(g.double().norm())     # pins the whole tensor
                     rec["grads"][k] = g[:24].clone() if g.dim() == 2 else g.clone()   # first 24 rows of matrices
+        # How far is the REFERENCE ITSELF from its fp32 result when run in bf16 (the precision the reference trains
+        # in under DeepSpeed bf16)?  Only the error numbers are stored; they bound what bf16 kernels can achieve.
+        import copy
+        mb = copy.deepcopy(model).to(torch.bfloat16)
+        for p_ in mb.parameters():
+            p_.grad = None
+        inputs_b = {k: (v.to(torch.bfloat16) if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in inputs.items()}
+        ob = mb(**inputs_b)
+        bf = {}
+        if kind == "pretrain":
+            lb, lgb = ob.head1_loss, ob.head1_logits.float()
+            bf["logits_relF"] = float((lgb - out.head1_logits.detach()).norm() / out.head1_logits.detach().norm())
+        else:
+            lb = ob.task_loss
+            bf["task_hidden_relF"] = float((ob.task_hidden_states.float() - out.task_hidden_states.detach()).norm()
+                                           / out.task_hidden_states.detach().norm())
+        if loss is not None:
+            bf["loss_rel"] = abs(float(lb) - float(loss)) / abs(float(loss))
+            lb.backward()
+            nb = dict(mb.named_parameters())
+            bf["grad_relF"] = {}
+            for k in rec["grads"]:
+                g32 = named[k].grad.detach()
+                g16 = nb[k].grad.detach().float()
+                a, b_ = (g16[:24], g32[:24]) if g32.dim() == 2 else (g16, g32)
+                bf["grad_relF"][k] = float((a - b_).norm() / (b_.norm() + 1e-30))
+        rec["ref_bf16_error"] = bf
         path = os.path.join(HERE, name + ".pt")
         torch.save(rec, path)
         print(f"{name}: loss={None if loss is None else float(loss):.6f}" if loss is not None else f"{name}: no loss",

@@ -4,7 +4,10 @@
 The kernels feed bf16 operands to the tensor cores (fp32 accumulate, fp32 residual stream / norms / softmax / CE),
 so parity with the fp32 reference is bounded by bf16 operand rounding (2^-9 relative per element):
   loss: <= 1e-3 relative (BASELINE north-star tolerance);  logits / hidden: relative Frobenius error <= 1e-2;
-  gradients: relative Frobenius <= 3e-2."""
+  gradients: relative Frobenius <= 3e-2.
+Each fixture also records how far the REFERENCE ITSELF lands from its fp32 result when run in bf16
+(rec["ref_bf16_error"]); every number is logged next to it in gpurun_out/parity_report.txt and a gradient may
+exceed 3e-2 only where the reference's own bf16 run does (tolerance = max(3e-2, 1.5 x reference bf16 error))."""
 import glob
 import os
 
@@ -51,7 +54,7 @@ def test_model_matches_reference_golden(path):
         assert tuple(lg.shape) == tuple(rec["logits_shape"])
         e_lg = _relf(lg[:: rec["logits_stride"]], rec["logits"])
         loss = out.head1_loss
-        _log(f"{name}: logits relF {e_lg:.3e}")
+        _log(f"{name}: logits relF {e_lg:.3e} (reference-in-bf16 relF {rec.get('ref_bf16_error', {}).get('logits_relF', float('nan')):.3e})")
         assert e_lg <= ACT_TOL
     else:
         e_tl = _relf(out.task_logits, rec["task_logits"])
@@ -63,7 +66,8 @@ def test_model_matches_reference_golden(path):
         assert e_th <= ACT_TOL and e_h <= ACT_TOL and e_tl <= 5 * ACT_TOL
     if "loss" in rec:
         e_loss = abs(loss.item() - rec["loss"].item()) / abs(rec["loss"].item())
-        _log(f"{name}: loss {loss.item():.6f} ref {rec['loss'].item():.6f} rel {e_loss:.3e}")
+        _log(f"{name}: loss {loss.item():.6f} ref {rec['loss'].item():.6f} rel {e_loss:.3e} "
+             f"(reference-in-bf16 rel {rec.get('ref_bf16_error', {}).get('loss_rel', float('nan')):.3e})")
         assert e_loss <= (LOSS_TOL if rec["kind"] == "pretrain" else 1e-2)
         loss.backward()
         named = dict(model.named_parameters())
@@ -73,8 +77,9 @@ def test_model_matches_reference_golden(path):
             e_n = abs(float(mine.double().norm()) - rec["grad_norms"][k]) / (rec["grad_norms"][k] + 1e-30)
             part = mine[:24] if mine.dim() == 2 else mine
             e_g = _relf(part, g)
-            _log(f"{name}: grad {k}: norm rel {e_n:.3e} relF {e_g:.3e}")
-            assert e_g <= GRAD_TOL and e_n <= GRAD_TOL, (k, e_g, e_n)
+            ref_bf = rec.get("ref_bf16_error", {}).get("grad_relF", {}).get(k, 0.0)
+            _log(f"{name}: grad {k}: norm rel {e_n:.3e} relF {e_g:.3e} (reference-in-bf16 relF {ref_bf:.3e})")
+            assert e_g <= max(GRAD_TOL, 1.5 * ref_bf) and e_n <= GRAD_TOL, (k, e_g, e_n, ref_bf)
 
 
 def test_c2_medium_vs_oracle():
