@@ -25,6 +25,8 @@ enum : int { EPI_BF16 = 0, EPI_F32 = 1, EPI_RESID = 2, EPI_GEGLU = 3, EPI_QKV_RO
 struct GemmParams {
   int M, N, K;
   int num_m_blocks, num_n_blocks, num_k_blocks;
+  int num_splits;       // split-K factor (wgrad: K = tokens is huge while M x N has few tiles); >1 => atomic fp32 adds
+  int kb_per_split;
   int b_half_rows;      // GEGLU: row offset of the `up` half inside B (= N/2)
   // epilogue
   void* C;              // bf16 (EPI_BF16/GEGLU/QKV_ROPE) or f32 (EPI_F32/RESID) output
@@ -81,7 +83,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  const int num_tiles = p.num_m_blocks * p.num_n_blocks * p.num_splits;   // work items = (tile, k-split)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -111,10 +113,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+        const int tile = item / p.num_splits, split = item % p.num_splits;
         const int m0 = (tile / p.num_n_blocks) * BM;
         const int nb = tile % p.num_n_blocks;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * S::kStageBytes;
           uint8_t* sb = sa + S::kABytes;
@@ -153,11 +158,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+        const int split = item % p.num_splits;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
@@ -168,7 +176,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                         : umma_desc_sw128(sa + kk * 32, 16, 1024);
             const uint64_t bdesc = B_MN ? umma_desc_sw128(sb + kk * 2048, 8192, 1024)
                                         : umma_desc_sw128(sb + kk * 32, 16, 1024);
-            tc_mma_bf16(d_tmem, adesc, bdesc, idesc, (kb | kk) != 0 ? 1u : 0u);
+            tc_mma_bf16(d_tmem, adesc, bdesc, idesc, (kb != kb0 || kk != 0) ? 1u : 0u);
           }
           tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
           if (++stage == kStages) {
@@ -189,7 +197,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int row_in_tile = quad * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+      const int tile = item / p.num_splits;
       const int m0 = (tile / p.num_n_blocks) * BM;
       const int nb = tile % p.num_n_blocks;
       const int row = m0 + row_in_tile;
@@ -233,11 +242,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 float4 o = make_float4(__uint_as_float(r[g * 4 + 0]), __uint_as_float(r[g * 4 + 1]),
                                        __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3]));
                 float4* dst = reinterpret_cast<float4*>(crow + c + g * 4);
-                if (p.accumulate) {
-                  float4 old = *dst;
-                  o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                if (p.num_splits > 1) {   // split-K partial sums: fire-and-forget vector reduction into L2
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(o.x), "f"(o.y),
+                               "f"(o.z), "f"(o.w)
+                               : "memory");
+                } else {
+                  if (p.accumulate) {
+                    float4 old = *dst;
+                    o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                  }
+                  *dst = o;
                 }
-                *dst = o;
               }
             }
           }
@@ -390,7 +405,19 @@ static int launch_gemm(const void* A, long long lda, const void* B, long long ld
   else p.num_n_blocks = (p.N + BN - 1) / BN;
   p.num_k_blocks = (p.K + BK - 1) / BK;
   p.b_half_rows = p.N / 2;
-  const int tiles = p.num_m_blocks * p.num_n_blocks;
+  // split-K only where it is safe (fp32 output that accumulates into a pre-initialised buffer) and useful
+  // (fewer tiles than ~2 waves of SMs while K is long): each split keeps >= 16 k-blocks.
+  p.num_splits = 1;
+  if (EPI == EPI_F32 && p.accumulate) {
+    const int mn_tiles = p.num_m_blocks * p.num_n_blocks;
+    const int want = (2 * num_sms() + mn_tiles - 1) / mn_tiles;
+    const int max_by_k = p.num_k_blocks / 16;
+    int sp = want < max_by_k ? want : max_by_k;
+    if (sp > 1) p.num_splits = sp;
+  }
+  p.kb_per_split = (p.num_k_blocks + p.num_splits - 1) / p.num_splits;
+  p.num_splits = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;   // no empty splits
+  const int tiles = p.num_m_blocks * p.num_n_blocks * p.num_splits;
   int grid = num_sms();
   if (grid > tiles) grid = tiles;
 

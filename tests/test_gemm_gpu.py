@@ -143,3 +143,17 @@ def test_gemm_qkv_rope(M, d, K):
     qk = (qk * cos + rot * sin).reshape(M, 2 * d)
     ref = torch.cat([qk, y[:, 2 * d:]], -1)
     _report("qkv_rope", out, ref, 6e-3)
+
+
+@pytest.mark.parametrize("M,N,K", [(768, 768, 20000), (2304, 768, 8192), (756, 768, 5000)])
+def test_gemm_wgrad_split_k(M, N, K):
+    """Long-K weight gradients take the split-K path (vector red.global.add into the fp32 gradient buffer)."""
+    from graphgpt_b200 import ops
+    Mp = (M + 7) // 8 * 8
+    dy = _rand((K, Mp), 21, 0.5)[:, :M]
+    x = _rand((K, N), 22, 0.5)
+    ref = dy.float().t() @ x.float()
+    base = torch.randn((M, N), generator=torch.Generator().manual_seed(23)).cuda()
+    out = ops.gemm(dy, x, a_mn_major=True, b_mn_major=True, out=base.clone(), out_dtype=torch.float32, accumulate=True)
+    torch.cuda.synchronize()
+    _report(f"wgrad split-k {M}x{N}x{K}", out, base + ref, 1e-4)

@@ -1,0 +1,174 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every declared symbol, host-side layout / config
+logic, the synthetic data contract, and the data-parallel reducer over gloo with world_size 2."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from graphgpt_b200.lib import LIB_PATH, parse_header
+    if not os.path.exists(LIB_PATH):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("ggpt_build", os.path.join(ROOT, "graph-gpt_b200", "build.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.build()
+    dll = ctypes.CDLL(LIB_PATH)
+    protos = parse_header()
+    assert len(protos) >= 25
+    for name in protos:
+        assert hasattr(dll, name), f"{name} declared in include/ggpt_b200.h but not exported"
+    dll.ggpt_abi_version.restype = ctypes.c_int
+    assert dll.ggpt_abi_version() == 1
+    dll.ggpt_attn_mask_words.restype = ctypes.c_int
+    assert dll.ggpt_attn_mask_words(1024) == 32 and dll.ggpt_attn_mask_words(40) == 4
+
+
+def test_argument_validation_without_gpu():
+    """Entry points validate arguments before touching the device, so bad calls fail loudly even here."""
+    from graphgpt_b200.lib import lib
+    with pytest.raises(RuntimeError, match="null operand"):
+        lib.ggpt_gemm_bf16(0, 8, 0, 0, 8, 0, 0, 8, 0, 0, 128, 128, 64, 0)
+    with pytest.raises(RuntimeError, match="not implemented"):
+        lib.ggpt_attn_mask_build(1, 4, 1, 8, 0, 1, 1, 0)
+
+
+def test_model_refuses_cpu_execution():
+    from graphgpt_b200 import GraphGPTConfig, GraphGPTPretrainBase
+    cfg = GraphGPTConfig(vocab_size=300, hidden_size=64, intermediate_size=256, num_hidden_layers=1, num_attention_heads=1,
+                         num_key_value_heads=1, hidden_act="gelu", stacked_feat=1, next_n_token=1, causal_attention=False)
+    m = GraphGPTPretrainBase(cfg)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(input_ids=torch.ones((1, 8), dtype=torch.long), attention_mask=torch.ones((1, 8), dtype=torch.long))
+
+
+def test_state_dict_keys_match_reference_checkpoint_contract():
+    from graphgpt_b200 import GraphGPTConfig, GraphGPTPretrainBase, GraphGPTTaskModel
+    for fx, cls in (("c2_smtp_stacked_2d", GraphGPTPretrainBase), ("c2_gated_agg", GraphGPTPretrainBase),
+                    ("c3_ft_layerscale", GraphGPTTaskModel), ("c1_toy_smtp_2d", GraphGPTPretrainBase)):
+        rec = torch.load(os.path.join(ROOT, "tests", "golden", fx + ".pt"))
+        m = cls(GraphGPTConfig(**rec["config"]))
+        mine = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        ref = {k: tuple(v.shape) for k, v in rec["state_dict"].items()}
+        assert mine == ref, (set(mine) ^ set(ref))
+
+
+def test_flat_layout_keeps_fused_weights_adjacent_and_aligned():
+    from graphgpt_b200 import GraphGPTConfig, GraphGPTPretrainBase
+    from graphgpt_b200.engine import FlatParams
+    cfg = GraphGPTConfig(vocab_size=756, hidden_size=128, intermediate_size=512, num_hidden_layers=2, num_attention_heads=2,
+                         num_key_value_heads=2, hidden_act="gelu", stacked_feat=13, stack_method="short", next_n_token=13,
+                         causal_attention=False)
+    m = GraphGPTPretrainBase(cfg)
+    fp = FlatParams(m, m._flat_param_order())
+    d, I = 128, 512
+    for i in range(2):
+        p = f"model.layers.{i}."
+        q, k, v = (fp.offsets[p + f"self_attn.{n}_proj.weight"][0] for n in "qkv")
+        assert k == q + d * d and v == k + d * d
+        g, u = fp.offsets[p + "mlp.gate_proj.weight"][0], fp.offsets[p + "mlp.up_proj.weight"][0]
+        assert u == g + I * d
+    assert all(off % 128 == 0 for off, _ in fp.offsets.values())
+    assert {n for n, _ in fp.order} == set(dict(m.named_parameters()))
+    a, b = fp.span("model.layers.1.self_attn.q_proj.weight", "model.layers.1.post_attention_layernorm.weight")
+    assert b - a >= 4 * d * d + 3 * d * I + 2 * d
+
+
+def test_config_roundtrip_and_legacy_conversion():
+    from types import SimpleNamespace as NS
+
+    from graphgpt_b200 import GraphGPTConfig, convert_to_legacy_config
+    mc = NS(vocab_size=756, hidden_size=768, intermediate_size=3072, num_hidden_layers=12, num_attention_heads=12,
+            num_key_value_heads=12, head_dim=64, attention_bias=False, mlp_bias=False, hidden_act="gelu",
+            max_position_embeddings=1024, initializer_range=0.02, rms_norm_eps=1e-6, tie_word_embeddings=False,
+            rope_theta=10000.0, use_cache=False, pad_token_id=0, bos_token_id=20, eos_token_id=19, cls_token_id=None,
+            causal_attention=False, rope_range=0, layer_scale_init_value=0.0,
+            dropout_settings=NS(embed_dropout=0.0, path_dropout=0.0, mlp_dropout=0.0, attention_dropout=0.1),
+            graph_input=NS(stacked_feat=13, stack_method="short", stacked_feat_agg_method="sum", embed_dim=0),
+            geometric_input=NS(pos_agg_method="sum", pos_bins=512),
+            pt_head=NS(next_n_token=13, use_generative=True, use_discriminative=False, focal_gamma=0.0, smtp_inside=False),
+            ft_head=NS(pooling_method="last", mlp=[], dropout=0.0, loss_type=None, num_neg=None, num_labels=2,
+                       problem_type=None, task_ratio=1.0))
+    cfg = convert_to_legacy_config(mc)
+    assert isinstance(cfg, GraphGPTConfig)
+    assert (cfg.stacked_feat, cfg.next_n_token, cfg.hidden_size, cfg.causal_attention) == (13, 13, 768, False)
+    assert cfg.attention_dropout == 0.1 and cfg.mlp == [] and cfg.num_labels == 2
+    d = cfg.to_dict()
+    assert d["model_type"] == "graphgpt" and d["stack_method"] == "short"
+
+
+def test_synthetic_batches_follow_the_collator_contract():
+    from graphgpt_b200 import synth
+    st = synth.rows_per_sample_stats(1500)
+    assert 21.5 <= st["mean"] <= 25.5 and 14 <= st["p5"] <= 17 and 29 <= st["p95"] <= 34      # 23.5 / 16 / 31
+    b = synth.make_batch(3, 256, layout="packed", seed=5, return_segments=True)
+    ids, lab, am = b["input_ids"], b["labels"], b["attention_mask"]
+    assert ids.shape == (3, 256, 13) and lab.shape == ids.shape and am.shape == (3, 256, 256)
+    assert ids.dtype == np.int64 and am.dtype == np.int64
+    assert ((lab == -100) | (ids == synth.MASK_ID) | (lab == 0)).all()          # masked entries carry <mask>
+    assert (lab[lab != -100] < 756).all() and (ids < 756).all() and (ids >= 0).all()
+    for n, lens in enumerate(b["segment_lens"]):
+        assert sum(lens) == 256
+        o = 0
+        for L in lens:                                                      # block-diagonal, nothing else
+            assert am[n, o:o + L, o:o + L].all()
+            assert am[n, o:o + L].sum() == L * L
+            o += L
+    u = synth.make_batch(5, 1024, layout="unpacked", seed=6)
+    assert u["attention_mask"].ndim == 2 and u["input_ids"].shape[1] % 8 == 0
+    rows = u["attention_mask"].sum(1)
+    for n in range(5):
+        assert (u["input_ids"][n, rows[n] - 1] == synth.EOS_ID).any() or (u["labels"][n, rows[n] - 1] == synth.EOS_ID).any()
+        assert (u["input_ids"][n, rows[n]:] == 0).all() and (u["labels"][n, rows[n]:] == -100).all()
+    t = synth.make_batch(2, 64, layout="unpacked", vocab=synth.TOY_VOCAB, seed=7)
+    assert t["input_ids"].ndim == 2
+
+
+def test_warmup_decay_lr():
+    from graphgpt_b200.dp import warmup_decay_lr
+    kw = dict(max_lr=3e-4, min_lr=0.0, warmup_steps=10, total_steps=110)
+    assert warmup_decay_lr(0, **kw) == 0.0
+    assert abs(warmup_decay_lr(5, **kw) - 1.5e-4) < 1e-12
+    assert abs(warmup_decay_lr(10, **kw) - 3e-4) < 1e-12
+    assert abs(warmup_decay_lr(60, **kw) - 1.5e-4) < 1e-12
+    assert warmup_decay_lr(110, **kw) == 0.0
+
+
+_GLOO_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from graphgpt_b200.dp import GradReducer
+rank, world = int(sys.argv[2]), 2
+os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=sys.argv[3], RANK=str(rank), WORLD_SIZE=str(world))
+dist.init_process_group("gloo", rank=rank, world_size=world)
+flat = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+red = GradReducer(flat)
+# segments complete in backward order: tail, two layers, head — exactly how engine.HotPath fires its hook
+for a, b in ((768, 1000), (512, 768), (128, 512), (0, 128)):
+    red.reduce_span(a, b)
+spans = red.wait()
+expect = torch.arange(1000, dtype=torch.float32) * 3
+assert torch.equal(flat, expect), (flat[:4], expect[:4])
+assert sorted(spans) == [(0, 128), (128, 512), (512, 768), (768, 1000)]
+dist.barrier(); dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_grad_reducer_gloo_world2(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(r), port], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(2)]
+    outs = [p.communicate(timeout=240)[0].decode() for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert "ok" in o
