@@ -91,6 +91,33 @@ __global__ void embed_bwd_kernel(const long long* __restrict__ ids, const float*
   }
 }
 
+// Token-count matrix for the embedding gradient as a GEMM:  C[t, v] = #{f : ids[t,f] == v} (bf16, exact small ints),
+// C[t, padding_idx] = 0.  Then dE[V,d] = C^T dX runs on the tensor cores (wgrad GEMM) instead of T*F*d fp32 atomics
+// that serialise on hot rows (<mask> carries ~half of all entries).  One warp per token; F <= 32.
+__global__ void embed_count_kernel(const long long* __restrict__ ids, __nv_bfloat16* __restrict__ cnt, long long ldc,
+                                   long long T, int F, int V, int padding_idx) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  for (long long t = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); t < T;
+       t += static_cast<long long>(gridDim.x) * warps_per_block) {
+    __nv_bfloat16* row = cnt + t * ldc;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (long long c = lane * 8; c < ldc; c += 256) *reinterpret_cast<uint4*>(row + c) = z;
+    __syncwarp();
+    long long my = (lane < F) ? ids[t * F + lane] : -1;
+    int count = 0;
+    bool first = true;
+    for (int f = 0; f < F; ++f) {
+      const long long other = __shfl_sync(0xffffffffu, my, f);
+      if (other == my) {
+        ++count;
+        if (f < lane) first = false;
+      }
+    }
+    if (lane < F && first && my >= 0 && my < V && my != padding_idx) row[my] = __float2bfloat16_rn(static_cast<float>(count));
+  }
+}
+
 // =============================================================================================
 // RMSNorm  y = bf16( w * x * rsqrt(mean(x^2) + eps) ), fp32 statistics.   ref: HF:59-64
 // =============================================================================================
@@ -127,7 +154,7 @@ __global__ void rmsnorm_fwd_kernel(const float* __restrict__ x, const float* __r
 // Each lane owns the same columns (lane*4 + k*128) for every row its warp visits, so the row is held in registers
 // (one HBM pass) and the dw partial sums stay in registers until one smem + global reduction per block.
 template <int NV>
-__global__ void rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const float* __restrict__ x,
+__global__ void __launch_bounds__(128, 4) rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const float* __restrict__ x,
                                    const float* __restrict__ rstd_in, const float* __restrict__ w,
                                    const float* __restrict__ dresid, float* __restrict__ dx_out,
                                    __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dw, long long T, int d) {
@@ -137,13 +164,9 @@ __global__ void rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long lo
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const float inv_d = 1.0f / static_cast<float>(d);
-  float4 wv[NV], dwacc[NV];
+  float4 dwacc[NV];
 #pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const int c = lane * 4 + k * 128;
-    wv[k] = (c < d) ? *reinterpret_cast<const float4*>(w + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-    dwacc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
+  for (int k = 0; k < NV; ++k) dwacc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (long long t = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); t < T;
        t += static_cast<long long>(gridDim.x) * warps_per_block) {
     const float* xr = x + t * d;
@@ -162,7 +185,8 @@ __global__ void rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long lo
         gv[k] = make_float4(d01.x, d01.y, d23.x, d23.y);
         dwacc[k].x += gv[k].x * xs[k].x; dwacc[k].y += gv[k].y * xs[k].y;
         dwacc[k].z += gv[k].z * xs[k].z; dwacc[k].w += gv[k].w * xs[k].w;
-        gv[k].x *= wv[k].x; gv[k].y *= wv[k].y; gv[k].z *= wv[k].z; gv[k].w *= wv[k].w;
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(w + c));   // 3 KB, L1-resident
+        gv[k].x *= wv.x; gv[k].y *= wv.y; gv[k].z *= wv.z; gv[k].w *= wv.w;
         dot += gv[k].x * xs[k].x + gv[k].y * xs[k].y + gv[k].z * xs[k].z + gv[k].w * xs[k].w;
       }
     }
@@ -568,6 +592,15 @@ int ggpt_embed_bwd(const long long* ids, const float* dx, const float* table, co
   return check_launch("embed_bwd_kernel");
 }
 
+int ggpt_embed_count(const long long* ids, void* cnt, long long ldc, long long T, int F, int V, int padding_idx,
+                     void* stream) {
+  GGPT_REQUIRE(ids && cnt, "embed_count: null pointer");
+  GGPT_REQUIRE(T > 0 && F > 0 && F <= 32 && ldc % 8 == 0 && ldc >= V, "embed_count: bad sizes T=%lld F=%d V=%d ldc=%lld", T, F, V, ldc);
+  embed_count_kernel<<<grid_for_rows(T, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      ids, static_cast<__nv_bfloat16*>(cnt), ldc, T, F, V, padding_idx);
+  return check_launch("embed_count_kernel");
+}
+
 int ggpt_rmsnorm_fwd(const float* x, const float* w, void* y, long long ldy, float* rstd, long long T, int d, float eps,
                      void* stream) {
   GGPT_REQUIRE(x && w && y, "rmsnorm_fwd: null pointer");
@@ -582,18 +615,18 @@ int ggpt_rmsnorm_bwd(const void* dy, long long lddy, const float* x, const float
   GGPT_REQUIRE(dy && x && rstd && w && dx_out && dw, "rmsnorm_bwd: null pointer");
   GGPT_REQUIRE(T > 0 && d % 4 == 0 && lddy % 4 == 0, "rmsnorm_bwd: bad sizes");
   GGPT_REQUIRE(d <= 2048, "rmsnorm_bwd: hidden size %d > 2048 is not instantiated", d);
-  const int grid = grid_for_rows(T, 8, 2);
+  const int grid = grid_for_rows(T, 4, 8);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const __nv_bfloat16* dyb = static_cast<const __nv_bfloat16*>(dy);
   __nv_bfloat16* dxb = static_cast<__nv_bfloat16*>(dx_bf16);
   const size_t sm = d * sizeof(float);
   const int nv = (d + 127) / 128;
-  if (nv <= 1) rmsnorm_bwd_kernel<1><<<grid, 256, sm, s>>>(dyb, lddy, x, rstd, w, dresid, dx_out, dxb, dw, T, d);
-  else if (nv <= 2) rmsnorm_bwd_kernel<2><<<grid, 256, sm, s>>>(dyb, lddy, x, rstd, w, dresid, dx_out, dxb, dw, T, d);
-  else if (nv <= 4) rmsnorm_bwd_kernel<4><<<grid, 256, sm, s>>>(dyb, lddy, x, rstd, w, dresid, dx_out, dxb, dw, T, d);
-  else if (nv <= 6) rmsnorm_bwd_kernel<6><<<grid, 256, sm, s>>>(dyb, lddy, x, rstd, w, dresid, dx_out, dxb, dw, T, d);
-  else if (nv <= 8) rmsnorm_bwd_kernel<8><<<grid, 256, sm, s>>>(dyb, lddy, x, rstd, w, dresid, dx_out, dxb, dw, T, d);
-  else rmsnorm_bwd_kernel<16><<<grid, 256, sm, s>>>(dyb, lddy, x, rstd, w, dresid, dx_out, dxb, dw, T, d);
+  if (nv <= 1) rmsnorm_bwd_kernel<1><<<grid, 128, sm, s>>>(dyb, lddy, x, rstd, w, dresid, dx_out, dxb, dw, T, d);
+  else if (nv <= 2) rmsnorm_bwd_kernel<2><<<grid, 128, sm, s>>>(dyb, lddy, x, rstd, w, dresid, dx_out, dxb, dw, T, d);
+  else if (nv <= 4) rmsnorm_bwd_kernel<4><<<grid, 128, sm, s>>>(dyb, lddy, x, rstd, w, dresid, dx_out, dxb, dw, T, d);
+  else if (nv <= 6) rmsnorm_bwd_kernel<6><<<grid, 128, sm, s>>>(dyb, lddy, x, rstd, w, dresid, dx_out, dxb, dw, T, d);
+  else if (nv <= 8) rmsnorm_bwd_kernel<8><<<grid, 128, sm, s>>>(dyb, lddy, x, rstd, w, dresid, dx_out, dxb, dw, T, d);
+  else rmsnorm_bwd_kernel<16><<<grid, 128, sm, s>>>(dyb, lddy, x, rstd, w, dresid, dx_out, dxb, dw, T, d);
   return check_launch("rmsnorm_bwd_kernel");
 }
 

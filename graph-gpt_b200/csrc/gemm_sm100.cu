@@ -2,8 +2,9 @@
 //
 //   C[M,N] = A[M,K] * B[N,K]^T      bf16 operands, fp32 accumulation in TMEM
 //
-// One persistent CTA per SM, 6 warps: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) and TMEM
-// owner, warps 2..5 = epilogue (TMEM -> registers -> fused epilogue -> HBM).  Tiles are 128 x BN x 64 with a
+// One persistent CTA per SM, 10 warps: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) and TMEM
+// owner, warps 2..9 = epilogue (TMEM -> registers -> fused epilogue -> HBM; each TMEM lane quadrant is served by
+// two warps that split the tile's columns, so the epilogue issue rate keeps up with the 128x256x64 mainloop).  Tiles are 128 x BN x 64 with a
 // multi-stage smem ring (TMA SWIZZLE_128B) and two TMEM accumulator buffers so the epilogue of tile i overlaps
 // the MMAs of tile i+1.
 //
@@ -46,7 +47,7 @@ struct GemmParams {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant)
 
 template <int BN>
 struct GemmSmem {
@@ -95,8 +96,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     mbar_init(&tfull_bar[0], 1);
     mbar_init(&tfull_bar[1], 1);
-    mbar_init(&tempty_bar[0], 4);
-    mbar_init(&tempty_bar[1], 4);
+    mbar_init(&tempty_bar[0], 8);
+    mbar_init(&tempty_bar[1], 8);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -192,8 +193,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else {
-    // ===================== Epilogue warps (2..5) =====================
+    // ===================== Epilogue warps (2..9) =====================
     const int quad = warp & 3;            // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;     // which half of the tile's columns this warp drains
     const int row_in_tile = quad * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -211,7 +213,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int n0 = nb * BN;
         __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<long long>(row) * p.ldc + n0;
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
+        for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
           uint32_t r[32];
           tmem_ld32(taddr + c, r);
           tmem_ld_wait();
@@ -231,7 +233,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int n0 = nb * BN;
         float* crow = reinterpret_cast<float*>(p.C) + static_cast<long long>(row) * p.ldc + n0;
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
+        for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
           uint32_t r[32];
           tmem_ld32(taddr + c, r);
           tmem_ld_wait();
@@ -263,7 +265,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const float* rrow = p.resid + static_cast<long long>(row) * p.ldr + n0;
         const float rs = (p.rowscale != nullptr && row_ok) ? p.rowscale[row] : 1.0f;
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
+        for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
           uint32_t r[32];
           tmem_ld32(taddr + c, r);
           tmem_ld_wait();
@@ -294,7 +296,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         __nv_bfloat16* act = reinterpret_cast<__nv_bfloat16*>(p.C2) + static_cast<long long>(row) * p.ldc2;
         const int half_n = p.N / 2;
 #pragma unroll 1
-        for (int c = 0; c < BN / 2; c += 32) {
+        for (int c = half * (BN / 4); c < (half + 1) * (BN / 4); c += 32) {
           uint32_t rg[32], ru[32];
           tmem_ld32(taddr + c, rg);
           tmem_ld32(taddr + BN / 2 + c, ru);
@@ -326,7 +328,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const float* cs = p.cos_tab + static_cast<long long>(pos) * 32;
         const float* sn = p.sin_tab + static_cast<long long>(pos) * 32;
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 64) {
+        for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 64) {
           uint32_t r1[32], r2[32];
           tmem_ld32(taddr + c, r1);
           tmem_ld32(taddr + c + 32, r2);

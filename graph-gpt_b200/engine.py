@@ -291,14 +291,19 @@ class HotPath:
             ops.gemm(dqkv, st["h1"], out=self._gqkv(i), **wgrad)
             dh1 = ops.gemm(dqkv, self._wqkv(i), b_mn_major=True)
             dx, dxb = ops.rmsnorm_bwd(dh1, st["x"], st["rstd1"], fp.w(p + "input_layernorm.weight"), dx2,
-                                      fp.g(p + "input_layernorm.weight"), want_bf16=(i > 0))
+                                      fp.g(p + "input_layernorm.weight"))
             stash["layers"][i] = None   # free activations as we go
             if self.grad_ready_hook:
                 names = [n for n, _ in self.flat.order if n.startswith(p)]
                 self.grad_ready_hook(names[0], names[-1])
         gate = fp.w("stacked_feat_agg.weight") if "stacked_feat_agg.weight" in fp.offsets else None
         emb_p = dict(self.flat.order)["model.embed_tokens.weight"]
-        if emb_p.requires_grad:
+        pad = self.cfg.pad_token_id if self.cfg.pad_token_id is not None else -1
+        if emb_p.requires_grad and gate is None and not stash["long_scale"] and self.V <= 4096 and stash["ids"].shape[1] <= 32:
+            # small vocabulary: dE = C^T dX on the tensor cores (C = per-token id counts) instead of contended atomics
+            cnt = ops.embed_count(stash["ids"], self.V, pad)
+            ops.gemm(cnt, dxb, out=fp.g("model.embed_tokens.weight"), **wgrad)
+        elif emb_p.requires_grad:
             ops.embed_bwd(stash["ids"], dx, fp.w("model.embed_tokens.weight") if gate is not None else None, gate,
                           fp.g("model.embed_tokens.weight"),
                           fp.g("stacked_feat_agg.weight") if gate is not None else None,

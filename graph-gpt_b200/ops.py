@@ -189,6 +189,16 @@ def embed_bwd(ids, dx, table, gate, dtable, dgate, padding_idx=0, long_scale=Fal
                        padding_idx, int(long_scale), _stream())
 
 
+def embed_count(ids, V, padding_idx):
+    """bf16 [T, ceil8(V)] count matrix for the GEMM form of the embedding gradient."""
+    _check(ids, torch.int64, "embed ids", 2)
+    T, F_ = ids.shape
+    ldc = (V + 7) // 8 * 8
+    cnt = torch.empty((T, ldc), device=ids.device, dtype=BF16)
+    lib.ggpt_embed_count(ids.data_ptr(), cnt.data_ptr(), ldc, T, F_, V, padding_idx, _stream())
+    return cnt[:, :V]
+
+
 def rmsnorm_fwd(x, w, eps, *, want_rstd=True):
     _check(x, F32, "rmsnorm x", 2)
     _check(w, F32, "rmsnorm w", 1)

@@ -105,6 +105,12 @@ int ggpt_embed_fwd(const long long* ids, const float* table, const float* gate, 
 int ggpt_embed_bwd(const long long* ids, const float* dx, const float* table, const float* gate, float* dtable,
                    float* dgate, long long T, int F, int d, int V, int padding_idx, int long_scale, void* stream);
 
+/* cnt[t, v] (bf16 [T, ldc], fully overwritten) = number of features f with ids[t,f] == v, 0 for v == padding_idx.
+ * The embedding gradient is then the wgrad GEMM dE = cnt^T dX (ggpt_gemm_bf16 with both operands MN-major),
+ * replacing T*F*d contended atomics.   ref: autograd of modeling_helpers.py:96 / modeling_common.py:134. */
+int ggpt_embed_count(const long long* ids, void* cnt, long long ldc, long long T, int F, int V, int padding_idx,
+                     void* stream);
+
 /* y = bf16(w * x * rsqrt(mean(x^2)+eps)), rstd[T] saved for backward (may be NULL).   ref: HF:59-64 */
 int ggpt_rmsnorm_fwd(const float* x, const float* w, void* y, long long ldy, float* rstd, long long T, int d, float eps,
                      void* stream);
