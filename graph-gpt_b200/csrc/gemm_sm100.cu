@@ -55,18 +55,10 @@ struct GemmSmem {
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kStagingBytes = 8 * 4096;   // one 32 x 128 B transposition buffer per epilogue warp
   static constexpr int kBarBytes = 256;
-  static constexpr int kTotal = kStages * kStageBytes + kBarBytes + 1024;  // +1024 alignment slack
+  static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kBarBytes + 1024;  // +1024 alignment slack
 };
-
-__device__ __forceinline__ void store8_bf16(__nv_bfloat16* dst, const float* v) {
-  uint4 o;
-  o.x = pack_bf16(v[0], v[1]);
-  o.y = pack_bf16(v[2], v[3]);
-  o.z = pack_bf16(v[4], v[5]);
-  o.w = pack_bf16(v[6], v[7]);
-  *reinterpret_cast<uint4*>(dst) = o;
-}
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -75,7 +67,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   constexpr int kStages = S::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* bar_base = smem + kStages * S::kStageBytes;
+  uint8_t* bar_base = smem + kStages * S::kStageBytes + S::kStagingBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;   // [2]
@@ -194,175 +186,177 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else {
     // ===================== Epilogue warps (2..9) =====================
+    // TMEM rows are thread-private (lane = row), so writing them straight to HBM would touch 32 different
+    // 128-byte lines per instruction.  Each warp instead transposes 32 x 128 B chunks through its own swizzled
+    // smem buffer: write phase lane = row, read phase 8 lanes cover one row's 128 B -> every global access is a
+    // full-line, fully coalesced 16 B/lane transaction (4 rows per instruction).
     const int quad = warp & 3;            // TMEM lane quadrant this warp may access
     const int half = (warp - 2) >> 2;     // which half of the tile's columns this warp drains
-    const int row_in_tile = quad * 32 + lane;
+    uint8_t* stg = smem + kStages * S::kStageBytes + (warp - 2) * 4096;
+    const int rd_row = lane >> 3;         // read phase: row (it*4 + rd_row), 16-byte chunk rd_j
+    const int rd_j = lane & 7;
+    auto stage_put = [&](int j, uint4 v) {
+      *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = v;
+    };
+    auto stage_get = [&](int rr) -> uint4 {
+      return *reinterpret_cast<const uint4*>(stg + rr * 128 + ((rd_j ^ (rr & 7)) << 4));
+    };
+    auto put_bf16_32 = [&](int jbase, const uint32_t (&r)[32]) {   // 32 fp32 accumulators -> 4 chunks of 8 bf16
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 o;
+        o.x = pack_bf16(__uint_as_float(r[g * 8 + 0]), __uint_as_float(r[g * 8 + 1]));
+        o.y = pack_bf16(__uint_as_float(r[g * 8 + 2]), __uint_as_float(r[g * 8 + 3]));
+        o.z = pack_bf16(__uint_as_float(r[g * 8 + 4]), __uint_as_float(r[g * 8 + 5]));
+        o.w = pack_bf16(__uint_as_float(r[g * 8 + 6]), __uint_as_float(r[g * 8 + 7]));
+        stage_put(jbase + g, o);
+      }
+    };
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
       const int tile = item / p.num_splits;
       const int m0 = (tile / p.num_n_blocks) * BM;
       const int nb = tile % p.num_n_blocks;
-      const int row = m0 + row_in_tile;
+      const int row0 = m0 + quad * 32;                 // first global row of this warp's quadrant
+      const int row = row0 + lane;                     // write-phase row of this thread
       const bool row_ok = row < p.M;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
 
+      // staged 32 x 64 bf16 chunk -> dst[row0.., col0..col0+64), columns clipped at col_limit
+      auto copy_out_bf16 = [&](__nv_bfloat16* dst, long long ld, int col0, int col_limit) {
+        __syncwarp();
+        const int gcol = col0 + rd_j * 8;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rr = it * 4 + rd_row;
+          if (row0 + rr < p.M && gcol < col_limit)
+            *reinterpret_cast<uint4*>(dst + static_cast<long long>(row0 + rr) * ld + gcol) = stage_get(rr);
+        }
+        __syncwarp();
+      };
+
       if constexpr (EPI == EPI_BF16) {
         const int n0 = nb * BN;
-        __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<long long>(row) * p.ldc + n0;
 #pragma unroll 1
-        for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
-          uint32_t r[32];
-          tmem_ld32(taddr + c, r);
+        for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 64) {
+          uint32_t r0[32], r1[32];
+          tmem_ld32(taddr + c, r0);
+          tmem_ld32(taddr + c + 32, r1);
           tmem_ld_wait();
-          if (row_ok) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              if (n0 + c + g * 8 < p.N) {
-                float v[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
-                store8_bf16(crow + c + g * 8, v);
-              }
-            }
-          }
+          put_bf16_32(0, r0);
+          put_bf16_32(4, r1);
+          copy_out_bf16(reinterpret_cast<__nv_bfloat16*>(p.C), p.ldc, n0 + c, p.N);
         }
-      } else if constexpr (EPI == EPI_F32) {
+      } else if constexpr (EPI == EPI_F32 || EPI == EPI_RESID) {
         const int n0 = nb * BN;
-        float* crow = reinterpret_cast<float*>(p.C) + static_cast<long long>(row) * p.ldc + n0;
+        float* C = reinterpret_cast<float*>(p.C);
 #pragma unroll 1
         for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
           uint32_t r[32];
           tmem_ld32(taddr + c, r);
           tmem_ld_wait();
-          if (row_ok) {
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              if (n0 + c + g * 4 < p.N) {
-                float4 o = make_float4(__uint_as_float(r[g * 4 + 0]), __uint_as_float(r[g * 4 + 1]),
-                                       __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3]));
-                float4* dst = reinterpret_cast<float4*>(crow + c + g * 4);
-                if (p.num_splits > 1) {   // split-K partial sums: fire-and-forget vector reduction into L2
-                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(o.x), "f"(o.y),
-                               "f"(o.z), "f"(o.w)
-                               : "memory");
-                } else {
-                  if (p.accumulate) {
-                    float4 old = *dst;
-                    o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-                  }
-                  *dst = o;
+          for (int j = 0; j < 8; ++j) stage_put(j, make_uint4(r[j * 4 + 0], r[j * 4 + 1], r[j * 4 + 2], r[j * 4 + 3]));
+          __syncwarp();
+          const int gcol = n0 + c + rd_j * 4;
+          float4 cs = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (EPI == EPI_RESID && p.colscale != nullptr && gcol < p.N)
+            cs = *reinterpret_cast<const float4*>(p.colscale + gcol);
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + rd_row;
+            const int grow = row0 + rr;
+            if (grow < p.M && gcol < p.N) {
+              const uint4 u = stage_get(rr);
+              float4 o = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+              float4* dst = reinterpret_cast<float4*>(C + static_cast<long long>(grow) * p.ldc + gcol);
+              if constexpr (EPI == EPI_RESID) {
+                const float4 res = *reinterpret_cast<const float4*>(p.resid + static_cast<long long>(grow) * p.ldr + gcol);
+                const float rs = p.rowscale != nullptr ? p.rowscale[grow] : 1.0f;
+                o.x = fmaf(o.x, cs.x * rs, res.x);
+                o.y = fmaf(o.y, cs.y * rs, res.y);
+                o.z = fmaf(o.z, cs.z * rs, res.z);
+                o.w = fmaf(o.w, cs.w * rs, res.w);
+                *dst = o;
+              } else if (p.num_splits > 1) {   // split-K partial sums: fire-and-forget vector reduction into L2
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(o.x), "f"(o.y), "f"(o.z),
+                             "f"(o.w)
+                             : "memory");
+              } else {
+                if (p.accumulate) {
+                  const float4 old = *dst;
+                  o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
                 }
+                *dst = o;
               }
             }
           }
-        }
-      } else if constexpr (EPI == EPI_RESID) {
-        const int n0 = nb * BN;
-        float* crow = reinterpret_cast<float*>(p.C) + static_cast<long long>(row) * p.ldc + n0;
-        const float* rrow = p.resid + static_cast<long long>(row) * p.ldr + n0;
-        const float rs = (p.rowscale != nullptr && row_ok) ? p.rowscale[row] : 1.0f;
-#pragma unroll 1
-        for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
-          uint32_t r[32];
-          tmem_ld32(taddr + c, r);
-          tmem_ld_wait();
-          if (row_ok) {
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              if (n0 + c + g * 4 < p.N) {
-                float4 res = *reinterpret_cast<const float4*>(rrow + c + g * 4);
-                float4 sc = make_float4(rs, rs, rs, rs);
-                if (p.colscale != nullptr) {
-                  float4 cs = *reinterpret_cast<const float4*>(p.colscale + n0 + c + g * 4);
-                  sc.x *= cs.x; sc.y *= cs.y; sc.z *= cs.z; sc.w *= cs.w;
-                }
-                float4 o;
-                o.x = fmaf(__uint_as_float(r[g * 4 + 0]), sc.x, res.x);
-                o.y = fmaf(__uint_as_float(r[g * 4 + 1]), sc.y, res.y);
-                o.z = fmaf(__uint_as_float(r[g * 4 + 2]), sc.z, res.z);
-                o.w = fmaf(__uint_as_float(r[g * 4 + 3]), sc.w, res.w);
-                *reinterpret_cast<float4*>(crow + c + g * 4) = o;
-              }
-            }
-          }
+          __syncwarp();
         }
       } else if constexpr (EPI == EPI_GEGLU) {
-        // tile columns [0,BN/2) = gate for fused columns nh.., [BN/2,BN) = matching up columns
+        // tile columns [0,BN/2) = gate for fused columns nh.., [BN/2,BN) = the matching up columns;
+        // this warp owns gate/up columns [c, c+64)
         const int nh = nb * (BN / 2);
-        __nv_bfloat16* gu = reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<long long>(row) * p.ldc;
-        __nv_bfloat16* act = reinterpret_cast<__nv_bfloat16*>(p.C2) + static_cast<long long>(row) * p.ldc2;
         const int half_n = p.N / 2;
+        const int c = half * (BN / 4);
+        __nv_bfloat16* gu = reinterpret_cast<__nv_bfloat16*>(p.C);
+        if (gu != nullptr) {
 #pragma unroll 1
-        for (int c = half * (BN / 4); c < (half + 1) * (BN / 4); c += 32) {
-          uint32_t rg[32], ru[32];
-          tmem_ld32(taddr + c, rg);
-          tmem_ld32(taddr + BN / 2 + c, ru);
-          tmem_ld_wait();
-          if (row_ok) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              if (nh + c + g * 8 < half_n) {
-                float vg[8], vu[8], va[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  vg[j] = __uint_as_float(rg[g * 8 + j]);
-                  vu[j] = __uint_as_float(ru[g * 8 + j]);
-                  va[j] = gelu_erf(vg[j]) * vu[j];
-                }
-                if (p.C != nullptr) {
-                  store8_bf16(gu + nh + c + g * 8, vg);
-                  store8_bf16(gu + half_n + nh + c + g * 8, vu);
-                }
-                store8_bf16(act + nh + c + g * 8, va);
-              }
-            }
+          for (int part = 0; part < 2; ++part) {          // 0: gate columns, 1: up columns
+            uint32_t r0[32], r1[32];
+            tmem_ld32(taddr + part * (BN / 2) + c, r0);
+            tmem_ld32(taddr + part * (BN / 2) + c + 32, r1);
+            tmem_ld_wait();
+            put_bf16_32(0, r0);
+            put_bf16_32(4, r1);
+            copy_out_bf16(gu, p.ldc, part * half_n + nh + c, part * half_n + half_n);
           }
         }
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {                  // act = gelu(gate) * up, 32 columns at a time
+          uint32_t rg[32], ru[32];
+          tmem_ld32(taddr + c + hh * 32, rg);
+          tmem_ld32(taddr + BN / 2 + c + hh * 32, ru);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            rg[j] = __float_as_uint(gelu_erf(__uint_as_float(rg[j])) * __uint_as_float(ru[j]));
+          put_bf16_32(hh * 4, rg);
+        }
+        copy_out_bf16(reinterpret_cast<__nv_bfloat16*>(p.C2), p.ldc2, nh + c, half_n);
       } else if constexpr (EPI == EPI_QKV_ROPE) {
         const int n0 = nb * BN;
-        __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<long long>(row) * p.ldc + n0;
         const int pos = row_ok ? p.pos[row] : 0;
         const float* cs = p.cos_tab + static_cast<long long>(pos) * 32;
         const float* sn = p.sin_tab + static_cast<long long>(pos) * 32;
 #pragma unroll 1
-        for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 64) {
+        for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 64) {   // one head (64 columns) per iteration
           uint32_t r1[32], r2[32];
           tmem_ld32(taddr + c, r1);
           tmem_ld32(taddr + c + 32, r2);
           tmem_ld_wait();
-          if (row_ok && n0 + c < p.N) {
-            const bool rot = (n0 + c) < p.rope_cols;
+          if ((n0 + c) < p.rope_cols) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              float o1[8], o2[8];
-              if (rot) {
-                const float4 c0 = *reinterpret_cast<const float4*>(cs + g * 8);
-                const float4 c1 = *reinterpret_cast<const float4*>(cs + g * 8 + 4);
-                const float4 s0 = *reinterpret_cast<const float4*>(sn + g * 8);
-                const float4 s1 = *reinterpret_cast<const float4*>(sn + g * 8 + 4);
-                const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-                const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+            for (int g = 0; g < 8; ++g) {
+              const float4 c4 = *reinterpret_cast<const float4*>(cs + g * 4);
+              const float4 s4 = *reinterpret_cast<const float4*>(sn + g * 4);
+              const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
+              const float ss[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const float x1 = __uint_as_float(r1[g * 8 + j]);
-                  const float x2 = __uint_as_float(r2[g * 8 + j]);
-                  o1[j] = x1 * cc[j] - x2 * ss[j];   // q*cos + rotate_half(q)*sin, first half
-                  o2[j] = x2 * cc[j] + x1 * ss[j];   // second half
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  o1[j] = __uint_as_float(r1[g * 8 + j]);
-                  o2[j] = __uint_as_float(r2[g * 8 + j]);
-                }
+              for (int j = 0; j < 4; ++j) {
+                const float x1 = __uint_as_float(r1[g * 4 + j]);
+                const float x2 = __uint_as_float(r2[g * 4 + j]);
+                r1[g * 4 + j] = __float_as_uint(x1 * cc[j] - x2 * ss[j]);   // q*cos + rotate_half(q)*sin, first half
+                r2[g * 4 + j] = __float_as_uint(x2 * cc[j] + x1 * ss[j]);   // second half
               }
-              store8_bf16(crow + c + g * 8, o1);
-              store8_bf16(crow + c + 32 + g * 8, o2);
             }
           }
+          put_bf16_32(0, r1);
+          put_bf16_32(4, r2);
+          copy_out_bf16(reinterpret_cast<__nv_bfloat16*>(p.C), p.ldc, n0 + c, p.N);
         }
       }
 
