@@ -24,10 +24,12 @@ constexpr int kBwdThreads = 192;
 
 struct AttnBwdParams {
   int N, S, H;
-  int n_t;                    // tiles per side
+  int max_tiles;              // allocation stride of the tile arrays (= ceil(S/64))
   int mask_words;
   const uint32_t* mask_bits;  // [N,S,words]
-  const uint8_t* tile_cls;    // [N,n_t,n_t]  (query tile major)
+  const int* tile_start;      // [N, max_tiles+1]  variable row tiles (see attn_fwd_sm100.cu)
+  const int* n_tiles;         // [N]
+  const uint8_t* tile_cls;    // [N,max_tiles,max_tiles]  (query tile major)
   const float* lse;           // [N,H,S]
   const float* dsum;          // [N,H,S]   D = rowsum(dO*O)
   __nv_bfloat16* dqkv;        // [N*S, ld]
@@ -50,6 +52,21 @@ struct BwdSmem {
   static constexpr int kBars = kDS + 32768;
   static constexpr int kTotal = kBars + 256;
 };
+
+// 128 mask bits of query row `mrow` for the key tile starting at key k0 (any alignment) with klen valid keys.
+__device__ __forceinline__ void load_mask_words_bwd(const uint32_t* __restrict__ mrow, int k0, int klen, uint32_t (&mw)[4]) {
+  const int w0 = k0 >> 5, sh = k0 & 31;
+  uint32_t w[5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) w[i] = mrow[w0 + i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t v = __funnelshift_r(w[i], w[i + 1], sh);
+    const int nvalid = klen - 32 * i;
+    const uint32_t keep = nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u));
+    mw[i] = v & keep;
+  }
+}
 
 template <bool DKV>
 __global__ void __launch_bounds__(kBwdThreads, 1)
@@ -75,9 +92,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int tile = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
-  const uint8_t* cls_n = p.tile_cls + static_cast<size_t>(n) * p.n_t * p.n_t;
+  const int n_t = p.n_tiles[n];
+  if (tile >= n_t) return;                      // uniform for the whole CTA, before any barrier / TMEM state
+  const int* ts = p.tile_start + static_cast<size_t>(n) * (p.max_tiles + 1);
+  const int row_base = ts[tile], row_len = ts[tile + 1] - row_base;   // rows of the fixed tile
+  const uint8_t* cls_n = p.tile_cls + static_cast<size_t>(n) * p.max_tiles * p.max_tiles;
   // class of (query tile, key tile) for streamed index t
-  auto cls_of = [&](int t) -> int { return DKV ? cls_n[t * p.n_t + tile] : cls_n[tile * p.n_t + t]; };
+  auto cls_of = [&](int t) -> int { return DKV ? cls_n[t * p.max_tiles + tile] : cls_n[tile * p.max_tiles + t]; };
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0) {
@@ -111,31 +132,31 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const uint32_t tmem_A1 = tmem_base + 320;    // DKV: dK   DQ: PK = P K (row-sum correction)
 
   int n_active = 0;
-  for (int t = 0; t < p.n_t; ++t) n_active += (cls_of(t) != 0);
+  for (int t = 0; t < n_t; ++t) n_active += (cls_of(t) != 0);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0 && n_active > 0) {
       mbar_expect_tx(fix_full, 32768);
       if (DKV) {
-        tma_load_3d(sFix0, &tmQKV, fix_full, p.k_col0 + h * 64, tile * 128, n);
-        tma_load_3d(sFix1, &tmQKV, fix_full, p.v_col0 + h * 64, tile * 128, n);
+        tma_load_3d(sFix0, &tmQKV, fix_full, p.k_col0 + h * 64, row_base, n);
+        tma_load_3d(sFix1, &tmQKV, fix_full, p.v_col0 + h * 64, row_base, n);
       } else {
-        tma_load_3d(sFix0, &tmQKV, fix_full, p.q_col0 + h * 64, tile * 128, n);
-        tma_load_3d(sFix1, &tmDO, fix_full, h * 64, tile * 128, n);
+        tma_load_3d(sFix0, &tmQKV, fix_full, p.q_col0 + h * 64, row_base, n);
+        tma_load_3d(sFix1, &tmDO, fix_full, h * 64, row_base, n);
       }
       int it = 0;
-      for (int t = 0; t < p.n_t; ++t) {
+      for (int t = 0; t < n_t; ++t) {
         if (cls_of(t) == 0) continue;
         const int st = it & 1;
         mbar_wait(&str_empty[st], ((it >> 1) & 1) ^ 1);
         mbar_expect_tx(&str_full[st], 32768);
         if (DKV) {
-          tma_load_3d(sStr + st * 32768, &tmQKV, &str_full[st], p.q_col0 + h * 64, t * 128, n);
-          tma_load_3d(sStr + st * 32768 + 16384, &tmDO, &str_full[st], h * 64, t * 128, n);
+          tma_load_3d(sStr + st * 32768, &tmQKV, &str_full[st], p.q_col0 + h * 64, ts[t], n);
+          tma_load_3d(sStr + st * 32768 + 16384, &tmDO, &str_full[st], h * 64, ts[t], n);
         } else {
-          tma_load_3d(sStr + st * 32768, &tmQKV, &str_full[st], p.k_col0 + h * 64, t * 128, n);
-          tma_load_3d(sStr + st * 32768 + 16384, &tmQKV, &str_full[st], p.v_col0 + h * 64, t * 128, n);
+          tma_load_3d(sStr + st * 32768, &tmQKV, &str_full[st], p.k_col0 + h * 64, ts[t], n);
+          tma_load_3d(sStr + st * 32768 + 16384, &tmQKV, &str_full[st], p.v_col0 + h * 64, ts[t], n);
         }
         ++it;
       }
@@ -210,24 +231,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
     float eps_run = 0.f;   // DQ: sum_k P (dP - D) of this thread's query row
     int it = 0;
-    for (int t = 0; t < p.n_t; ++t) {
+    for (int t = 0; t < n_t; ++t) {
       const int cls = cls_of(t);
       if (cls == 0) continue;
       const int qt = DKV ? t : tile;
       const int kt = DKV ? tile : t;
-      const int q_row = qt * 128 + r;
-      const bool row_ok = q_row < p.S;
+      const int q_row = ts[qt] + r;
+      const bool row_ok = r < ts[qt + 1] - ts[qt];
       float lse2 = 0.f, dsum = 0.f;
       uint32_t mw[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
       if (row_ok) {
         const size_t li = (static_cast<size_t>(n) * p.H + h) * p.S + q_row;
         lse2 = p.lse[li] * 1.4426950408889634f;
         dsum = p.dsum[li];
-        if (cls == 2) {
-          const uint4 v = *reinterpret_cast<const uint4*>(
-              p.mask_bits + (static_cast<size_t>(n) * p.S + q_row) * p.mask_words + kt * 4);
-          mw[0] = v.x; mw[1] = v.y; mw[2] = v.z; mw[3] = v.w;
-        }
+        if (cls == 2)
+          load_mask_words_bwd(p.mask_bits + (static_cast<size_t>(n) * p.S + q_row) * p.mask_words, ts[kt],
+                              ts[kt + 1] - ts[kt], mw);
       } else {
         mw[0] = mw[1] = mw[2] = mw[3] = 0u;
       }
@@ -275,12 +294,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     }
 
     // ---- epilogue: this thread owns output row `tile*128 + r`
-    const int out_row = tile * 128 + r;
+    const int out_row = row_base + r;
     if (n_active > 0) {
       mbar_wait(acc_full, 0);
       tc_fence_after();
     }
-    const bool ok = out_row < p.S;
+    const bool ok = r < row_len;
     const long long grow = static_cast<long long>(n) * p.S + out_row;
     const int pos = ok ? p.pos[grow] : 0;
     const float* cs = p.cos_tab + static_cast<long long>(pos) * 32;
@@ -394,7 +413,7 @@ static int launch_bwd(const CUtensorMap& tmQKV, const CUtensorMap& tmDO, const A
     }
     attr_set = true;
   }
-  dim3 grid(p.n_t, p.H, p.N);
+  dim3 grid(p.max_tiles, p.H, p.N);
   kern<<<grid, kBwdThreads, L::kTotal, s>>>(tmQKV, tmDO, p);
   return check_launch(DKV ? "attn_bwd_kernel<dkv>" : "attn_bwd_kernel<dq>");
 }
@@ -406,10 +425,10 @@ using namespace ggpt;
 extern "C" {
 
 int ggpt_attn_bwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int v_col0, const void* out, long long ldo,
-                  const void* dout, long long lddo, const float* lse, const uint32_t* mask_bits, const uint8_t* tile_cls,
-                  const int* pos, const float* cos_tab, const float* sin_tab, float* dsum_scratch, void* dqkv,
+                  const void* dout, long long lddo, const float* lse, const uint32_t* mask_bits, const int* tile_start,
+                  const int* n_tiles, const uint8_t* tile_cls, const int* pos, const float* cos_tab, const float* sin_tab, float* dsum_scratch, void* dqkv,
                   long long ld_dqkv, int N, int S, int H, void* stream) {
-  GGPT_REQUIRE(qkv && out && dout && lse && mask_bits && tile_cls && pos && cos_tab && sin_tab && dsum_scratch && dqkv,
+  GGPT_REQUIRE(qkv && out && dout && lse && mask_bits && tile_start && n_tiles && tile_cls && pos && cos_tab && sin_tab && dsum_scratch && dqkv,
                "attn_bwd: null pointer");
   GGPT_REQUIRE(N > 0 && S > 0 && H > 0, "attn_bwd: empty problem");
   GGPT_REQUIRE(ld_qkv % 8 == 0 && ldo % 8 == 0 && lddo % 8 == 0 && ld_dqkv % 8 == 0, "attn_bwd: ld must be multiples of 8");
@@ -428,9 +447,10 @@ int ggpt_attn_bwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int
     return rc;
   AttnBwdParams p{};
   p.N = N; p.S = S; p.H = H;
-  p.n_t = (S + 127) / 128;
+  p.max_tiles = ggpt_attn_max_tiles(S);
   p.mask_words = ggpt_attn_mask_words(S);
-  p.mask_bits = mask_bits; p.tile_cls = tile_cls; p.lse = lse; p.dsum = dsum_scratch;
+  p.mask_bits = mask_bits; p.tile_start = tile_start; p.n_tiles = n_tiles; p.tile_cls = tile_cls; p.lse = lse;
+  p.dsum = dsum_scratch;
   p.dqkv = static_cast<__nv_bfloat16*>(dqkv); p.ld = ld_dqkv;
   p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
   p.pos = pos; p.cos_tab = cos_tab; p.sin_tab = sin_tab;

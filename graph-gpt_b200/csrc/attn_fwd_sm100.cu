@@ -4,9 +4,15 @@
 //
 // The reference materialises an additive [N,1,S,S] mask (0 / finfo.min) and runs matmul-softmax-matmul
 // (HF:199-221 eager_attention_forward; mask from modeling_helpers.py:38-64).  Here the mask is a bit matrix
-// (1 bit per (q,k), built once per step by ggpt_attn_mask_build) plus a per-128x128-tile class
+// (1 bit per (q,k), built once per step by ggpt_attn_mask_build) plus a per-tile-pair class
 // (0 = all masked -> tile skipped, 1 = all visible -> no mask loads, 2 = mixed), which covers right-padding,
 // block-diagonal packing, causal and any other 2-D/3-D mask the reference accepts without an O(S^2) fp tensor.
+//
+// Row tiles are VARIABLE: each sequence is cut into tiles of <= 128 rows (shared by queries and keys) and a cut is
+// placed on a block boundary of the mask (no visible pair straddles it) whenever one exists 64..128 rows after the
+// previous cut.  Packed Eulerian-path segments (~24 rows) therefore never straddle a tile: every query tile sees
+// exactly one key tile, instead of the ~3 an aligned 128-grid gives.  Dense / padded / causal masks have no interior
+// boundaries and fall back to the uniform grid.
 //
 // One CTA per (128-query tile, head, sequence); 6 warps: TMA producer, MMA issuer, 4 softmax warps (one query row
 // per thread).  QK^T and PV run on tcgen05 with accumulators in TMEM; P goes through shared memory (bf16, 128B
@@ -25,16 +31,33 @@ constexpr int kAttSmem = 16384 /*Q*/ + 2 * 16384 /*K*/ + 2 * 16384 /*V*/ + 32768
 
 struct AttnFwdParams {
   int N, S, H;
-  int n_qt, n_kt;
-  int mask_words;             // uint32 words per mask row (multiple of 4)
+  int max_tiles;              // allocation stride of the tile arrays (= ceil(S/64))
+  int mask_words;             // uint32 words per mask row (multiple of 4, padded by 4)
   const uint32_t* mask_bits;  // [N, S, mask_words]
-  const uint8_t* tile_cls;    // [N, n_qt, n_kt]
+  const int* tile_start;      // [N, max_tiles+1]  row offsets of the variable row tiles
+  const int* n_tiles;         // [N]
+  const uint8_t* tile_cls;    // [N, max_tiles, max_tiles]  (query tile, key tile)
   __nv_bfloat16* out;         // [N*S, H*64]
   long long ldo;
   float* lse;                 // [N, H, S]  natural-log logsumexp of the scaled scores (for backward)
   int q_col0, k_col0, v_col0; // column offsets of q/k/v inside the fused qkv row
   float scale_log2;           // (1/sqrt(64)) * log2(e)
 };
+
+// 128 mask bits of query row `mrow` for the key tile starting at key k0 (any alignment) with klen valid keys.
+__device__ __forceinline__ void load_mask_words(const uint32_t* __restrict__ mrow, int k0, int klen, uint32_t (&mw)[4]) {
+  const int w0 = k0 >> 5, sh = k0 & 31;
+  uint32_t w[5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) w[i] = mrow[w0 + i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t v = __funnelshift_r(w[i], w[i + 1], sh);
+    const int nvalid = klen - 32 * i;
+    const uint32_t keep = nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u));
+    mw[i] = v & keep;
+  }
+}
 
 __global__ void __launch_bounds__(kAttThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p) {
@@ -55,7 +78,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
-  const uint8_t* cls_row = p.tile_cls + (static_cast<size_t>(n) * p.n_qt + qt) * p.n_kt;
+  const int n_kt = p.n_tiles[n];
+  if (qt >= n_kt) return;                       // uniform for the whole CTA, before any barrier / TMEM state
+  const int* ts = p.tile_start + static_cast<size_t>(n) * (p.max_tiles + 1);
+  const int q0 = ts[qt], qlen = ts[qt + 1] - q0;
+  const uint8_t* cls_row = p.tile_cls + (static_cast<size_t>(n) * p.max_tiles + qt) * p.max_tiles;
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0) {
@@ -88,15 +115,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
     // ===================== TMA producer =====================
     if (lane == 0) {
       mbar_expect_tx(q_full, 16384);
-      tma_load_3d(sQ, &tmQKV, q_full, p.q_col0 + h * kHeadDim, qt * kTileQ, n);
+      tma_load_3d(sQ, &tmQKV, q_full, p.q_col0 + h * kHeadDim, q0, n);
       int it = 0;
-      for (int kt = 0; kt < p.n_kt; ++kt) {
+      for (int kt = 0; kt < n_kt; ++kt) {
         if (cls_row[kt] == 0) continue;
         const int st = it & 1;
         mbar_wait(&kv_empty[st], ((it >> 1) & 1) ^ 1);
         mbar_expect_tx(&kv_full[st], 32768);
-        tma_load_3d(sK + st * 16384, &tmQKV, &kv_full[st], p.k_col0 + h * kHeadDim, kt * kTileK, n);
-        tma_load_3d(sV + st * 16384, &tmQKV, &kv_full[st], p.v_col0 + h * kHeadDim, kt * kTileK, n);
+        tma_load_3d(sK + st * 16384, &tmQKV, &kv_full[st], p.k_col0 + h * kHeadDim, ts[kt], n);
+        tma_load_3d(sV + st * 16384, &tmQKV, &kv_full[st], p.v_col0 + h * kHeadDim, ts[kt], n);
         ++it;
       }
     }
@@ -115,7 +142,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
         tc_commit(s_full);
       };
       int n_active = 0;
-      for (int kt = 0; kt < p.n_kt; ++kt) n_active += (cls_row[kt] != 0);
+      for (int kt = 0; kt < n_kt; ++kt) n_active += (cls_row[kt] != 0);
       if (n_active > 0) {
         mbar_wait(q_full, 0);
         mbar_wait(&kv_full[0], 0);
@@ -145,8 +172,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
     // ===================== softmax / epilogue warps: one query row per thread =====================
     const int quad = warp & 3;
     const int r = quad * 32 + lane;              // row inside the tile
-    const int q_row = qt * kTileQ + r;
-    const bool row_ok = q_row < p.S;
+    const int q_row = q0 + r;
+    const bool row_ok = r < qlen;
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t* mrow = p.mask_bits + (static_cast<size_t>(n) * p.S + (row_ok ? q_row : 0)) * p.mask_words;
 
@@ -157,14 +184,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
     float l_run = 0.f;
 
     int it = 0;
-    for (int kt = 0; kt < p.n_kt; ++kt) {
+    for (int kt = 0; kt < n_kt; ++kt) {
       const int cls = cls_row[kt];
       if (cls == 0) continue;
       uint32_t mw[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
       if (cls == 2) {
         if (row_ok) {
-          const uint4 v = *reinterpret_cast<const uint4*>(mrow + kt * 4);
-          mw[0] = v.x; mw[1] = v.y; mw[2] = v.z; mw[3] = v.w;
+          load_mask_words(mrow, ts[kt], ts[kt + 1] - ts[kt], mw);
         } else {
           mw[0] = mw[1] = mw[2] = mw[3] = 0u;
         }
@@ -290,32 +316,95 @@ __global__ void attn_mask_bits_kernel(const long long* __restrict__ am, int am_d
   if (lane == 0) bits[gw] = word;
 }
 
-__global__ void attn_tile_cls_kernel(const uint32_t* __restrict__ bits, int N, int S, int mask_words, int n_qt, int n_kt,
+// Row-tile plan for one sequence (one CTA per sequence).  lo/hi = first/last visible key of each query row;
+// r is a block boundary iff no visible pair straddles it: max_{q<r} hi[q] < r and min_{q>=r} lo[q] >= r.
+__global__ void attn_plan_kernel(const uint32_t* __restrict__ bits, int S, int mask_words, int max_tiles,
+                                 int* __restrict__ tile_start, int* __restrict__ n_tiles) {
+  extern __shared__ int s_plan[];   // lo[S], hi[S]
+  int* lo = s_plan;
+  int* hi = s_plan + S;
+  const int n = blockIdx.x;
+  const int nw = (S + 31) / 32;
+  for (int q = threadIdx.x; q < S; q += blockDim.x) {
+    const uint32_t* row = bits + (static_cast<size_t>(n) * S + q) * mask_words;
+    int l = 0x7fffffff, h = -1;
+    for (int w = 0; w < nw; ++w) {
+      const uint32_t v = row[w];
+      if (v) {
+        if (l == 0x7fffffff) l = w * 32 + (__ffs(v) - 1);
+        h = w * 32 + (31 - __clz(v));
+      }
+    }
+    lo[q] = l;
+    hi[q] = h;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {          // inclusive prefix max of hi
+    int m = -1;
+    for (int q = 0; q < S; ++q) {
+      m = max(m, hi[q]);
+      hi[q] = m;
+    }
+  } else if (threadIdx.x == 32) {  // inclusive suffix min of lo
+    int m = 0x7fffffff;
+    for (int q = S - 1; q >= 0; --q) {
+      m = min(m, lo[q]);
+      lo[q] = m;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int* ts = tile_start + static_cast<size_t>(n) * (max_tiles + 1);
+    int start = 0, t = 0;
+    while (start < S) {
+      int end = min(start + 128, S);
+      if (end < S) {
+        for (int b = end; b >= start + 64; --b) {
+          if (hi[b - 1] < b && lo[b] >= b) {
+            end = b;
+            break;
+          }
+        }
+      }
+      ts[t++] = start;
+      start = end;
+    }
+    ts[t] = S;
+    n_tiles[n] = t;
+  }
+}
+
+// class of every (query tile, key tile) pair: one warp per pair
+__global__ void attn_tile_cls_kernel(const uint32_t* __restrict__ bits, int N, int S, int mask_words, int max_tiles,
+                                     const int* __restrict__ tile_start, const int* __restrict__ n_tiles,
                                      uint8_t* __restrict__ cls) {
-  // one warp per (n, qt, kt): lane handles rows lane, lane+32, ...
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (gw >= N * n_qt * n_kt) return;
-  const int kt = gw % n_kt;
-  const int qt = (gw / n_kt) % n_qt;
-  const int n = gw / (n_kt * n_qt);
+  if (gw >= N * max_tiles * max_tiles) return;
+  const int kt = gw % max_tiles;
+  const int qt = (gw / max_tiles) % max_tiles;
+  const int n = gw / (max_tiles * max_tiles);
+  const int nt = n_tiles[n];
+  if (qt >= nt || kt >= nt) {
+    if (lane == 0) cls[gw] = 0;
+    return;
+  }
+  const int* ts = tile_start + static_cast<size_t>(n) * (max_tiles + 1);
+  const int q0 = ts[qt], qlen = ts[qt + 1] - q0, k0 = ts[kt], klen = ts[kt + 1] - k0;
   uint32_t any = 0, all = 0xffffffffu;
-  for (int r = lane; r < 128; r += 32) {
-    const int q = qt * 128 + r;
-    if (q < S) {
-      const uint4 v = *reinterpret_cast<const uint4*>(bits + (static_cast<size_t>(n) * S + q) * mask_words + kt * 4);
-      any |= v.x | v.y | v.z | v.w;
-      all &= v.x & v.y & v.z & v.w;
-    } else {
-      all = 0;
-    }
+  for (int r = lane; r < qlen; r += 32) {
+    uint32_t mw[4];
+    load_mask_words(bits + (static_cast<size_t>(n) * S + q0 + r) * mask_words, k0, klen, mw);
+    any |= mw[0] | mw[1] | mw[2] | mw[3];
+    all &= mw[0] & mw[1] & mw[2] & mw[3];
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     any |= __shfl_xor_sync(0xffffffffu, any, o);
     all &= __shfl_xor_sync(0xffffffffu, all, o);
   }
-  if (lane == 0) cls[gw] = (any == 0) ? 0 : ((all == 0xffffffffu) ? 1 : 2);
+  const bool full = (qlen == 128) && (klen == 128) && (all == 0xffffffffu);
+  if (lane == 0) cls[gw] = (any == 0) ? 0 : (full ? 1 : 2);
 }
 
 }  // namespace ggpt
@@ -324,30 +413,43 @@ using namespace ggpt;
 
 extern "C" {
 
-int ggpt_attn_mask_words(int S) { return ((S + 127) / 128) * 4; }
+int ggpt_attn_mask_words(int S) { return ((S + 127) / 128) * 4 + 4; }
+
+int ggpt_attn_max_tiles(int S) { return (S + 63) / 64; }
 
 int ggpt_attn_mask_build(const long long* attention_mask, int mask_dims, int N, int S, int causal, uint32_t* mask_bits,
-                         uint8_t* tile_cls, void* stream) {
+                         int* tile_start, int* n_tiles, uint8_t* tile_cls, void* stream) {
   GGPT_REQUIRE(N > 0 && S > 0, "attn_mask_build: empty batch");
   GGPT_REQUIRE(attention_mask == nullptr || mask_dims == 2 || mask_dims == 3,
                "attention_mask of %d dims is not implemented (expected [N,S] or [N,S,S])", mask_dims);
-  GGPT_REQUIRE(mask_bits && tile_cls, "attn_mask_build: null output");
+  GGPT_REQUIRE(mask_bits && tile_start && n_tiles && tile_cls, "attn_mask_build: null output");
+  GGPT_REQUIRE(S <= 16384, "attn_mask_build: S=%d exceeds the plan kernel's shared-memory budget", S);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int words = ggpt_attn_mask_words(S);
-  const int nt = (S + 127) / 128;
+  const int mt = ggpt_attn_max_tiles(S);
   const long long warps = static_cast<long long>(N) * S * words;
   const long long blocks = (warps * 32 + 255) / 256;
   attn_mask_bits_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(attention_mask, mask_dims, N, S, causal, words,
                                                                        mask_bits);
   if (int rc = check_launch("attn_mask_bits_kernel")) return rc;
-  const int warps2 = N * nt * nt;
-  attn_tile_cls_kernel<<<(warps2 * 32 + 255) / 256, 256, 0, s>>>(mask_bits, N, S, words, nt, nt, tile_cls);
+  const size_t plan_smem = 2 * static_cast<size_t>(S) * sizeof(int);
+  static bool attr_set = false;
+  if (!attr_set && plan_smem > 48 * 1024) {
+    cudaFuncSetAttribute(attn_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    attr_set = true;
+  }
+  attn_plan_kernel<<<N, 256, plan_smem, s>>>(mask_bits, S, words, mt, tile_start, n_tiles);
+  if (int rc = check_launch("attn_plan_kernel")) return rc;
+  const long long warps2 = static_cast<long long>(N) * mt * mt;
+  attn_tile_cls_kernel<<<static_cast<unsigned>((warps2 * 32 + 255) / 256), 256, 0, s>>>(mask_bits, N, S, words, mt,
+                                                                                         tile_start, n_tiles, tile_cls);
   return check_launch("attn_tile_cls_kernel");
 }
 
 int ggpt_attn_fwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int v_col0, const uint32_t* mask_bits,
-                  const uint8_t* tile_cls, void* out, long long ldo, float* lse, int N, int S, int H, void* stream) {
-  GGPT_REQUIRE(qkv && mask_bits && tile_cls && out, "attn_fwd: null pointer");
+                  const int* tile_start, const int* n_tiles, const uint8_t* tile_cls, void* out, long long ldo, float* lse,
+                  int N, int S, int H, void* stream) {
+  GGPT_REQUIRE(qkv && mask_bits && tile_start && n_tiles && tile_cls && out, "attn_fwd: null pointer");
   GGPT_REQUIRE(N > 0 && S > 0 && H > 0, "attn_fwd: empty problem");
   GGPT_REQUIRE(ld_qkv % 8 == 0 && ldo % 8 == 0 && q_col0 % 8 == 0 && k_col0 % 8 == 0 && v_col0 % 8 == 0,
                "attn_fwd: leading dimensions / column offsets must be multiples of 8");
@@ -355,10 +457,9 @@ int ggpt_attn_fwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int
   if (int rc = make_tmap_3d_bf16(&tm, qkv, N, S, ld_qkv, static_cast<uint64_t>(S) * ld_qkv, ld_qkv, 128, 64)) return rc;
   AttnFwdParams p{};
   p.N = N; p.S = S; p.H = H;
-  p.n_qt = (S + 127) / 128;
-  p.n_kt = p.n_qt;
+  p.max_tiles = ggpt_attn_max_tiles(S);
   p.mask_words = ggpt_attn_mask_words(S);
-  p.mask_bits = mask_bits; p.tile_cls = tile_cls;
+  p.mask_bits = mask_bits; p.tile_start = tile_start; p.n_tiles = n_tiles; p.tile_cls = tile_cls;
   p.out = static_cast<__nv_bfloat16*>(out); p.ldo = ldo; p.lse = lse;
   p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
@@ -371,7 +472,7 @@ int ggpt_attn_fwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int
     }
     attr_set = true;
   }
-  dim3 grid(p.n_qt, H, N);
+  dim3 grid(p.max_tiles, H, N);
   attn_fwd_kernel<<<grid, kAttThreads, kAttSmem, static_cast<cudaStream_t>(stream)>>>(tm, p);
   return check_launch("attn_fwd_kernel");
 }

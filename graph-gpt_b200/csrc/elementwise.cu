@@ -243,8 +243,13 @@ __global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ dact, const _
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float2 a = unpack_bf16(dau[j]), g = unpack_bf16(gvu[j]), u = unpack_bf16(uvu[j]);
-      og[j] = pack_bf16(a.x * u.x * gelu_erf_grad(g.x), a.y * u.y * gelu_erf_grad(g.y));
-      ou[j] = pack_bf16(a.x * gelu_erf(g.x), a.y * gelu_erf(g.y));
+      // one erf per element: cdf = Phi(g); gelu = g*cdf; gelu' = cdf + g*phi(g)
+      const float cx = 0.5f * (1.0f + erff(g.x * 0.70710678118654752f));
+      const float cy = 0.5f * (1.0f + erff(g.y * 0.70710678118654752f));
+      const float px = 0.3989422804014327f * __expf(-0.5f * g.x * g.x);
+      const float py = 0.3989422804014327f * __expf(-0.5f * g.y * g.y);
+      og[j] = pack_bf16(a.x * u.x * (cx + g.x * px), a.y * u.y * (cy + g.y * py));
+      ou[j] = pack_bf16(a.x * g.x * cx, a.y * g.y * cy);
     }
     *reinterpret_cast<uint4*>(dgu + t * 2 * I + c) = make_uint4(og[0], og[1], og[2], og[3]);
     *reinterpret_cast<uint4*>(dgu + t * 2 * I + I + c) = make_uint4(ou[0], ou[1], ou[2], ou[3]);

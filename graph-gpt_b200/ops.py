@@ -110,16 +110,18 @@ def gemm_qkv_rope(a, wqkv, pos, cos_tab, sin_tab, rope_cols):
 class AttnMask:
     """Bit-matrix form of the reference's additive attention mask (built once per step, shared by all layers)."""
 
-    def __init__(self, bits, cls, N, S):
-        self.bits, self.cls, self.N, self.S = bits, cls, N, S
+    def __init__(self, bits, tile_start, n_tiles, cls, N, S):
+        self.bits, self.tile_start, self.n_tiles, self.cls, self.N, self.S = bits, tile_start, n_tiles, cls, N, S
 
 
 def attn_mask_build(attention_mask, N, S, causal, device):
     """attention_mask: None, int64 [N,S] or int64 [N,S,S] (modeling_helpers.py:38-64)."""
     words = lib.ggpt_attn_mask_words(S)
-    nt = (S + 127) // 128
+    mt = lib.ggpt_attn_max_tiles(S)
     bits = torch.empty((N, S, words), device=device, dtype=torch.int32)
-    cls = torch.empty((N, nt, nt), device=device, dtype=torch.uint8)
+    tile_start = torch.empty((N, mt + 1), device=device, dtype=torch.int32)
+    n_tiles = torch.empty((N,), device=device, dtype=torch.int32)
+    cls = torch.empty((N, mt, mt), device=device, dtype=torch.uint8)
     dims = 0
     if attention_mask is not None:
         if attention_mask.dim() not in (2, 3):
@@ -131,8 +133,9 @@ def attn_mask_build(attention_mask, N, S, causal, device):
         dims = attention_mask.dim()
         if attention_mask.shape[0] != N or attention_mask.shape[-1] != S:
             raise RuntimeError(f"attention_mask shape {tuple(attention_mask.shape)} does not match N={N}, S={S}")
-    lib.ggpt_attn_mask_build(_ptr(attention_mask), dims, N, S, int(bool(causal)), bits.data_ptr(), cls.data_ptr(), _stream())
-    return AttnMask(bits, cls, N, S)
+    lib.ggpt_attn_mask_build(_ptr(attention_mask), dims, N, S, int(bool(causal)), bits.data_ptr(), tile_start.data_ptr(),
+                             n_tiles.data_ptr(), cls.data_ptr(), _stream())
+    return AttnMask(bits, tile_start, n_tiles, cls, N, S)
 
 
 def attn_fwd(qkv, mask: AttnMask, H, *, want_lse=True):
@@ -144,8 +147,9 @@ def attn_fwd(qkv, mask: AttnMask, H, *, want_lse=True):
         raise RuntimeError(f"attn_fwd: qkv shape {tuple(qkv.shape)} does not match N={N} S={S} H={H}")
     out = torch.empty((N * S, d), device=qkv.device, dtype=BF16)
     lse = torch.empty((N, H, S), device=qkv.device, dtype=F32) if want_lse else None
-    lib.ggpt_attn_fwd(qkv.data_ptr(), qkv.stride(0), 0, d, 2 * d, mask.bits.data_ptr(), mask.cls.data_ptr(),
-                      out.data_ptr(), out.stride(0), _ptr(lse), N, S, H, _stream())
+    lib.ggpt_attn_fwd(qkv.data_ptr(), qkv.stride(0), 0, d, 2 * d, mask.bits.data_ptr(), mask.tile_start.data_ptr(),
+                      mask.n_tiles.data_ptr(), mask.cls.data_ptr(), out.data_ptr(), out.stride(0), _ptr(lse), N, S, H,
+                      _stream())
     return out, lse
 
 
@@ -159,7 +163,8 @@ def attn_bwd(dout, qkv, out, lse, mask: AttnMask, H, pos, cos_tab, sin_tab):
     dqkv = torch.empty_like(qkv)
     dsum = torch.empty((N, H, S), device=qkv.device, dtype=F32)
     lib.ggpt_attn_bwd(qkv.data_ptr(), qkv.stride(0), 0, d, 2 * d, out.data_ptr(), out.stride(0), dout.data_ptr(),
-                      dout.stride(0), lse.data_ptr(), mask.bits.data_ptr(), mask.cls.data_ptr(), pos.data_ptr(),
+                      dout.stride(0), lse.data_ptr(), mask.bits.data_ptr(), mask.tile_start.data_ptr(),
+                      mask.n_tiles.data_ptr(), mask.cls.data_ptr(), pos.data_ptr(),
                       cos_tab.data_ptr(), sin_tab.data_ptr(), dsum.data_ptr(), dqkv.data_ptr(), dqkv.stride(0), N, S, H,
                       _stream())
     return dqkv

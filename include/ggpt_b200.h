@@ -66,30 +66,36 @@ int ggpt_gemm_bf16_qkv_rope(const void* A, long long lda, const void* Wqkv, long
  * Attention.  qkv is the fused projection output [N*S, ld_qkv] (bf16); q/k/v of head h live at columns
  * {q,k,v}_col0 + 64*h.  The mask is a bit matrix built once per step.
  * ------------------------------------------------------------------------------------------- */
-/* uint32 words per mask row for sequence length S (multiple of 4 = one 128-key tile per uint4). */
+/* uint32 words per mask row for sequence length S (one uint4 per 128 keys + 4 pad words so unaligned 128-key
+ * windows can be read), and the allocation stride of the per-sequence tile arrays (= ceil(S/64)). */
 int ggpt_attn_mask_words(int S);
+int ggpt_attn_max_tiles(int S);
 
 /* attention_mask: int64 [N,S] (key padding mask) if mask_dims == 2, [N,S,S] if 3, or NULL (all visible);
- * causal != 0 additionally hides keys k > q.  Outputs mask_bits [N,S,words] and tile_cls [N,nT,nT]
- * (nT = ceil(S/128); 0 = tile fully masked, 1 = fully visible, 2 = mixed).
+ * causal != 0 additionally hides keys k > q.  Outputs:
+ *   mask_bits  [N,S,words]            1 bit per (q,k)
+ *   tile_start [N,max_tiles+1], n_tiles [N]   variable row tiles (<= 128 rows, cut on block boundaries of the mask so
+ *                                     packed segments never straddle a tile; uniform 128 grid otherwise)
+ *   tile_cls   [N,max_tiles,max_tiles] class of every (query tile, key tile): 0 masked, 1 fully visible, 2 mixed
  * ref: modeling_helpers.py:38-64 (_update_causal_mask, _expand_mask_from_3d_mask: additive 0/finfo.min mask),
- *      HF:398-405 (causal mask when config.causal_attention).  Fully masked query rows yield 0 here (the
- *      reference yields a uniform average; such rows are padding and never consumed). */
+ *      HF:398-405 (causal mask when config.causal_attention); packing: tokenizer_utils.py:351-355.  Fully masked
+ *      query rows yield 0 here (the reference yields a uniform average; such rows are padding, never consumed). */
 int ggpt_attn_mask_build(const long long* attention_mask, int mask_dims, int N, int S, int causal, uint32_t* mask_bits,
-                         uint8_t* tile_cls, void* stream);
+                         int* tile_start, int* n_tiles, uint8_t* tile_cls, void* stream);
 
 /* out[N*S, H*64] = softmax(q k^T / 8 + mask) v per head; lse[N,H,S] (may be NULL) = log-sum-exp of the scaled
  * scores, kept for the backward pass.   ref: HF:199-221 (eager_attention_forward), fp32 softmax. */
 int ggpt_attn_fwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int v_col0, const uint32_t* mask_bits,
-                  const uint8_t* tile_cls, void* out, long long ldo, float* lse, int N, int S, int H, void* stream);
+                  const int* tile_start, const int* n_tiles, const uint8_t* tile_cls, void* out, long long ldo, float* lse,
+                  int N, int S, int H, void* stream);
 
 /* dqkv[N*S, ld_dqkv] (bf16) = gradient of the fused q|k|v projection output given dout = dL/d(attention output).
  * Recomputes P from lse; two deterministic tcgen05 passes (dK,dV then dQ); dQ/dK are un-rotated (inverse RoPE)
  * with the same pos / cos / sin tables as ggpt_gemm_bf16_qkv_rope.  dsum_scratch: fp32 [N,H,S].
  * ref: autograd of HF:199-221 and HF:146-168. */
 int ggpt_attn_bwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int v_col0, const void* out, long long ldo,
-                  const void* dout, long long lddo, const float* lse, const uint32_t* mask_bits, const uint8_t* tile_cls,
-                  const int* pos, const float* cos_tab, const float* sin_tab, float* dsum_scratch, void* dqkv,
+                  const void* dout, long long lddo, const float* lse, const uint32_t* mask_bits, const int* tile_start,
+                  const int* n_tiles, const uint8_t* tile_cls, const int* pos, const float* cos_tab, const float* sin_tab, float* dsum_scratch, void* dqkv,
                   long long ld_dqkv, int N, int S, int H, void* stream);
 
 /* ---------------------------------------------------------------------------------------------

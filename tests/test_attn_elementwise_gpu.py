@@ -2,6 +2,7 @@
 the same op (the oracle's formulas).  Tolerances are stated per test."""
 import math
 
+import numpy as np
 import pytest
 import torch
 
@@ -307,3 +308,36 @@ def test_attn_bwd(N, S, H, kind, causal, rope):
         rel_f = ((a - b).norm() / (b.norm() + 1e-20)).item()
         # P and dS are rounded to bf16 before the gradient MMAs and outputs are bf16
         assert err <= 2e-2 * scale and rel_f <= 1e-2, f"{name}: max err {err} (scale {scale}), relF {rel_f}"
+
+
+def test_attn_tile_plan_packed_and_dense():
+    """Packed block-diagonal masks get row tiles cut on segment boundaries (each query tile sees only itself);
+    masks without interior block boundaries keep the uniform 128 grid."""
+    from graphgpt_b200 import ops, synth
+    b = synth.make_batch(3, 1024, layout="packed", seed=9, return_segments=True)
+    am = torch.from_numpy(b["attention_mask"]).cuda()
+    m = ops.attn_mask_build(am, 3, 1024, False, am.device)
+    torch.cuda.synchronize()
+    for n in range(3):
+        nt = int(m.n_tiles[n])
+        ts = m.tile_start[n, : nt + 1].tolist()
+        assert ts[0] == 0 and ts[-1] == 1024 and all(0 < b_ - a_ <= 128 for a_, b_ in zip(ts, ts[1:]))
+        bounds = set(np.cumsum([0] + b["segment_lens"][n]).tolist())
+        assert all(t in bounds for t in ts), "tile cuts must sit on segment boundaries"
+        assert nt <= 11
+        cls = m.cls[n, :nt, :nt].cpu()
+        assert (cls.diagonal() == 2).all() and (cls - torch.diag(cls.diagonal())).abs().sum() == 0
+    # dense / key-padding / causal: uniform grid
+    am2 = torch.ones((2, 1024), dtype=torch.long).cuda()
+    am2[1, 700:] = 0
+    for causal in (False, True):
+        m2 = ops.attn_mask_build(am2, 2, 1024, causal, am2.device)
+        assert m2.n_tiles.tolist() == [8, 8]
+        assert m2.tile_start[0, :9].tolist() == list(range(0, 1025, 128))
+        cls = m2.cls[0, :8, :8].cpu()
+        if causal:
+            assert (cls.triu(1) == 0).all() and (cls.diagonal() == 2).all() and (cls.tril(-1)[cls.tril(-1) > 0] == 1).all()
+        else:
+            assert (cls == 1).all()
+            cls1 = m2.cls[1, :8, :8].cpu()
+            assert (cls1[:, 6:] == 0).all() and (cls1[:, :5] == 1).all() and (cls1[:, 5] == 2).all()

@@ -28,7 +28,9 @@ def test_library_exports_every_declared_symbol():
     dll.ggpt_abi_version.restype = ctypes.c_int
     assert dll.ggpt_abi_version() == 1
     dll.ggpt_attn_mask_words.restype = ctypes.c_int
-    assert dll.ggpt_attn_mask_words(1024) == 32 and dll.ggpt_attn_mask_words(40) == 4
+    assert dll.ggpt_attn_mask_words(1024) == 36 and dll.ggpt_attn_mask_words(40) == 8
+    dll.ggpt_attn_max_tiles.restype = ctypes.c_int
+    assert dll.ggpt_attn_max_tiles(1024) == 16 and dll.ggpt_attn_max_tiles(40) == 1
 
 
 def test_argument_validation_without_gpu():
@@ -37,7 +39,7 @@ def test_argument_validation_without_gpu():
     with pytest.raises(RuntimeError, match="null operand"):
         lib.ggpt_gemm_bf16(0, 8, 0, 0, 8, 0, 0, 8, 0, 0, 128, 128, 64, 0)
     with pytest.raises(RuntimeError, match="not implemented"):
-        lib.ggpt_attn_mask_build(1, 4, 1, 8, 0, 1, 1, 0)
+        lib.ggpt_attn_mask_build(1, 4, 1, 8, 0, 1, 1, 1, 1, 0)
 
 
 def test_model_refuses_cpu_execution():
