@@ -154,7 +154,7 @@ __global__ void rmsnorm_fwd_kernel(const float* __restrict__ x, const float* __r
 // Each lane owns the same columns (lane*4 + k*128) for every row its warp visits, so the row is held in registers
 // (one HBM pass) and the dw partial sums stay in registers until one smem + global reduction per block.
 template <int NV>
-__global__ void __launch_bounds__(128, 4) rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const float* __restrict__ x,
+__global__ void __launch_bounds__(128, 3) rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const float* __restrict__ x,
                                    const float* __restrict__ rstd_in, const float* __restrict__ w,
                                    const float* __restrict__ dresid, float* __restrict__ dx_out,
                                    __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dw, long long T, int d) {
@@ -172,8 +172,15 @@ __global__ void __launch_bounds__(128, 4) rmsnorm_bwd_kernel(const __nv_bfloat16
     const float* xr = x + t * d;
     const __nv_bfloat16* dyr = dy + t * lddy;
     const float rstd = rstd_in[t];
-    float4 xs[NV], gv[NV];   // xhat and dy (then g = dy*w)
+    float4 xs[NV], gv[NV], rv[NV];   // xhat, dy (then g = dy*w), residual-path gradient
     float dot = 0.f;
+    // issue every load of the row (x, dy, dresid) before the reduction so three streams are in flight per warp
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = lane * 4 + k * 128;
+      rv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < d && dresid != nullptr) rv[k] = *reinterpret_cast<const float4*>(dresid + t * d + c);
+    }
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       const int c = lane * 4 + k * 128;
@@ -195,8 +202,7 @@ __global__ void __launch_bounds__(128, 4) rmsnorm_bwd_kernel(const __nv_bfloat16
     for (int k = 0; k < NV; ++k) {
       const int c = lane * 4 + k * 128;
       if (c < d) {
-        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (dresid != nullptr) r = *reinterpret_cast<const float4*>(dresid + t * d + c);
+        const float4 r = rv[k];
         float4 o;
         o.x = r.x + rstd * (gv[k].x - xs[k].x * dot);
         o.y = r.y + rstd * (gv[k].y - xs[k].y * dot);
@@ -620,7 +626,7 @@ int ggpt_rmsnorm_bwd(const void* dy, long long lddy, const float* x, const float
   GGPT_REQUIRE(dy && x && rstd && w && dx_out && dw, "rmsnorm_bwd: null pointer");
   GGPT_REQUIRE(T > 0 && d % 4 == 0 && lddy % 4 == 0, "rmsnorm_bwd: bad sizes");
   GGPT_REQUIRE(d <= 2048, "rmsnorm_bwd: hidden size %d > 2048 is not instantiated", d);
-  const int grid = grid_for_rows(T, 4, 8);
+  const int grid = grid_for_rows(T, 4, 12);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const __nv_bfloat16* dyb = static_cast<const __nv_bfloat16*>(dy);
   __nv_bfloat16* dxb = static_cast<__nv_bfloat16*>(dx_bf16);

@@ -14,8 +14,15 @@
 //   wgrad    dW = dy^T x : A = dy [T,out] MN-major, B = x [T,in]   MN-major      (K = T rows)
 // so no transposed copies of weights or activations are ever made.
 //
+// L2 -> SM bandwidth is the limiter of a 128x256x64 tile (48 KB per k-block per CTA ~ the measured ~10 TB/s LTS cap
+// at ~1.05 PFLOP/s), so CTAs run as clusters of two along M (CL = 2): both need the same B tile, each CTA fetches
+// half of it with TMA .multicast::cluster into both CTAs' smem (32 KB of L2 reads per k-block per CTA instead of 48),
+// and smem slots are released with a multicast tcgen05.commit that arrives on both CTAs' empty barriers.
+//
 // Replaces (reference, all via torch/cuBLAS): q/k/v/o_proj HF modeling_llama.py:262-264,288; gate/up/down_proj
 // HF:182-184; n_token_proj modeling_pretrain.py:89-93; lm_head modeling_pretrain.py:218; and their autograd.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "../../include/ggpt_b200.h"
 
@@ -60,7 +67,7 @@ struct GemmSmem {
   static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kBarBytes + 1024;  // +1024 alignment slack
 };
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
+template <int BN, bool A_MN, bool B_MN, int EPI, int CL>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using S = GemmSmem<BN>;
@@ -76,7 +83,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_blocks * p.num_n_blocks * p.num_splits;   // work items = (tile, k-split)
+  // work items = (m-block group of CL, n-block, k-split); the CTAs of a cluster take consecutive m-blocks
+  const int num_tiles = ((p.num_m_blocks + CL - 1) / CL) * p.num_n_blocks * p.num_splits;
+  const int rank = (CL > 1) ? static_cast<int>(cluster_ctarank()) : 0;
+  const int item0 = blockIdx.x / CL;
+  const int item_stride = gridDim.x / CL;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -84,7 +95,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CL);   // released by the MMA warp of every CTA that receives the multicast B tile
     }
     mbar_init(&tfull_bar[0], 1);
     mbar_init(&tfull_bar[1], 1);
@@ -97,7 +108,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tmem_relinquish();
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all();   // peers' barriers must be initialised before any multicast / remote arrive
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -106,9 +118,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+      for (int item = item0; item < num_tiles; item += item_stride) {
         const int tile = item / p.num_splits, split = item % p.num_splits;
-        const int m0 = (tile / p.num_n_blocks) * BM;
+        const int m0 = ((tile / p.num_n_blocks) * CL + rank) * BM;
         const int nb = tile % p.num_n_blocks;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
@@ -124,17 +136,33 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             tma_load_2d(sa, &tmA, &full_bar[stage], m0, k0);
             tma_load_2d(sa + 8192, &tmA, &full_bar[stage], m0 + 64, k0);
           }
-          if (EPI == EPI_GEGLU) {
-            // B rows: [gate tile | up tile], each BN/2 rows, from the two halves of the fused weight
-            const int nh = nb * (BN / 2);
-            tma_load_2d(sb, &tmB, &full_bar[stage], k0, nh);
-            tma_load_2d(sb + (BN / 2) * 128, &tmB, &full_bar[stage], k0, p.b_half_rows + nh);
-          } else if (!B_MN) {
-            tma_load_2d(sb, &tmB, &full_bar[stage], k0, nb * BN);
-          } else {
+          if (CL == 1) {
+            if (EPI == EPI_GEGLU) {
+              // B rows: [gate tile | up tile], each BN/2 rows, from the two halves of the fused weight
+              const int nh = nb * (BN / 2);
+              tma_load_2d(sb, &tmB, &full_bar[stage], k0, nh);
+              tma_load_2d(sb + (BN / 2) * 128, &tmB, &full_bar[stage], k0, p.b_half_rows + nh);
+            } else if (!B_MN) {
+              tma_load_2d(sb, &tmB, &full_bar[stage], k0, nb * BN);
+            } else {
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i)
-              tma_load_2d(sb + i * 8192, &tmB, &full_bar[stage], nb * BN + i * 64, k0);
+              for (int i = 0; i < BN / 64; ++i)
+                tma_load_2d(sb + i * 8192, &tmB, &full_bar[stage], nb * BN + i * 64, k0);
+            }
+          } else {
+            // this CTA fetches half `rank` of the B tile and multicasts it into both CTAs of the cluster
+            if (EPI == EPI_GEGLU) {
+              const int nh = nb * (BN / 2);
+              tma_load_2d_mc(sb + rank * (BN / 2) * 128, &tmB, &full_bar[stage], k0, rank ? p.b_half_rows + nh : nh, 3);
+            } else if (!B_MN) {
+              tma_load_2d_mc(sb + rank * (BN / 2) * 128, &tmB, &full_bar[stage], k0, nb * BN + rank * (BN / 2), 3);
+            } else {
+#pragma unroll
+              for (int i = 0; i < BN / 128; ++i) {
+                const int bi = rank * (BN / 128) + i;
+                tma_load_2d_mc(sb + bi * 8192, &tmB, &full_bar[stage], nb * BN + bi * 64, k0, 3);
+              }
+            }
           }
           if (++stage == kStages) {
             stage = 0;
@@ -151,7 +179,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+      for (int item = item0; item < num_tiles; item += item_stride) {
         const int split = item % p.num_splits;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
@@ -171,7 +199,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                         : umma_desc_sw128(sb + kk * 32, 16, 1024);
             tc_mma_bf16(d_tmem, adesc, bdesc, idesc, (kb != kb0 || kk != 0) ? 1u : 0u);
           }
-          tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (CL > 1) tc_commit_mc(&empty_bar[stage], 3);   // frees the slot in BOTH CTAs (multicast B lands in both)
+          else tc_commit(&empty_bar[stage]);                // frees the smem slot when these MMAs retire
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -214,9 +243,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     };
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+    for (int item = item0; item < num_tiles; item += item_stride) {
       const int tile = item / p.num_splits;
-      const int m0 = (tile / p.num_n_blocks) * BM;
+      const int m0 = ((tile / p.num_n_blocks) * CL + rank) * BM;
       const int nb = tile % p.num_n_blocks;
       const int row0 = m0 + quad * 32;                 // first global row of this warp's quadrant
       const int row = row0 + lane;                     // write-phase row of this thread
@@ -371,7 +400,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all();   // the peer may still multicast into this CTA's smem / arrive on its barriers
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 2 * BN);
@@ -381,8 +411,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // ---------------------------------------------------------------------------------------------
 // Host launcher
 // ---------------------------------------------------------------------------------------------
-template <int BN, bool A_MN, bool B_MN, int EPI>
-static int launch_gemm(const void* A, long long lda, const void* B, long long ldb, GemmParams p, cudaStream_t stream) {
+template <int BN, bool A_MN, bool B_MN, int EPI, int CL>
+static int launch_gemm_cl(const void* A, long long lda, const void* B, long long ldb, GemmParams p, cudaStream_t stream) {
   using S = GemmSmem<BN>;
   CUtensorMap tmA, tmB;
   int rc;
@@ -391,11 +421,52 @@ static int launch_gemm(const void* A, long long lda, const void* B, long long ld
   else rc = make_tmap_2d_bf16(&tmA, A, p.K, p.M, lda, 64, 64);
   if (rc) return rc;
   const uint64_t b_rows_total = static_cast<uint64_t>(p.N);
-  if (EPI == EPI_GEGLU) rc = make_tmap_2d_bf16(&tmB, B, b_rows_total, p.K, ldb, BN / 2, 64);
+  // B K-major: box = whole tile (CL 1) or the half this CTA multicasts (CL 2; GEGLU always loads gate/up halves)
+  if (EPI == EPI_GEGLU || (!B_MN && CL == 2)) rc = make_tmap_2d_bf16(&tmB, B, b_rows_total, p.K, ldb, BN / 2, 64);
   else if (!B_MN) rc = make_tmap_2d_bf16(&tmB, B, b_rows_total, p.K, ldb, BN, 64);
   else rc = make_tmap_2d_bf16(&tmB, B, p.K, b_rows_total, ldb, 64, 64);
   if (rc) return rc;
 
+  const int items = ((p.num_m_blocks + CL - 1) / CL) * p.num_n_blocks * p.num_splits;
+  int grid = num_sms() / CL * CL;
+  if (grid > items * CL) grid = items * CL;
+
+  auto kern = gemm_kernel<BN, A_MN, B_MN, EPI, CL>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+    if (e != cudaSuccess) {
+      set_error("gemm: cudaFuncSetAttribute(%d B smem) failed: %s", S::kTotal, cudaGetErrorString(e));
+      return -2;
+    }
+    attr_set = true;
+  }
+  if (CL == 1) {
+    kern<<<grid, kGemmThreads, S::kTotal, stream>>>(tmA, tmB, p);
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = S::kTotal;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
+    if (e != cudaSuccess) {
+      set_error("gemm: cluster launch failed: %s", cudaGetErrorString(e));
+      return -2;
+    }
+  }
+  return check_launch("gemm_kernel");
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+static int launch_gemm(const void* A, long long lda, const void* B, long long ldb, GemmParams p, cudaStream_t stream) {
   p.num_m_blocks = (p.M + BM - 1) / BM;
   if (EPI == EPI_GEGLU) p.num_n_blocks = (p.N / 2 + BN / 2 - 1) / (BN / 2);
   else p.num_n_blocks = (p.N + BN - 1) / BN;
@@ -413,22 +484,10 @@ static int launch_gemm(const void* A, long long lda, const void* B, long long ld
   }
   p.kb_per_split = (p.num_k_blocks + p.num_splits - 1) / p.num_splits;
   p.num_splits = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;   // no empty splits
-  const int tiles = p.num_m_blocks * p.num_n_blocks * p.num_splits;
-  int grid = num_sms();
-  if (grid > tiles) grid = tiles;
-
-  auto kern = gemm_kernel<BN, A_MN, B_MN, EPI>;
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
-    if (e != cudaSuccess) {
-      set_error("gemm: cudaFuncSetAttribute(%d B smem) failed: %s", S::kTotal, cudaGetErrorString(e));
-      return -2;
-    }
-    attr_set = true;
-  }
-  kern<<<grid, kGemmThreads, S::kTotal, stream>>>(tmA, tmB, p);
-  return check_launch("gemm_kernel");
+  // clusters of two CTAs along M share (multicast) the B tile; single m-block problems stay un-clustered
+  static const bool no_cluster = getenv("GGPT_GEMM_NO_CLUSTER") != nullptr;
+  if (p.num_m_blocks >= 2 && !no_cluster) return launch_gemm_cl<BN, A_MN, B_MN, EPI, 2>(A, lda, B, ldb, p, stream);
+  return launch_gemm_cl<BN, A_MN, B_MN, EPI, 1>(A, lda, B, ldb, p, stream);
 }
 
 template <int BN, int EPI>
