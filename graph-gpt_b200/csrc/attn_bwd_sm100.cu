@@ -16,6 +16,7 @@
 // 128x64x128 MMA per tile) and eps_q = sum_k P (dP - D) in registers, and emits dQ = dS K - eps_q/8 * PK, which is
 // the gradient for the exact D = sum_k P dP.  dK and dV have no such common-mode term (eps varies per query row).
 #include "common.cuh"
+#include "attn_diag.cuh"
 #include "../../include/ggpt_b200.h"
 
 namespace ggpt {
@@ -30,6 +31,7 @@ struct AttnBwdParams {
   const int* tile_start;      // [N, max_tiles+1]  variable row tiles (see attn_fwd_sm100.cu)
   const int* n_tiles;         // [N]
   const uint8_t* tile_cls;    // [N,max_tiles,max_tiles]  (query tile major)
+  const uint8_t* iso_flags;   // [N,max_tiles] tiles handled by attn_diag_bwd_kernel (may be NULL)
   const float* lse;           // [N,H,S]
   const float* dsum;          // [N,H,S]   D = rowsum(dO*O)
   __nv_bfloat16* dqkv;        // [N*S, ld]
@@ -94,6 +96,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const int tile = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
   const int n_t = p.n_tiles[n];
   if (tile >= n_t) return;                      // uniform for the whole CTA, before any barrier / TMEM state
+  if (p.iso_flags != nullptr && p.iso_flags[n * p.max_tiles + tile]) return;   // done by attn_diag_bwd_kernel
   const int* ts = p.tile_start + static_cast<size_t>(n) * (p.max_tiles + 1);
   const int row_base = ts[tile], row_len = ts[tile + 1] - row_base;   // rows of the fixed tile
   const uint8_t* cls_n = p.tile_cls + static_cast<size_t>(n) * p.max_tiles * p.max_tiles;
@@ -426,7 +429,8 @@ extern "C" {
 
 int ggpt_attn_bwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int v_col0, const void* out, long long ldo,
                   const void* dout, long long lddo, const float* lse, const uint32_t* mask_bits, const int* tile_start,
-                  const int* n_tiles, const uint8_t* tile_cls, const int* pos, const float* cos_tab, const float* sin_tab, float* dsum_scratch, void* dqkv,
+                  const int* n_tiles, const uint8_t* tile_cls, const uint8_t* iso_flags, const int* iso_list,
+                  const int* iso_count, const int* pos, const float* cos_tab, const float* sin_tab, float* dsum_scratch, void* dqkv,
                   long long ld_dqkv, int N, int S, int H, void* stream) {
   GGPT_REQUIRE(qkv && out && dout && lse && mask_bits && tile_start && n_tiles && tile_cls && pos && cos_tab && sin_tab && dsum_scratch && dqkv,
                "attn_bwd: null pointer");
@@ -450,14 +454,23 @@ int ggpt_attn_bwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int
   p.max_tiles = ggpt_attn_max_tiles(S);
   p.mask_words = ggpt_attn_mask_words(S);
   p.mask_bits = mask_bits; p.tile_start = tile_start; p.n_tiles = n_tiles; p.tile_cls = tile_cls; p.lse = lse;
-  p.dsum = dsum_scratch;
+  p.dsum = dsum_scratch; p.iso_flags = iso_flags;
   p.dqkv = static_cast<__nv_bfloat16*>(dqkv); p.ld = ld_dqkv;
   p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
   p.pos = pos; p.cos_tab = cos_tab; p.sin_tab = sin_tab;
   p.scale = 0.125f;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
   if (int rc = launch_bwd<true>(tmQKV, tmDO, p, s)) return rc;
-  return launch_bwd<false>(tmQKV, tmDO, p, s);
+  if (int rc = launch_bwd<false>(tmQKV, tmDO, p, s)) return rc;
+  if (iso_flags == nullptr) return 0;
+  GGPT_REQUIRE(iso_list && iso_count, "attn_bwd: iso_flags given without iso_list / iso_count");
+  DiagParams d{};
+  d.N = N; d.S = S; d.H = H; d.max_tiles = p.max_tiles; d.mask_words = p.mask_words;
+  d.mask_bits = mask_bits; d.tile_start = tile_start; d.tile_cls = tile_cls; d.iso_list = iso_list; d.iso_count = iso_count;
+  d.q_col0 = q_col0; d.k_col0 = k_col0; d.v_col0 = v_col0; d.scale = p.scale; d.scale_log2 = p.scale_log2;
+  d.lse_in = lse; d.dsum = dsum_scratch; d.dqkv = p.dqkv; d.ld_dqkv = ld_dqkv;
+  d.pos = pos; d.cos_tab = cos_tab; d.sin_tab = sin_tab;
+  return attn_diag_bwd_launch(tmQKV, tmDO, d, s);
 }
 
 }  // extern "C"

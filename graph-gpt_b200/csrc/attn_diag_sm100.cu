@@ -1,0 +1,559 @@
+// Persistent attention kernels for ISOLATED DIAGONAL tiles — the packed-sequence fast path.
+//
+// With the variable row tiles of ggpt_attn_mask_build, a packed batch (block-diagonal mask over ~24-row
+// Eulerian-path segments) decomposes into row tiles whose only visible key tile is the tile itself.  For such a
+// tile there is no online-softmax loop at all: one QK^T, one softmax, one PV — and in backward one score pass
+// produces dQ, dK and dV together.  What is left is latency (TMA -> MMA -> softmax -> MMA -> store), so instead of
+// one short-lived CTA per tile these kernels are persistent (one CTA per SM) and software-pipelined over a device-side
+// work list of (sequence, tile) x head items: the TMA producer runs stages ahead, the MMA warp issues the scores of
+// item i+1 while the softmax warps work on item i, and the epilogue of item i-1 is interleaved after the softmax
+// of item i.  Two TMEM slots hold the accumulators of the two items in flight; in backward the gradient accumulators
+// alias the (by then consumed) S / dP columns of the same slot so that two slots fit in 512 columns.
+//
+// Arithmetic is identical to attn_fwd_sm100.cu / attn_bwd_sm100.cu (same bf16 rounding points), see there for the
+// reference citations (HF:199-221, HF:146-168).
+#include "common.cuh"
+#include "attn_diag.cuh"
+#include "../../include/ggpt_b200.h"
+
+namespace ggpt {
+
+__device__ __forceinline__ void diag_mask_words(const uint32_t* __restrict__ mrow, int k0, int klen, uint32_t (&mw)[4]) {
+  const int w0 = k0 >> 5, sh = k0 & 31;
+  uint32_t w[5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) w[i] = mrow[w0 + i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t v = __funnelshift_r(w[i], w[i + 1], sh);
+    const int nvalid = klen - 32 * i;
+    const uint32_t keep = nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u));
+    mw[i] = v & keep;
+  }
+}
+
+struct DiagItem {
+  int n, h, r0, len, cls;
+};
+__device__ __forceinline__ DiagItem diag_item(const DiagParams& p, int idx) {
+  DiagItem it;
+  const int e = p.iso_list[idx / p.H];
+  it.h = idx % p.H;
+  it.n = e / p.max_tiles;
+  const int t = e % p.max_tiles;
+  const int* ts = p.tile_start + static_cast<size_t>(it.n) * (p.max_tiles + 1);
+  it.r0 = ts[t];
+  it.len = ts[t + 1] - it.r0;
+  it.cls = p.tile_cls[(static_cast<size_t>(it.n) * p.max_tiles + t) * p.max_tiles + t];
+  return it;
+}
+
+// =====================================================================================================
+// forward
+// =====================================================================================================
+constexpr int kDFThreads = 192;                       // producer, MMA, 4 softmax warps
+constexpr int kDFStages = 3;
+constexpr int kDFStageBytes = 49152;                  // Q | K | V
+constexpr int kDFSmemP = kDFStages * kDFStageBytes;   // 2 x 32 KB P buffers
+constexpr int kDFSmemBars = kDFSmemP + 65536;
+constexpr int kDFSmem = kDFSmemBars + 256;
+
+__global__ void __launch_bounds__(kDFThreads, 1)
+attn_diag_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const DiagParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDFSmemBars);
+  uint64_t* full = bars;            // [3]
+  uint64_t* empty = bars + 3;       // [3]
+  uint64_t* s_full = bars + 6;      // [2]
+  uint64_t* p_full = bars + 8;      // count 4
+  uint64_t* o_full = bars + 9;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total = p.iso_count[0] * p.H;
+  if (static_cast<int>(blockIdx.x) >= total) return;   // uniform; nothing allocated yet
+  const int n_items = (total - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQKV);
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(&s_full[0], 1);
+    mbar_init(&s_full[1], 1);
+    mbar_init(p_full, 4);
+    mbar_init(&o_full[0], 1);
+    mbar_init(&o_full[1], 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;   // slot b: S at b*256, O at b*256 + 128
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < n_items; ++i) {
+        const DiagItem it = diag_item(p, blockIdx.x + i * gridDim.x);
+        const int st = i % kDFStages;
+        mbar_wait(&empty[st], ((i / kDFStages) & 1) ^ 1);
+        mbar_expect_tx(&full[st], kDFStageBytes);
+        uint8_t* s = smem + st * kDFStageBytes;
+        tma_load_3d(s, &tmQKV, &full[st], p.q_col0 + it.h * 64, it.r0, it.n);
+        tma_load_3d(s + 16384, &tmQKV, &full[st], p.k_col0 + it.h * 64, it.r0, it.n);
+        tma_load_3d(s + 32768, &tmQKV, &full[st], p.v_col0 + it.h * 64, it.r0, it.n);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, false, true);
+      auto issue_S = [&](int i) {
+        const int st = i % kDFStages;
+        mbar_wait(&full[st], (i / kDFStages) & 1);
+        tc_fence_after();
+        const uint32_t aQ = smem_u32(smem + st * kDFStageBytes), aK = aQ + 16384;
+        const uint32_t d = tmem_base + (i & 1) * 256;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          tc_mma_bf16(d, umma_desc_sw128(aQ + kk * 32, 16, 1024), umma_desc_sw128(aK + kk * 32, 16, 1024), idesc_s, kk != 0);
+        tc_commit(&s_full[i & 1]);
+      };
+      issue_S(0);
+      for (int i = 0; i < n_items; ++i) {
+        if (i + 1 < n_items) issue_S(i + 1);
+        mbar_wait(p_full, i & 1);
+        tc_fence_after();
+        const int st = i % kDFStages;
+        const uint32_t aV = smem_u32(smem + st * kDFStageBytes + 32768);
+        const uint32_t aP = smem_u32(smem + kDFSmemP + (i & 1) * 32768);
+        const uint32_t d = tmem_base + (i & 1) * 256 + 128;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          tc_mma_bf16(d, umma_desc_sw128(aP + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                      umma_desc_sw128(aV + kk * 2048, 8192, 1024), idesc_o, kk != 0);
+        tc_commit(&o_full[i & 1]);
+        tc_commit(&empty[st]);
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+    float l_prev = 0.f, m_prev = 0.f;
+    DiagItem prev{};
+    auto epilogue = [&](int i, const DiagItem& it, float l, float m) {
+      mbar_wait(&o_full[i & 1], (i >> 1) & 1);
+      tc_fence_after();
+      const float inv = (l > 0.f) ? 1.0f / l : 0.f;
+      const bool ok = r < it.len;
+      __nv_bfloat16* orow = p.out + (static_cast<long long>(it.n) * p.S + it.r0 + r) * p.ldo + it.h * 64;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t o[32];
+        tmem_ld32(tmem_base + (i & 1) * 256 + 128 + lane_addr + c * 32, o);
+        tmem_ld_wait();
+        if (ok) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 v;
+            v.x = pack_bf16(__uint_as_float(o[g * 8 + 0]) * inv, __uint_as_float(o[g * 8 + 1]) * inv);
+            v.y = pack_bf16(__uint_as_float(o[g * 8 + 2]) * inv, __uint_as_float(o[g * 8 + 3]) * inv);
+            v.z = pack_bf16(__uint_as_float(o[g * 8 + 4]) * inv, __uint_as_float(o[g * 8 + 5]) * inv);
+            v.w = pack_bf16(__uint_as_float(o[g * 8 + 6]) * inv, __uint_as_float(o[g * 8 + 7]) * inv);
+            *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = v;
+          }
+        }
+      }
+      if (ok && p.lse != nullptr)
+        p.lse[(static_cast<size_t>(it.n) * p.H + it.h) * p.S + it.r0 + r] =
+            (l > 0.f) ? (m * 0.6931471805599453f + logf(l)) : 0.f;
+    };
+    for (int i = 0; i < n_items; ++i) {
+      const DiagItem it = diag_item(p, blockIdx.x + i * gridDim.x);
+      const bool row_ok = r < it.len;
+      uint32_t mw[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+      if (!row_ok) mw[0] = mw[1] = mw[2] = mw[3] = 0u;
+      else if (it.cls == 2)
+        diag_mask_words(p.mask_bits + (static_cast<size_t>(it.n) * p.S + it.r0 + r) * p.mask_words, it.r0, it.len, mw);
+      mbar_wait(&s_full[i & 1], (i >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tS = tmem_base + (i & 1) * 256 + lane_addr;
+      float m = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t s[32];
+        tmem_ld32(tS + c * 32, s);
+        tmem_ld_wait();
+        const uint32_t w = (c == 0) ? mw[0] : (c == 1) ? mw[1] : (c == 2) ? mw[2] : mw[3];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) m = fmaxf(m, ((w >> j) & 1u) ? __uint_as_float(s[j]) * p.scale_log2 : -INFINITY);
+      }
+      const float m_use = (m == -INFINITY) ? 0.f : m;
+      float l = 0.f;
+      uint8_t* sP = smem + kDFSmemP + (i & 1) * 32768;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t s[32];
+        tmem_ld32(tS + c * 32, s);
+        tmem_ld_wait();
+        const uint32_t w = (c == 0) ? mw[0] : (c == 1) ? mw[1] : (c == 2) ? mw[2] : mw[3];
+        uint8_t* pbase = sP + (c >> 1) * 16384 + r * 128;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float pv[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float e = exp2f(__uint_as_float(s[g * 8 + j]) * p.scale_log2 - m_use);
+            pv[j] = ((w >> (g * 8 + j)) & 1u) ? e : 0.f;
+            l += pv[j];
+          }
+          uint4 o;
+          o.x = pack_bf16(pv[0], pv[1]); o.y = pack_bf16(pv[2], pv[3]);
+          o.z = pack_bf16(pv[4], pv[5]); o.w = pack_bf16(pv[6], pv[7]);
+          *reinterpret_cast<uint4*>(pbase + ((((c & 1) * 4 + g) ^ (r & 7)) << 4)) = o;
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      if (i > 0) epilogue(i - 1, prev, l_prev, m_prev);
+      prev = it;
+      l_prev = l;
+      m_prev = m;
+    }
+    epilogue(n_items - 1, prev, l_prev, m_prev);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// =====================================================================================================
+// backward: dQ, dK, dV of one isolated tile in a single pass
+// =====================================================================================================
+constexpr int kDBThreads = 320;                       // producer, MMA, 8 compute warps (two per TMEM lane quadrant)
+constexpr int kDBStageBytes = 65536;                  // Q | K | V | dO
+constexpr int kDBSmemP = 2 * kDBStageBytes;
+constexpr int kDBSmemDS = kDBSmemP + 32768;
+constexpr int kDBSmemEps = kDBSmemDS + 32768;         // float [2 items][2 halves][128]
+constexpr int kDBSmemBars = kDBSmemEps + 2048;
+constexpr int kDBSmem = kDBSmemBars + 256;
+
+__global__ void __launch_bounds__(kDBThreads, 1)
+attn_diag_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO, const DiagParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sP = smem + kDBSmemP;
+  uint8_t* sDS = smem + kDBSmemDS;
+  float* epsx = reinterpret_cast<float*>(smem + kDBSmemEps);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDBSmemBars);
+  uint64_t* full = bars;             // [2]
+  uint64_t* empty = bars + 2;        // [2]
+  uint64_t* sdp_full = bars + 4;     // [2]
+  uint64_t* pds_full = bars + 6;     // count 8
+  uint64_t* pds_empty = bars + 7;
+  uint64_t* acc_full = bars + 8;     // [2]
+  uint64_t* acc_empty = bars + 10;   // [2] count 8
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total = p.iso_count[0] * p.H;
+  if (static_cast<int>(blockIdx.x) >= total) return;
+  const int n_items = (total - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmDO);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+      mbar_init(&sdp_full[i], 1);
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 8);
+    }
+    mbar_init(pds_full, 8);
+    mbar_init(pds_empty, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // slot b (256 columns): S [0,128) dP [128,256); after the softmax pass the same columns are reused as
+  // dV [0,64) dK [64,128) dQ [128,192) PK [192,256)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < n_items; ++i) {
+        const DiagItem it = diag_item(p, blockIdx.x + i * gridDim.x);
+        const int st = i & 1;
+        mbar_wait(&empty[st], ((i >> 1) & 1) ^ 1);
+        mbar_expect_tx(&full[st], kDBStageBytes);
+        uint8_t* s = smem + st * kDBStageBytes;
+        tma_load_3d(s, &tmQKV, &full[st], p.q_col0 + it.h * 64, it.r0, it.n);
+        tma_load_3d(s + 16384, &tmQKV, &full[st], p.k_col0 + it.h * 64, it.r0, it.n);
+        tma_load_3d(s + 32768, &tmQKV, &full[st], p.v_col0 + it.h * 64, it.r0, it.n);
+        tma_load_3d(s + 49152, &tmDO, &full[st], it.h * 64, it.r0, it.n);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
+      constexpr uint32_t idesc_t = umma_idesc_bf16(128, 64, true, true);
+      constexpr uint32_t idesc_q = umma_idesc_bf16(128, 64, false, true);
+      const uint32_t aP = smem_u32(sP), aDS = smem_u32(sDS);
+      auto issue_scores = [&](int i) {
+        const int st = i & 1;
+        mbar_wait(&full[st], (i >> 1) & 1);
+        if (i >= 2) mbar_wait(&acc_empty[st], ((i >> 1) - 1) & 1);   // epilogue of item i-2 drained this slot
+        tc_fence_after();
+        const uint32_t aQ = smem_u32(smem + st * kDBStageBytes), aK = aQ + 16384, aV = aQ + 32768, aDO = aQ + 49152;
+        const uint32_t d = tmem_base + st * 256;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          tc_mma_bf16(d, umma_desc_sw128(aQ + kk * 32, 16, 1024), umma_desc_sw128(aK + kk * 32, 16, 1024), idesc_s, kk != 0);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          tc_mma_bf16(d + 128, umma_desc_sw128(aDO + kk * 32, 16, 1024), umma_desc_sw128(aV + kk * 32, 16, 1024), idesc_s,
+                      kk != 0);
+        tc_commit(&sdp_full[st]);
+      };
+      issue_scores(0);
+      for (int i = 0; i < n_items; ++i) {
+        mbar_wait(pds_full, i & 1);
+        tc_fence_after();
+        const int st = i & 1;
+        const uint32_t aQ = smem_u32(smem + st * kDBStageBytes), aK = aQ + 16384, aDO = aQ + 49152;
+        const uint32_t d = tmem_base + st * 256;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)   // dV = P^T dO
+          tc_mma_bf16(d, umma_desc_sw128(aP + kk * 2048, 16384, 1024), umma_desc_sw128(aDO + kk * 2048, 8192, 1024),
+                      idesc_t, kk != 0);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)   // dK = dS^T Q
+          tc_mma_bf16(d + 64, umma_desc_sw128(aDS + kk * 2048, 16384, 1024), umma_desc_sw128(aQ + kk * 2048, 8192, 1024),
+                      idesc_t, kk != 0);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)   // dQ = dS K
+          tc_mma_bf16(d + 128, umma_desc_sw128(aDS + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                      umma_desc_sw128(aK + kk * 2048, 8192, 1024), idesc_q, kk != 0);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)   // PK = P K  (row-sum correction, see attn_bwd_sm100.cu)
+          tc_mma_bf16(d + 192, umma_desc_sw128(aP + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                      umma_desc_sw128(aK + kk * 2048, 8192, 1024), idesc_q, kk != 0);
+        tc_commit(&acc_full[st]);
+        tc_commit(pds_empty);
+        tc_commit(&empty[st]);
+        // scores of the next item go behind the gradient MMAs: they need the TMEM slot that the epilogue of item
+        // i-1 (running on the compute warps right now, overlapped with the MMAs above) is draining
+        if (i + 1 < n_items) issue_scores(i + 1);
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;          // which 64 key columns (softmax pass) / which outputs (epilogue)
+    const int r = quad * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+    DiagItem prev{};
+    auto epilogue = [&](int i, const DiagItem& it) {
+      const int st = i & 1;
+      mbar_wait(&acc_full[st], (i >> 1) & 1);
+      tc_fence_after();
+      const uint32_t d = tmem_base + st * 256 + lane_addr;
+      const bool ok = r < it.len;
+      const long long grow = static_cast<long long>(it.n) * p.S + it.r0 + r;
+      const int pos = ok ? p.pos[grow] : 0;
+      const float* cs = p.cos_tab + static_cast<long long>(pos) * 32;
+      const float* sn = p.sin_tab + static_cast<long long>(pos) * 32;
+      auto store_pair = [&](uint32_t (&x1)[32], uint32_t (&x2)[32], bool rot, int col0) {
+        if (!ok) return;
+        __nv_bfloat16* orow = p.dqkv + grow * p.ld_dqkv + col0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float o1[8], o2[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float d1 = __uint_as_float(x1[g * 8 + j]), d2 = __uint_as_float(x2[g * 8 + j]);
+            if (rot) {
+              const float c = cs[g * 8 + j], s = sn[g * 8 + j];
+              o1[j] = d1 * c + d2 * s;
+              o2[j] = d2 * c - d1 * s;
+            } else {
+              o1[j] = d1;
+              o2[j] = d2;
+            }
+          }
+          uint4 v1, v2;
+          v1.x = pack_bf16(o1[0], o1[1]); v1.y = pack_bf16(o1[2], o1[3]);
+          v1.z = pack_bf16(o1[4], o1[5]); v1.w = pack_bf16(o1[6], o1[7]);
+          v2.x = pack_bf16(o2[0], o2[1]); v2.y = pack_bf16(o2[2], o2[3]);
+          v2.z = pack_bf16(o2[4], o2[5]); v2.w = pack_bf16(o2[6], o2[7]);
+          *reinterpret_cast<uint4*>(orow + g * 8) = v1;
+          *reinterpret_cast<uint4*>(orow + 32 + g * 8) = v2;
+        }
+      };
+      uint32_t x1[32], x2[32];
+      if (half == 0) {
+        tmem_ld32(d, x1);            // dV
+        tmem_ld32(d + 32, x2);
+        tmem_ld_wait();
+        store_pair(x1, x2, false, p.v_col0 + it.h * 64);
+        tmem_ld32(d + 64, x1);       // dK
+        tmem_ld32(d + 96, x2);
+        tmem_ld_wait();
+        store_pair(x1, x2, true, p.k_col0 + it.h * 64);
+      } else {
+        const float* e = epsx + (i & 1) * 256;
+        const float ce = (e[r] + e[128 + r]) * p.scale;
+        uint32_t y[32];
+        tmem_ld32(d + 128, x1);      // dQ
+        tmem_ld32(d + 160, x2);
+        tmem_ld32(d + 192, y);       // PK
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x1[j] = __float_as_uint(__uint_as_float(x1[j]) - ce * __uint_as_float(y[j]));
+        tmem_ld32(d + 224, y);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x2[j] = __float_as_uint(__uint_as_float(x2[j]) - ce * __uint_as_float(y[j]));
+        store_pair(x1, x2, true, p.q_col0 + it.h * 64);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[st]);
+    };
+
+    for (int i = 0; i < n_items; ++i) {
+      const DiagItem it = diag_item(p, blockIdx.x + i * gridDim.x);
+      const bool row_ok = r < it.len;
+      float lse2 = 0.f, dsum = 0.f;
+      uint32_t mw[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+      if (row_ok) {
+        const size_t li = (static_cast<size_t>(it.n) * p.H + it.h) * p.S + it.r0 + r;
+        lse2 = p.lse_in[li] * 1.4426950408889634f;
+        dsum = p.dsum[li];
+        if (it.cls == 2)
+          diag_mask_words(p.mask_bits + (static_cast<size_t>(it.n) * p.S + it.r0 + r) * p.mask_words, it.r0, it.len, mw);
+      } else {
+        mw[0] = mw[1] = mw[2] = mw[3] = 0u;
+      }
+      const int st = i & 1;
+      mbar_wait(&sdp_full[st], (i >> 1) & 1);
+      tc_fence_after();
+      if (i > 0) mbar_wait(pds_empty, (i - 1) & 1);
+      const uint32_t tS = tmem_base + st * 256 + lane_addr;
+      float eps = 0.f;
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = half * 2 + cc;
+        uint32_t s[32], dp[32];
+        tmem_ld32(tS + c * 32, s);
+        tmem_ld32(tS + 128 + c * 32, dp);
+        tmem_ld_wait();
+        const uint32_t w = (c == 0) ? mw[0] : (c == 1) ? mw[1] : (c == 2) ? mw[2] : mw[3];
+        uint8_t* pbase = sP + half * 16384 + r * 128;
+        uint8_t* dbase = sDS + half * 16384 + r * 128;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float pv[8], dv[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float e = exp2f(__uint_as_float(s[g * 8 + j]) * p.scale_log2 - lse2);
+            pv[j] = ((w >> (g * 8 + j)) & 1u) ? e : 0.f;
+            const float t0 = pv[j] * (__uint_as_float(dp[g * 8 + j]) - dsum);
+            eps += t0;
+            dv[j] = t0 * p.scale;
+          }
+          const int chunk = ((cc * 4 + g) ^ (r & 7)) << 4;
+          uint4 o, o2;
+          o.x = pack_bf16(pv[0], pv[1]); o.y = pack_bf16(pv[2], pv[3]);
+          o.z = pack_bf16(pv[4], pv[5]); o.w = pack_bf16(pv[6], pv[7]);
+          o2.x = pack_bf16(dv[0], dv[1]); o2.y = pack_bf16(dv[2], dv[3]);
+          o2.z = pack_bf16(dv[4], dv[5]); o2.w = pack_bf16(dv[6], dv[7]);
+          *reinterpret_cast<uint4*>(pbase + chunk) = o;
+          *reinterpret_cast<uint4*>(dbase + chunk) = o2;
+        }
+      }
+      epsx[(i & 1) * 256 + half * 128 + r] = eps;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_full);
+      if (i > 0) epilogue(i - 1, prev);
+      prev = it;
+    }
+    epilogue(n_items - 1, prev);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// isolated tile: its diagonal pair is active and nothing else in its row or column of the class matrix is
+__global__ void attn_iso_kernel(const uint8_t* __restrict__ cls, const int* __restrict__ n_tiles, int N, int max_tiles,
+                                uint8_t* __restrict__ iso_flags, int* __restrict__ iso_list, int* __restrict__ iso_count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * max_tiles) return;
+  const int n = i / max_tiles, t = i % max_tiles;
+  const int nt = n_tiles[n];
+  bool iso = false;
+  if (t < nt) {
+    const uint8_t* c = cls + static_cast<size_t>(n) * max_tiles * max_tiles;
+    iso = c[t * max_tiles + t] != 0;
+    for (int j = 0; j < nt && iso; ++j)
+      if (j != t && (c[t * max_tiles + j] != 0 || c[j * max_tiles + t] != 0)) iso = false;
+  }
+  iso_flags[i] = iso ? 1 : 0;
+  if (iso) iso_list[atomicAdd(iso_count, 1)] = i;
+}
+
+static int set_smem_attr(const void* fn, int bytes, bool* done) {
+  if (*done) return 0;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) {
+    set_error("attn_diag: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    return -2;
+  }
+  *done = true;
+  return 0;
+}
+
+int attn_iso_build(const uint8_t* cls, const int* n_tiles, int N, int max_tiles, uint8_t* iso_flags, int* iso_list,
+                   int* iso_count, cudaStream_t s) {
+  cudaMemsetAsync(iso_count, 0, sizeof(int), s);
+  const int n = N * max_tiles;
+  attn_iso_kernel<<<(n + 255) / 256, 256, 0, s>>>(cls, n_tiles, N, max_tiles, iso_flags, iso_list, iso_count);
+  return check_launch("attn_iso_kernel");
+}
+
+int attn_diag_fwd_launch(const CUtensorMap& tm, const DiagParams& p, cudaStream_t s) {
+  static bool done = false;
+  if (int rc = set_smem_attr(reinterpret_cast<const void*>(attn_diag_fwd_kernel), kDFSmem, &done)) return rc;
+  attn_diag_fwd_kernel<<<num_sms(), kDFThreads, kDFSmem, s>>>(tm, p);
+  return check_launch("attn_diag_fwd_kernel");
+}
+
+int attn_diag_bwd_launch(const CUtensorMap& tmQKV, const CUtensorMap& tmDO, const DiagParams& p, cudaStream_t s) {
+  static bool done = false;
+  if (int rc = set_smem_attr(reinterpret_cast<const void*>(attn_diag_bwd_kernel), kDBSmem, &done)) return rc;
+  attn_diag_bwd_kernel<<<num_sms(), kDBThreads, kDBSmem, s>>>(tmQKV, tmDO, p);
+  return check_launch("attn_diag_bwd_kernel");
+}
+
+}  // namespace ggpt

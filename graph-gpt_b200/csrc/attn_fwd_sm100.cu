@@ -19,6 +19,7 @@
 // swizzle) as the A operand of the PV MMA; V is consumed in place as an MN-major B operand.  Two CTAs fit per SM
 // (112 KB smem, 256 TMEM columns each) so one CTA's softmax overlaps the other's MMAs.
 #include "common.cuh"
+#include "attn_diag.cuh"
 #include "../../include/ggpt_b200.h"
 
 namespace ggpt {
@@ -37,6 +38,7 @@ struct AttnFwdParams {
   const int* tile_start;      // [N, max_tiles+1]  row offsets of the variable row tiles
   const int* n_tiles;         // [N]
   const uint8_t* tile_cls;    // [N, max_tiles, max_tiles]  (query tile, key tile)
+  const uint8_t* iso_flags;   // [N, max_tiles] tiles handled by the persistent diagonal kernel (may be NULL)
   __nv_bfloat16* out;         // [N*S, H*64]
   long long ldo;
   float* lse;                 // [N, H, S]  natural-log logsumexp of the scaled scores (for backward)
@@ -80,6 +82,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
   const int qt = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
   const int n_kt = p.n_tiles[n];
   if (qt >= n_kt) return;                       // uniform for the whole CTA, before any barrier / TMEM state
+  if (p.iso_flags != nullptr && p.iso_flags[n * p.max_tiles + qt]) return;   // done by attn_diag_fwd_kernel
   const int* ts = p.tile_start + static_cast<size_t>(n) * (p.max_tiles + 1);
   const int q0 = ts[qt], qlen = ts[qt + 1] - q0;
   const uint8_t* cls_row = p.tile_cls + (static_cast<size_t>(n) * p.max_tiles + qt) * p.max_tiles;
@@ -418,11 +421,13 @@ int ggpt_attn_mask_words(int S) { return ((S + 127) / 128) * 4 + 4; }
 int ggpt_attn_max_tiles(int S) { return (S + 63) / 64; }
 
 int ggpt_attn_mask_build(const long long* attention_mask, int mask_dims, int N, int S, int causal, uint32_t* mask_bits,
-                         int* tile_start, int* n_tiles, uint8_t* tile_cls, void* stream) {
+                         int* tile_start, int* n_tiles, uint8_t* tile_cls, uint8_t* iso_flags, int* iso_list,
+                         int* iso_count, void* stream) {
   GGPT_REQUIRE(N > 0 && S > 0, "attn_mask_build: empty batch");
   GGPT_REQUIRE(attention_mask == nullptr || mask_dims == 2 || mask_dims == 3,
                "attention_mask of %d dims is not implemented (expected [N,S] or [N,S,S])", mask_dims);
-  GGPT_REQUIRE(mask_bits && tile_start && n_tiles && tile_cls, "attn_mask_build: null output");
+  GGPT_REQUIRE(mask_bits && tile_start && n_tiles && tile_cls && iso_flags && iso_list && iso_count,
+               "attn_mask_build: null output");
   GGPT_REQUIRE(S <= 16384, "attn_mask_build: S=%d exceeds the plan kernel's shared-memory budget", S);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int words = ggpt_attn_mask_words(S);
@@ -443,12 +448,14 @@ int ggpt_attn_mask_build(const long long* attention_mask, int mask_dims, int N, 
   const long long warps2 = static_cast<long long>(N) * mt * mt;
   attn_tile_cls_kernel<<<static_cast<unsigned>((warps2 * 32 + 255) / 256), 256, 0, s>>>(mask_bits, N, S, words, mt,
                                                                                          tile_start, n_tiles, tile_cls);
-  return check_launch("attn_tile_cls_kernel");
+  if (int rc = check_launch("attn_tile_cls_kernel")) return rc;
+  return attn_iso_build(tile_cls, n_tiles, N, mt, iso_flags, iso_list, iso_count, s);
 }
 
 int ggpt_attn_fwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int v_col0, const uint32_t* mask_bits,
-                  const int* tile_start, const int* n_tiles, const uint8_t* tile_cls, void* out, long long ldo, float* lse,
-                  int N, int S, int H, void* stream) {
+                  const int* tile_start, const int* n_tiles, const uint8_t* tile_cls, const uint8_t* iso_flags,
+                  const int* iso_list, const int* iso_count, void* out, long long ldo, float* lse, int N, int S, int H,
+                  void* stream) {
   GGPT_REQUIRE(qkv && mask_bits && tile_start && n_tiles && tile_cls && out, "attn_fwd: null pointer");
   GGPT_REQUIRE(N > 0 && S > 0 && H > 0, "attn_fwd: empty problem");
   GGPT_REQUIRE(ld_qkv % 8 == 0 && ldo % 8 == 0 && q_col0 % 8 == 0 && k_col0 % 8 == 0 && v_col0 % 8 == 0,
@@ -460,6 +467,7 @@ int ggpt_attn_fwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int
   p.max_tiles = ggpt_attn_max_tiles(S);
   p.mask_words = ggpt_attn_mask_words(S);
   p.mask_bits = mask_bits; p.tile_start = tile_start; p.n_tiles = n_tiles; p.tile_cls = tile_cls;
+  p.iso_flags = iso_flags;
   p.out = static_cast<__nv_bfloat16*>(out); p.ldo = ldo; p.lse = lse;
   p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
@@ -474,7 +482,15 @@ int ggpt_attn_fwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int
   }
   dim3 grid(p.max_tiles, H, N);
   attn_fwd_kernel<<<grid, kAttThreads, kAttSmem, static_cast<cudaStream_t>(stream)>>>(tm, p);
-  return check_launch("attn_fwd_kernel");
+  if (int rc = check_launch("attn_fwd_kernel")) return rc;
+  if (iso_flags == nullptr) return 0;
+  GGPT_REQUIRE(iso_list && iso_count, "attn_fwd: iso_flags given without iso_list / iso_count");
+  DiagParams d{};
+  d.N = N; d.S = S; d.H = H; d.max_tiles = p.max_tiles; d.mask_words = p.mask_words;
+  d.mask_bits = mask_bits; d.tile_start = tile_start; d.tile_cls = tile_cls; d.iso_list = iso_list; d.iso_count = iso_count;
+  d.q_col0 = q_col0; d.k_col0 = k_col0; d.v_col0 = v_col0; d.scale = 0.125f; d.scale_log2 = p.scale_log2;
+  d.out = p.out; d.ldo = ldo; d.lse = lse;
+  return attn_diag_fwd_launch(tm, d, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

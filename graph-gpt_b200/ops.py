@@ -3,6 +3,8 @@
 Each function validates dtypes/shapes, hands raw device pointers + the current CUDA stream to the library and
 returns the output tensor.  No arithmetic happens in Python and nothing here falls back to torch ops.
 """
+import os
+
 import torch
 
 from .lib import lib
@@ -110,8 +112,15 @@ def gemm_qkv_rope(a, wqkv, pos, cos_tab, sin_tab, rope_cols):
 class AttnMask:
     """Bit-matrix form of the reference's additive attention mask (built once per step, shared by all layers)."""
 
-    def __init__(self, bits, tile_start, n_tiles, cls, N, S):
+    def __init__(self, bits, tile_start, n_tiles, cls, iso_flags, iso_list, iso_count, N, S):
         self.bits, self.tile_start, self.n_tiles, self.cls, self.N, self.S = bits, tile_start, n_tiles, cls, N, S
+        self.iso_flags, self.iso_list, self.iso_count = iso_flags, iso_list, iso_count
+        self.use_diag = os.environ.get("GGPT_ATTN_NO_DIAG") is None   # debug switch: force the general kernels
+
+    def _iso_ptrs(self):
+        if self.use_diag:
+            return self.iso_flags.data_ptr(), self.iso_list.data_ptr(), self.iso_count.data_ptr()
+        return 0, 0, 0
 
 
 def attn_mask_build(attention_mask, N, S, causal, device):
@@ -122,6 +131,9 @@ def attn_mask_build(attention_mask, N, S, causal, device):
     tile_start = torch.empty((N, mt + 1), device=device, dtype=torch.int32)
     n_tiles = torch.empty((N,), device=device, dtype=torch.int32)
     cls = torch.empty((N, mt, mt), device=device, dtype=torch.uint8)
+    iso_flags = torch.empty((N, mt), device=device, dtype=torch.uint8)
+    iso_list = torch.empty((N * mt,), device=device, dtype=torch.int32)
+    iso_count = torch.empty((1,), device=device, dtype=torch.int32)
     dims = 0
     if attention_mask is not None:
         if attention_mask.dim() not in (2, 3):
@@ -134,8 +146,9 @@ def attn_mask_build(attention_mask, N, S, causal, device):
         if attention_mask.shape[0] != N or attention_mask.shape[-1] != S:
             raise RuntimeError(f"attention_mask shape {tuple(attention_mask.shape)} does not match N={N}, S={S}")
     lib.ggpt_attn_mask_build(_ptr(attention_mask), dims, N, S, int(bool(causal)), bits.data_ptr(), tile_start.data_ptr(),
-                             n_tiles.data_ptr(), cls.data_ptr(), _stream())
-    return AttnMask(bits, tile_start, n_tiles, cls, N, S)
+                             n_tiles.data_ptr(), cls.data_ptr(), iso_flags.data_ptr(), iso_list.data_ptr(),
+                             iso_count.data_ptr(), _stream())
+    return AttnMask(bits, tile_start, n_tiles, cls, iso_flags, iso_list, iso_count, N, S)
 
 
 def attn_fwd(qkv, mask: AttnMask, H, *, want_lse=True):
@@ -148,8 +161,8 @@ def attn_fwd(qkv, mask: AttnMask, H, *, want_lse=True):
     out = torch.empty((N * S, d), device=qkv.device, dtype=BF16)
     lse = torch.empty((N, H, S), device=qkv.device, dtype=F32) if want_lse else None
     lib.ggpt_attn_fwd(qkv.data_ptr(), qkv.stride(0), 0, d, 2 * d, mask.bits.data_ptr(), mask.tile_start.data_ptr(),
-                      mask.n_tiles.data_ptr(), mask.cls.data_ptr(), out.data_ptr(), out.stride(0), _ptr(lse), N, S, H,
-                      _stream())
+                      mask.n_tiles.data_ptr(), mask.cls.data_ptr(), *mask._iso_ptrs(), out.data_ptr(), out.stride(0),
+                      _ptr(lse), N, S, H, _stream())
     return out, lse
 
 
@@ -164,7 +177,7 @@ def attn_bwd(dout, qkv, out, lse, mask: AttnMask, H, pos, cos_tab, sin_tab):
     dsum = torch.empty((N, H, S), device=qkv.device, dtype=F32)
     lib.ggpt_attn_bwd(qkv.data_ptr(), qkv.stride(0), 0, d, 2 * d, out.data_ptr(), out.stride(0), dout.data_ptr(),
                       dout.stride(0), lse.data_ptr(), mask.bits.data_ptr(), mask.tile_start.data_ptr(),
-                      mask.n_tiles.data_ptr(), mask.cls.data_ptr(), pos.data_ptr(),
+                      mask.n_tiles.data_ptr(), mask.cls.data_ptr(), *mask._iso_ptrs(), pos.data_ptr(),
                       cos_tab.data_ptr(), sin_tab.data_ptr(), dsum.data_ptr(), dqkv.data_ptr(), dqkv.stride(0), N, S, H,
                       _stream())
     return dqkv

@@ -39,7 +39,7 @@ def test_argument_validation_without_gpu():
     with pytest.raises(RuntimeError, match="null operand"):
         lib.ggpt_gemm_bf16(0, 8, 0, 0, 8, 0, 0, 8, 0, 0, 128, 128, 64, 0)
     with pytest.raises(RuntimeError, match="not implemented"):
-        lib.ggpt_attn_mask_build(1, 4, 1, 8, 0, 1, 1, 1, 1, 0)
+        lib.ggpt_attn_mask_build(1, 4, 1, 8, 0, 1, 1, 1, 1, 1, 1, 1, 0)
 
 
 def test_model_refuses_cpu_execution():
