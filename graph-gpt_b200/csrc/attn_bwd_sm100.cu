@@ -430,7 +430,7 @@ extern "C" {
 int ggpt_attn_bwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int v_col0, const void* out, long long ldo,
                   const void* dout, long long lddo, const float* lse, const uint32_t* mask_bits, const int* tile_start,
                   const int* n_tiles, const uint8_t* tile_cls, const uint8_t* iso_flags, const int* iso_list,
-                  const int* iso_count, const int* pos, const float* cos_tab, const float* sin_tab, float* dsum_scratch, void* dqkv,
+                  const int* iso_count, int run_general, const int* pos, const float* cos_tab, const float* sin_tab, float* dsum_scratch, void* dqkv,
                   long long ld_dqkv, int N, int S, int H, void* stream) {
   GGPT_REQUIRE(qkv && out && dout && lse && mask_bits && tile_start && n_tiles && tile_cls && pos && cos_tab && sin_tab && dsum_scratch && dqkv,
                "attn_bwd: null pointer");
@@ -460,8 +460,11 @@ int ggpt_attn_bwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int
   p.pos = pos; p.cos_tab = cos_tab; p.sin_tab = sin_tab;
   p.scale = 0.125f;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
-  if (int rc = launch_bwd<true>(tmQKV, tmDO, p, s)) return rc;
-  if (int rc = launch_bwd<false>(tmQKV, tmDO, p, s)) return rc;
+  GGPT_REQUIRE(run_general || iso_flags, "attn_bwd: run_general == 0 needs the isolated-tile work list");
+  if (run_general) {
+    if (int rc = launch_bwd<true>(tmQKV, tmDO, p, s)) return rc;
+    if (int rc = launch_bwd<false>(tmQKV, tmDO, p, s)) return rc;
+  }
   if (iso_flags == nullptr) return 0;
   GGPT_REQUIRE(iso_list && iso_count, "attn_bwd: iso_flags given without iso_list / iso_count");
   DiagParams d{};

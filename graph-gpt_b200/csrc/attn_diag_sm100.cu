@@ -51,7 +51,10 @@ __device__ __forceinline__ DiagItem diag_item(const DiagParams& p, int idx) {
 // =====================================================================================================
 // forward
 // =====================================================================================================
-constexpr int kDFThreads = 192;                       // producer, MMA, 4 softmax warps
+// warps: 0 = TMA producer, 1 = MMA issuer, 2..5 = softmax group 0, 6..9 = softmax group 1.  Item i lives in TMEM
+// slot / P buffer / softmax group (i & 1): while one group runs the softmax of item i the other finishes item i-1
+// (waits for its PV, normalises, stores), so eight warps keep the SM busy and no row statistic crosses a warp.
+constexpr int kDFThreads = 320;
 constexpr int kDFStages = 3;
 constexpr int kDFStageBytes = 49152;                  // Q | K | V
 constexpr int kDFSmemP = kDFStages * kDFStageBytes;   // 2 x 32 KB P buffers
@@ -65,9 +68,10 @@ attn_diag_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const DiagParams
   uint64_t* full = bars;            // [3]
   uint64_t* empty = bars + 3;       // [3]
   uint64_t* s_full = bars + 6;      // [2]
-  uint64_t* p_full = bars + 8;      // count 4
-  uint64_t* o_full = bars + 9;      // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* p_full = bars + 8;      // [2] count 4
+  uint64_t* o_full = bars + 10;     // [2]
+  uint64_t* slot_free = bars + 12;  // [2] count 4: group finished reading S / O of its slot
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total = p.iso_count[0] * p.H;
   if (static_cast<int>(blockIdx.x) >= total) return;   // uniform; nothing allocated yet
@@ -79,11 +83,12 @@ attn_diag_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const DiagParams
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
-    mbar_init(&s_full[0], 1);
-    mbar_init(&s_full[1], 1);
-    mbar_init(p_full, 4);
-    mbar_init(&o_full[0], 1);
-    mbar_init(&o_full[1], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&slot_free[i], 4);
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -113,77 +118,54 @@ attn_diag_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const DiagParams
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, false, true);
       auto issue_S = [&](int i) {
-        const int st = i % kDFStages;
+        const int st = i % kDFStages, b = i & 1;
         mbar_wait(&full[st], (i / kDFStages) & 1);
+        if (i >= 2) mbar_wait(&slot_free[b], ((i >> 1) - 1) & 1);   // group b is done with item i-2
         tc_fence_after();
         const uint32_t aQ = smem_u32(smem + st * kDFStageBytes), aK = aQ + 16384;
-        const uint32_t d = tmem_base + (i & 1) * 256;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          tc_mma_bf16(d, umma_desc_sw128(aQ + kk * 32, 16, 1024), umma_desc_sw128(aK + kk * 32, 16, 1024), idesc_s, kk != 0);
-        tc_commit(&s_full[i & 1]);
+          tc_mma_bf16(tmem_base + b * 256, umma_desc_sw128(aQ + kk * 32, 16, 1024), umma_desc_sw128(aK + kk * 32, 16, 1024),
+                      idesc_s, kk != 0);
+        tc_commit(&s_full[b]);
       };
-      issue_S(0);
-      for (int i = 0; i < n_items; ++i) {
-        if (i + 1 < n_items) issue_S(i + 1);
-        mbar_wait(p_full, i & 1);
+      auto issue_PV = [&](int i) {
+        const int st = i % kDFStages, b = i & 1;
+        mbar_wait(&p_full[b], (i >> 1) & 1);
         tc_fence_after();
-        const int st = i % kDFStages;
         const uint32_t aV = smem_u32(smem + st * kDFStageBytes + 32768);
-        const uint32_t aP = smem_u32(smem + kDFSmemP + (i & 1) * 32768);
-        const uint32_t d = tmem_base + (i & 1) * 256 + 128;
+        const uint32_t aP = smem_u32(smem + kDFSmemP + b * 32768);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
-          tc_mma_bf16(d, umma_desc_sw128(aP + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+          tc_mma_bf16(tmem_base + b * 256 + 128, umma_desc_sw128(aP + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
                       umma_desc_sw128(aV + kk * 2048, 8192, 1024), idesc_o, kk != 0);
-        tc_commit(&o_full[i & 1]);
+        tc_commit(&o_full[b]);
         tc_commit(&empty[st]);
+      };
+      for (int i = 0; i < n_items; ++i) {
+        issue_S(i);
+        if (i > 0) issue_PV(i - 1);
       }
+      issue_PV(n_items - 1);
     }
   } else {
+    const int grp = (warp - 2) >> 2;
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
-    float l_prev = 0.f, m_prev = 0.f;
-    DiagItem prev{};
-    auto epilogue = [&](int i, const DiagItem& it, float l, float m) {
-      mbar_wait(&o_full[i & 1], (i >> 1) & 1);
-      tc_fence_after();
-      const float inv = (l > 0.f) ? 1.0f / l : 0.f;
-      const bool ok = r < it.len;
-      __nv_bfloat16* orow = p.out + (static_cast<long long>(it.n) * p.S + it.r0 + r) * p.ldo + it.h * 64;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t o[32];
-        tmem_ld32(tmem_base + (i & 1) * 256 + 128 + lane_addr + c * 32, o);
-        tmem_ld_wait();
-        if (ok) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint4 v;
-            v.x = pack_bf16(__uint_as_float(o[g * 8 + 0]) * inv, __uint_as_float(o[g * 8 + 1]) * inv);
-            v.y = pack_bf16(__uint_as_float(o[g * 8 + 2]) * inv, __uint_as_float(o[g * 8 + 3]) * inv);
-            v.z = pack_bf16(__uint_as_float(o[g * 8 + 4]) * inv, __uint_as_float(o[g * 8 + 5]) * inv);
-            v.w = pack_bf16(__uint_as_float(o[g * 8 + 6]) * inv, __uint_as_float(o[g * 8 + 7]) * inv);
-            *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = v;
-          }
-        }
-      }
-      if (ok && p.lse != nullptr)
-        p.lse[(static_cast<size_t>(it.n) * p.H + it.h) * p.S + it.r0 + r] =
-            (l > 0.f) ? (m * 0.6931471805599453f + logf(l)) : 0.f;
-    };
-    for (int i = 0; i < n_items; ++i) {
+    uint8_t* sP = smem + kDFSmemP + grp * 32768;
+    const uint32_t tS = tmem_base + grp * 256 + lane_addr;
+    for (int i = grp; i < n_items; i += 2) {
       const DiagItem it = diag_item(p, blockIdx.x + i * gridDim.x);
       const bool row_ok = r < it.len;
+      const uint32_t ph = (i >> 1) & 1;
       uint32_t mw[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
       if (!row_ok) mw[0] = mw[1] = mw[2] = mw[3] = 0u;
       else if (it.cls == 2)
         diag_mask_words(p.mask_bits + (static_cast<size_t>(it.n) * p.S + it.r0 + r) * p.mask_words, it.r0, it.len, mw);
-      mbar_wait(&s_full[i & 1], (i >> 1) & 1);
+      mbar_wait(&s_full[grp], ph);
       tc_fence_after();
-      const uint32_t tS = tmem_base + (i & 1) * 256 + lane_addr;
-      float m = -INFINITY;
+      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // independent chains: ILP instead of a 128-deep max
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t s[32];
@@ -191,11 +173,12 @@ attn_diag_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const DiagParams
         tmem_ld_wait();
         const uint32_t w = (c == 0) ? mw[0] : (c == 1) ? mw[1] : (c == 2) ? mw[2] : mw[3];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) m = fmaxf(m, ((w >> j) & 1u) ? __uint_as_float(s[j]) * p.scale_log2 : -INFINITY);
+        for (int j = 0; j < 32; ++j)
+          m4[j & 3] = fmaxf(m4[j & 3], ((w >> j) & 1u) ? __uint_as_float(s[j]) * p.scale_log2 : -INFINITY);
       }
+      const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
       const float m_use = (m == -INFINITY) ? 0.f : m;
-      float l = 0.f;
-      uint8_t* sP = smem + kDFSmemP + (i & 1) * 32768;
+      float l4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t s[32];
@@ -210,7 +193,7 @@ attn_diag_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const DiagParams
           for (int j = 0; j < 8; ++j) {
             const float e = exp2f(__uint_as_float(s[g * 8 + j]) * p.scale_log2 - m_use);
             pv[j] = ((w >> (g * 8 + j)) & 1u) ? e : 0.f;
-            l += pv[j];
+            l4[j & 3] += pv[j];
           }
           uint4 o;
           o.x = pack_bf16(pv[0], pv[1]); o.y = pack_bf16(pv[2], pv[3]);
@@ -218,16 +201,40 @@ attn_diag_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const DiagParams
           *reinterpret_cast<uint4*>(pbase + ((((c & 1) * 4 + g) ^ (r & 7)) << 4)) = o;
         }
       }
+      const float l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
-      if (i > 0) epilogue(i - 1, prev, l_prev, m_prev);
-      prev = it;
-      l_prev = l;
-      m_prev = m;
+      if (lane == 0) mbar_arrive(&p_full[grp]);
+      // ---- epilogue of the same item (the other group runs its softmax meanwhile)
+      mbar_wait(&o_full[grp], ph);
+      tc_fence_after();
+      const float inv = (l > 0.f) ? 1.0f / l : 0.f;
+      __nv_bfloat16* orow = p.out + (static_cast<long long>(it.n) * p.S + it.r0 + r) * p.ldo + it.h * 64;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t o[32];
+        tmem_ld32(tS + 128 + c * 32, o);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 v;
+            v.x = pack_bf16(__uint_as_float(o[g * 8 + 0]) * inv, __uint_as_float(o[g * 8 + 1]) * inv);
+            v.y = pack_bf16(__uint_as_float(o[g * 8 + 2]) * inv, __uint_as_float(o[g * 8 + 3]) * inv);
+            v.z = pack_bf16(__uint_as_float(o[g * 8 + 4]) * inv, __uint_as_float(o[g * 8 + 5]) * inv);
+            v.w = pack_bf16(__uint_as_float(o[g * 8 + 6]) * inv, __uint_as_float(o[g * 8 + 7]) * inv);
+            *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = v;
+          }
+        }
+      }
+      if (row_ok && p.lse != nullptr)
+        p.lse[(static_cast<size_t>(it.n) * p.H + it.h) * p.S + it.r0 + r] =
+            (l > 0.f) ? (m * 0.6931471805599453f + logf(l)) : 0.f;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&slot_free[grp]);
     }
-    epilogue(n_items - 1, prev, l_prev, m_prev);
   }
 
   tc_fence_before();
@@ -521,6 +528,7 @@ __global__ void attn_iso_kernel(const uint8_t* __restrict__ cls, const int* __re
   }
   iso_flags[i] = iso ? 1 : 0;
   if (iso) iso_list[atomicAdd(iso_count, 1)] = i;
+  if (t == 0) atomicAdd(iso_count + 1, nt);   // iso_count[1] = total number of row tiles in the batch
 }
 
 static int set_smem_attr(const void* fn, int bytes, bool* done) {
@@ -536,7 +544,7 @@ static int set_smem_attr(const void* fn, int bytes, bool* done) {
 
 int attn_iso_build(const uint8_t* cls, const int* n_tiles, int N, int max_tiles, uint8_t* iso_flags, int* iso_list,
                    int* iso_count, cudaStream_t s) {
-  cudaMemsetAsync(iso_count, 0, sizeof(int), s);
+  cudaMemsetAsync(iso_count, 0, 2 * sizeof(int), s);
   const int n = N * max_tiles;
   attn_iso_kernel<<<(n + 255) / 256, 256, 0, s>>>(cls, n_tiles, N, max_tiles, iso_flags, iso_list, iso_count);
   return check_launch("attn_iso_kernel");

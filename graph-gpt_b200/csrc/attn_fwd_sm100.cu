@@ -454,8 +454,8 @@ int ggpt_attn_mask_build(const long long* attention_mask, int mask_dims, int N, 
 
 int ggpt_attn_fwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int v_col0, const uint32_t* mask_bits,
                   const int* tile_start, const int* n_tiles, const uint8_t* tile_cls, const uint8_t* iso_flags,
-                  const int* iso_list, const int* iso_count, void* out, long long ldo, float* lse, int N, int S, int H,
-                  void* stream) {
+                  const int* iso_list, const int* iso_count, int run_general, void* out, long long ldo, float* lse, int N,
+                  int S, int H, void* stream) {
   GGPT_REQUIRE(qkv && mask_bits && tile_start && n_tiles && tile_cls && out, "attn_fwd: null pointer");
   GGPT_REQUIRE(N > 0 && S > 0 && H > 0, "attn_fwd: empty problem");
   GGPT_REQUIRE(ld_qkv % 8 == 0 && ldo % 8 == 0 && q_col0 % 8 == 0 && k_col0 % 8 == 0 && v_col0 % 8 == 0,
@@ -480,9 +480,12 @@ int ggpt_attn_fwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int
     }
     attr_set = true;
   }
-  dim3 grid(p.max_tiles, H, N);
-  attn_fwd_kernel<<<grid, kAttThreads, kAttSmem, static_cast<cudaStream_t>(stream)>>>(tm, p);
-  if (int rc = check_launch("attn_fwd_kernel")) return rc;
+  GGPT_REQUIRE(run_general || iso_flags, "attn_fwd: run_general == 0 needs the isolated-tile work list");
+  if (run_general) {
+    dim3 grid(p.max_tiles, H, N);
+    attn_fwd_kernel<<<grid, kAttThreads, kAttSmem, static_cast<cudaStream_t>(stream)>>>(tm, p);
+    if (int rc = check_launch("attn_fwd_kernel")) return rc;
+  }
   if (iso_flags == nullptr) return 0;
   GGPT_REQUIRE(iso_list && iso_count, "attn_fwd: iso_flags given without iso_list / iso_count");
   DiagParams d{};

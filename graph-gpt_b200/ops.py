@@ -116,11 +116,23 @@ class AttnMask:
         self.bits, self.tile_start, self.n_tiles, self.cls, self.N, self.S = bits, tile_start, n_tiles, cls, N, S
         self.iso_flags, self.iso_list, self.iso_count = iso_flags, iso_list, iso_count
         self.use_diag = os.environ.get("GGPT_ATTN_NO_DIAG") is None   # debug switch: force the general kernels
+        # [#isolated tiles, #tiles] copied to pinned host memory right behind the mask build; read lazily so the
+        # host only waits for the mask kernels, never for the layers already queued behind them
+        self._counts_host = torch.empty((2,), dtype=torch.int32, pin_memory=True)
+        self._counts_host.copy_(iso_count, non_blocking=True)
+        self._counts_event = torch.cuda.Event()
+        self._counts_event.record()
+        self._run_general = None
 
-    def _iso_ptrs(self):
-        if self.use_diag:
-            return self.iso_flags.data_ptr(), self.iso_list.data_ptr(), self.iso_count.data_ptr()
-        return 0, 0, 0
+    def _iso_args(self):
+        """(iso_flags, iso_list, iso_count, run_general) for ggpt_attn_fwd / ggpt_attn_bwd."""
+        if not self.use_diag:
+            return 0, 0, 0, 1
+        if self._run_general is None:
+            self._counts_event.synchronize()
+            iso, total = self._counts_host.tolist()
+            self._run_general = int(iso != total)     # packed batches: every tile isolated -> general kernels skipped
+        return self.iso_flags.data_ptr(), self.iso_list.data_ptr(), self.iso_count.data_ptr(), self._run_general
 
 
 def attn_mask_build(attention_mask, N, S, causal, device):
@@ -133,7 +145,7 @@ def attn_mask_build(attention_mask, N, S, causal, device):
     cls = torch.empty((N, mt, mt), device=device, dtype=torch.uint8)
     iso_flags = torch.empty((N, mt), device=device, dtype=torch.uint8)
     iso_list = torch.empty((N * mt,), device=device, dtype=torch.int32)
-    iso_count = torch.empty((1,), device=device, dtype=torch.int32)
+    iso_count = torch.empty((2,), device=device, dtype=torch.int32)
     dims = 0
     if attention_mask is not None:
         if attention_mask.dim() not in (2, 3):
@@ -161,7 +173,7 @@ def attn_fwd(qkv, mask: AttnMask, H, *, want_lse=True):
     out = torch.empty((N * S, d), device=qkv.device, dtype=BF16)
     lse = torch.empty((N, H, S), device=qkv.device, dtype=F32) if want_lse else None
     lib.ggpt_attn_fwd(qkv.data_ptr(), qkv.stride(0), 0, d, 2 * d, mask.bits.data_ptr(), mask.tile_start.data_ptr(),
-                      mask.n_tiles.data_ptr(), mask.cls.data_ptr(), *mask._iso_ptrs(), out.data_ptr(), out.stride(0),
+                      mask.n_tiles.data_ptr(), mask.cls.data_ptr(), *mask._iso_args(), out.data_ptr(), out.stride(0),
                       _ptr(lse), N, S, H, _stream())
     return out, lse
 
@@ -177,7 +189,7 @@ def attn_bwd(dout, qkv, out, lse, mask: AttnMask, H, pos, cos_tab, sin_tab):
     dsum = torch.empty((N, H, S), device=qkv.device, dtype=F32)
     lib.ggpt_attn_bwd(qkv.data_ptr(), qkv.stride(0), 0, d, 2 * d, out.data_ptr(), out.stride(0), dout.data_ptr(),
                       dout.stride(0), lse.data_ptr(), mask.bits.data_ptr(), mask.tile_start.data_ptr(),
-                      mask.n_tiles.data_ptr(), mask.cls.data_ptr(), *mask._iso_ptrs(), pos.data_ptr(),
+                      mask.n_tiles.data_ptr(), mask.cls.data_ptr(), *mask._iso_args(), pos.data_ptr(),
                       cos_tab.data_ptr(), sin_tab.data_ptr(), dsum.data_ptr(), dqkv.data_ptr(), dqkv.stride(0), N, S, H,
                       _stream())
     return dqkv

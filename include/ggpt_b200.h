@@ -77,10 +77,11 @@ int ggpt_attn_max_tiles(int S);
  *   tile_start [N,max_tiles+1], n_tiles [N]   variable row tiles (<= 128 rows, cut on block boundaries of the mask so
  *                                     packed segments never straddle a tile; uniform 128 grid otherwise)
  *   tile_cls   [N,max_tiles,max_tiles] class of every (query tile, key tile): 0 masked, 1 fully visible, 2 mixed
- *   iso_flags  [N,max_tiles], iso_list [N*max_tiles], iso_count [1]   tiles whose only active pair is their own
+ *   iso_flags  [N,max_tiles], iso_list [N*max_tiles], iso_count [2]   tiles whose only active pair is their own
  *                                     diagonal one (every tile of a packed batch): flags + compact work list for the
- *                                     persistent single-pass kernels; pass iso_flags = NULL to ggpt_attn_fwd/bwd to
- *                                     force the general tile-loop kernels
+ *                                     persistent single-pass kernels (iso_count[0] = #isolated, iso_count[1] = #tiles);
+ *                                     pass iso_flags = NULL to ggpt_attn_fwd/bwd to force the general tile-loop
+ *                                     kernels, or run_general = 0 when the caller knows every tile is isolated
  * ref: modeling_helpers.py:38-64 (_update_causal_mask, _expand_mask_from_3d_mask: additive 0/finfo.min mask),
  *      HF:398-405 (causal mask when config.causal_attention); packing: tokenizer_utils.py:351-355.  Fully masked
  *      query rows yield 0 here (the reference yields a uniform average; such rows are padding, never consumed). */
@@ -92,8 +93,8 @@ int ggpt_attn_mask_build(const long long* attention_mask, int mask_dims, int N, 
  * scores, kept for the backward pass.   ref: HF:199-221 (eager_attention_forward), fp32 softmax. */
 int ggpt_attn_fwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int v_col0, const uint32_t* mask_bits,
                   const int* tile_start, const int* n_tiles, const uint8_t* tile_cls, const uint8_t* iso_flags,
-                  const int* iso_list, const int* iso_count, void* out, long long ldo, float* lse, int N, int S, int H,
-                  void* stream);
+                  const int* iso_list, const int* iso_count, int run_general, void* out, long long ldo, float* lse, int N,
+                  int S, int H, void* stream);
 
 /* dqkv[N*S, ld_dqkv] (bf16) = gradient of the fused q|k|v projection output given dout = dL/d(attention output).
  * Recomputes P from lse; two deterministic tcgen05 passes (dK,dV then dQ); dQ/dK are un-rotated (inverse RoPE)
@@ -102,7 +103,7 @@ int ggpt_attn_fwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int
 int ggpt_attn_bwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int v_col0, const void* out, long long ldo,
                   const void* dout, long long lddo, const float* lse, const uint32_t* mask_bits, const int* tile_start,
                   const int* n_tiles, const uint8_t* tile_cls, const uint8_t* iso_flags, const int* iso_list,
-                  const int* iso_count, const int* pos, const float* cos_tab, const float* sin_tab, float* dsum_scratch, void* dqkv,
+                  const int* iso_count, int run_general, const int* pos, const float* cos_tab, const float* sin_tab, float* dsum_scratch, void* dqkv,
                   long long ld_dqkv, int N, int S, int H, void* stream);
 
 /* ---------------------------------------------------------------------------------------------

@@ -368,7 +368,7 @@ def test_attn_diag_path_matches_general_path(S, H, monkeypatch):
         mask = ops.attn_mask_build(am, N, S, False, qkv.device)
         assert mask.use_diag == (mode == "diag")
         if mode == "diag":
-            assert int(mask.iso_count) == int(mask.n_tiles.sum())      # every tile of a packed batch is isolated
+            assert int(mask.iso_count[0]) == int(mask.n_tiles.sum()) == int(mask.iso_count[1])      # every tile of a packed batch is isolated
         out, lse = ops.attn_fwd(qkv, mask, H)
         dqkv = ops.attn_bwd(dout, qkv, out, lse, mask, H, pos, cos_tab, sin_tab)
         torch.cuda.synchronize()
