@@ -245,10 +245,27 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t v) {
   __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&v);
   return __bfloat1622float2(b);
 }
-// exact (erf) GELU, as transformers ACT2FN["gelu"]
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
-__device__ __forceinline__ float gelu_erf_grad(float x) {
-  return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+// erf GELU (transformers ACT2FN["gelu"]) and its derivative from ONE exponential:
+//   Phi(g) = 0.5 (1 + erf(g / sqrt2)),  erf(x) = sign(x) (1 - poly(t) e^{-x^2}),  t = 1 / (1 + 0.3275911 |x|)
+//   (Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7 — far below the bf16 rounding of the outputs), and with
+//   x = g / sqrt2 the same e^{-x^2} = e^{-g^2/2} is the Gaussian pdf needed by gelu'(g) = Phi(g) + g phi(g).
+__device__ __forceinline__ void gelu_cdf_pdf(float g, float& cdf, float& pdf) {
+  const float ax = fabsf(g) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  const float e = exp2f(g * g * -0.72134752044448170f);   // e^{-g^2/2}
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float erf_abs = fmaf(-poly, e, 1.0f);
+  cdf = 0.5f + 0.5f * copysignf(erf_abs, g);
+  pdf = 0.3989422804014327f * e;
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+  float cdf, pdf;
+  gelu_cdf_pdf(x, cdf, pdf);
+  return x * cdf;
 }
 #endif  // __CUDACC__
 

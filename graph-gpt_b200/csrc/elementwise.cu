@@ -249,11 +249,10 @@ __global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ dact, const _
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float2 a = unpack_bf16(dau[j]), g = unpack_bf16(gvu[j]), u = unpack_bf16(uvu[j]);
-      // one erf per element: cdf = Phi(g); gelu = g*cdf; gelu' = cdf + g*phi(g)
-      const float cx = 0.5f * (1.0f + erff(g.x * 0.70710678118654752f));
-      const float cy = 0.5f * (1.0f + erff(g.y * 0.70710678118654752f));
-      const float px = 0.3989422804014327f * __expf(-0.5f * g.x * g.x);
-      const float py = 0.3989422804014327f * __expf(-0.5f * g.y * g.y);
+      // gelu = g*Phi(g); gelu' = Phi(g) + g*phi(g), both from one exponential (common.cuh gelu_cdf_pdf)
+      float cx, px, cy, py;
+      gelu_cdf_pdf(g.x, cx, px);
+      gelu_cdf_pdf(g.y, cy, py);
       og[j] = pack_bf16(a.x * u.x * (cx + g.x * px), a.y * u.y * (cy + g.y * py));
       ou[j] = pack_bf16(a.x * g.x * cx, a.y * g.y * cy);
     }

@@ -28,7 +28,7 @@
 
 namespace ggpt {
 
-enum : int { EPI_BF16 = 0, EPI_F32 = 1, EPI_RESID = 2, EPI_GEGLU = 3, EPI_QKV_ROPE = 4 };
+enum : int { EPI_BF16 = 0, EPI_F32 = 1, EPI_RESID = 2, EPI_GEGLU = 3, EPI_QKV_ROPE = 4, EPI_DGEGLU = 5 };
 
 struct GemmParams {
   int M, N, K;
@@ -46,6 +46,8 @@ struct GemmParams {
   const float* colscale;  // RESID: optional per-column scale (LayerScale lambda), fp32 [N]
   const float* rowscale;  // RESID: optional per-row scale (DropPath keep/p), fp32 [M]
   int accumulate;         // F32: C += acc
+  const void* gu;         // DGEGLU: saved [gate | up] of the forward pass, bf16 [M, 2N]
+  long long ldgu;
   const int* pos;         // QKV_ROPE: position per row
   const float* cos_tab;   // QKV_ROPE: [max_pos, 32]
   const float* sin_tab;
@@ -356,6 +358,49 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           put_bf16_32(hh * 4, rg);
         }
         copy_out_bf16(reinterpret_cast<__nv_bfloat16*>(p.C2), p.ldc2, nh + c, half_n);
+      } else if constexpr (EPI == EPI_DGEGLU) {
+        // acc = dact = d(act); fused GeGLU backward: dgate = dact * up * gelu'(gate), dup = dact * gelu(gate)
+        const int n0 = nb * BN;
+        const __nv_bfloat16* gu = reinterpret_cast<const __nv_bfloat16*>(p.gu);
+        __nv_bfloat16* dgu = reinterpret_cast<__nv_bfloat16*>(p.C);
+#pragma unroll 1
+        for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) stage_put(j, make_uint4(r[j * 4 + 0], r[j * 4 + 1], r[j * 4 + 2], r[j * 4 + 3]));
+          __syncwarp();
+          const int gcol = n0 + c + rd_j * 4;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + rd_row;
+            const int grow = row0 + rr;
+            if (grow < p.M && gcol < p.N) {
+              const uint4 a4 = stage_get(rr);
+              const uint2 g2 = *reinterpret_cast<const uint2*>(gu + static_cast<long long>(grow) * p.ldgu + gcol);
+              const uint2 u2 = *reinterpret_cast<const uint2*>(gu + static_cast<long long>(grow) * p.ldgu + p.N + gcol);
+              const float2 g01 = unpack_bf16(g2.x), g23 = unpack_bf16(g2.y), u01 = unpack_bf16(u2.x), u23 = unpack_bf16(u2.y);
+              const float av[4] = {__uint_as_float(a4.x), __uint_as_float(a4.y), __uint_as_float(a4.z), __uint_as_float(a4.w)};
+              const float gv[4] = {g01.x, g01.y, g23.x, g23.y};
+              const float uv[4] = {u01.x, u01.y, u23.x, u23.y};
+              float dg[4], du[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float cdf, pdf;
+                gelu_cdf_pdf(gv[j], cdf, pdf);
+                dg[j] = av[j] * uv[j] * fmaf(gv[j], pdf, cdf);
+                du[j] = av[j] * gv[j] * cdf;
+              }
+              uint2 o;
+              o.x = pack_bf16(dg[0], dg[1]); o.y = pack_bf16(dg[2], dg[3]);
+              *reinterpret_cast<uint2*>(dgu + static_cast<long long>(grow) * p.ldc + gcol) = o;
+              o.x = pack_bf16(du[0], du[1]); o.y = pack_bf16(du[2], du[3]);
+              *reinterpret_cast<uint2*>(dgu + static_cast<long long>(grow) * p.ldc + p.N + gcol) = o;
+            }
+          }
+          __syncwarp();
+        }
       } else if constexpr (EPI == EPI_QKV_ROPE) {
         const int n0 = nb * BN;
         const int pos = row_ok ? p.pos[row] : 0;
@@ -556,6 +601,17 @@ int ggpt_gemm_bf16_geglu(const void* A, long long lda, const void* Wgu, long lon
   GemmParams p{};
   p.M = M; p.N = N2; p.K = K; p.C = gu; p.ldc = ldgu; p.C2 = act; p.ldc2 = ldact;
   return launch_gemm<256, false, false, EPI_GEGLU>(A, lda, Wgu, ldb, p, static_cast<cudaStream_t>(stream));
+}
+
+int ggpt_gemm_bf16_dgeglu(const void* dy, long long lda, const void* Wd, long long ldb, const void* gu, long long ldgu,
+                          void* dgu, long long lddgu, int M, int I, int K, void* stream) {
+  if (int rc = check_common(dy, lda, Wd, ldb, M, I, K)) return rc;
+  GGPT_REQUIRE(gu && dgu, "gemm_dgeglu: null gu / dgu");
+  GGPT_REQUIRE(I % 8 == 0 && ldgu % 8 == 0 && lddgu % 8 == 0 && ldgu >= 2 * I && lddgu >= 2 * I,
+               "gemm_dgeglu: I and leading dimensions must be multiples of 8 and cover [gate | up]");
+  GemmParams p{};
+  p.M = M; p.N = I; p.K = K; p.C = dgu; p.ldc = lddgu; p.gu = gu; p.ldgu = ldgu;
+  return launch_gemm<256, false, true, EPI_DGEGLU>(dy, lda, Wd, ldb, p, static_cast<cudaStream_t>(stream));
 }
 
 int ggpt_gemm_bf16_qkv_rope(const void* A, long long lda, const void* Wqkv, long long ldb, void* qkv, long long ldc,

@@ -271,9 +271,8 @@ class HotPath:
                 dyb = self._scaled_copy(dx, fp.w(p + "lambda_2") if self.layer_scale else None, st["rs"])
                 if self.layer_scale:
                     self._lambda_grad(fp.g(p + "lambda_2"), dx, st["x3"], st["x2"], fp.w(p + "lambda_2"))
-            dact = ops.gemm(dyb, fp.wb(p + "mlp.down_proj.weight"), b_mn_major=True)
+            dgu = ops.gemm_dgeglu(dyb, fp.wb(p + "mlp.down_proj.weight"), st["gu"])   # dgrad + GeGLU backward fused
             ops.gemm(dyb, st["act"], out=fp.g(p + "mlp.down_proj.weight"), **wgrad)
-            dgu = ops.geglu_bwd(dact, st["gu"])
             ops.gemm(dgu, st["h2"], out=self._ggu(i), **wgrad)
             dh2 = ops.gemm(dgu, self._wgu(i), b_mn_major=True)
             dx2, dx2b = ops.rmsnorm_bwd(dh2, st["x2"], st["rstd2"], fp.w(p + "post_attention_layernorm.weight"), dx,

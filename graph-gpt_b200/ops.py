@@ -91,6 +91,19 @@ def gemm_geglu(a, wgu, *, want_gu=True):
     return gu, act
 
 
+def gemm_dgeglu(dy, wd, gu):
+    """dgu[M,2I] = GeGLU backward of (dy @ wd) with the saved gu = [gate | up]; wd = down_proj.weight [d, I]."""
+    _check(dy, BF16, "gemm_dgeglu dy", 2)
+    _check(wd, BF16, "gemm_dgeglu wd", 2)
+    _check(gu, BF16, "gemm_dgeglu gu", 2)
+    M, K = dy.shape
+    I = wd.shape[1]
+    dgu = torch.empty_like(gu)
+    lib.ggpt_gemm_bf16_dgeglu(dy.data_ptr(), dy.stride(0), wd.data_ptr(), wd.stride(0), gu.data_ptr(), gu.stride(0),
+                              dgu.data_ptr(), dgu.stride(0), M, I, K, _stream())
+    return dgu
+
+
 def gemm_qkv_rope(a, wqkv, pos, cos_tab, sin_tab, rope_cols):
     """qkv[M,3d] = a @ wqkv.T with rotary embedding applied to the first rope_cols columns (heads of 64)."""
     _check(a, BF16, "gemm_qkv_rope a", 2)

@@ -55,6 +55,12 @@ int ggpt_gemm_bf16_resid(const void* A, long long lda, const void* B, long long 
 int ggpt_gemm_bf16_geglu(const void* A, long long lda, const void* Wgu, long long ldb, void* gu, long long ldgu,
                          void* act, long long ldact, int M, int N2, int K, void* stream);
 
+/* Fused down_proj dgrad + GeGLU backward: dact = dy[M,K] * Wd[K,I] (Wd = down_proj.weight [d, I] read in place) and,
+ * in the epilogue, dgu[M,2I] = [dact*up*gelu'(gate) | dact*gelu(gate)] from the saved gu = [gate | up].
+ * ref: autograd of HF:182-184 (down_proj, erf GELU, gate*up). */
+int ggpt_gemm_bf16_dgeglu(const void* dy, long long lda, const void* Wd, long long ldb, const void* gu, long long ldgu,
+                          void* dgu, long long lddgu, int M, int I, int K, void* stream);
+
 /* Fused q|k|v projection with rotary embedding applied to the first rope_cols columns (q and k heads of 64).
  * pos[M] = position id of each row; cos_tab/sin_tab = fp32 [max_pos, 32] (HF inv_freq table).
  * ref: HF:262-267 (projections + apply_rotary_pos_emb), HF:124-135,138-168 (cos/sin, rotate_half). */

@@ -157,3 +157,18 @@ def test_gemm_wgrad_split_k(M, N, K):
     out = ops.gemm(dy, x, a_mn_major=True, b_mn_major=True, out=base.clone(), out_dtype=torch.float32, accumulate=True)
     torch.cuda.synchronize()
     _report(f"wgrad split-k {M}x{N}x{K}", out, base + ref, 1e-4)
+
+
+@pytest.mark.parametrize("M,I,K", [(1000, 3072, 768), (130, 256, 64)])
+def test_gemm_dgeglu(M, I, K):
+    """Fused down_proj dgrad + GeGLU backward against torch autograd of gelu(g)*u."""
+    from graphgpt_b200 import ops
+    dy = _rand((M, K), 31)
+    wd = _rand((K, I), 32, 1.0 / math.sqrt(K))
+    gu = _rand((M, 2 * I), 33)
+    dact = dy.float() @ wd.float()
+    gg = gu.float().clone().requires_grad_(True)
+    (torch.nn.functional.gelu(gg[:, :I]) * gg[:, I:]).backward(dact)
+    dgu = ops.gemm_dgeglu(dy, wd, gu)
+    torch.cuda.synchronize()
+    _report("dgeglu", dgu, gg.grad, 6e-3)
