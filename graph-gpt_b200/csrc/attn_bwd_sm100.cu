@@ -51,7 +51,8 @@ struct BwdSmem {
   static constexpr int kStream = 32768;
   static constexpr int kP = kStream + 65536;
   static constexpr int kDS = kP + 32768;
-  static constexpr int kBars = kDS + 32768;
+  static constexpr int kGather = kDS + 32768;     // 4 warps x 4 KB: coalesced RoPE-table gather (epilogue)
+  static constexpr int kBars = kGather + 16384;
   static constexpr int kTotal = kBars + 256;
 };
 
@@ -305,8 +306,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const bool ok = r < row_len;
     const long long grow = static_cast<long long>(n) * p.S + out_row;
     const int pos = ok ? p.pos[grow] : 0;
-    const float* cs = p.cos_tab + static_cast<long long>(pos) * 32;
-    const float* sn = p.sin_tab + static_cast<long long>(pos) * 32;
+    float cs[32], sn[32];
+    {
+      uint8_t* gbuf = smem + L::kGather + quad * 4096;
+      warp_gather_rows32(p.cos_tab, pos, gbuf, lane, cs);
+      warp_gather_rows32(p.sin_tab, pos, gbuf, lane, sn);
+    }
     constexpr int kNumAcc = DKV ? 2 : 1;
 #pragma unroll
     for (int a = 0; a < kNumAcc; ++a) {

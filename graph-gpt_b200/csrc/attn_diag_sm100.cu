@@ -253,7 +253,8 @@ constexpr int kDBStageBytes = 65536;                  // Q | K | V | dO
 constexpr int kDBSmemP = 2 * kDBStageBytes;
 constexpr int kDBSmemDS = kDBSmemP + 32768;
 constexpr int kDBSmemEps = kDBSmemDS + 32768;         // float [2 items][2 halves][128]
-constexpr int kDBSmemBars = kDBSmemEps + 2048;
+constexpr int kDBSmemGather = kDBSmemEps + 2048;      // 8 warps x 4 KB: coalesced RoPE-table gather (epilogue)
+constexpr int kDBSmemBars = kDBSmemGather + 32768;
 constexpr int kDBSmem = kDBSmemBars + 256;
 
 __global__ void __launch_bounds__(kDBThreads, 1)
@@ -382,8 +383,12 @@ attn_diag_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       const bool ok = r < it.len;
       const long long grow = static_cast<long long>(it.n) * p.S + it.r0 + r;
       const int pos = ok ? p.pos[grow] : 0;
-      const float* cs = p.cos_tab + static_cast<long long>(pos) * 32;
-      const float* sn = p.sin_tab + static_cast<long long>(pos) * 32;
+      float cs[32], sn[32];
+      {
+        uint8_t* gbuf = smem + kDBSmemGather + (warp - 2) * 4096;
+        warp_gather_rows32(p.cos_tab, pos, gbuf, lane, cs);
+        warp_gather_rows32(p.sin_tab, pos, gbuf, lane, sn);
+      }
       auto store_pair = [&](uint32_t (&x1)[32], uint32_t (&x2)[32], bool rot, int col0) {
         if (!ok) return;
         __nv_bfloat16* orow = p.dqkv + grow * p.ld_dqkv + col0;

@@ -245,6 +245,29 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t v) {
   __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&v);
   return __bfloat1622float2(b);
 }
+// Every lane receives the 32 floats of table row `row_idx` (its own row; e.g. the RoPE cos/sin row of its token).
+// A per-lane read would touch 32 different 128-byte lines per instruction (32 L1 wavefronts for 16 useful bytes each),
+// so rows are fetched cooperatively — 8 lanes per row, 4 rows per 16-byte/lane instruction — and transposed through a
+// 4 KB per-warp smem buffer with the 128-byte XOR swizzle (conflict-free both ways).
+__device__ __forceinline__ void warp_gather_rows32(const float* __restrict__ tab, int row_idx, uint8_t* stg, int lane,
+                                                   float (&out)[32]) {
+  const int rd_row = lane >> 3, rd_j = lane & 7;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int rr = it * 4 + rd_row;
+    const int src = __shfl_sync(0xffffffffu, row_idx, rr);
+    const float4 v = *reinterpret_cast<const float4*>(tab + static_cast<long long>(src) * 32 + rd_j * 4);
+    *reinterpret_cast<float4*>(stg + rr * 128 + ((rd_j ^ (rr & 7)) << 4)) = v;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 v = *reinterpret_cast<const float4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4));
+    out[j * 4 + 0] = v.x; out[j * 4 + 1] = v.y; out[j * 4 + 2] = v.z; out[j * 4 + 3] = v.w;
+  }
+  __syncwarp();
+}
+
 // erf GELU (transformers ACT2FN["gelu"]) and its derivative from ONE exponential:
 //   Phi(g) = 0.5 (1 + erf(g / sqrt2)),  erf(x) = sign(x) (1 - poly(t) e^{-x^2}),  t = 1 / (1 + 0.3275911 |x|)
 //   (Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7 — far below the bf16 rounding of the outputs), and with

@@ -404,8 +404,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       } else if constexpr (EPI == EPI_QKV_ROPE) {
         const int n0 = nb * BN;
         const int pos = row_ok ? p.pos[row] : 0;
-        const float* cs = p.cos_tab + static_cast<long long>(pos) * 32;
-        const float* sn = p.sin_tab + static_cast<long long>(pos) * 32;
+        // cos/sin rows of this thread's token: the same for every head, gathered once per tile (coalesced)
+        float cc[32], ss[32];
+        const bool any_rot = (n0 + half * (BN / 2)) < p.rope_cols;   // warp-uniform
+        if (any_rot) {
+          warp_gather_rows32(p.cos_tab, pos, stg, lane, cc);
+          warp_gather_rows32(p.sin_tab, pos, stg, lane, ss);
+        }
 #pragma unroll 1
         for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 64) {   // one head (64 columns) per iteration
           uint32_t r1[32], r2[32];
@@ -414,18 +419,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           tmem_ld_wait();
           if ((n0 + c) < p.rope_cols) {
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const float4 c4 = *reinterpret_cast<const float4*>(cs + g * 4);
-              const float4 s4 = *reinterpret_cast<const float4*>(sn + g * 4);
-              const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
-              const float ss[4] = {s4.x, s4.y, s4.z, s4.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float x1 = __uint_as_float(r1[g * 4 + j]);
-                const float x2 = __uint_as_float(r2[g * 4 + j]);
-                r1[g * 4 + j] = __float_as_uint(x1 * cc[j] - x2 * ss[j]);   // q*cos + rotate_half(q)*sin, first half
-                r2[g * 4 + j] = __float_as_uint(x2 * cc[j] + x1 * ss[j]);   // second half
-              }
+            for (int j = 0; j < 32; ++j) {
+              const float x1 = __uint_as_float(r1[j]);
+              const float x2 = __uint_as_float(r2[j]);
+              r1[j] = __float_as_uint(x1 * cc[j] - x2 * ss[j]);   // q*cos + rotate_half(q)*sin, first half
+              r2[j] = __float_as_uint(x2 * cc[j] + x1 * ss[j]);   // second half
             }
           }
           put_bf16_32(0, r1);

@@ -271,7 +271,10 @@ class HotPath:
                 dyb = self._scaled_copy(dx, fp.w(p + "lambda_2") if self.layer_scale else None, st["rs"])
                 if self.layer_scale:
                     self._lambda_grad(fp.g(p + "lambda_2"), dx, st["x3"], st["x2"], fp.w(p + "lambda_2"))
-            dgu = ops.gemm_dgeglu(dyb, fp.wb(p + "mlp.down_proj.weight"), st["gu"])   # dgrad + GeGLU backward fused
+            # (ops.gemm_dgeglu fuses the next two calls, but its epilogue is slower than the separate HBM-bound kernel:
+            #  measured 0.97 ms vs 0.29 + 0.45 ms per layer on B200, profiles/r1_bench_packed_v8_fused_dgeglu.json)
+            dact = ops.gemm(dyb, fp.wb(p + "mlp.down_proj.weight"), b_mn_major=True)
+            dgu = ops.geglu_bwd(dact, st["gu"])
             ops.gemm(dyb, st["act"], out=fp.g(p + "mlp.down_proj.weight"), **wgrad)
             ops.gemm(dgu, st["h2"], out=self._ggu(i), **wgrad)
             dh2 = ops.gemm(dgu, self._wgu(i), b_mn_major=True)
