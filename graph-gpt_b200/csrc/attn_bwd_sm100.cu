@@ -42,6 +42,7 @@ struct AttnBwdParams {
   const float* sin_tab;
   float scale;                // 1/8
   float scale_log2;           // scale * log2(e)
+  DropParams drop;            // attention-probability dropout (same mask as the forward)
 };
 
 // smem: fixed pair 2x16K | streamed pair 2 stages x 2 x 16K | P 32K | dS 32K | barriers
@@ -254,6 +255,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       } else {
         mw[0] = mw[1] = mw[2] = mw[3] = 0u;
       }
+      const uint32_t rowkey = drop_rowkey(p.drop.seed_lo, p.drop.seed_hi, n, h, q_row);
+      const int kbase = ts[kt];
       mbar_wait(sdp_full, it & 1);
       tc_fence_after();
       if (it > 0) mbar_wait(pds_empty, (it - 1) & 1);   // previous P / dS consumed by the tensor core
@@ -273,9 +276,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           for (int j = 0; j < 8; ++j) {
             const float e = exp2f(__uint_as_float(s[g * 8 + j]) * p.scale_log2 - lse2);
             pv[j] = ((w >> (g * 8 + j)) & 1u) ? e : 0.f;
-            const float t0 = pv[j] * (__uint_as_float(dp[g * 8 + j]) - dsum);
+            float dpe = __uint_as_float(dp[g * 8 + j]);
+            bool keep = true;
+            if (p.drop.thresh != 0u) {
+              keep = drop_keep(rowkey, kbase + c * 32 + g * 8 + j, p.drop.thresh);
+              dpe = keep ? dpe * p.drop.inv_keep : 0.f;
+            }
+            const float t0 = pv[j] * (dpe - dsum);
             if (!DKV) eps_run += t0;
             dv[j] = t0 * p.scale;
+            if (DKV && !keep) pv[j] = 0.f;     // DKV: sP feeds dV = (P o mask)^T dO / (1-p); DQ: sP feeds P K (undropped)
           }
           const int chunk = ((c & 1) * 4 + g) ^ (r & 7);
           {
@@ -338,6 +348,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) x1[j] = x2[j] = 0u;
+      }
+      if (DKV && a == 0 && p.drop.thresh != 0u) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          x1[j] = __float_as_uint(__uint_as_float(x1[j]) * p.drop.inv_keep);
+          x2[j] = __float_as_uint(__uint_as_float(x2[j]) * p.drop.inv_keep);
+        }
       }
       if (ok) {
         __nv_bfloat16* orow = p.dqkv + grow * p.ld + col0;
@@ -435,7 +452,7 @@ extern "C" {
 int ggpt_attn_bwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int v_col0, const void* out, long long ldo,
                   const void* dout, long long lddo, const float* lse, const uint32_t* mask_bits, const int* tile_start,
                   const int* n_tiles, const uint8_t* tile_cls, const uint8_t* iso_flags, const int* iso_list,
-                  const int* iso_count, int run_general, const int* pos, const float* cos_tab, const float* sin_tab, float* dsum_scratch, void* dqkv,
+                  const int* iso_count, int run_general, float dropout_p, unsigned long long seed, const int* pos, const float* cos_tab, const float* sin_tab, float* dsum_scratch, void* dqkv,
                   long long ld_dqkv, int N, int S, int H, void* stream) {
   GGPT_REQUIRE(qkv && out && dout && lse && mask_bits && tile_start && n_tiles && tile_cls && pos && cos_tab && sin_tab && dsum_scratch && dqkv,
                "attn_bwd: null pointer");
@@ -465,6 +482,8 @@ int ggpt_attn_bwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int
   p.pos = pos; p.cos_tab = cos_tab; p.sin_tab = sin_tab;
   p.scale = 0.125f;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
+  GGPT_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "attn_bwd: dropout_p must be in [0,1)");
+  p.drop = make_drop_params(dropout_p, seed);
   GGPT_REQUIRE(run_general || iso_flags, "attn_bwd: run_general == 0 needs the isolated-tile work list");
   if (run_general) {
     if (int rc = launch_bwd<true>(tmQKV, tmDO, p, s)) return rc;
@@ -477,7 +496,7 @@ int ggpt_attn_bwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int
   d.mask_bits = mask_bits; d.tile_start = tile_start; d.tile_cls = tile_cls; d.iso_list = iso_list; d.iso_count = iso_count;
   d.q_col0 = q_col0; d.k_col0 = k_col0; d.v_col0 = v_col0; d.scale = p.scale; d.scale_log2 = p.scale_log2;
   d.lse_in = lse; d.dsum = dsum_scratch; d.dqkv = p.dqkv; d.ld_dqkv = ld_dqkv;
-  d.pos = pos; d.cos_tab = cos_tab; d.sin_tab = sin_tab;
+  d.pos = pos; d.cos_tab = cos_tab; d.sin_tab = sin_tab; d.drop = p.drop;
   return attn_diag_bwd_launch(tmQKV, tmDO, d, s);
 }
 

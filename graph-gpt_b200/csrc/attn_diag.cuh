@@ -15,6 +15,7 @@ struct DiagParams {
   const int* iso_count;        // [1]
   int q_col0, k_col0, v_col0;
   float scale, scale_log2;
+  DropParams drop;             // attention-probability dropout (training)
   // forward
   __nv_bfloat16* out;          // [N*S, H*64]
   long long ldo;

@@ -163,6 +163,7 @@ attn_diag_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const DiagParams
       if (!row_ok) mw[0] = mw[1] = mw[2] = mw[3] = 0u;
       else if (it.cls == 2)
         diag_mask_words(p.mask_bits + (static_cast<size_t>(it.n) * p.S + it.r0 + r) * p.mask_words, it.r0, it.len, mw);
+      const uint32_t rowkey = drop_rowkey(p.drop.seed_lo, p.drop.seed_hi, it.n, it.h, it.r0 + r);
       mbar_wait(&s_full[grp], ph);
       tc_fence_after();
       float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // independent chains: ILP instead of a 128-deep max
@@ -194,6 +195,7 @@ attn_diag_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const DiagParams
             const float e = exp2f(__uint_as_float(s[g * 8 + j]) * p.scale_log2 - m_use);
             pv[j] = ((w >> (g * 8 + j)) & 1u) ? e : 0.f;
             l4[j & 3] += pv[j];
+            if (p.drop.thresh != 0u && !drop_keep(rowkey, it.r0 + c * 32 + g * 8 + j, p.drop.thresh)) pv[j] = 0.f;
           }
           uint4 o;
           o.x = pack_bf16(pv[0], pv[1]); o.y = pack_bf16(pv[2], pv[3]);
@@ -209,7 +211,7 @@ attn_diag_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const DiagParams
       // ---- epilogue of the same item (the other group runs its softmax meanwhile)
       mbar_wait(&o_full[grp], ph);
       tc_fence_after();
-      const float inv = (l > 0.f) ? 1.0f / l : 0.f;
+      const float inv = (l > 0.f) ? p.drop.inv_keep / l : 0.f;
       __nv_bfloat16* orow = p.out + (static_cast<long long>(it.n) * p.S + it.r0 + r) * p.ldo + it.h * 64;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -421,6 +423,13 @@ attn_diag_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         tmem_ld32(d, x1);            // dV
         tmem_ld32(d + 32, x2);
         tmem_ld_wait();
+        if (p.drop.thresh != 0u) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            x1[j] = __float_as_uint(__uint_as_float(x1[j]) * p.drop.inv_keep);
+            x2[j] = __float_as_uint(__uint_as_float(x2[j]) * p.drop.inv_keep);
+          }
+        }
         store_pair(x1, x2, false, p.v_col0 + it.h * 64);
         tmem_ld32(d + 64, x1);       // dK
         tmem_ld32(d + 96, x2);
@@ -462,6 +471,7 @@ attn_diag_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         mw[0] = mw[1] = mw[2] = mw[3] = 0u;
       }
       const int st = i & 1;
+      const uint32_t rowkey = drop_rowkey(p.drop.seed_lo, p.drop.seed_hi, it.n, it.h, it.r0 + r);
       mbar_wait(&sdp_full[st], (i >> 1) & 1);
       tc_fence_after();
       if (i > 0) mbar_wait(pds_empty, (i - 1) & 1);
@@ -484,9 +494,18 @@ attn_diag_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
           for (int j = 0; j < 8; ++j) {
             const float e = exp2f(__uint_as_float(s[g * 8 + j]) * p.scale_log2 - lse2);
             pv[j] = ((w >> (g * 8 + j)) & 1u) ? e : 0.f;
-            const float t0 = pv[j] * (__uint_as_float(dp[g * 8 + j]) - dsum);
-            eps += t0;
-            dv[j] = t0 * p.scale;
+            float dpe = __uint_as_float(dp[g * 8 + j]);
+            if (p.drop.thresh != 0u) {
+              const bool keep = drop_keep(rowkey, it.r0 + c * 32 + g * 8 + j, p.drop.thresh);
+              dpe = keep ? dpe * p.drop.inv_keep : 0.f;
+              const float t0 = pv[j] * (dpe - dsum);
+              dv[j] = t0 * p.scale;
+              if (!keep) pv[j] = 0.f;          // sP holds the dropped P (unscaled) for dV = (P o mask)^T dO / (1-p)
+            } else {
+              const float t0 = pv[j] * (dpe - dsum);
+              eps += t0;
+              dv[j] = t0 * p.scale;
+            }
           }
           const int chunk = ((cc * 4 + g) ^ (r & 7)) << 4;
           uint4 o, o2;

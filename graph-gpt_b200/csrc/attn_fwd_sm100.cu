@@ -44,6 +44,7 @@ struct AttnFwdParams {
   float* lse;                 // [N, H, S]  natural-log logsumexp of the scaled scores (for backward)
   int q_col0, k_col0, v_col0; // column offsets of q/k/v inside the fused qkv row
   float scale_log2;           // (1/sqrt(64)) * log2(e)
+  DropParams drop;            // attention-probability dropout (training)
 };
 
 // 128 mask bits of query row `mrow` for the key tile starting at key k0 (any alignment) with klen valid keys.
@@ -183,6 +184,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
     float o_acc[64];
 #pragma unroll
     for (int i = 0; i < 64; ++i) o_acc[i] = 0.f;
+    const uint32_t rowkey = drop_rowkey(p.drop.seed_lo, p.drop.seed_hi, n, h, q_row);
     float m_run = -INFINITY;   // running max of scaled (log2-domain) scores
     float l_run = 0.f;
 
@@ -198,6 +200,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
           mw[0] = mw[1] = mw[2] = mw[3] = 0u;
         }
       }
+      const int k0 = ts[kt];
       mbar_wait(s_full, it & 1);
       tc_fence_after();
       // pass 1: row max
@@ -235,6 +238,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
             const float e = exp2f(__uint_as_float(s[g * 8 + j]) * p.scale_log2 - m_use);
             pv[j] = ((w >> (g * 8 + j)) & 1u) ? e : 0.f;
             l_tile += pv[j];
+            if (p.drop.thresh != 0u && !drop_keep(rowkey, k0 + c * 32 + g * 8 + j, p.drop.thresh)) pv[j] = 0.f;
           }
           uint4 o;
           o.x = pack_bf16(pv[0], pv[1]);
@@ -266,7 +270,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
     }
 
     if (row_ok) {
-      const float inv = (l_run > 0.f) ? 1.0f / l_run : 0.f;
+      const float inv = (l_run > 0.f) ? p.drop.inv_keep / l_run : 0.f;   // dropout keeps are rescaled by 1/(1-p)
       __nv_bfloat16* orow = p.out + (static_cast<long long>(n) * p.S + q_row) * p.ldo + h * kHeadDim;
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
@@ -454,8 +458,8 @@ int ggpt_attn_mask_build(const long long* attention_mask, int mask_dims, int N, 
 
 int ggpt_attn_fwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int v_col0, const uint32_t* mask_bits,
                   const int* tile_start, const int* n_tiles, const uint8_t* tile_cls, const uint8_t* iso_flags,
-                  const int* iso_list, const int* iso_count, int run_general, void* out, long long ldo, float* lse, int N,
-                  int S, int H, void* stream) {
+                  const int* iso_list, const int* iso_count, int run_general, float dropout_p, unsigned long long seed,
+                  void* out, long long ldo, float* lse, int N, int S, int H, void* stream) {
   GGPT_REQUIRE(qkv && mask_bits && tile_start && n_tiles && tile_cls && out, "attn_fwd: null pointer");
   GGPT_REQUIRE(N > 0 && S > 0 && H > 0, "attn_fwd: empty problem");
   GGPT_REQUIRE(ld_qkv % 8 == 0 && ldo % 8 == 0 && q_col0 % 8 == 0 && k_col0 % 8 == 0 && v_col0 % 8 == 0,
@@ -471,6 +475,8 @@ int ggpt_attn_fwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int
   p.out = static_cast<__nv_bfloat16*>(out); p.ldo = ldo; p.lse = lse;
   p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
+  GGPT_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "attn_fwd: dropout_p must be in [0,1)");
+  p.drop = make_drop_params(dropout_p, seed);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem);
@@ -492,7 +498,7 @@ int ggpt_attn_fwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int
   d.N = N; d.S = S; d.H = H; d.max_tiles = p.max_tiles; d.mask_words = p.mask_words;
   d.mask_bits = mask_bits; d.tile_start = tile_start; d.tile_cls = tile_cls; d.iso_list = iso_list; d.iso_count = iso_count;
   d.q_col0 = q_col0; d.k_col0 = k_col0; d.v_col0 = v_col0; d.scale = 0.125f; d.scale_log2 = p.scale_log2;
-  d.out = p.out; d.ldo = ldo; d.lse = lse;
+  d.out = p.out; d.ldo = ldo; d.lse = lse; d.drop = p.drop;
   return attn_diag_fwd_launch(tm, d, static_cast<cudaStream_t>(stream));
 }
 

@@ -268,6 +268,42 @@ __device__ __forceinline__ void warp_gather_rows32(const float* __restrict__ tab
   __syncwarp();
 }
 
+// Counter-based dropout mask for attention probabilities: keep(n,h,q,k) is a pure function of (seed, n, h, q, k), so the
+// forward and the backward kernels regenerate identical masks with no stored state (ref: HF:217 attention dropout).
+__device__ __forceinline__ uint32_t fmix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ uint32_t drop_rowkey(uint32_t seed_lo, uint32_t seed_hi, int n, int h, int q) {
+  uint32_t x = fmix32(seed_lo ^ (static_cast<uint32_t>(n) * 0x9E3779B1u));
+  x = fmix32(x ^ seed_hi ^ (static_cast<uint32_t>(h) * 0x85EBCA77u));
+  return fmix32(x ^ (static_cast<uint32_t>(q) * 0xC2B2AE3Du));
+}
+// drop probability = thresh / 2^32
+__device__ __forceinline__ bool drop_keep(uint32_t rowkey, int k, uint32_t thresh) {
+  return fmix32(rowkey + static_cast<uint32_t>(k) * 0x9E3779B1u) >= thresh;
+}
+#endif  // __CUDACC__
+
+struct DropParams {
+  uint32_t thresh;      // 0 = dropout off
+  uint32_t seed_lo, seed_hi;
+  float inv_keep;       // 1 / (1 - p)
+};
+
+inline DropParams make_drop_params(float p, unsigned long long seed) {
+  DropParams d;
+  d.thresh = 0; d.seed_lo = static_cast<uint32_t>(seed); d.seed_hi = static_cast<uint32_t>(seed >> 32); d.inv_keep = 1.0f;
+  if (p > 0.f) {
+    double t = static_cast<double>(p) * 4294967296.0;
+    if (t > 4294967295.0) t = 4294967295.0;
+    d.thresh = static_cast<uint32_t>(t);
+    d.inv_keep = static_cast<float>(1.0 / (1.0 - static_cast<double>(d.thresh) / 4294967296.0));
+  }
+  return d;
+}
+#ifdef __CUDACC__
+
 // erf GELU (transformers ACT2FN["gelu"]) and its derivative from ONE exponential:
 //   Phi(g) = 0.5 (1 + erf(g / sqrt2)),  erf(x) = sign(x) (1 - poly(t) e^{-x^2}),  t = 1 / (1 + 0.3275911 |x|)
 //   (Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7 — far below the bf16 rounding of the outputs), and with

@@ -195,7 +195,7 @@ class HotPath:
         return p
 
     # ------------------------------------------------------------------ backbone
-    def backbone_forward(self, ids2d, N, S, attention_mask, position_ids, stash, droppath_scales=None):
+    def backbone_forward(self, ids2d, N, S, attention_mask, position_ids, stash, droppath_scales=None, attn_dropout=0.0):
         """ids2d int64 [T,F].  Returns final-norm hidden states bf16 [T,d]; fills `stash` (a dict) when not None."""
         fp = self.flat
         cfg = self.cfg
@@ -208,15 +208,18 @@ class HotPath:
         pos, cos, sin = self._rope_inputs(position_ids, N, S, dev)
         mask = ops.attn_mask_build(attention_mask, N, S, cfg.causal_attention, dev)
         keep = stash is not None
+        # attention dropout (HF:217, config.attention_dropout, training only): one 64-bit seed per forward drawn from
+        # torch's CPU generator (so torch.manual_seed controls it); layer i uses seed + i, backward reuses it
+        drop_seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if attn_dropout > 0 else 0
         if keep:
             stash.update(ids=ids2d, N=N, S=S, mask=mask, pos=pos, cos=cos, sin=sin, layers=[], err=err,
-                         long_scale=long_scale)
+                         long_scale=long_scale, attn_dropout=attn_dropout, drop_seed=drop_seed)
         for i in range(self.L):
             p = f"model.layers.{i}."
             rs = None if droppath_scales is None else droppath_scales[i]
             h1, rstd1 = ops.rmsnorm_fwd(x, fp.w(p + "input_layernorm.weight"), self.eps, want_rstd=keep)
             qkv = ops.gemm_qkv_rope(h1, self._wqkv(i), pos, cos, sin, 2 * d)
-            a, lse = ops.attn_fwd(qkv, mask, H, want_lse=keep)
+            a, lse = ops.attn_fwd(qkv, mask, H, want_lse=keep, dropout_p=attn_dropout, seed=drop_seed + i)
             lam1 = fp.w(p + "lambda_1") if self.layer_scale else None
             x2 = ops.gemm_resid(a, fp.wb(p + "self_attn.o_proj.weight"), x, colscale=lam1, rowscale=rs)
             h2, rstd2 = ops.rmsnorm_fwd(x2, fp.w(p + "post_attention_layernorm.weight"), self.eps, want_rstd=keep)
@@ -289,7 +292,7 @@ class HotPath:
             da = ops.gemm(dyb, fp.wb(p + "self_attn.o_proj.weight"), b_mn_major=True)
             ops.gemm(dyb, st["a"], out=fp.g(p + "self_attn.o_proj.weight"), **wgrad)
             dqkv = ops.attn_bwd(da, st["qkv"], st["a"], st["lse"], stash["mask"], H, stash["pos"], stash["cos"],
-                                stash["sin"])
+                                stash["sin"], dropout_p=stash["attn_dropout"], seed=stash["drop_seed"] + i)
             ops.gemm(dqkv, st["h1"], out=self._gqkv(i), **wgrad)
             dh1 = ops.gemm(dqkv, self._wqkv(i), b_mn_major=True)
             dx, dxb = ops.rmsnorm_bwd(dh1, st["x"], st["rstd1"], fp.w(p + "input_layernorm.weight"), dx2,
@@ -340,9 +343,9 @@ class BackboneFn(torch.autograd.Function):
     buffer by backward(); autograd only carries the activation gradient."""
 
     @staticmethod
-    def forward(ctx, hot, ids2d, N, S, attention_mask, position_ids, droppath_scales, *params):
+    def forward(ctx, hot, ids2d, N, S, attention_mask, position_ids, droppath_scales, attn_dropout, *params):
         stash = {}
-        hf = hot.backbone_forward(ids2d, N, S, attention_mask, position_ids, stash, droppath_scales)
+        hf = hot.backbone_forward(ids2d, N, S, attention_mask, position_ids, stash, droppath_scales, attn_dropout)
         ctx.hot, ctx.stash = hot, stash
         return hf
 
@@ -356,7 +359,7 @@ class BackboneFn(torch.autograd.Function):
             dhf = dhf.to(BF16)
         hot.backbone_backward(dhf.contiguous(), stash)
         ctx.stash = None
-        return (None,) * 7 + (None,) * (len(ctx.needs_input_grad) - 7)
+        return (None,) * len(ctx.needs_input_grad)
 
 
 class PretrainHeadFn(torch.autograd.Function):

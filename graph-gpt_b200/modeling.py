@@ -296,11 +296,11 @@ class _GraphGPTBase(nn.Module):
 
     def _check_unsupported_dropout(self):
         cfg = self.config
-        if self.training and (getattr(cfg, "attention_dropout", 0) > 0 or cfg.mlp_pdrop > 0 or cfg.embed_pdrop > 0):
+        if self.training and (cfg.mlp_pdrop > 0 or cfg.embed_pdrop > 0):
             if not getattr(self, "_dropout_warned", False):
                 import warnings
-                warnings.warn("graphgpt_b200: attention_dropout / mlp_pdrop / embed_pdrop are not applied by the "
-                              "sm_100a kernels yet; training proceeds without them")
+                warnings.warn("graphgpt_b200: mlp_pdrop / embed_pdrop are not applied by the sm_100a kernels yet "
+                              "(attention_dropout and DropPath are); training proceeds without them")
                 self._dropout_warned = True
 
     def _run_backbone(self, input_ids, attention_mask, position_ids):
@@ -313,11 +313,12 @@ class _GraphGPTBase(nn.Module):
             attention_mask = attention_mask.to(dev)
         self._check_unsupported_dropout()
         dps = self._droppath_scales(N, S, dev)
+        attn_drop = float(getattr(self.config, "attention_dropout", 0.0) or 0.0) if self.training else 0.0
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             params = [p for _, p in hot.flat.order]
-            hf = BackboneFn.apply(hot, ids2d, N, S, attention_mask, position_ids, dps, *params)
+            hf = BackboneFn.apply(hot, ids2d, N, S, attention_mask, position_ids, dps, attn_drop, *params)
         else:
-            hf = hot.backbone_forward(ids2d, N, S, attention_mask, position_ids, None, dps)
+            hf = hot.backbone_forward(ids2d, N, S, attention_mask, position_ids, None, dps, attn_drop)
         return hf, in_, N, S
 
 

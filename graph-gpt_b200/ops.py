@@ -176,7 +176,7 @@ def attn_mask_build(attention_mask, N, S, causal, device):
     return AttnMask(bits, tile_start, n_tiles, cls, iso_flags, iso_list, iso_count, N, S)
 
 
-def attn_fwd(qkv, mask: AttnMask, H, *, want_lse=True):
+def attn_fwd(qkv, mask: AttnMask, H, *, want_lse=True, dropout_p=0.0, seed=0):
     """qkv bf16 [N*S, 3*H*64] (q | k | v).  Returns (out bf16 [N*S, H*64], lse f32 [N,H,S] or None)."""
     _check(qkv, BF16, "attn_fwd qkv", 2)
     N, S = mask.N, mask.S
@@ -186,12 +186,12 @@ def attn_fwd(qkv, mask: AttnMask, H, *, want_lse=True):
     out = torch.empty((N * S, d), device=qkv.device, dtype=BF16)
     lse = torch.empty((N, H, S), device=qkv.device, dtype=F32) if want_lse else None
     lib.ggpt_attn_fwd(qkv.data_ptr(), qkv.stride(0), 0, d, 2 * d, mask.bits.data_ptr(), mask.tile_start.data_ptr(),
-                      mask.n_tiles.data_ptr(), mask.cls.data_ptr(), *mask._iso_args(), out.data_ptr(), out.stride(0),
-                      _ptr(lse), N, S, H, _stream())
+                      mask.n_tiles.data_ptr(), mask.cls.data_ptr(), *mask._iso_args(), float(dropout_p), int(seed),
+                      out.data_ptr(), out.stride(0), _ptr(lse), N, S, H, _stream())
     return out, lse
 
 
-def attn_bwd(dout, qkv, out, lse, mask: AttnMask, H, pos, cos_tab, sin_tab):
+def attn_bwd(dout, qkv, out, lse, mask: AttnMask, H, pos, cos_tab, sin_tab, *, dropout_p=0.0, seed=0):
     """Returns dqkv bf16 [N*S, 3*H*64] (gradient of the fused projection output, RoPE already undone)."""
     _check(dout, BF16, "attn_bwd dout", 2)
     _check(qkv, BF16, "attn_bwd qkv", 2)
@@ -202,7 +202,8 @@ def attn_bwd(dout, qkv, out, lse, mask: AttnMask, H, pos, cos_tab, sin_tab):
     dsum = torch.empty((N, H, S), device=qkv.device, dtype=F32)
     lib.ggpt_attn_bwd(qkv.data_ptr(), qkv.stride(0), 0, d, 2 * d, out.data_ptr(), out.stride(0), dout.data_ptr(),
                       dout.stride(0), lse.data_ptr(), mask.bits.data_ptr(), mask.tile_start.data_ptr(),
-                      mask.n_tiles.data_ptr(), mask.cls.data_ptr(), *mask._iso_args(), pos.data_ptr(),
+                      mask.n_tiles.data_ptr(), mask.cls.data_ptr(), *mask._iso_args(), float(dropout_p), int(seed),
+                      pos.data_ptr(),
                       cos_tab.data_ptr(), sin_tab.data_ptr(), dsum.data_ptr(), dqkv.data_ptr(), dqkv.stride(0), N, S, H,
                       _stream())
     return dqkv

@@ -95,12 +95,14 @@ int ggpt_attn_mask_build(const long long* attention_mask, int mask_dims, int N, 
                          int* tile_start, int* n_tiles, uint8_t* tile_cls, uint8_t* iso_flags, int* iso_list,
                          int* iso_count, void* stream);
 
-/* out[N*S, H*64] = softmax(q k^T / 8 + mask) v per head; lse[N,H,S] (may be NULL) = log-sum-exp of the scaled
- * scores, kept for the backward pass.   ref: HF:199-221 (eager_attention_forward), fp32 softmax. */
+/* out[N*S, H*64] = dropout(softmax(q k^T / 8 + mask)) v per head; lse[N,H,S] (may be NULL) = log-sum-exp of the scaled
+ * scores, kept for the backward pass.  dropout_p > 0 (training, config.attention_dropout) drops attention
+ * probabilities with a counter-based mask that is a pure function of (seed, n, h, q, k); pass the same (dropout_p, seed)
+ * to ggpt_attn_bwd.   ref: HF:199-221 (eager_attention_forward: fp32 softmax, dropout on the weights). */
 int ggpt_attn_fwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int v_col0, const uint32_t* mask_bits,
                   const int* tile_start, const int* n_tiles, const uint8_t* tile_cls, const uint8_t* iso_flags,
-                  const int* iso_list, const int* iso_count, int run_general, void* out, long long ldo, float* lse, int N,
-                  int S, int H, void* stream);
+                  const int* iso_list, const int* iso_count, int run_general, float dropout_p, unsigned long long seed,
+                  void* out, long long ldo, float* lse, int N, int S, int H, void* stream);
 
 /* dqkv[N*S, ld_dqkv] (bf16) = gradient of the fused q|k|v projection output given dout = dL/d(attention output).
  * Recomputes P from lse; two deterministic tcgen05 passes (dK,dV then dQ); dQ/dK are un-rotated (inverse RoPE)
@@ -109,7 +111,7 @@ int ggpt_attn_fwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int
 int ggpt_attn_bwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int v_col0, const void* out, long long ldo,
                   const void* dout, long long lddo, const float* lse, const uint32_t* mask_bits, const int* tile_start,
                   const int* n_tiles, const uint8_t* tile_cls, const uint8_t* iso_flags, const int* iso_list,
-                  const int* iso_count, int run_general, const int* pos, const float* cos_tab, const float* sin_tab, float* dsum_scratch, void* dqkv,
+                  const int* iso_count, int run_general, float dropout_p, unsigned long long seed, const int* pos, const float* cos_tab, const float* sin_tab, float* dsum_scratch, void* dqkv,
                   long long ld_dqkv, int N, int S, int H, void* stream);
 
 /* ---------------------------------------------------------------------------------------------

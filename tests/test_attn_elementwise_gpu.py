@@ -377,3 +377,60 @@ def test_attn_diag_path_matches_general_path(S, H, monkeypatch):
         err = (a - b_).abs().max().item()
         scale = b_.abs().max().item()
         assert err <= tol * scale, f"{name}: diag vs general max err {err} (scale {scale})"
+
+
+@pytest.mark.parametrize("kind,S", [("packed", 384), ("none", 256)])
+def test_attn_dropout_consistent_forward_backward(kind, S):
+    """Attention dropout (HF:217): the kernels regenerate the keep mask from (seed, n, h, q, k).  Recover the mask
+    from a forward pass with V = identity-like probes, then check forward output and dq/dk/dv against torch autograd
+    of softmax -> (mask / (1-p)) -> PV with that same mask; also check the drop rate and seed sensitivity."""
+    from graphgpt_b200 import ops, synth
+    N, H, p_drop, seed = 2, 2, 0.25, 123456789
+    d = H * 64
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(S)
+    if kind == "packed":
+        am = torch.from_numpy(synth.make_batch(N, S, layout="packed", seed=5)["attention_mask"]).to(dev)
+    else:
+        am = None
+    mask = ops.attn_mask_build(am, N, S, False, dev)
+    # ---- recover the keep mask column block by column block: uniform scores (q = 0) and one-hot V rows
+    keep = torch.zeros((N, H, S, S), device=dev)
+    visible = torch.ones((N, 1, S, S), dtype=torch.bool, device=dev) if am is None else am[:, None].bool()
+    nvis = visible.sum(-1, keepdim=True).float()
+    for kb in range(0, S, 64):
+        qkv = torch.zeros((N, S, 3, H, 64), device=dev)
+        for j in range(min(64, S - kb)):
+            qkv[:, kb + j, 2, :, j] = 1.0
+        out, _ = ops.attn_fwd(qkv.reshape(N * S, 3 * d).to(torch.bfloat16), mask, H, dropout_p=p_drop, seed=seed)
+        o = out.float().view(N, S, H, 64).permute(0, 2, 1, 3)               # [N,H,S,64] = P_drop[:, :, :, kb:kb+64]
+        keep[:, :, :, kb:kb + 64] = (o[..., : min(64, S - kb)] * nvis > 0.5).float()
+    keep = keep * visible
+    rate = 1.0 - keep.sum().item() / visible.expand(N, H, S, S).sum().item()
+    assert abs(rate - p_drop) < 0.01, f"drop rate {rate}"
+    # ---- forward / backward parity with the recovered mask
+    qkv_b = (torch.randn((N * S, 3 * d), generator=g) * 1.2).to(torch.bfloat16).to(dev)
+    dout = torch.randn((N * S, d), generator=g).to(torch.bfloat16).to(dev)
+    x = qkv_b.float().requires_grad_(True)
+    xx = x.view(N, S, 3, H, 64)
+    q, k, v = (xx[:, :, i].transpose(1, 2) for i in range(3))
+    s_ = (q @ k.transpose(2, 3)) * 0.125
+    s_ = s_.masked_fill(~visible, float("-inf"))
+    pr = torch.softmax(s_, -1) * keep / (1.0 - p_drop)
+    ref_o = (pr @ v).transpose(1, 2).reshape(N * S, d)
+    ref_o.backward(dout.float())
+    out, lse = ops.attn_fwd(qkv_b, mask, H, dropout_p=p_drop, seed=seed)
+    pos = torch.zeros((N * S,), dtype=torch.int32, device=dev)
+    cos_tab = torch.ones((1, 32), device=dev)
+    sin_tab = torch.zeros((1, 32), device=dev)
+    dqkv = ops.attn_bwd(dout, qkv_b, out, lse, mask, H, pos, cos_tab, sin_tab, dropout_p=p_drop, seed=seed)
+    torch.cuda.synchronize()
+    assert (out.float() - ref_o).abs().max().item() <= 1.5e-2 * ref_o.abs().max().item()
+    for name, sl in (("dq", slice(0, d)), ("dk", slice(d, 2 * d)), ("dv", slice(2 * d, 3 * d))):
+        a, b_ = dqkv[:, sl].float(), x.grad[:, sl]
+        rel = ((a - b_).norm() / b_.norm()).item()
+        assert rel <= 2e-2, f"{name} relF {rel}"
+    out2, _ = ops.attn_fwd(qkv_b, mask, H, dropout_p=p_drop, seed=seed + 1)
+    assert (out2.float() - out.float()).abs().max().item() > 1e-2          # a different seed gives a different mask
+    out3, _ = ops.attn_fwd(qkv_b, mask, H, dropout_p=p_drop, seed=seed)
+    assert torch.equal(out3, out)                                          # same seed: bitwise reproducible
