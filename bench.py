@@ -28,7 +28,7 @@ MODEL = dict(vocab_size=756, hidden_size=768, intermediate_size=3072, num_hidden
              num_key_value_heads=12, head_dim=64, hidden_act="gelu", max_position_embeddings=1024, rms_norm_eps=1e-6,
              rope_theta=10000.0, pad_token_id=0, bos_token_id=20, eos_token_id=19, causal_attention=False,
              stacked_feat=13, stack_method="short", stacked_feat_agg_method="sum", next_n_token=13, use_cache=False,
-             attention_dropout=0.0)
+             attention_dropout=0.1)   # examples/graph_lvl/pcqm4m_v2_pretrain.sh:20 — active in the training step
 SEQ = 1024
 METRIC = "tokens/sec (device-timed) PCQM4M-v2 SMTP pretrain"
 
@@ -333,7 +333,26 @@ def run_b200(args):
 
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
-        run_reference(a)
-    else:
-        run_b200(a)
+    # stdout must carry exactly ONE JSON line (rank 0): anything libraries print there (e.g. NCCL's version banner)
+    # is diverted to stderr, and the result line is written to the original stdout at the end.
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    _buf = []
+    _print = print
+
+    def print(*args, **kw):  # noqa: A001 - the only print() calls below emit the result line
+        _buf.append(" ".join(str(x) for x in args))
+
+    import builtins
+    builtins.print = print
+    try:
+        if a.impl == "reference":
+            run_reference(a)
+        else:
+            run_b200(a)
+    finally:
+        builtins.print = _print
+        sys.stdout.flush()
+        os.dup2(_real_stdout, 1)
+        for line in _buf:
+            os.write(1, (line + "\n").encode())
