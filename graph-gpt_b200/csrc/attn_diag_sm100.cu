@@ -167,39 +167,58 @@ attn_diag_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const DiagParams
       mbar_wait(&s_full[grp], ph);
       tc_fence_after();
       float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // independent chains: ILP instead of a 128-deep max
+      // Packed segments leave most of a 128 x 128 tile masked (~24 visible keys per row): 32-column chunks / 8-column
+      // groups that no row of this warp can see are skipped (warp-uniform votes), they only get their zeros stored.
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
+        const uint32_t w = (c == 0) ? mw[0] : (c == 1) ? mw[1] : (c == 2) ? mw[2] : mw[3];
+        if (!__any_sync(0xffffffffu, w != 0u)) continue;
         uint32_t s[32];
         tmem_ld32(tS + c * 32, s);
         tmem_ld_wait();
-        const uint32_t w = (c == 0) ? mw[0] : (c == 1) ? mw[1] : (c == 2) ? mw[2] : mw[3];
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          m4[j & 3] = fmaxf(m4[j & 3], ((w >> j) & 1u) ? __uint_as_float(s[j]) * p.scale_log2 : -INFINITY);
+        for (int g = 0; g < 4; ++g) {
+          if (!__any_sync(0xffffffffu, ((w >> (g * 8)) & 0xffu) != 0u)) continue;
+#pragma unroll
+          for (int j = g * 8; j < g * 8 + 8; ++j)
+            m4[j & 3] = fmaxf(m4[j & 3], ((w >> j) & 1u) ? __uint_as_float(s[j]) : -INFINITY);
+        }
       }
-      const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * p.scale_log2;   // scale > 0 commutes with max
       const float m_use = (m == -INFINITY) ? 0.f : m;
       float l4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
+        const uint32_t w = (c == 0) ? mw[0] : (c == 1) ? mw[1] : (c == 2) ? mw[2] : mw[3];
+        uint8_t* pbase = sP + (c >> 1) * 16384 + r * 128;
+        if (!__any_sync(0xffffffffu, w != 0u)) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<uint4*>(pbase + ((((c & 1) * 4 + g) ^ (r & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+          continue;
+        }
         uint32_t s[32];
         tmem_ld32(tS + c * 32, s);
         tmem_ld_wait();
-        const uint32_t w = (c == 0) ? mw[0] : (c == 1) ? mw[1] : (c == 2) ? mw[2] : mw[3];
-        uint8_t* pbase = sP + (c >> 1) * 16384 + r * 128;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          float pv[8];
+          uint4 o = make_uint4(0u, 0u, 0u, 0u);
+          if (__any_sync(0xffffffffu, ((w >> (g * 8)) & 0xffu) != 0u)) {
+            float pv[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float e = exp2f(__uint_as_float(s[g * 8 + j]) * p.scale_log2 - m_use);
-            pv[j] = ((w >> (g * 8 + j)) & 1u) ? e : 0.f;
-            l4[j & 3] += pv[j];
-            if (p.drop.thresh != 0u && !drop_keep(rowkey, it.r0 + c * 32 + g * 8 + j, p.drop.thresh)) pv[j] = 0.f;
+            for (int j = 0; j < 8; ++j) {
+              const float e = fast_exp2(fmaf(__uint_as_float(s[g * 8 + j]), p.scale_log2, -m_use));
+              pv[j] = ((w >> (g * 8 + j)) & 1u) ? e : 0.f;
+              l4[j & 3] += pv[j];
+            }
+            if (p.drop.thresh != 0u) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (!drop_keep(rowkey, it.r0 + c * 32 + g * 8 + j, p.drop.thresh)) pv[j] = 0.f;
+            }
+            o.x = pack_bf16(pv[0], pv[1]); o.y = pack_bf16(pv[2], pv[3]);
+            o.z = pack_bf16(pv[4], pv[5]); o.w = pack_bf16(pv[6], pv[7]);
           }
-          uint4 o;
-          o.x = pack_bf16(pv[0], pv[1]); o.y = pack_bf16(pv[2], pv[3]);
-          o.z = pack_bf16(pv[4], pv[5]); o.w = pack_bf16(pv[6], pv[7]);
           *reinterpret_cast<uint4*>(pbase + ((((c & 1) * 4 + g) ^ (r & 7)) << 4)) = o;
         }
       }
@@ -477,42 +496,54 @@ attn_diag_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       if (i > 0) mbar_wait(pds_empty, (i - 1) & 1);
       const uint32_t tS = tmem_base + st * 256 + lane_addr;
       float eps = 0.f;
+      // chunks / groups no row of this warp can see only get zeros stored (see the forward kernel)
 #pragma unroll 1
       for (int cc = 0; cc < 2; ++cc) {
         const int c = half * 2 + cc;
+        const uint32_t w = (c == 0) ? mw[0] : (c == 1) ? mw[1] : (c == 2) ? mw[2] : mw[3];
+        uint8_t* pbase = sP + half * 16384 + r * 128;
+        uint8_t* dbase = sDS + half * 16384 + r * 128;
+        if (!__any_sync(0xffffffffu, w != 0u)) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int chunk = ((cc * 4 + g) ^ (r & 7)) << 4;
+            *reinterpret_cast<uint4*>(pbase + chunk) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(dbase + chunk) = make_uint4(0u, 0u, 0u, 0u);
+          }
+          continue;
+        }
         uint32_t s[32], dp[32];
         tmem_ld32(tS + c * 32, s);
         tmem_ld32(tS + 128 + c * 32, dp);
         tmem_ld_wait();
-        const uint32_t w = (c == 0) ? mw[0] : (c == 1) ? mw[1] : (c == 2) ? mw[2] : mw[3];
-        uint8_t* pbase = sP + half * 16384 + r * 128;
-        uint8_t* dbase = sDS + half * 16384 + r * 128;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          float pv[8], dv[8];
+          uint4 o = make_uint4(0u, 0u, 0u, 0u), o2 = make_uint4(0u, 0u, 0u, 0u);
+          if (__any_sync(0xffffffffu, ((w >> (g * 8)) & 0xffu) != 0u)) {
+            float pv[8], dv[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float e = exp2f(__uint_as_float(s[g * 8 + j]) * p.scale_log2 - lse2);
-            pv[j] = ((w >> (g * 8 + j)) & 1u) ? e : 0.f;
-            float dpe = __uint_as_float(dp[g * 8 + j]);
-            if (p.drop.thresh != 0u) {
-              const bool keep = drop_keep(rowkey, it.r0 + c * 32 + g * 8 + j, p.drop.thresh);
-              dpe = keep ? dpe * p.drop.inv_keep : 0.f;
-              const float t0 = pv[j] * (dpe - dsum);
-              dv[j] = t0 * p.scale;
-              if (!keep) pv[j] = 0.f;          // sP holds the dropped P (unscaled) for dV = (P o mask)^T dO / (1-p)
-            } else {
-              const float t0 = pv[j] * (dpe - dsum);
-              eps += t0;
-              dv[j] = t0 * p.scale;
+            for (int j = 0; j < 8; ++j) {
+              const float e = fast_exp2(fmaf(__uint_as_float(s[g * 8 + j]), p.scale_log2, -lse2));
+              pv[j] = ((w >> (g * 8 + j)) & 1u) ? e : 0.f;
+              float dpe = __uint_as_float(dp[g * 8 + j]);
+              if (p.drop.thresh != 0u) {
+                const bool keep = drop_keep(rowkey, it.r0 + c * 32 + g * 8 + j, p.drop.thresh);
+                dpe = keep ? dpe * p.drop.inv_keep : 0.f;
+                const float t0 = pv[j] * (dpe - dsum);
+                dv[j] = t0 * p.scale;
+                if (!keep) pv[j] = 0.f;          // sP holds the dropped P (unscaled) for dV = (P o mask)^T dO / (1-p)
+              } else {
+                const float t0 = pv[j] * (dpe - dsum);
+                eps += t0;
+                dv[j] = t0 * p.scale;
+              }
             }
+            o.x = pack_bf16(pv[0], pv[1]); o.y = pack_bf16(pv[2], pv[3]);
+            o.z = pack_bf16(pv[4], pv[5]); o.w = pack_bf16(pv[6], pv[7]);
+            o2.x = pack_bf16(dv[0], dv[1]); o2.y = pack_bf16(dv[2], dv[3]);
+            o2.z = pack_bf16(dv[4], dv[5]); o2.w = pack_bf16(dv[6], dv[7]);
           }
           const int chunk = ((cc * 4 + g) ^ (r & 7)) << 4;
-          uint4 o, o2;
-          o.x = pack_bf16(pv[0], pv[1]); o.y = pack_bf16(pv[2], pv[3]);
-          o.z = pack_bf16(pv[4], pv[5]); o.w = pack_bf16(pv[6], pv[7]);
-          o2.x = pack_bf16(dv[0], dv[1]); o2.y = pack_bf16(dv[2], dv[3]);
-          o2.z = pack_bf16(dv[4], dv[5]); o2.w = pack_bf16(dv[6], dv[7]);
           *reinterpret_cast<uint4*>(pbase + chunk) = o;
           *reinterpret_cast<uint4*>(dbase + chunk) = o2;
         }

@@ -149,6 +149,55 @@ __global__ void rmsnorm_fwd_kernel(const float* __restrict__ x, const float* __r
   }
 }
 
+// Fused residual add + RMSNorm:  x_out = x_in + rowscale[t] * colscale[:] * y   (y = bf16 branch output of o_proj /
+// down_proj; colscale = LayerScale lambda, rowscale = DropPath scale, both optional), h = bf16(w * x_out * rstd).
+// One HBM pass (600 B/token-dim... 4+2 in, 4+2 out) instead of a latency-bound fp32 read-modify-write in the GEMM
+// epilogue followed by a separate norm pass.   ref: HF:325,331 (residual adds) + HF:59-64 (next RMSNorm)
+__global__ void add_rmsnorm_fwd_kernel(const float* __restrict__ x_in, const __nv_bfloat16* __restrict__ y, long long ldy,
+                                       const float* __restrict__ colscale, const float* __restrict__ rowscale,
+                                       const float* __restrict__ w, float* __restrict__ x_out,
+                                       __nv_bfloat16* __restrict__ h, float* __restrict__ rstd_out, long long T, int d,
+                                       float eps) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  for (long long t = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); t < T;
+       t += static_cast<long long>(gridDim.x) * warps_per_block) {
+    const float* xr = x_in + t * d;
+    const __nv_bfloat16* yr = y + t * ldy;
+    float* xo = x_out + t * d;
+    const float rs = rowscale != nullptr ? rowscale[t] : 1.0f;
+    float ss = 0.f;
+    for (int c = lane * 4; c < d; c += 128) {
+      const float4 xv = *reinterpret_cast<const float4*>(xr + c);
+      const uint2 yv = *reinterpret_cast<const uint2*>(yr + c);
+      const float2 y01 = unpack_bf16(yv.x), y23 = unpack_bf16(yv.y);
+      float4 sc = make_float4(rs, rs, rs, rs);
+      if (colscale != nullptr) {
+        const float4 cs = *reinterpret_cast<const float4*>(colscale + c);
+        sc.x *= cs.x; sc.y *= cs.y; sc.z *= cs.z; sc.w *= cs.w;
+      }
+      float4 o;
+      o.x = fmaf(y01.x, sc.x, xv.x); o.y = fmaf(y01.y, sc.y, xv.y);
+      o.z = fmaf(y23.x, sc.z, xv.z); o.w = fmaf(y23.y, sc.w, xv.w);
+      *reinterpret_cast<float4*>(xo + c) = o;
+      ss += o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
+    }
+    ss = warp_sum(ss);
+    const float rstd = rsqrtf(ss / static_cast<float>(d) + eps);
+    if (lane == 0 && rstd_out != nullptr) rstd_out[t] = rstd;
+    if (h == nullptr) continue;
+    __nv_bfloat16* hr = h + t * d;
+    for (int c = lane * 4; c < d; c += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(xo + c);     // just written by this lane: L1/L2 hit
+      const float4 ww = *reinterpret_cast<const float4*>(w + c);
+      uint2 o;
+      o.x = pack_bf16(ww.x * (v.x * rstd), ww.y * (v.y * rstd));
+      o.y = pack_bf16(ww.z * (v.z * rstd), ww.w * (v.w * rstd));
+      *reinterpret_cast<uint2*>(hr + c) = o;
+    }
+  }
+}
+
 // dx_out = dresid + rstd * (g - xhat * mean(g * xhat)),  g = dy * w,  xhat = x * rstd;  dw += sum_t dy * xhat
 // Also emits a bf16 copy of dx_out (the A operand of the next dgrad GEMMs).
 // Each lane owns the same columns (lane*4 + k*128) for every row its warp visits, so the row is held in registers
@@ -618,6 +667,16 @@ int ggpt_rmsnorm_fwd(const float* x, const float* w, void* y, long long ldy, flo
   rmsnorm_fwd_kernel<<<grid_for_rows(T, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       x, w, static_cast<__nv_bfloat16*>(y), ldy, rstd, T, d, eps);
   return check_launch("rmsnorm_fwd_kernel");
+}
+
+int ggpt_add_rmsnorm_fwd(const float* x_in, const void* y, long long ldy, const float* colscale, const float* rowscale,
+                         const float* w, float* x_out, void* h, float* rstd, long long T, int d, float eps, void* stream) {
+  GGPT_REQUIRE(x_in && y && w && x_out, "add_rmsnorm_fwd: null pointer");
+  GGPT_REQUIRE(T > 0 && d % 4 == 0 && ldy % 4 == 0, "add_rmsnorm_fwd: bad sizes");
+  add_rmsnorm_fwd_kernel<<<grid_for_rows(T, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x_in, static_cast<const __nv_bfloat16*>(y), ldy, colscale, rowscale, w, x_out, static_cast<__nv_bfloat16*>(h), rstd, T,
+      d, eps);
+  return check_launch("add_rmsnorm_fwd_kernel");
 }
 
 int ggpt_rmsnorm_bwd(const void* dy, long long lddy, const float* x, const float* rstd, const float* w,

@@ -58,21 +58,22 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kGemmThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant)
 
-template <int BN>
+template <int BN, bool PAIR>
 struct GemmSmem {
   static constexpr int kABytes = BM * BK * 2;  // 16 KB
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBBytes = (PAIR ? BN / 2 : BN) * BK * 2;   // a CTA of a pair holds half of the B tile's rows
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kStages = (BN == 256 && !PAIR) ? 4 : 6;
   static constexpr int kStagingBytes = 8 * 4096;   // one 32 x 128 B transposition buffer per epilogue warp
   static constexpr int kBarBytes = 256;
   static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kBarBytes + 1024;  // +1024 alignment slack
 };
 
-template <int BN, bool A_MN, bool B_MN, int EPI, int CL>
+template <int BN, bool A_MN, bool B_MN, int EPI, int CL, bool PAIR>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using S = GemmSmem<BN>;
+  static_assert(!PAIR || CL == 2, "a CTA pair is a cluster of two");
+  using S = GemmSmem<BN, PAIR>;
   constexpr int kStages = S::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -86,7 +87,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   // work items = (m-block group of CL, n-block, k-split); the CTAs of a cluster take consecutive m-blocks
-  const int num_tiles = ((p.num_m_blocks + CL - 1) / CL) * p.num_n_blocks * p.num_splits;
+  // k-split is the SLOW index: the CTAs running concurrently work on the same K range of different output tiles, so the
+  // A / B slabs of that range are fetched from HBM once and shared through L2 (split-fastest order re-read them ~2x).
+  const int mn_tiles = ((p.num_m_blocks + CL - 1) / CL) * p.num_n_blocks;
+  const int num_tiles = mn_tiles * p.num_splits;
   const int rank = (CL > 1) ? static_cast<int>(cluster_ctarank()) : 0;
   const int item0 = blockIdx.x / CL;
   const int item_stride = gridDim.x / CL;
@@ -97,17 +101,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], CL);   // released by the MMA warp of every CTA that receives the multicast B tile
+      // multicast mode: released by the MMA warp of every CTA that receives the multicast B tile;
+      // pair mode: released by the leader's (multicast) commit only
+      mbar_init(&empty_bar[s], PAIR ? 1 : CL);
     }
     mbar_init(&tfull_bar[0], 1);
     mbar_init(&tfull_bar[1], 1);
-    mbar_init(&tempty_bar[0], 8);
-    mbar_init(&tempty_bar[1], 8);
+    mbar_init(&tempty_bar[0], PAIR ? 16 : 8);   // pair mode: the epilogue warps of BOTH CTAs arrive on the leader's barrier
+    mbar_init(&tempty_bar[1], PAIR ? 16 : 8);
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 2 * BN);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc_pair(tmem_slot, 2 * BN);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, 2 * BN);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   if (CL > 1) cluster_sync_all();   // peers' barriers must be initialised before any multicast / remote arrive
@@ -121,7 +132,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int stage = 0;
       uint32_t phase = 0;
       for (int item = item0; item < num_tiles; item += item_stride) {
-        const int tile = item / p.num_splits, split = item % p.num_splits;
+        const int tile = item % mn_tiles, split = item / mn_tiles;
         const int m0 = ((tile / p.num_n_blocks) * CL + rank) * BM;
         const int nb = tile % p.num_n_blocks;
         const int kb0 = split * p.kb_per_split;
@@ -130,8 +141,34 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * S::kStageBytes;
           uint8_t* sb = sa + S::kABytes;
-          mbar_expect_tx(&full_bar[stage], S::kStageBytes);
           const int k0 = kb * BK;
+          if constexpr (PAIR) {
+            // Both CTAs load their own 128 rows of A and their own half of B's rows into their own smem; every byte
+            // completes on the LEADER's full barrier, which therefore expects two stages' worth.
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * S::kStageBytes);
+            if (!A_MN) {
+              tma_load_2d_pair(sa, &tmA, &full_bar[stage], k0, m0);
+            } else {
+              tma_load_2d_pair(sa, &tmA, &full_bar[stage], m0, k0);
+              tma_load_2d_pair(sa + 8192, &tmA, &full_bar[stage], m0 + 64, k0);
+            }
+            if (EPI == EPI_GEGLU) {          // leader: gate rows, peer: the matching up rows
+              const int nh = nb * (BN / 2);
+              tma_load_2d_pair(sb, &tmB, &full_bar[stage], k0, rank ? p.b_half_rows + nh : nh);
+            } else if (!B_MN) {
+              tma_load_2d_pair(sb, &tmB, &full_bar[stage], k0, nb * BN + rank * (BN / 2));
+            } else {
+#pragma unroll
+              for (int i = 0; i < BN / 128; ++i)
+                tma_load_2d_pair(sb + i * 8192, &tmB, &full_bar[stage], nb * BN + (rank * (BN / 128) + i) * 64, k0);
+            }
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
+          mbar_expect_tx(&full_bar[stage], S::kStageBytes);
           if (!A_MN) {
             tma_load_2d(sa, &tmA, &full_bar[stage], k0, m0);
           } else {
@@ -175,14 +212,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+    if (lane == 0 && (!PAIR || rank == 0)) {   // pair mode: the leader issues every MMA for both CTAs
+      constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * BM : BM, BN, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int item = item0; item < num_tiles; item += item_stride) {
-        const int split = item % p.num_splits;
+        const int split = item / mn_tiles;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -199,16 +236,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                         : umma_desc_sw128(sa + kk * 32, 16, 1024);
             const uint64_t bdesc = B_MN ? umma_desc_sw128(sb + kk * 2048, 8192, 1024)
                                         : umma_desc_sw128(sb + kk * 32, 16, 1024);
-            tc_mma_bf16(d_tmem, adesc, bdesc, idesc, (kb != kb0 || kk != 0) ? 1u : 0u);
+            if (PAIR) tc_mma_bf16_pair(d_tmem, adesc, bdesc, idesc, (kb != kb0 || kk != 0) ? 1u : 0u);
+            else tc_mma_bf16(d_tmem, adesc, bdesc, idesc, (kb != kb0 || kk != 0) ? 1u : 0u);
           }
-          if (CL > 1) tc_commit_mc(&empty_bar[stage], 3);   // frees the slot in BOTH CTAs (multicast B lands in both)
-          else tc_commit(&empty_bar[stage]);                // frees the smem slot when these MMAs retire
+          if (PAIR) tc_commit_pair_mc(&empty_bar[stage], 3);     // frees the slot in both CTAs of the pair
+          else if (CL > 1) tc_commit_mc(&empty_bar[stage], 3);   // frees the slot in BOTH CTAs (multicast B lands in both)
+          else tc_commit(&empty_bar[stage]);                     // frees the smem slot when these MMAs retire
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        tc_commit(&tfull_bar[acc]);  // accumulator complete
+        if (PAIR) tc_commit_pair_mc(&tfull_bar[acc], 3);   // each CTA's epilogue drains its own 128 rows
+        else tc_commit(&tfull_bar[acc]);                   // accumulator complete
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -246,7 +286,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int item = item0; item < num_tiles; item += item_stride) {
-      const int tile = item / p.num_splits;
+      const int tile = item % mn_tiles;
       const int m0 = ((tile / p.num_n_blocks) * CL + rank) * BM;
       const int nb = tile % p.num_n_blocks;
       const int row0 = m0 + quad * 32;                 // first global row of this warp's quadrant
@@ -434,7 +474,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(&tempty_bar[acc], 0);
+        else mbar_arrive(&tempty_bar[acc]);
+      }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
@@ -447,16 +490,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BN);
+    if (PAIR) tmem_dealloc_pair(tmem_base, 2 * BN);
+    else tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // Host launcher
 // ---------------------------------------------------------------------------------------------
-template <int BN, bool A_MN, bool B_MN, int EPI, int CL>
+template <int BN, bool A_MN, bool B_MN, int EPI, int CL, bool PAIR>
 static int launch_gemm_cl(const void* A, long long lda, const void* B, long long ldb, GemmParams p, cudaStream_t stream) {
-  using S = GemmSmem<BN>;
+  using S = GemmSmem<BN, PAIR>;
   CUtensorMap tmA, tmB;
   int rc;
   // A: K-major -> global [M rows, K cols], box 128 x 64.  MN-major -> global [K rows, M cols], box 64 x 64.
@@ -474,7 +518,7 @@ static int launch_gemm_cl(const void* A, long long lda, const void* B, long long
   int grid = num_sms() / CL * CL;
   if (grid > items * CL) grid = items * CL;
 
-  auto kern = gemm_kernel<BN, A_MN, B_MN, EPI, CL>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, EPI, CL, PAIR>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
@@ -528,9 +572,12 @@ static int launch_gemm(const void* A, long long lda, const void* B, long long ld
   p.kb_per_split = (p.num_k_blocks + p.num_splits - 1) / p.num_splits;
   p.num_splits = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;   // no empty splits
   // clusters of two CTAs along M share (multicast) the B tile; single m-block problems stay un-clustered
-  static const bool no_cluster = getenv("GGPT_GEMM_NO_CLUSTER") != nullptr;
-  if (p.num_m_blocks >= 2 && !no_cluster) return launch_gemm_cl<BN, A_MN, B_MN, EPI, 2>(A, lda, B, ldb, p, stream);
-  return launch_gemm_cl<BN, A_MN, B_MN, EPI, 1>(A, lda, B, ldb, p, stream);
+  // (GGPT_GEMM_MODE = single | multicast | pair overrides the choice — a profiling aid)
+  static const char* mode_env = getenv("GGPT_GEMM_MODE");
+  static const int mode = mode_env == nullptr ? 2 : (mode_env[0] == 's' ? 0 : (mode_env[0] == 'm' ? 1 : 2));
+  if (p.num_m_blocks >= 2 && mode == 2) return launch_gemm_cl<BN, A_MN, B_MN, EPI, 2, true>(A, lda, B, ldb, p, stream);
+  if (p.num_m_blocks >= 2 && mode == 1) return launch_gemm_cl<BN, A_MN, B_MN, EPI, 2, false>(A, lda, B, ldb, p, stream);
+  return launch_gemm_cl<BN, A_MN, B_MN, EPI, 1, false>(A, lda, B, ldb, p, stream);
 }
 
 template <int BN, int EPI>

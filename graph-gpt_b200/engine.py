@@ -214,23 +214,31 @@ class HotPath:
         if keep:
             stash.update(ids=ids2d, N=N, S=S, mask=mask, pos=pos, cos=cos, sin=sin, layers=[], err=err,
                          long_scale=long_scale, attn_dropout=attn_dropout, drop_seed=drop_seed)
+        # Layer i:  h1 = norm(x) -> qkv(+RoPE) -> attention -> y1 = o_proj -> [x2 = x + y1 ; h2 = norm(x2)] (one fused
+        # pass) -> gate|up + GeGLU -> y2 = down_proj -> [x3 = x2 + y2 ; h1' = next layer's input norm / final norm].
+        # The residual adds live in the norm kernels: a GEMM epilogue doing fp32 read-modify-write of the residual
+        # stream is latency-bound (measured 14 % tensor-pipe on o_proj), a streaming add+norm pass is not.
+        h1, rstd1 = ops.rmsnorm_fwd(x, fp.w("model.layers.0.input_layernorm.weight"), self.eps, want_rstd=keep)
         for i in range(self.L):
             p = f"model.layers.{i}."
             rs = None if droppath_scales is None else droppath_scales[i]
-            h1, rstd1 = ops.rmsnorm_fwd(x, fp.w(p + "input_layernorm.weight"), self.eps, want_rstd=keep)
             qkv = ops.gemm_qkv_rope(h1, self._wqkv(i), pos, cos, sin, 2 * d)
             a, lse = ops.attn_fwd(qkv, mask, H, want_lse=keep, dropout_p=attn_dropout, seed=drop_seed + i)
+            y1 = ops.gemm(a, fp.wb(p + "self_attn.o_proj.weight"))
             lam1 = fp.w(p + "lambda_1") if self.layer_scale else None
-            x2 = ops.gemm_resid(a, fp.wb(p + "self_attn.o_proj.weight"), x, colscale=lam1, rowscale=rs)
-            h2, rstd2 = ops.rmsnorm_fwd(x2, fp.w(p + "post_attention_layernorm.weight"), self.eps, want_rstd=keep)
+            x2, h2, rstd2 = ops.add_rmsnorm_fwd(x, y1, fp.w(p + "post_attention_layernorm.weight"), self.eps,
+                                                colscale=lam1, rowscale=rs, want_rstd=keep)
             gu, act = ops.gemm_geglu(h2, self._wgu(i), want_gu=keep)
+            y2 = ops.gemm(act, fp.wb(p + "mlp.down_proj.weight"))
             lam2 = fp.w(p + "lambda_2") if self.layer_scale else None
-            x3 = ops.gemm_resid(act, fp.wb(p + "mlp.down_proj.weight"), x2, colscale=lam2, rowscale=rs)
+            next_w = fp.w(f"model.layers.{i + 1}.input_layernorm.weight") if i + 1 < self.L else fp.w("model.norm.weight")
+            x3, h_next, rstd_next = ops.add_rmsnorm_fwd(x2, y2, next_w, self.eps, colscale=lam2, rowscale=rs,
+                                                        want_rstd=keep)
             if keep:
                 stash["layers"].append(dict(x=x, rstd1=rstd1, h1=h1, qkv=qkv, a=a, lse=lse, x2=x2, rstd2=rstd2, h2=h2,
                                             gu=gu, act=act, x3=x3 if self.layer_scale else None, rs=rs))
-            x = x3
-        hf, rstdf = ops.rmsnorm_fwd(x, fp.w("model.norm.weight"), self.eps, want_rstd=keep)
+            x, h1, rstd1 = x3, h_next, rstd_next
+        hf, rstdf = h1, rstd1
         if keep:
             stash.update(x_final=x, rstdf=rstdf)
         return hf

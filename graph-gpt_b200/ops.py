@@ -253,6 +253,19 @@ def rmsnorm_fwd(x, w, eps, *, want_rstd=True):
     return y, rstd
 
 
+def add_rmsnorm_fwd(x_in, y, w, eps, *, colscale=None, rowscale=None, want_rstd=True, want_h=True):
+    """x_out = x_in + rowscale*colscale*y; h = rmsnorm(x_out; w) in bf16.  Returns (x_out, h, rstd)."""
+    _check(x_in, F32, "add_rmsnorm x_in", 2)
+    _check(y, BF16, "add_rmsnorm y", 2)
+    T, d = x_in.shape
+    x_out = torch.empty_like(x_in)
+    h = torch.empty((T, d), device=x_in.device, dtype=BF16) if want_h else None
+    rstd = torch.empty((T,), device=x_in.device, dtype=F32) if want_rstd else None
+    lib.ggpt_add_rmsnorm_fwd(x_in.data_ptr(), y.data_ptr(), y.stride(0), _ptr(colscale), _ptr(rowscale), w.data_ptr(),
+                             x_out.data_ptr(), _ptr(h), _ptr(rstd), T, d, float(eps), _stream())
+    return x_out, h, rstd
+
+
 def rmsnorm_bwd(dy, x, rstd, w, dresid, dw, *, want_bf16=True):
     """Returns (dx f32 [T,d], dx bf16 or None); accumulates into dw."""
     _check(dy, BF16, "rmsnorm_bwd dy", 2)

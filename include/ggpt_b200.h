@@ -136,6 +136,12 @@ int ggpt_embed_count(const long long* ids, void* cnt, long long ldc, long long T
 /* y = bf16(w * x * rsqrt(mean(x^2)+eps)), rstd[T] saved for backward (may be NULL).   ref: HF:59-64 */
 int ggpt_rmsnorm_fwd(const float* x, const float* w, void* y, long long ldy, float* rstd, long long T, int d, float eps,
                      void* stream);
+/* Fused residual add + RMSNorm: x_out = x_in + rowscale[t]*colscale[:]*y (y = bf16 output of o_proj / down_proj;
+ * colscale = LayerScale lambda, rowscale = DropPath scale, either may be NULL), h = bf16(w * x_out * rstd) (h may be
+ * NULL when only the sum is wanted), rstd[T] saved for backward (may be NULL).
+ * ref: HF:325,331 (residual adds; utils_graphgpt.py:153-166 for lambda / drop_path) followed by HF:59-64. */
+int ggpt_add_rmsnorm_fwd(const float* x_in, const void* y, long long ldy, const float* colscale, const float* rowscale,
+                         const float* w, float* x_out, void* h, float* rstd, long long T, int d, float eps, void* stream);
 /* dx_out = dresid (may be NULL) + dRMSNorm(dy); dx_bf16 (may be NULL) = bf16 copy; dw += sum_t dy * xhat. */
 int ggpt_rmsnorm_bwd(const void* dy, long long lddy, const float* x, const float* rstd, const float* w,
                      const float* dresid, float* dx_out, void* dx_bf16, float* dw, long long T, int d, void* stream);
