@@ -21,7 +21,7 @@
 
 namespace ggpt {
 
-constexpr int kBwdThreads = 192;
+constexpr int kBwdThreads = 320;   // TMA producer, MMA issuer, 8 softmax-gradient warps (two per TMEM lane quadrant)
 
 struct AttnBwdParams {
   int N, S, H;
@@ -52,8 +52,9 @@ struct BwdSmem {
   static constexpr int kStream = 32768;
   static constexpr int kP = kStream + 65536;
   static constexpr int kDS = kP + 32768;
-  static constexpr int kGather = kDS + 32768;     // 4 warps x 4 KB: coalesced RoPE-table gather (epilogue)
-  static constexpr int kBars = kGather + 16384;
+  static constexpr int kGather = kDS + 32768;     // 8 warps x 4 KB: coalesced RoPE-table gather (epilogue)
+  static constexpr int kEps = kGather + 32768;    // float [2 halves][128]: per-row eps partial sums (DQ)
+  static constexpr int kBars = kEps + 1024;
   static constexpr int kTotal = kBars + 256;
 };
 
@@ -118,7 +119,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     mbar_init(&str_empty[0], 1);
     mbar_init(&str_empty[1], 1);
     mbar_init(sdp_full, 1);
-    mbar_init(pds_full, 4);
+    mbar_init(pds_full, 8);
     mbar_init(pds_empty, 1);
     mbar_init(acc_full, 1);
     fence_mbar_init();
@@ -230,8 +231,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       }
     }
   } else {
-    // ===================== softmax-gradient warps: one query row per thread =====================
+    // ===================== softmax-gradient warps: two threads per query row (64 key columns each) =====================
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int r = quad * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
     float eps_run = 0.f;   // DQ: sum_k P (dP - D) of this thread's query row
@@ -256,12 +258,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         mw[0] = mw[1] = mw[2] = mw[3] = 0u;
       }
       const uint32_t rowkey = drop_rowkey(p.drop.seed_lo, p.drop.seed_hi, n, h, q_row);
+      const uint32_t rowkey2 = drop_rowkey2(rowkey);
       const int kbase = ts[kt];
       mbar_wait(sdp_full, it & 1);
       tc_fence_after();
       if (it > 0) mbar_wait(pds_empty, (it - 1) & 1);   // previous P / dS consumed by the tensor core
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = half * 2 + cc;
         uint32_t s[32], dp[32];
         tmem_ld32(tmem_S + lane_addr + c * 32, s);
         tmem_ld32(tmem_dP + lane_addr + c * 32, dp);
@@ -272,14 +276,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           float pv[8], dv[8];
+          uint32_t bits = 0u;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float e = exp2f(__uint_as_float(s[g * 8 + j]) * p.scale_log2 - lse2);
+            const float e = fast_exp2(fmaf(__uint_as_float(s[g * 8 + j]), p.scale_log2, -lse2));
             pv[j] = ((w >> (g * 8 + j)) & 1u) ? e : 0.f;
             float dpe = __uint_as_float(dp[g * 8 + j]);
             bool keep = true;
             if (p.drop.thresh != 0u) {
-              keep = drop_keep(rowkey, kbase + c * 32 + g * 8 + j, p.drop.thresh);
+              if ((j & 1) == 0) bits = drop_bits(rowkey, rowkey2, kbase + c * 32 + g * 8 + j);
+              keep = (j & 1) ? drop_keep_odd(bits, p.drop.thresh) : drop_keep_even(bits, p.drop.thresh);
               dpe = keep ? dpe * p.drop.inv_keep : 0.f;
             }
             const float t0 = pv[j] * (dpe - dsum);
@@ -318,13 +324,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const int pos = ok ? p.pos[grow] : 0;
     float cs[32], sn[32];
     {
-      uint8_t* gbuf = smem + L::kGather + quad * 4096;
+      uint8_t* gbuf = smem + L::kGather + (warp - 2) * 4096;
       warp_gather_rows32(p.cos_tab, pos, gbuf, lane, cs);
       warp_gather_rows32(p.sin_tab, pos, gbuf, lane, sn);
     }
-    constexpr int kNumAcc = DKV ? 2 : 1;
-#pragma unroll
-    for (int a = 0; a < kNumAcc; ++a) {
+    if (!DKV) {   // the two threads of a row exchange their eps partial sums
+      float* epsx = reinterpret_cast<float*>(smem + L::kEps);
+      epsx[half * 128 + r] = eps_run;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      eps_run = epsx[r] + epsx[128 + r];
+    }
+    // Work split between the two warps of a quadrant: DKV — warp half 0 stores dV, half 1 stores dK;
+    // DQ — each stores two of the four 8-column groups of both rotation halves.
+    {
+      const int a = DKV ? half : 0;
       // a == 0: dV (DKV, no rotation) or dQ (DQ, rotated);  a == 1: dK (rotated)
       const bool rot = DKV ? (a == 1) : true;
       const int col0 = (DKV ? (a == 0 ? p.v_col0 : p.k_col0) : p.q_col0) + h * 64;
@@ -360,6 +373,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         __nv_bfloat16* orow = p.dqkv + grow * p.ld + col0;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
+          if (!DKV && (g >> 1) != half) continue;
           float o1[8], o2[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {

@@ -164,6 +164,7 @@ attn_diag_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const DiagParams
       else if (it.cls == 2)
         diag_mask_words(p.mask_bits + (static_cast<size_t>(it.n) * p.S + it.r0 + r) * p.mask_words, it.r0, it.len, mw);
       const uint32_t rowkey = drop_rowkey(p.drop.seed_lo, p.drop.seed_hi, it.n, it.h, it.r0 + r);
+      const uint32_t rowkey2 = drop_rowkey2(rowkey);
       mbar_wait(&s_full[grp], ph);
       tc_fence_after();
       float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // independent chains: ILP instead of a 128-deep max
@@ -213,8 +214,11 @@ attn_diag_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const DiagParams
             }
             if (p.drop.thresh != 0u) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                if (!drop_keep(rowkey, it.r0 + c * 32 + g * 8 + j, p.drop.thresh)) pv[j] = 0.f;
+              for (int j = 0; j < 8; j += 2) {
+                const uint32_t bits = drop_bits(rowkey, rowkey2, it.r0 + c * 32 + g * 8 + j);
+                if (!drop_keep_even(bits, p.drop.thresh)) pv[j] = 0.f;
+                if (!drop_keep_odd(bits, p.drop.thresh)) pv[j + 1] = 0.f;
+              }
             }
             o.x = pack_bf16(pv[0], pv[1]); o.y = pack_bf16(pv[2], pv[3]);
             o.z = pack_bf16(pv[4], pv[5]); o.w = pack_bf16(pv[6], pv[7]);
@@ -491,6 +495,7 @@ attn_diag_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       }
       const int st = i & 1;
       const uint32_t rowkey = drop_rowkey(p.drop.seed_lo, p.drop.seed_hi, it.n, it.h, it.r0 + r);
+      const uint32_t rowkey2 = drop_rowkey2(rowkey);
       mbar_wait(&sdp_full[st], (i >> 1) & 1);
       tc_fence_after();
       if (i > 0) mbar_wait(pds_empty, (i - 1) & 1);
@@ -521,13 +526,15 @@ attn_diag_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
           uint4 o = make_uint4(0u, 0u, 0u, 0u), o2 = make_uint4(0u, 0u, 0u, 0u);
           if (__any_sync(0xffffffffu, ((w >> (g * 8)) & 0xffu) != 0u)) {
             float pv[8], dv[8];
+            uint32_t bits = 0u;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float e = fast_exp2(fmaf(__uint_as_float(s[g * 8 + j]), p.scale_log2, -lse2));
               pv[j] = ((w >> (g * 8 + j)) & 1u) ? e : 0.f;
               float dpe = __uint_as_float(dp[g * 8 + j]);
               if (p.drop.thresh != 0u) {
-                const bool keep = drop_keep(rowkey, it.r0 + c * 32 + g * 8 + j, p.drop.thresh);
+                if ((j & 1) == 0) bits = drop_bits(rowkey, rowkey2, it.r0 + c * 32 + g * 8 + j);
+                const bool keep = (j & 1) ? drop_keep_odd(bits, p.drop.thresh) : drop_keep_even(bits, p.drop.thresh);
                 dpe = keep ? dpe * p.drop.inv_keep : 0.f;
                 const float t0 = pv[j] * (dpe - dsum);
                 dv[j] = t0 * p.scale;

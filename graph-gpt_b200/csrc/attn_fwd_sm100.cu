@@ -62,6 +62,74 @@ __device__ __forceinline__ void load_mask_words(const uint32_t* __restrict__ mro
   }
 }
 
+// Online-softmax update of one thread's query row for one 128-key tile: reads the scores twice from TMEM (row max, then
+// probabilities), writes bf16 P into the swizzled K-major A-operand buffer, returns the rescale factor of the running
+// output.  MASKED = the tile pair is "mixed" (class 2) and every element consults its mask bit; full tiles (class 1) skip
+// all mask work.  DROP = attention dropout is on (one 32-bit draw per key pair, see common.cuh).
+template <bool MASKED, bool DROP>
+__device__ __forceinline__ float fwd_softmax_tile(uint32_t tS, uint8_t* prow, int r, const uint32_t (&mw)[4],
+                                                  float scale_log2, float& m_run, float& l_run, uint32_t rk1,
+                                                  uint32_t rk2, int k0, uint32_t thresh) {
+  float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // independent chains instead of a 128-deep max
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    uint32_t s[32];
+    tmem_ld32(tS + c * 32, s);
+    tmem_ld_wait();
+    const uint32_t w = (c == 0) ? mw[0] : (c == 1) ? mw[1] : (c == 2) ? mw[2] : mw[3];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float v = __uint_as_float(s[j]);
+      if (MASKED) v = ((w >> j) & 1u) ? v : -INFINITY;
+      m4[j & 3] = fmaxf(m4[j & 3], v);
+    }
+  }
+  const float m_tile = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * scale_log2;   // scale > 0 commutes with max
+  const float m_new = fmaxf(m_run, m_tile);
+  const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+  const float alpha = (m_run == -INFINITY) ? 0.f : fast_exp2(m_run - m_use);
+  float l4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    uint32_t s[32];
+    tmem_ld32(tS + c * 32, s);
+    tmem_ld_wait();
+    const uint32_t w = (c == 0) ? mw[0] : (c == 1) ? mw[1] : (c == 2) ? mw[2] : mw[3];
+    // columns c*32 .. c*32+31 of P: half = c/2 (64-col K block), 16-byte chunks (c&1)*4 .. +3
+    uint8_t* pbase = prow + (c >> 1) * 16384;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float pv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float e = fast_exp2(fmaf(__uint_as_float(s[g * 8 + j]), scale_log2, -m_use));
+        if (MASKED) e = ((w >> (g * 8 + j)) & 1u) ? e : 0.f;
+        pv[j] = e;
+        l4[j & 3] += e;
+      }
+      if (DROP) {
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          const uint32_t bits = drop_bits(rk1, rk2, k0 + c * 32 + g * 8 + j);
+          if (!drop_keep_even(bits, thresh)) pv[j] = 0.f;
+          if (!drop_keep_odd(bits, thresh)) pv[j + 1] = 0.f;
+        }
+      }
+      uint4 o;
+      o.x = pack_bf16(pv[0], pv[1]);
+      o.y = pack_bf16(pv[2], pv[3]);
+      o.z = pack_bf16(pv[4], pv[5]);
+      o.w = pack_bf16(pv[6], pv[7]);
+      const int chunk = ((c & 1) * 4 + g) ^ (r & 7);
+      *reinterpret_cast<uint4*>(pbase + chunk * 16) = o;
+    }
+  }
+  l_run = l_run * alpha + ((l4[0] + l4[1]) + (l4[2] + l4[3]));
+  m_run = m_new;
+  return alpha;
+}
+
+template <bool DROP>
 __global__ void __launch_bounds__(kAttThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -185,6 +253,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
 #pragma unroll
     for (int i = 0; i < 64; ++i) o_acc[i] = 0.f;
     const uint32_t rowkey = drop_rowkey(p.drop.seed_lo, p.drop.seed_hi, n, h, q_row);
+    const uint32_t rowkey2 = drop_rowkey2(rowkey);
     float m_run = -INFINITY;   // running max of scaled (log2-domain) scores
     float l_run = 0.f;
 
@@ -203,54 +272,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
       const int k0 = ts[kt];
       mbar_wait(s_full, it & 1);
       tc_fence_after();
-      // pass 1: row max
-      float m_tile = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t s[32];
-        tmem_ld32(tmem_S + lane_addr + c * 32, s);
-        tmem_ld_wait();
-        const uint32_t w = (c == 0) ? mw[0] : (c == 1) ? mw[1] : (c == 2) ? mw[2] : mw[3];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float v = __uint_as_float(s[j]) * p.scale_log2;
-          m_tile = fmaxf(m_tile, ((w >> j) & 1u) ? v : -INFINITY);
-        }
-      }
-      const float m_new = fmaxf(m_run, m_tile);
-      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run - m_use);
-      // pass 2: probabilities -> smem (bf16, swizzled K-major A operand), row sum
-      float l_tile = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t s[32];
-        tmem_ld32(tmem_S + lane_addr + c * 32, s);
-        tmem_ld_wait();
-        const uint32_t w = (c == 0) ? mw[0] : (c == 1) ? mw[1] : (c == 2) ? mw[2] : mw[3];
-        // columns c*32 .. c*32+31 of P: half = c/2 (64-col K block), 16-byte chunks (c&1)*4 .. +3
-        uint8_t* pbase = sP + (c >> 1) * 16384 + r * 128;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float pv[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float e = exp2f(__uint_as_float(s[g * 8 + j]) * p.scale_log2 - m_use);
-            pv[j] = ((w >> (g * 8 + j)) & 1u) ? e : 0.f;
-            l_tile += pv[j];
-            if (p.drop.thresh != 0u && !drop_keep(rowkey, k0 + c * 32 + g * 8 + j, p.drop.thresh)) pv[j] = 0.f;
-          }
-          uint4 o;
-          o.x = pack_bf16(pv[0], pv[1]);
-          o.y = pack_bf16(pv[2], pv[3]);
-          o.z = pack_bf16(pv[4], pv[5]);
-          o.w = pack_bf16(pv[6], pv[7]);
-          const int chunk = ((c & 1) * 4 + g) ^ (r & 7);
-          *reinterpret_cast<uint4*>(pbase + chunk * 16) = o;
-        }
-      }
-      l_run = l_run * alpha + l_tile;
-      m_run = m_new;
+      const float alpha = (cls == 2)
+          ? fwd_softmax_tile<true, DROP>(tmem_S + lane_addr, sP + r * 128, r, mw, p.scale_log2, m_run, l_run, rowkey, rowkey2,
+                                         k0, p.drop.thresh)
+          : fwd_softmax_tile<false, DROP>(tmem_S + lane_addr, sP + r * 128, r, mw, p.scale_log2, m_run, l_run, rowkey,
+                                          rowkey2, k0, p.drop.thresh);
       fence_proxy_async_smem();   // make P visible to the tensor-core (async) proxy
       tc_fence_before();
       __syncwarp();
@@ -479,7 +505,9 @@ int ggpt_attn_fwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int
   p.drop = make_drop_params(dropout_p, seed);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem);
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem);
     if (e != cudaSuccess) {
       set_error("attn_fwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return -2;
@@ -489,7 +517,8 @@ int ggpt_attn_fwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int
   GGPT_REQUIRE(run_general || iso_flags, "attn_fwd: run_general == 0 needs the isolated-tile work list");
   if (run_general) {
     dim3 grid(p.max_tiles, H, N);
-    attn_fwd_kernel<<<grid, kAttThreads, kAttSmem, static_cast<cudaStream_t>(stream)>>>(tm, p);
+    if (p.drop.thresh != 0u) attn_fwd_kernel<true><<<grid, kAttThreads, kAttSmem, static_cast<cudaStream_t>(stream)>>>(tm, p);
+    else attn_fwd_kernel<false><<<grid, kAttThreads, kAttSmem, static_cast<cudaStream_t>(stream)>>>(tm, p);
     if (int rc = check_launch("attn_fwd_kernel")) return rc;
   }
   if (iso_flags == nullptr) return 0;

@@ -322,8 +322,11 @@ __device__ __forceinline__ void warp_gather_rows32(const float* __restrict__ tab
   __syncwarp();
 }
 
-// Counter-based dropout mask for attention probabilities: keep(n,h,q,k) is a pure function of (seed, n, h, q, k), so the
-// forward and the backward kernels regenerate identical masks with no stored state (ref: HF:217 attention dropout).
+// Counter-based dropout mask for attention probabilities: keep(n,h,q,k) is a pure function of (seed, n, h, q, k) and of
+// the row-tile plan, so the forward and the backward kernels regenerate identical masks with no stored state
+// (ref: HF:217 attention dropout).  One 32-bit draw serves a PAIR of adjacent keys of a key tile (16 bits each:
+// the keep probability is quantised to 1/65536 and inv_keep is derived from the quantised value): two rounds of a
+// wide multiply (Philox-style hi ^ lo folding) keyed by a well-mixed per-row key — 5 integer instructions per pair.
 __device__ __forceinline__ uint32_t fmix32(uint32_t x) {
   x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
   return x;
@@ -333,26 +336,33 @@ __device__ __forceinline__ uint32_t drop_rowkey(uint32_t seed_lo, uint32_t seed_
   x = fmix32(x ^ seed_hi ^ (static_cast<uint32_t>(h) * 0x85EBCA77u));
   return fmix32(x ^ (static_cast<uint32_t>(q) * 0xC2B2AE3Du));
 }
-// drop probability = thresh / 2^32
-__device__ __forceinline__ bool drop_keep(uint32_t rowkey, int k, uint32_t thresh) {
-  return fmix32(rowkey + static_cast<uint32_t>(k) * 0x9E3779B1u) >= thresh;
+__device__ __forceinline__ uint32_t drop_rowkey2(uint32_t rowkey) { return fmix32(rowkey ^ 0x68BC21EBu); }
+// 32 random bits for the key pair whose first (even tile-local) key has absolute index k_even
+__device__ __forceinline__ uint32_t drop_bits(uint32_t rk1, uint32_t rk2, int k_even) {
+  const uint64_t m1 = static_cast<uint64_t>(static_cast<uint32_t>(k_even) ^ rk1) * 0xD2511F53ull;
+  const uint32_t y = static_cast<uint32_t>(m1 >> 32) ^ static_cast<uint32_t>(m1) ^ rk2;
+  const uint64_t m2 = static_cast<uint64_t>(y) * 0xCD9E8D57ull;
+  return static_cast<uint32_t>(m2 >> 32) ^ static_cast<uint32_t>(m2);
 }
+// thresh = (16-bit drop threshold) << 16;  even key of the pair uses the low half of the draw, odd key the high half
+__device__ __forceinline__ bool drop_keep_even(uint32_t bits, uint32_t thresh) { return (bits << 16) >= thresh; }
+__device__ __forceinline__ bool drop_keep_odd(uint32_t bits, uint32_t thresh) { return bits >= thresh; }
 #endif  // __CUDACC__
 
 struct DropParams {
-  uint32_t thresh;      // 0 = dropout off
+  uint32_t thresh;      // (round(p * 65536) << 16); 0 = dropout off
   uint32_t seed_lo, seed_hi;
-  float inv_keep;       // 1 / (1 - p)
+  float inv_keep;       // 1 / (1 - p_quantised)
 };
 
 inline DropParams make_drop_params(float p, unsigned long long seed) {
   DropParams d;
   d.thresh = 0; d.seed_lo = static_cast<uint32_t>(seed); d.seed_hi = static_cast<uint32_t>(seed >> 32); d.inv_keep = 1.0f;
   if (p > 0.f) {
-    double t = static_cast<double>(p) * 4294967296.0;
-    if (t > 4294967295.0) t = 4294967295.0;
-    d.thresh = static_cast<uint32_t>(t);
-    d.inv_keep = static_cast<float>(1.0 / (1.0 - static_cast<double>(d.thresh) / 4294967296.0));
+    long t = static_cast<long>(static_cast<double>(p) * 65536.0 + 0.5);
+    if (t > 65535) t = 65535;
+    d.thresh = static_cast<uint32_t>(t) << 16;
+    d.inv_keep = static_cast<float>(1.0 / (1.0 - static_cast<double>(t) / 65536.0));
   }
   return d;
 }

@@ -140,6 +140,31 @@ def test_rmsnorm_fwd_bwd(T, d):
     assert (dxb.float() - dx).abs().max().item() <= 5e-3 * dx.abs().max().item()
 
 
+@pytest.mark.parametrize("T,d,scaled", [(1000, 768, False), (300, 64, True), (129, 1024, True)])
+def test_add_rmsnorm_fwd(T, d, scaled):
+    """Fused residual add (+ LayerScale column scale, DropPath row scale) + RMSNorm: HF:325,331 then HF:59-64."""
+    from graphgpt_b200 import ops
+    g = torch.Generator().manual_seed(T + d)
+    x = torch.randn((T, d), generator=g).cuda() * 2
+    y = torch.randn((T, d), generator=g).to(torch.bfloat16).cuda()
+    w = (1 + 0.1 * torch.randn((d,), generator=g)).cuda()
+    cs = (0.5 + torch.rand((d,), generator=g)).cuda() if scaled else None
+    rs = (torch.rand((T,), generator=g) > 0.2).float().cuda() / 0.8 if scaled else None
+    x_out, h, rstd = ops.add_rmsnorm_fwd(x, y, w, 1e-6, colscale=cs, rowscale=rs)
+    yy = y.float()
+    if scaled:
+        yy = yy * cs[None, :] * rs[:, None]
+    ref_x = x + yy
+    ref_rstd = torch.rsqrt(ref_x.pow(2).mean(-1) + 1e-6)
+    ref_h = w * (ref_x * ref_rstd[:, None])
+    torch.cuda.synchronize()
+    assert (x_out - ref_x).abs().max().item() <= 1e-5 * ref_x.abs().max().item()
+    assert (rstd - ref_rstd).abs().max().item() <= 1e-5 * ref_rstd.abs().max().item()
+    assert (h.float() - ref_h).abs().max().item() <= 5e-3 * ref_h.abs().max().item()        # one bf16 rounding
+    x2, h2, r2 = ops.add_rmsnorm_fwd(x, y, w, 1e-6, colscale=cs, rowscale=rs, want_rstd=False, want_h=False)
+    assert h2 is None and r2 is None and torch.equal(x2, x_out)
+
+
 def test_geglu_bwd():
     from graphgpt_b200 import ops
     g = torch.Generator().manual_seed(5)
