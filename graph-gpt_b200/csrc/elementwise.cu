@@ -472,12 +472,14 @@ __global__ void scatter_rows_kernel(const __nv_bfloat16* __restrict__ src, long 
 // =============================================================================================
 // Cross-entropy over fp32 logits [L, ldl] (first V columns valid).  One warp per row.
 //   row_lse[e] = logsumexp(logits[e,:V]);  loss_sum += wgt[e] * (row_lse[e] - logits[e, label[e]])
+// focal_gamma > 0 (FocalLoss, utils_graphgpt.py:340-377): every entry is additionally weighted by (1 - p_t)^gamma with
+// p_t = softmax(logits[e])[label[e]] treated as a constant (the reference detaches it: Variable(logpt.data.exp())).
 // ref: modeling_helpers.py:145-198 (_get_ce_loss / _get_dlm_ce_loss on logits.float())
 // =============================================================================================
 __global__ void ce_fwd_kernel(const float* __restrict__ logits, long long ldl, const int* __restrict__ labels,
                               const float* __restrict__ wgt, float* __restrict__ row_lse, float* __restrict__ row_loss,
                               double* __restrict__ loss_sum, double* __restrict__ wgt_sum, int L, int V,
-                              int* __restrict__ err) {
+                              float focal_gamma, int* __restrict__ err) {
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   double local = 0.0, local_w = 0.0;
@@ -497,7 +499,8 @@ __global__ void ce_fwd_kernel(const float* __restrict__ logits, long long ldl, c
         lab = 0;
       }
       const float w = wgt ? wgt[e] : 1.0f;
-      const float l = lse - row[lab];
+      float l = lse - row[lab];
+      if (focal_gamma > 0.f) l *= powf(fmaxf(1.0f - __expf(-l), 0.f), focal_gamma);
       row_lse[e] = lse;
       if (row_loss) row_loss[e] = l;
       local += static_cast<double>(l) * w;
@@ -526,7 +529,8 @@ __global__ void ce_fwd_kernel(const float* __restrict__ logits, long long ldl, c
 __global__ void ce_bwd_kernel(const float* __restrict__ logits, long long ldl, const int* __restrict__ labels,
                               const float* __restrict__ wgt, const float* __restrict__ row_lse,
                               const float* __restrict__ scale, const float* __restrict__ gout,
-                              __nv_bfloat16* __restrict__ dlogits, long long ldd, int L, int V, int Vpad) {
+                              __nv_bfloat16* __restrict__ dlogits, long long ldd, int L, int V, int Vpad,
+                              float focal_gamma) {
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const float g = scale[0] * (gout ? gout[0] : 1.0f);
@@ -535,7 +539,8 @@ __global__ void ce_bwd_kernel(const float* __restrict__ logits, long long ldl, c
     __nv_bfloat16* drow = dlogits + static_cast<long long>(e) * ldd;
     const float lse = row_lse[e];
     const int lab = labels[e];
-    const float w = (wgt ? wgt[e] : 1.0f) * g;
+    float w = (wgt ? wgt[e] : 1.0f) * g;
+    if (focal_gamma > 0.f) w *= powf(fmaxf(1.0f - __expf(row[lab] - lse), 0.f), focal_gamma);   // detached (1 - p_t)^gamma
     for (int c = lane * 2; c < Vpad; c += 64) {
       float v0 = 0.f, v1 = 0.f;
       if (c < V) v0 = (__expf(row[c] - lse) - (c == lab ? 1.f : 0.f)) * w;
@@ -750,12 +755,12 @@ int ggpt_scatter_rows(const void* src, long long lds, const int* idx, void* out,
 }
 
 int ggpt_ce_fwd(const float* logits, long long ldl, const int* labels, const float* wgt, float* row_lse, float* row_loss,
-                double* loss_sum, double* wgt_sum, int L, int V, int* err_flag, void* stream) {
+                double* loss_sum, double* wgt_sum, int L, int V, float focal_gamma, int* err_flag, void* stream) {
   GGPT_REQUIRE(logits && labels && row_lse && loss_sum, "ce_fwd: null pointer");
   if (L <= 0) return 0;
   ce_fwd_kernel<<<grid_for_rows(L, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, ldl, labels, wgt, row_lse,
                                                                                     row_loss, loss_sum, wgt_sum, L, V,
-                                                                                    err_flag);
+                                                                                    focal_gamma, err_flag);
   return check_launch("ce_fwd_kernel");
 }
 
@@ -769,12 +774,14 @@ int ggpt_ce_finalize(const double* loss_sum, const double* wgt_sum, const int* c
 }
 
 int ggpt_ce_bwd(const float* logits, long long ldl, const int* labels, const float* wgt, const float* row_lse,
-                const float* scale, const float* gout, void* dlogits, long long ldd, int L, int V, void* stream) {
+                const float* scale, const float* gout, void* dlogits, long long ldd, int L, int V, float focal_gamma,
+                void* stream) {
   GGPT_REQUIRE(logits && labels && row_lse && scale && dlogits, "ce_bwd: null pointer");
   GGPT_REQUIRE(ldd % 8 == 0 && ldd >= ((V + 7) / 8) * 8, "ce_bwd: ldd must be a multiple of 8 covering V");
   if (L <= 0) return 0;
   ce_bwd_kernel<<<grid_for_rows(L, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      logits, ldl, labels, wgt, row_lse, scale, gout, static_cast<__nv_bfloat16*>(dlogits), ldd, L, V, ((V + 7) / 8) * 8);
+      logits, ldl, labels, wgt, row_lse, scale, gout, static_cast<__nv_bfloat16*>(dlogits), ldd, L, V, ((V + 7) / 8) * 8,
+      focal_gamma);
   return check_launch("ce_bwd_kernel");
 }
 

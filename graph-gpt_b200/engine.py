@@ -393,14 +393,16 @@ class PretrainHeadFn(torch.autograd.Function):
             hl = hsel                                                               # F == 1: entries == rows
         logits = ops.gemm(hl, fp.wb("lm_head.weight"), out_dtype=F32)              # [L, V] (ld padded to 8)
         wgt = ent_wgt_fn(hi, L) if ent_wgt_fn is not None else None
-        row_lse, _, sums = ops.ce_fwd(logits, hi.ent_label, V, wgt, err_flag=None)
+        # FocalLoss only on the unweighted branch (modeling_pretrain.py:221-236: the dLM loss ignores focal_gamma)
+        focal = float(getattr(hot.cfg, "focal_gamma", 0.0) or 0.0) if wgt is None else 0.0
+        row_lse, _, sums = ops.ce_fwd(logits, hi.ent_label, V, wgt, err_flag=None, focal_gamma=focal)
         if loss_mode == "mean":
             ls = ops.ce_finalize(sums, hi.counts.data_ptr() + 4, 0)
         else:                                                                       # dLM: sum / (N*S*F)
             ls = ops.ce_finalize(sums, 0, 2, float(N * S * hot.cfg.next_n_token))
         ctx.hot, ctx.hi, ctx.M, ctx.L, ctx.T = hot, hi, M, L, hf.shape[0]
         ctx.saved = (hsel, hl, logits, row_lse, wgt, ls)
-        ctx.has_proj, ctx.empty = has_proj, False
+        ctx.has_proj, ctx.empty, ctx.focal = has_proj, False, focal
         ctx.mark_non_differentiable(logits)
         return ls[0], logits
 
@@ -417,7 +419,7 @@ class PretrainHeadFn(torch.autograd.Function):
         fp.prepare_grads()
         wgrad = dict(a_mn_major=True, b_mn_major=True, out_dtype=F32, accumulate=True)
         gout = gloss.reshape(1).to(F32).contiguous()
-        dlog = ops.ce_bwd(logits, hi.ent_label, V, row_lse, ls.data_ptr() + 4, gout, wgt)   # bf16 [L, ld]
+        dlog = ops.ce_bwd(logits, hi.ent_label, V, row_lse, ls.data_ptr() + 4, gout, wgt, focal_gamma=ctx.focal)  # bf16 [L, ld]
         dlv = dlog[:, :V]
         ops.gemm(dlv, hl, out=fp.g("lm_head.weight"), **wgrad)
         dhl = ops.gemm(dlv, fp.wb("lm_head.weight"), b_mn_major=True)                        # [L, d]

@@ -332,8 +332,6 @@ class GraphGPTPretrainBase(_GraphGPTBase):
             raise NotImplementedError("use_generative=False (contrastive-only pre-training) is out of scope")
         if config.smtp_inside:
             raise NotImplementedError("smtp_inside (in-model SMTP masking, modeling_helpers.py:399-468) is SURVEY §8f N1")
-        if getattr(config, "focal_gamma", 0) > 0:
-            raise NotImplementedError("focal loss (focal_gamma > 0) is not built")
         self.stacked_feat_agg = _StackedFeatAgg(config)
         d = config.hidden_size
         if config.next_n_token > 1:

@@ -332,7 +332,7 @@ def scatter_rows(src, idx, out, n, *, n_ptr=None):
     return out
 
 
-def ce_fwd(logits, labels, V, wgt=None, *, want_row_loss=False, err_flag=None):
+def ce_fwd(logits, labels, V, wgt=None, *, want_row_loss=False, err_flag=None, focal_gamma=0.0):
     """logits f32 [L, ld>=V]; labels int32 [>=L].  Returns (row_lse, row_loss|None, loss_sum f64[1], wgt_sum f64[1])."""
     _check(logits, F32, "ce logits", 2)
     L = logits.shape[0]
@@ -341,7 +341,7 @@ def ce_fwd(logits, labels, V, wgt=None, *, want_row_loss=False, err_flag=None):
     row_loss = torch.empty((L,), device=dev, dtype=F32) if want_row_loss else None
     sums = torch.zeros((2,), device=dev, dtype=torch.float64)
     lib.ggpt_ce_fwd(logits.data_ptr(), logits.stride(0), labels.data_ptr(), _ptr(wgt), row_lse.data_ptr(), _ptr(row_loss),
-                    sums.data_ptr(), sums.data_ptr() + 8, L, V, _ptr(err_flag), _stream())
+                    sums.data_ptr(), sums.data_ptr() + 8, L, V, float(focal_gamma), _ptr(err_flag), _stream())
     return row_lse, row_loss, sums
 
 
@@ -352,12 +352,12 @@ def ce_finalize(sums, count_ptr, mode, fixed_denom=1.0):
     return out
 
 
-def ce_bwd(logits, labels, V, row_lse, scale_ptr, gout, wgt=None):
+def ce_bwd(logits, labels, V, row_lse, scale_ptr, gout, wgt=None, focal_gamma=0.0):
     L = logits.shape[0]
     ldd = (V + 7) // 8 * 8
     dlogits = torch.empty((L, ldd), device=logits.device, dtype=BF16)
     lib.ggpt_ce_bwd(logits.data_ptr(), logits.stride(0), labels.data_ptr(), _ptr(wgt), row_lse.data_ptr(), scale_ptr,
-                    _ptr(gout), dlogits.data_ptr(), ldd, L, V, _stream())
+                    _ptr(gout), dlogits.data_ptr(), ldd, L, V, float(focal_gamma), _stream())
     return dlogits
 
 

@@ -165,15 +165,18 @@ int ggpt_scatter_rows(const void* src, long long lds, const int* idx, void* out,
 
 /* fp32 cross-entropy over logits [L, ldl] (V valid columns): row_lse, optional row_loss, and
  * loss_sum += wgt[e]*(lse - logit[label]) (wgt NULL -> 1), wgt_sum += wgt[e] (may be NULL).
- * ref: modeling_helpers.py:145-198 (CrossEntropyLoss on logits.float()). */
+ * focal_gamma > 0: each entry's loss is additionally scaled by the detached (1 - p_t)^gamma of FocalLoss.
+ * ref: modeling_helpers.py:145-198 (CrossEntropyLoss on logits.float()); utils_graphgpt.py:340-377 (FocalLoss). */
 int ggpt_ce_fwd(const float* logits, long long ldl, const int* labels, const float* wgt, float* row_lse, float* row_loss,
-                double* loss_sum, double* wgt_sum, int L, int V, int* err_flag, void* stream);
+                double* loss_sum, double* wgt_sum, int L, int V, float focal_gamma, int* err_flag, void* stream);
 /* loss = loss_sum / denom, scale = 1/denom; mode 0: denom = *count (mean), 1: *wgt_sum + 1e-7, 2: fixed_denom. */
 int ggpt_ce_finalize(const double* loss_sum, const double* wgt_sum, const int* count, int mode, float fixed_denom,
                      float* loss, float* scale, void* stream);
-/* dlogits (bf16 [L, ldd], pad columns zeroed) = (softmax - onehot) * wgt[e] * scale[0] * gout[0] (gout NULL -> 1). */
+/* dlogits (bf16 [L, ldd], pad columns zeroed) = (softmax - onehot) * wgt[e] * scale[0] * gout[0] (gout NULL -> 1),
+ * times (1 - p_t)^focal_gamma when focal_gamma > 0 (p_t is a constant in the reference's FocalLoss). */
 int ggpt_ce_bwd(const float* logits, long long ldl, const int* labels, const float* wgt, const float* row_lse,
-                const float* scale, const float* gout, void* dlogits, long long ldd, int L, int V, void* stream);
+                const float* scale, const float* gout, void* dlogits, long long ldd, int L, int V, float focal_gamma,
+                void* stream);
 
 /* out += sum(g^2) (double accumulator, pre-zeroed by the caller). */
 int ggpt_sumsq(const float* g, long long n, double* out, void* stream);

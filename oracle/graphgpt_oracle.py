@@ -57,6 +57,7 @@ class OracleConfig:
         self.num_labels = kw.get("num_labels", 2)
         self.problem_type = kw.get("problem_type", None)
         self.loss_type = kw.get("loss_type", None)
+        self.focal_gamma = kw.get("focal_gamma", 0.0)
 
     @classmethod
     def from_any(cls, cfg):
@@ -65,7 +66,7 @@ class OracleConfig:
         keys = ["vocab_size", "hidden_size", "intermediate_size", "num_hidden_layers", "head_dim",
                 "num_attention_heads", "rms_norm_eps", "rope_theta", "causal_attention", "stacked_feat",
                 "next_n_token", "stack_method", "stacked_feat_agg_method", "layer_scale_init_value", "rope_range",
-                "pad_token_id", "num_labels", "problem_type", "loss_type"]
+                "pad_token_id", "num_labels", "problem_type", "loss_type", "focal_gamma"]
         get = (lambda k: cfg.get(k)) if isinstance(cfg, dict) else (lambda k: getattr(cfg, k, None))
         kw = {k: get(k) for k in keys if get(k) is not None}
         if "rope_theta" not in kw:
@@ -237,9 +238,18 @@ def head_select(hidden, labels, sd, cfg, sample_wgt=None):
     return h, lab, wgt
 
 
-def ce_loss(logits, labels, wgt=None, dlm=False):
+def focal_loss(logits, labels, gamma):
+    """FocalLoss (utils_graphgpt.py:340-377), reduction "mean": -(1 - p_t)^gamma log p_t with p_t detached."""
+    logpt = F.log_softmax(logits.float(), dim=-1).gather(1, labels.view(-1, 1)).view(-1)
+    pt = logpt.detach().exp()
+    return (-1 * (1 - pt) ** gamma * logpt).mean()
+
+
+def ce_loss(logits, labels, wgt=None, dlm=False, focal_gamma=0.0):
     """_get_ce_loss (modeling_helpers.py:145-177) / _get_dlm_ce_loss (:180-198): CE on logits.float()."""
     if wgt is None:
+        if focal_gamma > 0:
+            return focal_loss(logits, labels, focal_gamma)
         return F.cross_entropy(logits.float(), labels)
     loss = F.cross_entropy(logits.float(), labels, reduction="none")
     w = wgt.view(-1).float()
@@ -262,7 +272,7 @@ def pretrain_forward(sd, cfg, input_ids, attention_mask=None, labels=None, sampl
     loss = None
     if lab is not None:
         if wgt is None:
-            loss = ce_loss(logits, lab)
+            loss = ce_loss(logits, lab, focal_gamma=getattr(cfg, "focal_gamma", 0.0) or 0.0)   # :221-228
         else:
             N, S, _ = hidden.shape
             # wgt is not None for stack_method "long" (normalised weights) and for "short" + sample_wgt:

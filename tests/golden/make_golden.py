@@ -107,6 +107,14 @@ def _gated():
     return "pretrain", cfg, dict(input_ids=t(b["input_ids"]), attention_mask=t(b["attention_mask"]), labels=t(b["labels"]))
 
 
+@case("c2_focal_loss")
+def _focal():
+    """FocalLoss head (config.focal_gamma > 0, utils_graphgpt.py:340-377; unweighted branch modeling_pretrain.py:221-228)."""
+    cfg = base_cfg(vocab_size=756, hidden_size=64, intermediate_size=256, stacked_feat=13, next_n_token=13, focal_gamma=2.0)
+    b = synth.make_batch(2, 48, layout="unpacked", seed=18)
+    return "pretrain", cfg, dict(input_ids=t(b["input_ids"]), attention_mask=t(b["attention_mask"]), labels=t(b["labels"]))
+
+
 @case("c2_infer_all_entries")
 def _infer():
     """labels=None: the head runs on every (n,s,f) entry (generation path, modeling_helpers.py:284-292)."""
