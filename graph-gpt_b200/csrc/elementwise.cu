@@ -119,6 +119,40 @@ __global__ void embed_count_kernel(const long long* __restrict__ ids, __nv_bfloa
 }
 
 // =============================================================================================
+// In-model SMTP masking (config.smtp_inside): the collator ships raw ids [N, S, Ftot] whose column F+2 holds each
+// row's node index; one uniform draw per (sample, node, feature) decides whether that feature of that NODE is masked,
+// and every row of the Eulerian path that revisits the node looks the decision up — all rows of a node are masked
+// together.  keep-rate threshold = mr[n]^power with mr ~ U(0,1) per sample.
+//   out_ids[n,s,f] = masked ? mask_token : ids[n,s,f];   labels[n,s,f] = masked ? ids[n,s,f] : label_pad
+//   masked = (u_node[n, node_idx[n,s], f] > mr[n]^power) && ids[n,s,f] > 0
+// ref: modeling_helpers.py:399-452 (prepare_for_2d_smtp_inputs_labels with smtp_2d_rate = 1, replace_rate = 0,
+// global_2d_mask = False, as called from modeling_pretrain.py:175-189).  One thread per (n, s, f) entry.
+// =============================================================================================
+__global__ void smtp_mask_2d_kernel(const long long* __restrict__ ids, int Ftot, int node_col,
+                                    const float* __restrict__ mr, const float* __restrict__ u_node, float power,
+                                    long long* __restrict__ out_ids, long long* __restrict__ labels, int N, int S, int F,
+                                    long long mask_token, long long label_pad, int* __restrict__ err) {
+  const long long total = static_cast<long long>(N) * S * F;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int f = static_cast<int>(i % F);
+    const long long ns = i / F;
+    const int n = static_cast<int>(ns / S);
+    const long long v = ids[ns * Ftot + f];
+    long long node = ids[ns * Ftot + node_col];
+    if (node < 0) node += S;                       // torch advanced indexing wraps negative indices
+    if (node < 0 || node >= S) {
+      if (err) atomicExch(err, 3);
+      node = 0;
+    }
+    const float thr = powf(mr[n], power);
+    const bool masked = (u_node[(static_cast<long long>(n) * S + node) * F + f] > thr) && (v > 0);
+    out_ids[i] = masked ? mask_token : v;
+    labels[i] = masked ? v : label_pad;
+  }
+}
+
+// =============================================================================================
 // RMSNorm  y = bf16( w * x * rsqrt(mean(x^2) + eps) ), fp32 statistics.   ref: HF:59-64
 // =============================================================================================
 __global__ void rmsnorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
@@ -663,6 +697,18 @@ int ggpt_embed_count(const long long* ids, void* cnt, long long ldc, long long T
   embed_count_kernel<<<grid_for_rows(T, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       ids, static_cast<__nv_bfloat16*>(cnt), ldc, T, F, V, padding_idx);
   return check_launch("embed_count_kernel");
+}
+
+int ggpt_smtp_mask_2d(const long long* ids, int Ftot, int node_col, const float* mr, const float* u_node, float power,
+                      long long* out_ids, long long* labels, int N, int S, int F, long long mask_token,
+                      long long label_pad, int* err_flag, void* stream) {
+  GGPT_REQUIRE(ids && mr && u_node && out_ids && labels, "smtp_mask_2d: null pointer");
+  GGPT_REQUIRE(N > 0 && S > 0 && F > 0 && Ftot >= F && node_col >= 0 && node_col < Ftot,
+               "smtp_mask_2d: bad sizes N=%d S=%d F=%d Ftot=%d node_col=%d", N, S, F, Ftot, node_col);
+  const long long total = static_cast<long long>(N) * S * F;
+  smtp_mask_2d_kernel<<<grid_for_rows(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      ids, Ftot, node_col, mr, u_node, power, out_ids, labels, N, S, F, mask_token, label_pad, err_flag);
+  return check_launch("smtp_mask_2d_kernel");
 }
 
 int ggpt_rmsnorm_fwd(const float* x, const float* w, void* y, long long ldy, float* rstd, long long T, int d, float eps,

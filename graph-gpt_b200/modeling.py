@@ -330,8 +330,8 @@ class GraphGPTPretrainBase(_GraphGPTBase):
         super().__init__(config)
         if not config.use_generative:
             raise NotImplementedError("use_generative=False (contrastive-only pre-training) is out of scope")
-        if config.smtp_inside:
-            raise NotImplementedError("smtp_inside (in-model SMTP masking, modeling_helpers.py:399-468) is SURVEY §8f N1")
+        self.smtp_inside = bool(config.smtp_inside)     # modeling_pretrain.py:62-63
+        self.smtp_power = float(config.smtp_power)
         self.stacked_feat_agg = _StackedFeatAgg(config)
         d = config.hidden_size
         if config.next_n_token > 1:
@@ -347,6 +347,8 @@ class GraphGPTPretrainBase(_GraphGPTBase):
         if inputs_embeds is not None:
             raise AssertionError("inputs_embeds must be None (modeling_helpers.py:95)")
         cfg = self.config
+        if self.smtp_inside:
+            input_ids, labels = self._smtp_inside_inputs(input_ids)
         hf, in_, N, S = self._run_backbone(input_ids, attention_mask, position_ids)
         hot = self._hot
         dev = hf.device
@@ -379,6 +381,24 @@ class GraphGPTPretrainBase(_GraphGPTBase):
             loss, logits = PretrainHeadFn.apply(hot, hf, lab2d, N, S, wgt_fn, mode, *params)
         return DoubleHeadsModelOutput(head1_loss=loss, head1_logits=logits, head2_loss=None, head2_logits=None,
                                       past_key_values=None, hidden_states=None, attentions=None)
+
+
+    def _smtp_inside_inputs(self, input_ids):
+        """modeling_pretrain.py:175-189 -> prepare_for_2d_smtp_inputs_labels (modeling_helpers.py:399-452) with
+        smtp_2d_rate=1, replace_rate=0, global_2d_mask=False.  The uniform draws come from torch's generator in the
+        reference's order and shapes (so a seeded run consumes the same random stream); the node-level look-up, the
+        masking and the label construction run in one kernel (ggpt_smtp_mask_2d)."""
+        from . import ops
+        F_ = self.config.stacked_feat
+        dev = self.device
+        ids = input_ids.to(dev).contiguous()
+        N, S, _ = ids.shape
+        torch.rand((N, 1, 1), dtype=torch.float32, device=dev)            # sample_mask draw: `< smtp_2d_rate` = always true
+        mr = torch.rand((N, 1, 1), dtype=torch.float32, device=dev)       # mr_per_sample
+        u_node = torch.rand((N, S, F_), dtype=torch.float32, device=dev)  # mask_per_node draw
+        torch.randn((N, S, F_), dtype=torch.float32, device=dev)          # _get_gaussian_rnd_tokens (unused: replace_rate = 0)
+        torch.rand((N, S, F_), dtype=torch.float32, device=dev)           # replace_mask draw (unused: replace_rate = 0)
+        return ops.smtp_mask_2d(ids, F_, mr.view(-1), u_node, self.smtp_power)
 
 
 # The task description's names for the two pre-training modes; both are the same class (SURVEY §0 fact 1).

@@ -243,6 +243,25 @@ def embed_count(ids, V, padding_idx):
     return cnt[:, :V]
 
 
+def smtp_mask_2d(ids, F, mr, u_node, power, *, mask_token=1, label_pad=-100, err_flag=None):
+    """In-model SMTP masking.  ids int64 [N,S,Ftot] (column F+2 = node index), mr f32 [N], u_node f32 [N,S,F].
+    Returns (input_ids int64 [N,S,F], labels int64 [N,S,F])."""
+    if ids.dtype != torch.int64 or ids.dim() != 3 or not ids.is_cuda or not ids.is_contiguous():
+        raise RuntimeError("smtp_mask_2d: ids must be a contiguous CUDA int64 [N,S,Ftot] tensor")
+    N, S, Ftot = ids.shape
+    if Ftot < F + 3:
+        raise RuntimeError(f"smtp_mask_2d: ids has {Ftot} columns, expected stacked_feat + 4 = {F + 4} (node index at {F + 2})")
+    _check(mr, F32, "smtp_mask_2d mr")
+    _check(u_node, F32, "smtp_mask_2d u_node")
+    if mr.numel() != N or u_node.numel() != N * S * F:
+        raise RuntimeError("smtp_mask_2d: mr / u_node sizes do not match ids")
+    out = torch.empty((N, S, F), device=ids.device, dtype=torch.int64)
+    labels = torch.empty((N, S, F), device=ids.device, dtype=torch.int64)
+    lib.ggpt_smtp_mask_2d(ids.data_ptr(), Ftot, F + 2, mr.data_ptr(), u_node.data_ptr(), float(power), out.data_ptr(),
+                          labels.data_ptr(), N, S, F, int(mask_token), int(label_pad), _ptr(err_flag), _stream())
+    return out, labels
+
+
 def rmsnorm_fwd(x, w, eps, *, want_rstd=True):
     _check(x, F32, "rmsnorm x", 2)
     _check(w, F32, "rmsnorm w", 1)

@@ -133,6 +133,16 @@ int ggpt_embed_bwd(const long long* ids, const float* dx, const float* table, co
 int ggpt_embed_count(const long long* ids, void* cnt, long long ldc, long long T, int F, int V, int padding_idx,
                      void* stream);
 
+/* In-model SMTP masking (config.smtp_inside).  ids int64 [N,S,Ftot]: columns [0,F) are the stacked token ids, column
+ * node_col (= F+2 in the reference's layout) is the row's node index.  mr f32 [N] and u_node f32 [N,S,F] are uniform
+ * draws supplied by the caller (torch's generator, so the stream of random numbers stays the reference's).
+ * masked = u_node[n, node_idx[n,s], f] > mr[n]^power && ids[n,s,f] > 0;  out_ids = masked ? mask_token : id;
+ * labels = masked ? id : label_pad.  A node index outside [-S, S) sets *err_flag = 3 (may be NULL).
+ * ref: modeling_helpers.py:399-452 (prepare_for_2d_smtp_inputs_labels), modeling_pretrain.py:175-189. */
+int ggpt_smtp_mask_2d(const long long* ids, int Ftot, int node_col, const float* mr, const float* u_node, float power,
+                      long long* out_ids, long long* labels, int N, int S, int F, long long mask_token,
+                      long long label_pad, int* err_flag, void* stream);
+
 /* y = bf16(w * x * rsqrt(mean(x^2)+eps)), rstd[T] saved for backward (may be NULL).   ref: HF:59-64 */
 int ggpt_rmsnorm_fwd(const float* x, const float* w, void* y, long long ldy, float* rstd, long long T, int d, float eps,
                      void* stream);

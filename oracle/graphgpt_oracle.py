@@ -238,6 +238,19 @@ def head_select(hidden, labels, sd, cfg, sample_wgt=None):
     return h, lab, wgt
 
 
+def smtp_mask_2d(input_ids, node_idx, mr, u_node, power, mask_token_id=1, label_pad_token_id=-100):
+    """prepare_for_2d_smtp_inputs_labels (modeling_helpers.py:399-452) for smtp_2d_rate=1, replace_rate=0,
+    global_2d_mask=False (the arguments of modeling_pretrain.py:175-189), with the uniform draws passed in:
+    mr [N] = mr_per_sample, u_node [N,S,F] = the mask_per_node draw.  Returns (input_ids, labels)."""
+    N = input_ids.shape[0]
+    mask_per_node = u_node > (mr.view(N, 1, 1) ** power)                      # :430-433 (sample_mask is all-true)
+    bz_idx = torch.arange(N).view(-1, 1)
+    mask_per_token = mask_per_node[bz_idx, node_idx] & (input_ids > 0)         # :437-438
+    labels = input_ids.clone().masked_fill_(~mask_per_token, label_pad_token_id)
+    out = input_ids.clone().masked_fill_(mask_per_token, mask_token_id)
+    return out, labels
+
+
 def focal_loss(logits, labels, gamma):
     """FocalLoss (utils_graphgpt.py:340-377), reduction "mean": -(1 - p_t)^gamma log p_t with p_t detached."""
     logpt = F.log_softmax(logits.float(), dim=-1).gather(1, labels.view(-1, 1)).view(-1)

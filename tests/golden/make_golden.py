@@ -166,10 +166,42 @@ def _patch_dropout_backbone():
     utils_graphgpt.LlamaDecoderLayer._ggpt_patched = True
 
 
+def make_smtp_inside():
+    """tests/golden/aux/smtp_inside.pt: the reference's prepare_for_2d_smtp_inputs_labels (modeling_helpers.py:399-452)
+    run on CPU with a seeded generator; the uniform draws it consumes are re-created with the same seed / order /
+    shapes and stored next to its outputs, so the oracle and the kernel can be fed identical randomness."""
+    from src.models.graphgpt import modeling_helpers as mh
+    recs = []
+    for seed, (N, S, F_, power) in enumerate([(3, 40, 13, 1.0), (2, 64, 4, 0.5), (4, 24, 1, 2.0)]):
+        g = np.random.default_rng(100 + seed)
+        ids = g.integers(1, 700, size=(N, S, F_ + 4)).astype(np.int64)
+        n_nodes = g.integers(3, S // 2, size=N)
+        for n in range(N):
+            ln = int(g.integers(S // 2, S + 1))
+            ids[n, :ln, F_ + 2] = g.integers(0, n_nodes[n], size=ln)
+            ids[n, ln:, :] = 0                                         # pad rows: ids 0, node index 0
+            ids[n, :ln, :F_][g.random((ln, F_)) < 0.1] = 0             # some pad entries inside valid rows
+        ids = torch.from_numpy(ids)
+        torch.manual_seed(4242 + seed)
+        torch.rand((N, 1, 1))
+        mr = torch.rand((N, 1, 1))
+        u = torch.rand((N, S, F_))
+        torch.manual_seed(4242 + seed)
+        out_ids, labels = mh.prepare_for_2d_smtp_inputs_labels(ids[:, :, :F_], ids[:, :, F_ + 2], smtp_2d_rate=1, power=power,
+                                                               replace_rate=0, vocab=756, global_2d_mask=False)
+        recs.append(dict(ids=ids, F=F_, power=power, mr=mr.view(-1).clone(), u_node=u.clone(), seed=4242 + seed,
+                         out_ids=out_ids.clone(), labels=labels.clone()))
+        print(f"smtp_inside case {seed}: masked {(labels != -100).float().mean():.3f} of entries")
+    os.makedirs(os.path.join(HERE, "aux"), exist_ok=True)
+    torch.save(recs, os.path.join(HERE, "aux", "smtp_inside.pt"))
+
+
 def main():
     mp, mf, GraphGPTConfig = load_reference()
     _patch_dropout_backbone()
     only = set(sys.argv[1:])
+    if not only or "smtp_inside" in only:
+        make_smtp_inside()
     for name, fn in CASES.items():
         if only and name not in only:
             continue

@@ -3,6 +3,8 @@ the same op (the oracle's formulas).  Tolerances are stated per test."""
 import math
 
 import numpy as np
+import os
+
 import pytest
 import torch
 
@@ -459,3 +461,51 @@ def test_attn_dropout_consistent_forward_backward(kind, S):
     assert (out2.float() - out.float()).abs().max().item() > 1e-2          # a different seed gives a different mask
     out3, _ = ops.attn_fwd(qkv_b, mask, H, dropout_p=p_drop, seed=seed)
     assert torch.equal(out3, out)                                          # same seed: bitwise reproducible
+
+
+def test_smtp_mask_2d_matches_reference_golden():
+    """ggpt_smtp_mask_2d (config.smtp_inside) — bit-exact against the reference's outputs for the stored draws."""
+    import os
+    from graphgpt_b200 import ops
+    recs = torch.load(os.path.join(os.path.dirname(__file__), "golden", "aux", "smtp_inside.pt"))
+    for r in recs:
+        err = torch.zeros((1,), dtype=torch.int32, device="cuda")
+        out, lab = ops.smtp_mask_2d(r["ids"].cuda(), r["F"], r["mr"].cuda(), r["u_node"].cuda().contiguous(), r["power"],
+                                    err_flag=err)
+        assert torch.equal(out.cpu(), r["out_ids"]) and torch.equal(lab.cpu(), r["labels"])
+        assert err.item() == 0
+    bad = recs[0]["ids"].clone()
+    bad[0, 0, recs[0]["F"] + 2] = 10 ** 6                     # node index out of range -> flagged, not a wild read
+    err = torch.zeros((1,), dtype=torch.int32, device="cuda")
+    ops.smtp_mask_2d(bad.cuda(), recs[0]["F"], recs[0]["mr"].cuda(), recs[0]["u_node"].cuda().contiguous(), 1.0, err_flag=err)
+    assert err.item() == 3
+
+
+def test_smtp_inside_model_forward_matches_oracle():
+    """config.smtp_inside: the model masks inside forward() from torch's CUDA generator in the reference's draw order;
+    re-creating the draws with the same seed gives the oracle's inputs / labels, and the loss must match."""
+    from graphgpt_b200 import GraphGPTConfig, GraphGPTPretrainBase
+    from oracle import graphgpt_oracle as oracle
+    r = torch.load(os.path.join(os.path.dirname(__file__), "golden", "aux", "smtp_inside.pt"))[0]
+    F_ = r["F"]
+    cfgd = dict(vocab_size=756, hidden_size=64, intermediate_size=256, num_hidden_layers=2, num_attention_heads=1,
+                num_key_value_heads=1, head_dim=64, hidden_act="gelu", max_position_embeddings=256, rms_norm_eps=1e-6,
+                rope_theta=10000.0, pad_token_id=0, causal_attention=False, stacked_feat=F_, stack_method="short",
+                stacked_feat_agg_method="sum", next_n_token=F_, use_cache=False, smtp_inside=True, smtp_power=1.0)
+    sd = oracle.init_state_dict(cfgd, seed=9)
+    model = GraphGPTPretrainBase(GraphGPTConfig(**cfgd))
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().eval()
+    ids = r["ids"]
+    N, S, _ = ids.shape
+    am = (ids[:, :, 0] != 0).long()
+    torch.manual_seed(77)
+    out = model(input_ids=ids.cuda(), attention_mask=am.cuda())
+    torch.manual_seed(77)
+    torch.rand((N, 1, 1), device="cuda")
+    mr = torch.rand((N, 1, 1), device="cuda").view(-1).cpu()
+    u = torch.rand((N, S, F_), device="cuda").cpu()
+    ids_m, labels = oracle.smtp_mask_2d(ids[:, :, :F_], ids[:, :, F_ + 2], mr, u, 1.0)
+    ref = oracle.pretrain_forward(sd, cfgd, ids_m, am, labels)
+    assert out.head1_logits.shape == ref["logits"].shape
+    assert abs(out.head1_loss.item() - ref["loss"].item()) <= 1e-3 * abs(ref["loss"].item())
