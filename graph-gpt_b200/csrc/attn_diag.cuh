@@ -11,7 +11,7 @@ struct DiagParams {
   const uint32_t* mask_bits;   // [N,S,words]
   const int* tile_start;       // [N,max_tiles+1]
   const uint8_t* tile_cls;     // [N,max_tiles,max_tiles]
-  const int* iso_list;         // [count] entries n*max_tiles + tile
+  const int* iso_list;         // [count] 16-byte descriptors {sequence, first row, rows, class} (16-byte aligned)
   const int* iso_count;        // [1]
   int q_col0, k_col0, v_col0;
   float scale, scale_log2;
@@ -32,8 +32,8 @@ struct DiagParams {
 
 // iso_flags[N*max_tiles] = 1 for tiles whose only active pair (row and column of tile_cls) is the diagonal one;
 // iso_list / iso_count = compact device-side work list of those tiles.
-int attn_iso_build(const uint8_t* cls, const int* n_tiles, int N, int max_tiles, uint8_t* iso_flags, int* iso_list,
-                   int* iso_count, cudaStream_t s);
+int attn_iso_build(const uint8_t* cls, const int* n_tiles, const int* tile_start, int N, int max_tiles, uint8_t* iso_flags,
+                   int* iso_list, int* iso_count, cudaStream_t s);
 int attn_diag_fwd_launch(const CUtensorMap& tm, const DiagParams& p, cudaStream_t s);
 int attn_diag_bwd_launch(const CUtensorMap& tmQKV, const CUtensorMap& tmDO, const DiagParams& p, cudaStream_t s);
 

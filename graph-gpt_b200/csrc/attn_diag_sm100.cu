@@ -18,11 +18,26 @@
 
 namespace ggpt {
 
-__device__ __forceinline__ void diag_mask_words(const uint32_t* __restrict__ mrow, int k0, int klen, uint32_t (&mw)[4]) {
-  const int w0 = k0 >> 5, sh = k0 & 31;
-  uint32_t w[5];
+struct DiagItem {
+  int n, h, r0, len, cls;
+};
+// Work item idx = (isolated tile idx / H, head idx % H).  The tile's {sequence, first row, rows, class} come from ONE
+// 16-byte descriptor load (written by attn_iso_kernel) — no dependent chain of list -> tile_start -> class loads.
+__device__ __forceinline__ DiagItem diag_item(const DiagParams& p, int idx) {
+  const int4 d = __ldg(reinterpret_cast<const int4*>(p.iso_list) + idx / p.H);
+  DiagItem it;
+  it.n = d.x; it.r0 = d.y; it.len = d.z; it.cls = d.w;
+  it.h = idx % p.H;
+  return it;
+}
+// raw 160 mask bits of one query row covering key columns [k0, k0 + 128) (any alignment); see diag_mask_finish
+__device__ __forceinline__ void diag_mask_raw(const uint32_t* __restrict__ mrow, int k0, uint32_t (&w)[5]) {
+  const int w0 = k0 >> 5;
 #pragma unroll
-  for (int i = 0; i < 5; ++i) w[i] = mrow[w0 + i];
+  for (int i = 0; i < 5; ++i) w[i] = __ldg(mrow + w0 + i);
+}
+__device__ __forceinline__ void diag_mask_finish(const uint32_t (&w)[5], int k0, int klen, uint32_t (&mw)[4]) {
+  const int sh = k0 & 31;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const uint32_t v = __funnelshift_r(w[i], w[i + 1], sh);
@@ -30,22 +45,6 @@ __device__ __forceinline__ void diag_mask_words(const uint32_t* __restrict__ mro
     const uint32_t keep = nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u));
     mw[i] = v & keep;
   }
-}
-
-struct DiagItem {
-  int n, h, r0, len, cls;
-};
-__device__ __forceinline__ DiagItem diag_item(const DiagParams& p, int idx) {
-  DiagItem it;
-  const int e = p.iso_list[idx / p.H];
-  it.h = idx % p.H;
-  it.n = e / p.max_tiles;
-  const int t = e % p.max_tiles;
-  const int* ts = p.tile_start + static_cast<size_t>(it.n) * (p.max_tiles + 1);
-  it.r0 = ts[t];
-  it.len = ts[t + 1] - it.r0;
-  it.cls = p.tile_cls[(static_cast<size_t>(it.n) * p.max_tiles + t) * p.max_tiles + t];
-  return it;
 }
 
 // =====================================================================================================
@@ -155,14 +154,26 @@ attn_diag_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const DiagParams
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
     uint8_t* sP = smem + kDFSmemP + grp * 32768;
     const uint32_t tS = tmem_base + grp * 256 + lane_addr;
+    // Global loads are kept off the critical path: the descriptor of this group's item after next and the mask words of
+    // its next item are requested while the current item is processed (they land one iteration before they are used).
+    auto load_item = [&](int i) -> DiagItem {
+      return (i < n_items) ? diag_item(p, blockIdx.x + i * gridDim.x) : DiagItem{0, 0, 0, 0, 0};
+    };
+    auto load_mask = [&](const DiagItem& it, uint32_t (&w)[5]) {
+      const int row = it.r0 + min(r, max(it.len - 1, 0));
+      diag_mask_raw(p.mask_bits + (static_cast<size_t>(it.n) * p.S + row) * p.mask_words, it.r0, w);
+    };
+    DiagItem it = load_item(grp), it_next = load_item(grp + 2);
+    uint32_t mraw[5];
+    load_mask(it, mraw);
     for (int i = grp; i < n_items; i += 2) {
-      const DiagItem it = diag_item(p, blockIdx.x + i * gridDim.x);
+      const DiagItem it_next2 = load_item(i + 4);
       const bool row_ok = r < it.len;
       const uint32_t ph = (i >> 1) & 1;
       uint32_t mw[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
       if (!row_ok) mw[0] = mw[1] = mw[2] = mw[3] = 0u;
-      else if (it.cls == 2)
-        diag_mask_words(p.mask_bits + (static_cast<size_t>(it.n) * p.S + it.r0 + r) * p.mask_words, it.r0, it.len, mw);
+      else if (it.cls == 2) diag_mask_finish(mraw, it.r0, it.len, mw);
+      load_mask(it_next, mraw);            // for the next iteration
       const uint32_t rowkey = drop_rowkey(p.drop.seed_lo, p.drop.seed_hi, it.n, it.h, it.r0 + r);
       const uint32_t rowkey2 = drop_rowkey2(rowkey);
       mbar_wait(&s_full[grp], ph);
@@ -259,6 +270,8 @@ attn_diag_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const DiagParams
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&slot_free[grp]);
+      it = it_next;
+      it_next = it_next2;
     }
   }
 
@@ -400,20 +413,45 @@ attn_diag_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     const int r = quad * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
     DiagItem prev{};
+    // RoPE table rows of the epilogue's tokens: the two warps of a lane quadrant need the same 32 cos rows and 32 sin rows,
+    // so warp `half` fetches table `half` for both with cp.async (no registers, issued BEFORE the softmax pass of the next
+    // item so the L2 latency is hidden) into a 4 KB swizzled buffer; a 64-thread named barrier publishes them.
+    uint8_t* gb_cos = smem + kDBSmemGather + (quad * 2) * 4096;
+    uint8_t* gb_sin = gb_cos + 4096;
+    auto pair_barrier = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory"); };
+    auto issue_gather = [&](int pos_row) {
+      pair_barrier();                                 // the partner has finished reading the previous tables
+      const float* tab = half ? p.sin_tab : p.cos_tab;
+      uint8_t* dst = half ? gb_sin : gb_cos;
+      const int rd_row = lane >> 3, rd_j = lane & 7;
+#pragma unroll
+      for (int it8 = 0; it8 < 8; ++it8) {
+        const int rr = it8 * 4 + rd_row;
+        const int src = __shfl_sync(0xffffffffu, pos_row, rr);
+        const float* g = tab + static_cast<long long>(src) * 32 + rd_j * 4;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + rr * 128 + ((rd_j ^ (rr & 7)) << 4))),
+                     "l"(g)
+                     : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     auto epilogue = [&](int i, const DiagItem& it) {
       const int st = i & 1;
-      mbar_wait(&acc_full[st], (i >> 1) & 1);
-      tc_fence_after();
       const uint32_t d = tmem_base + st * 256 + lane_addr;
       const bool ok = r < it.len;
       const long long grow = static_cast<long long>(it.n) * p.S + it.r0 + r;
-      const int pos = ok ? p.pos[grow] : 0;
       float cs[32], sn[32];
-      {
-        uint8_t* gbuf = smem + kDBSmemGather + (warp - 2) * 4096;
-        warp_gather_rows32(p.cos_tab, pos, gbuf, lane, cs);
-        warp_gather_rows32(p.sin_tab, pos, gbuf, lane, sn);
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      pair_barrier();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 a = *reinterpret_cast<const float4*>(gb_cos + lane * 128 + ((j ^ (lane & 7)) << 4));
+        const float4 b = *reinterpret_cast<const float4*>(gb_sin + lane * 128 + ((j ^ (lane & 7)) << 4));
+        cs[j * 4 + 0] = a.x; cs[j * 4 + 1] = a.y; cs[j * 4 + 2] = a.z; cs[j * 4 + 3] = a.w;
+        sn[j * 4 + 0] = b.x; sn[j * 4 + 1] = b.y; sn[j * 4 + 2] = b.z; sn[j * 4 + 3] = b.w;
       }
+      mbar_wait(&acc_full[st], (i >> 1) & 1);
+      tc_fence_after();
       auto store_pair = [&](uint32_t (&x1)[32], uint32_t (&x2)[32], bool rot, int col0) {
         if (!ok) return;
         __nv_bfloat16* orow = p.dqkv + grow * p.ld_dqkv + col0;
@@ -479,19 +517,52 @@ attn_diag_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       if (lane == 0) mbar_arrive(&acc_empty[st]);
     };
 
+    // Per-row inputs (the 3 mask words covering this warp's 64 key columns, lse, D, position) of item i+1 and the
+    // descriptor of item i+2 are requested while item i is processed: no global-load latency on the critical path.
+    struct RowPre {
+      uint32_t w[3];
+      float lse, dsum;
+      int pos;
+    };
+    auto load_item = [&](int i) -> DiagItem {
+      return (i < n_items) ? diag_item(p, blockIdx.x + i * gridDim.x) : DiagItem{0, 0, 0, 0, 0};
+    };
+    auto load_row = [&](const DiagItem& it, RowPre& o) {
+      const int rr = min(r, max(it.len - 1, 0));
+      const size_t row = static_cast<size_t>(it.n) * p.S + it.r0 + rr;
+      const uint32_t* mrow = p.mask_bits + row * p.mask_words + (it.r0 >> 5) + half * 2;
+      o.w[0] = __ldg(mrow);
+      o.w[1] = __ldg(mrow + 1);
+      o.w[2] = __ldg(mrow + 2);
+      const size_t li = (static_cast<size_t>(it.n) * p.H + it.h) * p.S + it.r0 + rr;
+      o.lse = __ldg(p.lse_in + li);
+      o.dsum = __ldg(p.dsum + li);
+      o.pos = __ldg(p.pos + row);
+    };
+    DiagItem it = load_item(0), it_next = load_item(1);
+    RowPre rp;
+    load_row(it, rp);
+    int pos_prev = 0;
     for (int i = 0; i < n_items; ++i) {
-      const DiagItem it = diag_item(p, blockIdx.x + i * gridDim.x);
+      const DiagItem it_next2 = load_item(i + 2);
+      RowPre rp_next;
+      load_row(it_next, rp_next);
+      if (i > 0) issue_gather(pos_prev);     // tables for epilogue(i-1), hidden behind the softmax pass below
       const bool row_ok = r < it.len;
-      float lse2 = 0.f, dsum = 0.f;
-      uint32_t mw[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-      if (row_ok) {
-        const size_t li = (static_cast<size_t>(it.n) * p.H + it.h) * p.S + it.r0 + r;
-        lse2 = p.lse_in[li] * 1.4426950408889634f;
-        dsum = p.dsum[li];
-        if (it.cls == 2)
-          diag_mask_words(p.mask_bits + (static_cast<size_t>(it.n) * p.S + it.r0 + r) * p.mask_words, it.r0, it.len, mw);
-      } else {
-        mw[0] = mw[1] = mw[2] = mw[3] = 0u;
+      const float lse2 = row_ok ? rp.lse * 1.4426950408889634f : 0.f;
+      const float dsum = row_ok ? rp.dsum : 0.f;
+      // mw[cc] = 32 mask bits of this row for key columns (half*2 + cc)*32 ..
+      uint32_t mw[2] = {0xffffffffu, 0xffffffffu};
+      if (!row_ok) {
+        mw[0] = mw[1] = 0u;
+      } else if (it.cls == 2) {
+        const int sh = it.r0 & 31;
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const uint32_t v = __funnelshift_r(rp.w[cc], rp.w[cc + 1], sh);
+          const int nvalid = it.len - 32 * (half * 2 + cc);
+          mw[cc] = v & (nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u)));
+        }
       }
       const int st = i & 1;
       const uint32_t rowkey = drop_rowkey(p.drop.seed_lo, p.drop.seed_hi, it.n, it.h, it.r0 + r);
@@ -505,7 +576,7 @@ attn_diag_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
 #pragma unroll 1
       for (int cc = 0; cc < 2; ++cc) {
         const int c = half * 2 + cc;
-        const uint32_t w = (c == 0) ? mw[0] : (c == 1) ? mw[1] : (c == 2) ? mw[2] : mw[3];
+        const uint32_t w = cc ? mw[1] : mw[0];
         uint8_t* pbase = sP + half * 16384 + r * 128;
         uint8_t* dbase = sDS + half * 16384 + r * 128;
         if (!__any_sync(0xffffffffu, w != 0u)) {
@@ -562,7 +633,12 @@ attn_diag_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       if (lane == 0) mbar_arrive(pds_full);
       if (i > 0) epilogue(i - 1, prev);
       prev = it;
+      pos_prev = rp.pos;
+      it = it_next;
+      it_next = it_next2;
+      rp = rp_next;
     }
+    issue_gather(pos_prev);
     epilogue(n_items - 1, prev);
   }
 
@@ -575,7 +651,9 @@ attn_diag_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
 }
 
 // isolated tile: its diagonal pair is active and nothing else in its row or column of the class matrix is
-__global__ void attn_iso_kernel(const uint8_t* __restrict__ cls, const int* __restrict__ n_tiles, int N, int max_tiles,
+// The work list holds one 16-byte descriptor {sequence, first row, rows, class} per isolated tile.
+__global__ void attn_iso_kernel(const uint8_t* __restrict__ cls, const int* __restrict__ n_tiles,
+                                const int* __restrict__ tile_start, int N, int max_tiles,
                                 uint8_t* __restrict__ iso_flags, int* __restrict__ iso_list, int* __restrict__ iso_count) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * max_tiles) return;
@@ -589,7 +667,12 @@ __global__ void attn_iso_kernel(const uint8_t* __restrict__ cls, const int* __re
       if (j != t && (c[t * max_tiles + j] != 0 || c[j * max_tiles + t] != 0)) iso = false;
   }
   iso_flags[i] = iso ? 1 : 0;
-  if (iso) iso_list[atomicAdd(iso_count, 1)] = i;
+  if (iso) {
+    const int* ts = tile_start + static_cast<size_t>(n) * (max_tiles + 1);
+    const int slot = atomicAdd(iso_count, 1);
+    reinterpret_cast<int4*>(iso_list)[slot] =
+        make_int4(n, ts[t], ts[t + 1] - ts[t], cls[(static_cast<size_t>(n) * max_tiles + t) * max_tiles + t]);
+  }
   if (t == 0) atomicAdd(iso_count + 1, nt);   // iso_count[1] = total number of row tiles in the batch
 }
 
@@ -604,11 +687,11 @@ static int set_smem_attr(const void* fn, int bytes, bool* done) {
   return 0;
 }
 
-int attn_iso_build(const uint8_t* cls, const int* n_tiles, int N, int max_tiles, uint8_t* iso_flags, int* iso_list,
-                   int* iso_count, cudaStream_t s) {
+int attn_iso_build(const uint8_t* cls, const int* n_tiles, const int* tile_start, int N, int max_tiles, uint8_t* iso_flags,
+                   int* iso_list, int* iso_count, cudaStream_t s) {
   cudaMemsetAsync(iso_count, 0, 2 * sizeof(int), s);
   const int n = N * max_tiles;
-  attn_iso_kernel<<<(n + 255) / 256, 256, 0, s>>>(cls, n_tiles, N, max_tiles, iso_flags, iso_list, iso_count);
+  attn_iso_kernel<<<(n + 255) / 256, 256, 0, s>>>(cls, n_tiles, tile_start, N, max_tiles, iso_flags, iso_list, iso_count);
   return check_launch("attn_iso_kernel");
 }
 

@@ -328,25 +328,33 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
 // ---------------------------------------------------------------------------------------------
 __global__ void attn_mask_bits_kernel(const long long* __restrict__ am, int am_dims, int N, int S, int causal,
                                       int mask_words, uint32_t* __restrict__ bits) {
-  // one warp per (n, q, word)
+  // one warp per (n, q, group of 4 words = 128 keys): four independent 8-byte loads per lane are in flight at once
+  // (the [N,S,S] int64 mask of a packed batch is 537 MB per step — this pass is pure HBM streaming)
   const long long gw = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  const long long total = static_cast<long long>(N) * S * mask_words;
+  const int groups = mask_words >> 2;   // mask_words is a multiple of 4
+  const long long total = static_cast<long long>(N) * S * groups;
   if (gw >= total) return;
-  const int w = static_cast<int>(gw % mask_words);
-  const long long nq = gw / mask_words;
+  const int w0 = static_cast<int>(gw % groups) * 4;
+  const long long nq = gw / groups;
   const int q = static_cast<int>(nq % S);
   const int n = static_cast<int>(nq / S);
-  const int k = w * 32 + lane;
-  bool keep = false;
-  if (k < S) {
-    if (am == nullptr) keep = true;
-    else if (am_dims == 2) keep = am[static_cast<long long>(n) * S + k] != 0;
-    else keep = am[(static_cast<long long>(n) * S + q) * S + k] != 0;
-    if (causal && k > q) keep = false;
+  long long v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = (w0 + i) * 32 + lane;
+    v[i] = 1;
+    if (k < S && am != nullptr)
+      v[i] = (am_dims == 2) ? am[static_cast<long long>(n) * S + k] : am[(static_cast<long long>(n) * S + q) * S + k];
   }
-  const uint32_t word = __ballot_sync(0xffffffffu, keep);
-  if (lane == 0) bits[gw] = word;
+  uint32_t word[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = (w0 + i) * 32 + lane;
+    const bool keep = (k < S) && (v[i] != 0) && !(causal && k > q);
+    word[i] = __ballot_sync(0xffffffffu, keep);
+  }
+  if (lane == 0) *reinterpret_cast<uint4*>(bits + nq * mask_words + w0) = make_uint4(word[0], word[1], word[2], word[3]);
 }
 
 // Row-tile plan for one sequence (one CTA per sequence).  lo/hi = first/last visible key of each query row;
@@ -462,7 +470,7 @@ int ggpt_attn_mask_build(const long long* attention_mask, int mask_dims, int N, 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int words = ggpt_attn_mask_words(S);
   const int mt = ggpt_attn_max_tiles(S);
-  const long long warps = static_cast<long long>(N) * S * words;
+  const long long warps = static_cast<long long>(N) * S * (words / 4);
   const long long blocks = (warps * 32 + 255) / 256;
   attn_mask_bits_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(attention_mask, mask_dims, N, S, causal, words,
                                                                        mask_bits);
@@ -479,7 +487,8 @@ int ggpt_attn_mask_build(const long long* attention_mask, int mask_dims, int N, 
   attn_tile_cls_kernel<<<static_cast<unsigned>((warps2 * 32 + 255) / 256), 256, 0, s>>>(mask_bits, N, S, words, mt,
                                                                                          tile_start, n_tiles, tile_cls);
   if (int rc = check_launch("attn_tile_cls_kernel")) return rc;
-  return attn_iso_build(tile_cls, n_tiles, N, mt, iso_flags, iso_list, iso_count, s);
+  GGPT_REQUIRE((reinterpret_cast<uintptr_t>(iso_list) & 15) == 0, "attn_mask_build: iso_list must be 16-byte aligned");
+  return attn_iso_build(tile_cls, n_tiles, tile_start, N, mt, iso_flags, iso_list, iso_count, s);
 }
 
 int ggpt_attn_fwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int v_col0, const uint32_t* mask_bits,

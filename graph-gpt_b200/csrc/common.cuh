@@ -117,6 +117,14 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// 1-D bulk copy global -> shared (TMA engine, no tensor map): 16-byte aligned addresses, size a multiple of 16.
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // ---- thread-block clusters -------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -389,6 +397,22 @@ __device__ __forceinline__ float gelu_erf(float x) {
   float cdf, pdf;
   gelu_cdf_pdf(x, cdf, pdf);
   return x * cdf;
+}
+// Forward-only erf GELU with ONE MUFU op (the GEMM epilogue is MUFU-limited): Abramowitz-Stegun 7.1.28,
+//   erf(x) = 1 - 1 / (1 + a1 x + ... + a6 x^6)^16  (x >= 0, |error| <= 3e-7);  |gelu error| <= 8.2e-7 over [-12, 12]
+//   (checked against scipy in fp32 emulation), far below the bf16 rounding of the output.  Overflow of the 16th power
+//   for |x| > ~17 gives 1/inf = 0, i.e. Phi = 0 or 1 exactly.
+__device__ __forceinline__ float gelu_erf_fwd(float g) {
+  const float ax = fabsf(g) * 0.70710678118654752f;
+  float p = fmaf(0.0000430638f, ax, 0.0002765672f);
+  p = fmaf(p, ax, 0.0001520143f);
+  p = fmaf(p, ax, 0.0092705272f);
+  p = fmaf(p, ax, 0.0422820123f);
+  p = fmaf(p, ax, 0.0705230784f);
+  p = fmaf(p, ax, 1.0f);
+  p *= p; p *= p; p *= p; p *= p;
+  const float r = __fdividef(0.5f, p);          // 0.5 * (1 - erf|x|)
+  return g * (g >= 0.f ? 1.0f - r : r);
 }
 #endif  // __CUDACC__
 

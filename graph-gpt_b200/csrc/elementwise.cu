@@ -1,6 +1,10 @@
 // HBM-bound kernels of the GraphGPT hot path: stacked-token embedding gather-sum, RMSNorm, GeGLU backward,
 // loss-head compaction / gathers, fp32 cross-entropy, fused AdamW.  All are one-pass, vectorised (16-byte
 // accesses), warp-shuffle reductions, grid sized from the SM count.
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "common.cuh"
 #include "../../include/ggpt_b200.h"
 
@@ -313,6 +317,121 @@ __global__ void __launch_bounds__(128, 3) rmsnorm_bwd_kernel(const __nv_bfloat16
   for (int c = threadIdx.x; c < d; c += blockDim.x) atomicAdd(dw + c, s_dw[c]);
 }
 
+// Same computation with the row inputs streamed through shared memory by 1-D bulk copies (cp.async.bulk, the TMA engine
+// without a tensor map): every warp owns a private ring of kStages row slots (x | dresid | dy = 10*d bytes) guarded by
+// its own mbarriers, lane 0 keeps kStages rows of loads in flight while the warp reduces / writes the current one.
+// The register version above alternates "issue loads - wait - compute - store" per warp and reaches ~3.7 TB/s on a
+// B200 (12 warps per SM at 154 registers); decoupling the loads from the registers keeps 24 rows per SM in flight.
+template <int NV, int kStages>
+__global__ void __launch_bounds__(256, 1)
+rmsnorm_bwd_bulk_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const float* __restrict__ x,
+                        const float* __restrict__ rstd_in, const float* __restrict__ w,
+                        const float* __restrict__ dresid, float* __restrict__ dx_out,
+                        __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dw, long long T, int d) {
+  extern __shared__ __align__(128) uint8_t rb_smem[];
+  constexpr int kWarps = 8;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row_bytes = 10 * d;                                   // x (4d) | dresid (4d) | dy (2d)
+  float* s_dw = reinterpret_cast<float*>(rb_smem);                // [d]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rb_smem + ((4 * d + 127) / 128) * 128);   // [kWarps][kStages]
+  uint8_t* ring = reinterpret_cast<uint8_t*>(bars) + 128 * ((kWarps * kStages * 8 + 127) / 128) +
+                  static_cast<size_t>(warp) * kStages * row_bytes;
+  uint64_t* my_bar = bars + warp * kStages;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) s_dw[c] = 0.f;
+  if (lane == 0) {
+    for (int s = 0; s < kStages; ++s) mbar_init(&my_bar[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const long long t0 = static_cast<long long>(blockIdx.x) * kWarps + warp;
+  const long long tstep = static_cast<long long>(gridDim.x) * kWarps;
+  const uint32_t tx_bytes = static_cast<uint32_t>((dresid != nullptr ? 10 : 6) * d);
+  auto issue = [&](long long t, int s) {   // lane 0 only
+    uint8_t* dst = ring + s * row_bytes;
+    mbar_expect_tx(&my_bar[s], tx_bytes);
+    bulk_load_1d(dst, x + t * d, 4 * d, &my_bar[s]);
+    if (dresid != nullptr) bulk_load_1d(dst + 4 * d, dresid + t * d, 4 * d, &my_bar[s]);
+    bulk_load_1d(dst + 8 * d, dy + t * lddy, 2 * d, &my_bar[s]);
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s)
+      if (t0 + s * tstep < T) issue(t0 + s * tstep, s);
+  }
+  const float inv_d = 1.0f / static_cast<float>(d);
+  float4 dwacc[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) dwacc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  int stage = 0;
+  uint32_t phase = 0;
+  float rstd_next = (t0 < T) ? rstd_in[t0] : 0.f;
+  for (long long t = t0; t < T; t += tstep) {
+    const float rstd = rstd_next;
+    if (t + tstep < T) rstd_next = rstd_in[t + tstep];   // one row ahead: its latency overlaps this row's work
+    mbar_wait(&my_bar[stage], phase);
+    const uint8_t* src = ring + stage * row_bytes;
+    float4 xs[NV], gv[NV];
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = lane * 4 + k * 128;
+      if (c < d) {
+        const float4 xv = *reinterpret_cast<const float4*>(src + 4 * c);
+        const uint2 dv = *reinterpret_cast<const uint2*>(src + 8 * d + 2 * c);
+        const float2 d01 = unpack_bf16(dv.x), d23 = unpack_bf16(dv.y);
+        xs[k] = make_float4(xv.x * rstd, xv.y * rstd, xv.z * rstd, xv.w * rstd);
+        gv[k] = make_float4(d01.x, d01.y, d23.x, d23.y);
+        dwacc[k].x += gv[k].x * xs[k].x; dwacc[k].y += gv[k].y * xs[k].y;
+        dwacc[k].z += gv[k].z * xs[k].z; dwacc[k].w += gv[k].w * xs[k].w;
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(w + c));
+        gv[k].x *= wv.x; gv[k].y *= wv.y; gv[k].z *= wv.z; gv[k].w *= wv.w;
+        dot += gv[k].x * xs[k].x + gv[k].y * xs[k].y + gv[k].z * xs[k].z + gv[k].w * xs[k].w;
+      }
+    }
+    dot = warp_sum(dot) * inv_d;  // mean(g * xhat)
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = lane * 4 + k * 128;
+      if (c < d) {
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (dresid != nullptr) r = *reinterpret_cast<const float4*>(src + 4 * d + 4 * c);
+        float4 o;
+        o.x = r.x + rstd * (gv[k].x - xs[k].x * dot);
+        o.y = r.y + rstd * (gv[k].y - xs[k].y * dot);
+        o.z = r.z + rstd * (gv[k].z - xs[k].z * dot);
+        o.w = r.w + rstd * (gv[k].w - xs[k].w * dot);
+        *reinterpret_cast<float4*>(dx_out + t * d + c) = o;
+        if (dx_bf16 != nullptr) {
+          uint2 ob;
+          ob.x = pack_bf16(o.x, o.y);
+          ob.y = pack_bf16(o.z, o.w);
+          *reinterpret_cast<uint2*>(dx_bf16 + t * d + c) = ob;
+        }
+      }
+    }
+    // the slot is free once every lane has read it: refill it with the row kStages iterations ahead
+    __syncwarp();
+    if (lane == 0 && t + kStages * tstep < T) {
+      fence_proxy_async_smem();
+      issue(t + kStages * tstep, stage);
+    }
+    if (++stage == kStages) {
+      stage = 0;
+      phase ^= 1;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = lane * 4 + k * 128;
+    if (c < d) {
+      atomicAdd(&s_dw[c + 0], dwacc[k].x); atomicAdd(&s_dw[c + 1], dwacc[k].y);
+      atomicAdd(&s_dw[c + 2], dwacc[k].z); atomicAdd(&s_dw[c + 3], dwacc[k].w);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < d; c += blockDim.x) atomicAdd(dw + c, s_dw[c]);
+}
+
 // =============================================================================================
 // GeGLU backward: dg = dact * u * gelu'(g), du = dact * gelu(g)      (gu = [g | u], bf16)
 // =============================================================================================
@@ -560,6 +679,8 @@ __global__ void ce_fwd_kernel(const float* __restrict__ logits, long long ldl, c
 }
 
 // dlogits[e,c] = (softmax(logits[e])[c] - [c == label[e]]) * wgt[e] * scale[0] * gout[0]   (bf16, pad columns = 0)
+// (FOCAL is a template flag so that powf's slow path costs the plain cross-entropy kernel no registers)
+template <bool FOCAL>
 __global__ void ce_bwd_kernel(const float* __restrict__ logits, long long ldl, const int* __restrict__ labels,
                               const float* __restrict__ wgt, const float* __restrict__ row_lse,
                               const float* __restrict__ scale, const float* __restrict__ gout,
@@ -574,7 +695,7 @@ __global__ void ce_bwd_kernel(const float* __restrict__ logits, long long ldl, c
     const float lse = row_lse[e];
     const int lab = labels[e];
     float w = (wgt ? wgt[e] : 1.0f) * g;
-    if (focal_gamma > 0.f) w *= powf(fmaxf(1.0f - __expf(row[lab] - lse), 0.f), focal_gamma);   // detached (1 - p_t)^gamma
+    if (FOCAL) w *= powf(fmaxf(1.0f - __expf(row[lab] - lse), 0.f), focal_gamma);   // detached (1 - p_t)^gamma
     for (int c = lane * 2; c < Vpad; c += 64) {
       float v0 = 0.f, v1 = 0.f;
       if (c < V) v0 = (__expf(row[c] - lse) - (c == lab ? 1.f : 0.f)) * w;
@@ -735,10 +856,37 @@ int ggpt_rmsnorm_bwd(const void* dy, long long lddy, const float* x, const float
   GGPT_REQUIRE(dy && x && rstd && w && dx_out && dw, "rmsnorm_bwd: null pointer");
   GGPT_REQUIRE(T > 0 && d % 4 == 0 && lddy % 4 == 0, "rmsnorm_bwd: bad sizes");
   GGPT_REQUIRE(d <= 2048, "rmsnorm_bwd: hidden size %d > 2048 is not instantiated", d);
-  const int grid = grid_for_rows(T, 4, 12);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const __nv_bfloat16* dyb = static_cast<const __nv_bfloat16*>(dy);
   __nv_bfloat16* dxb = static_cast<__nv_bfloat16*>(dx_bf16);
+  // bulk-copy pipelined version: 16-byte aligned rows, the per-warp rings must fit in shared memory
+  {
+    auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    const size_t head = ((4 * static_cast<size_t>(d) + 127) / 128) * 128 + 128 * ((8 * 3 * 8 + 127) / 128);
+    const size_t smem3 = head + static_cast<size_t>(8) * 3 * 10 * d;
+    static const bool no_bulk = getenv("GGPT_RMSNORM_BWD_NO_BULK") != nullptr;
+    if (!no_bulk && d % 8 == 0 && lddy % 8 == 0 && aligned16(x) && aligned16(dy) && (dresid == nullptr || aligned16(dresid)) &&
+        smem3 <= 200 * 1024 && (d == 768 || d == 1024 || d == 512 || d == 256)) {
+      const int grid_b = static_cast<int>(std::min<long long>((T + 7) / 8, num_sms()));
+      auto launch = [&](auto kern) -> int {
+        static bool attr_set = false;   // one static per instantiation of this lambda's operator()
+        if (!attr_set) {
+          if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+            set_error("rmsnorm_bwd: cudaFuncSetAttribute failed");
+            return -2;
+          }
+          attr_set = true;
+        }
+        kern<<<grid_b, 256, smem3, s>>>(dyb, lddy, x, rstd, w, dresid, dx_out, dxb, dw, T, d);
+        return check_launch("rmsnorm_bwd_bulk_kernel");
+      };
+      if (d == 256) return launch(rmsnorm_bwd_bulk_kernel<2, 3>);
+      if (d == 512) return launch(rmsnorm_bwd_bulk_kernel<4, 3>);
+      if (d == 768) return launch(rmsnorm_bwd_bulk_kernel<6, 3>);
+      return launch(rmsnorm_bwd_bulk_kernel<8, 3>);
+    }
+  }
+  const int grid = grid_for_rows(T, 4, 12);
   const size_t sm = d * sizeof(float);
   const int nv = (d + 127) / 128;
   if (nv <= 1) rmsnorm_bwd_kernel<1><<<grid, 128, sm, s>>>(dyb, lddy, x, rstd, w, dresid, dx_out, dxb, dw, T, d);
@@ -825,9 +973,14 @@ int ggpt_ce_bwd(const float* logits, long long ldl, const int* labels, const flo
   GGPT_REQUIRE(logits && labels && row_lse && scale && dlogits, "ce_bwd: null pointer");
   GGPT_REQUIRE(ldd % 8 == 0 && ldd >= ((V + 7) / 8) * 8, "ce_bwd: ldd must be a multiple of 8 covering V");
   if (L <= 0) return 0;
-  ce_bwd_kernel<<<grid_for_rows(L, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      logits, ldl, labels, wgt, row_lse, scale, gout, static_cast<__nv_bfloat16*>(dlogits), ldd, L, V, ((V + 7) / 8) * 8,
-      focal_gamma);
+  if (focal_gamma > 0.f)
+    ce_bwd_kernel<true><<<grid_for_rows(L, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        logits, ldl, labels, wgt, row_lse, scale, gout, static_cast<__nv_bfloat16*>(dlogits), ldd, L, V,
+        ((V + 7) / 8) * 8, focal_gamma);
+  else
+    ce_bwd_kernel<false><<<grid_for_rows(L, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        logits, ldl, labels, wgt, row_lse, scale, gout, static_cast<__nv_bfloat16*>(dlogits), ldd, L, V,
+        ((V + 7) / 8) * 8, focal_gamma);
   return check_launch("ce_bwd_kernel");
 }
 

@@ -292,6 +292,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int row0 = m0 + quad * 32;                 // first global row of this warp's quadrant
       const int row = row0 + lane;                     // write-phase row of this thread
       const bool row_ok = row < p.M;
+      // QKV_ROPE: cos/sin rows of this thread's token — the same for every head — are gathered (coalesced, through the
+      // staging buffer) BEFORE waiting for the accumulator, so the dependent pos -> table-row loads overlap the mainloop
+      float cc[(EPI == EPI_QKV_ROPE) ? 32 : 1], ss[(EPI == EPI_QKV_ROPE) ? 32 : 1];
+      if constexpr (EPI == EPI_QKV_ROPE) {
+        if (nb * BN + half * (BN / 2) < p.rope_cols) {   // warp-uniform
+          const int pos = row_ok ? p.pos[row] : 0;
+          warp_gather_rows32(p.cos_tab, pos, stg, lane, cc);
+          warp_gather_rows32(p.sin_tab, pos, stg, lane, ss);
+        }
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
@@ -394,7 +404,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            rg[j] = __float_as_uint(gelu_erf(__uint_as_float(rg[j])) * __uint_as_float(ru[j]));
+            rg[j] = __float_as_uint(gelu_erf_fwd(__uint_as_float(rg[j])) * __uint_as_float(ru[j]));
           put_bf16_32(hh * 4, rg);
         }
         copy_out_bf16(reinterpret_cast<__nv_bfloat16*>(p.C2), p.ldc2, nh + c, half_n);
@@ -443,14 +453,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       } else if constexpr (EPI == EPI_QKV_ROPE) {
         const int n0 = nb * BN;
-        const int pos = row_ok ? p.pos[row] : 0;
-        // cos/sin rows of this thread's token: the same for every head, gathered once per tile (coalesced)
-        float cc[32], ss[32];
-        const bool any_rot = (n0 + half * (BN / 2)) < p.rope_cols;   // warp-uniform
-        if (any_rot) {
-          warp_gather_rows32(p.cos_tab, pos, stg, lane, cc);
-          warp_gather_rows32(p.sin_tab, pos, stg, lane, ss);
-        }
 #pragma unroll 1
         for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 64) {   // one head (64 columns) per iteration
           uint32_t r1[32], r2[32];

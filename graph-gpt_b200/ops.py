@@ -157,7 +157,7 @@ def attn_mask_build(attention_mask, N, S, causal, device):
     n_tiles = torch.empty((N,), device=device, dtype=torch.int32)
     cls = torch.empty((N, mt, mt), device=device, dtype=torch.uint8)
     iso_flags = torch.empty((N, mt), device=device, dtype=torch.uint8)
-    iso_list = torch.empty((N * mt,), device=device, dtype=torch.int32)
+    iso_list = torch.empty((N * mt, 4), device=device, dtype=torch.int32)    # {sequence, first row, rows, class} per tile
     iso_count = torch.empty((2,), device=device, dtype=torch.int32)
     dims = 0
     if attention_mask is not None:

@@ -83,9 +83,10 @@ int ggpt_attn_max_tiles(int S);
  *   tile_start [N,max_tiles+1], n_tiles [N]   variable row tiles (<= 128 rows, cut on block boundaries of the mask so
  *                                     packed segments never straddle a tile; uniform 128 grid otherwise)
  *   tile_cls   [N,max_tiles,max_tiles] class of every (query tile, key tile): 0 masked, 1 fully visible, 2 mixed
- *   iso_flags  [N,max_tiles], iso_list [N*max_tiles], iso_count [2]   tiles whose only active pair is their own
- *                                     diagonal one (every tile of a packed batch): flags + compact work list for the
- *                                     persistent single-pass kernels (iso_count[0] = #isolated, iso_count[1] = #tiles);
+ *   iso_flags  [N,max_tiles], iso_list [4*N*max_tiles] (16-byte aligned), iso_count [2]   tiles whose only active pair
+ *                                     is their own diagonal one (every tile of a packed batch): flags + compact work
+ *                                     list (one {sequence, first row, rows, class} descriptor of 4 ints per tile) for
+ *                                     the persistent single-pass kernels (iso_count[0] = #isolated, [1] = #tiles);
  *                                     pass iso_flags = NULL to ggpt_attn_fwd/bwd to force the general tile-loop
  *                                     kernels, or run_general = 0 when the caller knows every tile is isolated
  * ref: modeling_helpers.py:38-64 (_update_causal_mask, _expand_mask_from_3d_mask: additive 0/finfo.min mask),
