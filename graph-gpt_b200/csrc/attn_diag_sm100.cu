@@ -246,24 +246,25 @@ attn_diag_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const DiagParams
       mbar_wait(&o_full[grp], ph);
       tc_fence_after();
       const float inv = (l > 0.f) ? p.drop.inv_keep / l : 0.f;
-      __nv_bfloat16* orow = p.out + (static_cast<long long>(it.n) * p.S + it.r0 + r) * p.ldo + it.h * 64;
+      // PV has retired (o_full), so this warp's own 32 rows of the P buffer are free: they stage the coalesced store
+      uint8_t* stg = sP + quad * 4096;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t o[32];
         tmem_ld32(tS + 128 + c * 32, o);
         tmem_ld_wait();
-        if (row_ok) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint4 v;
-            v.x = pack_bf16(__uint_as_float(o[g * 8 + 0]) * inv, __uint_as_float(o[g * 8 + 1]) * inv);
-            v.y = pack_bf16(__uint_as_float(o[g * 8 + 2]) * inv, __uint_as_float(o[g * 8 + 3]) * inv);
-            v.z = pack_bf16(__uint_as_float(o[g * 8 + 4]) * inv, __uint_as_float(o[g * 8 + 5]) * inv);
-            v.w = pack_bf16(__uint_as_float(o[g * 8 + 6]) * inv, __uint_as_float(o[g * 8 + 7]) * inv);
-            *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = v;
-          }
+        for (int g = 0; g < 4; ++g) {
+          uint4 v;
+          v.x = pack_bf16(__uint_as_float(o[g * 8 + 0]) * inv, __uint_as_float(o[g * 8 + 1]) * inv);
+          v.y = pack_bf16(__uint_as_float(o[g * 8 + 2]) * inv, __uint_as_float(o[g * 8 + 3]) * inv);
+          v.z = pack_bf16(__uint_as_float(o[g * 8 + 4]) * inv, __uint_as_float(o[g * 8 + 5]) * inv);
+          v.w = pack_bf16(__uint_as_float(o[g * 8 + 6]) * inv, __uint_as_float(o[g * 8 + 7]) * inv);
+          stage_put16(stg, lane, c * 4 + g, v);
         }
       }
+      stage_flush_rows(stg, lane, p.out + (static_cast<long long>(it.n) * p.S + it.r0 + quad * 32) * p.ldo + it.h * 64, p.ldo,
+                       it.len - quad * 32);
       if (row_ok && p.lse != nullptr)
         p.lse[(static_cast<size_t>(it.n) * p.H + it.h) * p.S + it.r0 + r] =
             (l > 0.f) ? (m * 0.6931471805599453f + logf(l)) : 0.f;
@@ -452,6 +453,8 @@ attn_diag_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       }
       mbar_wait(&acc_full[st], (i >> 1) & 1);
       tc_fence_after();
+      // (staging these stores through smem for full-line writes, as the forward kernel does, was measured slower here:
+      //  the extra live state spills — 6.9 -> 8.0 ms per step)
       auto store_pair = [&](uint32_t (&x1)[32], uint32_t (&x2)[32], bool rot, int col0) {
         if (!ok) return;
         __nv_bfloat16* orow = p.dqkv + grow * p.ld_dqkv + col0;

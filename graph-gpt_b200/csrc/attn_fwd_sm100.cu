@@ -295,9 +295,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
       ++it;
     }
 
-    if (row_ok) {
+    {
+      // every PV has retired (o_full of the last tile was waited for), so this warp's own 32 rows of the P buffer stage the
+      // output for full-line stores (stage_flush_rows) instead of 32 scattered 16-byte pieces per instruction
       const float inv = (l_run > 0.f) ? p.drop.inv_keep / l_run : 0.f;   // dropout keeps are rescaled by 1/(1-p)
-      __nv_bfloat16* orow = p.out + (static_cast<long long>(n) * p.S + q_row) * p.ldo + h * kHeadDim;
+      uint8_t* stg = sP + quad * 4096;
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
         uint4 o;
@@ -305,8 +307,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
         o.y = pack_bf16(o_acc[g * 8 + 2] * inv, o_acc[g * 8 + 3] * inv);
         o.z = pack_bf16(o_acc[g * 8 + 4] * inv, o_acc[g * 8 + 5] * inv);
         o.w = pack_bf16(o_acc[g * 8 + 6] * inv, o_acc[g * 8 + 7] * inv);
-        *reinterpret_cast<uint4*>(orow + g * 8) = o;
+        stage_put16(stg, lane, g, o);
       }
+      stage_flush_rows(stg, lane, p.out + (static_cast<long long>(n) * p.S + q0 + quad * 32) * p.ldo + h * kHeadDim, p.ldo,
+                       qlen - quad * 32);
+    }
+    if (row_ok) {
       if (p.lse != nullptr) {
         const float lse = (l_run > 0.f) ? (m_run * 0.6931471805599453f + logf(l_run)) : 0.f;
         p.lse[(static_cast<size_t>(n) * p.H + h) * p.S + q_row] = lse;

@@ -330,6 +330,26 @@ __device__ __forceinline__ void warp_gather_rows32(const float* __restrict__ tab
   __syncwarp();
 }
 
+// Coalesced store of a warp's 32 rows x 128 bytes (64 bf16) that are held one row per lane: the rows are transposed
+// through a 4 KB swizzled smem buffer so that each store instruction writes 4 complete 128-byte lines (8 lanes per row)
+// instead of 32 scattered 16-byte pieces (32 LSU wavefronts and half-used sectors per instruction).
+//   put: lane writes 16-byte chunk j (0..7) of its row;   flush: rows [0, rows_valid) go to dst_row0 + row * ld.
+__device__ __forceinline__ void stage_put16(uint8_t* stg, int lane, int j, uint4 v) {
+  *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = v;
+}
+__device__ __forceinline__ void stage_flush_rows(uint8_t* stg, int lane, __nv_bfloat16* dst_row0, long long ld, int rows_valid) {
+  __syncwarp();
+  const int rd_row = lane >> 3, rd_j = lane & 7;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int rr = it * 4 + rd_row;
+    if (rr < rows_valid)
+      *reinterpret_cast<uint4*>(dst_row0 + static_cast<long long>(rr) * ld + rd_j * 8) =
+          *reinterpret_cast<const uint4*>(stg + rr * 128 + ((rd_j ^ (rr & 7)) << 4));
+  }
+  __syncwarp();
+}
+
 // Counter-based dropout mask for attention probabilities: keep(n,h,q,k) is a pure function of (seed, n, h, q, k) and of
 // the row-tile plan, so the forward and the backward kernels regenerate identical masks with no stored state
 // (ref: HF:217 attention dropout).  One 32-bit draw serves a PAIR of adjacent keys of a key tile (16 bits each:

@@ -432,6 +432,23 @@ rmsnorm_bwd_bulk_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, co
   for (int c = threadIdx.x; c < d; c += blockDim.x) atomicAdd(dw + c, s_dw[c]);
 }
 
+template <int NV>
+static int launch_rmsnorm_bwd_bulk(int grid, size_t smem, cudaStream_t s, const __nv_bfloat16* dy, long long lddy,
+                                   const float* x, const float* rstd, const float* w, const float* dresid, float* dx_out,
+                                   __nv_bfloat16* dx_bf16, float* dw, long long T, int d) {
+  auto kern = rmsnorm_bwd_bulk_kernel<NV, 3>;
+  static bool attr_set = false;   // per instantiation
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+      set_error("rmsnorm_bwd: cudaFuncSetAttribute failed");
+      return -2;
+    }
+    attr_set = true;
+  }
+  kern<<<grid, 256, smem, s>>>(dy, lddy, x, rstd, w, dresid, dx_out, dx_bf16, dw, T, d);
+  return check_launch("rmsnorm_bwd_bulk_kernel");
+}
+
 // =============================================================================================
 // GeGLU backward: dg = dact * u * gelu'(g), du = dact * gelu(g)      (gu = [g | u], bf16)
 // =============================================================================================
@@ -868,22 +885,10 @@ int ggpt_rmsnorm_bwd(const void* dy, long long lddy, const float* x, const float
     if (!no_bulk && d % 8 == 0 && lddy % 8 == 0 && aligned16(x) && aligned16(dy) && (dresid == nullptr || aligned16(dresid)) &&
         smem3 <= 200 * 1024 && (d == 768 || d == 1024 || d == 512 || d == 256)) {
       const int grid_b = static_cast<int>(std::min<long long>((T + 7) / 8, num_sms()));
-      auto launch = [&](auto kern) -> int {
-        static bool attr_set = false;   // one static per instantiation of this lambda's operator()
-        if (!attr_set) {
-          if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
-            set_error("rmsnorm_bwd: cudaFuncSetAttribute failed");
-            return -2;
-          }
-          attr_set = true;
-        }
-        kern<<<grid_b, 256, smem3, s>>>(dyb, lddy, x, rstd, w, dresid, dx_out, dxb, dw, T, d);
-        return check_launch("rmsnorm_bwd_bulk_kernel");
-      };
-      if (d == 256) return launch(rmsnorm_bwd_bulk_kernel<2, 3>);
-      if (d == 512) return launch(rmsnorm_bwd_bulk_kernel<4, 3>);
-      if (d == 768) return launch(rmsnorm_bwd_bulk_kernel<6, 3>);
-      return launch(rmsnorm_bwd_bulk_kernel<8, 3>);
+      if (d == 256) return launch_rmsnorm_bwd_bulk<2>(grid_b, smem3, s, dyb, lddy, x, rstd, w, dresid, dx_out, dxb, dw, T, d);
+      if (d == 512) return launch_rmsnorm_bwd_bulk<4>(grid_b, smem3, s, dyb, lddy, x, rstd, w, dresid, dx_out, dxb, dw, T, d);
+      if (d == 768) return launch_rmsnorm_bwd_bulk<6>(grid_b, smem3, s, dyb, lddy, x, rstd, w, dresid, dx_out, dxb, dw, T, d);
+      return launch_rmsnorm_bwd_bulk<8>(grid_b, smem3, s, dyb, lddy, x, rstd, w, dresid, dx_out, dxb, dw, T, d);
     }
   }
   const int grid = grid_for_rows(T, 4, 12);

@@ -14,10 +14,15 @@
 //   wgrad    dW = dy^T x : A = dy [T,out] MN-major, B = x [T,in]   MN-major      (K = T rows)
 // so no transposed copies of weights or activations are ever made.
 //
-// L2 -> SM bandwidth is the limiter of a 128x256x64 tile (48 KB per k-block per CTA ~ the measured ~10 TB/s LTS cap
-// at ~1.05 PFLOP/s), so CTAs run as clusters of two along M (CL = 2): both need the same B tile, each CTA fetches
-// half of it with TMA .multicast::cluster into both CTAs' smem (32 KB of L2 reads per k-block per CTA instead of 48),
-// and smem slots are released with a multicast tcgen05.commit that arrives on both CTAs' empty barriers.
+// CTA pairs (PAIR = true, the default for problems with >= 2 m-blocks): the two CTAs of a cluster — the two SMs of a
+// TPC — execute ONE tcgen05.mma.cta_group::2 of shape 256 x BN x 16 per step.  Each CTA stages its own 128 rows of A and
+// only HALF of the B tile's rows (16 + 16 KB per stage instead of 16 + 32 KB), all TMA bytes complete on the leader's
+// full barrier, the leader's elected thread issues every MMA, a multicast tcgen05.commit releases the smem slot in both
+// CTAs and hands each CTA its own 128 x BN accumulator, and the peer's epilogue warps arrive remotely on the leader's
+// accumulator-empty barrier.  Halving the B bytes per FLOP (L2 -> SM and smem -> tensor core) is worth +5..9 % on every
+// shape of the training step.  Two older modes remain for single-m-block problems and A/B profiling (GGPT_GEMM_MODE):
+// a single CTA per tile, and a cluster of two CTAs along M that each fetch half of the shared B tile with TMA
+// .multicast::cluster (32 KB of L2 reads per k-block per CTA instead of 48) and release slots with a multicast commit.
 //
 // Replaces (reference, all via torch/cuBLAS): q/k/v/o_proj HF modeling_llama.py:262-264,288; gate/up/down_proj
 // HF:182-184; n_token_proj modeling_pretrain.py:89-93; lm_head modeling_pretrain.py:218; and their autograd.

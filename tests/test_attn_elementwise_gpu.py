@@ -120,7 +120,7 @@ def test_embed_fwd_bwd():
     assert (dgate - g3.grad).abs().max().item() <= 2e-4 * g3.grad.abs().max().item()
 
 
-@pytest.mark.parametrize("T,d", [(1000, 768), (300, 64), (200, 128), (100, 1024)])
+@pytest.mark.parametrize("T,d", [(1000, 768), (300, 64), (200, 128), (100, 1024), (1500, 256), (77, 512), (5, 768)])
 def test_rmsnorm_fwd_bwd(T, d):
     from graphgpt_b200 import ops
     g = torch.Generator().manual_seed(d)
