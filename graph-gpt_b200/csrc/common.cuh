@@ -396,6 +396,23 @@ inline DropParams make_drop_params(float p, unsigned long long seed) {
 }
 #ifdef __CUDACC__
 
+// Element dropout (nn.Dropout on activations: embed_pdrop / mlp_pdrop, ref: modeling_helpers.py:97-98,
+// utils_graphgpt.py:69-83): keep(e) is a pure function of (seed, e) with e the linear element index of the tensor, so
+// forward and backward regenerate the same mask.  One 32-bit draw per PAIR of adjacent elements (16 bits each).
+__device__ __forceinline__ uint32_t edrop_bits(const DropParams& dp, unsigned long long pair) {
+  const uint32_t x = fmix32(static_cast<uint32_t>(pair) ^ dp.seed_lo);
+  return fmix32(x ^ dp.seed_hi ^ (static_cast<uint32_t>(pair >> 32) * 0x9E3779B1u));
+}
+// keep/(1-p) scales of elements 2*pair and 2*pair+1
+__device__ __forceinline__ float2 edrop_scale2(const DropParams& dp, unsigned long long pair) {
+  const uint32_t bits = edrop_bits(dp, pair);
+  return make_float2(drop_keep_even(bits, dp.thresh) ? dp.inv_keep : 0.f, drop_keep_odd(bits, dp.thresh) ? dp.inv_keep : 0.f);
+}
+__device__ __forceinline__ float edrop_scale1(const DropParams& dp, unsigned long long e) {
+  const float2 s = edrop_scale2(dp, e >> 1);
+  return (e & 1ull) ? s.y : s.x;
+}
+
 // erf GELU (transformers ACT2FN["gelu"]) and its derivative from ONE exponential:
 //   Phi(g) = 0.5 (1 + erf(g / sqrt2)),  erf(x) = sign(x) (1 - poly(t) e^{-x^2}),  t = 1 / (1 + 0.3275911 |x|)
 //   (Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7 — far below the bf16 rounding of the outputs), and with

@@ -24,7 +24,7 @@ static inline int grid_for_rows(long long rows, int rows_per_block, int max_wave
 // =============================================================================================
 __global__ void embed_fwd_kernel(const long long* __restrict__ ids, const float* __restrict__ table,
                                  const float* __restrict__ gate, float* __restrict__ out, long long T, int F, int d,
-                                 int V, int long_scale, int* __restrict__ err) {
+                                 int V, int long_scale, int* __restrict__ err, DropParams dp) {
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   for (long long t = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); t < T;
@@ -41,6 +41,11 @@ __global__ void embed_fwd_kernel(const long long* __restrict__ ids, const float*
         }
         if (c == lane * 4) nnz += (id != 0);
         float4 e = *reinterpret_cast<const float4*>(table + id * d + c);
+        if (dp.thresh != 0u) {  // embed_dropout acts on the gathered [T,F,d] rows before aggregation (modeling_helpers.py:97-98)
+          const unsigned long long pair = (static_cast<unsigned long long>(t * F + f) * d + c) >> 1;
+          const float2 s01 = edrop_scale2(dp, pair), s23 = edrop_scale2(dp, pair + 1);
+          e.x *= s01.x; e.y *= s01.y; e.z *= s23.x; e.w *= s23.y;
+        }
         if (gate != nullptr) {
           const float4 g = *reinterpret_cast<const float4*>(gate + static_cast<long long>(f) * d + c);
           e.x *= g.x; e.y *= g.y; e.z *= g.z; e.w *= g.w;
@@ -60,7 +65,7 @@ __global__ void embed_fwd_kernel(const long long* __restrict__ ids, const float*
 __global__ void embed_bwd_kernel(const long long* __restrict__ ids, const float* __restrict__ dx,
                                  const float* __restrict__ table, const float* __restrict__ gate,
                                  float* __restrict__ dtable, float* __restrict__ dgate, long long T, int F, int d, int V,
-                                 int padding_idx, int long_scale) {
+                                 int padding_idx, int long_scale, DropParams dp) {
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   for (long long t = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); t < T;
@@ -79,14 +84,21 @@ __global__ void embed_bwd_kernel(const long long* __restrict__ ids, const float*
         long long id = idrow[f];
         if (id < 0 || id >= V) continue;
         float4 v = g;
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (dp.thresh != 0u) {
+          const unsigned long long pair = (static_cast<unsigned long long>(t * F + f) * d + c) >> 1;
+          const float2 s01 = edrop_scale2(dp, pair), s23 = edrop_scale2(dp, pair + 1);
+          sc = make_float4(s01.x, s01.y, s23.x, s23.y);
+        }
         if (gate != nullptr) {
           const float4 gt = *reinterpret_cast<const float4*>(gate + static_cast<long long>(f) * d + c);
           const float4 e = *reinterpret_cast<const float4*>(table + id * d + c);
           float* dg = dgate + static_cast<long long>(f) * d + c;
-          atomicAdd(dg + 0, e.x * g.x); atomicAdd(dg + 1, e.y * g.y);
-          atomicAdd(dg + 2, e.z * g.z); atomicAdd(dg + 3, e.w * g.w);
+          atomicAdd(dg + 0, e.x * sc.x * g.x); atomicAdd(dg + 1, e.y * sc.y * g.y);
+          atomicAdd(dg + 2, e.z * sc.z * g.z); atomicAdd(dg + 3, e.w * sc.w * g.w);
           v.x *= gt.x; v.y *= gt.y; v.z *= gt.z; v.w *= gt.w;
         }
+        v.x *= sc.x; v.y *= sc.y; v.z *= sc.z; v.w *= sc.w;
         if (id == padding_idx) continue;  // nn.Embedding(padding_idx): row never receives gradient (HF:361)
         float* dst = dtable + id * d + c;
         atomicAdd(dst + 0, v.x); atomicAdd(dst + 1, v.y); atomicAdd(dst + 2, v.z); atomicAdd(dst + 3, v.w);
@@ -811,20 +823,23 @@ using namespace ggpt;
 extern "C" {
 
 int ggpt_embed_fwd(const long long* ids, const float* table, const float* gate, float* out, long long T, int F, int d,
-                   int V, int long_scale, int* err_flag, void* stream) {
+                   int V, int long_scale, int* err_flag, float drop_p, unsigned long long drop_seed, void* stream) {
   GGPT_REQUIRE(ids && table && out, "embed_fwd: null pointer");
   GGPT_REQUIRE(T > 0 && F > 0 && d > 0 && d % 4 == 0, "embed_fwd: bad sizes T=%lld F=%d d=%d", T, F, d);
-  embed_fwd_kernel<<<grid_for_rows(T, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(ids, table, gate, out, T, F, d,
-                                                                                       V, long_scale, err_flag);
+  GGPT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "embed_fwd: dropout p=%f outside [0,1)", drop_p);
+  embed_fwd_kernel<<<grid_for_rows(T, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      ids, table, gate, out, T, F, d, V, long_scale, err_flag, make_drop_params(drop_p, drop_seed));
   return check_launch("embed_fwd_kernel");
 }
 
 int ggpt_embed_bwd(const long long* ids, const float* dx, const float* table, const float* gate, float* dtable,
-                   float* dgate, long long T, int F, int d, int V, int padding_idx, int long_scale, void* stream) {
+                   float* dgate, long long T, int F, int d, int V, int padding_idx, int long_scale, float drop_p,
+                   unsigned long long drop_seed, void* stream) {
   GGPT_REQUIRE(ids && dx && dtable, "embed_bwd: null pointer");
+  GGPT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "embed_bwd: dropout p=%f outside [0,1)", drop_p);
   GGPT_REQUIRE(gate == nullptr || (table && dgate), "embed_bwd: gated aggregation needs table and dgate");
   embed_bwd_kernel<<<grid_for_rows(T, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      ids, dx, table, gate, dtable, dgate, T, F, d, V, padding_idx, long_scale);
+      ids, dx, table, gate, dtable, dgate, T, F, d, V, padding_idx, long_scale, make_drop_params(drop_p, drop_seed));
   return check_launch("embed_bwd_kernel");
 }
 

@@ -1,0 +1,202 @@
+// Side branches of the GraphGPT hot path that the headline configs leave off but the reference supports:
+//   * raw-embedding input branch (config.embed_dim > 0): mask-token swap + RMSNorm over the E raw features, feeding the
+//     embed_proj GEMM (ref: modeling_pretrain.py:119-150, modeling_helpers.py:127-139)
+//   * element dropout on activations (config.mlp_pdrop / embed_pdrop; ref: utils_graphgpt.py:69-83)
+// All HBM-bound, one pass, warp-per-row or 16-byte grid-stride.
+#include "common.cuh"
+#include "../../include/ggpt_b200.h"
+
+namespace ggpt {
+
+static inline int grid_cap(long long blocks, int waves) {
+  const long long cap = static_cast<long long>(num_sms()) * waves;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+// =============================================================================================
+// Raw-embedding branch, forward.  Row t of the result is RMSNorm_E(src_t; w) in bf16 with
+//   src_t = keep_t ? raw[t,:] : mask_tok[:],   keep_t = any_{f < fchk} labels[t*ldl + f] == -100   (labels NULL: keep)
+// i.e. the reference's `embed_mask * raw + (~embed_mask) * emb_mask_token` followed by embed_layernorm.
+// One warp per row; E % 4 == 0.
+// =============================================================================================
+__global__ void raw_embed_norm_fwd_kernel(const float* __restrict__ raw, const long long* __restrict__ labels,
+                                          long long ldl, int fchk, const float* __restrict__ mask_tok,
+                                          const float* __restrict__ w, __nv_bfloat16* __restrict__ h, long long ldh,
+                                          float* __restrict__ rstd_out, unsigned char* __restrict__ keep_out, long long T,
+                                          int E, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (long long t = static_cast<long long>(blockIdx.x) * wpb + (threadIdx.x >> 5); t < T;
+       t += static_cast<long long>(gridDim.x) * wpb) {
+    bool keep = true;
+    if (labels != nullptr) {
+      bool any = false;
+      for (int f = lane; f < fchk; f += 32) any |= (labels[t * ldl + f] == -100);
+      keep = __any_sync(0xffffffffu, any);
+    }
+    const float* src = keep ? raw + t * E : mask_tok;
+    float ss = 0.f;
+    for (int c = lane * 4; c < E; c += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(src + c);
+      ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    ss = warp_sum(ss);
+    const float rstd = rsqrtf(ss / static_cast<float>(E) + eps);
+    if (lane == 0) {
+      if (rstd_out != nullptr) rstd_out[t] = rstd;
+      if (keep_out != nullptr) keep_out[t] = keep ? 1 : 0;
+    }
+    __nv_bfloat16* hr = h + t * ldh;
+    for (int c = lane * 4; c < E; c += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(src + c);
+      const float4 ww = *reinterpret_cast<const float4*>(w + c);
+      uint2 o;
+      o.x = pack_bf16(ww.x * (v.x * rstd), ww.y * (v.y * rstd));
+      o.y = pack_bf16(ww.z * (v.z * rstd), ww.w * (v.w * rstd));
+      *reinterpret_cast<uint2*>(hr + c) = o;
+    }
+  }
+}
+
+// Backward of the above w.r.t. the parameters only (the raw features are data): dw += sum_t dh * xhat, and for the rows
+// that took the mask token, dmask_tok += rstd * (g - xhat * mean(g * xhat)) with g = dh * w.  Block-level accumulation
+// in shared memory (2 * E floats), one global atomic per column per block.
+__global__ void raw_embed_norm_bwd_kernel(const __nv_bfloat16* __restrict__ dh, long long lddh,
+                                          const float* __restrict__ raw, const unsigned char* __restrict__ keep_in,
+                                          const float* __restrict__ mask_tok, const float* __restrict__ rstd_in,
+                                          const float* __restrict__ w, float* __restrict__ dw,
+                                          float* __restrict__ dmask_tok, long long T, int E) {
+  extern __shared__ float acc[];   // [0,E): dw partial, [E,2E): dmask partial
+  for (int i = threadIdx.x; i < 2 * E; i += blockDim.x) acc[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (long long t = static_cast<long long>(blockIdx.x) * wpb + (threadIdx.x >> 5); t < T;
+       t += static_cast<long long>(gridDim.x) * wpb) {
+    const bool keep = keep_in == nullptr || keep_in[t] != 0;
+    const float* src = keep ? raw + t * E : mask_tok;
+    const float rstd = rstd_in[t];
+    const __nv_bfloat16* dr = dh + t * lddh;
+    float dot = 0.f;
+    for (int c = lane * 4; c < E; c += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(src + c);
+      const float4 ww = *reinterpret_cast<const float4*>(w + c);
+      const uint2 dv = *reinterpret_cast<const uint2*>(dr + c);
+      const float2 d01 = unpack_bf16(dv.x), d23 = unpack_bf16(dv.y);
+      const float x0 = v.x * rstd, x1 = v.y * rstd, x2 = v.z * rstd, x3 = v.w * rstd;
+      atomicAdd(acc + c + 0, d01.x * x0); atomicAdd(acc + c + 1, d01.y * x1);
+      atomicAdd(acc + c + 2, d23.x * x2); atomicAdd(acc + c + 3, d23.y * x3);
+      dot += d01.x * ww.x * x0 + d01.y * ww.y * x1 + d23.x * ww.z * x2 + d23.y * ww.w * x3;
+    }
+    if (keep || dmask_tok == nullptr) continue;      // warp-uniform
+    dot = warp_sum(dot) / static_cast<float>(E);
+    for (int c = lane * 4; c < E; c += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(src + c);
+      const float4 ww = *reinterpret_cast<const float4*>(w + c);
+      const uint2 dv = *reinterpret_cast<const uint2*>(dr + c);
+      const float2 d01 = unpack_bf16(dv.x), d23 = unpack_bf16(dv.y);
+      atomicAdd(acc + E + c + 0, rstd * (d01.x * ww.x - v.x * rstd * dot));
+      atomicAdd(acc + E + c + 1, rstd * (d01.y * ww.y - v.y * rstd * dot));
+      atomicAdd(acc + E + c + 2, rstd * (d23.x * ww.z - v.z * rstd * dot));
+      atomicAdd(acc + E + c + 3, rstd * (d23.y * ww.w - v.w * rstd * dot));
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < E; i += blockDim.x) {
+    atomicAdd(dw + i, acc[i]);
+    if (dmask_tok != nullptr) atomicAdd(dmask_tok + i, acc[E + i]);
+  }
+}
+
+// =============================================================================================
+// Element dropout.  x[e] *= keep(e) / (1 - p) in place on a bf16 tensor viewed as a flat array of n elements;
+// scale_f32 writes the keep/(1-p) factors themselves (tests and tooling read the mask through it).
+// =============================================================================================
+__global__ void dropout_bf16_kernel(__nv_bfloat16* __restrict__ x, long long n, DropParams dp) {
+  const long long nvec = n >> 3;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    uint4 v = *reinterpret_cast<uint4*>(x + i * 8);
+    uint32_t* q = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 s = edrop_scale2(dp, static_cast<unsigned long long>(i) * 4 + k);
+      const float2 a = unpack_bf16(q[k]);
+      q[k] = pack_bf16(a.x * s.x, a.y * s.y);
+    }
+    *reinterpret_cast<uint4*>(x + i * 8) = v;
+  }
+  if (blockIdx.x == 0) {
+    for (long long e = nvec * 8 + threadIdx.x; e < n; e += blockDim.x)
+      x[e] = __float2bfloat16_rn(__bfloat162float(x[e]) * edrop_scale1(dp, static_cast<unsigned long long>(e)));
+  }
+}
+
+__global__ void dropout_scale_f32_kernel(float* __restrict__ out, long long n, DropParams dp) {
+  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < n;
+       e += static_cast<long long>(gridDim.x) * blockDim.x)
+    out[e] = dp.thresh != 0u ? edrop_scale1(dp, static_cast<unsigned long long>(e)) : 1.0f;
+}
+
+}  // namespace ggpt
+
+using namespace ggpt;
+
+extern "C" {
+
+int ggpt_raw_embed_norm_fwd(const float* raw, const long long* labels, long long ldl, int fchk, const float* mask_tok,
+                            const float* w, void* h, long long ldh, float* rstd, unsigned char* keep, long long T, int E,
+                            float eps, void* stream) {
+  GGPT_REQUIRE(raw && w && h, "raw_embed_norm_fwd: null pointer");
+  GGPT_REQUIRE(labels == nullptr || (mask_tok != nullptr && fchk > 0 && ldl >= fchk),
+               "raw_embed_norm_fwd: labels need mask_tok and 0 < fchk <= ldl");
+  GGPT_REQUIRE(T > 0 && E > 0 && E % 4 == 0 && ldh % 4 == 0, "raw_embed_norm_fwd: bad sizes T=%lld E=%d ldh=%lld", T, E, ldh);
+  raw_embed_norm_fwd_kernel<<<grid_cap((T + 7) / 8, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      raw, labels, ldl, fchk, mask_tok, w, static_cast<__nv_bfloat16*>(h), ldh, rstd, keep, T, E, eps);
+  return check_launch("raw_embed_norm_fwd_kernel");
+}
+
+int ggpt_raw_embed_norm_bwd(const void* dh, long long lddh, const float* raw, const unsigned char* keep,
+                            const float* mask_tok, const float* rstd, const float* w, float* dw, float* dmask_tok,
+                            long long T, int E, void* stream) {
+  GGPT_REQUIRE(dh && raw && rstd && w && dw, "raw_embed_norm_bwd: null pointer");
+  GGPT_REQUIRE(keep == nullptr || mask_tok != nullptr, "raw_embed_norm_bwd: keep flags need mask_tok");
+  GGPT_REQUIRE(T > 0 && E > 0 && E % 4 == 0 && lddh % 4 == 0 && E <= 8192, "raw_embed_norm_bwd: bad sizes T=%lld E=%d", T, E);
+  const size_t smem = 2 * static_cast<size_t>(E) * sizeof(float);
+  if (smem > 48 * 1024) {
+    static bool raised = false;
+    if (!raised) {
+      cudaError_t e = cudaFuncSetAttribute(raw_embed_norm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+      if (e != cudaSuccess) {
+        set_error("raw_embed_norm_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return -2;
+      }
+      raised = true;
+    }
+  }
+  raw_embed_norm_bwd_kernel<<<grid_cap((T + 7) / 8, 2), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dh), lddh, raw, keep, mask_tok, rstd, w, dw, dmask_tok, T, E);
+  return check_launch("raw_embed_norm_bwd_kernel");
+}
+
+int ggpt_dropout_bf16(void* x, long long n, float p, unsigned long long seed, void* stream) {
+  GGPT_REQUIRE(x != nullptr && n > 0, "dropout_bf16: null pointer / empty tensor");
+  GGPT_REQUIRE(p >= 0.f && p < 1.f, "dropout_bf16: p=%f outside [0,1)", p);
+  GGPT_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "dropout_bf16: x must be 16-byte aligned");
+  if (p == 0.f) return 0;
+  dropout_bf16_kernel<<<grid_cap(((n >> 3) + 255) / 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<__nv_bfloat16*>(x), n, make_drop_params(p, seed));
+  return check_launch("dropout_bf16_kernel");
+}
+
+int ggpt_dropout_scale_f32(float* out, long long n, float p, unsigned long long seed, void* stream) {
+  GGPT_REQUIRE(out != nullptr && n > 0, "dropout_scale_f32: null pointer / empty tensor");
+  GGPT_REQUIRE(p >= 0.f && p < 1.f, "dropout_scale_f32: p=%f outside [0,1)", p);
+  dropout_scale_f32_kernel<<<grid_cap((n + 255) / 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      out, n, make_drop_params(p, seed));
+  return check_launch("dropout_scale_f32_kernel");
+}
+
+}  // extern "C"

@@ -24,6 +24,22 @@ def _align(n, a=128):
     return (n + a - 1) // a * a
 
 
+_M64 = (1 << 64) - 1
+
+
+def mix_seed(base, k):
+    """splitmix64 of (base + k): well-separated 63-bit seeds for the per-forward dropout streams (attention layer i,
+    GeGLU output / MLP output of layer i, embedding, raw embedding), so that no two streams are index-shifted copies."""
+    z = (base + 0x9E3779B97F4A7C15 * (k + 1)) & _M64
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M64
+    return (z ^ (z >> 31)) >> 1
+
+
+# stream ids of mix_seed for one forward pass (attention dropout keeps its historical `seed + layer` numbering)
+_SEED_ACT, _SEED_MLP, _SEED_EMBED, _SEED_RAW = 0x1000, 0x2000, 0x3000, 0x3001
+
+
 class FlatParams:
     """Lays every parameter of `module` out in one flat fp32 buffer (each segment 128-element aligned so bf16
     views stay 16-byte aligned for TMA) and keeps `param.data` / `param.grad` aliased to it."""
@@ -195,8 +211,11 @@ class HotPath:
         return p
 
     # ------------------------------------------------------------------ backbone
-    def backbone_forward(self, ids2d, N, S, attention_mask, position_ids, stash, droppath_scales=None, attn_dropout=0.0):
-        """ids2d int64 [T,F].  Returns final-norm hidden states bf16 [T,d]; fills `stash` (a dict) when not None."""
+    def backbone_forward(self, ids2d, N, S, attention_mask, position_ids, stash, droppath_scales=None, attn_dropout=0.0,
+                         raw=None, embed_pdrop=0.0, mlp_pdrop=0.0):
+        """ids2d int64 [T,F].  Returns final-norm hidden states bf16 [T,d]; fills `stash` (a dict) when not None.
+        raw = (raw_embeds f32 [T,E], labels int64 [T,F] | None, fchk) feeds the raw-embedding branch (embed_dim > 0);
+        embed_pdrop / mlp_pdrop are the training-time element dropouts (0 in eval)."""
         fp = self.flat
         cfg = self.cfg
         dev = ids2d.device
@@ -204,21 +223,40 @@ class HotPath:
         gate = fp.w("stacked_feat_agg.weight") if "stacked_feat_agg.weight" in fp.offsets else None
         long_scale = getattr(cfg, "stack_method", None) == "long" and ids2d.shape[1] > 1
         err = torch.zeros((1,), device=dev, dtype=torch.int32)
-        x = ops.embed_fwd(ids2d, fp.w("model.embed_tokens.weight"), gate, long_scale, err)
+        # dropout (training only): one 62-bit seed per forward drawn from torch's CPU generator (so torch.manual_seed
+        # controls it).  Attention (HF:217): layer i uses seed + i; the element dropouts use mix_seed streams.
+        # Every mask is a pure function of (seed, index), regenerated by the backward pass — nothing is stored.
+        any_drop = attn_dropout > 0 or embed_pdrop > 0 or mlp_pdrop > 0
+        drop_seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if any_drop else 0
+        x = ops.embed_fwd(ids2d, fp.w("model.embed_tokens.weight"), gate, long_scale, err, drop_p=embed_pdrop,
+                          drop_seed=mix_seed(drop_seed, _SEED_EMBED))
         pos, cos, sin = self._rope_inputs(position_ids, N, S, dev)
         mask = ops.attn_mask_build(attention_mask, N, S, cfg.causal_attention, dev)
         keep = stash is not None
-        # attention dropout (HF:217, config.attention_dropout, training only): one 64-bit seed per forward drawn from
-        # torch's CPU generator (so torch.manual_seed controls it); layer i uses seed + i, backward reuses it
-        drop_seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if attn_dropout > 0 else 0
         if keep:
             stash.update(ids=ids2d, N=N, S=S, mask=mask, pos=pos, cos=cos, sin=sin, layers=[], err=err,
-                         long_scale=long_scale, attn_dropout=attn_dropout, drop_seed=drop_seed)
+                         long_scale=long_scale, attn_dropout=attn_dropout, drop_seed=drop_seed,
+                         embed_pdrop=embed_pdrop, mlp_pdrop=mlp_pdrop, raw=None)
         # Layer i:  h1 = norm(x) -> qkv(+RoPE) -> attention -> y1 = o_proj -> [x2 = x + y1 ; h2 = norm(x2)] (one fused
         # pass) -> gate|up + GeGLU -> y2 = down_proj -> [x3 = x2 + y2 ; h1' = next layer's input norm / final norm].
         # The residual adds live in the norm kernels: a GEMM epilogue doing fp32 read-modify-write of the residual
         # stream is latency-bound (measured 14 % tensor-pipe on o_proj), a streaming add+norm pass is not.
-        h1, rstd1 = ops.rmsnorm_fwd(x, fp.w("model.layers.0.input_layernorm.weight"), self.eps, want_rstd=keep)
+        w_in0 = fp.w("model.layers.0.input_layernorm.weight")
+        if raw is not None:
+            # raw-embedding branch (modeling_pretrain.py:119-150 / modeling_helpers.py:127-139): mask-token swap + RMSNorm
+            # over E in one kernel, embed_proj on the tensor cores, and the sum with the token embeddings rides in the
+            # add+norm pass that produces layer 0's input norm
+            raw2d, rlabels, fchk = raw
+            mask_tok = fp.w("emb_mask_token") if rlabels is not None else None
+            hr, rstd_r, keep_r = ops.raw_embed_norm_fwd(raw2d, fp.w("embed_layernorm.weight"), self.eps, labels=rlabels,
+                                                        fchk=fchk, mask_tok=mask_tok, want_stash=keep)
+            ops.dropout_(hr, embed_pdrop, mix_seed(drop_seed, _SEED_RAW))              # raw_embed_dropout
+            yr = ops.gemm(hr, fp.wb("embed_proj.weight"))
+            x, h1, rstd1 = ops.add_rmsnorm_fwd(x, yr, w_in0, self.eps, want_rstd=keep)
+            if keep:
+                stash["raw"] = dict(raw=raw2d, hr=hr, rstd=rstd_r, keep=keep_r, mask_tok=mask_tok)
+        else:
+            h1, rstd1 = ops.rmsnorm_fwd(x, w_in0, self.eps, want_rstd=keep)
         for i in range(self.L):
             p = f"model.layers.{i}."
             rs = None if droppath_scales is None else droppath_scales[i]
@@ -229,7 +267,9 @@ class HotPath:
             x2, h2, rstd2 = ops.add_rmsnorm_fwd(x, y1, fp.w(p + "post_attention_layernorm.weight"), self.eps,
                                                 colscale=lam1, rowscale=rs, want_rstd=keep)
             gu, act = ops.gemm_geglu(h2, self._wgu(i), want_gu=keep)
+            ops.dropout_(act, mlp_pdrop, mix_seed(drop_seed, _SEED_ACT + i))          # mlp_act_dropout, utils_graphgpt.py:80
             y2 = ops.gemm(act, fp.wb(p + "mlp.down_proj.weight"))
+            ops.dropout_(y2, mlp_pdrop, mix_seed(drop_seed, _SEED_MLP + i))           # mlp_dropout, utils_graphgpt.py:81
             lam2 = fp.w(p + "lambda_2") if self.layer_scale else None
             next_w = fp.w(f"model.layers.{i + 1}.input_layernorm.weight") if i + 1 < self.L else fp.w("model.norm.weight")
             x3, h_next, rstd_next = ops.add_rmsnorm_fwd(x2, y2, next_w, self.eps, colscale=lam2, rowscale=rs,
@@ -282,9 +322,12 @@ class HotPath:
                 dyb = self._scaled_copy(dx, fp.w(p + "lambda_2") if self.layer_scale else None, st["rs"])
                 if self.layer_scale:
                     self._lambda_grad(fp.g(p + "lambda_2"), dx, st["x3"], st["x2"], fp.w(p + "lambda_2"))
+            mlp_p, seed = stash["mlp_pdrop"], stash["drop_seed"]
+            ops.dropout_(dyb, mlp_p, mix_seed(seed, _SEED_MLP + i))      # in place: dyb is this block's private bf16 copy
             # (ops.gemm_dgeglu fuses the next two calls, but its epilogue is slower than the separate HBM-bound kernel:
             #  measured 0.97 ms vs 0.29 + 0.45 ms per layer on B200, profiles/r1_bench_packed_v8_fused_dgeglu.json)
             dact = ops.gemm(dyb, fp.wb(p + "mlp.down_proj.weight"), b_mn_major=True)
+            ops.dropout_(dact, mlp_p, mix_seed(seed, _SEED_ACT + i))
             dgu = ops.geglu_bwd(dact, st["gu"])
             ops.gemm(dyb, st["act"], out=fp.g(p + "mlp.down_proj.weight"), **wgrad)
             ops.gemm(dgu, st["h2"], out=self._ggu(i), **wgrad)
@@ -312,7 +355,18 @@ class HotPath:
         gate = fp.w("stacked_feat_agg.weight") if "stacked_feat_agg.weight" in fp.offsets else None
         emb_p = dict(self.flat.order)["model.embed_tokens.weight"]
         pad = self.cfg.pad_token_id if self.cfg.pad_token_id is not None else -1
-        if emb_p.requires_grad and gate is None and not stash["long_scale"] and self.V <= 4096 and stash["ids"].shape[1] <= 32:
+        embed_p, seed = stash["embed_pdrop"], stash["drop_seed"]
+        rw = stash["raw"]
+        if rw is not None:
+            # x0 = token-embedding sum + embed_proj(hr): dxb is the gradient of both summands
+            ops.gemm(dxb, rw["hr"], out=fp.g("embed_proj.weight"), **wgrad)
+            dhr = ops.gemm(dxb, fp.wb("embed_proj.weight"), b_mn_major=True)
+            ops.dropout_(dhr, embed_p, mix_seed(seed, _SEED_RAW))
+            ops.raw_embed_norm_bwd(dhr, rw["raw"], rw["keep"], rw["mask_tok"], rw["rstd"], fp.w("embed_layernorm.weight"),
+                                   fp.g("embed_layernorm.weight"),
+                                   fp.g("emb_mask_token") if rw["mask_tok"] is not None else None)
+        if (emb_p.requires_grad and gate is None and not stash["long_scale"] and self.V <= 4096
+                and stash["ids"].shape[1] <= 32 and embed_p == 0):
             # small vocabulary: dE = C^T dX on the tensor cores (C = per-token id counts) instead of contended atomics
             cnt = ops.embed_count(stash["ids"], self.V, pad)
             ops.gemm(cnt, dxb, out=fp.g("model.embed_tokens.weight"), **wgrad)
@@ -321,10 +375,10 @@ class HotPath:
                           fp.g("model.embed_tokens.weight"),
                           fp.g("stacked_feat_agg.weight") if gate is not None else None,
                           padding_idx=self.cfg.pad_token_id if self.cfg.pad_token_id is not None else -1,
-                          long_scale=stash["long_scale"])
+                          long_scale=stash["long_scale"], drop_p=embed_p, drop_seed=mix_seed(seed, _SEED_EMBED))
         if self.grad_ready_hook:
-            self.grad_ready_hook(self.flat.order[0][0],
-                                 "model.embed_tokens.weight" if gate is None else "stacked_feat_agg.weight")
+            names = [n for n, _ in self.flat.order]
+            self.grad_ready_hook(names[0], names[names.index("model.layers.0.self_attn.q_proj.weight") - 1])
 
     # LayerScale / DropPath are fine-tuning-only options (ppa: lsi=1, path_dropout=0.2); their few elementwise
     # gradient terms are formed with torch ops on device — not on the pre-training hot path.
@@ -351,9 +405,10 @@ class BackboneFn(torch.autograd.Function):
     buffer by backward(); autograd only carries the activation gradient."""
 
     @staticmethod
-    def forward(ctx, hot, ids2d, N, S, attention_mask, position_ids, droppath_scales, attn_dropout, *params):
+    def forward(ctx, hot, ids2d, N, S, attention_mask, position_ids, droppath_scales, attn_dropout, extras, *params):
         stash = {}
-        hf = hot.backbone_forward(ids2d, N, S, attention_mask, position_ids, stash, droppath_scales, attn_dropout)
+        hf = hot.backbone_forward(ids2d, N, S, attention_mask, position_ids, stash, droppath_scales, attn_dropout,
+                                  **extras)
         ctx.hot, ctx.stash = hot, stash
         return hf
 

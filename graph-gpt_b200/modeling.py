@@ -191,12 +191,24 @@ class _GraphGPTBase(nn.Module):
     def __init__(self, config: GraphGPTConfig):
         super().__init__()
         self.config = config
-        if getattr(config, "embed_dim", 0) > 0:
-            raise NotImplementedError("inputs_raw_embeds (embed_dim > 0) is not built yet (SURVEY §8 row a4: not in C1-C5)")
+        if getattr(config, "embed_dim", 0) > 0 and config.embed_dim % 8 != 0:
+            raise NotImplementedError(f"embed_dim={config.embed_dim}: the embed_proj GEMM reads bf16 rows through TMA, which "
+                                      "needs 16-byte row pitches (embed_dim % 8 == 0); zero-pad the raw features")
         if getattr(config, "use_discriminative", False):
             raise NotImplementedError("contrastive head (use_discriminative) is out of scope (SURVEY §2 row 16)")
         self.model = _Backbone(config)
         self._hot = None
+
+    def _init_raw_embed(self, with_mask_token):
+        """Raw-embedding input branch (config.embed_dim > 0): embed_layernorm [E], embed_proj [d,E] and, for
+        pre-training, emb_mask_token [1,1,E]  (modeling_pretrain.py:69-84, modeling_finetune.py:76-86)."""
+        cfg = self.config
+        if cfg.embed_dim <= 0:
+            return
+        self.embed_layernorm = _Weight(cfg.embed_dim)
+        if with_mask_token:
+            self.emb_mask_token = nn.Parameter(torch.empty((1, 1, cfg.embed_dim)).normal_(mean=0.0, std=cfg.initializer_range))
+        self.embed_proj = nn.Linear(cfg.embed_dim, cfg.hidden_size, bias=False)
 
     # ---- init like HF LlamaPreTrainedModel._init_weights: normal(0, initializer_range), padding row zero
     def _init_weights(self):
@@ -217,8 +229,9 @@ class _GraphGPTBase(nn.Module):
         lambdas — q|k|v and gate|up adjacent so the fused GEMMs see one [3d,d] / [2I,d] weight) | final norm | head."""
         named = dict(self.named_parameters())
         order = ["model.embed_tokens.weight"]
-        if "stacked_feat_agg.weight" in named:
-            order.append("stacked_feat_agg.weight")
+        for k in ("stacked_feat_agg.weight", "embed_layernorm.weight", "emb_mask_token", "embed_proj.weight"):
+            if k in named:
+                order.append(k)
         for i in range(self.config.num_hidden_layers):
             p = f"model.layers.{i}."
             order += [p + "self_attn.q_proj.weight", p + "self_attn.k_proj.weight", p + "self_attn.v_proj.weight",
@@ -294,31 +307,44 @@ class _GraphGPTBase(nn.Module):
             out.append(m.repeat_interleave(S).contiguous())
         return out
 
-    def _check_unsupported_dropout(self):
+    def _raw_embed_inputs(self, inputs_raw_embeds, N, S, labels, fchk):
+        """(raw f32 [T,E], labels int64 [T,F] | None, fchk) for HotPath.backbone_forward, or None when embed_dim == 0."""
         cfg = self.config
-        if self.training and (cfg.mlp_pdrop > 0 or cfg.embed_pdrop > 0):
-            if not getattr(self, "_dropout_warned", False):
-                import warnings
-                warnings.warn("graphgpt_b200: mlp_pdrop / embed_pdrop are not applied by the sm_100a kernels yet "
-                              "(attention_dropout and DropPath are); training proceeds without them")
-                self._dropout_warned = True
+        if cfg.embed_dim <= 0:
+            return None
+        if inputs_raw_embeds is None:
+            raise ValueError("config.embed_dim > 0: inputs_raw_embeds [N, S, embed_dim] is required")
+        if inputs_raw_embeds.dim() != 3:
+            raise NotImplementedError("inputs_raw_embeds of shape [N,S,S,E] (edge-embedding sum, modeling_helpers.py:135-136) "
+                                      "is not built; pass [N,S,E]")
+        if tuple(inputs_raw_embeds.shape) != (N, S, cfg.embed_dim):
+            raise RuntimeError(f"inputs_raw_embeds shape {tuple(inputs_raw_embeds.shape)} != {(N, S, cfg.embed_dim)}")
+        raw2d = inputs_raw_embeds.to(device=self.device, dtype=torch.float32).reshape(N * S, cfg.embed_dim).contiguous()
+        lab2d = None
+        if labels is not None:
+            lab2d = labels.to(self.device).reshape(N * S, -1).contiguous()
+        return raw2d, lab2d, fchk
 
-    def _run_backbone(self, input_ids, attention_mask, position_ids):
+    def _run_backbone(self, input_ids, attention_mask, position_ids, raw=None):
         ids2d, in_, N, S = self._prep_ids(input_ids)
         hot = self.hot
         dev = self.device
+        cfg = self.config
         if ids2d.device != dev:
             ids2d = ids2d.to(dev)
         if attention_mask is not None and attention_mask.device != dev:
             attention_mask = attention_mask.to(dev)
-        self._check_unsupported_dropout()
         dps = self._droppath_scales(N, S, dev)
-        attn_drop = float(getattr(self.config, "attention_dropout", 0.0) or 0.0) if self.training else 0.0
+        attn_drop = float(getattr(cfg, "attention_dropout", 0.0) or 0.0) if self.training else 0.0
+        # the reference swaps in the dropout MLP only together with the dropout backbone (modeling_common.py:148-169,
+        # utils_graphgpt.py:91-93): mlp_pdrop > 0 always selects it, so the condition reduces to mlp_pdrop itself
+        extras = dict(raw=raw, embed_pdrop=float(cfg.embed_pdrop) if self.training else 0.0,
+                      mlp_pdrop=float(cfg.mlp_pdrop) if self.training else 0.0)
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             params = [p for _, p in hot.flat.order]
-            hf = BackboneFn.apply(hot, ids2d, N, S, attention_mask, position_ids, dps, attn_drop, *params)
+            hf = BackboneFn.apply(hot, ids2d, N, S, attention_mask, position_ids, dps, attn_drop, extras, *params)
         else:
-            hf = hot.backbone_forward(ids2d, N, S, attention_mask, position_ids, None, dps, attn_drop)
+            hf = hot.backbone_forward(ids2d, N, S, attention_mask, position_ids, None, dps, attn_drop, **extras)
         return hf, in_, N, S
 
 
@@ -333,6 +359,7 @@ class GraphGPTPretrainBase(_GraphGPTBase):
         self.smtp_inside = bool(config.smtp_inside)     # modeling_pretrain.py:62-63
         self.smtp_power = float(config.smtp_power)
         self.stacked_feat_agg = _StackedFeatAgg(config)
+        self._init_raw_embed(with_mask_token=True)
         d = config.hidden_size
         if config.next_n_token > 1:
             self.n_token_proj = nn.Linear(d, d * config.next_n_token, bias=False)
@@ -349,7 +376,16 @@ class GraphGPTPretrainBase(_GraphGPTBase):
         cfg = self.config
         if self.smtp_inside:
             input_ids, labels = self._smtp_inside_inputs(input_ids)
-        hf, in_, N, S = self._run_backbone(input_ids, attention_mask, position_ids)
+        raw = None
+        if cfg.embed_dim > 0:
+            if labels is None:
+                raise ValueError("config.embed_dim > 0 needs labels: the mask-token swap of the raw embeddings is driven by "
+                                 "them (modeling_pretrain.py:134-137)")
+            # rows keep their raw features when ANY of the examined labels is -100 (all F of them; only column 0 under
+            # smtp_inside), modeling_pretrain.py:134-137
+            raw = self._raw_embed_inputs(inputs_raw_embeds, input_ids.shape[0], input_ids.shape[1], labels,
+                                         1 if self.smtp_inside else labels.reshape(labels.shape[0], labels.shape[1], -1).shape[-1])
+        hf, in_, N, S = self._run_backbone(input_ids, attention_mask, position_ids, raw)
         hot = self._hot
         dev = hf.device
         loss = None
@@ -431,6 +467,7 @@ class GraphGPTTaskModel(_GraphGPTBase):
         super().__init__(config)
         if config.stack_method in {"short", "long"}:
             self.stacked_feat_agg = _StackedFeatAgg(config)
+        self._init_raw_embed(with_mask_token=False)
         bias = config.problem_type == "regression"
         self.num_labels = config.num_labels
         if len(config.mlp) > 0:
@@ -447,7 +484,10 @@ class GraphGPTTaskModel(_GraphGPTBase):
         cfg = self.config
         if input_ids is not None and input_ids.dim() == 3:
             input_ids = input_ids[:, :, : cfg.stacked_feat]
-        hf, in_, N, S = self._run_backbone(input_ids, attention_mask, position_ids)
+        raw = None
+        if cfg.embed_dim > 0:
+            raw = self._raw_embed_inputs(inputs_raw_embeds, input_ids.shape[0], input_ids.shape[1], None, 0)
+        hf, in_, N, S = self._run_backbone(input_ids, attention_mask, position_ids, raw)
         dev = hf.device
         hidden = hf.view(N, S, -1)
         if cfg.pad_token_id is None:

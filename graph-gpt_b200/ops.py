@@ -212,25 +212,25 @@ def attn_bwd(dout, qkv, out, lse, mask: AttnMask, H, pos, cos_tab, sin_tab, *, d
 # ------------------------------------------------------------------------------------------------
 # HBM-bound kernels
 # ------------------------------------------------------------------------------------------------
-def embed_fwd(ids, table, gate=None, long_scale=False, err_flag=None):
-    """ids int64 [T,F]; table f32 [V,d] -> x f32 [T,d]."""
+def embed_fwd(ids, table, gate=None, long_scale=False, err_flag=None, *, drop_p=0.0, drop_seed=0):
+    """ids int64 [T,F]; table f32 [V,d] -> x f32 [T,d].  drop_p > 0: embed_dropout on the gathered rows."""
     _check(ids, torch.int64, "embed ids", 2)
     _check(table, F32, "embed table", 2)
     T, F_ = ids.shape
     V, d = table.shape
     out = torch.empty((T, d), device=table.device, dtype=F32)
     lib.ggpt_embed_fwd(ids.data_ptr(), table.data_ptr(), _ptr(gate), out.data_ptr(), T, F_, d, V, int(long_scale),
-                       _ptr(err_flag), _stream())
+                       _ptr(err_flag), float(drop_p), int(drop_seed), _stream())
     return out
 
 
-def embed_bwd(ids, dx, table, gate, dtable, dgate, padding_idx=0, long_scale=False):
+def embed_bwd(ids, dx, table, gate, dtable, dgate, padding_idx=0, long_scale=False, *, drop_p=0.0, drop_seed=0):
     _check(ids, torch.int64, "embed ids", 2)
     _check(dx, F32, "embed dx", 2)
     T, F_ = ids.shape
     V, d = dtable.shape
     lib.ggpt_embed_bwd(ids.data_ptr(), dx.data_ptr(), _ptr(table), _ptr(gate), dtable.data_ptr(), _ptr(dgate), T, F_, d, V,
-                       padding_idx, int(long_scale), _stream())
+                       padding_idx, int(long_scale), float(drop_p), int(drop_seed), _stream())
 
 
 def embed_count(ids, V, padding_idx):
@@ -260,6 +260,55 @@ def smtp_mask_2d(ids, F, mr, u_node, power, *, mask_token=1, label_pad=-100, err
     lib.ggpt_smtp_mask_2d(ids.data_ptr(), Ftot, F + 2, mr.data_ptr(), u_node.data_ptr(), float(power), out.data_ptr(),
                           labels.data_ptr(), N, S, F, int(mask_token), int(label_pad), _ptr(err_flag), _stream())
     return out, labels
+
+
+def raw_embed_norm_fwd(raw, w, eps, *, labels=None, fchk=0, mask_tok=None, want_stash=True):
+    """raw f32 [T,E]; labels int64 [T,F] or None.  Returns (h bf16 [T,E], rstd f32 [T] | None, keep u8 [T] | None):
+    rows whose first `fchk` labels are all labelled take `mask_tok` instead of their raw features, then RMSNorm."""
+    _check(raw, F32, "raw_embed raw", 2)
+    _check(w, F32, "raw_embed w", 1)
+    if not raw.is_contiguous():
+        raise RuntimeError("raw_embed raw: expected a contiguous [T,E] tensor")
+    T, E = raw.shape
+    ldl = 0
+    if labels is not None:
+        _check(labels, torch.int64, "raw_embed labels", 2)
+        if labels.shape[0] != T or mask_tok is None:
+            raise RuntimeError("raw_embed: labels must have T rows and come with mask_tok")
+        _check(mask_tok, F32, "raw_embed mask_tok")
+        ldl = labels.stride(0)
+    h = torch.empty((T, E), device=raw.device, dtype=BF16)
+    rstd = torch.empty((T,), device=raw.device, dtype=F32) if want_stash else None
+    keep = torch.empty((T,), device=raw.device, dtype=torch.uint8) if (want_stash and labels is not None) else None
+    lib.ggpt_raw_embed_norm_fwd(raw.data_ptr(), _ptr(labels), ldl, int(fchk), _ptr(mask_tok), w.data_ptr(), h.data_ptr(), E,
+                                _ptr(rstd), _ptr(keep), T, E, float(eps), _stream())
+    return h, rstd, keep
+
+
+def raw_embed_norm_bwd(dh, raw, keep, mask_tok, rstd, w, dw, dmask_tok):
+    """Accumulates dw [E] (and dmask_tok [E] when given) from dh bf16 [T,E]."""
+    _check(dh, BF16, "raw_embed_bwd dh", 2)
+    _check(raw, F32, "raw_embed_bwd raw", 2)
+    T, E = raw.shape
+    lib.ggpt_raw_embed_norm_bwd(dh.data_ptr(), dh.stride(0), raw.data_ptr(), _ptr(keep), _ptr(mask_tok), rstd.data_ptr(),
+                                w.data_ptr(), dw.data_ptr(), _ptr(dmask_tok), T, E, _stream())
+
+
+def dropout_(x, p, seed):
+    """In-place element dropout on a contiguous bf16 tensor (mask = pure function of (seed, linear index))."""
+    _check(x, BF16, "dropout x")
+    if not x.is_contiguous():
+        raise RuntimeError("dropout: expected a contiguous tensor")
+    if p > 0:
+        lib.ggpt_dropout_bf16(x.data_ptr(), x.numel(), float(p), int(seed), _stream())
+    return x
+
+
+def dropout_scale(n, p, seed, device):
+    """f32 [n] of keep(e)/(1-p): the factors ggpt_dropout_bf16 / ggpt_embed_fwd apply for this (p, seed)."""
+    out = torch.empty((n,), device=device, dtype=F32)
+    lib.ggpt_dropout_scale_f32(out.data_ptr(), n, float(p), int(seed), _stream())
+    return out
 
 
 def rmsnorm_fwd(x, w, eps, *, want_rstd=True):

@@ -118,15 +118,18 @@ int ggpt_attn_bwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int
 /* ---------------------------------------------------------------------------------------------
  * HBM-bound kernels
  * ------------------------------------------------------------------------------------------- */
-/* x[t,:] = sum_f gate[f,:] * table[ids[t,f],:] (gate NULL -> plain sum); long_scale applies the
+/* x[t,:] = sum_f gate[f,:] * drop(table[ids[t,f],:]) (gate NULL -> plain sum); long_scale applies the
  * stack_method=="long" 1/nnz rescale.  err_flag (may be NULL) is set to 1 on an out-of-range id.
- * ref: modeling_helpers.py:89-114, modeling_common.py:127-135. */
+ * drop_p > 0 (training, config.embed_pdrop): element dropout on the gathered [T,F,d] rows before aggregation, mask =
+ * the counter-based one of ggpt_dropout_scale_f32 over the linear index (t*F+f)*d+j.
+ * ref: modeling_helpers.py:89-114 (embed_dropout :97-98), modeling_common.py:127-135. */
 int ggpt_embed_fwd(const long long* ids, const float* table, const float* gate, float* out, long long T, int F, int d,
-                   int V, int long_scale, int* err_flag, void* stream);
+                   int V, int long_scale, int* err_flag, float drop_p, unsigned long long drop_seed, void* stream);
 /* dtable[id,:] += gate[f,:]*dx[t,:] for id != padding_idx (dtable pre-zeroed / accumulating), dgate likewise.
  * ref: autograd of the above; nn.Embedding(padding_idx=0) HF:361. */
 int ggpt_embed_bwd(const long long* ids, const float* dx, const float* table, const float* gate, float* dtable,
-                   float* dgate, long long T, int F, int d, int V, int padding_idx, int long_scale, void* stream);
+                   float* dgate, long long T, int F, int d, int V, int padding_idx, int long_scale, float drop_p,
+                   unsigned long long drop_seed, void* stream);
 
 /* cnt[t, v] (bf16 [T, ldc], fully overwritten) = number of features f with ids[t,f] == v, 0 for v == padding_idx.
  * The embedding gradient is then the wgrad GEMM dE = cnt^T dX (ggpt_gemm_bf16 with both operands MN-major),
@@ -143,6 +146,28 @@ int ggpt_embed_count(const long long* ids, void* cnt, long long ldc, long long T
 int ggpt_smtp_mask_2d(const long long* ids, int Ftot, int node_col, const float* mr, const float* u_node, float power,
                       long long* out_ids, long long* labels, int N, int S, int F, long long mask_token,
                       long long label_pad, int* err_flag, void* stream);
+
+/* Raw-embedding input branch (config.embed_dim = E > 0).  h[t,:] (bf16 [T, ldh]) = RMSNorm_E(src_t; w) with
+ * src_t = keep_t ? raw[t,:] : mask_tok[:], keep_t = any_{f<fchk}(labels[t*ldl+f] == -100); labels NULL (fine-tuning:
+ * no mask-token swap) keeps every row.  rstd[T] / keep[T] (u8) are saved for backward (either may be NULL).  The
+ * result feeds embed_proj (ggpt_gemm_bf16) and is added to the token-embedding sum by ggpt_add_rmsnorm_fwd.
+ * ref: modeling_pretrain.py:119-150 (pre-training: fchk = F, or 1 when smtp_inside), modeling_helpers.py:127-139 (FT). */
+int ggpt_raw_embed_norm_fwd(const float* raw, const long long* labels, long long ldl, int fchk, const float* mask_tok,
+                            const float* w, void* h, long long ldh, float* rstd, unsigned char* keep, long long T, int E,
+                            float eps, void* stream);
+/* Parameter gradients of the above from dh (bf16 [T, lddh] = d loss / d h): dw[E] += sum_t dh*xhat; dmask_tok[E]
+ * (may be NULL) += sum over swapped rows of dRMSNorm(dh).  The raw features are data and receive no gradient. */
+int ggpt_raw_embed_norm_bwd(const void* dh, long long lddh, const float* raw, const unsigned char* keep,
+                            const float* mask_tok, const float* rstd, const float* w, float* dw, float* dmask_tok,
+                            long long T, int E, void* stream);
+
+/* Element dropout on activations, training only (config.mlp_pdrop: GeGLU output and down_proj output; embed_pdrop:
+ * normalised raw embeddings).  x (bf16, n contiguous elements, 16-byte aligned) is scaled in place by keep(e)/(1-p);
+ * keep(e) is a pure function of (seed, e) — the backward pass applies the same call to the incoming gradient.
+ * p is quantised to 1/65536.  ggpt_dropout_scale_f32 writes the factors keep(e)/(1-p) for e in [0, n).
+ * ref: utils_graphgpt.py:69-83 (mlp_act_dropout, mlp_dropout), modeling_pretrain.py:146-147 (raw_embed_dropout). */
+int ggpt_dropout_bf16(void* x, long long n, float p, unsigned long long seed, void* stream);
+int ggpt_dropout_scale_f32(float* out, long long n, float p, unsigned long long seed, void* stream);
 
 /* y = bf16(w * x * rsqrt(mean(x^2)+eps)), rstd[T] saved for backward (may be NULL).   ref: HF:59-64 */
 int ggpt_rmsnorm_fwd(const float* x, const float* w, void* y, long long ldy, float* rstd, long long T, int d, float eps,

@@ -137,8 +137,10 @@ def attention(q, k, v, mask4d, scaling):
     return o.transpose(1, 2).contiguous()
 
 
-def decoder_layer(x, sd, prefix, cfg, cos, sin, mask4d):
-    """HF:313-332 LlamaDecoderLayer.forward (+ LayerScale of utils_graphgpt.py:153-166; dropouts inactive in eval)."""
+def decoder_layer(x, sd, prefix, cfg, cos, sin, mask4d, act_scale=None, mlp_scale=None):
+    """HF:313-332 LlamaDecoderLayer.forward (+ LayerScale of utils_graphgpt.py:153-166).  act_scale / mlp_scale are the
+    training-mode nn.Dropout factors keep/(1-p) of mlp_act_dropout [N,S,I] and mlp_dropout [N,S,d]
+    (utils_graphgpt.py:69-83) supplied by the caller — None = eval mode (identity)."""
     N, S, d = x.shape
     H, hd = cfg.num_attention_heads, cfg.head_dim
     h = rmsnorm(x, sd[prefix + "input_layernorm.weight"], cfg.rms_norm_eps)
@@ -154,7 +156,12 @@ def decoder_layer(x, sd, prefix, cfg, cos, sin, mask4d):
     h = rmsnorm(x, sd[prefix + "post_attention_layernorm.weight"], cfg.rms_norm_eps)
     g = F.linear(h, sd[prefix + "mlp.gate_proj.weight"])
     u = F.linear(h, sd[prefix + "mlp.up_proj.weight"])
-    m = F.linear(F.gelu(g) * u, sd[prefix + "mlp.down_proj.weight"])   # exact erf GELU, HF:182-184
+    act = F.gelu(g) * u                                                # exact erf GELU, HF:182-184
+    if act_scale is not None:
+        act = act * act_scale                                          # utils_graphgpt.py:80
+    m = F.linear(act, sd[prefix + "mlp.down_proj.weight"])
+    if mlp_scale is not None:
+        m = m * mlp_scale                                              # utils_graphgpt.py:81
     if prefix + "lambda_2" in sd:
         m = sd[prefix + "lambda_2"] * m
     return x + m
@@ -168,9 +175,12 @@ def reset_pos_ids(position_ids, cfg):
     return position_ids
 
 
-def stacked_embed(input_ids, sd, cfg):
-    """modeling_helpers.py:89-114 + StackedFeatAggregation.forward modeling_common.py:127-135."""
+def stacked_embed(input_ids, sd, cfg, embed_scale=None):
+    """modeling_helpers.py:89-114 + StackedFeatAggregation.forward modeling_common.py:127-135.  embed_scale: the
+    embed_dropout factors keep/(1-p) on the gathered rows ([N,S,F,d] / [N,S,d]; :97-98), None = eval."""
     emb = sd["model.embed_tokens.weight"][input_ids]
+    if embed_scale is not None:
+        emb = emb * embed_scale
     if input_ids.dim() == 3:
         if cfg.stacked_feat_agg_method == "gated":
             emb = torch.einsum("nsfd,fd->nsd", emb, sd["stacked_feat_agg.weight"])
@@ -185,8 +195,27 @@ def stacked_embed(input_ids, sd, cfg):
     return emb, in_
 
 
-def backbone(inputs_embeds, attention_mask, position_ids, sd, cfg, collect=None):
-    """HF:375-425 LlamaModel.forward over `inputs_embeds`; returns the final-norm hidden states [N,S,d]."""
+def raw_embed_branch(inputs_raw_embeds, sd, cfg, labels=None, smtp_inside=False, raw_scale=None):
+    """Raw-embedding input branch (config.embed_dim > 0).
+    pre-training (labels given): modeling_pretrain.py:130-148 — rows where ANY examined label is -100 keep their raw
+    features, the others take emb_mask_token; then embed_layernorm, raw_embed_dropout, embed_proj.
+    fine-tuning (labels None): modeling_helpers.py:127-139 — embed_layernorm, dropout, embed_proj."""
+    x = inputs_raw_embeds.float()
+    if labels is not None:
+        if smtp_inside:
+            embed_mask = labels[:, :, 0:1] == -100                                       # :134-135
+        else:
+            embed_mask = (labels == -100).sum(dim=-1, keepdim=True).to(torch.bool)       # :136-137
+        x = embed_mask.float() * x + (~embed_mask).float() * sd["emb_mask_token"]        # :139-143
+    x = rmsnorm(x, sd["embed_layernorm.weight"], cfg.rms_norm_eps)
+    if raw_scale is not None:
+        x = x * raw_scale
+    return F.linear(x, sd["embed_proj.weight"])
+
+
+def backbone(inputs_embeds, attention_mask, position_ids, sd, cfg, collect=None, drop=None):
+    """HF:375-425 LlamaModel.forward over `inputs_embeds`; returns the final-norm hidden states [N,S,d].
+    drop: optional {"act": [L x [N,S,I]], "mlp": [L x [N,S,d]]} dropout factors (training mode)."""
     N, S, _ = inputs_embeds.shape
     if position_ids is None:
         position_ids = torch.arange(S)[None, :].expand(N, -1)          # HF:394-397
@@ -194,7 +223,9 @@ def backbone(inputs_embeds, attention_mask, position_ids, sd, cfg, collect=None)
     mask4d = additive_mask(attention_mask, S, cfg.causal_attention)
     x = inputs_embeds
     for i in range(cfg.num_hidden_layers):
-        x = decoder_layer(x, sd, f"model.layers.{i}.", cfg, cos, sin, mask4d)
+        x = decoder_layer(x, sd, f"model.layers.{i}.", cfg, cos, sin, mask4d,
+                          None if drop is None or "act" not in drop else drop["act"][i],
+                          None if drop is None or "mlp" not in drop else drop["mlp"][i])
         if collect is not None:
             collect.append(x)
     return rmsnorm(x, sd["model.norm.weight"], cfg.rms_norm_eps)
@@ -272,14 +303,18 @@ def ce_loss(logits, labels, wgt=None, dlm=False, focal_gamma=0.0):
 
 
 def pretrain_forward(sd, cfg, input_ids, attention_mask=None, labels=None, sample_wgt=None, position_ids=None,
-                     collect=None):
-    """GraphGPTPretrainBase.forward (modeling_pretrain.py:152-266), generative head only, embed_dim == 0.
+                     collect=None, inputs_raw_embeds=None, smtp_inside=False, drop=None):
+    """GraphGPTPretrainBase.forward (modeling_pretrain.py:152-266), generative head only.
+    drop: optional training-mode dropout factors {"embed", "raw", "act", "mlp"} (see the helpers above).
     Returns dict(loss, logits, hidden)."""
     cfg = OracleConfig.from_any(cfg)
-    sd = {k: v.float() for k, v in sd.items()}
+    sd = {k: (v.float() if v.is_floating_point() else v) for k, v in sd.items()}
     position_ids = reset_pos_ids(position_ids, cfg)
-    emb, _ = stacked_embed(input_ids, sd, cfg)
-    hidden = backbone(emb, attention_mask, position_ids, sd, cfg, collect)
+    drop = drop or {}
+    emb, _ = stacked_embed(input_ids, sd, cfg, drop.get("embed"))
+    if inputs_raw_embeds is not None:
+        emb = emb + raw_embed_branch(inputs_raw_embeds, sd, cfg, labels, smtp_inside, drop.get("raw"))   # :149
+    hidden = backbone(emb, attention_mask, position_ids, sd, cfg, collect, drop)
     h, lab, wgt = head_select(hidden, labels, sd, cfg, sample_wgt)
     logits = F.linear(h, sd["lm_head.weight"])                                        # :218
     loss = None
@@ -297,7 +332,8 @@ def pretrain_forward(sd, cfg, input_ids, attention_mask=None, labels=None, sampl
 # ------------------------------------------------------------------------------------------------
 # fine-tuning head
 # ------------------------------------------------------------------------------------------------
-def task_forward(sd, cfg, input_ids, attention_mask=None, position_ids=None, task_labels=None, sample_wgt=None):
+def task_forward(sd, cfg, input_ids, attention_mask=None, position_ids=None, task_labels=None, sample_wgt=None,
+                 inputs_raw_embeds=None):
     """GraphGPTTaskModel.forward (modeling_finetune.py:236-326): score on all positions, pool at the last non-pad
     index (modeling_helpers.py:78-86), CE / MSE / L1 / BCE loss (modeling_finetune.py:167-234)."""
     cfg = OracleConfig.from_any(cfg)
@@ -306,6 +342,8 @@ def task_forward(sd, cfg, input_ids, attention_mask=None, position_ids=None, tas
     if input_ids.dim() == 3:
         input_ids = input_ids[:, :, : cfg.stacked_feat]
     emb, in_ = stacked_embed(input_ids, sd, cfg)
+    if inputs_raw_embeds is not None:
+        emb = emb + raw_embed_branch(inputs_raw_embeds, sd, cfg)                          # modeling_finetune.py:130-134
     hidden = backbone(emb, attention_mask, position_ids, sd, cfg)
     logits = F.linear(hidden, sd["score.weight"], sd.get("score.bias"))
     seq_len = (in_ != cfg.pad_token_id).sum(-1) - 1

@@ -24,6 +24,7 @@ GRAD_KEYS = [
     "model.layers.0.mlp.gate_proj.weight", "model.layers.1.mlp.down_proj.weight",
     "model.layers.1.input_layernorm.weight", "model.norm.weight", "lm_head.weight", "n_token_proj.weight",
     "score.weight", "stacked_feat_agg.weight", "model.layers.0.lambda_1",
+    "embed_proj.weight", "embed_layernorm.weight", "emb_mask_token",
 ]
 
 
@@ -149,6 +150,34 @@ def _ft_ls():
                                  position_ids=t(b["position_ids"]), task_labels=labels)
 
 
+@case("c2_raw_embed_pretrain")
+def _raw_pt():
+    """Raw-embedding input branch in pre-training (embed_dim = 24): mask-token swap on fully labelled rows,
+    embed_layernorm, embed_proj, added to the token-embedding sum (modeling_pretrain.py:119-150)."""
+    cfg = base_cfg(vocab_size=756, hidden_size=64, intermediate_size=256, stacked_feat=13, next_n_token=13, embed_dim=24)
+    b = synth.make_batch(3, 64, layout="unpacked", seed=21)
+    lab = b["labels"].copy()
+    g = np.random.default_rng(5)
+    full = (g.random(lab.shape[:2]) < 0.3) & (b["attention_mask"] == 1)      # some rows with every feature labelled
+    lab[full] = np.where(lab[full] == -100, b["input_ids"][full], lab[full])
+    raw = torch.from_numpy(g.standard_normal(lab.shape[:2] + (24,)).astype(np.float32)) * 1.5
+    return "pretrain", cfg, dict(input_ids=t(b["input_ids"]), attention_mask=t(b["attention_mask"]), labels=t(lab),
+                                 inputs_raw_embeds=raw)
+
+
+@case("c3_raw_embed_ft")
+def _raw_ft():
+    """Raw-embedding input branch in fine-tuning (embed_dim = 16; modeling_finetune.py:118-135)."""
+    cfg = base_cfg(vocab_size=1200, hidden_size=64, intermediate_size=256, stacked_feat=4, next_n_token=4,
+                   num_labels=2, problem_type="single_label_classification", pooling_method="last", embed_dim=16)
+    vocab = synth.VocabLayout(vocab_size=1200, scope=512, n_node_attr=2, n_edge_attr=1)
+    b = synth.make_batch(3, 48, layout="unpacked", task="ntp", vocab=vocab, seed=22)
+    g = np.random.default_rng(6)
+    raw = torch.from_numpy(g.standard_normal(b["input_ids"].shape[:2] + (16,)).astype(np.float32))
+    return "finetune", cfg, dict(input_ids=t(b["input_ids"]), attention_mask=t(b["attention_mask"]),
+                                 task_labels=torch.tensor([1, 0, 0]), inputs_raw_embeds=raw)
+
+
 def _patch_dropout_backbone():
     """transformers 5.5.0's LlamaModel loop expects decoder layers to return a tensor; the reference's dropout
     layer (utils_graphgpt.py:168-173) returns the 4.53-style tuple.  Unwrap it (SURVEY §8c caveat)."""
@@ -214,6 +243,8 @@ def main():
             for n_, p in model.named_parameters():
                 if "layernorm" in n_ or n_.endswith("norm.weight"):
                     p.add_(0.1 * torch.randn_like(p))
+                if n_ == "emb_mask_token":
+                    p.add_(0.5 * torch.randn_like(p))
                 if "lambda_" in n_:
                     p.mul_(1.0 + 0.2 * torch.randn_like(p))
         out = model(**inputs)

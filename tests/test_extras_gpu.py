@@ -1,0 +1,165 @@
+"""GPU parity of the side branches of the hot path: raw-embedding input kernels, element dropout (embed_pdrop /
+mlp_pdrop) and their model-level wiring.  Dropout masks are pure functions of (seed, element index), so the test reads
+the exact factors through ggpt_dropout_scale_f32 and feeds them to the CPU oracle: training-mode parity is checked
+value for value, not statistically (tolerances as in test_model_gpu.py: loss 1e-3, logits 1e-2, gradients 3e-2)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _relf(a, b):
+    return ((a.double().cpu() - b.double().cpu()).norm() / (b.double().cpu().norm() + 1e-30)).item()
+
+
+@pytest.mark.parametrize("p", [0.1, 0.5])
+def test_dropout_factors_and_inplace_kernel(p):
+    from graphgpt_b200 import ops
+    n = 8 * 40000 + 5                       # vector body + scalar tail
+    sc = ops.dropout_scale(n, p, 1234, "cuda")
+    pq = round(p * 65536) / 65536
+    vals = torch.unique(sc)
+    assert vals.numel() == 2 and vals[0].item() == 0.0 and abs(vals[1].item() - 1 / (1 - pq)) < 1e-6
+    keep = (sc > 0).float().mean().item()
+    assert abs(keep - (1 - pq)) < 5 * math.sqrt(pq * (1 - pq) / n)
+    # neighbours (the two halves of one 32-bit draw) and distant elements are uncorrelated
+    k = (sc > 0).float() - (1 - pq)
+    for lag in (1, 2, 3, 8, 1024):
+        c = (k[:-lag] * k[lag:]).mean().item() / (pq * (1 - pq))
+        assert abs(c) < 5 / math.sqrt(n), (lag, c)
+    assert torch.equal(sc, ops.dropout_scale(n, p, 1234, "cuda"))
+    assert not torch.equal(sc, ops.dropout_scale(n, p, 1235, "cuda"))
+    x = torch.randn(n, device="cuda").bfloat16()
+    want = (x.float() * sc).bfloat16()
+    got = ops.dropout_(x.clone(), p, 1234)
+    assert torch.equal(got, want)
+    assert torch.equal(ops.dropout_(x.clone(), 0.0, 1), x)
+
+
+@pytest.mark.parametrize("gated", [False, True])
+def test_embed_dropout_fwd_bwd(gated):
+    from graphgpt_b200 import ops
+    T, F_, d, V, p, seed = 300, 5, 128, 97, 0.25, 99
+    g = torch.Generator(device="cuda").manual_seed(3)
+    ids = torch.randint(0, V, (T, F_), device="cuda", generator=g)
+    table = torch.randn(V, d, device="cuda", generator=g).requires_grad_(True)
+    gate = torch.rand(F_, d, device="cuda", generator=g).requires_grad_(True) if gated else None
+    sc = ops.dropout_scale(T * F_ * d, p, seed, "cuda").view(T, F_, d)
+    e = table[ids] * sc
+    ref = (e * gate[None]).sum(1) if gated else e.sum(1)
+    out = ops.embed_fwd(ids, table.detach(), gate.detach() if gated else None, drop_p=p, drop_seed=seed)
+    assert _relf(out, ref) < 1e-6
+    dx = torch.randn(T, d, device="cuda", generator=g)
+    ref.backward(dx)
+    dtable = torch.zeros(V, d, device="cuda")
+    dgate = torch.zeros(F_, d, device="cuda") if gated else None
+    ops.embed_bwd(ids, dx, table.detach() if gated else None, gate.detach() if gated else None, dtable, dgate,
+                  padding_idx=-1, drop_p=p, drop_seed=seed)
+    assert _relf(dtable, table.grad) < 1e-5
+    if gated:
+        assert _relf(dgate, gate.grad) < 1e-5
+
+
+@pytest.mark.parametrize("E,with_labels", [(24, True), (16, False), (200, True)])
+def test_raw_embed_norm_kernels(E, with_labels):
+    from graphgpt_b200 import ops
+    T, F_, eps = 777, 13, 1e-6
+    g = torch.Generator(device="cuda").manual_seed(5)
+    raw = torch.randn(T, E, device="cuda", generator=g) * 2
+    w = (1 + 0.1 * torch.randn(E, device="cuda", generator=g)).requires_grad_(True)
+    tok = (0.3 * torch.randn(1, 1, E, device="cuda", generator=g)).requires_grad_(True)
+    labels = None
+    if with_labels:
+        labels = torch.randint(0, 50, (T, F_), device="cuda", generator=g)
+        labels[torch.rand(T, F_, device="cuda", generator=g) < 0.15] = -100     # ~12 % of rows fully labelled -> swapped
+        keep_ref = (labels == -100).any(-1, keepdim=True)
+        src = torch.where(keep_ref, raw, tok.view(1, E))
+    else:
+        src = raw
+    rstd_ref = torch.rsqrt(src.pow(2).mean(-1, keepdim=True) + eps)
+    h_ref = w * (src * rstd_ref)
+    h, rstd, keep = ops.raw_embed_norm_fwd(raw, w.detach(), eps, labels=labels, fchk=F_ if with_labels else 0,
+                                           mask_tok=tok.detach() if with_labels else None)
+    assert _relf(h, h_ref) < 4e-3                                              # bf16 output rounding
+    assert _relf(rstd, rstd_ref.view(-1)) < 1e-6
+    if with_labels:
+        assert torch.equal(keep.bool(), keep_ref.view(-1)) and 0 < (~keep.bool()).sum().item() < T
+    dh = torch.randn(T, E, device="cuda", generator=g).bfloat16()
+    h_ref.backward(dh.float())
+    dw = torch.zeros(E, device="cuda")
+    dtok = torch.zeros(1, 1, E, device="cuda") if with_labels else None
+    ops.raw_embed_norm_bwd(dh, raw, keep, tok.detach() if with_labels else None, rstd, w.detach(), dw, dtok)
+    assert _relf(dw, w.grad) < 1e-4
+    if with_labels:
+        assert _relf(dtok, tok.grad) < 1e-4
+
+
+def _cfg(**kw):
+    cfg = dict(vocab_size=756, hidden_size=128, intermediate_size=512, num_hidden_layers=2, num_attention_heads=2,
+               num_key_value_heads=2, head_dim=64, hidden_act="gelu", max_position_embeddings=1024, rms_norm_eps=1e-6,
+               rope_theta=10000.0, pad_token_id=0, bos_token_id=20, eos_token_id=19, causal_attention=False,
+               stacked_feat=13, stack_method="short", stacked_feat_agg_method="sum", next_n_token=13, use_cache=False,
+               attention_dropout=0.0)
+    cfg.update(kw)
+    return cfg
+
+
+@pytest.mark.parametrize("embed_dim", [0, 16])
+def test_training_mode_dropout_matches_oracle_with_the_same_masks(embed_dim):
+    """mlp_pdrop + embed_pdrop (+ raw_embed_dropout) in train() mode: loss, logits and every gradient against the
+    oracle evaluated with the kernels' own masks (utils_graphgpt.py:69-83, modeling_helpers.py:97-98)."""
+    from graphgpt_b200 import GraphGPTConfig, GraphGPTPretrainBase, ops, synth
+    from graphgpt_b200.engine import _SEED_ACT, _SEED_EMBED, _SEED_MLP, _SEED_RAW, mix_seed
+    from oracle import graphgpt_oracle as oracle
+    cfgd = _cfg(mlp_pdrop=0.1, embed_pdrop=0.2, embed_dim=embed_dim)
+    b = synth.make_batch(3, 128, layout="packed", seed=31)
+    ids, am, labels = (torch.from_numpy(b[k]) for k in ("input_ids", "attention_mask", "labels"))
+    N, S, F_ = ids.shape
+    d, I, L = cfgd["hidden_size"], cfgd["intermediate_size"], cfgd["num_hidden_layers"]
+    sd = oracle.init_state_dict(cfgd, seed=9)
+    kw = {}
+    if embed_dim:
+        g = torch.Generator().manual_seed(2)
+        sd["embed_layernorm.weight"] = 1 + 0.1 * torch.randn(embed_dim, generator=g)
+        sd["emb_mask_token"] = 0.3 * torch.randn(1, 1, embed_dim, generator=g)
+        sd["embed_proj.weight"] = 0.05 * torch.randn(d, embed_dim, generator=g)
+        full = (torch.rand(N, S, generator=g) < 0.3) & (am.diagonal(dim1=1, dim2=2) == 1 if am.dim() == 3 else am == 1)
+        labels = torch.where(full[:, :, None] & (labels == -100), ids, labels)    # some fully labelled rows -> mask token
+        kw["inputs_raw_embeds"] = torch.randn(N, S, embed_dim, generator=g)
+    model = GraphGPTPretrainBase(GraphGPTConfig(**cfgd))
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().train()
+    torch.manual_seed(77)
+    out = model(input_ids=ids.cuda(), attention_mask=am.cuda(), labels=labels.cuda(),
+                **{k: v.cuda() for k, v in kw.items()})
+    out.head1_loss.backward()
+    torch.manual_seed(77)
+    base = int(torch.randint(0, 2 ** 62, (1,)).item())          # the draw HotPath.backbone_forward made
+    T = N * S
+
+    def scale(n, p, stream, shape):
+        return ops.dropout_scale(n, p, mix_seed(base, stream), "cuda").view(shape).cpu()
+
+    drop = {"embed": scale(T * F_ * d, 0.2, _SEED_EMBED, (N, S, F_, d)),
+            "act": [scale(T * I, 0.1, _SEED_ACT + i, (N, S, I)) for i in range(L)],
+            "mlp": [scale(T * d, 0.1, _SEED_MLP + i, (N, S, d)) for i in range(L)]}
+    if embed_dim:
+        drop["raw"] = scale(T * embed_dim, 0.2, _SEED_RAW, (N, S, embed_dim))
+    sd_ref = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ref = oracle.pretrain_forward(sd_ref, cfgd, ids, am, labels, drop=drop, **kw)
+    ref["loss"].backward()
+    e_loss = abs(out.head1_loss.item() - ref["loss"].item()) / ref["loss"].item()
+    e_lg = _relf(out.head1_logits, ref["logits"].detach())
+    assert e_loss <= 1e-3 and e_lg <= 1e-2, (e_loss, e_lg)
+    worst = max((_relf(p.grad, sd_ref[k].grad), k) for k, p in model.named_parameters())
+    assert worst[0] <= 3e-2, worst
+    # eval mode: every dropout is the identity and matches the plain oracle
+    model.eval()
+    with torch.no_grad():
+        out_e = model(input_ids=ids.cuda(), attention_mask=am.cuda(), labels=labels.cuda(),
+                      **{k: v.cuda() for k, v in kw.items()})
+    ref_e = oracle.pretrain_forward(sd, cfgd, ids, am, labels, **kw)
+    assert abs(out_e.head1_loss.item() - ref_e["loss"].item()) / ref_e["loss"].item() <= 1e-3
+    assert abs(out_e.head1_loss.item() - out.head1_loss.item()) > 1e-4       # and training mode really dropped

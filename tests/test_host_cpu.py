@@ -40,6 +40,10 @@ def test_argument_validation_without_gpu():
         lib.ggpt_gemm_bf16(0, 8, 0, 0, 8, 0, 0, 8, 0, 0, 128, 128, 64, 0)
     with pytest.raises(RuntimeError, match="not implemented"):
         lib.ggpt_attn_mask_build(1, 4, 1, 8, 0, 1, 1, 1, 1, 1, 1, 1, 0)
+    with pytest.raises(RuntimeError, match=r"outside \[0,1\)"):
+        lib.ggpt_dropout_bf16(16, 8, 1.5, 0, 0)
+    with pytest.raises(RuntimeError, match="bad sizes"):
+        lib.ggpt_raw_embed_norm_fwd(16, 0, 0, 0, 0, 16, 16, 6, 0, 0, 4, 6, 1e-6, 0)
 
 
 def test_model_refuses_cpu_execution():
@@ -54,7 +58,8 @@ def test_model_refuses_cpu_execution():
 def test_state_dict_keys_match_reference_checkpoint_contract():
     from graphgpt_b200 import GraphGPTConfig, GraphGPTPretrainBase, GraphGPTTaskModel
     for fx, cls in (("c2_smtp_stacked_2d", GraphGPTPretrainBase), ("c2_gated_agg", GraphGPTPretrainBase),
-                    ("c3_ft_layerscale", GraphGPTTaskModel), ("c1_toy_smtp_2d", GraphGPTPretrainBase)):
+                    ("c3_ft_layerscale", GraphGPTTaskModel), ("c1_toy_smtp_2d", GraphGPTPretrainBase),
+                    ("c2_raw_embed_pretrain", GraphGPTPretrainBase), ("c3_raw_embed_ft", GraphGPTTaskModel)):
         rec = torch.load(os.path.join(ROOT, "tests", "golden", fx + ".pt"))
         m = cls(GraphGPTConfig(**rec["config"]))
         mine = {k: tuple(v.shape) for k, v in m.state_dict().items()}
