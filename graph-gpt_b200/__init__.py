@@ -11,4 +11,7 @@ def __getattr__(name):  # lazy: keep `import graphgpt_b200` cheap and torch-free
                 "GraphGPTForMaskedLM", "GraphGPTForCausalLM", "convert_to_legacy_config"):
         from . import modeling
         return getattr(modeling, name)
+    if name in ("GenerationConfig", "sample_per_batch", "sample_per_example", "sample_tokens"):
+        from . import generation
+        return getattr(generation, name)
     raise AttributeError(name)

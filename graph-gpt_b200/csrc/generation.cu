@@ -7,6 +7,8 @@
 // (_batch_unmask_without_for_loop).  HBM-bound: the logits [R, V] fp32 are read exactly once.
 #include <float.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "../../include/ggpt_b200.h"
 
@@ -114,14 +116,14 @@ __global__ void __launch_bounds__(256) gen_sample_kernel(const float* __restrict
       for (int j = t; j < V; j += G) m = fmaxf(m, row[j]);
       m = g.max(m);
       float z = 0.f;
-      for (int j = t; j < V; j += G) z += __expf(row[j] - m);
+      for (int j = t; j < V; j += G) z += expf(row[j] - m);
       z = g.sum(z);
       const float budget = top_p * z;
       uint32_t lo = 0u, hi = 0xffffffffu;                   // smallest key K with mass(key > K) <= budget
       while (lo < hi) {
         const uint32_t mid = lo + ((hi - lo) >> 1);
         float above = 0.f;
-        for (int j = t; j < V; j += G) above += (fkey(row[j]) > mid) ? __expf(row[j] - m) : 0.f;
+        for (int j = t; j < V; j += G) above += (fkey(row[j]) > mid) ? expf(row[j] - m) : 0.f;
         above = g.sum(above);
         if (above <= budget) hi = mid; else lo = mid + 1u;
       }
@@ -152,7 +154,7 @@ __global__ void __launch_bounds__(256) gen_sample_kernel(const float* __restrict
       if (row[j] > m || (row[j] == m && j < am)) { m = row[j]; am = j; }
     g.argmax(m, am);
     float z = 0.f;
-    for (int j = t; j < V; j += G) z += __expf(row[j] - m);
+    for (int j = t; j < V; j += G) z += expf(row[j] - m);
     z = g.sum(z);
     const float inv_z = 1.0f / z;
     int pick = am;
@@ -162,7 +164,7 @@ __global__ void __launch_bounds__(256) gen_sample_kernel(const float* __restrict
       const int chunk = (V + G - 1) / G;
       const int j0 = t * chunk, j1 = min(V, j0 + chunk);
       float part = 0.f;
-      for (int j = j0; j < j1; ++j) part += __expf(row[j] - m);
+      for (int j = j0; j < j1; ++j) part += expf(row[j] - m);
       // exclusive prefix of the per-thread partial sums (warp scan, then across warps in CTA mode)
       float incl = part;
 #pragma unroll
@@ -182,7 +184,7 @@ __global__ void __launch_bounds__(256) gen_sample_kernel(const float* __restrict
       if (before <= target && target < before + part) {
         float c = before;
         for (int j = j0; j < j1; ++j) {
-          c += __expf(row[j] - m);
+          c += expf(row[j] - m);
           if (c > target) { found = j; break; }
         }
       }
@@ -201,23 +203,23 @@ __global__ void __launch_bounds__(256) gen_sample_kernel(const float* __restrict
         pick = li >= 0 ? li : am;
       }
     }
-    float conf = __expf(row[pick] - m) * inv_z;
+    float conf = expf(row[pick] - m) * inv_z;
     if (conf_mode == 1) {                                   // margin: top1 - top2 probability
       float m2 = kFiniteMin;
       for (int j = t; j < V; j += G)
         if (j != am) m2 = fmaxf(m2, row[j]);
       m2 = g.max(m2);
-      conf = inv_z - __expf(m2 - m) * inv_z;
+      conf = inv_z - expf(m2 - m) * inv_z;
     } else if (conf_mode == 2) {                            // negative entropy: sum p log(p + 1e-10)
       float e = 0.f;
       for (int j = t; j < V; j += G) {
-        const float p = __expf(row[j] - m) * inv_z;
-        e += p * __logf(p + 1e-10f);
+        const float p = expf(row[j] - m) * inv_z;
+        e += p * logf(p + 1e-10f);
       }
       conf = g.sum(e);
     }
     if (probs_out != nullptr)
-      for (int j = t; j < V; j += G) probs_out[r * ldp + j] = __expf(row[j] - m) * inv_z;
+      for (int j = t; j < V; j += G) probs_out[r * ldp + j] = expf(row[j] - m) * inv_z;
     if (t == 0) {
       x0_out[r] = pick;
       if (conf_out != nullptr) conf_out[r] = conf;

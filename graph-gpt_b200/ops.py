@@ -429,6 +429,53 @@ def ce_bwd(logits, labels, V, row_lse, scale_ptr, gout, wgt=None, focal_gamma=0.
     return dlogits
 
 
+# ------------------------------------------------------------------------------------------------
+# Generation
+# ------------------------------------------------------------------------------------------------
+def gen_sample(logits, V, *, temperature=0.0, top_k=None, top_p=None, u=None, conf_mode=0, want_probs=False):
+    """logits f32 [R, ld>=V].  Returns (conf f32 [R], x0 int64 [R][, probs f32 [R,V]])."""
+    _check(logits, F32, "gen_sample logits", 2)
+    R = logits.shape[0]
+    dev = logits.device
+    if u is not None:
+        _check(u, F32, "gen_sample u", 1)
+        if u.numel() != R:
+            raise RuntimeError("gen_sample: one uniform draw per row expected")
+    x0 = torch.empty((R,), device=dev, dtype=torch.int64)
+    conf = torch.empty((R,), device=dev, dtype=F32)
+    probs = torch.empty((R, V), device=dev, dtype=F32) if want_probs else None
+    lib.ggpt_gen_sample(logits.data_ptr(), logits.stride(0), R, V, float(temperature), int(top_k or 0),
+                        float(top_p) if top_p is not None else 0.0, _ptr(u), int(conf_mode), x0.data_ptr(), conf.data_ptr(),
+                        _ptr(probs), V, _stream())
+    return (conf, x0, probs) if want_probs else (conf, x0)
+
+
+def gen_unmask_origin(x, x0, u, p_transfer, mask_token):
+    _check(x, torch.int64, "gen_unmask x")
+    _check(x0, torch.int64, "gen_unmask x0")
+    _check(u, F32, "gen_unmask u")
+    if not (x.is_contiguous() and x0.is_contiguous() and u.is_contiguous()) or x0.numel() != x.numel() or u.numel() != x.numel():
+        raise RuntimeError("gen_unmask_origin: x, x0, u must be contiguous and equally sized")
+    lib.ggpt_gen_unmask_origin(x.data_ptr(), x0.data_ptr(), u.data_ptr(), float(p_transfer), int(mask_token), x.numel(),
+                               _stream())
+    return x
+
+
+def gen_unmask_topk(x, x0, conf, k_per_sample, mask_token, *, gumbel_u=None, alg_temp=0.0):
+    _check(x, torch.int64, "gen_unmask x", 2)
+    _check(x0, torch.int64, "gen_unmask x0", 2)
+    _check(conf, F32, "gen_unmask conf", 2)
+    _check(k_per_sample, torch.int32, "gen_unmask k_per_sample", 1)
+    B, P = x.shape
+    if not (x.is_contiguous() and x0.is_contiguous() and conf.is_contiguous()) or x0.shape != x.shape or conf.shape != x.shape:
+        raise RuntimeError("gen_unmask_topk: x, x0, conf must be contiguous [B,P]")
+    if gumbel_u is not None:
+        _check(gumbel_u, F32, "gen_unmask gumbel_u", 2)
+    lib.ggpt_gen_unmask_topk(x.data_ptr(), x0.data_ptr(), conf.data_ptr(), _ptr(gumbel_u), float(alg_temp),
+                             k_per_sample.data_ptr(), int(mask_token), B, P, _stream())
+    return x
+
+
 def sumsq(g, out):
     lib.ggpt_sumsq(g.data_ptr(), g.numel(), out.data_ptr(), _stream())
 

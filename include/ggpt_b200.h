@@ -214,6 +214,27 @@ int ggpt_ce_bwd(const float* logits, long long ldl, const int* labels, const flo
                 const float* scale, const float* gout, void* dlogits, long long ldd, int L, int V, float focal_gamma,
                 void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Un-masking generation.  ref: src/utils/generation_utils.py
+ * ------------------------------------------------------------------------------------------- */
+/* sample_tokens (:44-82) over logits f32 [R, ldl] (V valid columns), one row per (sample, position, feature) entry:
+ * logits / temperature (temperature > 0), top-p filter (0 < top_p < 1; :22-33: a token is dropped when the softmax mass
+ * of the strictly larger logits exceeds top_p), top-k filter (0 < top_k < V; :36-41), fp32 softmax, then
+ *   x0[r]  = temperature > 0 && u != NULL ? inverse-CDF sample with the uniform draw u[r] : arg max (lowest index)
+ *   conf[r] (may be NULL) = conf_mode 0: p[x0];  1: top1 - top2 probability (margin_confidence);  2: sum p log(p + 1e-10)
+ * probs (may be NULL; f32 [R, ldp]) receives the filtered softmax (tests / tooling). */
+int ggpt_gen_sample(const float* logits, long long ldl, long long R, int V, float temperature, int top_k, float top_p,
+                    const float* u, int conf_mode, long long* x0, float* conf, float* probs, long long ldp,
+                    void* stream);
+/* alg "origin" (:156-170): x[i] = x0[i] where x[i] == mask_token and u[i] < p_transfer (u = caller's uniform draws). */
+int ggpt_gen_unmask_origin(long long* x, const long long* x0, const float* u, float p_transfer, long long mask_token,
+                           long long n, void* stream);
+/* algs maskgit_plus / topk_margin / entropy (:171-228): in each sample b of x int64 [B,P] the k_per_sample[b] most
+ * confident masked entries take x0 (ties: lowest position first).  gumbel_u (may be NULL; f32 [B,P] uniform draws)
+ * perturbs the scores as conf / alg_temp - log(-log(u + 1e-9) + 1e-9) (:197-205). */
+int ggpt_gen_unmask_topk(long long* x, const long long* x0, const float* conf, const float* gumbel_u, float alg_temp,
+                         const int* k_per_sample, long long mask_token, int B, int P, void* stream);
+
 /* out += sum(g^2) (double accumulator, pre-zeroed by the caller). */
 int ggpt_sumsq(const float* g, long long n, double* out, void* stream);
 /* Fused AdamW (torch.optim.AdamW semantics) over a flat fp32 parameter buffer, with optional global-norm clipping
