@@ -8,7 +8,7 @@ __version__ = "0.1.0"
 
 def __getattr__(name):  # lazy: keep `import graphgpt_b200` cheap and torch-free until a class is requested
     if name in ("GraphGPTConfig", "GraphGPTPretrainBase", "GraphGPTTaskModel", "DoubleHeadsModelOutput",
-                "GraphGPTForMaskedLM", "GraphGPTForCausalLM", "convert_to_legacy_config"):
+                "GraphGPTForMaskedLM", "GraphGPTForCausalLM", "convert_to_legacy_config", "GraphGPTDoubleHeadsModel"):
         from . import modeling
         return getattr(modeling, name)
     if name in ("GenerationConfig", "sample_per_batch", "sample_per_example", "sample_tokens"):

@@ -425,16 +425,25 @@ class BackboneFn(torch.autograd.Function):
         return (None,) * len(ctx.needs_input_grad)
 
 
+PRETRAIN_HEAD = ("lm_head.weight", "n_token_proj.weight", None)
+
+
 class PretrainHeadFn(torch.autograd.Function):
-    """hidden (bf16 [T,d]) + labels -> (loss, logits[L,V]).  ref: modeling_pretrain.py:213-237."""
+    """hidden (bf16 [T,d]) + labels -> (loss, logits[L,V]).  ref: modeling_pretrain.py:213-237.
+    `head` = (vocabulary projection, per-feature projection | None, V | None) names the weights: the SMTP / NTP head by
+    default; ("score.weight", None, num_labels) is the token-level fine-tuning loss (modeling_finetune.py:195-199) and
+    ("lm_head.weight", None, None) the auxiliary LM head of GraphGPTDoubleHeadsModel (:402-411) — the same compaction of
+    labelled rows, GEMM on those rows only and fp32 cross-entropy."""
 
     @staticmethod
-    def forward(ctx, hot, hf, labels2d, N, S, ent_wgt_fn, loss_mode, *params):
+    def forward(ctx, hot, hf, labels2d, N, S, ent_wgt_fn, loss_mode, head, *params):
         fp = hot.flat
-        d, F_, V = hot.d, labels2d.shape[1], hot.V
+        head_w, proj_w, V = head
+        V = hot.V if V is None else V
+        d, F_ = hot.d, labels2d.shape[1]
         hi = ops.head_compact(labels2d)
         M, L = hi.sync_counts()
-        has_proj = "n_token_proj.weight" in fp.offsets
+        has_proj = proj_w is not None and proj_w in fp.offsets
         if M == 0:
             loss = torch.full((), float("nan"), device=hf.device, dtype=F32)
             ctx.empty = True
@@ -442,11 +451,11 @@ class PretrainHeadFn(torch.autograd.Function):
             return loss, torch.empty((0, V), device=hf.device, dtype=F32)
         hsel = ops.gather_rows(hf, hi.sel_rows, M)
         if has_proj:
-            proj = ops.gemm(hsel, fp.wb("n_token_proj.weight"))                      # [M, F*d]
+            proj = ops.gemm(hsel, fp.wb(proj_w))                                     # [M, F*d]
             hl = ops.gather_rows(proj.view(M * F_, d), hi.ent_src, L)
         else:
             hl = hsel                                                               # F == 1: entries == rows
-        logits = ops.gemm(hl, fp.wb("lm_head.weight"), out_dtype=F32)              # [L, V] (ld padded to 8)
+        logits = ops.gemm(hl, fp.wb(head_w), out_dtype=F32)                        # [L, V] (ld padded to 8)
         wgt = ent_wgt_fn(hi, L) if ent_wgt_fn is not None else None
         # FocalLoss only on the unweighted branch (modeling_pretrain.py:221-236: the dLM loss ignores focal_gamma)
         focal = float(getattr(hot.cfg, "focal_gamma", 0.0) or 0.0) if wgt is None else 0.0
@@ -456,6 +465,7 @@ class PretrainHeadFn(torch.autograd.Function):
         else:                                                                       # dLM: sum / (N*S*F)
             ls = ops.ce_finalize(sums, 0, 2, float(N * S * hot.cfg.next_n_token))
         ctx.hot, ctx.hi, ctx.M, ctx.L, ctx.T = hot, hi, M, L, hf.shape[0]
+        ctx.head_w, ctx.proj_w, ctx.V, ctx.F = head_w, proj_w, V, F_
         ctx.saved = (hsel, hl, logits, row_lse, wgt, ls)
         ctx.has_proj, ctx.empty, ctx.focal = has_proj, False, focal
         ctx.mark_non_differentiable(logits)
@@ -468,7 +478,7 @@ class PretrainHeadFn(torch.autograd.Function):
             return (None,) * n_in
         hot, hi, M, L = ctx.hot, ctx.hi, ctx.M, ctx.L
         fp = hot.flat
-        d, V = hot.d, hot.V
+        d, V = hot.d, ctx.V
         hsel, hl, logits, row_lse, wgt, ls = ctx.saved
         ctx.saved = None
         fp.prepare_grads()
@@ -476,15 +486,15 @@ class PretrainHeadFn(torch.autograd.Function):
         gout = gloss.reshape(1).to(F32).contiguous()
         dlog = ops.ce_bwd(logits, hi.ent_label, V, row_lse, ls.data_ptr() + 4, gout, wgt, focal_gamma=ctx.focal)  # bf16 [L, ld]
         dlv = dlog[:, :V]
-        ops.gemm(dlv, hl, out=fp.g("lm_head.weight"), **wgrad)
-        dhl = ops.gemm(dlv, fp.wb("lm_head.weight"), b_mn_major=True)                        # [L, d]
+        ops.gemm(dlv, hl, out=fp.g(ctx.head_w), **wgrad)
+        dhl = ops.gemm(dlv, fp.wb(ctx.head_w), b_mn_major=True)                              # [L, d]
         if ctx.has_proj:
-            F_ = hot.cfg.next_n_token
+            F_ = ctx.F
             dproj = torch.zeros((M * F_, d), device=dhl.device, dtype=BF16)
             ops.scatter_rows(dhl, hi.ent_src, dproj, L)
             dproj = dproj.view(M, F_ * d)
-            ops.gemm(dproj, hsel, out=fp.g("n_token_proj.weight"), **wgrad)
-            dhsel = ops.gemm(dproj, fp.wb("n_token_proj.weight"), b_mn_major=True)           # [M, d]
+            ops.gemm(dproj, hsel, out=fp.g(ctx.proj_w), **wgrad)
+            dhsel = ops.gemm(dproj, fp.wb(ctx.proj_w), b_mn_major=True)                      # [M, d]
         else:
             dhsel = dhl
         dhf = torch.zeros((ctx.T, d), device=dhl.device, dtype=BF16)

@@ -19,7 +19,7 @@ from torch import nn
 from transformers import LlamaConfig
 from transformers.utils import ModelOutput
 
-from .engine import BackboneFn, HotPath, PretrainHeadFn
+from .engine import PRETRAIN_HEAD, BackboneFn, HotPath, PretrainHeadFn
 
 # GraphGPT-specific config fields and their defaults (same names as the reference so YAML / checkpoints map 1:1).
 _GRAPHGPT_FIELDS = dict(
@@ -27,7 +27,7 @@ _GRAPHGPT_FIELDS = dict(
     embed_pdrop=0.0, path_pdrop=0.0, mlp_pdrop=0.0, layer_scale_init_value=0.0,
     stacked_feat=1, stack_method=None, stacked_feat_agg_method="sum", pos_agg_method="sum", pos_bins=512,
     embed_dim=0, next_n_token=1, use_generative=True, use_discriminative=False, focal_gamma=0.0, smtp_inside=False,
-    cls_token_id=None, mlp=None, dropout=0.0, loss_type=None, num_neg=None,
+    cls_token_id=None, mlp=None, dropout=0.0, loss_type=None, num_neg=None, use_aux=False,
     # 3-D position pre-training / denoising heads: carried for config round-trips, not executed by this package
     smtp_power=1.0, pt_problem_type="pos-smtp-line", smtp_3d_power=1.0, smtp_3d_noise_scale=0.2, coord_lvl_mask=True,
     pt_num_bins=1024, pt_num_bins_line=256, pt_num_bins_cube=32, apply_denoise=False, label_smoothing=0.0,
@@ -243,6 +243,8 @@ class _GraphGPTBase(nn.Module):
         for k in ("n_token_proj.weight", "lm_head.weight"):
             if k in named:
                 order.append(k)
+        if self.config.loss_type == "token_ce" and "score.weight" in named and "score.bias" not in named:
+            order.append("score.weight")     # token-level FT: the score head runs on the tensor cores over labelled rows
         return [(k, named[k]) for k in order]
 
     @property
@@ -414,7 +416,7 @@ class GraphGPTPretrainBase(_GraphGPTBase):
                 def wgt_fn(hi, L, per_sample=per_sample, S=S):
                     return per_sample[(hi.ent_tok[:L].long() // S)].contiguous()
             params = [p for _, p in hot.flat.order]
-            loss, logits = PretrainHeadFn.apply(hot, hf, lab2d, N, S, wgt_fn, mode, *params)
+            loss, logits = PretrainHeadFn.apply(hot, hf, lab2d, N, S, wgt_fn, mode, PRETRAIN_HEAD, *params)
         return DoubleHeadsModelOutput(head1_loss=loss, head1_logits=logits, head2_loss=None, head2_logits=None,
                                       past_key_values=None, hidden_states=None, attentions=None)
 
@@ -494,17 +496,46 @@ class GraphGPTTaskModel(_GraphGPTBase):
             raise AssertionError("pad_token_id must be set")
         if self.pooling_method != "last":
             raise AssertionError(f"{self.pooling_method}!='last'")
-        if cfg.loss_type in {"token_ce", "token_ce_intra"}:
-            raise NotImplementedError("token-level fine-tuning losses are not built (node-level tasks; SURVEY §8f N3)")
+        if cfg.loss_type == "token_ce_intra":
+            raise NotImplementedError("token_ce_intra (intra-instance label embeddings, modeling_finetune.py:139-161) is not "
+                                      "built (SURVEY §8f N3)")
         seq_len = (in_.to(dev) != cfg.pad_token_id).sum(-1) - 1                      # modeling_helpers.py:78-86
         rows = torch.arange(N, device=dev)
         pooled_hidden = hidden[rows, seq_len]                                        # [N, d] bf16
+        self._last_backbone = (hf, N, S)
+        if cfg.loss_type == "token_ce":
+            return self._token_ce_outputs(hf, hidden, pooled_hidden, task_labels, N, S)
         pooled_logits = self.score(pooled_hidden.float())
         task_loss = None
         if task_labels is not None:
             task_loss = self._task_loss(task_labels.to(dev), pooled_logits, sample_wgt)
         return DoubleHeadsModelOutput(pretrain_loss=None, task_loss=task_loss, pretrain_logits=None,
                                       task_logits=pooled_logits.float(), past_key_values=None, hidden_states=hidden,
+                                      task_hidden_states=pooled_hidden, attentions=None)
+
+    def _token_ce_outputs(self, hf, hidden, pooled_hidden, task_labels, N, S):
+        """loss_type == "token_ce" (node-level tasks): `score` on every position, CrossEntropyLoss over the labelled
+        positions (modeling_finetune.py:161-165, 195-199).  task_logits is the full [N,S,num_labels] grid as in the
+        reference; the loss path runs the score GEMM on the labelled rows only (same values, ignore_index = -100)."""
+        from . import ops
+        hot = self._hot
+        if "score.weight" not in hot.flat.offsets:
+            raise NotImplementedError("token_ce needs the plain Linear score head without bias (config.mlp == [], "
+                                      "problem_type != 'regression')")
+        nl = self.num_labels
+        with torch.no_grad():
+            logits = ops.gemm(hf.detach(), hot.flat.wb("score.weight"), out_dtype=torch.float32)
+        task_loss = None
+        if task_labels is not None:
+            if self.config.problem_type is None:
+                self.config.problem_type = "single_label_classification"
+            if self.config.problem_type != "single_label_classification":
+                raise NotImplementedError(f"token_ce with problem_type={self.config.problem_type!r}")
+            lab2d = task_labels.to(hf.device).reshape(N * S, 1).contiguous()
+            params = [p for _, p in hot.flat.order]
+            task_loss, _ = PretrainHeadFn.apply(hot, hf, lab2d, N, S, None, "mean", ("score.weight", None, nl), *params)
+        return DoubleHeadsModelOutput(pretrain_loss=None, task_loss=task_loss, pretrain_logits=None,
+                                      task_logits=logits.reshape(N, S, nl), past_key_values=None, hidden_states=hidden,
                                       task_hidden_states=pooled_hidden, attentions=None)
 
     def _task_loss(self, labels, pooled_logits, sample_wgt):
@@ -535,3 +566,41 @@ class GraphGPTTaskModel(_GraphGPTBase):
             return (l * w).sum() / w.sum()
         ok = labels == labels
         return F.binary_cross_entropy_with_logits(pooled_logits[ok], labels[ok], pos_weight=self.pos_weight)
+
+
+class GraphGPTDoubleHeadsModel(GraphGPTTaskModel):
+    """Task head + auxiliary LM head on one backbone pass (modeling_finetune.py:329-423).  The aux loss is
+    CrossEntropyLoss(lm_head(hidden).float().view(-1, V), pretrain_labels.view(-1)): labelled rows are compacted on the
+    device and lm_head runs on those rows only.  `pretrain_logits` ([N,S,V], bf16) is materialised in eval mode only —
+    at C3 sizes it is a 5 GB tensor no training loop reads."""
+
+    def __init__(self, config: GraphGPTConfig):
+        super().__init__(config)
+        self.vocab_size = config.vocab_size
+        if config.use_aux:
+            self.lm_head = nn.Linear(config.hidden_size, config.vocab_size, bias=False)
+            nn.init.normal_(self.lm_head.weight, mean=0.0, std=config.initializer_range)
+            self._hot = None
+
+    def forward(self, input_ids=None, attention_mask=None, position_ids=None, past_key_values=None, inputs_embeds=None,
+                inputs_raw_embeds=None, pretrain_labels=None, task_labels=None, cls_idx=None, sample_wgt=None,
+                use_cache=None, output_attentions=None, output_hidden_states=None, return_dict=None):
+        res = super().forward(input_ids=input_ids, attention_mask=attention_mask, position_ids=position_ids,
+                              inputs_embeds=inputs_embeds, inputs_raw_embeds=inputs_raw_embeds, task_labels=task_labels,
+                              cls_idx=cls_idx, sample_wgt=sample_wgt)
+        pretrain_loss, pretrain_logits = None, None
+        if self.config.use_aux:
+            from . import ops
+            hf, N, S = self._last_backbone
+            hot = self._hot
+            if pretrain_labels is not None:
+                lab2d = pretrain_labels.to(hf.device).reshape(N * S, 1).contiguous()
+                params = [p for _, p in hot.flat.order]
+                pretrain_loss, _ = PretrainHeadFn.apply(hot, hf, lab2d, N, S, None, "mean", ("lm_head.weight", None, None),
+                                                        *params)
+            if not self.training:
+                with torch.no_grad():
+                    pretrain_logits = ops.gemm(hf.detach(), hot.flat.wb("lm_head.weight")).reshape(N, S, -1)
+        self._last_backbone = None
+        return DoubleHeadsModelOutput(pretrain_loss=pretrain_loss, task_loss=res.task_loss, pretrain_logits=pretrain_logits,
+                                      task_logits=res.task_logits, past_key_values=None, hidden_states=None, attentions=None)

@@ -333,7 +333,7 @@ def pretrain_forward(sd, cfg, input_ids, attention_mask=None, labels=None, sampl
 # fine-tuning head
 # ------------------------------------------------------------------------------------------------
 def task_forward(sd, cfg, input_ids, attention_mask=None, position_ids=None, task_labels=None, sample_wgt=None,
-                 inputs_raw_embeds=None):
+                 inputs_raw_embeds=None, pretrain_labels=None):
     """GraphGPTTaskModel.forward (modeling_finetune.py:236-326): score on all positions, pool at the last non-pad
     index (modeling_helpers.py:78-86), CE / MSE / L1 / BCE loss (modeling_finetune.py:167-234)."""
     cfg = OracleConfig.from_any(cfg)
@@ -350,6 +350,18 @@ def task_forward(sd, cfg, input_ids, attention_mask=None, position_ids=None, tas
     idx = torch.arange(hidden.shape[0])
     pooled_logits = logits[idx, seq_len]
     pooled_hidden = hidden[idx, seq_len]
+    aux = {}
+    if pretrain_labels is not None:
+        # GraphGPTDoubleHeadsModel (modeling_finetune.py:402-411): auxiliary LM head over every position
+        pl = F.linear(hidden, sd["lm_head.weight"])
+        aux = {"pretrain_logits": pl,
+               "pretrain_loss": F.cross_entropy(pl.float().view(-1, pl.shape[-1]), pretrain_labels.view(-1))}
+    if cfg.loss_type == "token_ce":
+        # token-level task (modeling_finetune.py:161-165,195-199): every position is scored, CE ignores -100
+        loss = None
+        if task_labels is not None:
+            loss = F.cross_entropy(logits.view(-1, cfg.num_labels).float(), task_labels.view(-1))
+        return {"loss": loss, "task_logits": logits.float(), "hidden": hidden, "task_hidden": pooled_hidden, **aux}
     loss = None
     if task_labels is not None:
         problem = cfg.problem_type
@@ -373,7 +385,7 @@ def task_forward(sd, cfg, input_ids, attention_mask=None, position_ids=None, tas
         else:
             ok = task_labels == task_labels
             loss = F.binary_cross_entropy_with_logits(pooled_logits[ok], task_labels[ok])
-    return {"loss": loss, "task_logits": pooled_logits.float(), "hidden": hidden, "task_hidden": pooled_hidden}
+    return {"loss": loss, "task_logits": pooled_logits.float(), "hidden": hidden, "task_hidden": pooled_hidden, **aux}
 
 
 # ------------------------------------------------------------------------------------------------

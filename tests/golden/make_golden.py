@@ -178,6 +178,35 @@ def _raw_ft():
                                  task_labels=torch.tensor([1, 0, 0]), inputs_raw_embeds=raw)
 
 
+@case("c3_ft_token_ce")
+def _ft_tok():
+    """Node-level fine-tune: loss_type token_ce, score on every position, CE over labelled positions
+    (modeling_finetune.py:161-165,195-199)."""
+    cfg = base_cfg(vocab_size=1200, hidden_size=64, intermediate_size=256, stacked_feat=4, next_n_token=4,
+                   num_labels=7, problem_type="single_label_classification", pooling_method="last", loss_type="token_ce")
+    vocab = synth.VocabLayout(vocab_size=1200, scope=512, n_node_attr=2, n_edge_attr=1)
+    b = synth.make_batch(3, 48, layout="unpacked", task="ntp", vocab=vocab, seed=23)
+    g = np.random.default_rng(8)
+    lab = g.integers(0, 7, size=b["attention_mask"].shape).astype(np.int64)
+    lab[(b["attention_mask"] == 0) | (g.random(lab.shape) < 0.4)] = -100
+    return "finetune", cfg, dict(input_ids=t(b["input_ids"]), attention_mask=t(b["attention_mask"]), task_labels=t(lab))
+
+
+@case("c3_ft_double_heads")
+def _ft_double():
+    """GraphGPTDoubleHeadsModel with use_aux: edge-level task loss + auxiliary LM loss over pretrain_labels [N,S]
+    (modeling_finetune.py:329-423); gradients are those of task_loss + pretrain_loss."""
+    cfg = base_cfg(vocab_size=1200, hidden_size=64, intermediate_size=256, stacked_feat=4, next_n_token=4,
+                   num_labels=2, problem_type="single_label_classification", pooling_method="last", use_aux=True)
+    vocab = synth.VocabLayout(vocab_size=1200, scope=512, n_node_attr=2, n_edge_attr=1)
+    b = synth.make_batch(3, 48, layout="unpacked", task="ntp", vocab=vocab, seed=24)
+    g = np.random.default_rng(9)
+    pl = b["input_ids"][:, :, 0].copy()
+    pl[(b["attention_mask"] == 0) | (g.random(pl.shape) < 0.5)] = -100
+    return "double", cfg, dict(input_ids=t(b["input_ids"]), attention_mask=t(b["attention_mask"]),
+                               task_labels=torch.tensor([1, 1, 0]), pretrain_labels=t(pl))
+
+
 def _patch_dropout_backbone():
     """transformers 5.5.0's LlamaModel loop expects decoder layers to return a tensor; the reference's dropout
     layer (utils_graphgpt.py:168-173) returns the 4.53-style tuple.  Unwrap it (SURVEY §8c caveat)."""
@@ -238,7 +267,9 @@ def main():
         cfg = GraphGPTConfig(**cfgd)
         cfg._attn_implementation = "eager"
         torch.manual_seed(1000 + len(name))
-        model = (mp.GraphGPTPretrainBase if kind == "pretrain" else mf.GraphGPTTaskModel)(cfg).eval().float()
+        klass = {"pretrain": mp.GraphGPTPretrainBase, "finetune": mf.GraphGPTTaskModel,
+                 "double": mf.GraphGPTDoubleHeadsModel}[kind]
+        model = klass(cfg).eval().float()
         with torch.no_grad():  # make norm weights / lambdas non-trivial so their gradients and scaling are exercised
             for n_, p in model.named_parameters():
                 if "layernorm" in n_ or n_.endswith("norm.weight"):
@@ -257,6 +288,11 @@ def main():
             rec["logits_stride"] = 4 if lg.numel() > 100_000 else 1
             rec["logits"] = lg[:: rec["logits_stride"]].clone()  # full rows, every stride-th row
             loss = out.head1_loss
+        elif kind == "double":
+            rec["task_logits"] = out.task_logits.detach().clone()
+            rec["pretrain_logits_rowsum"] = out.pretrain_logits.detach().double().sum(-1)
+            rec["task_loss"], rec["pretrain_loss"] = out.task_loss.detach().clone(), out.pretrain_loss.detach().clone()
+            loss = out.task_loss + out.pretrain_loss
         else:
             rec["task_logits"] = out.task_logits.detach().clone()
             rec["hidden"] = out.hidden_states.detach().clone()
@@ -284,6 +320,8 @@ def main():
         if kind == "pretrain":
             lb, lgb = ob.head1_loss, ob.head1_logits.float()
             bf["logits_relF"] = float((lgb - out.head1_logits.detach()).norm() / out.head1_logits.detach().norm())
+        elif kind == "double":
+            lb = ob.task_loss + ob.pretrain_loss
         else:
             lb = ob.task_loss
             bf["task_hidden_relF"] = float((ob.task_hidden_states.float() - out.task_hidden_states.detach()).norm()

@@ -33,9 +33,9 @@ def _log(msg):
 
 
 def _build(rec):
-    from graphgpt_b200 import GraphGPTConfig, GraphGPTPretrainBase, GraphGPTTaskModel
+    from graphgpt_b200 import GraphGPTConfig, GraphGPTDoubleHeadsModel, GraphGPTPretrainBase, GraphGPTTaskModel
     cfg = GraphGPTConfig(**rec["config"])
-    cls = GraphGPTPretrainBase if rec["kind"] == "pretrain" else GraphGPTTaskModel
+    cls = {"pretrain": GraphGPTPretrainBase, "finetune": GraphGPTTaskModel, "double": GraphGPTDoubleHeadsModel}[rec["kind"]]
     model = cls(cfg)
     missing, unexpected = model.load_state_dict(rec["state_dict"], strict=False)
     assert not missing and not unexpected, (missing, unexpected)
@@ -56,10 +56,22 @@ def test_model_matches_reference_golden(path):
         loss = out.head1_loss
         _log(f"{name}: logits relF {e_lg:.3e} (reference-in-bf16 relF {rec.get('ref_bf16_error', {}).get('logits_relF', float('nan')):.3e})")
         assert e_lg <= ACT_TOL
-    else:
+    elif rec["kind"] == "double":
         e_tl = _relf(out.task_logits, rec["task_logits"])
-        e_th = _relf(out.task_hidden_states, rec["task_hidden"])
+        e_t = abs(out.task_loss.item() - rec["task_loss"].item()) / abs(rec["task_loss"].item())
+        e_p = abs(out.pretrain_loss.item() - rec["pretrain_loss"].item()) / abs(rec["pretrain_loss"].item())
+        N_, S_ = rec["inputs"]["attention_mask"].shape
+        assert tuple(out.pretrain_logits.shape) == (N_, S_, rec["config"]["vocab_size"]) and out.hidden_states is None
+        _log(f"{name}: task_logits relF {e_tl:.3e} task_loss rel {e_t:.3e} pretrain_loss rel {e_p:.3e}")
+        assert e_tl <= 5 * ACT_TOL and e_t <= 1e-2 and e_p <= LOSS_TOL
+        loss = out.task_loss + out.pretrain_loss
+    else:
         am = rec["inputs"]["attention_mask"].bool()
+        if out.task_logits.dim() == 3:       # token-level task: the full [N,S,labels] grid, valid positions compared
+            e_tl = _relf(out.task_logits.float().cpu()[am], rec["task_logits"][am])
+        else:
+            e_tl = _relf(out.task_logits, rec["task_logits"])
+        e_th = _relf(out.task_hidden_states, rec["task_hidden"])
         e_h = _relf(out.hidden_states.float().cpu()[am], rec["hidden"][am])
         loss = out.task_loss
         _log(f"{name}: task_logits relF {e_tl:.3e} task_hidden relF {e_th:.3e} hidden relF {e_h:.3e}")
