@@ -44,6 +44,9 @@ CASES = [
     (2, 300, 2, "pad", True),
     (1, 1024, 12, "none", False),
     (2, 512, 2, "random", False),
+    (1, 2048, 2, "pad", True),        # C5: causal NTP at seq 2048
+    (1, 4096, 1, "none", False),      # C4: citation2 sequences of 4096
+    (1, 4096, 1, "packed", False),
 ]
 
 
@@ -262,6 +265,8 @@ BWD_CASES = [
     (2, 384, 2, "packed", False, True),
     (1, 1024, 4, "none", False, False),
     (2, 512, 2, "random", False, True),
+    (1, 2048, 2, "pad", True, True),       # C5
+    (1, 4096, 1, "none", False, True),     # C4
 ]
 
 
@@ -291,7 +296,7 @@ def test_attn_bwd(N, S, H, kind, causal, rope):
         am = (torch.rand((N, S, S), generator=g) < 0.3).long()
         am[:, torch.arange(S), torch.arange(S)] = 1
         am = am.to(dev)
-    max_pos = 2048
+    max_pos = 4096
     inv_freq = 1.0 / (10000.0 ** (torch.arange(0, 64, 2, dtype=torch.int64).float() / 64))
     freqs = torch.arange(max_pos).float()[:, None] * inv_freq[None, :]
     cos_tab, sin_tab = freqs.cos().to(dev), freqs.sin().to(dev)

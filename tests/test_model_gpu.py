@@ -127,6 +127,59 @@ def test_c2_medium_vs_oracle():
     assert worst <= GRAD_TOL
 
 
+def _oracle_parity(cfgd, b, tag, train=True):
+    from graphgpt_b200 import GraphGPTConfig, GraphGPTPretrainBase
+    from oracle import graphgpt_oracle as oracle
+    sd = oracle.init_state_dict(cfgd, seed=5)
+    ids, am, labels = (torch.from_numpy(b[k]) for k in ("input_ids", "attention_mask", "labels"))
+    sd_ref = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ref = oracle.pretrain_forward(sd_ref, cfgd, ids, am, labels)
+    ref["loss"].backward()
+    model = GraphGPTPretrainBase(GraphGPTConfig(**cfgd))
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().train()
+    out = model(input_ids=ids.cuda(), attention_mask=am.cuda(), labels=labels.cuda())
+    e_loss = abs(out.head1_loss.item() - ref["loss"].item()) / ref["loss"].item()
+    e_lg = _relf(out.head1_logits, ref["logits"].detach())
+    _log(f"{tag}: loss {out.head1_loss.item():.6f} ref {ref['loss'].item():.6f} rel {e_loss:.3e}; logits relF {e_lg:.3e}")
+    assert e_loss <= LOSS_TOL and e_lg <= ACT_TOL
+    out.head1_loss.backward()
+    worst = max((_relf(p.grad, sd_ref[k].grad), k) for k, p in model.named_parameters())
+    _log(f"{tag}: worst grad relF {worst[0]:.3e} ({worst[1]})")
+    assert worst[0] <= GRAD_TOL, worst
+
+
+def test_c5_shape_causal_ntp_seq2048_vs_oracle():
+    """C5 geometry (d=1024, 16 heads, I=4096, causal NTP, seq 2048) at 2 layers, one padded + one full sequence."""
+    from graphgpt_b200 import synth
+    cfgd = dict(vocab_size=756, hidden_size=1024, intermediate_size=4096, num_hidden_layers=2, num_attention_heads=16,
+                num_key_value_heads=16, head_dim=64, hidden_act="gelu", max_position_embeddings=2048, rms_norm_eps=1e-6,
+                rope_theta=10000.0, pad_token_id=0, bos_token_id=20, eos_token_id=19, causal_attention=True,
+                stacked_feat=13, stack_method="short", stacked_feat_agg_method="sum", next_n_token=13, use_cache=False,
+                attention_dropout=0.0)
+    b = synth.make_batch(2, 2048, layout="dense", task="ntp", seed=41)
+    b["attention_mask"][1, 1500:] = 0
+    b["input_ids"][1, 1500:] = 0
+    b["labels"][1, 1500:] = -100
+    _oracle_parity(cfgd, b, "c5_shape")
+
+
+def test_c4_shape_seq4096_vs_oracle():
+    """C4 geometry: bidirectional sequences of 4096 rows (citation2 sub-graph sampling), F=4, 2L/128d."""
+    from graphgpt_b200 import synth
+    cfgd = dict(vocab_size=1200, hidden_size=128, intermediate_size=512, num_hidden_layers=2, num_attention_heads=2,
+                num_key_value_heads=2, head_dim=64, hidden_act="gelu", max_position_embeddings=4096, rms_norm_eps=1e-6,
+                rope_theta=10000.0, pad_token_id=0, bos_token_id=20, eos_token_id=19, causal_attention=False,
+                stacked_feat=4, stack_method="short", stacked_feat_agg_method="sum", next_n_token=4, use_cache=False,
+                attention_dropout=0.0)
+    vocab = synth.VocabLayout(vocab_size=1200, scope=512, n_node_attr=2, n_edge_attr=1)
+    b = synth.make_batch(2, 4096, layout="dense", vocab=vocab, seed=42)
+    b["attention_mask"][0, 3000:] = 0
+    b["input_ids"][0, 3000:] = 0
+    b["labels"][0, 3000:] = -100
+    _oracle_parity(cfgd, b, "c4_shape")
+
+
 def test_no_cpu_fallback():
     from graphgpt_b200 import GraphGPTConfig, GraphGPTPretrainBase
     cfg = GraphGPTConfig(vocab_size=300, hidden_size=64, intermediate_size=256, num_hidden_layers=1, num_attention_heads=1,
