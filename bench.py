@@ -162,7 +162,7 @@ def run_b200(args):
 
     from graphgpt_b200 import GraphGPTConfig, GraphGPTPretrainBase, synth
     from graphgpt_b200.dp import GraphGPTEngine
-    from graphgpt_b200.lib import KernelTimer, lib
+    from graphgpt_b200.lib import GEMM_FUNCS, KernelTimer, lib
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -221,15 +221,23 @@ def run_b200(args):
     clk_path = os.path.join(tempfile.gettempdir(), f"ggpt_clocks_{os.getpid()}.csv")
     sampler = clocks_sampler_start(clk_path) if rank == 0 else None
     launches0 = lib.launch_count
-    lib.timer = KernelTimer()
+    # inside the timed region only the dominant kernel (the tcgen05 GEMM, every launch of it) is bracketed by CUDA
+    # events: those durations give roofline.achieved.  The other entry points are timed in a separate pass below.
+    lib.timer = KernelTimer(only=GEMM_FUNCS)
     total_ms = timed(lambda i: step(devb[i % len(devb)]), args.steps)
-    ktimes = lib.timer.summary()
+    gtimes = lib.timer.summary()
     lib.timer = None
     launches = lib.launch_count - launches0
     if sampler is not None:
         sampler.terminate()
     ms_per_step = total_ms / args.steps
     value = world * tok_per_step / (ms_per_step / 1e3)
+    # per-entry-point breakdown (informational `kernel_ms_per_step`): every call bracketed, outside the timed region
+    n_prof = min(args.steps, 4)
+    lib.timer = KernelTimer()
+    timed(lambda i: step(devb[i % len(devb)]), n_prof)
+    ktimes = lib.timer.summary()
+    lib.timer = None
 
     # ---- end-to-end: pinned host batches -> H2D -> step -> loss.item() ---------------------------------------------
     e2e = None
@@ -290,10 +298,10 @@ def run_b200(args):
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback (B200_PROFILING.md ~1.4 PF sustained)"
     # dominant kernel = the tcgen05 GEMM (all instantiations of gemm_kernel<>): FLOPs of every launch / summed time
-    gemm = [(k, v) for k, v in ktimes.items() if k.startswith("ggpt_gemm")]
+    gemm = [(k, v) for k, v in gtimes.items() if k.startswith("ggpt_gemm")]
     g_ms = sum(v["ms"] for _, v in gemm)
     g_fl = sum(v["flops"] for _, v in gemm)
-    all_ms = sum(v["ms"] for v in ktimes.values())
+    all_ms = total_ms
     top = max(gemm, key=lambda kv: kv[1]["ms"]) if gemm else None
     traffic = None
     try:
@@ -303,7 +311,7 @@ def run_b200(args):
     roofline = {"bound": "tensor", "kernel": "ggpt::gemm_kernel<> (tcgen05 GEMM, all instantiations)",
                 "achieved": g_fl / (g_ms / 1e3) / 1e12 if g_ms > 0 else None, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": (g_fl / (g_ms / 1e3) / 1e12) / peak_tf if g_ms > 0 else None, "traffic": traffic,
-                "peak_source": peak_src, "share_of_kernel_time": g_ms / all_ms if all_ms > 0 else None,
+                "peak_source": peak_src, "share_of_step_time": g_ms / all_ms if all_ms > 0 else None,
                 "launches": sum(v["calls"] for _, v in gemm),
                 "top_instance": None if top is None else {
                     "name": top[0], "calls": top[1]["calls"], "ms": top[1]["ms"],
@@ -319,7 +327,7 @@ def run_b200(args):
             "model_tflops_per_gpu": step_tf, "model_tflops_frac_of_peak": step_tf / peak_tf,
             "roofline": roofline, "e2e": e2e, "gpu_launches": launches,
             "clocks": clocks_summary(clk_path, local),
-            "kernel_ms_per_step": {k: round(v["ms"] / args.steps, 4) for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1]["ms"])}}
+            "kernel_ms_per_step": {k: round(v["ms"] / n_prof, 4) for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1]["ms"])}}
     if fwd is not None:
         fwd["frac_of_peak"] = fwd["model_tflops_per_gpu"] / peak_tf
         line["forward_only"] = fwd

@@ -60,8 +60,10 @@ class KernelTimer:
     """CUDA-event timing of C-ABI calls on the launching stream (used by bench.py inside the timed region).
     Collects, per entry point (GEMMs are keyed by operand majors too): calls, device ms, FLOPs."""
 
-    def __init__(self):
+    def __init__(self, only=None):
         self.events = []   # (key, start, end, flops)
+        self.only = only   # optional set of entry-point names to time (others run untimed: every event pair costs the
+                           # stream a few microseconds, which adds up over ~250 calls per training step)
 
     def summary(self):
         import torch
@@ -106,7 +108,7 @@ class _Lib:
         dll = self.load()
         self.launch_count += _LAUNCHES.get(name, 1)
         timer = self.timer
-        if timer is not None and _LAUNCHES.get(name, 1) > 0:
+        if timer is not None and _LAUNCHES.get(name, 1) > 0 and (timer.only is None or name in timer.only):
             import torch
             key, flops = name, 0.0
             if name in _GEMM_FUNCS:
@@ -133,4 +135,5 @@ class _Lib:
         raise AttributeError(name)
 
 
+GEMM_FUNCS = frozenset(_GEMM_FUNCS)
 lib = _Lib()
