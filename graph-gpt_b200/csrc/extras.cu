@@ -111,6 +111,66 @@ __global__ void raw_embed_norm_bwd_kernel(const __nv_bfloat16* __restrict__ dh, 
 }
 
 // =============================================================================================
+// LayerScale / DropPath backward of a residual branch  x_out = x_in + rowscale[t] * lam[c] * y  (utils_graphgpt.py:153-166):
+//   dy[t,c]  = bf16(dx[t,c] * lam[c] * rowscale[t])                       gradient handed to the branch's dgrad / wgrad GEMMs
+//   dlam[c] += sum_t dx[t,c] * rowscale[t] * y[t,c] = sum_t dx[t,c] * (x_out[t,c] - x_in[t,c]) / lam[c]
+// (y itself is never stored: the fused add+norm pass consumed it).  One HBM pass; each lane owns columns
+// lane*4 + k*128 for every row its warp visits, so the dlam partial sums stay in registers.
+// =============================================================================================
+template <int NV>
+__global__ void __launch_bounds__(256) layerscale_bwd_kernel(const float* __restrict__ dx, const float* __restrict__ x_out,
+                                                             const float* __restrict__ x_in, const float* __restrict__ lam,
+                                                             const float* __restrict__ rowscale,
+                                                             __nv_bfloat16* __restrict__ dy, float* __restrict__ dlam,
+                                                             long long T, int d) {
+  extern __shared__ float s_acc[];   // [d]
+  for (int c = threadIdx.x; c < d; c += blockDim.x) s_acc[c] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  float4 acc[NV], lv[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = lane * 4 + k * 128;
+    acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    lv[k] = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (c < d && lam != nullptr) lv[k] = *reinterpret_cast<const float4*>(lam + c);
+  }
+  for (long long t = static_cast<long long>(blockIdx.x) * wpb + (threadIdx.x >> 5); t < T;
+       t += static_cast<long long>(gridDim.x) * wpb) {
+    const float rs = rowscale != nullptr ? rowscale[t] : 1.0f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = lane * 4 + k * 128;
+      if (c < d) {
+        const float4 g = *reinterpret_cast<const float4*>(dx + t * d + c);
+        if (dlam != nullptr) {
+          const float4 a = *reinterpret_cast<const float4*>(x_out + t * d + c);
+          const float4 b = *reinterpret_cast<const float4*>(x_in + t * d + c);
+          acc[k].x += g.x * (a.x - b.x); acc[k].y += g.y * (a.y - b.y);
+          acc[k].z += g.z * (a.z - b.z); acc[k].w += g.w * (a.w - b.w);
+        }
+        uint2 o;
+        o.x = pack_bf16(g.x * lv[k].x * rs, g.y * lv[k].y * rs);
+        o.y = pack_bf16(g.z * lv[k].z * rs, g.w * lv[k].w * rs);
+        *reinterpret_cast<uint2*>(dy + t * d + c) = o;
+      }
+    }
+  }
+  if (dlam == nullptr) return;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = lane * 4 + k * 128;
+    if (c < d) {
+      atomicAdd(&s_acc[c + 0], acc[k].x / lv[k].x); atomicAdd(&s_acc[c + 1], acc[k].y / lv[k].y);
+      atomicAdd(&s_acc[c + 2], acc[k].z / lv[k].z); atomicAdd(&s_acc[c + 3], acc[k].w / lv[k].w);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < d; c += blockDim.x) atomicAdd(dlam + c, s_acc[c]);
+}
+
+// =============================================================================================
 // Element dropout.  x[e] *= keep(e) / (1 - p) in place on a bf16 tensor viewed as a flat array of n elements;
 // scale_f32 writes the keep/(1-p) factors themselves (tests and tooling read the mask through it).
 // =============================================================================================
@@ -179,6 +239,25 @@ int ggpt_raw_embed_norm_bwd(const void* dh, long long lddh, const float* raw, co
   raw_embed_norm_bwd_kernel<<<grid_cap((T + 7) / 8, 2), 256, smem, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(dh), lddh, raw, keep, mask_tok, rstd, w, dw, dmask_tok, T, E);
   return check_launch("raw_embed_norm_bwd_kernel");
+}
+
+int ggpt_layerscale_bwd(const float* dx, const float* x_out, const float* x_in, const float* lam, const float* rowscale,
+                        void* dy, float* dlam, long long T, int d, void* stream) {
+  GGPT_REQUIRE(dx && dy, "layerscale_bwd: null pointer");
+  GGPT_REQUIRE(dlam == nullptr || (lam && x_out && x_in), "layerscale_bwd: dlam needs lam, x_out and x_in");
+  GGPT_REQUIRE(T > 0 && d > 0 && d % 4 == 0 && d <= 2048, "layerscale_bwd: bad sizes T=%lld d=%d", T, d);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  __nv_bfloat16* dyb = static_cast<__nv_bfloat16*>(dy);
+  const int grid = grid_cap((T + 7) / 8, 4);
+  const size_t sm = d * sizeof(float);
+  const int nv = (d + 127) / 128;
+  if (nv <= 1) layerscale_bwd_kernel<1><<<grid, 256, sm, s>>>(dx, x_out, x_in, lam, rowscale, dyb, dlam, T, d);
+  else if (nv <= 2) layerscale_bwd_kernel<2><<<grid, 256, sm, s>>>(dx, x_out, x_in, lam, rowscale, dyb, dlam, T, d);
+  else if (nv <= 4) layerscale_bwd_kernel<4><<<grid, 256, sm, s>>>(dx, x_out, x_in, lam, rowscale, dyb, dlam, T, d);
+  else if (nv <= 6) layerscale_bwd_kernel<6><<<grid, 256, sm, s>>>(dx, x_out, x_in, lam, rowscale, dyb, dlam, T, d);
+  else if (nv <= 8) layerscale_bwd_kernel<8><<<grid, 256, sm, s>>>(dx, x_out, x_in, lam, rowscale, dyb, dlam, T, d);
+  else layerscale_bwd_kernel<16><<<grid, 256, sm, s>>>(dx, x_out, x_in, lam, rowscale, dyb, dlam, T, d);
+  return check_launch("layerscale_bwd_kernel");
 }
 
 int ggpt_dropout_bf16(void* x, long long n, float p, unsigned long long seed, void* stream) {

@@ -259,24 +259,25 @@ class HotPath:
             h1, rstd1 = ops.rmsnorm_fwd(x, w_in0, self.eps, want_rstd=keep)
         for i in range(self.L):
             p = f"model.layers.{i}."
-            rs = None if droppath_scales is None else droppath_scales[i]
+            # DropPath draws an independent per-sample mask for each of the two residual branches (utils_graphgpt.py:156,166)
+            rs1, rs2 = (None, None) if droppath_scales is None else droppath_scales[i]
             qkv = ops.gemm_qkv_rope(h1, self._wqkv(i), pos, cos, sin, 2 * d)
             a, lse = ops.attn_fwd(qkv, mask, H, want_lse=keep, dropout_p=attn_dropout, seed=drop_seed + i)
             y1 = ops.gemm(a, fp.wb(p + "self_attn.o_proj.weight"))
             lam1 = fp.w(p + "lambda_1") if self.layer_scale else None
             x2, h2, rstd2 = ops.add_rmsnorm_fwd(x, y1, fp.w(p + "post_attention_layernorm.weight"), self.eps,
-                                                colscale=lam1, rowscale=rs, want_rstd=keep)
+                                                colscale=lam1, rowscale=rs1, want_rstd=keep)
             gu, act = ops.gemm_geglu(h2, self._wgu(i), want_gu=keep)
             ops.dropout_(act, mlp_pdrop, mix_seed(drop_seed, _SEED_ACT + i))          # mlp_act_dropout, utils_graphgpt.py:80
             y2 = ops.gemm(act, fp.wb(p + "mlp.down_proj.weight"))
             ops.dropout_(y2, mlp_pdrop, mix_seed(drop_seed, _SEED_MLP + i))           # mlp_dropout, utils_graphgpt.py:81
             lam2 = fp.w(p + "lambda_2") if self.layer_scale else None
             next_w = fp.w(f"model.layers.{i + 1}.input_layernorm.weight") if i + 1 < self.L else fp.w("model.norm.weight")
-            x3, h_next, rstd_next = ops.add_rmsnorm_fwd(x2, y2, next_w, self.eps, colscale=lam2, rowscale=rs,
+            x3, h_next, rstd_next = ops.add_rmsnorm_fwd(x2, y2, next_w, self.eps, colscale=lam2, rowscale=rs2,
                                                         want_rstd=keep)
             if keep:
                 stash["layers"].append(dict(x=x, rstd1=rstd1, h1=h1, qkv=qkv, a=a, lse=lse, x2=x2, rstd2=rstd2, h2=h2,
-                                            gu=gu, act=act, x3=x3 if self.layer_scale else None, rs=rs))
+                                            gu=gu, act=act, x3=x3 if self.layer_scale else None, rs1=rs1, rs2=rs2))
             x, h1, rstd1 = x3, h_next, rstd_next
         hf, rstdf = h1, rstd1
         if keep:
@@ -318,10 +319,10 @@ class HotPath:
             st = stash["layers"][i]
             # ---- MLP block:  x3 = x2 + rs * lam2 * (act @ Wd^T)
             dyb = dxb
-            if self.layer_scale or st["rs"] is not None:
-                dyb = self._scaled_copy(dx, fp.w(p + "lambda_2") if self.layer_scale else None, st["rs"])
-                if self.layer_scale:
-                    self._lambda_grad(fp.g(p + "lambda_2"), dx, st["x3"], st["x2"], fp.w(p + "lambda_2"))
+            if self.layer_scale or st["rs2"] is not None:
+                ls = self.layer_scale
+                dyb = ops.layerscale_bwd(dx, st["x3"] if ls else None, st["x2"] if ls else None,
+                                         fp.w(p + "lambda_2") if ls else None, st["rs2"], fp.g(p + "lambda_2") if ls else None)
             mlp_p, seed = stash["mlp_pdrop"], stash["drop_seed"]
             ops.dropout_(dyb, mlp_p, mix_seed(seed, _SEED_MLP + i))      # in place: dyb is this block's private bf16 copy
             # (ops.gemm_dgeglu fuses the next two calls, but its epilogue is slower than the separate HBM-bound kernel:
@@ -336,10 +337,10 @@ class HotPath:
                                         fp.g(p + "post_attention_layernorm.weight"))
             # ---- attention block:  x2 = x + rs * lam1 * (a @ Wo^T)
             dyb = dx2b
-            if self.layer_scale or st["rs"] is not None:
-                dyb = self._scaled_copy(dx2, fp.w(p + "lambda_1") if self.layer_scale else None, st["rs"])
-                if self.layer_scale:
-                    self._lambda_grad(fp.g(p + "lambda_1"), dx2, st["x2"], st["x"], fp.w(p + "lambda_1"))
+            if self.layer_scale or st["rs1"] is not None:
+                ls = self.layer_scale
+                dyb = ops.layerscale_bwd(dx2, st["x2"] if ls else None, st["x"] if ls else None,
+                                         fp.w(p + "lambda_1") if ls else None, st["rs1"], fp.g(p + "lambda_1") if ls else None)
             da = ops.gemm(dyb, fp.wb(p + "self_attn.o_proj.weight"), b_mn_major=True)
             ops.gemm(dyb, st["a"], out=fp.g(p + "self_attn.o_proj.weight"), **wgrad)
             dqkv = ops.attn_bwd(da, st["qkv"], st["a"], st["lse"], stash["mask"], H, stash["pos"], stash["cos"],
@@ -379,22 +380,6 @@ class HotPath:
         if self.grad_ready_hook:
             names = [n for n, _ in self.flat.order]
             self.grad_ready_hook(names[0], names[names.index("model.layers.0.self_attn.q_proj.weight") - 1])
-
-    # LayerScale / DropPath are fine-tuning-only options (ppa: lsi=1, path_dropout=0.2); their few elementwise
-    # gradient terms are formed with torch ops on device — not on the pre-training hot path.
-    @staticmethod
-    def _scaled_copy(dx, lam, rs):
-        y = dx
-        if lam is not None:
-            y = y * lam[None, :]
-        if rs is not None:
-            y = y * rs[:, None]
-        return y.to(BF16)
-
-    @staticmethod
-    def _lambda_grad(glam, dx, x_out, x_in, lam):
-        # x_out = x_in + rs*lam*y  =>  dlam = sum_t dx * rs*y = sum_t dx * (x_out - x_in) / lam
-        glam.add_((dx * (x_out - x_in)).sum(0) / lam)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -295,18 +295,24 @@ class _GraphGPTBase(nn.Module):
         return ids2d.contiguous(), in_, N, S
 
     def _droppath_scales(self, N, S, device):
-        """Per-layer per-row scale implementing BeitDropPath (keep mask / keep_prob per SAMPLE), training only."""
+        """Per-layer (attention-branch, MLP-branch) per-row scales implementing BeitDropPath, training only: each call of
+        the reference's drop_path draws torch.rand((N,1,1)) on the device and keeps sample n iff floor(keep + u_n) == 1,
+        scaled by 1/keep (utils_graphgpt.py:156,166).  The draws are made here in the reference's order (layer by layer,
+        attention branch first), so a seeded run with attention_dropout == 0 drops the same samples as the reference."""
         if not self.training or self.config.path_pdrop <= 0:
             return None
         out = []
         for layer in self.model.layers:
             p = layer.drop_prob
             if p <= 0:
-                out.append(None)
+                out.append((None, None))
                 continue
             keep = 1.0 - p
-            m = (torch.rand((N,), device=device) < keep).float() / keep
-            out.append(m.repeat_interleave(S).contiguous())
+            pair = []
+            for _ in range(2):
+                m = torch.floor(keep + torch.rand((N, 1, 1), dtype=torch.float32, device=device)).view(N) / keep
+                pair.append(m.repeat_interleave(S).contiguous())
+            out.append(tuple(pair))
         return out
 
     def _raw_embed_inputs(self, inputs_raw_embeds, N, S, labels, fchk):

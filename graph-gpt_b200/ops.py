@@ -294,6 +294,16 @@ def raw_embed_norm_bwd(dh, raw, keep, mask_tok, rstd, w, dw, dmask_tok):
                                 w.data_ptr(), dw.data_ptr(), _ptr(dmask_tok), T, E, _stream())
 
 
+def layerscale_bwd(dx, x_out, x_in, lam, rowscale, dlam):
+    """dy bf16 [T,d] = dx * lam * rowscale; accumulates dlam [d] += sum_t dx * (x_out - x_in) / lam when dlam is given."""
+    _check(dx, F32, "layerscale_bwd dx", 2)
+    T, d = dx.shape
+    dy = torch.empty((T, d), device=dx.device, dtype=BF16)
+    lib.ggpt_layerscale_bwd(dx.data_ptr(), _ptr(x_out), _ptr(x_in), _ptr(lam), _ptr(rowscale), dy.data_ptr(), _ptr(dlam),
+                            T, d, _stream())
+    return dy
+
+
 def dropout_(x, p, seed):
     """In-place element dropout on a contiguous bf16 tensor (mask = pure function of (seed, linear index))."""
     _check(x, BF16, "dropout x")

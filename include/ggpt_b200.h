@@ -161,6 +161,13 @@ int ggpt_raw_embed_norm_bwd(const void* dh, long long lddh, const float* raw, co
                             const float* mask_tok, const float* rstd, const float* w, float* dw, float* dmask_tok,
                             long long T, int E, void* stream);
 
+/* Backward of a LayerScale / DropPath residual branch x_out = x_in + rowscale[t]*lam[c]*y (ppa fine-tuning: lsi = 1,
+ * path_dropout = 0.2): dy (bf16 [T,d]) = dx*lam*rowscale, the gradient handed to the branch's GEMMs, and
+ * dlam[c] += sum_t dx*(x_out - x_in)/lam (y itself is not kept).  lam / rowscale may be NULL (factor 1); dlam NULL skips
+ * the reduction (then x_out / x_in may be NULL).   ref: autograd of utils_graphgpt.py:153-166. */
+int ggpt_layerscale_bwd(const float* dx, const float* x_out, const float* x_in, const float* lam, const float* rowscale,
+                        void* dy, float* dlam, long long T, int d, void* stream);
+
 /* Element dropout on activations, training only (config.mlp_pdrop: GeGLU output and down_proj output; embed_pdrop:
  * normalised raw embeddings).  x (bf16, n contiguous elements, 16-byte aligned) is scaled in place by keep(e)/(1-p);
  * keep(e) is a pure function of (seed, e) — the backward pass applies the same call to the incoming gradient.

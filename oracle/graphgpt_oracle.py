@@ -137,10 +137,11 @@ def attention(q, k, v, mask4d, scaling):
     return o.transpose(1, 2).contiguous()
 
 
-def decoder_layer(x, sd, prefix, cfg, cos, sin, mask4d, act_scale=None, mlp_scale=None):
+def decoder_layer(x, sd, prefix, cfg, cos, sin, mask4d, act_scale=None, mlp_scale=None, path_scale=None):
     """HF:313-332 LlamaDecoderLayer.forward (+ LayerScale of utils_graphgpt.py:153-166).  act_scale / mlp_scale are the
     training-mode nn.Dropout factors keep/(1-p) of mlp_act_dropout [N,S,I] and mlp_dropout [N,S,d]
-    (utils_graphgpt.py:69-83) supplied by the caller — None = eval mode (identity)."""
+    (utils_graphgpt.py:69-83) supplied by the caller — None = eval mode (identity).  path_scale = (s1, s2): the DropPath
+    factors floor(keep + u)/keep per sample ([N]) of the attention and the MLP branch (utils_graphgpt.py:156,166)."""
     N, S, d = x.shape
     H, hd = cfg.num_attention_heads, cfg.head_dim
     h = rmsnorm(x, sd[prefix + "input_layernorm.weight"], cfg.rms_norm_eps)
@@ -152,6 +153,8 @@ def decoder_layer(x, sd, prefix, cfg, cos, sin, mask4d, act_scale=None, mlp_scal
     a = F.linear(a, sd[prefix + "self_attn.o_proj.weight"])
     if prefix + "lambda_1" in sd:
         a = sd[prefix + "lambda_1"] * a
+    if path_scale is not None and path_scale[0] is not None:
+        a = a * path_scale[0][:, None, None]
     x = x + a
     h = rmsnorm(x, sd[prefix + "post_attention_layernorm.weight"], cfg.rms_norm_eps)
     g = F.linear(h, sd[prefix + "mlp.gate_proj.weight"])
@@ -164,6 +167,8 @@ def decoder_layer(x, sd, prefix, cfg, cos, sin, mask4d, act_scale=None, mlp_scal
         m = m * mlp_scale                                              # utils_graphgpt.py:81
     if prefix + "lambda_2" in sd:
         m = sd[prefix + "lambda_2"] * m
+    if path_scale is not None and path_scale[1] is not None:
+        m = m * path_scale[1][:, None, None]
     return x + m
 
 
@@ -225,7 +230,8 @@ def backbone(inputs_embeds, attention_mask, position_ids, sd, cfg, collect=None,
     for i in range(cfg.num_hidden_layers):
         x = decoder_layer(x, sd, f"model.layers.{i}.", cfg, cos, sin, mask4d,
                           None if drop is None or "act" not in drop else drop["act"][i],
-                          None if drop is None or "mlp" not in drop else drop["mlp"][i])
+                          None if drop is None or "mlp" not in drop else drop["mlp"][i],
+                          None if drop is None or "path" not in drop else drop["path"][i])
         if collect is not None:
             collect.append(x)
     return rmsnorm(x, sd["model.norm.weight"], cfg.rms_norm_eps)
@@ -333,7 +339,7 @@ def pretrain_forward(sd, cfg, input_ids, attention_mask=None, labels=None, sampl
 # fine-tuning head
 # ------------------------------------------------------------------------------------------------
 def task_forward(sd, cfg, input_ids, attention_mask=None, position_ids=None, task_labels=None, sample_wgt=None,
-                 inputs_raw_embeds=None, pretrain_labels=None):
+                 inputs_raw_embeds=None, pretrain_labels=None, drop=None):
     """GraphGPTTaskModel.forward (modeling_finetune.py:236-326): score on all positions, pool at the last non-pad
     index (modeling_helpers.py:78-86), CE / MSE / L1 / BCE loss (modeling_finetune.py:167-234)."""
     cfg = OracleConfig.from_any(cfg)
@@ -344,7 +350,7 @@ def task_forward(sd, cfg, input_ids, attention_mask=None, position_ids=None, tas
     emb, in_ = stacked_embed(input_ids, sd, cfg)
     if inputs_raw_embeds is not None:
         emb = emb + raw_embed_branch(inputs_raw_embeds, sd, cfg)                          # modeling_finetune.py:130-134
-    hidden = backbone(emb, attention_mask, position_ids, sd, cfg)
+    hidden = backbone(emb, attention_mask, position_ids, sd, cfg, drop=drop)
     logits = F.linear(hidden, sd["score.weight"], sd.get("score.bias"))
     seq_len = (in_ != cfg.pad_token_id).sum(-1) - 1
     idx = torch.arange(hidden.shape[0])

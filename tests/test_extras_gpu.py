@@ -163,3 +163,72 @@ def test_training_mode_dropout_matches_oracle_with_the_same_masks(embed_dim):
     ref_e = oracle.pretrain_forward(sd, cfgd, ids, am, labels, **kw)
     assert abs(out_e.head1_loss.item() - ref_e["loss"].item()) / ref_e["loss"].item() <= 1e-3
     assert abs(out_e.head1_loss.item() - out.head1_loss.item()) > 1e-4       # and training mode really dropped
+
+
+@pytest.mark.parametrize("T,d,use_lam,use_rs", [(1000, 768, True, True), (333, 128, True, False), (500, 1024, False, True)])
+def test_layerscale_bwd_kernel(T, d, use_lam, use_rs):
+    from graphgpt_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(T)
+    dx = torch.randn(T, d, device="cuda", generator=g)
+    lam = (1 + 0.3 * torch.randn(d, device="cuda", generator=g)) if use_lam else None
+    rs = ((torch.rand(T, device="cuda", generator=g) < 0.8).float() / 0.8) if use_rs else None
+    y = torch.randn(T, d, device="cuda", generator=g)
+    x_in = torch.randn(T, d, device="cuda", generator=g)
+    scale = (lam[None, :] if use_lam else 1.0) * (rs[:, None] if use_rs else 1.0)
+    x_out = x_in + scale * y
+    dlam = torch.zeros(d, device="cuda") if use_lam else None
+    dy = ops.layerscale_bwd(dx, x_out if use_lam else None, x_in if use_lam else None, lam, rs, dlam)
+    want_dy = dx
+    if use_lam:
+        want_dy = want_dy * lam[None, :]
+    if use_rs:
+        want_dy = want_dy * rs[:, None]
+    assert torch.equal(dy, want_dy.bfloat16())          # same multiplication order as the kernel: (dx * lam) * rs
+    if use_lam:
+        want = (dx * (rs[:, None] if use_rs else 1.0) * y).sum(0)
+        assert _relf(dlam, want) < 2e-4          # (x_out - x_in)/lam recovers rs*y to fp32 round-off
+
+
+def test_ppa_finetune_training_mode_droppath_layerscale_matches_oracle():
+    """C3 (ogbl-ppa fine-tune) training mode: LayerScale (lsi = 1) + DropPath 0.2 with the reference's own draw order
+    (torch.rand((N,1,1)) per residual branch, layer by layer) — loss and every gradient against the oracle fed the
+    same per-sample masks (utils_graphgpt.py:137-173)."""
+    from graphgpt_b200 import GraphGPTConfig, GraphGPTTaskModel, synth
+    from oracle import graphgpt_oracle as oracle
+    cfgd = _cfg(vocab_size=1200, stacked_feat=4, next_n_token=4, num_hidden_layers=3, num_labels=2,
+                problem_type="single_label_classification", pooling_method="last", layer_scale_init_value=1.0,
+                path_pdrop=0.4)
+    vocab = synth.VocabLayout(vocab_size=1200, scope=512, n_node_attr=2, n_edge_attr=1)
+    N = 8
+    b = synth.make_batch(N, 64, layout="unpacked", task="ntp", vocab=vocab, seed=51)
+    ids, am = torch.from_numpy(b["input_ids"]), torch.from_numpy(b["attention_mask"])
+    labels = torch.tensor([1, 0, 1, 1, 0, 0, 1, 0])
+    sd = oracle.init_state_dict(cfgd, seed=4, task_head=True)
+    g = torch.Generator().manual_seed(1)
+    for k in sd:
+        if "lambda_" in k:
+            sd[k] = sd[k] * (1 + 0.2 * torch.randn(sd[k].shape, generator=g))
+    model = GraphGPTTaskModel(GraphGPTConfig(**cfgd))
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().train()
+    torch.manual_seed(123)
+    out = model(input_ids=ids.cuda(), attention_mask=am.cuda(), task_labels=labels.cuda())
+    out.task_loss.backward()
+    # replay the DropPath draws: linspace(0, p, L) per layer, two draws per layer with p > 0
+    torch.manual_seed(123)
+    L, p = cfgd["num_hidden_layers"], cfgd["path_pdrop"]
+    path = []
+    for i in range(L):
+        pi = p * i / (L - 1)
+        if pi <= 0:
+            path.append((None, None))
+            continue
+        keep = 1 - pi
+        path.append(tuple((torch.floor(keep + torch.rand((N, 1, 1), device="cuda")).view(N) / keep).cpu() for _ in range(2)))
+    assert any(s is not None and bool((s == 0).any()) for pr in path for s in pr)     # some sample really was dropped
+    sd_ref = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ref = oracle.task_forward(sd_ref, cfgd, ids, am, task_labels=labels, drop={"path": path})
+    ref["loss"].backward()
+    assert abs(out.task_loss.item() - ref["loss"].item()) / ref["loss"].item() <= 1e-2
+    worst = max((_relf(p_.grad, sd_ref[k].grad), k) for k, p_ in model.named_parameters() if sd_ref[k].grad is not None)
+    assert worst[0] <= 3e-2, worst
