@@ -180,6 +180,65 @@ def test_c4_shape_seq4096_vs_oracle():
     _oracle_parity(cfgd, b, "c4_shape")
 
 
+def test_full_size_c2_packing_invariance_and_batch_linearity():
+    """BASELINE configs[1] at FULL size (12L/768d/F13/V756, 64 x 1024 packed tokens) through size-independent
+    properties, since no CPU oracle finishes this size in seconds:
+      * packing invariance — attention is block-diagonal and RoPE is relative, so the same graphs fed one per row
+        (right-padded [n_seg, 40] grid, 2-D mask) must give the same labelled-entry logits and the same loss as the
+        packed [64, 1024] grid with its [N,S,S] mask (different kernels: isolated-tile vs general attention path);
+      * batch linearity — gradients of the mean loss over the full batch = label-count-weighted mean of the two
+        half-batch gradients (exercises split-K wgrad accumulation and the compaction of labelled rows)."""
+    from graphgpt_b200 import GraphGPTConfig, GraphGPTPretrainBase, synth
+    import numpy as np
+    cfgd = dict(vocab_size=756, hidden_size=768, intermediate_size=3072, num_hidden_layers=12, num_attention_heads=12,
+                num_key_value_heads=12, head_dim=64, hidden_act="gelu", max_position_embeddings=1024, rms_norm_eps=1e-6,
+                rope_theta=10000.0, pad_token_id=0, bos_token_id=20, eos_token_id=19, causal_attention=False,
+                stacked_feat=13, stack_method="short", stacked_feat_agg_method="sum", next_n_token=13, use_cache=False,
+                attention_dropout=0.0)
+    N, S, F_ = 64, 1024, 13
+    b = synth.make_batch(N, S, layout="packed", seed=2024, return_segments=True)
+    torch.manual_seed(0)
+    model = GraphGPTPretrainBase(GraphGPTConfig(**cfgd)).cuda().train()
+    ids, am, labels = (torch.from_numpy(b[k]).cuda() for k in ("input_ids", "attention_mask", "labels"))
+    out = model(input_ids=ids, attention_mask=am, labels=labels)
+    loss_packed, logits_packed = out.head1_loss.item(), out.head1_logits.float().cpu()
+    out.head1_loss.backward()
+    g_full = {k: p.grad.clone() for k, p in model.named_parameters()}
+    n_full = int((labels != -100).sum())
+    assert logits_packed.shape[0] == n_full and np.isfinite(loss_packed)
+    # ---- the same graphs, one per row
+    segs = [(n, o, L) for n, lens in enumerate(b["segment_lens"]) for o, L in zip(np.cumsum([0] + lens[:-1]), lens)]
+    Su = (max(L for _, _, L in segs) + 7) // 8 * 8
+    u_ids = np.zeros((len(segs), Su, F_), np.int64)
+    u_lab = np.full((len(segs), Su, F_), -100, np.int64)
+    u_am = np.zeros((len(segs), Su), np.int64)
+    for i, (n, o, L) in enumerate(segs):
+        u_ids[i, :L], u_lab[i, :L], u_am[i, :L] = b["input_ids"][n, o:o + L], b["labels"][n, o:o + L], 1
+    model.zero_grad(set_to_none=True)
+    with torch.no_grad():
+        out_u = model(input_ids=torch.from_numpy(u_ids).cuda(), attention_mask=torch.from_numpy(u_am).cuda(),
+                      labels=torch.from_numpy(u_lab).cuda())
+    e_loss = abs(out_u.head1_loss.item() - loss_packed) / loss_packed
+    e_lg = _relf(out_u.head1_logits, logits_packed)
+    _log(f"full_size_c2: packed loss {loss_packed:.6f} vs one-graph-per-row {out_u.head1_loss.item():.6f} (rel {e_loss:.2e}); "
+         f"logits relF {e_lg:.2e} over {n_full} entries, {len(segs)} graphs")
+    assert e_loss <= LOSS_TOL and e_lg <= ACT_TOL
+    # ---- batch linearity of the gradients
+    acc, cnt = None, 0
+    for sl in (slice(0, N // 2), slice(N // 2, N)):
+        model.zero_grad(set_to_none=True)
+        o2 = model(input_ids=ids[sl], attention_mask=am[sl], labels=labels[sl])
+        o2.head1_loss.backward()
+        n_part = int((labels[sl] != -100).sum())
+        part = {k: p.grad.clone() * n_part for k, p in model.named_parameters()}
+        acc = part if acc is None else {k: acc[k] + part[k] for k in acc}
+        cnt += n_part
+    assert cnt == n_full
+    worst = max((_relf(acc[k] / cnt, g_full[k]), k) for k in g_full)
+    _log(f"full_size_c2: worst gradient deviation from batch linearity {worst[0]:.2e} ({worst[1]})")
+    assert worst[0] <= 2e-2, worst
+
+
 def test_no_cpu_fallback():
     from graphgpt_b200 import GraphGPTConfig, GraphGPTPretrainBase
     cfg = GraphGPTConfig(vocab_size=300, hidden_size=64, intermediate_size=256, num_hidden_layers=1, num_attention_heads=1,
