@@ -462,9 +462,11 @@ static int launch_rmsnorm_bwd_bulk(int grid, size_t smem, cudaStream_t s, const 
 }
 
 // =============================================================================================
-// GeGLU backward: dg = dact * u * gelu'(g), du = dact * gelu(g)      (gu = [g | u], bf16)
+// GeGLU backward from the factors saved by the forward epilogue, gf = [u * gelu'(g) | gelu(g)] (bf16):
+//   dgu = [dact * gf[:, 0:I] | dact * gf[:, I:2I]]
+// (the stand-alone form of the fused down_proj-dgrad epilogue; used when dropout sits between the two)
 // =============================================================================================
-__global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ dact, const __nv_bfloat16* __restrict__ gu,
+__global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ dact, const __nv_bfloat16* __restrict__ gf,
                                  __nv_bfloat16* __restrict__ dgu, long long T, int I) {
   const long long groups_per_row = I / 8;
   const long long total = T * groups_per_row;
@@ -473,19 +475,15 @@ __global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ dact, const _
     const long long t = i / groups_per_row;
     const int c = static_cast<int>(i % groups_per_row) * 8;
     const uint4 da = *reinterpret_cast<const uint4*>(dact + t * I + c);
-    const uint4 gv = *reinterpret_cast<const uint4*>(gu + t * 2 * I + c);
-    const uint4 uv = *reinterpret_cast<const uint4*>(gu + t * 2 * I + I + c);
-    const uint32_t dau[4] = {da.x, da.y, da.z, da.w}, gvu[4] = {gv.x, gv.y, gv.z, gv.w}, uvu[4] = {uv.x, uv.y, uv.z, uv.w};
+    const uint4 f1 = *reinterpret_cast<const uint4*>(gf + t * 2 * I + c);
+    const uint4 f2 = *reinterpret_cast<const uint4*>(gf + t * 2 * I + I + c);
+    const uint32_t dau[4] = {da.x, da.y, da.z, da.w}, f1u[4] = {f1.x, f1.y, f1.z, f1.w}, f2u[4] = {f2.x, f2.y, f2.z, f2.w};
     uint32_t og[4], ou[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float2 a = unpack_bf16(dau[j]), g = unpack_bf16(gvu[j]), u = unpack_bf16(uvu[j]);
-      // gelu = g*Phi(g); gelu' = Phi(g) + g*phi(g), both from one exponential (common.cuh gelu_cdf_pdf)
-      float cx, px, cy, py;
-      gelu_cdf_pdf(g.x, cx, px);
-      gelu_cdf_pdf(g.y, cy, py);
-      og[j] = pack_bf16(a.x * u.x * (cx + g.x * px), a.y * u.y * (cy + g.y * py));
-      ou[j] = pack_bf16(a.x * g.x * cx, a.y * g.y * cy);
+      const float2 a = unpack_bf16(dau[j]), p = unpack_bf16(f1u[j]), q = unpack_bf16(f2u[j]);
+      og[j] = pack_bf16(a.x * p.x, a.y * p.y);
+      ou[j] = pack_bf16(a.x * q.x, a.y * q.y);
     }
     *reinterpret_cast<uint4*>(dgu + t * 2 * I + c) = make_uint4(og[0], og[1], og[2], og[3]);
     *reinterpret_cast<uint4*>(dgu + t * 2 * I + I + c) = make_uint4(ou[0], ou[1], ou[2], ou[3]);

@@ -307,6 +307,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           warp_gather_rows32(p.sin_tab, pos, stg, lane, ss);
         }
       }
+      // DGEGLU: saved GeGLU factors of this thread's (row, 4-column) pieces of one 32-column chunk (read-phase layout)
+      uint2 f1[(EPI == EPI_DGEGLU) ? 8 : 1], f2[(EPI == EPI_DGEGLU) ? 8 : 1];
+      auto dgeglu_load = [&](const __nv_bfloat16* gf, int c, uint2 (&o1)[8], uint2 (&o2)[8]) {
+        const int gcol = nb * BN + c + rd_j * 4;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int grow = row0 + it * 4 + rd_row;
+          o1[it] = make_uint2(0u, 0u);
+          o2[it] = make_uint2(0u, 0u);
+          if (grow < p.M && gcol < p.N) {
+            const __nv_bfloat16* src = gf + static_cast<long long>(grow) * p.ldgu + gcol;
+            o1[it] = __ldg(reinterpret_cast<const uint2*>(src));
+            o2[it] = __ldg(reinterpret_cast<const uint2*>(src + p.N));
+          }
+        }
+      };
+      if constexpr (EPI == EPI_DGEGLU)   // chunk 0's factors are fetched while the mainloop of this tile still runs
+        dgeglu_load(reinterpret_cast<const __nv_bfloat16*>(p.gu), half * (BN / 2), f1, f2);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
@@ -388,73 +406,122 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int nh = nb * (BN / 2);
         const int half_n = p.N / 2;
         const int c = half * (BN / 4);
-        __nv_bfloat16* gu = reinterpret_cast<__nv_bfloat16*>(p.C);
-        if (gu != nullptr) {
-#pragma unroll 1
-          for (int part = 0; part < 2; ++part) {          // 0: gate columns, 1: up columns
-            uint32_t r0[32], r1[32];
-            tmem_ld32(taddr + part * (BN / 2) + c, r0);
-            tmem_ld32(taddr + part * (BN / 2) + c + 32, r1);
-            tmem_ld_wait();
-            put_bf16_32(0, r0);
-            put_bf16_32(4, r1);
-            copy_out_bf16(gu, p.ldc, part * half_n + nh + c, part * half_n + half_n);
-          }
-        }
-#pragma unroll 1
-        for (int hh = 0; hh < 2; ++hh) {                  // act = gelu(gate) * up, 32 columns at a time
-          uint32_t rg[32], ru[32];
-          tmem_ld32(taddr + c + hh * 32, rg);
-          tmem_ld32(taddr + BN / 2 + c + hh * 32, ru);
-          tmem_ld_wait();
+        __nv_bfloat16* gf = reinterpret_cast<__nv_bfloat16*>(p.C);
+        if (gf != nullptr) {
+          // training: besides act = gelu(g) * u, store the two factors the backward pass multiplies dact with,
+          //   gf = [ u * gelu'(g) | gelu(g) ]   (gelu = g Phi(g), gelu' = Phi(g) + g phi(g), both from ONE exponential),
+          // so that GeGLU backward is transcendental-free and fits the epilogue of the down_proj dgrad GEMM.
+          uint32_t actp[2][16];
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            rg[j] = __float_as_uint(gelu_erf_fwd(__uint_as_float(rg[j])) * __uint_as_float(ru[j]));
-          put_bf16_32(hh * 4, rg);
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t rg[32], ru[32];
+            tmem_ld32(taddr + c + hh * 32, rg);
+            tmem_ld32(taddr + BN / 2 + c + hh * 32, ru);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              float a1[2], a2[2], ac[2];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const float g = __uint_as_float(rg[j + e]), u = __uint_as_float(ru[j + e]);
+                float cdf, pdf;
+                gelu_cdf_pdf(g, cdf, pdf);
+                a2[e] = g * cdf;
+                a1[e] = u * fmaf(g, pdf, cdf);
+                ac[e] = a2[e] * u;
+              }
+              rg[j >> 1] = pack_bf16(a1[0], a1[1]);          // packed in place: entries [0,16) of rg / ru
+              ru[j >> 1] = pack_bf16(a2[0], a2[1]);
+              actp[hh][j >> 1] = pack_bf16(ac[0], ac[1]);
+            }
+            // staging row = [ 32 cols of u*gelu' (64 B) | 32 cols of gelu (64 B) ]; lanes 0-3 of a row group write the first
+            // factor, lanes 4-7 the second — 64-byte contiguous pieces, two full sectors each
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              stage_put(q, make_uint4(rg[q * 4 + 0], rg[q * 4 + 1], rg[q * 4 + 2], rg[q * 4 + 3]));
+              stage_put(4 + q, make_uint4(ru[q * 4 + 0], ru[q * 4 + 1], ru[q * 4 + 2], ru[q * 4 + 3]));
+            }
+            __syncwarp();
+            {
+              const int fcol = nh + c + hh * 32 + (rd_j & 3) * 8;            // column inside the factor's half
+              __nv_bfloat16* dst = gf + (rd_j >> 2) * half_n + fcol;
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                const int rr = it * 4 + rd_row;
+                if (row0 + rr < p.M && fcol < half_n)
+                  *reinterpret_cast<uint4*>(dst + static_cast<long long>(row0 + rr) * p.ldc) = stage_get(rr);
+              }
+            }
+            __syncwarp();
+          }
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              stage_put(hh * 4 + q, make_uint4(actp[hh][q * 4 + 0], actp[hh][q * 4 + 1], actp[hh][q * 4 + 2], actp[hh][q * 4 + 3]));
+        } else {
+#pragma unroll 1
+          for (int hh = 0; hh < 2; ++hh) {                  // inference: act only, 1-MUFU GELU
+            uint32_t rg[32], ru[32];
+            tmem_ld32(taddr + c + hh * 32, rg);
+            tmem_ld32(taddr + BN / 2 + c + hh * 32, ru);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              rg[j] = __float_as_uint(gelu_erf_fwd(__uint_as_float(rg[j])) * __uint_as_float(ru[j]));
+            put_bf16_32(hh * 4, rg);
+          }
         }
         copy_out_bf16(reinterpret_cast<__nv_bfloat16*>(p.C2), p.ldc2, nh + c, half_n);
       } else if constexpr (EPI == EPI_DGEGLU) {
-        // acc = dact = d(act); fused GeGLU backward: dgate = dact * up * gelu'(gate), dup = dact * gelu(gate)
+        // acc = dact = d(act); fused GeGLU backward with the factors saved by the forward epilogue:
+        //   dgate = dact * gf[:, 0:N] (= u gelu'(g)),  dup = dact * gf[:, N:2N] (= gelu(g))  — two multiplies per element.
+        // The epilogue moves 8 bytes per accumulator element (4 in, 4 out), so it is the factor loads that must be kept
+        // in flight: the loads of chunk k+1 are issued before chunk k is processed (and those of chunk 0 before the
+        // accumulator wait, see above) — they do not depend on the accumulator.
         const int n0 = nb * BN;
-        const __nv_bfloat16* gu = reinterpret_cast<const __nv_bfloat16*>(p.gu);
+        const __nv_bfloat16* gf = reinterpret_cast<const __nv_bfloat16*>(p.gu);
         __nv_bfloat16* dgu = reinterpret_cast<__nv_bfloat16*>(p.C);
-#pragma unroll 1
-        for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
+        constexpr int kChunks = BN / 64;                       // 32-column chunks in this warp's half of the tile
+        const int cbase = half * (BN / 2);
+#pragma unroll
+        for (int k = 0; k < kChunks; ++k) {
+          const int c = cbase + k * 32;
+          const int gcol = n0 + c + rd_j * 4;
+          uint2 n1[8], n2[8];
+          if (k + 1 < kChunks) dgeglu_load(gf, c + 32, n1, n2);
           uint32_t r[32];
           tmem_ld32(taddr + c, r);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 8; ++j) stage_put(j, make_uint4(r[j * 4 + 0], r[j * 4 + 1], r[j * 4 + 2], r[j * 4 + 3]));
           __syncwarp();
-          const int gcol = n0 + c + rd_j * 4;
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int rr = it * 4 + rd_row;
             const int grow = row0 + rr;
             if (grow < p.M && gcol < p.N) {
               const uint4 a4 = stage_get(rr);
-              const uint2 g2 = *reinterpret_cast<const uint2*>(gu + static_cast<long long>(grow) * p.ldgu + gcol);
-              const uint2 u2 = *reinterpret_cast<const uint2*>(gu + static_cast<long long>(grow) * p.ldgu + p.N + gcol);
-              const float2 g01 = unpack_bf16(g2.x), g23 = unpack_bf16(g2.y), u01 = unpack_bf16(u2.x), u23 = unpack_bf16(u2.y);
-              const float av[4] = {__uint_as_float(a4.x), __uint_as_float(a4.y), __uint_as_float(a4.z), __uint_as_float(a4.w)};
-              const float gv[4] = {g01.x, g01.y, g23.x, g23.y};
-              const float uv[4] = {u01.x, u01.y, u23.x, u23.y};
-              float dg[4], du[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float cdf, pdf;
-                gelu_cdf_pdf(gv[j], cdf, pdf);
-                dg[j] = av[j] * uv[j] * fmaf(gv[j], pdf, cdf);
-                du[j] = av[j] * gv[j] * cdf;
-              }
+              const float a0 = __uint_as_float(a4.x), a1 = __uint_as_float(a4.y), a2 = __uint_as_float(a4.z),
+                          a3 = __uint_as_float(a4.w);
+              const float2 p01 = unpack_bf16(f1[it].x), p23 = unpack_bf16(f1[it].y);
+              const float2 q01 = unpack_bf16(f2[it].x), q23 = unpack_bf16(f2[it].y);
+              __nv_bfloat16* dst = dgu + static_cast<long long>(grow) * p.ldc + gcol;
               uint2 o;
-              o.x = pack_bf16(dg[0], dg[1]); o.y = pack_bf16(dg[2], dg[3]);
-              *reinterpret_cast<uint2*>(dgu + static_cast<long long>(grow) * p.ldc + gcol) = o;
-              o.x = pack_bf16(du[0], du[1]); o.y = pack_bf16(du[2], du[3]);
-              *reinterpret_cast<uint2*>(dgu + static_cast<long long>(grow) * p.ldc + p.N + gcol) = o;
+              o.x = pack_bf16(a0 * p01.x, a1 * p01.y); o.y = pack_bf16(a2 * p23.x, a3 * p23.y);
+              *reinterpret_cast<uint2*>(dst) = o;
+              o.x = pack_bf16(a0 * q01.x, a1 * q01.y); o.y = pack_bf16(a2 * q23.x, a3 * q23.y);
+              *reinterpret_cast<uint2*>(dst + p.N) = o;
             }
           }
           __syncwarp();
+          if (k + 1 < kChunks) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              f1[it] = n1[it];
+              f2[it] = n2[it];
+            }
+          }
         }
       } else if constexpr (EPI == EPI_QKV_ROPE) {
         const int n0 = nb * BN;

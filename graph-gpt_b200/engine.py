@@ -325,11 +325,15 @@ class HotPath:
                                          fp.w(p + "lambda_2") if ls else None, st["rs2"], fp.g(p + "lambda_2") if ls else None)
             mlp_p, seed = stash["mlp_pdrop"], stash["drop_seed"]
             ops.dropout_(dyb, mlp_p, mix_seed(seed, _SEED_MLP + i))      # in place: dyb is this block's private bf16 copy
-            # (ops.gemm_dgeglu fuses the next two calls, but its epilogue is slower than the separate HBM-bound kernel:
-            #  measured 0.97 ms vs 0.29 + 0.45 ms per layer on B200, profiles/r1_bench_packed_v8_fused_dgeglu.json)
-            dact = ops.gemm(dyb, fp.wb(p + "mlp.down_proj.weight"), b_mn_major=True)
-            ops.dropout_(dact, mlp_p, mix_seed(seed, _SEED_ACT + i))
-            dgu = ops.geglu_bwd(dact, st["gu"])
+            # down_proj dgrad with the GeGLU backward in its epilogue: the forward stored gf = [u gelu'(g) | gelu(g)], so the
+            # epilogue is two multiplies per element and dact never goes to HBM.  With mlp dropout the mask sits between
+            # the GEMM and the multiply, so the two steps run separately.
+            if mlp_p > 0:
+                dact = ops.gemm(dyb, fp.wb(p + "mlp.down_proj.weight"), b_mn_major=True)
+                ops.dropout_(dact, mlp_p, mix_seed(seed, _SEED_ACT + i))
+                dgu = ops.geglu_bwd(dact, st["gu"])
+            else:
+                dgu = ops.gemm_dgeglu(dyb, fp.wb(p + "mlp.down_proj.weight"), st["gu"])
             ops.gemm(dyb, st["act"], out=fp.g(p + "mlp.down_proj.weight"), **wgrad)
             ops.gemm(dgu, st["h2"], out=self._ggu(i), **wgrad)
             dh2 = ops.gemm(dgu, self._wgu(i), b_mn_major=True)

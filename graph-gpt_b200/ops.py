@@ -79,7 +79,8 @@ def gemm_resid(a, w, resid, *, colscale=None, rowscale=None, out=None):
 
 
 def gemm_geglu(a, wgu, *, want_gu=True):
-    """wgu = [gate_proj.weight ; up_proj.weight] ([2I, K]).  Returns (gu [M,2I] or None, act [M,I])."""
+    """wgu = [gate_proj.weight ; up_proj.weight] ([2I, K]).  Returns (gf [M,2I] or None, act [M,I]) with
+    act = gelu(g) * u and gf = [u * gelu'(g) | gelu(g)], the factors GeGLU backward multiplies dact with."""
     _check(a, BF16, "gemm_geglu a", 2)
     _check(wgu, BF16, "gemm_geglu wgu", 2)
     M, K = a.shape
@@ -92,7 +93,8 @@ def gemm_geglu(a, wgu, *, want_gu=True):
 
 
 def gemm_dgeglu(dy, wd, gu):
-    """dgu[M,2I] = GeGLU backward of (dy @ wd) with the saved gu = [gate | up]; wd = down_proj.weight [d, I]."""
+    """dgu[M,2I] = [dact * gf[:, :I] | dact * gf[:, I:]] with dact = dy @ wd (never stored); gf = the factors saved by
+    gemm_geglu, wd = down_proj.weight [d, I]."""
     _check(dy, BF16, "gemm_dgeglu dy", 2)
     _check(wd, BF16, "gemm_dgeglu wd", 2)
     _check(gu, BF16, "gemm_dgeglu gu", 2)

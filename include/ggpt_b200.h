@@ -50,15 +50,16 @@ int ggpt_gemm_bf16_resid(const void* A, long long lda, const void* B, long long 
                          int M, int N, int K, void* stream);
 
 /* Fused gate|up projection with GeGLU epilogue.  Wgu is [2I, K]: rows [0,I) = gate_proj.weight, rows [I,2I) =
- * up_proj.weight.  Writes gu[M,2I] = [gate | up] (bf16, may be NULL for inference) and
- * act[M,I] = gelu_erf(gate) * up (bf16).   ref: HF:182-184 with hidden_act="gelu" (exact erf GELU). */
-int ggpt_gemm_bf16_geglu(const void* A, long long lda, const void* Wgu, long long ldb, void* gu, long long ldgu,
+ * up_proj.weight.  Writes act[M,I] = gelu_erf(gate) * up (bf16) and, when gf != NULL (training), the two factors GeGLU
+ * backward multiplies d(act) with: gf[M,2I] = [ up * gelu'(gate) | gelu(gate) ] (bf16) — gate and up themselves are not
+ * needed again.   ref: HF:182-184 with hidden_act="gelu" (exact erf GELU). */
+int ggpt_gemm_bf16_geglu(const void* A, long long lda, const void* Wgu, long long ldb, void* gf, long long ldgf,
                          void* act, long long ldact, int M, int N2, int K, void* stream);
 
-/* Fused down_proj dgrad + GeGLU backward: dact = dy[M,K] * Wd[K,I] (Wd = down_proj.weight [d, I] read in place) and,
- * in the epilogue, dgu[M,2I] = [dact*up*gelu'(gate) | dact*gelu(gate)] from the saved gu = [gate | up].
+/* Fused down_proj dgrad + GeGLU backward: dact = dy[M,K] * Wd[K,I] (Wd = down_proj.weight [d, I] read in place) stays
+ * in TMEM and the epilogue writes dgu[M,2I] = [ dact * gf[:,0:I] | dact * gf[:,I:2I] ] from the saved factors.
  * ref: autograd of HF:182-184 (down_proj, erf GELU, gate*up). */
-int ggpt_gemm_bf16_dgeglu(const void* dy, long long lda, const void* Wd, long long ldb, const void* gu, long long ldgu,
+int ggpt_gemm_bf16_dgeglu(const void* dy, long long lda, const void* Wd, long long ldb, const void* gf, long long ldgf,
                           void* dgu, long long lddgu, int M, int I, int K, void* stream);
 
 /* Fused q|k|v projection with rotary embedding applied to the first rope_cols columns (q and k heads of 64).
@@ -189,8 +190,10 @@ int ggpt_add_rmsnorm_fwd(const float* x_in, const void* y, long long ldy, const 
 int ggpt_rmsnorm_bwd(const void* dy, long long lddy, const float* x, const float* rstd, const float* w,
                      const float* dresid, float* dx_out, void* dx_bf16, float* dw, long long T, int d, void* stream);
 
-/* dgu = [dact*u*gelu'(g) | dact*gelu(g)] for gu = [g | u].   ref: autograd of HF:182-184 with erf GELU */
-int ggpt_geglu_bwd(const void* dact, const void* gu, void* dgu, long long T, int I, void* stream);
+/* dgu = [dact * gf[:,0:I] | dact * gf[:,I:2I]] for the saved factors gf = [u*gelu'(g) | gelu(g)] — the stand-alone form of
+ * the ggpt_gemm_bf16_dgeglu epilogue (used when dropout sits between the dgrad GEMM and the multiply).
+ * ref: autograd of HF:182-184 with erf GELU */
+int ggpt_geglu_bwd(const void* dact, const void* gf, void* dgu, long long T, int I, void* stream);
 
 /* Loss-head compaction without host-side boolean indexing.  labels int64 [T,F] (-100 = ignore).
  * counts[0] = M rows with >= 1 label, counts[1] = L labelled entries; sel_rows[M] token index per selected row;

@@ -45,8 +45,10 @@ def worker():
         "fwd o_proj   [T,768]x[768,768]": (lambda: ops.gemm(x, w_o), 2 * T * d * d, lambda y: relerr(y, x.float() @ w_o.float().t())),
         "fwd down     [T,3072]x[768,3072]": (lambda: ops.gemm(xi, w_d), 2 * T * d * I, lambda y: relerr(y, xi.float() @ w_d.float().t())),
         "fwd qkv+rope [T,768]x[2304,768]": (lambda: ops.gemm_qkv_rope(x, w_qkv, pos, cos, sin, 2 * d), 2 * T * 3 * d * d, None),
-        "fwd geglu    [T,768]x[6144,768]": (lambda: ops.gemm_geglu(x, w_gu, want_gu=True)[0], 2 * T * 2 * I * d,
-                                           lambda y: relerr(y, x.float() @ w_gu.float().t())),
+        "fwd geglu    [T,768]x[6144,768]": (lambda: ops.gemm_geglu(x, w_gu, want_gu=True)[0], 2 * T * 2 * I * d, None),
+        "fwd geglu (inference epilogue)": (lambda: ops.gemm_geglu(x, w_gu, want_gu=False)[1], 2 * T * 2 * I * d, None),
+        "dgrad down + GeGLU bwd (fused epilogue)": (lambda: ops.gemm_dgeglu(x, w_d, x6), 2 * T * d * I, None),
+        "geglu_bwd stand-alone kernel": (lambda: ops.geglu_bwd(xi, x6), 0, None),
         "dgrad d->d   dy[T,768] W[768,768]": (lambda: ops.gemm(x, w_o, b_mn_major=True), 2 * T * d * d, lambda y: relerr(y, x.float() @ w_o.float())),
         "dgrad qkv    dy[T,2304] W[2304,768]": (lambda: ops.gemm(x3, w_qkv, b_mn_major=True), 2 * T * 3 * d * d, lambda y: relerr(y, x3.float() @ w_qkv.float())),
         "dgrad down   dy[T,768] W[768,3072]": (lambda: ops.gemm(x, w_d, b_mn_major=True), 2 * T * d * I, lambda y: relerr(y, x.float() @ w_d.float())),
