@@ -54,8 +54,12 @@ def warmup_decay_lr(step, *, max_lr, min_lr=0.0, warmup_steps=0, total_steps=1):
 
 class GraphGPTEngine:
     def __init__(self, model, *, lr=3e-4, betas=(0.9, 0.95), eps=1e-6, weight_decay=0.1, max_grad_norm=1.0,
-                 lr_schedule=None, process_group=None, overlap_comm=True):
+                 lr_schedule=None, process_group=None, overlap_comm=True, gradient_accumulation_steps=1):
         self.module = model
+        # DeepSpeed semantics (ds_config["gradient_accumulation_steps"], conf_utils.py:62-65): backward() scales the loss
+        # by 1/gas and accumulates; the gradient exchange and the optimizer run on every gas-th step() only
+        self.gas = max(1, int(gradient_accumulation_steps))
+        self.micro_steps = 0
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.max_grad_norm = max_grad_norm
         self.lr_schedule = lr_schedule
@@ -100,8 +104,18 @@ class GraphGPTEngine:
     def parameters(self):
         return self.module.parameters()
 
+    def is_gradient_accumulation_boundary(self):
+        return (self.micro_steps + 1) % self.gas == 0
+
     def backward(self, loss):
         hot = self.module._hot
+        boundary = self.is_gradient_accumulation_boundary()
+        if self.gas > 1:
+            loss = loss / self.gas
+        if not boundary:                      # accumulate locally; nothing is exchanged until the boundary micro-step
+            hot.grad_ready_hook = None
+            loss.backward()
+            return
         self.reducer = GradReducer(self.flat.flat_grad, self.group)
         if self.world > 1 and self.overlap_comm:
             hot.grad_ready_hook = lambda first, last: self.reducer.reduce_span(*self.flat.span(first, last))
@@ -115,6 +129,9 @@ class GraphGPTEngine:
             self.reducer.reduce_span(0, self.flat.numel)
 
     def step(self):
+        self.micro_steps += 1
+        if self.micro_steps % self.gas != 0:
+            return                            # not a boundary: gradients keep accumulating in the flat buffer
         self.global_steps += 1
         fp = self.flat
         self.reducer.wait()

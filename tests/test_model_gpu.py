@@ -239,6 +239,44 @@ def test_full_size_c2_packing_invariance_and_batch_linearity():
     assert worst[0] <= 2e-2, worst
 
 
+def test_engine_gradient_accumulation_follows_deepspeed_semantics():
+    """gradient_accumulation_steps = 2 (ds_config, conf_utils.py:62-65): backward() scales each micro-batch loss by 1/2 and
+    accumulates into the flat gradient buffer, step() is a no-op on the first micro-step and applies AdamW on the
+    second; the accumulated gradient equals the mean of the two micro-batch gradients."""
+    import copy
+    from graphgpt_b200 import GraphGPTConfig, GraphGPTPretrainBase, synth
+    from graphgpt_b200.dp import GraphGPTEngine
+    cfgd = dict(vocab_size=756, hidden_size=128, intermediate_size=512, num_hidden_layers=2, num_attention_heads=2,
+                num_key_value_heads=2, head_dim=64, hidden_act="gelu", max_position_embeddings=1024, rms_norm_eps=1e-6,
+                rope_theta=10000.0, pad_token_id=0, causal_attention=False, stacked_feat=13, stack_method="short",
+                stacked_feat_agg_method="sum", next_n_token=13, use_cache=False, attention_dropout=0.0)
+    torch.manual_seed(0)
+    model = GraphGPTPretrainBase(GraphGPTConfig(**cfgd)).cuda().train()
+    probe = copy.deepcopy(model)
+    batches = []
+    for seed in (61, 62):
+        b = synth.make_batch(2, 256, layout="packed", seed=seed)
+        batches.append({k: torch.from_numpy(b[k]).cuda() for k in ("input_ids", "attention_mask", "labels")})
+    grads = []
+    for b in batches:                                   # reference gradients of each micro-batch, plain autograd surface
+        probe.zero_grad(set_to_none=True)
+        probe(**b).head1_loss.backward()
+        grads.append({k: p.grad.clone() for k, p in probe.named_parameters()})
+    engine = GraphGPTEngine(model, lr=1e-3, max_grad_norm=0.0, gradient_accumulation_steps=2)
+    w0 = {k: p.detach().clone() for k, p in model.named_parameters()}
+    engine.backward(engine(**batches[0]).head1_loss)
+    engine.step()
+    assert engine.global_steps == 0 and all(torch.equal(p.detach(), w0[k]) for k, p in model.named_parameters())
+    engine.backward(engine(**batches[1]).head1_loss)
+    acc = {k: p.grad.clone() for k, p in model.named_parameters()}
+    worst = max(_relf(acc[k], 0.5 * (grads[0][k] + grads[1][k])) for k in acc)
+    assert worst <= 1e-2, worst                          # (bf16 rounding of the 1/2-scaled backward signal)
+    engine.step()
+    assert engine.global_steps == 1 and engine.micro_steps == 2
+    assert any(not torch.equal(p.detach(), w0[k]) for k, p in model.named_parameters())
+    assert all(p.grad is None for p in model.parameters())
+
+
 def test_no_cpu_fallback():
     from graphgpt_b200 import GraphGPTConfig, GraphGPTPretrainBase
     cfg = GraphGPTConfig(vocab_size=300, hidden_size=64, intermediate_size=256, num_hidden_layers=1, num_attention_heads=1,
