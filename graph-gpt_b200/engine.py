@@ -18,6 +18,8 @@ import torch
 from . import ops
 
 BF16, F32 = torch.bfloat16, torch.float32
+# GGPT_DGEGLU_FUSED=0 runs GeGLU backward as the stand-alone multiply kernel after a plain down_proj dgrad GEMM (A/B aid)
+_FUSE_DGEGLU = __import__("os").environ.get("GGPT_DGEGLU_FUSED", "1") != "0"
 
 
 def _align(n, a=128):
@@ -328,7 +330,7 @@ class HotPath:
             # down_proj dgrad with the GeGLU backward in its epilogue: the forward stored gf = [u gelu'(g) | gelu(g)], so the
             # epilogue is two multiplies per element and dact never goes to HBM.  With mlp dropout the mask sits between
             # the GEMM and the multiply, so the two steps run separately.
-            if mlp_p > 0:
+            if mlp_p > 0 or not _FUSE_DGEGLU:
                 dact = ops.gemm(dyb, fp.wb(p + "mlp.down_proj.weight"), b_mn_major=True)
                 ops.dropout_(dact, mlp_p, mix_seed(seed, _SEED_ACT + i))
                 dgu = ops.geglu_bwd(dact, st["gu"])

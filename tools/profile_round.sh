@@ -14,9 +14,10 @@ ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $out/
 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
     --kernel-name-base demangled -k regex:gemm_kernel -s 151 -c 151 --csv --log-file $out/${tag}_gemm_traffic.csv \
     python bench.py --steps 1 --warmup 1 --batches 1 --no-e2e --no-cpu-baseline > $out/${tag}_ncu_traffic.log 2>&1
+python tools/gemm_traffic_json.py $out/${tag}_gemm_traffic.csv > $out/${tag}_gemm_traffic_summary.json && cp profiles/r1_gemm_traffic.json $out/r1_gemm_traffic.json
 # full-set capture around the forward/backward boundary of the timed step
 ncu --set full --clock-control none --kernel-name-base demangled \
-    -k "regex:gemm_kernel|attn_diag|attn_fwd_kernel|attn_bwd_kernel|rmsnorm_bwd_kernel|geglu_bwd_kernel|rmsnorm_fwd_kernel" \
+    -k "regex:gemm_kernel|attn_diag|attn_fwd_kernel|attn_bwd_kernel|rmsnorm_bwd|add_rmsnorm_fwd_kernel|rmsnorm_fwd_kernel" \
     -s 262 -c 36 -o /tmp/${tag}_full python bench.py --steps 1 --warmup 1 --batches 1 --no-e2e --no-cpu-baseline > $out/${tag}_ncu_full.log 2>&1
 tools/ncu_extract.sh /tmp/${tag}_full.ncu-rep $out/${tag}_ncu_full
 sz=$(stat -c %s /tmp/${tag}_full.ncu-rep 2>/dev/null || echo 999999999)
