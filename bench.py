@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--seqs", type=int, default=64, help="sequences of 1024 tokens per GPU per step")
     ap.add_argument("--layout", default="packed", choices=["packed", "dense"])
     ap.add_argument("--batches", type=int, default=4, help="distinct synthetic batches cycled through")
+    ap.add_argument("--mask-format", default="reference", choices=["reference", "segments"],
+                    help="packed layout only: 'reference' = the collator's int64 [N,S,S] block-diagonal mask (default, the "
+                         "reference-facing contract); 'segments' = the [N,S] segment-id mask of graphgpt_b200.packing")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--fwd-only", action="store_true", help="also report the forward-only pass (inference mode)")
@@ -122,7 +125,8 @@ def run_reference(args):
 
 
 def workload_name(args):
-    return f"pcqm4m-v2-smtp-pretrain-B12(12L/768d/F13/V756)-seq1024-{args.layout}"
+    suffix = "-segment-id-mask" if (args.layout == "packed" and getattr(args, "mask_format", "reference") == "segments") else ""
+    return f"pcqm4m-v2-smtp-pretrain-B12(12L/768d/F13/V756)-seq1024-{args.layout}{suffix}"
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -180,6 +184,12 @@ def run_b200(args):
     for i in range(args.batches):
         b = synth.make_batch(args.seqs, SEQ, layout=args.layout, seed=1234 + 1000 * rank + i, return_segments=True)
         stats.append(batch_stats(b, args.layout))
+        if args.layout == "packed" and args.mask_format == "segments":
+            import numpy as np
+            seg = np.zeros((args.seqs, SEQ), np.int64)
+            for n_, lens in enumerate(b["segment_lens"]):
+                seg[n_] = np.repeat(np.arange(1, len(lens) + 1), lens)[:SEQ]
+            b["attention_mask"] = seg
         host.append({k: torch.from_numpy(b[k]).pin_memory() for k in ("input_ids", "attention_mask", "labels")})
     tok_per_step = args.seqs * SEQ                                   # packed / dense layouts have no pad tokens
     st = {k: sum(s[k] for s in stats) / len(stats) for k in stats[0]}

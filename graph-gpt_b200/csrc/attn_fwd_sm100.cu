@@ -332,8 +332,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
 // Mask preparation: int64 attention_mask ([N,S] key mask or [N,S,S]) (+ causal) -> bit matrix + tile classes
 // ref: modeling_helpers.py:38-64 (_update_causal_mask / _expand_mask_from_3d_mask), HF:398-405 (causal)
 // ---------------------------------------------------------------------------------------------
+// kind[n] = 1 when the [N,S] mask of sequence n carries segment ids (some value >= 2), else 0 (plain 0/1 key mask)
+__global__ void attn_mask_kind_kernel(const long long* __restrict__ am, int S, int* __restrict__ kind) {
+  __shared__ int any;
+  if (threadIdx.x == 0) any = 0;
+  __syncthreads();
+  const long long* row = am + static_cast<long long>(blockIdx.x) * S;
+  bool mine = false;
+  for (int k = threadIdx.x; k < S; k += blockDim.x) mine |= (row[k] >= 2);
+  if (mine) atomicOr(&any, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) kind[blockIdx.x] = any;
+}
+
 __global__ void attn_mask_bits_kernel(const long long* __restrict__ am, int am_dims, int N, int S, int causal,
-                                      int mask_words, uint32_t* __restrict__ bits) {
+                                      int mask_words, uint32_t* __restrict__ bits, const int* __restrict__ kind) {
   // one warp per (n, q, group of 4 words = 128 keys): four independent 8-byte loads per lane are in flight at once
   // (the [N,S,S] int64 mask of a packed batch is 537 MB per step — this pass is pure HBM streaming)
   const long long gw = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -353,11 +366,21 @@ __global__ void attn_mask_bits_kernel(const long long* __restrict__ am, int am_d
     if (k < S && am != nullptr)
       v[i] = (am_dims == 2) ? am[static_cast<long long>(n) * S + k] : am[(static_cast<long long>(n) * S + q) * S + k];
   }
+  // [N,S] masks: 0/1 = the reference's key-padding mask (every query, pad rows included, sees the non-zero keys).
+  // A sequence whose mask holds values >= 2 carries SEGMENT IDS of a packed sequence (ggpt_pack_sequences): a query
+  // sees exactly the keys of its own segment and pad rows (id 0) see nothing, i.e. the block-diagonal [N,S,S] mask of
+  // tokenizer_utils.py:351-355 without materialising it.
+  bool q_all = true;          // this query row sees every non-zero key
+  long long aq = 0;
+  if (am_dims == 2 && am != nullptr && kind != nullptr && kind[n] != 0) {
+    aq = am[static_cast<long long>(n) * S + q];
+    q_all = false;
+  }
   uint32_t word[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int k = (w0 + i) * 32 + lane;
-    const bool keep = (k < S) && (v[i] != 0) && !(causal && k > q);
+    const bool keep = (k < S) && (v[i] != 0) && (q_all || aq == v[i]) && !(causal && k > q);
     word[i] = __ballot_sync(0xffffffffu, keep);
   }
   if (lane == 0) *reinterpret_cast<uint4*>(bits + nq * mask_words + w0) = make_uint4(word[0], word[1], word[2], word[3]);
@@ -478,8 +501,14 @@ int ggpt_attn_mask_build(const long long* attention_mask, int mask_dims, int N, 
   const int mt = ggpt_attn_max_tiles(S);
   const long long warps = static_cast<long long>(N) * S * (words / 4);
   const long long blocks = (warps * 32 + 255) / 256;
+  const int* kind = nullptr;
+  if (mask_dims == 2 && attention_mask != nullptr) {   // n_tiles doubles as the per-sequence scratch until the plan kernel fills it
+    attn_mask_kind_kernel<<<N, 256, 0, s>>>(attention_mask, S, n_tiles);
+    if (int rc = check_launch("attn_mask_kind_kernel")) return rc;
+    kind = n_tiles;
+  }
   attn_mask_bits_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(attention_mask, mask_dims, N, S, causal, words,
-                                                                       mask_bits);
+                                                                       mask_bits, kind);
   if (int rc = check_launch("attn_mask_bits_kernel")) return rc;
   const size_t plan_smem = 2 * static_cast<size_t>(S) * sizeof(int);
   static bool attr_set = false;

@@ -200,6 +200,63 @@ __global__ void dropout_scale_f32_kernel(float* __restrict__ out, long long n, D
     out[e] = dp.thresh != 0u ? edrop_scale1(dp, static_cast<unsigned long long>(e)) : 1.0f;
 }
 
+// =============================================================================================
+// Device-side sequence packer.  Packed sequence n is the concatenation of the graphs
+// seq_graphs[cu_seq[n] .. cu_seq[n+1]), each followed by ONE separator row (the reference's <eos> row: pack_token_seq
+// appends `seps` between graphs and prepare_inputs_for_pretrain_mlm appends the final one — tokenizer.py:359-415,
+// tokenizer_utils.py:228-233,246), truncated to S rows (collator: val[:pad_to]) and padded with pad_id.
+// Output: input_ids [N,S,F] and the segment id of every row (1-based, 0 = pad) — the [N,S] form of the block-diagonal
+// attention mask of tokenizer_utils.py:351-355 that ggpt_attn_mask_build understands.  One CTA per packed sequence.
+// =============================================================================================
+constexpr int kPackMaxGraphs = 4096;
+__global__ void __launch_bounds__(256) pack_sequences_kernel(const long long* __restrict__ rows, int F,
+                                                             const int* __restrict__ cu_rows,
+                                                             const int* __restrict__ seq_graphs,
+                                                             const int* __restrict__ cu_seq, int S,
+                                                             const long long* __restrict__ sep_row, long long pad_id,
+                                                             long long* __restrict__ input_ids,
+                                                             long long* __restrict__ seg_ids,
+                                                             long long* __restrict__ position_ids,
+                                                             int* __restrict__ n_valid) {
+  __shared__ int seg_end[kPackMaxGraphs];
+  __shared__ int n_seg;
+  const int n = blockIdx.x;
+  const int g0 = cu_seq[n], g1 = cu_seq[n + 1];
+  if (threadIdx.x == 0) {
+    int tot = 0, k = 0;
+    for (int g = g0; g < g1 && k < kPackMaxGraphs && tot < S; ++g, ++k) {
+      const int gi = seq_graphs[g];
+      tot += cu_rows[gi + 1] - cu_rows[gi] + 1;           // the graph's rows + its separator row
+      seg_end[k] = tot;
+    }
+    n_seg = k;
+    if (n_valid != nullptr) n_valid[n] = min(tot, S);
+  }
+  __syncthreads();
+  const int ns = n_seg;
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    int lo = 0, hi = ns;                                  // first segment whose end is > s
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (seg_end[mid] > s) hi = mid; else lo = mid + 1;
+    }
+    long long* dst = input_ids + (static_cast<long long>(n) * S + s) * F;
+    long long seg = 0;
+    if (lo < ns) {
+      const int start = lo == 0 ? 0 : seg_end[lo - 1];
+      const int gi = seq_graphs[g0 + lo];
+      const int r0 = cu_rows[gi], nr = cu_rows[gi + 1] - r0;
+      const long long* src = (s - start < nr) ? rows + static_cast<long long>(r0 + s - start) * F : sep_row;
+      for (int f = 0; f < F; ++f) dst[f] = src[f];
+      seg = lo + 1;
+    } else {
+      for (int f = 0; f < F; ++f) dst[f] = pad_id;
+    }
+    seg_ids[static_cast<long long>(n) * S + s] = seg;
+    if (position_ids != nullptr) position_ids[static_cast<long long>(n) * S + s] = s;
+  }
+}
+
 }  // namespace ggpt
 
 using namespace ggpt;
@@ -258,6 +315,16 @@ int ggpt_layerscale_bwd(const float* dx, const float* x_out, const float* x_in, 
   else if (nv <= 8) layerscale_bwd_kernel<8><<<grid, 256, sm, s>>>(dx, x_out, x_in, lam, rowscale, dyb, dlam, T, d);
   else layerscale_bwd_kernel<16><<<grid, 256, sm, s>>>(dx, x_out, x_in, lam, rowscale, dyb, dlam, T, d);
   return check_launch("layerscale_bwd_kernel");
+}
+
+int ggpt_pack_sequences(const long long* rows, int F, const int* cu_rows, const int* seq_graphs, const int* cu_seq, int N,
+                        int S, const long long* sep_row, long long pad_id, long long* input_ids, long long* seg_ids,
+                        long long* position_ids, int* n_valid, void* stream) {
+  GGPT_REQUIRE(rows && cu_rows && seq_graphs && cu_seq && sep_row && input_ids && seg_ids, "pack_sequences: null pointer");
+  GGPT_REQUIRE(N > 0 && S > 0 && F > 0, "pack_sequences: bad sizes N=%d S=%d F=%d", N, S, F);
+  pack_sequences_kernel<<<N, 256, 0, static_cast<cudaStream_t>(stream)>>>(rows, F, cu_rows, seq_graphs, cu_seq, S, sep_row,
+                                                                           pad_id, input_ids, seg_ids, position_ids, n_valid);
+  return check_launch("pack_sequences_kernel");
 }
 
 int ggpt_dropout_bf16(void* x, long long n, float p, unsigned long long seed, void* stream) {

@@ -78,8 +78,10 @@ int ggpt_gemm_bf16_qkv_rope(const void* A, long long lda, const void* Wqkv, long
 int ggpt_attn_mask_words(int S);
 int ggpt_attn_max_tiles(int S);
 
-/* attention_mask: int64 [N,S] (key padding mask) if mask_dims == 2, [N,S,S] if 3, or NULL (all visible);
- * causal != 0 additionally hides keys k > q.  Outputs:
+/* attention_mask: int64 [N,S] if mask_dims == 2, [N,S,S] if 3, or NULL (all visible); causal != 0 additionally hides
+ * keys k > q.  An [N,S] mask of 0/1 values is the reference's key-padding mask (every query sees the non-zero keys); a
+ * sequence whose [N,S] mask holds values >= 2 carries the SEGMENT IDS written by ggpt_pack_sequences (1-based, 0 = pad)
+ * and expands to the block-diagonal mask — query q sees key k iff both lie in the same non-zero segment.  Outputs:
  *   mask_bits  [N,S,words]            1 bit per (q,k)
  *   tile_start [N,max_tiles+1], n_tiles [N]   variable row tiles (<= 128 rows, cut on block boundaries of the mask so
  *                                     packed segments never straddle a tile; uniform 128 grid otherwise)
@@ -168,6 +170,17 @@ int ggpt_raw_embed_norm_bwd(const void* dh, long long lddh, const float* raw, co
  * the reduction (then x_out / x_in may be NULL).   ref: autograd of utils_graphgpt.py:153-166. */
 int ggpt_layerscale_bwd(const float* dx, const float* x_out, const float* x_in, const float* lam, const float* rowscale,
                         void* dy, float* dlam, long long T, int d, void* stream);
+
+/* Device-side sequence packer.  rows int64 [R,F] = the token rows of a pool of graphs, graph g owning rows
+ * [cu_rows[g], cu_rows[g+1]); packed sequence n = graphs seq_graphs[cu_seq[n] .. cu_seq[n+1]) in order, each followed by
+ * one separator row sep_row[F] (<eos>), truncated to S rows, padded with pad_id (at most 4096 graphs per sequence).
+ * Writes input_ids [N,S,F], seg_ids int64 [N,S] (1-based segment per row, 0 = pad: pass it as the [N,S] attention_mask —
+ * ggpt_attn_mask_build expands segment ids to the block-diagonal mask), position_ids [N,S] = 0..S-1 (may be NULL) and
+ * n_valid[N] non-pad rows (may be NULL).
+ * ref: tokenizer.py:359-415 (pack_token_seq), tokenizer_utils.py:228-233,351-355 (final <eos>, block_diag mask). */
+int ggpt_pack_sequences(const long long* rows, int F, const int* cu_rows, const int* seq_graphs, const int* cu_seq, int N,
+                        int S, const long long* sep_row, long long pad_id, long long* input_ids, long long* seg_ids,
+                        long long* position_ids, int* n_valid, void* stream);
 
 /* Element dropout on activations, training only (config.mlp_pdrop: GeGLU output and down_proj output; embed_pdrop:
  * normalised raw embeddings).  x (bf16, n contiguous elements, 16-byte aligned) is scaled in place by keep(e)/(1-p);

@@ -232,3 +232,50 @@ def test_ppa_finetune_training_mode_droppath_layerscale_matches_oracle():
     assert abs(out.task_loss.item() - ref["loss"].item()) / ref["loss"].item() <= 1e-2
     worst = max((_relf(p_.grad, sd_ref[k].grad), k) for k, p_ in model.named_parameters() if sd_ref[k].grad is not None)
     assert worst[0] <= 3e-2, worst
+
+
+def test_device_packer_matches_oracle_and_segment_mask_equals_block_diagonal():
+    """ggpt_pack_sequences against oracle/packing_oracle.py (bit-exact), and the [N,S] segment-id mask it emits against
+    the reference's [N,S,S] block-diagonal mask: the model must produce bit-identical logits and loss with either."""
+    import numpy as np
+    from graphgpt_b200 import GraphGPTConfig, GraphGPTPretrainBase, ops
+    from graphgpt_b200.packing import pack_sequences, plan_greedy
+    from oracle import graphgpt_oracle as oracle
+    from oracle import packing_oracle as po
+    rng = np.random.default_rng(3)
+    F_, S = 13, 256
+    lengths = rng.integers(4, 40, size=150)
+    lengths[7] = 300                                               # one graph longer than a whole sequence
+    graphs = [rng.integers(22, 756, size=(L, F_)) for L in lengths]
+    rows = torch.from_numpy(np.concatenate(graphs)).cuda()
+    cu_rows = np.concatenate([[0], np.cumsum(lengths)])
+    seq_graphs, cu_seq = plan_greedy(lengths, S)
+    sep = [19] * F_
+    out = pack_sequences(rows, cu_rows, seq_graphs, cu_seq, S, sep)
+    N = len(cu_seq) - 1
+    am3 = np.zeros((N, S, S), np.int64)
+    for n in range(N):
+        ids, am, seg = po.pack_one([graphs[g] for g in seq_graphs[cu_seq[n]:cu_seq[n + 1]]], sep, S)
+        assert np.array_equal(out["input_ids"][n].cpu().numpy(), ids)
+        assert np.array_equal(out["attention_mask"][n].cpu().numpy(), seg)
+        assert int(out["n_valid"][n]) == int((seg > 0).sum())
+        am3[n] = am
+    assert torch.equal(out["position_ids"].cpu(), torch.arange(S).expand(N, S))
+    # mask bits from segment ids == mask bits from the [N,S,S] tensor
+    m_seg = ops.attn_mask_build(out["attention_mask"], N, S, False, rows.device)
+    m_3d = ops.attn_mask_build(torch.from_numpy(am3).cuda(), N, S, False, rows.device)
+    valid = out["attention_mask"] > 0
+    assert torch.equal(m_seg.bits, m_3d.bits) and torch.equal(m_seg.cls, m_3d.cls)     # pad rows included: they see nothing
+    assert torch.equal(m_seg.iso_count, m_3d.iso_count)
+    # ... and the model agrees bit for bit on every labelled entry
+    cfgd = _cfg()
+    model = GraphGPTPretrainBase(GraphGPTConfig(**cfgd))
+    model.load_state_dict(oracle.init_state_dict(cfgd, seed=2), strict=True)
+    model = model.cuda().eval()
+    labels = torch.where((torch.rand(N, S, F_, device="cuda") < 0.4) & valid[:, :, None], out["input_ids"],
+                         torch.full_like(out["input_ids"], -100))
+    ids_in = torch.where(labels != -100, torch.ones_like(labels), out["input_ids"])
+    with torch.no_grad():
+        a = model(input_ids=ids_in, attention_mask=out["attention_mask"], labels=labels)
+        b = model(input_ids=ids_in, attention_mask=torch.from_numpy(am3).cuda(), labels=labels)
+    assert torch.equal(a.head1_logits, b.head1_logits) and a.head1_loss.item() == b.head1_loss.item()

@@ -180,3 +180,30 @@ def test_grad_reducer_gloo_world2(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "ok" in o
+
+
+def test_packing_oracle_and_greedy_plan():
+    """oracle/packing_oracle.py against an independent scipy block_diag construction, and plan_greedy against the
+    reference's `while token_len < mpe` rule (tokenizer.py:366-371)."""
+    import numpy as np
+    from scipy.linalg import block_diag
+    from graphgpt_b200.packing import plan_greedy
+    from oracle import packing_oracle as po
+    rng = np.random.default_rng(0)
+    lengths = rng.integers(3, 30, size=40)
+    graphs = [rng.integers(22, 700, size=(L, 5)) for L in lengths]
+    sep = [19] * 5
+    seq_graphs, cu_seq = plan_greedy(lengths, 64)
+    assert cu_seq[0] == 0 and cu_seq[-1] == len(seq_graphs) == 40
+    for n in range(len(cu_seq) - 1):
+        gs = seq_graphs[cu_seq[n]:cu_seq[n + 1]]
+        run = np.cumsum([lengths[g] + 1 for g in gs])
+        assert all(r < 64 for r in run[:-1])                       # kept appending while below mpe
+        assert run[-1] >= 64 or n == len(cu_seq) - 2               # ... and stopped at the first length >= mpe
+        ids, am, seg = po.pack_one([graphs[g] for g in gs], sep, 64)
+        want = block_diag(*[np.ones((lengths[g] + 1,) * 2, dtype=np.int64) for g in gs])[:64, :64]
+        k = want.shape[0]
+        assert np.array_equal(am[:k, :k], want) and am[k:].sum() == 0 and am[:, k:].sum() == 0
+        assert np.array_equal(am, (seg[:, None] == seg[None, :]) & (seg[:, None] > 0))
+        flat = np.concatenate([np.vstack([graphs[g], np.asarray(sep)[None]]) for g in gs])[:64]
+        assert np.array_equal(ids[:len(flat)], flat) and (ids[len(flat):] == 0).all()
