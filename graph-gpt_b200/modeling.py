@@ -451,19 +451,20 @@ GraphGPTForCausalLM = GraphGPTPretrainBase
 
 
 class _ScoreMLP(nn.Module):
-    """src/utils/modules_utils.py:8-34 — optional MLP score head: Linear, then (act, dropout, Linear)*."""
+    """src/utils/modules_utils.py:8-34 — optional MLP score head.  As in the reference, EVERY Linear (the first included) is
+    preceded by the activation and the dropout, and all of them share the `bias` flag."""
 
-    def __init__(self, d, num_labels, mlp, dropout, bias):
+    def __init__(self, d, num_labels, mlp, dropout, bias, hidden_act="gelu"):
         super().__init__()
         dims = [d] + list(mlp) + [num_labels]
-        self.mlp_modules = nn.ModuleList([nn.Linear(dims[i], dims[i + 1], bias=bias or i < len(dims) - 2)
-                                          for i in range(len(dims) - 1)])
+        self.mlp_modules = nn.ModuleList([nn.Linear(dims[i], dims[i + 1], bias=bias) for i in range(len(dims) - 1)])
+        from transformers.activations import ACT2FN
+        self.act_fn = ACT2FN[hidden_act]
         self.dropout = nn.Dropout(dropout)
 
     def forward(self, x):
-        x = self.mlp_modules[0](x)
-        for m in list(self.mlp_modules)[1:]:
-            x = m(self.dropout(torch.nn.functional.gelu(x)))
+        for m in self.mlp_modules:
+            x = m(self.dropout(self.act_fn(x)))
         return x
 
 
@@ -479,7 +480,7 @@ class GraphGPTTaskModel(_GraphGPTBase):
         bias = config.problem_type == "regression"
         self.num_labels = config.num_labels
         if len(config.mlp) > 0:
-            self.score = _ScoreMLP(config.hidden_size, self.num_labels, config.mlp, config.dropout, bias)
+            self.score = _ScoreMLP(config.hidden_size, self.num_labels, config.mlp, config.dropout, bias, config.hidden_act)
         else:
             self.score = nn.Linear(config.hidden_size, self.num_labels, bias=bias)
         self.pos_weight = None

@@ -351,7 +351,13 @@ def task_forward(sd, cfg, input_ids, attention_mask=None, position_ids=None, tas
     if inputs_raw_embeds is not None:
         emb = emb + raw_embed_branch(inputs_raw_embeds, sd, cfg)                          # modeling_finetune.py:130-134
     hidden = backbone(emb, attention_mask, position_ids, sd, cfg, drop=drop)
-    logits = F.linear(hidden, sd["score.weight"], sd.get("score.bias"))
+    if "score.weight" in sd:
+        logits = F.linear(hidden, sd["score.weight"], sd.get("score.bias"))
+    else:       # MLP score head (src/utils/modules_utils.py:8-34): act -> (dropout) -> Linear, for every Linear
+        logits, j = hidden, 0
+        while f"score.mlp_modules.{j}.weight" in sd:
+            logits = F.linear(F.gelu(logits), sd[f"score.mlp_modules.{j}.weight"], sd.get(f"score.mlp_modules.{j}.bias"))
+            j += 1
     seq_len = (in_ != cfg.pad_token_id).sum(-1) - 1
     idx = torch.arange(hidden.shape[0])
     pooled_logits = logits[idx, seq_len]

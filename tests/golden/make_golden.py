@@ -25,6 +25,7 @@ GRAD_KEYS = [
     "model.layers.1.input_layernorm.weight", "model.norm.weight", "lm_head.weight", "n_token_proj.weight",
     "score.weight", "stacked_feat_agg.weight", "model.layers.0.lambda_1",
     "embed_proj.weight", "embed_layernorm.weight", "emb_mask_token",
+    "score.bias", "score.mlp_modules.0.weight", "score.mlp_modules.1.weight", "score.mlp_modules.1.bias",
 ]
 
 
@@ -205,6 +206,32 @@ def _ft_double():
     pl[(b["attention_mask"] == 0) | (g.random(pl.shape) < 0.5)] = -100
     return "double", cfg, dict(input_ids=t(b["input_ids"]), attention_mask=t(b["attention_mask"]),
                                task_labels=torch.tensor([1, 1, 0]), pretrain_labels=t(pl))
+
+
+def _ft_graph(seed, n=4, s=48):
+    vocab = synth.VocabLayout(vocab_size=756, scope=512, n_node_attr=9, n_edge_attr=3)
+    b = synth.make_batch(n, s, layout="unpacked", task="ntp", vocab=vocab, seed=seed)
+    return dict(input_ids=t(b["input_ids"]), attention_mask=t(b["attention_mask"]))
+
+
+@case("ft_graph_regression_l1")
+def _ft_reg():
+    """PCQM4M-v2 fine-tune head: 1 label, regression, L1 loss, score with bias (examples/graph_lvl/pcqm4m_v2_supervised.sh:74-76)."""
+    cfg = base_cfg(vocab_size=756, hidden_size=64, intermediate_size=256, stacked_feat=13, next_n_token=13,
+                   num_labels=1, problem_type="regression", loss_type="l1", pooling_method="last")
+    return "finetune", cfg, dict(_ft_graph(25), task_labels=torch.tensor([0.3, -1.2, 2.5, 0.0]))
+
+
+@case("ft_graph_multilabel_bce_mlp")
+def _ft_ml():
+    """molpcba-style head: 8 labels, multi-label BCE with NaN = unlabelled (molpcba_supervised.sh:74-76), MLP score head
+    (config.mlp = [32]; src/utils/modules_utils.py:8-34)."""
+    cfg = base_cfg(vocab_size=756, hidden_size=64, intermediate_size=256, stacked_feat=13, next_n_token=13,
+                   num_labels=8, problem_type="multi_label_classification", pooling_method="last", mlp=[32])
+    g = np.random.default_rng(11)
+    lab = (g.random((4, 8)) < 0.4).astype(np.float32)
+    lab[g.random((4, 8)) < 0.25] = np.nan
+    return "finetune", cfg, dict(_ft_graph(26), task_labels=torch.from_numpy(lab))
 
 
 def _patch_dropout_backbone():

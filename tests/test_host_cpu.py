@@ -59,6 +59,7 @@ def test_state_dict_keys_match_reference_checkpoint_contract():
     from graphgpt_b200 import GraphGPTConfig, GraphGPTDoubleHeadsModel, GraphGPTPretrainBase, GraphGPTTaskModel
     for fx, cls in (("c2_smtp_stacked_2d", GraphGPTPretrainBase), ("c2_gated_agg", GraphGPTPretrainBase),
                     ("c3_ft_token_ce", GraphGPTTaskModel), ("c3_ft_double_heads", GraphGPTDoubleHeadsModel),
+                    ("ft_graph_regression_l1", GraphGPTTaskModel), ("ft_graph_multilabel_bce_mlp", GraphGPTTaskModel),
                     ("c3_ft_layerscale", GraphGPTTaskModel), ("c1_toy_smtp_2d", GraphGPTPretrainBase),
                     ("c2_raw_embed_pretrain", GraphGPTPretrainBase), ("c3_raw_embed_ft", GraphGPTTaskModel)):
         rec = torch.load(os.path.join(ROOT, "tests", "golden", fx + ".pt"))
