@@ -179,14 +179,18 @@ class HotPath:
     def rope_tables(self, max_pos, device):
         if self._rope_tab is None or self._rope_tab[0].shape[0] < max_pos or self._rope_tab[0].device != device:
             n = max(max_pos, self.cfg.max_position_embeddings)
-            theta = getattr(self.cfg, "rope_theta", None)
-            if theta is None:
-                theta = self.cfg.rope_parameters["rope_theta"]
+            theta = self._rope_theta()
             # HF:117-135 in fp32: inv_freq = theta^(-2i/64); freqs = pos * inv_freq
             inv_freq = 1.0 / (theta ** (torch.arange(0, 64, 2, dtype=torch.int64).float() / 64))
             freqs = torch.arange(n, dtype=torch.float32)[:, None] * inv_freq[None, :]
             self._rope_tab = (freqs.cos().to(device).contiguous(), freqs.sin().to(device).contiguous())
         return self._rope_tab
+
+    def _rope_theta(self):
+        theta = getattr(self.cfg, "rope_theta", None)      # transformers 4.x attribute; 5.x keeps it in rope_parameters
+        if theta is None:
+            theta = self.cfg.rope_parameters["rope_theta"]
+        return theta
 
     def _rope_inputs(self, position_ids, N, S, device):
         """Returns (pos int32 [T], cos_tab, sin_tab)."""
@@ -200,7 +204,7 @@ class HotPath:
             # utils_graphgpt.py:574-581: fractional positions -> per-token cos/sin table, indexed by row
             mx = position_ids.max(dim=-1, keepdim=True)[0] + 1
             fpos = (position_ids.float() * rope_range / mx.float()).reshape(-1)
-            inv_freq = 1.0 / (self.cfg.rope_theta ** (torch.arange(0, 64, 2, dtype=torch.int64, device=device).float() / 64))
+            inv_freq = 1.0 / (self._rope_theta() ** (torch.arange(0, 64, 2, dtype=torch.int64, device=device).float() / 64))
             freqs = fpos[:, None] * inv_freq[None, :]
             return torch.arange(N * S, device=device, dtype=torch.int32), freqs.cos().contiguous(), freqs.sin().contiguous()
         pos = position_ids.reshape(-1).to(torch.int32)

@@ -183,7 +183,8 @@ def reset_pos_ids(position_ids, cfg):
 def stacked_embed(input_ids, sd, cfg, embed_scale=None):
     """modeling_helpers.py:89-114 + StackedFeatAggregation.forward modeling_common.py:127-135.  embed_scale: the
     embed_dropout factors keep/(1-p) on the gathered rows ([N,S,F,d] / [N,S,d]; :97-98), None = eval."""
-    emb = sd["model.embed_tokens.weight"][input_ids]
+    # nn.Embedding(padding_idx=pad_token_id) (HF:361): an ordinary look-up of row 0 in forward, no gradient into it
+    emb = F.embedding(input_ids, sd["model.embed_tokens.weight"], padding_idx=cfg.pad_token_id)
     if embed_scale is not None:
         emb = emb * embed_scale
     if input_ids.dim() == 3:

@@ -208,6 +208,28 @@ def _ft_double():
                                task_labels=torch.tensor([1, 1, 0]), pretrain_labels=t(pl))
 
 
+@case("c2_long_stack")
+def _long():
+    """stack_method "long": embedding sum rescaled by 1/#non-pad features (modeling_helpers.py:106-110) and the per-feat
+    head with per-sample normalised weights + dLM reduction (modeling_helpers.py:327-342, modeling_pretrain.py:229-236)."""
+    cfg = base_cfg(vocab_size=756, hidden_size=64, intermediate_size=256, stacked_feat=13, next_n_token=13,
+                   stack_method="long")
+    b = synth.make_batch(3, 48, layout="unpacked", seed=27)
+    ids = b["input_ids"].copy()
+    g = np.random.default_rng(12)
+    ids[(g.random(ids.shape) < 0.2) & (b["labels"] == -100)] = 0          # pad entries inside valid rows -> nnz varies
+    return "pretrain", cfg, dict(input_ids=t(ids), attention_mask=t(b["attention_mask"]), labels=t(b["labels"]))
+
+
+@case("c2_rope_range")
+def _rope_range():
+    """rope_range > 0: position_ids rescaled to [0, rope_range) per sample before RoPE (utils_graphgpt.py:574-581)."""
+    cfg = base_cfg(vocab_size=756, hidden_size=64, intermediate_size=256, stacked_feat=13, next_n_token=13, rope_range=50)
+    b = synth.make_batch(3, 48, layout="unpacked", seed=28)
+    return "pretrain", cfg, dict(input_ids=t(b["input_ids"]), attention_mask=t(b["attention_mask"]), labels=t(b["labels"]),
+                                 position_ids=t(b["position_ids"]))
+
+
 def _ft_graph(seed, n=4, s=48):
     vocab = synth.VocabLayout(vocab_size=756, scope=512, n_node_attr=9, n_edge_attr=3)
     b = synth.make_batch(n, s, layout="unpacked", task="ntp", vocab=vocab, seed=seed)
