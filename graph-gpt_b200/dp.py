@@ -44,12 +44,22 @@ class GradReducer:
         return spans
 
 
-def warmup_decay_lr(step, *, max_lr, min_lr=0.0, warmup_steps=0, total_steps=1):
-    """DeepSpeed WarmupDecayLR (ds_config2_pt_bf16.json:17-25): linear warm-up then linear decay to min_lr."""
+def warmup_decay_lr(step, *, max_lr, min_lr=0.0, warmup_steps=0, total_steps=1, warmup_type="log"):
+    """DeepSpeed WarmupDecayLR (deepspeed==0.15.4, ds_config2_pt_bf16.json:15-23; the reference's helper
+    loss_utils.py:186-201 sets min/max lr and the two step counts and leaves `warmup_type` at DeepSpeed's default "log"):
+      step <  warmup_steps : gamma = log(step + 1) / log(warmup_steps)     ("log")   |   step / warmup_steps   ("linear")
+      step >= warmup_steps : gamma = max(0, (total_steps - step) / max(1, total_steps - warmup_steps))
+      lr = min_lr + (max_lr - min_lr) * gamma"""
     if warmup_steps > 0 and step < warmup_steps:
-        return min_lr + (max_lr - min_lr) * step / warmup_steps
-    frac = max(0.0, (total_steps - step) / max(1, total_steps - warmup_steps))
-    return min_lr + (max_lr - min_lr) * frac
+        if warmup_type == "log":
+            gamma = math.log(step + 1) / math.log(warmup_steps) if warmup_steps > 1 else 1.0
+        elif warmup_type == "linear":
+            gamma = step / warmup_steps
+        else:
+            raise ValueError(f"warmup_type={warmup_type!r}")
+    else:
+        gamma = max(0.0, (total_steps - step) / max(1, total_steps - warmup_steps))
+    return min_lr + (max_lr - min_lr) * gamma
 
 
 class GraphGPTEngine:

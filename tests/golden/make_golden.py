@@ -244,6 +244,24 @@ def _ft_reg():
     return "finetune", cfg, dict(_ft_graph(25), task_labels=torch.tensor([0.3, -1.2, 2.5, 0.0]))
 
 
+@case("ft_cls_sample_wgt")
+def _ft_wgt():
+    """single-label CE with per-sample weights (modeling_finetune.py:213-227) on a 14-class graph-level head."""
+    cfg = base_cfg(vocab_size=756, hidden_size=64, intermediate_size=256, stacked_feat=13, next_n_token=13,
+                   num_labels=14, problem_type="single_label_classification", pooling_method="last")
+    return "finetune", cfg, dict(_ft_graph(29), task_labels=torch.tensor([3, 0, 13, 7]),
+                                 sample_wgt=torch.tensor([0.5, 2.0, 1.0, 0.25]))
+
+
+@case("ft_graph_regression_mse3")
+def _ft_mse():
+    """regression with 3 targets and the default (MSE) loss (modeling_finetune.py:181-192)."""
+    cfg = base_cfg(vocab_size=756, hidden_size=64, intermediate_size=256, stacked_feat=13, next_n_token=13,
+                   num_labels=3, problem_type="regression", pooling_method="last")
+    g = np.random.default_rng(13)
+    return "finetune", cfg, dict(_ft_graph(30), task_labels=torch.from_numpy(g.standard_normal((4, 3)).astype(np.float32)))
+
+
 @case("ft_graph_multilabel_bce_mlp")
 def _ft_ml():
     """molpcba-style head: 8 labels, multi-label BCE with NaN = unlabelled (molpcba_supervised.sh:74-76), MLP score head

@@ -141,13 +141,20 @@ def test_synthetic_batches_follow_the_collator_contract():
 
 
 def test_warmup_decay_lr():
+    import math
     from graphgpt_b200.dp import warmup_decay_lr
     kw = dict(max_lr=3e-4, min_lr=0.0, warmup_steps=10, total_steps=110)
+    lin = dict(kw, warmup_type="linear")
+    assert warmup_decay_lr(0, **lin) == 0.0
+    assert abs(warmup_decay_lr(5, **lin) - 1.5e-4) < 1e-12
+    # DeepSpeed's default warm-up is logarithmic: gamma = log(step + 1) / log(warmup_num_steps)
     assert warmup_decay_lr(0, **kw) == 0.0
-    assert abs(warmup_decay_lr(5, **kw) - 1.5e-4) < 1e-12
-    assert abs(warmup_decay_lr(10, **kw) - 3e-4) < 1e-12
-    assert abs(warmup_decay_lr(60, **kw) - 1.5e-4) < 1e-12
-    assert warmup_decay_lr(110, **kw) == 0.0
+    assert abs(warmup_decay_lr(4, **kw) - 3e-4 * math.log(5) / math.log(10)) < 1e-12
+    assert abs(warmup_decay_lr(9, **kw) - 3e-4) < 1e-12
+    for k in (kw, lin):
+        assert abs(warmup_decay_lr(10, **k) - 3e-4) < 1e-12
+        assert abs(warmup_decay_lr(60, **k) - 1.5e-4) < 1e-12
+        assert warmup_decay_lr(110, **k) == 0.0
 
 
 _GLOO_WORKER = r"""
