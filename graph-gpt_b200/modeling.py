@@ -88,6 +88,24 @@ def convert_to_legacy_config(model_config):
                         use_discriminative="use_discriminative", focal_gamma="focal_gamma", smtp_inside="smtp_inside"),
         "ft_head": dict(pooling_method="pooling_method", mlp="mlp", dropout="dropout", loss_type="loss_type",
                         num_neg="num_neg", num_labels="num_labels", problem_type="problem_type"),
+        # 3-D position pre-training / denoising heads: carried through so that configs round-trip (smtp_power also
+        # drives the in-model SMTP masking of GraphGPTPretrainBase)
+        "pos_pt_head": dict(smtp_power="smtp_power", pt_problem_type="problem_type", smtp_3d_power="smtp_3d_power",
+                            smtp_3d_noise_scale="smtp_3d_noise_scale", coord_lvl_mask="coord_lvl_mask",
+                            pt_num_bins="num_bins", pt_num_bins_line="num_bins_line", pt_num_bins_cube="num_bins_cube",
+                            apply_denoise="apply_denoise", label_smoothing="label_smoothing",
+                            pt_pos_agg_method="pos_agg_method", use_pos_proj="use_pos_proj", loss_agg="loss_agg",
+                            pt_pos_range="pos_range", pt_smtp_2d_rate="smtp_2d_rate",
+                            smtp_2d_replace_rate="smtp_2d_replace_rate", sep_2d3d_inputs="sep_2d3d_inputs",
+                            global_2d_mask="global_2d_mask", pt_use_discriminative="use_discriminative"),
+        "denoise_head": dict(noise_scale="noise_scale", denoise_wgt="denoise_wgt",
+                             denoise_schedule_pow="denoise_schedule_pow", bi_causal="bi_causal", r_2d="r_2d", r_3d="r_3d",
+                             r_both="r_both", add_pos_type="add_pos_type", inputs_transform="inputs_transform",
+                             num_bins_line="num_bins_line", num_bins_cube="num_bins_cube", dn_pos_range="pos_range",
+                             dn_use_pos_proj="use_pos_proj", smtp_3d="smtp_3d", smtp_wgt="smtp_wgt",
+                             smtp_3d_scheduler_power="smtp_3d_scheduler_power", smtp_denoise="smtp_denoise",
+                             smtp_vocab="smtp_vocab", dn_smtp_2d_rate="smtp_2d_rate",
+                             smtp_2d_scheduler_power="smtp_2d_scheduler_power"),
     }
     for group, fields in nested.items():
         sub = getattr(mc, group, None)

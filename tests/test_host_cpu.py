@@ -215,3 +215,19 @@ def test_packing_oracle_and_greedy_plan():
         assert np.array_equal(am, (seg[:, None] == seg[None, :]) & (seg[:, None] > 0))
         flat = np.concatenate([np.vstack([graphs[g], np.asarray(sep)[None]]) for g in gs])[:64]
         assert np.array_equal(ids[:len(flat)], flat) and (ids[len(flat):] == 0).all()
+
+
+def test_convert_to_legacy_config_matches_reference_fixture():
+    """Every flat field the reference's own convert_to_legacy_config produces for a structured GraphGPTModelConfig with
+    non-default nested values (tests/golden/aux/legacy_config.json, written by make_golden_config.py)."""
+    import json
+    from types import SimpleNamespace as NS
+    from graphgpt_b200 import convert_to_legacy_config
+    rec = json.load(open(os.path.join(ROOT, "tests", "golden", "aux", "legacy_config.json")))
+
+    def tree(d):
+        return NS(**{k: (tree(v) if isinstance(v, dict) else v) for k, v in d.items()})
+
+    mine = json.loads(json.dumps(convert_to_legacy_config(tree(rec["structured"])).to_dict()))   # JSON-normalised keys
+    bad = {k: (v, mine.get(k, "<missing>")) for k, v in rec["flat"].items() if mine.get(k, "<missing>") != v}
+    assert not bad, bad
