@@ -185,6 +185,48 @@ class GraphGPTEngine:
         """Global gradient norm of the last step (after averaging), as a python float (syncs)."""
         return math.sqrt(float(self.gnorm_sq.item())) / self.world
 
+    @property
+    def device(self):
+        return self.flat.flat.device
+
+    # ---- DeepSpeed-style checkpoint directory (misc_utils.py:67-98: `model.save_checkpoint(model_dir)` is called by ALL
+    # ranks, files land in model_dir/global_step<N>/ and model_dir/latest names the tag) ---------------------------
+    def save_checkpoint(self, save_dir, tag=None, client_state=None):
+        import os
+        tag = tag or f"global_step{self.global_steps}"
+        rank = dist.get_rank(self.group) if self.world > 1 else 0
+        if rank == 0:                         # replicated state: one writer
+            os.makedirs(os.path.join(save_dir, tag), exist_ok=True)
+            sd = self.state_dict()
+            sd["client_state"] = client_state or {}
+            sd["micro_steps"] = self.micro_steps
+            torch.save(sd, os.path.join(save_dir, tag, "ggpt_engine_states.pt"))
+            with open(os.path.join(save_dir, "latest"), "w") as f:
+                f.write(tag)
+        if self.world > 1:
+            dist.barrier(self.group)
+        return True
+
+    def load_checkpoint(self, load_dir, tag=None, load_optimizer_states=True):
+        """Returns (path, client_state) like DeepSpeedEngine.load_checkpoint; (None, None) when nothing is there."""
+        import os
+        if tag is None:
+            latest = os.path.join(load_dir, "latest")
+            if not os.path.exists(latest):
+                return None, None
+            tag = open(latest).read().strip()
+        path = os.path.join(load_dir, tag, "ggpt_engine_states.pt")
+        if not os.path.exists(path):
+            return None, None
+        sd = torch.load(path, map_location=self.device)
+        if load_optimizer_states:
+            self.load_state_dict(sd)
+            self.micro_steps = int(sd.get("micro_steps", self.global_steps * self.gas))
+        else:
+            self.module.load_state_dict(sd["model"])
+            self.flat.ensure()
+        return path, sd.get("client_state", {})
+
     # ---- checkpoint surface (DDP-style files; misc_utils.py:105-121) -------------------------------
     def state_dict(self):
         return {"model": self.module.state_dict(), "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq,
