@@ -152,17 +152,22 @@ class GraphGPTEngine:
                     dist.all_reduce(p.grad, group=self.group)
                     p.grad.mul_(inv_world)
         lr = self.lr_schedule(self.global_steps) if self.lr_schedule is not None else self.lr
+        # frozen parameters (requires_grad = False, e.g. freeze_llama_layers, modules_utils.py:45-54) are skipped entirely —
+        # no update, no weight decay, not in the clipping norm — exactly as torch / DeepSpeed optimizers skip them
+        spans = self._trainable_spans()
         gn = None
         if self.max_grad_norm and self.max_grad_norm > 0:
             self.gnorm_sq.zero_()
-            ops.sumsq(fp.flat_grad, self.gnorm_sq)
+            for a, b in spans:
+                ops.sumsq(fp.flat_grad[a:b], self.gnorm_sq)
             for p in self.extra:
                 if p.grad is not None:       # extra grads are already averaged; flat ones are scaled in-kernel
                     self.gnorm_sq += (p.grad.double().pow(2).sum() * (self.world ** 2))
             gn = self.gnorm_sq
-        ops.adamw(fp.flat, fp.flat_bf16, fp.flat_grad, self.exp_avg, self.exp_avg_sq, lr=lr, betas=self.betas,
-                  eps=self.eps, weight_decay=self.weight_decay, step=self.global_steps, gnorm_sq=gn,
-                  max_norm=self.max_grad_norm or 0.0, grad_scale=inv_world)
+        for a, b in spans:
+            ops.adamw(fp.flat[a:b], fp.flat_bf16[a:b], fp.flat_grad[a:b], self.exp_avg[a:b], self.exp_avg_sq[a:b], lr=lr,
+                      betas=self.betas, eps=self.eps, weight_decay=self.weight_decay, step=self.global_steps, gnorm_sq=gn,
+                      max_norm=self.max_grad_norm or 0.0, grad_scale=inv_world)
         fp.mark_bf16_fresh()
         if self.extra_opt is not None:
             if gn is not None:
@@ -174,6 +179,19 @@ class GraphGPTEngine:
                 grp["lr"] = lr
             self.extra_opt.step()
         self.zero_grad()
+
+    def _trainable_spans(self):
+        """Coalesced [start, end) element ranges of the flat buffers that belong to trainable parameters."""
+        spans = []
+        for name, p in self.flat.order:
+            if not p.requires_grad:
+                continue
+            a, b = self.flat.span(name, name)
+            if spans and spans[-1][1] == a:
+                spans[-1][1] = b
+            else:
+                spans.append([a, b])
+        return [(a, b) for a, b in spans]
 
     def zero_grad(self):
         for _, p in self.flat.order:

@@ -320,7 +320,21 @@ class HotPath:
                                   fp.g("model.norm.weight"))
         if self.grad_ready_hook:
             self.grad_ready_hook("model.norm.weight", self.flat.order[-1][0])
+        # frozen prefix (freeze_llama_layers, modules_utils.py:45-54: embeddings + the first k layers have requires_grad =
+        # False): nothing below the first trainable layer needs a gradient, so backward stops there, as autograd would
+        named = dict(self.flat.order)
+        head_names = [n for n, _ in self.flat.order[: [n for n, _ in self.flat.order].index("model.layers.0.self_attn.q_proj.weight")]]
+        first_trainable = 0 if any(named[n].requires_grad for n in head_names) else self.L
+        if first_trainable:
+            for i in range(self.L):
+                if any(q.requires_grad for n, q in self.flat.order if n.startswith(f"model.layers.{i}.")):
+                    first_trainable = i
+                    break
         for i in reversed(range(self.L)):
+            if i < first_trainable:
+                for j in range(i + 1):
+                    stash["layers"][j] = None
+                return
             p = f"model.layers.{i}."
             st = stash["layers"][i]
             # ---- MLP block:  x3 = x2 + rs * lam2 * (act @ Wd^T)

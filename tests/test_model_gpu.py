@@ -322,6 +322,48 @@ def test_batch_without_any_label_gives_nan_loss_and_empty_logits():
     assert torch.isnan(out.head1_loss) and tuple(out.head1_logits.shape) == (0, 300)
 
 
+def test_frozen_prefix_like_freeze_llama_layers():
+    """finetune.freeze (modules_utils.py:45-54): embeddings + the first k layers get requires_grad = False.  Frozen
+    parameters must stay bit-identical through engine.step() (no update, no weight decay), backward stops at the first
+    trainable layer, and the trainable gradients equal those of the unfrozen model."""
+    import copy
+    from graphgpt_b200 import GraphGPTConfig, GraphGPTTaskModel, synth
+    from graphgpt_b200.dp import GraphGPTEngine
+    cfgd = dict(vocab_size=1200, hidden_size=128, intermediate_size=512, num_hidden_layers=3, num_attention_heads=2,
+                num_key_value_heads=2, head_dim=64, hidden_act="gelu", max_position_embeddings=1024, rms_norm_eps=1e-6,
+                rope_theta=10000.0, pad_token_id=0, causal_attention=False, stacked_feat=4, stack_method="short",
+                stacked_feat_agg_method="sum", next_n_token=4, use_cache=False, attention_dropout=0.0, num_labels=2,
+                problem_type="single_label_classification", pooling_method="last")
+    vocab = synth.VocabLayout(vocab_size=1200, scope=512, n_node_attr=2, n_edge_attr=1)
+    b = synth.make_batch(4, 64, layout="unpacked", task="ntp", vocab=vocab, seed=81)
+    batch = dict(input_ids=torch.from_numpy(b["input_ids"]).cuda(), attention_mask=torch.from_numpy(b["attention_mask"]).cuda(),
+                 task_labels=torch.tensor([1, 0, 0, 1]).cuda())
+    torch.manual_seed(0)
+    full = GraphGPTTaskModel(GraphGPTConfig(**cfgd)).cuda().train()
+    frozen = copy.deepcopy(full)
+    for p in frozen.model.embed_tokens.parameters():
+        p.requires_grad = False
+    for layer in frozen.model.layers[:2]:
+        for p in layer.parameters():
+            p.requires_grad = False
+    full(**batch).task_loss.backward()
+    ref_grads = {k: p.grad.clone() for k, p in full.named_parameters()}
+    eng = GraphGPTEngine(frozen, lr=1e-2, weight_decay=0.1, max_grad_norm=1.0)
+    before = {k: p.detach().clone() for k, p in frozen.named_parameters()}
+    eng.backward(eng(**batch).task_loss)
+    for k, p in frozen.named_parameters():
+        if p.requires_grad:
+            assert _relf(p.grad, ref_grads[k]) <= 1e-3, k          # same kernels, same values (split-K order noise only)
+        else:
+            assert p.grad is None, k
+    eng.step()
+    for k, p in frozen.named_parameters():
+        if p.requires_grad:
+            assert not torch.equal(p.detach(), before[k]), k
+        else:
+            assert torch.equal(p.detach(), before[k]), k
+
+
 def test_engine_checkpoint_roundtrip(tmp_path):
     """save_checkpoint / load_checkpoint (DeepSpeed-style directory): weights, Adam moments and step counters come back
     exactly, and training continues bit-identically from the restored state."""
