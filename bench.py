@@ -216,10 +216,21 @@ def run_b200(args):
         sync_all()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
+        marks = []
         for i in range(n):
             fn(i)
+            if os.environ.get("GGPT_BENCH_DEBUG"):
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append(ev)
         b.record()
         sync_all()
+        if marks:
+            prev, per = a, []
+            for ev in marks:
+                per.append(round(prev.elapsed_time(ev), 2))
+                prev = ev
+            sys.stderr.write(f"[bench debug] per-step device ms: {per}\n")
         ms = torch.tensor([a.elapsed_time(b)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -228,8 +239,12 @@ def run_b200(args):
     # ---- warm-up, then the timed region (inputs resident in HBM) -------------------------------------------------
     for i in range(args.warmup):
         step(devb[i % len(devb)])
+    # Everything built so far (model, batches, numpy scaffolding of the synthetic data) is long-lived: move it out of the
+    # garbage collector's reach, otherwise a full collection walks it in the middle of a step and stalls the launch
+    # thread for tens of milliseconds (the queue runs only ~5 ms ahead of the device).
+    engine.freeze_gc()
     clk_path = os.path.join(tempfile.gettempdir(), f"ggpt_clocks_{os.getpid()}.csv")
-    sampler = clocks_sampler_start(clk_path) if rank == 0 else None
+    sampler = clocks_sampler_start(clk_path) if (rank == 0 and not os.environ.get("GGPT_BENCH_NO_SAMPLER")) else None
     launches0 = lib.launch_count
     # inside the timed region only the dominant kernel (the tcgen05 GEMM, every launch of it) is bracketed by CUDA
     # events: those durations give roofline.achieved.  The other entry points are timed in a separate pass below.

@@ -173,6 +173,7 @@ class HotPath:
         self.eps = config.rms_norm_eps
         self.flat = FlatParams(module, module._flat_param_order())
         self._rope_tab = None
+        self._param_groups = None
         self.grad_ready_hook = None   # callable(first_name, last_name) fired as gradient segments complete
 
     # ------------------------------------------------------------------ helpers
@@ -290,6 +291,23 @@ class HotPath:
             stash.update(x_final=x, rstdf=rstdf)
         return hf
 
+    def _first_trainable_layer(self):
+        """0 when anything in front of the layer stack (embeddings, gate, raw-embedding branch) is trainable; else the
+        index of the first layer holding a trainable parameter (L when there is none)."""
+        if self._param_groups is None:
+            names = [n for n, _ in self.flat.order]
+            k0 = names.index("model.layers.0.self_attn.q_proj.weight")
+            front = [p for _, p in self.flat.order[:k0]]
+            layers = [[p for n, p in self.flat.order if n.startswith(f"model.layers.{i}.")] for i in range(self.L)]
+            self._param_groups = (front, layers)
+        front, layers = self._param_groups
+        if any(p.requires_grad for p in front):
+            return 0
+        for i, ps in enumerate(layers):
+            if any(p.requires_grad for p in ps):
+                return i
+        return self.L
+
     def _wqkv(self, i):
         """bf16 [3d, d] view: q_proj, k_proj, v_proj weights are adjacent in the flat layout."""
         fp = self.flat
@@ -322,14 +340,7 @@ class HotPath:
             self.grad_ready_hook("model.norm.weight", self.flat.order[-1][0])
         # frozen prefix (freeze_llama_layers, modules_utils.py:45-54: embeddings + the first k layers have requires_grad =
         # False): nothing below the first trainable layer needs a gradient, so backward stops there, as autograd would
-        named = dict(self.flat.order)
-        head_names = [n for n, _ in self.flat.order[: [n for n, _ in self.flat.order].index("model.layers.0.self_attn.q_proj.weight")]]
-        first_trainable = 0 if any(named[n].requires_grad for n in head_names) else self.L
-        if first_trainable:
-            for i in range(self.L):
-                if any(q.requires_grad for n, q in self.flat.order if n.startswith(f"model.layers.{i}.")):
-                    first_trainable = i
-                    break
+        first_trainable = self._first_trainable_layer()
         for i in reversed(range(self.L)):
             if i < first_trainable:
                 for j in range(i + 1):
