@@ -11,8 +11,6 @@ Reference call sites reproduced (kernel-level citations are in include/ggpt_b200
   LlamaModel.forward HF:375-425, LlamaDecoderLayer.forward HF:313-332 (+ utils_graphgpt.py:137-166 LayerScale /
   DropPath), prepare_for_stacked_feat_labels modeling_helpers.py:362-393, lm_head + CE modeling_pretrain.py:213-237.
 """
-import math
-
 import torch
 
 from . import ops

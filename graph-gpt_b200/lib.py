@@ -83,6 +83,7 @@ class _Lib:
         self._protos = None
         self.launch_count = 0
         self.timer = None
+        self._cache = {}
 
     def load(self):
         if self._dll is not None:
@@ -105,33 +106,50 @@ class _Lib:
         return self.load().ggpt_last_error().decode(errors="replace")
 
     def call(self, name, *args):
+        return self._bound(name)(*args)
+
+    def _bound(self, name):
+        """One Python callable per entry point, built on first use: resolves the function pointer, the launch count and
+        the status-code convention once, so the per-launch host cost is a dict look-up and the ctypes call."""
+        fn = self._cache.get(name)
+        if fn is not None:
+            return fn
         dll = self.load()
-        self.launch_count += _LAUNCHES.get(name, 1)
-        timer = self.timer
-        if timer is not None and _LAUNCHES.get(name, 1) > 0 and (timer.only is None or name in timer.only):
-            import torch
-            key, flops = name, 0.0
-            if name in _GEMM_FUNCS:
-                M, N, K = args[-4], args[-3], args[-2]
-                flops = 2.0 * M * N * K
-                if name == "ggpt_gemm_bf16":
-                    key = f"{name}[a_mn={args[2]},b_mn={args[5]}]"
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            rc = getattr(dll, name)(*args)
-            b.record()
-            timer.events.append((key, a, b, flops))
-        else:
-            rc = getattr(dll, name)(*args)
-        if self._protos[name][0] is ctypes.c_int and name not in _VALUE_FUNCS:
-            if rc != 0:
-                raise RuntimeError(f"{name} failed (rc={rc}): {self.last_error()}")
-            return None
-        return rc
+        cfn = getattr(dll, name)
+        n_launch = _LAUNCHES.get(name, 1)
+        is_status = self._protos[name][0] is ctypes.c_int and name not in _VALUE_FUNCS
+        is_gemm = name in _GEMM_FUNCS
+
+        def run(*args):
+            self.launch_count += n_launch
+            timer = self.timer
+            if timer is not None and n_launch > 0 and (timer.only is None or name in timer.only):
+                import torch
+                key, flops = name, 0.0
+                if is_gemm:
+                    M, N, K = args[-4], args[-3], args[-2]
+                    flops = 2.0 * M * N * K
+                    if name == "ggpt_gemm_bf16":
+                        key = f"{name}[a_mn={args[2]},b_mn={args[5]}]"
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                rc = cfn(*args)
+                b.record()
+                timer.events.append((key, a, b, flops))
+            else:
+                rc = cfn(*args)
+            if is_status:
+                if rc != 0:
+                    raise RuntimeError(f"{name} failed (rc={rc}): {self.last_error()}")
+                return None
+            return rc
+
+        self._cache[name] = run
+        return run
 
     def __getattr__(self, name):
         if name.startswith("ggpt_"):
-            return lambda *args: self.call(name, *args)
+            return self._bound(name)
         raise AttributeError(name)
 
 
