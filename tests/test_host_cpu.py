@@ -231,3 +231,19 @@ def test_convert_to_legacy_config_matches_reference_fixture():
     mine = json.loads(json.dumps(convert_to_legacy_config(tree(rec["structured"])).to_dict()))   # JSON-normalised keys
     bad = {k: (v, mine.get(k, "<missing>")) for k, v in rec["flat"].items() if mine.get(k, "<missing>") != v}
     assert not bad, bad
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver times next to the GPU arm): one JSON line on stdout with the
+    contract's keys, runnable without a GPU."""
+    import json
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "tokens/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"].startswith("pcqm4m-v2-smtp-pretrain") and d["gpu_launches"] == 0
