@@ -160,12 +160,15 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
       : "memory");
 }
-// arrive on the mbarrier at this offset in CTA `cta` of the cluster
+// arrive on the mbarrier at this offset in CTA `cta` of the cluster.  Default semantics (release at CTA scope), as in
+// CUTLASS's ClusterBarrier::arrive: the barrier only hands a drained TMEM accumulator back to the MMA thread, and the
+// tcgen05 fences order the TMEM reads — a `.release.cluster` arrive would additionally wait until every global store of
+// the epilogue warp is visible cluster-wide (ncu: "membar" was the second largest stall of the pair-mode GEMMs).
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(smem_u32(bar)), "r"(cta)
       : "memory");
 }
