@@ -649,6 +649,51 @@ __global__ void scatter_rows_kernel(const __nv_bfloat16* __restrict__ src, long 
   }
 }
 
+// out[j,:] = src[i,:] if idx[i] == j for some i, else 0 — idx STRICTLY INCREASING (the compaction indices of
+// head_compact are), so one kernel replaces memset + scatter: each CTA owns 256 consecutive output rows, finds the slice
+// of idx that lands in them with one binary search, records it in a shared-memory map and then streams the rows.
+__global__ void __launch_bounds__(256) expand_rows_kernel(const __nv_bfloat16* __restrict__ src, long long lds,
+                                                          const int* __restrict__ idx, int n,
+                                                          __nv_bfloat16* __restrict__ out, long long ldo,
+                                                          long long n_out, int d) {
+  __shared__ int map[256];
+  __shared__ int i_first;
+  const int vec_per_row = d / 8;
+  const long long n_blocks = (n_out + 255) / 256;
+  for (long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+    const long long j0 = blk * 256;
+    const long long left = n_out - j0;
+    const int rows = left < 256 ? static_cast<int>(left) : 256;
+    map[threadIdx.x] = -1;
+    if (threadIdx.x == 0) {                 // first i with idx[i] >= j0
+      int lo = 0, hi = n;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (idx[mid] < j0) lo = mid + 1; else hi = mid;
+      }
+      i_first = lo;
+    }
+    __syncthreads();
+    {
+      const int i = i_first + threadIdx.x;  // at most 256 indices can fall into 256 consecutive rows
+      if (i < n) {
+        const long long j = idx[i];
+        if (j < j0 + rows) map[static_cast<int>(j - j0)] = i;
+      }
+    }
+    __syncthreads();
+    const int total = rows * vec_per_row;
+    for (int e = threadIdx.x; e < total; e += 256) {
+      const int r = e / vec_per_row, c = (e % vec_per_row) * 8;
+      const int i = map[r];
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (i >= 0) v = *reinterpret_cast<const uint4*>(src + static_cast<long long>(i) * lds + c);
+      *reinterpret_cast<uint4*>(out + (j0 + r) * ldo + c) = v;
+    }
+    __syncthreads();
+  }
+}
+
 // =============================================================================================
 // Cross-entropy over fp32 logits [L, ldl] (first V columns valid).  One warp per row.
 //   row_lse[e] = logsumexp(logits[e,:V]);  loss_sum += wgt[e] * (row_lse[e] - logits[e, label[e]])
@@ -964,6 +1009,17 @@ int ggpt_scatter_rows(const void* src, long long lds, const int* idx, void* out,
   scatter_rows_kernel<<<grid_for_rows(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(src), lds, idx, static_cast<__nv_bfloat16*>(out), ldo, n_ptr, n_max, d);
   return check_launch("scatter_rows_kernel");
+}
+
+int ggpt_expand_rows(const void* src, long long lds, const int* idx, int n, void* out, long long ldo, long long n_out, int d,
+                     void* stream) {
+  GGPT_REQUIRE(out && (n == 0 || (src && idx)), "expand_rows: null pointer");
+  GGPT_REQUIRE(n >= 0 && n_out > 0 && d % 8 == 0 && lds % 8 == 0 && ldo % 8 == 0, "expand_rows: bad sizes n=%d n_out=%lld d=%d", n,
+               n_out, d);
+  const long long blocks = (n_out + 255) / 256;
+  expand_rows_kernel<<<grid_for_rows(blocks, 1, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(src), lds, idx, n, static_cast<__nv_bfloat16*>(out), ldo, n_out, d);
+  return check_launch("expand_rows_kernel");
 }
 
 int ggpt_ce_fwd(const float* logits, long long ldl, const int* labels, const float* wgt, float* row_lse, float* row_loss,

@@ -508,13 +508,10 @@ class PretrainHeadFn(torch.autograd.Function):
         dhl = ops.gemm(dlv, fp.wb(ctx.head_w), b_mn_major=True)                              # [L, d]
         if ctx.has_proj:
             F_ = ctx.F
-            dproj = torch.zeros((M * F_, d), device=dhl.device, dtype=BF16)
-            ops.scatter_rows(dhl, hi.ent_src, dproj, L)
-            dproj = dproj.view(M, F_ * d)
+            dproj = ops.expand_rows(dhl, hi.ent_src, L, M * F_).view(M, F_ * d)
             ops.gemm(dproj, hsel, out=fp.g(ctx.proj_w), **wgrad)
             dhsel = ops.gemm(dproj, fp.wb(ctx.proj_w), b_mn_major=True)                      # [M, d]
         else:
             dhsel = dhl
-        dhf = torch.zeros((ctx.T, d), device=dhl.device, dtype=BF16)
-        ops.scatter_rows(dhsel, hi.sel_rows, dhf, M)
+        dhf = ops.expand_rows(dhsel, hi.sel_rows, M, ctx.T)
         return (None, dhf) + (None,) * (n_in - 2)

@@ -412,6 +412,16 @@ def scatter_rows(src, idx, out, n, *, n_ptr=None):
     return out
 
 
+def expand_rows(src, idx, n, n_out):
+    """bf16 [n_out, d] with out[idx[i]] = src[i] (idx strictly increasing) and zero rows elsewhere, in one pass."""
+    _check(src, BF16, "expand_rows src", 2)
+    _check(idx, torch.int32, "expand_rows idx", 1)
+    d = src.shape[1]
+    out = torch.empty((n_out, d), device=src.device, dtype=BF16)
+    lib.ggpt_expand_rows(src.data_ptr(), src.stride(0), idx.data_ptr(), int(n), out.data_ptr(), d, int(n_out), d, _stream())
+    return out
+
+
 def ce_fwd(logits, labels, V, wgt=None, *, want_row_loss=False, err_flag=None, focal_gamma=0.0):
     """logits f32 [L, ld>=V]; labels int32 [>=L].  Returns (row_lse, row_loss|None, loss_sum f64[1], wgt_sum f64[1])."""
     _check(logits, F32, "ce logits", 2)

@@ -221,6 +221,11 @@ int ggpt_gather_rows(const void* src, long long lds, const int* idx, void* out, 
                      int n_max, int d, void* stream);
 int ggpt_scatter_rows(const void* src, long long lds, const int* idx, void* out, long long ldo, const int* n_ptr,
                       int n_max, int d, void* stream);
+/* out[j,:] (bf16 [n_out, ldo], fully written) = src[i,:] where idx[i] == j, zero rows elsewhere; idx[n] must be strictly
+ * increasing (sel_rows / ent_src of ggpt_head_compact are).  One pass instead of memset + ggpt_scatter_rows: the
+ * backward of the boolean-mask indexing of modeling_helpers.py:288-300. */
+int ggpt_expand_rows(const void* src, long long lds, const int* idx, int n, void* out, long long ldo, long long n_out, int d,
+                     void* stream);
 
 /* fp32 cross-entropy over logits [L, ldl] (V valid columns): row_lse, optional row_loss, and
  * loss_sum += wgt[e]*(lse - logit[label]) (wgt NULL -> 1), wgt_sum += wgt[e] (may be NULL).

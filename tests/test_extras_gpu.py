@@ -279,3 +279,18 @@ def test_device_packer_matches_oracle_and_segment_mask_equals_block_diagonal():
         a = model(input_ids=ids_in, attention_mask=out["attention_mask"], labels=labels)
         b = model(input_ids=ids_in, attention_mask=torch.from_numpy(am3).cuda(), labels=labels)
     assert torch.equal(a.head1_logits, b.head1_logits) and a.head1_loss.item() == b.head1_loss.item()
+
+
+@pytest.mark.parametrize("n_out,d,density", [(1000, 768, 0.5), (70000, 64, 0.9), (513, 128, 0.01), (256, 768, 1.0), (300, 64, 0.0)])
+def test_expand_rows_equals_memset_plus_scatter(n_out, d, density):
+    from graphgpt_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(n_out)
+    keep = torch.rand(n_out, device="cuda", generator=g) < density
+    idx = keep.nonzero().view(-1).to(torch.int32)
+    n = idx.numel()
+    src = torch.randn(max(n, 1), d, device="cuda", generator=g).bfloat16()
+    want = torch.zeros(n_out, d, device="cuda", dtype=torch.bfloat16)
+    if n:
+        want[idx.long()] = src[:n]
+    got = ops.expand_rows(src, idx if n else torch.zeros(1, device="cuda", dtype=torch.int32), n, n_out)
+    assert torch.equal(got, want)
