@@ -5,9 +5,10 @@ Restates, with plain Python lists and numpy as the reference does, what its toke
   prepare_inputs_for_pretrain_mlm (src/utils/tokenizer_utils.py:228-233,246): one more <eos> row after the last graph
   block-wise attention (tokenizer_utils.py:351-355): scipy-style block_diag of ones, one block per ls_len increment
   collator pad() (tokenizer.py:340-357): truncate to pad_to = mpe, right-pad.
-PARITY PIN: unpinned against a run of the reference — pack_token_seq is a method of the dataset-bound tokenizer (needs
-torch_geometric datasets, absent here); the restatement follows the cited lines and tests/test_host_cpu.py checks it
-against an independent scipy.linalg.block_diag construction."""
+PARITY PIN: pinned.  tests/golden/make_golden_packing.py calls the reference's own `pack_token_seq` (as an unbound
+method on a stand-in exposing only the attributes it touches; F = 1, 5, 13) and builds the mask from its `ls_len` with
+the reference's block_diag lines; tests/test_oracle_golden.py::test_packing_oracle_matches_reference_pack_token_seq
+compares token rows, mask and segment boundaries exactly.  tests/test_host_cpu.py adds an independent scipy check."""
 import numpy as np
 
 
