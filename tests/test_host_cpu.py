@@ -247,3 +247,34 @@ def test_bench_reference_arm_contract():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"].startswith("pcqm4m-v2-smtp-pretrain") and d["gpu_launches"] == 0
+
+
+def test_mix_seed_streams_are_well_separated():
+    """The per-forward dropout streams (attention layer i, GeGLU / MLP output of layer i, embedding, raw embedding) get
+    splitmix64-separated seeds: all distinct, 63-bit, and no two differ by a small XOR / additive constant (which would
+    make one stream an index-shifted copy of another under the counter-based generator)."""
+    from graphgpt_b200.engine import _SEED_ACT, _SEED_EMBED, _SEED_MLP, _SEED_RAW, mix_seed
+    base = 0x1234_5678_9ABC
+    ks = [_SEED_ACT + i for i in range(48)] + [_SEED_MLP + i for i in range(48)] + [_SEED_EMBED, _SEED_RAW]
+    seeds = [mix_seed(base, k) for k in ks]
+    assert len(set(seeds)) == len(seeds) and all(0 <= s < 2 ** 63 for s in seeds)
+    lows = [s & 0xFFFFFFFF for s in seeds]
+    for i in range(len(lows)):
+        for j in range(i + 1, len(lows)):
+            assert bin(lows[i] ^ lows[j]).count("1") >= 5, (ks[i], ks[j])
+    assert mix_seed(base, 1) != mix_seed(base + 1, 1) and mix_seed(base, 1) == mix_seed(base, 1)
+
+
+def test_plan_greedy_properties():
+    """Every graph is placed exactly once and in order; a sequence is closed by the first graph that takes it to >= mpe."""
+    import numpy as np
+    from graphgpt_b200.packing import plan_greedy
+    rng = np.random.default_rng(1)
+    for mpe in (16, 100, 1024):
+        lengths = rng.integers(1, 60, size=500)
+        order = rng.permutation(500)
+        seq_graphs, cu_seq = plan_greedy(lengths, mpe, order)
+        assert np.array_equal(seq_graphs, order.astype(np.int32))
+        for n in range(len(cu_seq) - 1):
+            run = np.cumsum(lengths[seq_graphs[cu_seq[n]:cu_seq[n + 1]]] + 1)
+            assert (run[:-1] < mpe).all() and (run[-1] >= mpe or n == len(cu_seq) - 2)
