@@ -101,3 +101,27 @@ def batch_unmask(x, logits, timesteps, i, *, alg="origin", alg_temp=None, temper
         cut = torch.arange(k)[None, :] >= ntps[:, None]
         x.scatter_(1, order, torch.where(cut, torch.gather(x, 1, order), upd))
     return x, i
+
+
+def sample_per_batch(logits_fn, input_ids, *, alg, steps, eps=1e-3, mask_token_id=1, alg_temp=None, temperature=0.0,
+                     top_p=None, top_k=None, draws=None):
+    """sample_per_batch (:85-135) over a callable `logits_fn(x [bz, seq, next_n]) -> [bz*seq*next_n, V]`.
+    draws: optional callable(name, shape) -> uniform tensor, consulted for "transfer" / "gumbel" draws (None: torch.rand).
+    Returns (x [bz, seq*next_n], number of forward passes)."""
+    bz, seq, next_n = input_ids.shape
+    x = input_ids.clone().view(bz, seq * next_n)
+    m = x == mask_token_id
+    n_steps = min(int(torch.max(m.sum(dim=-1).float()).item()), steps)
+    timesteps = torch.linspace(1, eps, n_steps + 1)
+    rnd = draws if draws is not None else (lambda name, shape: torch.rand(shape))
+    i, calls = 0, 0
+    while i < n_steps:
+        logits = logits_fn(x.view(bz, seq, next_n)).view(bz, seq * next_n, -1)
+        calls += 1
+        if int((x == mask_token_id).sum()) == 0 and alg != "origin":
+            break          # the reference would spin here; nothing is left to reveal
+        x, i = batch_unmask(x, logits, timesteps, i, alg=alg, alg_temp=alg_temp, temperature=temperature, top_p=top_p,
+                            top_k=top_k, mask_token_id=mask_token_id,
+                            u_transfer=rnd("transfer", x.shape) if alg == "origin" else None,
+                            u_gumbel=rnd("gumbel", x.shape) if (alg_temp is not None and alg_temp > 0) else None)
+    return x, calls

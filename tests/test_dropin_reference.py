@@ -49,3 +49,61 @@ def test_reference_training_modes_resolve_to_the_b200_classes(tmp_path):
     script.write_text(_SCRIPT)
     p = subprocess.run([sys.executable, str(script), ROOT], capture_output=True, text=True, timeout=600)
     assert p.returncode == 0 and "dropin ok" in p.stdout, (p.stdout + p.stderr)[-3000:]
+
+
+_GEN_SCRIPT = r'''
+import sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests/golden")
+import ref_shim
+ref_shim._Finder.roots = tuple(r for r in ref_shim._Finder.roots if r != "accelerate")
+ref_shim.load_reference()
+import torch
+from types import SimpleNamespace as NS
+from src.utils import generation_utils as gu
+from oracle import generation_oracle as go
+
+bz, seq, F_, V, mask_id = 4, 12, 3, 50, 1
+g = torch.Generator().manual_seed(0)
+W = torch.randn(V, V, generator=g)                       # a deterministic stand-in "model": logits depend on the tokens
+pos = torch.randn(seq * F_, V, generator=g)
+
+
+def logits_fn(x):
+    xf = x.reshape(x.shape[0], -1)
+    ctx = torch.nn.functional.one_hot(xf, V).float().mean(1, keepdim=True) @ W      # [bz,1,V]: every entry sees the whole row
+    return (W[xf] * 0.3 + ctx + pos[None]).reshape(-1, V)
+
+
+class Model:
+    def eval(self):
+        return self
+
+    def __call__(self, input_ids=None, attention_mask=None, labels=None, inputs_raw_embeds=None):
+        return NS(head1_logits=logits_fn(input_ids))
+
+
+ids = torch.randint(2, V, (bz, seq, F_), generator=g)
+flat = ids.view(bz, -1)
+for b in range(bz):                                      # the same number of masked entries in every sample: the
+    flat[b, torch.randperm(seq * F_, generator=g)[:20]] = mask_id   # reference's re-masking quirk never triggers
+for alg in ("origin", "maskgit_plus", "topk_margin", "entropy"):
+    for steps in (3, 7, 50):
+        cfg = NS(eps=1e-3, steps=steps, mask_token_id=mask_id, output_history=False, temperature=0.0, top_p=None, top_k=None,
+                 alg=alg, alg_temp=None)
+        torch.manual_seed(11)
+        ref, _ = gu.sample_per_batch(Model(), cfg, input_ids=ids, attention_mask=None, inputs_raw_embeds=None)
+        torch.manual_seed(11)
+        mine, calls = go.sample_per_batch(logits_fn, ids, alg=alg, steps=steps, mask_token_id=mask_id)
+        assert torch.equal(ref, mine), (alg, steps, int((ref != mine).sum()))
+        assert int((mine == mask_id).sum()) <= int((logits_fn(mine.view(bz, seq, F_)).argmax(-1) == mask_id).sum()) + bz * seq * F_
+print("generation loop ok")
+'''
+
+
+def test_generation_oracle_loop_matches_reference_sample_per_batch(tmp_path):
+    """The whole decoding loop of the reference (generation_utils.sample_per_batch, all four algorithms, three step
+    budgets) against oracle/generation_oracle.sample_per_batch on a deterministic stand-in model."""
+    script = tmp_path / "gen.py"
+    script.write_text(_GEN_SCRIPT)
+    p = subprocess.run([sys.executable, str(script), ROOT], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "generation loop ok" in p.stdout, (p.stdout + p.stderr)[-3000:]
