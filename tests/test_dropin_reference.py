@@ -107,3 +107,45 @@ def test_generation_oracle_loop_matches_reference_sample_per_batch(tmp_path):
     script.write_text(_GEN_SCRIPT)
     p = subprocess.run([sys.executable, str(script), ROOT], capture_output=True, text=True, timeout=600)
     assert p.returncode == 0 and "generation loop ok" in p.stdout, (p.stdout + p.stderr)[-3000:]
+
+
+_PAD_SCRIPT = r'''
+import sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests/golden")
+import ref_shim
+ref_shim._Finder.roots = tuple(r for r in ref_shim._Finder.roots if r != "accelerate")
+ref_shim.load_reference()
+import numpy as np, torch
+from src.data import tokenizer as rtok
+from graphgpt_b200 import synth
+
+for F_vocab, seed in ((synth.PCQM_VOCAB, 3), (synth.TOY_VOCAB, 4)):
+    b = synth.make_batch(6, 64, layout="unpacked", vocab=F_vocab, seed=seed)
+    feats = []
+    for n in range(6):
+        L = int(b["attention_mask"][n].sum())
+        feats.append({"input_ids": b["input_ids"][n, :L].tolist(), "labels": b["labels"][n, :L].tolist(),
+                      "attention_mask": [1] * L, "position_ids": list(range(L))})
+
+    class Fake:
+        pad_token_id, label_pad_token_id, padding_side, eos_idx = 0, -100, "right", int(1e8)
+        def set_eos_idx(self, x):
+            pass
+    fake = Fake()
+    fake._pad_each_datapoint = lambda feat, pad_to: rtok.GSTTokenizer._pad_each_datapoint(fake, feat, pad_to)
+    out = rtok.GSTTokenizer.pad(fake, feats, padding=True, max_length=1024, pad_to_multiple_of=8, return_tensors="pt")
+    for k in ("input_ids", "labels", "attention_mask"):
+        assert out[k].dtype == torch.int64 and torch.equal(out[k], torch.from_numpy(b[k])), (k, out[k].shape, b[k].shape)
+    am = torch.from_numpy(b["attention_mask"]).bool()
+    assert torch.equal(out["position_ids"][am], torch.from_numpy(b["position_ids"])[am])
+print("collator pad ok")
+'''
+
+
+def test_synthetic_unpacked_batches_equal_the_reference_collator_padding(tmp_path):
+    """graphgpt_b200.synth's right-padded batches (keys, dtypes, pad values, multiple-of-8 length) against the reference's
+    own tokenizer.pad() (src/data/tokenizer.py:227-357) fed the same ragged samples."""
+    script = tmp_path / "pad.py"
+    script.write_text(_PAD_SCRIPT)
+    p = subprocess.run([sys.executable, str(script), ROOT], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "collator pad ok" in p.stdout, (p.stdout + p.stderr)[-3000:]
