@@ -149,3 +149,28 @@ def test_synthetic_unpacked_batches_equal_the_reference_collator_padding(tmp_pat
     script.write_text(_PAD_SCRIPT)
     p = subprocess.run([sys.executable, str(script), ROOT], capture_output=True, text=True, timeout=600)
     assert p.returncode == 0 and "collator pad ok" in p.stdout, (p.stdout + p.stderr)[-3000:]
+
+
+_SURFACE_SCRIPT = r'''
+import sys, inspect, dataclasses
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests/golden")
+from ref_shim import load_reference
+mp, mf, RefCfg = load_reference()
+import graphgpt_b200 as gb
+from src.models.graphgpt.modeling_common import DoubleHeadsModelOutput as RefOut
+for name, ref in (("GraphGPTPretrainBase", mp.GraphGPTPretrainBase), ("GraphGPTTaskModel", mf.GraphGPTTaskModel),
+                  ("GraphGPTDoubleHeadsModel", mf.GraphGPTDoubleHeadsModel)):
+    assert list(inspect.signature(ref.forward).parameters) == list(inspect.signature(getattr(gb, name).forward).parameters), name
+assert [f.name for f in dataclasses.fields(RefOut)] == [f.name for f in dataclasses.fields(gb.DoubleHeadsModelOutput)]
+a, b = RefCfg().to_dict(), gb.GraphGPTConfig().to_dict()
+diff = {k for k in set(a) | set(b) if a.get(k, "<missing>") != b.get(k, "<missing>")} - {"transformers_version", "use_aux"}
+assert not diff, diff
+print("surface ok")
+'''
+
+
+def test_forward_signatures_output_fields_and_config_defaults_equal_the_reference(tmp_path):
+    script = tmp_path / "surface.py"
+    script.write_text(_SURFACE_SCRIPT)
+    p = subprocess.run([sys.executable, str(script), ROOT], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "surface ok" in p.stdout, (p.stdout + p.stderr)[-3000:]
