@@ -1,16 +1,30 @@
 #!/usr/bin/env python
-"""bench.py — tokens/sec of the GraphGPT SMTP pre-training step on B200 (BASELINE.json metric).
+"""bench.py — tokens/sec of the GraphGPT training step on B200 (BASELINE.json metric), for each configuration
+BASELINE.json lists.
 
   python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
-  python bench.py --impl reference ...                     (CPU arm: the oracle port on the host cores)
+  python bench.py --config c2|c3|c4|c5 [--layout ...]      (default c2 = the configuration the metric is quoted on)
+  python bench.py --impl reference ...                     (CPU arm: the UNMODIFIED reference on the host cores)
 
-Workload (config.workload): PCQM4M-v2 SMTP pre-training, GraphGPT-B12 = 12L / 768d / 12 heads x 64 / GeGLU 3072,
-F=13 stacked tokens, V=756, sequences of 1024 tokens; synthetic PCQM4M-shaped Eulerian-path samples (mean 23.3 rows)
-packed to 1024 with a block-diagonal attention mask, per-sequence SMTP masking (see graph-gpt_b200/synth.py).
-A step = forward + backward + gradient all-reduce + AdamW over one batch of `--seqs` x 1024 tokens per GPU (weak
-scaling).  `value` = non-pad tokens of all ranks / max-over-ranks device time with inputs resident in HBM;
-`e2e` = same step driven from pinned host batches (H2D copies of ids / labels / mask inside the timed region, loss
-read back every step).  Distinct batches (> L2) are cycled, so no flush is needed between iterations.
+Configurations (shapes from the reference's scripts, data synthetic):
+  c2  PCQM4M-v2 SMTP pre-training, GraphGPT-B12 = 12L/768d/12 heads x 64/GeGLU 3072, F=13 stacked tokens, V=756,
+      sequences of 1024 tokens: PCQM4M-shaped Eulerian-path samples (mean 23.3 rows) packed to 1024 with the collator's
+      block-diagonal [N,S,S] mask (`--layout packed`, default) or one attention span per row (`--layout dense`),
+      attention_dropout 0.1 (examples/graph_lvl/pcqm4m_v2_pretrain.sh:17-29)
+  c3  ogbl-ppa edge-level fine-tune: GraphGPTTaskModel 12L/768d, F=4, V=41 244, right-padded sub-graph sequences
+      (lengths U[256,1024]), LayerScale (lsi=1), DropPath 0.2, attention_dropout 0.1, 2 labels
+      (examples/edge_lvl/ppa_supervised.sh:13-25,78-80)
+  c4  ogbl-citation2 link prediction: GraphGPTTaskModel 12L/768d, gated stacked aggregation, raw 128-d node embeddings
+      (`embed_dim=128`), sequences of up to 4096 rows (lengths U[2048,4096]), DropPath 0.05
+      (examples/edge_lvl/citation2_supervised.sh:29-45; its tokenization json is not shipped: F=2, V=1200 are stand-ins)
+  c5  PCQM4M-v2 NTP causal pre-training, 24L/1024d/16 heads ("large"), F=13, V=756, dense sequences of 2048 rows
+
+A step = forward + backward + gradient all-reduce + AdamW over one batch of `--seqs` sequences per GPU (weak scaling).
+`value` = non-pad tokens of all ranks / max-over-ranks device time with inputs resident in HBM; `e2e` = the same step
+driven from pinned host batches (H2D copies of every input tensor inside the timed region, loss read back every step).
+Distinct batches (> L2) are cycled, so no flush is needed between iterations.  The default (c2) line also carries
+`forward_only`: the inference pass of the same model on the DENSE seq-1024 layout — the north star's "fused
+attention+MLP forward at seq 1024 / d_model 768" figure with its fraction of the measured bf16 peak.
 """
 import argparse
 import json
@@ -23,14 +37,42 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "baseline"))
 
-MODEL = dict(vocab_size=756, hidden_size=768, intermediate_size=3072, num_hidden_layers=12, num_attention_heads=12,
-             num_key_value_heads=12, head_dim=64, hidden_act="gelu", max_position_embeddings=1024, rms_norm_eps=1e-6,
+
+def _model(L, d, V, F_, S, **kw):
+    m = dict(vocab_size=V, hidden_size=d, intermediate_size=4 * d, num_hidden_layers=L, num_attention_heads=d // 64,
+             num_key_value_heads=d // 64, head_dim=64, hidden_act="gelu", max_position_embeddings=S, rms_norm_eps=1e-6,
              rope_theta=10000.0, pad_token_id=0, bos_token_id=20, eos_token_id=19, causal_attention=False,
-             stacked_feat=13, stack_method="short", stacked_feat_agg_method="sum", next_n_token=13, use_cache=False,
-             attention_dropout=0.1)   # examples/graph_lvl/pcqm4m_v2_pretrain.sh:20 — active in the training step
-SEQ = 1024
+             stacked_feat=F_, stack_method="short", stacked_feat_agg_method="sum", next_n_token=F_, use_cache=False,
+             attention_dropout=0.1)
+    m.update(kw)
+    return m
+
+
+_FT = dict(num_labels=2, problem_type="single_label_classification", pooling_method="last")
+CONFIGS = {
+    "c2": dict(model=_model(12, 768, 756, 13, 1024), seq=1024, seqs=64, kind="pretrain", task="smtp", layout="packed",
+               name="pcqm4m-v2-smtp-pretrain-B12(12L/768d/F13/V756)-seq1024", vocab=dict(vocab_size=756, scope=512, n_node_attr=9, n_edge_attr=3),
+               opt=dict(lr=3e-4, betas=(0.9, 0.95), eps=1e-6, weight_decay=0.1)),
+    "c3": dict(model=_model(12, 768, 41244, 4, 1024, path_pdrop=0.2, layer_scale_init_value=1.0, **_FT), seq=1024, seqs=64,
+               kind="finetune", layout="padded", name="ogbl-ppa-edge-finetune-B12(12L/768d/F4/V41244/lsi1/pdp0.2)-seq1024",
+               vocab=dict(vocab_size=41244, scope=512, n_node_attr=2, n_edge_attr=1), min_frac=0.25,
+               opt=dict(lr=3e-5, betas=(0.9, 0.99), eps=1e-10, weight_decay=0.0)),
+    "c4": dict(model=_model(12, 768, 1200, 2, 4096, path_pdrop=0.05, stacked_feat_agg_method="gated", embed_dim=128, **_FT),
+               seq=4096, seqs=16, kind="finetune", layout="padded",
+               name="ogbl-citation2-linkpred-B12(12L/768d/F2/gated/embed128/pdp0.05)-seq4096",
+               vocab=dict(vocab_size=1200, scope=512, n_node_attr=1, n_edge_attr=0), min_frac=0.5,
+               opt=dict(lr=3e-5, betas=(0.9, 0.99), eps=1e-10, weight_decay=0.0)),
+    "c5": dict(model=_model(24, 1024, 756, 13, 2048, causal_attention=True), seq=2048, seqs=16, kind="pretrain", task="ntp",
+               layout="dense", name="pcqm4m-v2-ntp-causal-pretrain-L24(24L/1024d/F13/V756)-seq2048",
+               vocab=dict(vocab_size=756, scope=512, n_node_attr=9, n_edge_attr=3),
+               opt=dict(lr=3e-4, betas=(0.9, 0.95), eps=1e-6, weight_decay=0.1)),
+}
 METRIC = "tokens/sec (device-timed) PCQM4M-v2 SMTP pretrain"
+METRICS = {"c2": METRIC, "c3": "tokens/sec (device-timed) ogbl-ppa edge-level fine-tune",
+           "c4": "tokens/sec (device-timed) ogbl-citation2 link-pred fine-tune seq 4096",
+           "c5": "tokens/sec (device-timed) PCQM4M-v2 NTP causal pretrain 24L/1024d seq 2048"}
 
 
 def parse():
@@ -39,94 +81,230 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--seqs", type=int, default=64, help="sequences of 1024 tokens per GPU per step")
-    ap.add_argument("--layout", default="packed", choices=["packed", "dense"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--seqs", type=int, default=0, help="sequences per GPU per step (default: the configuration's)")
+    ap.add_argument("--layout", default=None, choices=["packed", "dense"], help="c2 only: packed (default) or dense")
     ap.add_argument("--batches", type=int, default=4, help="distinct synthetic batches cycled through")
     ap.add_argument("--mask-format", default="reference", choices=["reference", "segments"],
                     help="packed layout only: 'reference' = the collator's int64 [N,S,S] block-diagonal mask (default, the "
                          "reference-facing contract); 'segments' = the [N,S] segment-id mask of graphgpt_b200.packing")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--fwd-only", action="store_true", help="also report the forward-only pass (inference mode)")
-    return ap.parse_args()
+    ap.add_argument("--no-fwd-only", action="store_true", help="skip the forward-only (inference) measurement")
+    a = ap.parse_args()
+    cfg = CONFIGS[a.config]
+    if a.layout is None or a.config != "c2":
+        a.layout = cfg["layout"]
+    if a.seqs <= 0:
+        a.seqs = cfg["seqs"]
+    return a
 
 
-def flops_per_token(layout, batch_stats):
-    """Forward model FLOPs per token: L*(8d^2 + 6dI + 4*S_vis*d) + head."""
-    d, I, L, F, V = 768, 3072, 12, 13, 756
-    s_vis = batch_stats["s_vis"]
-    backbone = L * (8 * d * d + 6 * d * I + 4 * s_vis * d)
-    head = batch_stats["row_frac"] * 2 * d * d * F + batch_stats["entry_per_tok"] * 2 * d * V
-    return backbone + head
-
-
-def batch_stats(b, layout):
+# ------------------------------------------------------------------------------------------------------------------
+# synthetic workload
+# ------------------------------------------------------------------------------------------------------------------
+def make_host_batch(cfgname, layout, n_seq, seed, mask_format="reference"):
+    """numpy batch dict with the collator's keys for this configuration (+ 'segment_lens' for the statistics)."""
     import numpy as np
+
+    from graphgpt_b200 import synth
+    c = CONFIGS[cfgname]
+    vocab = synth.VocabLayout(**c["vocab"])
+    S = c["seq"]
+    if c["kind"] == "finetune":
+        return synth.make_ft_batch(n_seq, S, vocab=vocab, seed=seed, min_frac=c["min_frac"],
+                                   embed_dim=c["model"].get("embed_dim", 0))
+    b = synth.make_batch(n_seq, S, layout=layout, task=c["task"], vocab=vocab, seed=seed, return_segments=True)
+    if layout == "packed" and mask_format == "segments":
+        seg = np.zeros((n_seq, S), np.int64)
+        for n_, lens in enumerate(b["segment_lens"]):
+            seg[n_] = np.repeat(np.arange(1, len(lens) + 1), lens)[:S]
+        b["attention_mask"] = seg
+    return b
+
+
+def model_inputs(cfgname, b):
+    """The tensors the reference's training loop hands to forward() for this configuration (training_utils.py:30-37 for
+    pre-training — position_ids are NOT passed; :136-145 for fine-tuning)."""
+    if CONFIGS[cfgname]["kind"] == "finetune":
+        keys = {"input_ids": "input_ids", "attention_mask": "attention_mask", "position_ids": "position_ids",
+                "task_labels": "edge_labels"}
+        if "embed" in b:
+            keys["inputs_raw_embeds"] = "embed"
+        return {k: b[v] for k, v in keys.items()}
+    return {k: b[k] for k in ("input_ids", "attention_mask", "labels")}
+
+
+def batch_stats(cfgname, layout, b):
+    c = CONFIGS[cfgname]
     lab = b["labels"]
     N, S = lab.shape[:2]
-    mask = lab != -100
-    st = {"row_frac": float(mask.any(-1).mean()), "entry_per_tok": float(mask.sum() / (N * S))}
-    if layout == "packed":
-        segs = b["segment_lens"]
-        st["s_vis"] = float(sum(l * l for row in segs for l in row) / (N * S))
+    segs = b["segment_lens"] if layout != "dense" else [[S]] * N     # attention spans (dense: the whole row)
+    tokens = float(sum(sum(row) for row in segs))
+    if c["kind"] == "pretrain":
+        mask = (lab != -100).reshape(N, S, -1)
+        st = {"row_frac": float(mask.any(-1).sum() / tokens), "entry_per_tok": float(mask.sum() / tokens)}
     else:
+        st = {"row_frac": 0.0, "entry_per_tok": 0.0}
+    if c["model"]["causal_attention"]:
+        st["s_vis"] = float(sum(l * (l + 1) / 2 for row in segs for l in row) / tokens)
+    elif layout == "dense":
         st["s_vis"] = float(S)
+    else:
+        st["s_vis"] = float(sum(l * l for row in segs for l in row) / tokens)
+    st["tokens"] = tokens
     return st
 
 
+def flops_per_token(cfgname, st):
+    """Forward model FLOPs per non-pad token: L*(8d^2 + 6dI + 4*S_vis*d) + head."""
+    m = CONFIGS[cfgname]["model"]
+    d, I, L, F, V = m["hidden_size"], m["intermediate_size"], m["num_hidden_layers"], m["stacked_feat"], m["vocab_size"]
+    backbone = L * (8 * d * d + 6 * d * I + 4 * st["s_vis"] * d)
+    head = st["row_frac"] * 2 * d * d * F + st["entry_per_tok"] * 2 * d * V
+    return backbone + head
+
+
+def workload_name(args):
+    n = CONFIGS[args.config]["name"]
+    if args.config == "c2":
+        n += f"-{args.layout}"
+        if args.layout == "packed" and getattr(args, "mask_format", "reference") == "segments":
+            n += "-segment-id-mask"
+    return n
+
+
+def bench_config(args, world, st, fpt):
+    """`config` of the JSON line — identical for the b200 and the reference arm (the reference times a bounded sample of
+    this workload; what the sample was is stated in cpu_baseline.sample)."""
+    c = CONFIGS[args.config]
+    return {"workload": workload_name(args), "seq_len": c["seq"], "seqs_per_gpu": args.seqs,
+            "tokens_per_step_per_gpu": st["tokens"], "parallelism": f"dp{world}",
+            "l2_policy": f"{args.batches} distinct batches cycled; activations per step >> 126 MB L2",
+            "mean_visible_keys": st["s_vis"], "fwd_mflop_per_token": fpt / 1e6}
+
+
+def workload_stats(args, rank=0):
+    stats = [batch_stats(args.config, args.layout, make_host_batch(args.config, args.layout, args.seqs, 1234 + 1000 * rank + i))
+             for i in range(args.batches)]
+    return {k: sum(s[k] for s in stats) / len(stats) for k in stats[0]}
+
+
 # ------------------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port timed on the host cores (reported baseline; the reference is pure Python/torch and
-# cannot travel to the GPU box, so kind = "port")
+# CPU arm.  kind "reference": the reference's own classes (GraphGPTPretrainBase / GraphGPTTaskModel over HF Llama, fp32,
+# default SDPA attention) in their stock training configuration — train mode, gradient checkpointing on as
+# TrainingPipeline always sets it (pipeline.py:163), clip + AdamW (opt_utils.py:18-24, training_utils.py:71-86) — imported
+# from baseline/_ref (a verbatim copy made by baseline/make_ref.py; /root/reference in the build container).
+# kind "port": oracle/graphgpt_oracle.py, fp32 forward + backward without dropout / recomputation (second row).
 # ------------------------------------------------------------------------------------------------------------------
-def cpu_step_tokens_per_s(n_seq, steps, warmup, layout):
+def _cpu_batch(cfgname, layout, n_seq):
+    import torch
+    b = make_host_batch(cfgname, layout, n_seq, 1234)
+    st = batch_stats(cfgname, layout, b)
+    return {k: torch.from_numpy(v) for k, v in model_inputs(cfgname, b).items()}, st["tokens"]
+
+
+def reference_tokens_per_s(cfgname, layout, steps, warmup, n_seq=1):
     import torch
 
-    from graphgpt_b200 import synth
-    from oracle import graphgpt_oracle as oracle
-
+    import ref_loader
+    _, mp, mf, RefCfg = ref_loader.load_reference()
+    c = CONFIGS[cfgname]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    b = synth.make_batch(n_seq, SEQ, layout=layout, seed=1234)
-    ids, am, labels = (torch.from_numpy(b[k]) for k in ("input_ids", "attention_mask", "labels"))
-    sd = {k: v.requires_grad_(True) for k, v in oracle.init_state_dict(MODEL, seed=0).items()}
+    torch.manual_seed(0)
+    cfg = RefCfg(**c["model"])
+    model = (mp.GraphGPTPretrainBase if c["kind"] == "pretrain" else mf.GraphGPTTaskModel)(cfg)
+    model.gradient_checkpointing_enable()
+    model.config.use_cache = False
+    model.train()
+    o = c["opt"]
+    opt = torch.optim.AdamW(model.parameters(), lr=o["lr"], betas=o["betas"], eps=o["eps"], weight_decay=o["weight_decay"])
+    batch, tokens = _cpu_batch(cfgname, layout, n_seq)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        out = oracle.pretrain_forward(sd, MODEL, ids, am, labels)
-        out["loss"].backward()
-        with torch.no_grad():                      # plain SGD-free timing: AdamW cost on CPU is negligible vs fwd/bwd
-            for v in sd.values():
-                v.grad = None
+        opt.zero_grad()
+        out = model(**batch)
+        loss = out.head1_loss if c["kind"] == "pretrain" else out.task_loss
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
-    tok = n_seq * SEQ
     ms = statistics.median(times) * 1e3
-    return tok / (ms / 1e3), ms, cores, f"{n_seq} x {SEQ} tokens ({layout}), fwd+bwd, fp32, {cores} threads, median of {steps}"
+    sample = (f"{n_seq} x {c['seq']} rows ({tokens:.0f} non-pad tokens, {layout}), the reference's own "
+              f"{'GraphGPTPretrainBase' if c['kind'] == 'pretrain' else 'GraphGPTTaskModel'} (HF Llama, SDPA, fp32), train mode, "
+              f"gradient checkpointing on (pipeline.py:163), fwd+bwd+clip+AdamW, {cores} threads, median of {steps}")
+    return tokens / (ms / 1e3), ms, cores, sample
+
+
+def port_tokens_per_s(cfgname, layout, steps, warmup, n_seq=1):
+    import torch
+
+    from oracle import graphgpt_oracle as oracle
+    c = CONFIGS[cfgname]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    batch, tokens = _cpu_batch(cfgname, layout, n_seq)
+    sd = {k: v.requires_grad_(True) for k, v in oracle.init_state_dict(c["model"], seed=0, task_head=c["kind"] == "finetune").items()}
+    if c["model"].get("embed_dim", 0) > 0:
+        E, d = c["model"]["embed_dim"], c["model"]["hidden_size"]
+        sd["embed_layernorm.weight"] = torch.ones(E, requires_grad=True)
+        sd["embed_proj.weight"] = (torch.randn(d, E) * 0.02).requires_grad_(True)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        if c["kind"] == "pretrain":
+            out = oracle.pretrain_forward(sd, c["model"], batch["input_ids"], batch["attention_mask"], batch["labels"])
+        else:
+            out = oracle.task_forward(sd, c["model"], batch["input_ids"], batch["attention_mask"], batch["position_ids"],
+                                      batch["task_labels"], inputs_raw_embeds=batch.get("inputs_raw_embeds"))
+        out["loss"].backward()
+        for v in sd.values():
+            v.grad = None
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    ms = statistics.median(times) * 1e3
+    return tokens / (ms / 1e3), ms, cores, (f"{n_seq} x {c['seq']} rows ({tokens:.0f} non-pad tokens, {layout}), oracle port, fwd+bwd, "
+                                            f"fp32, no dropout / recomputation / optimizer, {cores} threads, median of {steps}")
+
+
+def cpu_baseline(cfgname, layout, steps, warmup):
+    """cpu_baseline object: the real reference when baseline/_ref (or /root/reference) is there, else the port."""
+    try:
+        tps, ms, cores, sample = reference_tokens_per_s(cfgname, layout, steps, warmup)
+        kind = "reference"
+    except Exception as e:   # reference copy missing / not importable: say so and time the port
+        sys.stderr.write(f"[bench] reference arm unavailable ({type(e).__name__}: {e}); timing the oracle port\n")
+        tps, ms, cores, sample = port_tokens_per_s(cfgname, layout, steps, warmup)
+        kind = "port"
+    return {"value": tps, "unit": "tokens/s", "cores": cores, "kind": kind, "sample": sample, "ms_per_step": ms}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_seq = 1
-    steps = max(1, min(args.steps, 3))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    steps = max(1, min(args.steps, 3 if args.config in ("c2", "c3") else 1))
     warm = 1
-    tps, ms, cores, sample = cpu_step_tokens_per_s(n_seq, steps, warm, args.layout)
-    line = {"impl": "reference", "metric": METRIC, "value": tps, "unit": "tokens/s", "n_gpus": args.gpus, "steps": steps,
-            "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args), "seq_len": SEQ, "tokens_per_step": n_seq * SEQ,
-                       "note": "CPU oracle port of the reference path (oracle/graphgpt_oracle.py), bounded sample"},
-            "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    st = workload_stats(args)
+    fpt = flops_per_token(args.config, st)
+    base = cpu_baseline(args.config, args.layout, steps, warm)
+    ms = base.pop("ms_per_step")
+    line = {"impl": "reference", "metric": METRICS[args.config], "value": base["value"], "unit": "tokens/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": bench_config(args, world, st, fpt),
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if base["kind"] == "reference" and args.config == "c2":
+        tps, pms, cores, sample = port_tokens_per_s(args.config, args.layout, steps, warm)
+        line["cpu_baseline_port"] = {"value": tps, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample}
     print(json.dumps(line))
-
-
-def workload_name(args):
-    suffix = "-segment-id-mask" if (args.layout == "packed" and getattr(args, "mask_format", "reference") == "segments") else ""
-    return f"pcqm4m-v2-smtp-pretrain-B12(12L/768d/F13/V756)-seq1024-{args.layout}{suffix}"
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -164,10 +342,11 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
 
-    from graphgpt_b200 import GraphGPTConfig, GraphGPTPretrainBase, synth
+    from graphgpt_b200 import GraphGPTConfig, GraphGPTPretrainBase, GraphGPTTaskModel
     from graphgpt_b200.dp import GraphGPTEngine
     from graphgpt_b200.lib import GEMM_FUNCS, KernelTimer, lib
 
+    c = CONFIGS[args.config]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -182,29 +361,25 @@ def run_b200(args):
     # ---- synthetic batches (host, pinned) -------------------------------------------------------------------
     host, stats = [], []
     for i in range(args.batches):
-        b = synth.make_batch(args.seqs, SEQ, layout=args.layout, seed=1234 + 1000 * rank + i, return_segments=True)
-        stats.append(batch_stats(b, args.layout))
-        if args.layout == "packed" and args.mask_format == "segments":
-            import numpy as np
-            seg = np.zeros((args.seqs, SEQ), np.int64)
-            for n_, lens in enumerate(b["segment_lens"]):
-                seg[n_] = np.repeat(np.arange(1, len(lens) + 1), lens)[:SEQ]
-            b["attention_mask"] = seg
-        host.append({k: torch.from_numpy(b[k]).pin_memory() for k in ("input_ids", "attention_mask", "labels")})
-    tok_per_step = args.seqs * SEQ                                   # packed / dense layouts have no pad tokens
+        b = make_host_batch(args.config, args.layout, args.seqs, 1234 + 1000 * rank + i, args.mask_format)
+        stats.append(batch_stats(args.config, args.layout, b))
+        host.append({k: torch.from_numpy(v).pin_memory() for k, v in model_inputs(args.config, b).items()})
     st = {k: sum(s[k] for s in stats) / len(stats) for k in stats[0]}
-    fpt = flops_per_token(args.layout, st)
+    tok_per_step = st["tokens"]
+    fpt = flops_per_token(args.config, st)
     devb = [{k: v.to(dev, non_blocking=True) for k, v in hb.items()} for hb in host]
 
     torch.manual_seed(0)
-    model = GraphGPTPretrainBase(GraphGPTConfig(**MODEL)).to(dev).train()
-    engine = GraphGPTEngine(model, lr=3e-4, betas=(0.9, 0.95), eps=1e-6, weight_decay=0.1, max_grad_norm=1.0)
+    is_pt = c["kind"] == "pretrain"
+    model = (GraphGPTPretrainBase if is_pt else GraphGPTTaskModel)(GraphGPTConfig(**c["model"])).to(dev).train()
+    engine = GraphGPTEngine(model, max_grad_norm=1.0, **c["opt"])
 
     def step(batch):
-        out = engine(input_ids=batch["input_ids"], attention_mask=batch["attention_mask"], labels=batch["labels"])
-        engine.backward(out.head1_loss)
+        out = engine(**batch)
+        loss = out.head1_loss if is_pt else out.task_loss
+        engine.backward(loss)
         engine.step()
-        return out.head1_loss
+        return loss
 
     def sync_all():
         torch.cuda.synchronize()
@@ -295,20 +470,34 @@ def run_b200(args):
         e2e = {"value": world * tok_per_step / (ms / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": 4, "ms_per_step": ms}
 
-    # ---- forward-only (the north-star "fused attention+MLP forward" figure) ---------------------------------------------
+    # ---- forward-only (inference mode).  For c2 this is the north-star "fused attention+MLP forward at seq 1024 /
+    # d_model 768" figure and is always measured on the DENSE layout (every query sees all 1024 keys) -------------------
     fwd = None
-    if args.fwd_only:
+    if not args.no_fwd_only:
+        f_layout = "dense" if args.config == "c2" else args.layout
+        if f_layout == args.layout:
+            fb, fst = devb, st
+        else:
+            fstats, fb = [], []
+            for i in range(min(2, args.batches)):
+                b = make_host_batch(args.config, f_layout, args.seqs, 4321 + 1000 * rank + i)
+                fstats.append(batch_stats(args.config, f_layout, b))
+                fb.append({k: torch.from_numpy(v).to(dev) for k, v in model_inputs(args.config, b).items()})
+            fst = {k: sum(s[k] for s in fstats) / len(fstats) for k in fstats[0]}
+        f_fpt = flops_per_token(args.config, fst)
         model.eval()
         with torch.no_grad():
             def fstep(i):
-                b = devb[i % len(devb)]
-                return model(input_ids=b["input_ids"], attention_mask=b["attention_mask"], labels=b["labels"]).head1_loss
-            for i in range(2):
+                out = model(**fb[i % len(fb)])
+                return out.head1_loss if is_pt else out.task_loss
+            for i in range(max(2, args.warmup)):
                 fstep(i)
             ms = timed(fstep, args.steps) / args.steps
         model.train()
-        tf = fpt * tok_per_step / (ms / 1e3) / 1e12
-        fwd = {"ms_per_step": ms, "tokens_per_s_per_gpu": tok_per_step / (ms / 1e3), "model_tflops_per_gpu": tf}
+        tf = f_fpt * fst["tokens"] / (ms / 1e3) / 1e12
+        fwd = {"workload": CONFIGS[args.config]["name"] + (f"-{f_layout}" if args.config == "c2" else ""),
+               "ms_per_step": ms, "tokens_per_s_per_gpu": fst["tokens"] / (ms / 1e3), "model_tflops_per_gpu": tf,
+               "mean_visible_keys": fst["s_vis"], "fwd_mflop_per_token": f_fpt / 1e6}
 
     if rank != 0:
         if world > 1:
@@ -329,10 +518,12 @@ def run_b200(args):
     all_ms = total_ms
     top = max(gemm, key=lambda kv: kv[1]["ms"]) if gemm else None
     traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_gemm_traffic.json"))).get("dram_bytes_per_launch")
-    except Exception:
-        pass
+    for name in ("r2_gemm_traffic.json", "r1_gemm_traffic.json"):
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", name))).get("dram_bytes_per_launch")
+            break
+        except Exception:
+            pass
     roofline = {"bound": "tensor", "kernel": "ggpt::gemm_kernel<> (tcgen05 GEMM, all instantiations)",
                 "achieved": g_fl / (g_ms / 1e3) / 1e12 if g_ms > 0 else None, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": (g_fl / (g_ms / 1e3) / 1e12) / peak_tf if g_ms > 0 else None, "traffic": traffic,
@@ -349,23 +540,22 @@ def run_b200(args):
                                "frac": v["flops"] / (v["ms"] / 1e3) / 1e12 / peak_tf}
                               for k, v in sorted(gemm, key=lambda kv: -kv[1]["ms"])]}
     step_tf = 3 * fpt * tok_per_step / (ms_per_step / 1e3) / 1e12
-    line = {"metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+    line = {"metric": METRICS[args.config], "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload_name(args), "seq_len": SEQ, "seqs_per_gpu": args.seqs,
-                       "tokens_per_step_per_gpu": tok_per_step, "parallelism": f"dp{world}",
-                       "l2_policy": f"{args.batches} distinct batches cycled; activations per step >> 126 MB L2",
-                       "mean_visible_keys": st["s_vis"], "fwd_mflop_per_token": fpt / 1e6},
+            "config": bench_config(args, world, st, fpt),
             "model_tflops_per_gpu": step_tf, "model_tflops_frac_of_peak": step_tf / peak_tf,
             "roofline": roofline, "e2e": e2e, "gpu_launches": launches,
             "clocks": clocks_summary(clk_path, local),
             "kernel_ms_per_step": {k: round(v["ms"] / n_prof, 4) for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1]["ms"])}}
     if fwd is not None:
         fwd["frac_of_peak"] = fwd["model_tflops_per_gpu"] / peak_tf
+        fwd["frac_of_burst_peak"] = fwd["model_tflops_per_gpu"] / peaks.get("bf16_tflops", 1590.0)
         line["forward_only"] = fwd
     if not args.no_cpu_baseline and world == 1:
-        tps, ms, cores, sample = cpu_step_tokens_per_s(1, 2, 1, args.layout)
-        line["cpu_baseline"] = {"value": tps, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample}
+        base = cpu_baseline(args.config, args.layout, 2 if args.config in ("c2", "c3") else 1, 1)
+        base.pop("ms_per_step", None)
+        line["cpu_baseline"] = base
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -373,8 +563,8 @@ def run_b200(args):
 
 if __name__ == "__main__":
     a = parse()
-    # stdout must carry exactly ONE JSON line (rank 0): anything libraries print there (e.g. NCCL's version banner)
-    # is diverted to stderr, and the result line is written to the original stdout at the end.
+    # stdout must carry exactly ONE JSON line (rank 0): anything libraries print there (e.g. NCCL's version banner, the
+    # reference's own print() calls) is diverted to stderr, and the result line is written to the original stdout at the end.
     _real_stdout = os.dup(1)
     os.dup2(2, 1)
     _buf = []
@@ -395,4 +585,7 @@ if __name__ == "__main__":
         sys.stdout.flush()
         os.dup2(_real_stdout, 1)
         for line in _buf:
-            os.write(1, (line + "\n").encode())
+            if line.startswith("{"):
+                os.write(1, (line + "\n").encode())
+            else:
+                os.write(2, (line + "\n").encode())

@@ -46,10 +46,17 @@ class GradReducer:
 
 def warmup_decay_lr(step, *, max_lr, min_lr=0.0, warmup_steps=0, total_steps=1, warmup_type="log"):
     """DeepSpeed WarmupDecayLR (deepspeed==0.15.4, ds_config2_pt_bf16.json:15-23; the reference's helper
-    loss_utils.py:186-201 sets min/max lr and the two step counts and leaves `warmup_type` at DeepSpeed's default "log"):
+    loss_utils.py:186-201 sets min/max lr and the two step counts and leaves `warmup_type` at DeepSpeed's default "log"),
+    as a function of DeepSpeed's `last_batch_iteration` (= `step`):
+      step <  0            : min_lr   (get_lr() before the scheduler has stepped)
       step <  warmup_steps : gamma = log(step + 1) / log(warmup_steps)     ("log")   |   step / warmup_steps   ("linear")
       step >= warmup_steps : gamma = max(0, (total_steps - step) / max(1, total_steps - warmup_steps))
-      lr = min_lr + (max_lr - min_lr) * gamma"""
+      lr = min_lr + (max_lr - min_lr) * gamma
+    GraphGPTEngine evaluates it the way the DeepSpeed engine does — the scheduler steps AFTER the optimizer, starting from
+    last_batch_iteration = -1 — so the k-th parameter update runs at warmup_decay_lr(k - 2): the first two updates use
+    min_lr (see GraphGPTEngine.schedule_iteration)."""
+    if step < 0:
+        return min_lr
     if warmup_steps > 0 and step < warmup_steps:
         if warmup_type == "log":
             gamma = math.log(step + 1) / math.log(warmup_steps) if warmup_steps > 1 else 1.0
@@ -60,6 +67,18 @@ def warmup_decay_lr(step, *, max_lr, min_lr=0.0, warmup_steps=0, total_steps=1, 
     else:
         gamma = max(0.0, (total_steps - step) / max(1, total_steps - warmup_steps))
     return min_lr + (max_lr - min_lr) * gamma
+
+
+def write_model_pt(module, ckp_dir):
+    """`<ckp_dir>/model.pt` = the plain fp32 state dict on the CPU.  This is the file the reference's fine-tuning / eval
+    pipeline opens FIRST when it loads a pre-trained checkpoint (`load_from_ckp_with_try`, loader_utils.py:176-220:
+    torch.load(os.path.join(ckp, "model.pt")), falling back to DeepSpeed's zero_to_fp32 only on failure), so a checkpoint
+    written by GraphGPTEngine.save_checkpoint is consumed by the unchanged pipeline."""
+    import os
+    sd = {k: v.detach().to("cpu", copy=True) for k, v in module.state_dict().items()}
+    path = os.path.join(ckp_dir, "model.pt")
+    torch.save(sd, path)
+    return path
 
 
 class GraphGPTEngine:
@@ -96,7 +115,7 @@ class GraphGPTEngine:
         dist.broadcast(self.flat.flat, src=0, group=self.group)
         for p in self.extra:
             dist.broadcast(p.data, src=0, group=self.group)
-        self.flat._bf16_key = None            # force a re-cast of the bf16 copy
+        self.flat.invalidate_bf16()           # the broadcast wrote through raw storage: re-cast the bf16 copy
         self.flat.ensure()
 
     # ---- DeepSpeed-engine-like surface -----------------------------------------------------------
@@ -138,11 +157,20 @@ class GraphGPTEngine:
         if self.world > 1 and not self.overlap_comm:
             self.reducer.reduce_span(0, self.flat.numel)
 
+    @staticmethod
+    def schedule_iteration(updates_done):
+        """DeepSpeed's `last_batch_iteration` in effect during parameter update number `updates_done + 1`: the scheduler
+        starts at -1 and steps once AFTER every optimizer step (DeepSpeedEngine._take_model_step), so update 1 sees -1
+        (WarmupLR.get_lr() -> min_lr), update 2 sees 0, update k sees k - 2."""
+        return updates_done - 1
+
     def step(self):
         self.micro_steps += 1
         if self.micro_steps % self.gas != 0:
             return                            # not a boundary: gradients keep accumulating in the flat buffer
+        sched_it = self.schedule_iteration(self.global_steps)
         self.global_steps += 1
+        self.module._hot.check_device_errors(block=False)
         fp = self.flat
         self.reducer.wait()
         inv_world = 1.0 / self.world
@@ -151,7 +179,7 @@ class GraphGPTEngine:
                 if p.grad is not None:
                     dist.all_reduce(p.grad, group=self.group)
                     p.grad.mul_(inv_world)
-        lr = self.lr_schedule(self.global_steps) if self.lr_schedule is not None else self.lr
+        lr = self.lr_schedule(sched_it) if self.lr_schedule is not None else self.lr
         # frozen parameters (requires_grad = False, e.g. freeze_llama_layers, modules_utils.py:45-54) are skipped entirely —
         # no update, no weight decay, not in the clipping norm — exactly as torch / DeepSpeed optimizers skip them
         spans = self._trainable_spans()
@@ -234,6 +262,7 @@ class GraphGPTEngine:
             sd["client_state"] = client_state or {}
             sd["micro_steps"] = self.micro_steps
             torch.save(sd, os.path.join(save_dir, tag, "ggpt_engine_states.pt"))
+            write_model_pt(self.module, save_dir)
             with open(os.path.join(save_dir, "latest"), "w") as f:
                 f.write(tag)
         if self.world > 1:

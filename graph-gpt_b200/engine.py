@@ -100,6 +100,12 @@ class FlatParams:
             ops.cast_f32_bf16(self.flat, self.flat_bf16)
             self._bf16_key = key
 
+    def invalidate_bf16(self):
+        """Force a re-cast of the bf16 compute copy at the next forward.  ensure() notices in-place edits through
+        `param._version`; edits made through `param.data` (or raw pointers) bypass the version counter — call this after
+        them (GraphGPTEngine does after its parameter broadcast)."""
+        self._bf16_key = None
+
     def mark_bf16_fresh(self):
         """Called by the fused optimizer, which updates fp32 and bf16 copies together through raw pointers."""
         self._bf16_key = sum(p._version for _, p in self.order)
@@ -173,6 +179,46 @@ class HotPath:
         self._rope_tab = None
         self._param_groups = None
         self.grad_ready_hook = None   # callable(first_name, last_name) fired as gradient segments complete
+        # device-side input validation (the reference raises IndexError / a device-side assert for an id or label outside
+        # the vocabulary): kernels set err[0] (input id), err[1] (label), err[2] (position id); the flags are copied to
+        # pinned memory behind every forward and examined — without blocking — at the next forward / optimizer step, or
+        # blocking through check_device_errors()
+        self._err = None
+        self._err_host = None
+        self._err_event = None
+
+    _ERR_TEXT = ("input_ids holds a token id outside [0, vocab_size)", "labels holds a target outside [0, vocab_size) other "
+                 "than -100", "position_ids holds a position outside the rotary table")
+
+    def err_flags(self, device):
+        if self._err is None or self._err.device != device:
+            self._err = torch.zeros((4,), device=device, dtype=torch.int32)
+            self._err_host = torch.zeros((4,), dtype=torch.int32, pin_memory=True)
+            self._err_event = None
+        return self._err
+
+    def post_error_flags(self):
+        """Queue the D2H copy of the flags behind the kernels launched so far."""
+        if self._err is not None:
+            self._err_host.copy_(self._err, non_blocking=True)
+            self._err_event = torch.cuda.Event()
+            self._err_event.record()
+
+    def check_device_errors(self, block=True):
+        """Raise IndexError if a kernel of an earlier forward saw an out-of-range id / label / position.  block=False only
+        looks when the copy has already landed (no host wait)."""
+        ev = self._err_event
+        if ev is None:
+            return
+        if not block and not ev.query():
+            return
+        ev.synchronize()
+        self._err_event = None
+        flags = self._err_host.tolist()
+        if any(flags):
+            self._err.zero_()
+            msgs = [t for f, t in zip(flags, self._ERR_TEXT) if f]
+            raise IndexError("graphgpt_b200: " + "; ".join(msgs) + " (vocab_size = %d)" % self.V)
 
     # ------------------------------------------------------------------ helpers
     def rope_tables(self, max_pos, device):
@@ -209,7 +255,13 @@ class HotPath:
         pos = position_ids.reshape(-1).to(torch.int32)
         max_pos = max(S, self.cfg.max_position_embeddings)
         cos, sin = self.rope_tables(max_pos, device)
-        return pos.contiguous(), cos, sin
+        # HF computes cos/sin from the position VALUES and accepts anything; the kernels index a table of cos.shape[0] rows,
+        # so out-of-range positions are flagged (IndexError at the next forward / step, check_device_errors()) and clamped
+        n_rows = cos.shape[0]
+        bad = ((pos < 0) | (pos >= n_rows)).any().to(torch.int32)
+        flag = self.err_flags(device)[2:3]
+        flag.copy_(torch.maximum(flag, bad.reshape(1)))
+        return pos.clamp(0, n_rows - 1).contiguous(), cos, sin
 
     def _layer_names(self, i):
         p = f"model.layers.{i}."
@@ -227,7 +279,8 @@ class HotPath:
         d, H = self.d, self.H
         gate = fp.w("stacked_feat_agg.weight") if "stacked_feat_agg.weight" in fp.offsets else None
         long_scale = getattr(cfg, "stack_method", None) == "long" and ids2d.shape[1] > 1
-        err = torch.zeros((1,), device=dev, dtype=torch.int32)
+        self.check_device_errors(block=False)
+        err = self.err_flags(dev)[0:1]
         # dropout (training only): one 62-bit seed per forward drawn from torch's CPU generator (so torch.manual_seed
         # controls it).  Attention (HF:217): layer i uses seed + i; the element dropouts use mix_seed streams.
         # Every mask is a pure function of (seed, index), regenerated by the backward pass — nothing is stored.
@@ -458,15 +511,19 @@ class PretrainHeadFn(torch.autograd.Function):
         fp = hot.flat
         head_w, proj_w, V = head
         V = hot.V if V is None else V
-        d, F_ = hot.d, labels2d.shape[1]
-        hi = ops.head_compact(labels2d)
+        hi = labels2d if isinstance(labels2d, ops.HeadIndex) else ops.head_compact(labels2d)
+        d, F_ = hot.d, hi.F
         M, L = hi.sync_counts()
         has_proj = proj_w is not None and proj_w in fp.offsets
         if M == 0:
+            # no labelled entry: CrossEntropyLoss over zero targets is NaN in the reference too, and its backward still
+            # runs (zero gradients) — under data parallelism every rank must keep issuing its gradient exchanges
             loss = torch.full((), float("nan"), device=hf.device, dtype=F32)
-            ctx.empty = True
-            ctx.mark_non_differentiable()
-            return loss, torch.empty((0, V), device=hf.device, dtype=F32)
+            ctx.hot, ctx.empty, ctx.T = hot, True, hf.shape[0]
+            logits = torch.empty((0, V), device=hf.device, dtype=F32)
+            ctx.mark_non_differentiable(logits)
+            hot.post_error_flags()
+            return loss, logits
         hsel = ops.gather_rows(hf, hi.sel_rows, M)
         if has_proj:
             proj = ops.gemm(hsel, fp.wb(proj_w))                                     # [M, F*d]
@@ -477,7 +534,8 @@ class PretrainHeadFn(torch.autograd.Function):
         wgt = ent_wgt_fn(hi, L) if ent_wgt_fn is not None else None
         # FocalLoss only on the unweighted branch (modeling_pretrain.py:221-236: the dLM loss ignores focal_gamma)
         focal = float(getattr(hot.cfg, "focal_gamma", 0.0) or 0.0) if wgt is None else 0.0
-        row_lse, _, sums = ops.ce_fwd(logits, hi.ent_label, V, wgt, err_flag=None, focal_gamma=focal)
+        row_lse, _, sums = ops.ce_fwd(logits, hi.ent_label, V, wgt, err_flag=hot.err_flags(hf.device)[1:2], focal_gamma=focal)
+        hot.post_error_flags()
         if loss_mode == "mean":
             ls = ops.ce_finalize(sums, hi.counts.data_ptr() + 4, 0)
         else:                                                                       # dLM: sum / (N*S*F)
@@ -493,7 +551,9 @@ class PretrainHeadFn(torch.autograd.Function):
     def backward(ctx, gloss, _glogits):
         n_in = len(ctx.needs_input_grad)
         if ctx.empty:
-            return (None,) * n_in
+            ctx.hot.flat.prepare_grads()
+            dhf = torch.zeros((ctx.T, ctx.hot.d), device=gloss.device, dtype=BF16)
+            return (None, dhf) + (None,) * (n_in - 2)
         hot, hi, M, L = ctx.hot, ctx.hi, ctx.M, ctx.L
         fp = hot.flat
         d, V = hot.d, ctx.V

@@ -19,6 +19,7 @@ from torch import nn
 from transformers import LlamaConfig
 from transformers.utils import ModelOutput
 
+from . import precise
 from .engine import PRETRAIN_HEAD, BackboneFn, HotPath, PretrainHeadFn
 
 # GraphGPT-specific config fields and their defaults (same names as the reference so YAML / checkpoints map 1:1).
@@ -295,6 +296,14 @@ class _GraphGPTBase(nn.Module):
     def num_parameters(self):
         return sum(p.numel() for p in self.parameters())
 
+    def check_device_errors(self):
+        """Blocks until the kernels launched so far have run and raises IndexError if any of them met a token id / label
+        outside the vocabulary or a position outside the rotary table (the reference fails with IndexError / a device-side
+        assert).  Without this call the same error surfaces at the next forward() or optimizer step."""
+        if self._hot is not None:
+            torch.cuda.current_stream().synchronize()
+            self._hot.check_device_errors(block=True)
+
     # ---- shared forward pieces ----------------------------------------------------------------------
     def _prep_ids(self, input_ids):
         if input_ids is None:
@@ -360,6 +369,11 @@ class _GraphGPTBase(nn.Module):
             ids2d = ids2d.to(dev)
         if attention_mask is not None and attention_mask.device != dev:
             attention_mask = attention_mask.to(dev)
+        if precise.enabled():
+            # validation-only fp32 forward (split-bf16 operands through the same tcgen05 GEMM); see precise.py
+            if self.training or torch.is_grad_enabled():
+                raise RuntimeError("GGPT_PRECISE=1 is a validation-only inference mode: call model.eval() under torch.no_grad()")
+            return precise.backbone_forward(hot, ids2d, N, S, attention_mask, position_ids, raw), in_, N, S
         dps = self._droppath_scales(N, S, dev)
         attn_drop = float(getattr(cfg, "attention_dropout", 0.0) or 0.0) if self.training else 0.0
         # the reference swaps in the dropout MLP only together with the dropout backbone (modeling_common.py:148-169,
@@ -411,11 +425,22 @@ class GraphGPTPretrainBase(_GraphGPTBase):
             # smtp_inside), modeling_pretrain.py:134-137
             raw = self._raw_embed_inputs(inputs_raw_embeds, input_ids.shape[0], input_ids.shape[1], labels,
                                          1 if self.smtp_inside else labels.reshape(labels.shape[0], labels.shape[1], -1).shape[-1])
+        hi = None
+        if labels is not None and not precise.enabled():
+            # label compaction first: its two counts travel to the host while the backbone runs (ops.HeadIndex)
+            from . import ops
+            lab2d = labels.to(self.device).reshape(labels.shape[0] * labels.shape[1], -1).contiguous()
+            self.hot                                         # flat buffers / library are validated before the first launch
+            hi = ops.head_compact(lab2d)
         hf, in_, N, S = self._run_backbone(input_ids, attention_mask, position_ids, raw)
         hot = self._hot
         dev = hf.device
         loss = None
         if labels is None:
+            hot.post_error_flags()
+        if labels is None and precise.enabled():
+            logits = precise.head_all_entries(hot, hf)
+        elif labels is None:
             # inference / generation: every (n,s,f) entry gets logits (modeling_helpers.py:284-292)
             from . import ops
             fp = hot.flat
@@ -439,8 +464,11 @@ class GraphGPTPretrainBase(_GraphGPTBase):
 
                 def wgt_fn(hi, L, per_sample=per_sample, S=S):
                     return per_sample[(hi.ent_tok[:L].long() // S)].contiguous()
-            params = [p for _, p in hot.flat.order]
-            loss, logits = PretrainHeadFn.apply(hot, hf, lab2d, N, S, wgt_fn, mode, PRETRAIN_HEAD, *params)
+            if precise.enabled():
+                loss, logits = precise.labelled_head(hot, hf, lab2d, N, S, wgt_fn, mode, PRETRAIN_HEAD)
+            else:
+                params = [p for _, p in hot.flat.order]
+                loss, logits = PretrainHeadFn.apply(hot, hf, hi, N, S, wgt_fn, mode, PRETRAIN_HEAD, *params)
         return DoubleHeadsModelOutput(head1_loss=loss, head1_logits=logits, head2_loss=None, head2_logits=None,
                                       past_key_values=None, hidden_states=None, attentions=None)
 
@@ -515,6 +543,7 @@ class GraphGPTTaskModel(_GraphGPTBase):
         if cfg.embed_dim > 0:
             raw = self._raw_embed_inputs(inputs_raw_embeds, input_ids.shape[0], input_ids.shape[1], None, 0)
         hf, in_, N, S = self._run_backbone(input_ids, attention_mask, position_ids, raw)
+        self._hot.post_error_flags()
         dev = hf.device
         hidden = hf.view(N, S, -1)
         if cfg.pad_token_id is None:
@@ -549,7 +578,10 @@ class GraphGPTTaskModel(_GraphGPTBase):
                                       "problem_type != 'regression')")
         nl = self.num_labels
         with torch.no_grad():
-            logits = ops.gemm(hf.detach(), hot.flat.wb("score.weight"), out_dtype=torch.float32)
+            if precise.enabled():
+                logits = precise.linear(hf, hot.flat.w("score.weight"))
+            else:
+                logits = ops.gemm(hf.detach(), hot.flat.wb("score.weight"), out_dtype=torch.float32)
         task_loss = None
         if task_labels is not None:
             if self.config.problem_type is None:
@@ -557,8 +589,11 @@ class GraphGPTTaskModel(_GraphGPTBase):
             if self.config.problem_type != "single_label_classification":
                 raise NotImplementedError(f"token_ce with problem_type={self.config.problem_type!r}")
             lab2d = task_labels.to(hf.device).reshape(N * S, 1).contiguous()
-            params = [p for _, p in hot.flat.order]
-            task_loss, _ = PretrainHeadFn.apply(hot, hf, lab2d, N, S, None, "mean", ("score.weight", None, nl), *params)
+            if precise.enabled():
+                task_loss, _ = precise.labelled_head(hot, hf, lab2d, N, S, None, "mean", ("score.weight", None, nl))
+            else:
+                params = [p for _, p in hot.flat.order]
+                task_loss, _ = PretrainHeadFn.apply(hot, hf, lab2d, N, S, None, "mean", ("score.weight", None, nl), *params)
         return DoubleHeadsModelOutput(pretrain_loss=None, task_loss=task_loss, pretrain_logits=None,
                                       task_logits=logits.reshape(N, S, nl), past_key_values=None, hidden_states=hidden,
                                       task_hidden_states=pooled_hidden, attentions=None)
@@ -620,12 +655,18 @@ class GraphGPTDoubleHeadsModel(GraphGPTTaskModel):
             hot = self._hot
             if pretrain_labels is not None:
                 lab2d = pretrain_labels.to(hf.device).reshape(N * S, 1).contiguous()
-                params = [p for _, p in hot.flat.order]
-                pretrain_loss, _ = PretrainHeadFn.apply(hot, hf, lab2d, N, S, None, "mean", ("lm_head.weight", None, None),
-                                                        *params)
+                if precise.enabled():
+                    pretrain_loss, _ = precise.labelled_head(hot, hf, lab2d, N, S, None, "mean", ("lm_head.weight", None, None))
+                else:
+                    params = [p for _, p in hot.flat.order]
+                    pretrain_loss, _ = PretrainHeadFn.apply(hot, hf, lab2d, N, S, None, "mean",
+                                                            ("lm_head.weight", None, None), *params)
             if not self.training:
                 with torch.no_grad():
-                    pretrain_logits = ops.gemm(hf.detach(), hot.flat.wb("lm_head.weight")).reshape(N, S, -1)
+                    if precise.enabled():
+                        pretrain_logits = precise.linear(hf, hot.flat.w("lm_head.weight")).reshape(N, S, -1)
+                    else:
+                        pretrain_logits = ops.gemm(hf.detach(), hot.flat.wb("lm_head.weight")).reshape(N, S, -1)
         self._last_backbone = None
         return DoubleHeadsModelOutput(pretrain_loss=pretrain_loss, task_loss=res.task_loss, pretrain_logits=pretrain_logits,
                                       task_logits=res.task_logits, past_key_values=None, hidden_states=None, attentions=None)

@@ -368,15 +368,26 @@ def geglu_bwd(dact, gu):
 
 
 class HeadIndex:
-    """Device-side compaction of the labelled rows / entries (modeling_helpers.py:263-301)."""
+    """Device-side compaction of the labelled rows / entries (modeling_helpers.py:263-301).
+
+    (M, L) = (#rows with a label, #labelled entries) size the head GEMMs and the returned [L, V] logits, so the host needs
+    them.  The compaction is launched at the START of forward() and the two counts are copied to pinned host memory right
+    behind it; the head reads them ~a whole backbone later, when the copy has long completed — the wait is an event that is
+    already signalled, and the device never runs dry because of it (the reference's `hidden_states[mask_m]`,
+    modeling_helpers.py:288, drains the stream in the middle of every step)."""
 
     def __init__(self, counts, sel_rows, ent_src, ent_label, ent_tok):
         self.counts, self.sel_rows, self.ent_src, self.ent_label, self.ent_tok = counts, sel_rows, ent_src, ent_label, ent_tok
         self.M = self.L = None
+        self._host = torch.empty((2,), dtype=torch.int32, pin_memory=True)
+        self._host.copy_(counts, non_blocking=True)
+        self._event = torch.cuda.Event()
+        self._event.record()
 
     def sync_counts(self):
         if self.M is None:
-            self.M, self.L = (int(v) for v in self.counts.tolist())  # the one D2H read of the step
+            self._event.synchronize()
+            self.M, self.L = (int(v) for v in self._host.tolist())
         return self.M, self.L
 
 
@@ -393,7 +404,9 @@ def head_compact(labels):
     ent_tok = torch.empty((T * F_,), device=dev, dtype=torch.int32)
     lib.ggpt_head_compact(labels.data_ptr(), T, F_, scratch.data_ptr(), counts.data_ptr(), sel_rows.data_ptr(),
                           ent_src.data_ptr(), ent_label.data_ptr(), ent_tok.data_ptr(), _stream())
-    return HeadIndex(counts, sel_rows, ent_src, ent_label, ent_tok)
+    hi = HeadIndex(counts, sel_rows, ent_src, ent_label, ent_tok)
+    hi.F = F_
+    return hi
 
 
 def gather_rows(src, idx, n, *, n_ptr=None):

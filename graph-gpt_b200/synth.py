@@ -222,6 +222,28 @@ def make_batch(n_seq, seq_len, *, layout="packed", task="smtp", vocab: VocabLayo
     return batch
 
 
+def make_ft_batch(n_seq, seq_len, *, vocab: VocabLayout = PPA_VOCAB, seed=1234, min_frac=0.25, embed_dim=0, num_labels=2):
+    """Edge-level fine-tuning batch shaped like ft_batch_training's input (training_utils.py:98-205): right-padded
+    [N,S] sequences (sub-graph samples of varying length, the longest one filling seq_len), `position_ids`,
+    `edge_labels` ~ Bernoulli(0.5) (tokenizer_utils.py:571-633 appends the two target-node rows; here they are just the
+    last two valid rows), `labels` all -100 (no auxiliary LM loss), optional raw node embeddings `embed` [N,S,E]."""
+    rng = np.random.default_rng(seed + 7)
+    b = make_batch(n_seq, seq_len, layout="dense", task="ntp", vocab=vocab, seed=seed)
+    lens = rng.integers(max(2, int(seq_len * min_frac)), seq_len + 1, size=n_seq)
+    lens[0] = seq_len
+    am = (np.arange(seq_len)[None, :] < lens[:, None]).astype(np.int64)
+    ids = b["input_ids"].copy()
+    ids[am == 0] = PAD_ID
+    out = {"input_ids": ids, "attention_mask": am, "position_ids": b["position_ids"],
+           "labels": np.full_like(ids, -100), "edge_labels": rng.integers(0, num_labels, size=n_seq).astype(np.int64),
+           "segment_lens": [[int(l)] for l in lens]}
+    if embed_dim > 0:
+        emb = rng.standard_normal((n_seq, seq_len, embed_dim)).astype(np.float32)
+        emb[am == 0] = 0.0
+        out["embed"] = emb
+    return out
+
+
 def rows_per_sample_stats(n=3000, seed=0, vocab: VocabLayout = PCQM_VOCAB):
     rng = np.random.default_rng(seed)
     lens = np.array([sample_graph_rows(rng, vocab).shape[0] for _ in range(n)])

@@ -273,6 +273,29 @@ int ggpt_adamw(float* p, void* p_bf16, const float* g, float* m, float* v, long 
                float grad_scale, void* stream);
 int ggpt_cast_f32_bf16(const float* src, void* dst, long long n, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Validation-only PRECISE mode (GGPT_PRECISE=1 in the Python host; never on the bench / training path).
+ * Every GEMM still goes through ggpt_gemm_bf16 (the same tcgen05 kernel) on split-bf16 operands — ggpt_vp_split3 writes
+ * an fp32 matrix [R,C] as bf16 [R,3C]: role 0 (A operand) = hi | lo | hi, role 1 (B operand) = hi | hi | lo, with
+ * hi = bf16(x), lo = bf16(x - hi), so that A' B'^T = A_hi B_hi^T + A_lo B_hi^T + A_hi B_lo^T (error ~2^-17) — and the
+ * element-wise steps between the GEMMs run as plain fp32 SIMT kernels straight from the reference formulas.  The mode
+ * exists to show that the fast path's distance from the fp32 reference is bf16 storage rounding and nothing else.
+ * ref: HF:59-64 (RMSNorm), HF:138-168 (RoPE), HF:199-221 (attention), HF:182-184 (GeGLU), HF:325,331 (residual adds),
+ *      modeling_pretrain.py:134-145 / modeling_helpers.py:127-139 (raw-embedding swap + norm).
+ * ------------------------------------------------------------------------------------------- */
+int ggpt_vp_split3(const float* x, long long ldx, void* out, long long ldo, long long R, int C, int role, void* stream);
+int ggpt_vp_rmsnorm_f32(const float* x, const float* w, float* y, long long T, int d, float eps, void* stream);
+int ggpt_vp_raw_embed_f32(const float* raw, const long long* labels, long long ldl, int fchk, const float* mask_tok,
+                          const float* w, float* y, long long T, int E, float eps, void* stream);
+int ggpt_vp_rope_f32(float* qkv, long long ld, const int* pos, const float* cos_tab, const float* sin_tab, long long T,
+                     int rope_cols, void* stream);
+int ggpt_vp_attn_f32(const float* qkv, long long ld, int q_col0, int k_col0, int v_col0, const uint32_t* mask_bits,
+                     float* out, long long ldo, int N, int S, int H, void* stream);
+int ggpt_vp_geglu_f32(const float* gu, long long ldgu, float* act, long long T, int I, void* stream);
+int ggpt_vp_add_f32(const float* x_in, const float* y, long long ldy, const float* colscale, const float* rowscale,
+                    float* x_out, long long T, int d, void* stream);
+int ggpt_vp_gather_rows_f32(const float* src, long long lds, const int* idx, float* out, long long n, int d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,6 +30,25 @@ import torch.nn.functional as F
 
 _EPSILON = 1e-7  # modeling_common.py:44
 
+# Two optional departures from plain fp32, both used by tests only to EXPLAIN the distance between the bf16 tensor-core
+# kernels and the fp32 reference (tests/test_parity_depth_gpu.py):
+#   dtype=torch.bfloat16  — the reference as DeepSpeed-bf16 runs it: parameters, activations and the residual stream in
+#                           bf16, RMSNorm / softmax / RoPE tables / CE internally fp32 exactly as HF:62-67,129-135,216.
+#   emulate_bf16=True     — fp32 arithmetic with a round-to-bf16 at exactly the points where the sm_100a kernels store a
+#                           bf16 tensor (GEMM weights, h = norm(x), q|k|v after RoPE, the un-normalised
+#                           softmax numerators P, the attention output, the o_proj / down_proj outputs, act = gelu(g)*u,
+#                           n_token_proj's output); the residual stream, statistics and accumulations stay fp32.
+_GEMM_WEIGHT_SUFFIXES = ("_proj.weight", "lm_head.weight", "n_token_proj.weight")
+
+
+def _ste_bf16(t):
+    """round-to-nearest-even to bf16, straight-through gradient"""
+    return t + (t.detach().bfloat16().to(t.dtype) - t.detach())
+
+
+def _ident(t):
+    return t
+
 
 # ------------------------------------------------------------------------------------------------
 # config helper
@@ -81,16 +100,19 @@ class OracleConfig:
 # ------------------------------------------------------------------------------------------------
 def rmsnorm(x, w, eps):
     """HF:59-64  LlamaRMSNorm.forward (fp32 throughout here)."""
-    var = x.pow(2).mean(-1, keepdim=True)
-    return w * (x * torch.rsqrt(var + eps))
+    xf = x.to(torch.float32)
+    var = xf.pow(2).mean(-1, keepdim=True)
+    return w * (xf * torch.rsqrt(var + eps)).to(x.dtype)
 
 
-def rope_cos_sin(position_ids, head_dim, theta):
-    """HF:117-135.  position_ids [N,S] -> cos, sin [N,S,head_dim] (fp32; emb = cat(freqs, freqs))."""
-    inv_freq = 1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.int64).float() / head_dim))
+def rope_cos_sin(position_ids, head_dim, theta, dtype=torch.float32):
+    """HF:117-135.  position_ids [N,S] -> cos, sin [N,S,head_dim] (computed in fp32, cast to the activation dtype;
+    emb = cat(freqs, freqs))."""
+    dev = position_ids.device
+    inv_freq = 1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.int64, device=dev).float() / head_dim))
     freqs = position_ids[:, :, None].float() * inv_freq[None, None, :]
     emb = torch.cat((freqs, freqs), dim=-1)
-    return emb.cos(), emb.sin()
+    return emb.cos().to(dtype), emb.sin().to(dtype)
 
 
 def rotate_half(x):
@@ -105,16 +127,16 @@ def apply_rope(q, k, cos, sin):
     return q * cos + rotate_half(q) * sin, k * cos + rotate_half(k) * sin
 
 
-def additive_mask(attention_mask, seq_len, causal, dtype=torch.float32):
+def additive_mask(attention_mask, seq_len, causal, dtype=torch.float32, device=None):
     """Additive [N,1,S,S] mask with 0 / finfo.min.
     bidirectional 2-D: transformers _prepare_4d_attention_mask (modeling_helpers.py:41-42)
     bidirectional 3-D: _expand_mask_from_3d_mask (modeling_helpers.py:51-64)
     causal (config.causal_attention): the 2-D mask goes to LlamaModel, which builds causal AND key-padding
     (HF:398-405 create_causal_mask)."""
     neg = torch.finfo(dtype).min
+    device = attention_mask.device if attention_mask is not None else device
     if attention_mask is None:
-        keep = torch.ones((1, 1, seq_len, seq_len), dtype=torch.bool)
-        N = 1
+        keep = torch.ones((1, 1, seq_len, seq_len), dtype=torch.bool, device=device)
     elif attention_mask.dim() == 2:
         keep = attention_mask[:, None, None, :].bool().expand(-1, 1, seq_len, -1)
     elif attention_mask.dim() == 3:
@@ -122,47 +144,54 @@ def additive_mask(attention_mask, seq_len, causal, dtype=torch.float32):
     else:
         raise NotImplementedError(f"attention_mask of shape {tuple(attention_mask.shape)} is not Implemented")
     if causal:
-        tri = torch.ones((seq_len, seq_len), dtype=torch.bool).tril()
+        tri = torch.ones((seq_len, seq_len), dtype=torch.bool, device=device).tril()
         keep = keep & tri[None, None]
-    out = torch.zeros(keep.shape, dtype=dtype)
+    out = torch.zeros(keep.shape, dtype=dtype, device=device)
     return out.masked_fill(~keep, neg)
 
 
-def attention(q, k, v, mask4d, scaling):
-    """HF:199-221 eager_attention_forward, fp32 softmax."""
+def attention(q, k, v, mask4d, scaling, rnd=None):
+    """HF:199-221 eager_attention_forward, fp32 softmax.  rnd (emulate_bf16): the kernels feed the un-normalised
+    numerators exp(s - max) to the PV product in bf16 and divide by the fp32 sum of the UNROUNDED numerators."""
     w = torch.matmul(q, k.transpose(2, 3)) * scaling
     w = w + mask4d
-    w = F.softmax(w, dim=-1, dtype=torch.float32)
+    if rnd is not None:
+        e = torch.exp(w - w.max(dim=-1, keepdim=True)[0])
+        o = torch.matmul(rnd(e), v) / e.sum(dim=-1, keepdim=True)
+        return o.transpose(1, 2).contiguous()
+    w = F.softmax(w, dim=-1, dtype=torch.float32).to(q.dtype)
     o = torch.matmul(w, v)
     return o.transpose(1, 2).contiguous()
 
 
-def decoder_layer(x, sd, prefix, cfg, cos, sin, mask4d, act_scale=None, mlp_scale=None, path_scale=None):
+def decoder_layer(x, sd, prefix, cfg, cos, sin, mask4d, act_scale=None, mlp_scale=None, path_scale=None, rnd=None):
     """HF:313-332 LlamaDecoderLayer.forward (+ LayerScale of utils_graphgpt.py:153-166).  act_scale / mlp_scale are the
     training-mode nn.Dropout factors keep/(1-p) of mlp_act_dropout [N,S,I] and mlp_dropout [N,S,d]
     (utils_graphgpt.py:69-83) supplied by the caller — None = eval mode (identity).  path_scale = (s1, s2): the DropPath
     factors floor(keep + u)/keep per sample ([N]) of the attention and the MLP branch (utils_graphgpt.py:156,166)."""
     N, S, d = x.shape
     H, hd = cfg.num_attention_heads, cfg.head_dim
-    h = rmsnorm(x, sd[prefix + "input_layernorm.weight"], cfg.rms_norm_eps)
+    r = rnd or _ident                  # emulate_bf16: the kernels' bf16 stores (weights are pre-rounded by the caller)
+    h = r(rmsnorm(x, sd[prefix + "input_layernorm.weight"], cfg.rms_norm_eps))
     q = F.linear(h, sd[prefix + "self_attn.q_proj.weight"]).view(N, S, H, hd).transpose(1, 2)   # HF:262
     k = F.linear(h, sd[prefix + "self_attn.k_proj.weight"]).view(N, S, H, hd).transpose(1, 2)
     v = F.linear(h, sd[prefix + "self_attn.v_proj.weight"]).view(N, S, H, hd).transpose(1, 2)
     q, k = apply_rope(q, k, cos, sin)
-    a = attention(q, k, v, mask4d, hd ** -0.5).reshape(N, S, H * hd)
-    a = F.linear(a, sd[prefix + "self_attn.o_proj.weight"])
+    q, k, v = r(q), r(k), r(v)
+    a = r(attention(q, k, v, mask4d, hd ** -0.5, rnd).reshape(N, S, H * hd))
+    a = r(F.linear(a, sd[prefix + "self_attn.o_proj.weight"]))
     if prefix + "lambda_1" in sd:
         a = sd[prefix + "lambda_1"] * a
     if path_scale is not None and path_scale[0] is not None:
         a = a * path_scale[0][:, None, None]
     x = x + a
-    h = rmsnorm(x, sd[prefix + "post_attention_layernorm.weight"], cfg.rms_norm_eps)
+    h = r(rmsnorm(x, sd[prefix + "post_attention_layernorm.weight"], cfg.rms_norm_eps))
     g = F.linear(h, sd[prefix + "mlp.gate_proj.weight"])
     u = F.linear(h, sd[prefix + "mlp.up_proj.weight"])
-    act = F.gelu(g) * u                                                # exact erf GELU, HF:182-184
+    act = r(F.gelu(g) * u)                                             # exact erf GELU, HF:182-184
     if act_scale is not None:
         act = act * act_scale                                          # utils_graphgpt.py:80
-    m = F.linear(act, sd[prefix + "mlp.down_proj.weight"])
+    m = r(F.linear(act, sd[prefix + "mlp.down_proj.weight"]))
     if mlp_scale is not None:
         m = m * mlp_scale                                              # utils_graphgpt.py:81
     if prefix + "lambda_2" in sd:
@@ -219,29 +248,30 @@ def raw_embed_branch(inputs_raw_embeds, sd, cfg, labels=None, smtp_inside=False,
     return F.linear(x, sd["embed_proj.weight"])
 
 
-def backbone(inputs_embeds, attention_mask, position_ids, sd, cfg, collect=None, drop=None):
+def backbone(inputs_embeds, attention_mask, position_ids, sd, cfg, collect=None, drop=None, rnd=None):
     """HF:375-425 LlamaModel.forward over `inputs_embeds`; returns the final-norm hidden states [N,S,d].
     drop: optional {"act": [L x [N,S,I]], "mlp": [L x [N,S,d]]} dropout factors (training mode)."""
     N, S, _ = inputs_embeds.shape
+    dev, dt = inputs_embeds.device, inputs_embeds.dtype
     if position_ids is None:
-        position_ids = torch.arange(S)[None, :].expand(N, -1)          # HF:394-397
-    cos, sin = rope_cos_sin(position_ids, cfg.head_dim, cfg.rope_theta)
-    mask4d = additive_mask(attention_mask, S, cfg.causal_attention)
+        position_ids = torch.arange(S, device=dev)[None, :].expand(N, -1)          # HF:394-397
+    cos, sin = rope_cos_sin(position_ids, cfg.head_dim, cfg.rope_theta, dt)
+    mask4d = additive_mask(attention_mask, S, cfg.causal_attention, dt, dev)
     x = inputs_embeds
     for i in range(cfg.num_hidden_layers):
         x = decoder_layer(x, sd, f"model.layers.{i}.", cfg, cos, sin, mask4d,
                           None if drop is None or "act" not in drop else drop["act"][i],
                           None if drop is None or "mlp" not in drop else drop["mlp"][i],
-                          None if drop is None or "path" not in drop else drop["path"][i])
+                          None if drop is None or "path" not in drop else drop["path"][i], rnd)
         if collect is not None:
             collect.append(x)
-    return rmsnorm(x, sd["model.norm.weight"], cfg.rms_norm_eps)
+    return (rnd or _ident)(rmsnorm(x, sd["model.norm.weight"], cfg.rms_norm_eps))
 
 
 # ------------------------------------------------------------------------------------------------
 # pre-training head (SMTP / NTP)
 # ------------------------------------------------------------------------------------------------
-def head_select(hidden, labels, sd, cfg, sample_wgt=None):
+def head_select(hidden, labels, sd, cfg, sample_wgt=None, rnd=None):
     """prepare_for_stacked_feat_labels (modeling_helpers.py:362-393).
 
     short & wgt None -> _prepare_for_stacked_feat_labels_per_mix_lvl (:263-301): rows with any label, n_token_proj,
@@ -250,7 +280,8 @@ def head_select(hidden, labels, sd, cfg, sample_wgt=None):
     long             -> per-feat lvl with normalised weights (:327-342)."""
     d = hidden.shape[-1]
     F_ = cfg.next_n_token
-    proj = (lambda t: F.linear(t, sd["n_token_proj.weight"])) if F_ > 1 else (lambda t: t)
+    r = rnd or _ident
+    proj = (lambda t: r(F.linear(t, sd["n_token_proj.weight"]))) if F_ > 1 else (lambda t: t)
     wgt = None
     if labels is None:
         h = proj(hidden.reshape(-1, d)).reshape(-1, d)
@@ -309,20 +340,37 @@ def ce_loss(logits, labels, wgt=None, dlm=False, focal_gamma=0.0):
     return (loss * w).sum() / (w.sum() + _EPSILON)
 
 
+def _prep_sd(sd, dtype, emulate_bf16):
+    """fp32 (default) / bf16 copies of the parameters; emulate_bf16 rounds the GEMM weights (the kernels' bf16 compute
+    copy) and leaves norms, LayerScale, gates and the embedding table (read in fp32 by embed_fwd) alone."""
+    out = {}
+    for k, v in sd.items():
+        if not v.is_floating_point():
+            out[k] = v
+            continue
+        v = v.to(dtype)
+        if emulate_bf16 and (k.endswith(_GEMM_WEIGHT_SUFFIXES)):
+            v = _ste_bf16(v)
+        out[k] = v
+    return out
+
+
 def pretrain_forward(sd, cfg, input_ids, attention_mask=None, labels=None, sample_wgt=None, position_ids=None,
-                     collect=None, inputs_raw_embeds=None, smtp_inside=False, drop=None):
+                     collect=None, inputs_raw_embeds=None, smtp_inside=False, drop=None, dtype=torch.float32,
+                     emulate_bf16=False):
     """GraphGPTPretrainBase.forward (modeling_pretrain.py:152-266), generative head only.
     drop: optional training-mode dropout factors {"embed", "raw", "act", "mlp"} (see the helpers above).
     Returns dict(loss, logits, hidden)."""
     cfg = OracleConfig.from_any(cfg)
-    sd = {k: (v.float() if v.is_floating_point() else v) for k, v in sd.items()}
+    sd = _prep_sd(sd, dtype, emulate_bf16)
+    rnd = _ste_bf16 if emulate_bf16 else None
     position_ids = reset_pos_ids(position_ids, cfg)
     drop = drop or {}
     emb, _ = stacked_embed(input_ids, sd, cfg, drop.get("embed"))
     if inputs_raw_embeds is not None:
         emb = emb + raw_embed_branch(inputs_raw_embeds, sd, cfg, labels, smtp_inside, drop.get("raw"))   # :149
-    hidden = backbone(emb, attention_mask, position_ids, sd, cfg, collect, drop)
-    h, lab, wgt = head_select(hidden, labels, sd, cfg, sample_wgt)
+    hidden = backbone(emb, attention_mask, position_ids, sd, cfg, collect, drop, rnd)
+    h, lab, wgt = head_select(hidden, labels, sd, cfg, sample_wgt, rnd)
     logits = F.linear(h, sd["lm_head.weight"])                                        # :218
     loss = None
     if lab is not None:
@@ -340,18 +388,19 @@ def pretrain_forward(sd, cfg, input_ids, attention_mask=None, labels=None, sampl
 # fine-tuning head
 # ------------------------------------------------------------------------------------------------
 def task_forward(sd, cfg, input_ids, attention_mask=None, position_ids=None, task_labels=None, sample_wgt=None,
-                 inputs_raw_embeds=None, pretrain_labels=None, drop=None):
+                 inputs_raw_embeds=None, pretrain_labels=None, drop=None, dtype=torch.float32, emulate_bf16=False,
+                 collect=None):
     """GraphGPTTaskModel.forward (modeling_finetune.py:236-326): score on all positions, pool at the last non-pad
     index (modeling_helpers.py:78-86), CE / MSE / L1 / BCE loss (modeling_finetune.py:167-234)."""
     cfg = OracleConfig.from_any(cfg)
-    sd = {k: v.float() for k, v in sd.items()}
+    sd = _prep_sd(sd, dtype, emulate_bf16)
     position_ids = reset_pos_ids(position_ids, cfg)
     if input_ids.dim() == 3:
         input_ids = input_ids[:, :, : cfg.stacked_feat]
     emb, in_ = stacked_embed(input_ids, sd, cfg)
     if inputs_raw_embeds is not None:
         emb = emb + raw_embed_branch(inputs_raw_embeds, sd, cfg)                          # modeling_finetune.py:130-134
-    hidden = backbone(emb, attention_mask, position_ids, sd, cfg, drop=drop)
+    hidden = backbone(emb, attention_mask, position_ids, sd, cfg, collect, drop, _ste_bf16 if emulate_bf16 else None)
     if "score.weight" in sd:
         logits = F.linear(hidden, sd["score.weight"], sd.get("score.bias"))
     else:       # MLP score head (src/utils/modules_utils.py:8-34): act -> (dropout) -> Linear, for every Linear
@@ -360,7 +409,7 @@ def task_forward(sd, cfg, input_ids, attention_mask=None, position_ids=None, tas
             logits = F.linear(F.gelu(logits), sd[f"score.mlp_modules.{j}.weight"], sd.get(f"score.mlp_modules.{j}.bias"))
             j += 1
     seq_len = (in_ != cfg.pad_token_id).sum(-1) - 1
-    idx = torch.arange(hidden.shape[0])
+    idx = torch.arange(hidden.shape[0], device=hidden.device)
     pooled_logits = logits[idx, seq_len]
     pooled_hidden = hidden[idx, seq_len]
     aux = {}

@@ -174,3 +174,41 @@ def test_forward_signatures_output_fields_and_config_defaults_equal_the_referenc
     script.write_text(_SURFACE_SCRIPT)
     p = subprocess.run([sys.executable, str(script), ROOT], capture_output=True, text=True, timeout=600)
     assert p.returncode == 0 and "surface ok" in p.stdout, (p.stdout + p.stderr)[-3000:]
+
+
+_CKPT_SCRIPT = r'''
+import sys, os, tempfile
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests/golden")
+import ref_shim
+ref_shim._Finder.roots = tuple(r for r in ref_shim._Finder.roots if r != "accelerate")
+ref_shim.load_reference()
+import torch
+import graphgpt_b200 as gb
+from graphgpt_b200.dp import write_model_pt
+from src.utils import loader_utils
+cfg = dict(vocab_size=300, hidden_size=64, intermediate_size=256, num_hidden_layers=2, num_attention_heads=1,
+           num_key_value_heads=1, hidden_act="gelu", stacked_feat=5, next_n_token=5, stack_method="short", causal_attention=False)
+torch.manual_seed(0)
+pre = gb.GraphGPTPretrainBase(gb.GraphGPTConfig(**cfg))
+d = tempfile.mkdtemp()
+write_model_pt(pre, d)                                              # what GraphGPTEngine.save_checkpoint(d) leaves in d
+torch.manual_seed(1)
+ft = gb.GraphGPTTaskModel(gb.GraphGPTConfig(**cfg, num_labels=2, problem_type="single_label_classification"))
+before = ft.score.weight.detach().clone()
+ft = loader_utils.load_from_ckp_with_try(ft, d, skip_keys=True, strict=False)   # finetune_mode path (loader_utils.py:176-220)
+sd_pre, sd_ft = pre.state_dict(), ft.state_dict()
+for k in sd_ft:
+    if k.startswith("model."):
+        assert torch.equal(sd_ft[k], sd_pre[k]), k
+assert torch.equal(ft.score.weight, before)                          # head keys are not in a pre-training checkpoint
+print("checkpoint handoff ok")
+'''
+
+
+def test_engine_checkpoint_is_readable_by_the_reference_finetune_loader(tmp_path):
+    """ADVICE r1: a checkpoint pre-trained with GraphGPTEngine must be loadable by the UNCHANGED fine-tuning pipeline:
+    `load_from_ckp_with_try` (src/utils/loader_utils.py:176-220) opens <ckp>/model.pt first."""
+    script = tmp_path / "ckpt.py"
+    script.write_text(_CKPT_SCRIPT)
+    p = subprocess.run([sys.executable, str(script), ROOT], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "checkpoint handoff ok" in p.stdout, (p.stdout + p.stderr)[-3000:]

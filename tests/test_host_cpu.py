@@ -157,6 +157,33 @@ def test_warmup_decay_lr():
         assert warmup_decay_lr(110, **k) == 0.0
 
 
+def test_engine_evaluates_the_schedule_in_deepspeed_order():
+    """DeepSpeed steps the scheduler AFTER the optimizer, starting from last_batch_iteration = -1 (WarmupLR.get_lr() then
+    returns min_lr; DeepSpeedEngine._take_model_step; deepspeed 0.15.4 runtime/lr_schedules.py): the first TWO parameter
+    updates run at min_lr and update k at the schedule value of iteration k - 2.  Restated here step by step and compared
+    with the iteration GraphGPTEngine.step() hands to its lr_schedule callable."""
+    import math
+    from graphgpt_b200.dp import GraphGPTEngine, warmup_decay_lr
+    kw = dict(max_lr=3e-4, min_lr=1e-6, warmup_steps=8, total_steps=40)
+
+    def ds_get_lr(last_batch_iteration):                       # WarmupDecayLR.get_lr, warmup_type "log"
+        if last_batch_iteration < 0:
+            return kw["min_lr"]
+        if last_batch_iteration < kw["warmup_steps"]:
+            gamma = math.log(last_batch_iteration + 1) / math.log(kw["warmup_steps"])
+        else:
+            gamma = max(0.0, (kw["total_steps"] - last_batch_iteration) / max(1.0, kw["total_steps"] - kw["warmup_steps"]))
+        return kw["min_lr"] + (kw["max_lr"] - kw["min_lr"]) * gamma
+
+    last_batch_iteration, lr_in_optimizer = -1, ds_get_lr(-1)   # scheduler construction writes get_lr() into the optimizer
+    for updates_done in range(45):
+        mine = warmup_decay_lr(GraphGPTEngine.schedule_iteration(updates_done), **kw)
+        assert abs(mine - lr_in_optimizer) < 1e-15, (updates_done, mine, lr_in_optimizer)
+        last_batch_iteration += 1                               # optimizer.step(); then lr_scheduler.step()
+        lr_in_optimizer = ds_get_lr(last_batch_iteration)
+    assert warmup_decay_lr(-1, **kw) == kw["min_lr"] == warmup_decay_lr(0, **kw)   # updates 1 and 2 both run at min_lr
+
+
 _GLOO_WORKER = r"""
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[1])
@@ -244,9 +271,15 @@ def test_bench_reference_arm_contract():
     assert len(lines) == 1, lines
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "tokens/s" and d["higher_is_better"] is True and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    have_ref = os.path.isdir("/root/reference/src") or os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "src"))
+    # the UNMODIFIED reference (baseline/_ref or /root/reference) when it is there, else the oracle port — and it says which
+    assert d["cpu_baseline"]["kind"] == ("reference" if have_ref else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert ("GraphGPTPretrainBase" in d["cpu_baseline"]["sample"]) == have_ref
     assert d["e2e"] == {"value": d["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"].startswith("pcqm4m-v2-smtp-pretrain") and d["gpu_launches"] == 0
+    # same `config` as the b200 arm prints for this workload (the driver compares the two lines)
+    assert d["config"]["seqs_per_gpu"] == 64 and d["config"]["seq_len"] == 1024 and d["config"]["parallelism"] == "dp1"
 
 
 def test_mix_seed_streams_are_well_separated():

@@ -3,8 +3,8 @@
   (2) the CPU oracle on fresh seeded inputs at a larger size.
 The kernels feed bf16 operands to the tensor cores (fp32 accumulate, fp32 residual stream / norms / softmax / CE),
 so parity with the fp32 reference is bounded by bf16 operand rounding (2^-9 relative per element):
-  loss: <= 1e-3 relative (BASELINE north-star tolerance);  logits / hidden: relative Frobenius error <= 1e-2;
-  gradients: relative Frobenius <= 3e-2.
+  loss: <= 1e-3 relative (BASELINE north-star tolerance);  logits: relative Frobenius error <= the error of the
+  reference's own bf16 run on the same fixture (hidden states of fine-tune fixtures: <= 1e-2);  gradients: <= 3e-2.
 Each fixture also records how far the REFERENCE ITSELF lands from its fp32 result when run in bf16
 (rec["ref_bf16_error"]); every number is logged next to it in gpurun_out/parity_report.txt and a gradient may
 exceed 3e-2 only where the reference's own bf16 run does (tolerance = max(3e-2, 1.5 x reference bf16 error))."""
@@ -54,8 +54,11 @@ def test_model_matches_reference_golden(path):
         assert tuple(lg.shape) == tuple(rec["logits_shape"])
         e_lg = _relf(lg[:: rec["logits_stride"]], rec["logits"])
         loss = out.head1_loss
-        _log(f"{name}: logits relF {e_lg:.3e} (reference-in-bf16 relF {rec.get('ref_bf16_error', {}).get('logits_relF', float('nan')):.3e})")
-        assert e_lg <= ACT_TOL
+        ref_bf = rec.get("ref_bf16_error", {}).get("logits_relF")
+        _log(f"{name}: logits relF {e_lg:.3e} (reference-in-bf16 relF {ref_bf if ref_bf is not None else float('nan'):.3e})")
+        # bf16 storage bounds the fast path (tests/test_parity_depth_gpu.py explains the number, the precise mode of
+        # tests/test_precise_mode_gpu.py meets 1e-3 outright): never further from fp32 than the reference's own bf16 run
+        assert e_lg <= (max(ref_bf, 2e-3) if ref_bf is not None else ACT_TOL), (e_lg, ref_bf)
     elif rec["kind"] == "double":
         e_tl = _relf(out.task_logits, rec["task_logits"])
         e_t = abs(out.task_loss.item() - rec["task_loss"].item()) / abs(rec["task_loss"].item())
@@ -185,8 +188,9 @@ def test_c4_shape_seq4096_vs_oracle():
 
 
 def test_full_size_c2_packing_invariance_and_batch_linearity():
-    """BASELINE configs[1] at FULL size (12L/768d/F13/V756, 64 x 1024 packed tokens) through size-independent
-    properties, since no CPU oracle finishes this size in seconds:
+    """BASELINE configs[1] at FULL size (12L/768d/F13/V756, 64 x 1024 packed tokens = one bench step) through
+    size-independent properties (the oracle comparison at this depth runs on 2 x 1024 tokens in
+    tests/test_parity_depth_gpu.py; 64 x 1024 would take the CPU oracle minutes):
       * packing invariance — attention is block-diagonal and RoPE is relative, so the same graphs fed one per row
         (right-padded [n_seg, 40] grid, 2-D mask) must give the same labelled-entry logits and the same loss as the
         packed [64, 1024] grid with its [N,S,S] mask (different kernels: isolated-tile vs general attention path);
@@ -320,6 +324,41 @@ def test_batch_without_any_label_gives_nan_loss_and_empty_logits():
     ids = torch.randint(2, 300, (2, 16)).cuda()
     out = model(input_ids=ids, attention_mask=torch.ones_like(ids), labels=torch.full_like(ids, -100))
     assert torch.isnan(out.head1_loss) and tuple(out.head1_logits.shape) == (0, 300)
+    # ... and its backward still runs, as the reference's does (zero gradients from the loss head; under data parallelism
+    # every rank must keep issuing its gradient exchanges — ADVICE r1)
+    out.head1_loss.backward()
+    assert all(p.grad is not None and float(p.grad.abs().max()) == 0.0 for p in model.parameters())
+
+
+def test_out_of_range_ids_labels_and_positions_raise_index_error():
+    """The reference fails with IndexError / a device-side assert when a token id or a label lies outside the vocabulary
+    (nn.Embedding, CrossEntropyLoss).  The kernels flag it on the device; the flag is read back without a mid-step sync,
+    so the IndexError surfaces at the next forward / optimizer step, or at once through check_device_errors()."""
+    from graphgpt_b200 import GraphGPTConfig, GraphGPTPretrainBase, GraphGPTTaskModel
+    model = GraphGPTPretrainBase(GraphGPTConfig(**_small_cfg())).cuda().eval()
+    good = torch.randint(2, 300, (2, 16)).cuda()
+    am = torch.ones_like(good)
+    model(input_ids=good, attention_mask=am, labels=good)
+    model.check_device_errors()                                            # clean batch: nothing to report
+    bad_ids = good.clone()
+    bad_ids[1, 3] = 300                                                    # == vocab_size
+    model(input_ids=bad_ids, attention_mask=am, labels=good)
+    with pytest.raises(IndexError, match="input_ids"):
+        model.check_device_errors()
+    bad_lab = good.clone()
+    bad_lab[0, 5] = 4000
+    model(input_ids=good, attention_mask=am, labels=bad_lab)
+    torch.cuda.synchronize()
+    with pytest.raises(IndexError, match="labels"):                        # not checked explicitly: the NEXT forward raises
+        model(input_ids=good, attention_mask=am, labels=good)
+    model(input_ids=good, attention_mask=am, labels=good)                  # the flag was consumed: training can go on
+    model.check_device_errors()
+    ft = GraphGPTTaskModel(GraphGPTConfig(**_small_cfg(num_labels=2, problem_type="single_label_classification"))).cuda().eval()
+    pos = torch.arange(16).repeat(2, 1).cuda()
+    pos[0, 2] = 100000                                                     # beyond the rotary table
+    ft(input_ids=good, attention_mask=am, position_ids=pos, task_labels=torch.tensor([0, 1]).cuda())
+    with pytest.raises(IndexError, match="position_ids"):
+        ft.check_device_errors()
 
 
 def test_frozen_prefix_like_freeze_llama_layers():
@@ -391,6 +430,12 @@ def test_engine_checkpoint_roundtrip(tmp_path):
         train_step(a)
     assert a.save_checkpoint(str(tmp_path), client_state={"epoch": 4})
     assert (tmp_path / "latest").read_text() == "global_step3" and a.device.type == "cuda"
+    # <dir>/model.pt: the plain state dict the reference's fine-tune / eval loaders open first (loader_utils.py:176-220)
+    plain = torch.load(tmp_path / "model.pt")
+    assert all(v.device.type == "cpu" for v in plain.values())
+    probe = GraphGPTPretrainBase(GraphGPTConfig(**cfgd))
+    assert not any(probe.load_state_dict(plain, strict=True))
+    assert all(torch.equal(v, a.module.state_dict()[k].cpu()) for k, v in plain.items())
     cont = [train_step(a) for _ in range(2)]
     fresh = make()
     path, client = fresh.load_checkpoint(str(tmp_path))
