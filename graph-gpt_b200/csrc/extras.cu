@@ -111,6 +111,85 @@ __global__ void raw_embed_norm_bwd_kernel(const __nv_bfloat16* __restrict__ dh, 
 }
 
 // =============================================================================================
+// Raw EDGE embeddings [N,S,S,E] (fine-tuning only; modeling_helpers.py:127-139 with a 4-D input): every (n, s, s') row is
+// layer-normed, dropped out and projected, then summed over s'.  embed_proj has no bias, so the sum commutes with it:
+//   h[t,:] = sum_j w * raw[t,j,:] * rstd[t,j] * drop(t,j,:)     (bf16, fed to ONE embed_proj GEMM of T rows)
+// One warp per token t = (n, s); the partial sums stay in registers (E <= 1024).  Backward: only embed_layernorm.weight
+// has a gradient (the features are data):  dw += sum_t dh[t,:] * sum_j raw[t,j,:] rstd[t,j] drop(t,j,:).
+// =============================================================================================
+__global__ void raw_embed_norm_sum_kernel(const float* __restrict__ raw, const float* __restrict__ w,
+                                          __nv_bfloat16* __restrict__ h, long long ldh, const __nv_bfloat16* __restrict__ dh,
+                                          long long lddh, float* __restrict__ dw, long long T, int S2, int E, float eps,
+                                          DropParams dp) {
+  extern __shared__ float acc_dw[];   // backward only: [E]
+  const bool bwd = dh != nullptr;
+  if (bwd) {
+    for (int i = threadIdx.x; i < E; i += blockDim.x) acc_dw[i] = 0.f;
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (long long t = static_cast<long long>(blockIdx.x) * wpb + (threadIdx.x >> 5); t < T;
+       t += static_cast<long long>(gridDim.x) * wpb) {
+    float4 sum[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sum[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < S2; ++j) {
+      const float* src = raw + (t * S2 + j) * E;
+      float ss = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int c = lane * 4 + k * 128;
+        if (c < E) {
+          const float4 v = *reinterpret_cast<const float4*>(src + c);
+          ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        }
+      }
+      ss = warp_sum(ss);
+      if (ss == 0.f) continue;                       // an all-zero (absent edge) row contributes nothing
+      const float rstd = rsqrtf(ss / static_cast<float>(E) + eps);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int c = lane * 4 + k * 128;
+        if (c < E) {
+          const float4 v = *reinterpret_cast<const float4*>(src + c);
+          float2 s01 = make_float2(1.f, 1.f), s23 = make_float2(1.f, 1.f);
+          if (dp.thresh != 0u) {
+            const unsigned long long e0 = (static_cast<unsigned long long>(t) * S2 + j) * E + c;
+            s01 = edrop_scale2(dp, e0 >> 1);
+            s23 = edrop_scale2(dp, (e0 >> 1) + 1);
+          }
+          sum[k].x += v.x * rstd * s01.x; sum[k].y += v.y * rstd * s01.y;
+          sum[k].z += v.z * rstd * s23.x; sum[k].w += v.w * rstd * s23.y;
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = lane * 4 + k * 128;
+      if (c < E) {
+        if (!bwd) {
+          const float4 ww = *reinterpret_cast<const float4*>(w + c);
+          uint2 o;
+          o.x = pack_bf16(ww.x * sum[k].x, ww.y * sum[k].y);
+          o.y = pack_bf16(ww.z * sum[k].z, ww.w * sum[k].w);
+          *reinterpret_cast<uint2*>(h + t * ldh + c) = o;
+        } else {
+          const uint2 dv = *reinterpret_cast<const uint2*>(dh + t * lddh + c);
+          const float2 d01 = unpack_bf16(dv.x), d23 = unpack_bf16(dv.y);
+          atomicAdd(acc_dw + c + 0, d01.x * sum[k].x); atomicAdd(acc_dw + c + 1, d01.y * sum[k].y);
+          atomicAdd(acc_dw + c + 2, d23.x * sum[k].z); atomicAdd(acc_dw + c + 3, d23.y * sum[k].w);
+        }
+      }
+    }
+  }
+  if (bwd) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < E; i += blockDim.x) atomicAdd(dw + i, acc_dw[i]);
+  }
+}
+
+// =============================================================================================
 // LayerScale / DropPath backward of a residual branch  x_out = x_in + rowscale[t] * lam[c] * y  (utils_graphgpt.py:153-166):
 //   dy[t,c]  = bf16(dx[t,c] * lam[c] * rowscale[t])                       gradient handed to the branch's dgrad / wgrad GEMMs
 //   dlam[c] += sum_t dx[t,c] * rowscale[t] * y[t,c] = sum_t dx[t,c] * (x_out[t,c] - x_in[t,c]) / lam[c]
@@ -296,6 +375,19 @@ int ggpt_raw_embed_norm_bwd(const void* dh, long long lddh, const float* raw, co
   raw_embed_norm_bwd_kernel<<<grid_cap((T + 7) / 8, 2), 256, smem, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(dh), lddh, raw, keep, mask_tok, rstd, w, dw, dmask_tok, T, E);
   return check_launch("raw_embed_norm_bwd_kernel");
+}
+
+int ggpt_raw_embed_norm_sum(const float* raw, const float* w, void* h, long long ldh, const void* dh, long long lddh,
+                            float* dw, long long T, int S2, int E, float eps, float drop_p, unsigned long long drop_seed,
+                            void* stream) {
+  GGPT_REQUIRE(raw && T > 0 && S2 > 0 && E > 0 && E % 4 == 0 && E <= 1024, "raw_embed_norm_sum: bad sizes T=%lld S2=%d E=%d (E %% 4 == 0, E <= 1024)", T, S2, E);
+  GGPT_REQUIRE((dh == nullptr) ? (w && h && ldh % 4 == 0) : (dw != nullptr && lddh % 4 == 0), "raw_embed_norm_sum: forward needs w / h, backward needs dh / dw");
+  GGPT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "raw_embed_norm_sum: dropout p=%f outside [0,1)", drop_p);
+  const size_t smem = dh != nullptr ? static_cast<size_t>(E) * sizeof(float) : 0;
+  raw_embed_norm_sum_kernel<<<grid_cap((T + 7) / 8, 8), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      raw, w, static_cast<__nv_bfloat16*>(h), ldh, static_cast<const __nv_bfloat16*>(dh), lddh, dw, T, S2, E, eps,
+      make_drop_params(drop_p, drop_seed));
+  return check_launch("raw_embed_norm_sum_kernel");
 }
 
 int ggpt_layerscale_bwd(const float* dx, const float* x_out, const float* x_in, const float* lam, const float* rowscale,

@@ -306,9 +306,16 @@ class HotPath:
             # add+norm pass that produces layer 0's input norm
             raw2d, rlabels, fchk = raw
             mask_tok = fp.w("emb_mask_token") if rlabels is not None else None
-            hr, rstd_r, keep_r = ops.raw_embed_norm_fwd(raw2d, fp.w("embed_layernorm.weight"), self.eps, labels=rlabels,
-                                                        fchk=fchk, mask_tok=mask_tok, want_stash=keep)
-            ops.dropout_(hr, embed_pdrop, mix_seed(drop_seed, _SEED_RAW))              # raw_embed_dropout
+            if raw2d.dim() == 3:
+                # [N,S,S,E] edge embeddings (fine-tuning): norm + dropout per (n,s,s') row, summed over s' BEFORE the
+                # bias-free projection (modeling_helpers.py:127-139)
+                hr = ops.raw_embed_norm_sum_fwd(raw2d, fp.w("embed_layernorm.weight"), self.eps, drop_p=embed_pdrop,
+                                                drop_seed=mix_seed(drop_seed, _SEED_RAW))
+                rstd_r = keep_r = None
+            else:
+                hr, rstd_r, keep_r = ops.raw_embed_norm_fwd(raw2d, fp.w("embed_layernorm.weight"), self.eps, labels=rlabels,
+                                                            fchk=fchk, mask_tok=mask_tok, want_stash=keep)
+                ops.dropout_(hr, embed_pdrop, mix_seed(drop_seed, _SEED_RAW))          # raw_embed_dropout
             yr = ops.gemm(hr, fp.wb("embed_proj.weight"))
             x, h1, rstd1 = ops.add_rmsnorm_fwd(x, yr, w_in0, self.eps, want_rstd=keep)
             if keep:
@@ -448,10 +455,14 @@ class HotPath:
             # x0 = token-embedding sum + embed_proj(hr): dxb is the gradient of both summands
             ops.gemm(dxb, rw["hr"], out=fp.g("embed_proj.weight"), **wgrad)
             dhr = ops.gemm(dxb, fp.wb("embed_proj.weight"), b_mn_major=True)
-            ops.dropout_(dhr, embed_p, mix_seed(seed, _SEED_RAW))
-            ops.raw_embed_norm_bwd(dhr, rw["raw"], rw["keep"], rw["mask_tok"], rw["rstd"], fp.w("embed_layernorm.weight"),
-                                   fp.g("embed_layernorm.weight"),
-                                   fp.g("emb_mask_token") if rw["mask_tok"] is not None else None)
+            if rw["raw"].dim() == 3:
+                ops.raw_embed_norm_sum_bwd(dhr, rw["raw"], fp.g("embed_layernorm.weight"), self.eps, drop_p=embed_p,
+                                           drop_seed=mix_seed(seed, _SEED_RAW))
+            else:
+                ops.dropout_(dhr, embed_p, mix_seed(seed, _SEED_RAW))
+                ops.raw_embed_norm_bwd(dhr, rw["raw"], rw["keep"], rw["mask_tok"], rw["rstd"], fp.w("embed_layernorm.weight"),
+                                       fp.g("embed_layernorm.weight"),
+                                       fp.g("emb_mask_token") if rw["mask_tok"] is not None else None)
         if (emb_p.requires_grad and gate is None and not stash["long_scale"] and self.V <= 4096
                 and stash["ids"].shape[1] <= 32 and embed_p == 0):
             # small vocabulary: dE = C^T dX on the tensor cores (C = per-token id counts) instead of contended atomics
@@ -575,3 +586,59 @@ class PretrainHeadFn(torch.autograd.Function):
             dhsel = dhl
         dhf = ops.expand_rows(dhsel, hi.sel_rows, M, ctx.T)
         return (None, dhf) + (None,) * (n_in - 2)
+
+
+class FtHeadFn(torch.autograd.Function):
+    """hidden (bf16 [T,d]) -> (task loss | None, task_logits f32 [N,C], pooled hidden bf16 [N,d]): last-valid-row pooling,
+    the `score` head and the task loss in one kernel per direction (csrc/ft_head.cu; ref: modeling_finetune.py:281-296,
+    167-234, modeling_helpers.py:78-86, modules_utils.py:8-34).  `layers` = [(weight name, bias name | None), ...] in the
+    flat parameter buffer; gradients of the head go straight into the flat gradient buffer."""
+
+    @staticmethod
+    def forward(ctx, hot, hf, in_ids, layers, act, drop_p, mode, labels_i, labels_f, sample_wgt, *params):
+        fp = hot.flat
+        weights = [fp.w(w) for w, _ in layers]
+        biases = [fp.w(b) if b is not None else None for _, b in layers]
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if (act and drop_p > 0) else 0
+        st = ops.ft_head_fwd(hf, in_ids, hot.cfg.pad_token_id, weights, biases, act=act, drop_p=drop_p, drop_seed=seed,
+                             mode=mode, labels_i=labels_i, labels_f=labels_f, sample_wgt=sample_wgt,
+                             err_flag=hot.err_flags(hf.device)[1:2])
+        hot.post_error_flags()
+        ctx.hot, ctx.st, ctx.layers, ctx.T = hot, st, layers, hf.shape[0]
+        ctx.mark_non_differentiable(st.logits, st.pooled)
+        loss = st.loss[0] if mode >= 0 else torch.zeros((), device=hf.device, dtype=F32)
+        return loss, st.logits, st.pooled
+
+    @staticmethod
+    def backward(ctx, gloss, _gl, _gp):
+        hot, st = ctx.hot, ctx.st
+        fp = hot.flat
+        fp.prepare_grads()
+        named = dict(fp.order)
+        dW = [fp.g(w) if named[w].requires_grad else None for w, _ in ctx.layers]
+        dB = [fp.g(b) if (b is not None and named[b].requires_grad) else None for _, b in ctx.layers]
+        dhf = torch.zeros((ctx.T, hot.d), device=gloss.device, dtype=BF16)
+        ops.ft_head_bwd(st, gloss.reshape(1).to(F32).contiguous(), dW, dB, dhf)
+        ctx.st = None
+        return (None, dhf) + (None,) * (len(ctx.needs_input_grad) - 2)
+
+
+class FtIntraFn(torch.autograd.Function):
+    """loss_type "token_ce_intra" (modeling_finetune.py:137-165): hidden (bf16 [T,d]) -> (loss | 0, logits f32 [T,C]); the
+    sample's own hidden states at its class-token positions are the label embeddings (csrc/ft_head.cu)."""
+
+    @staticmethod
+    def forward(ctx, hot, hf, cls_idx, labels, N, S, C, *params):
+        st = ops.ft_intra_fwd(hf, cls_idx, labels, N, S, C, err_flag=hot.err_flags(hf.device)[1:2])
+        hot.post_error_flags()
+        ctx.hot, ctx.st = hot, st
+        ctx.mark_non_differentiable(st.logits)
+        loss = st.loss[0] if labels is not None else torch.zeros((), device=hf.device, dtype=F32)
+        return loss, st.logits
+
+    @staticmethod
+    def backward(ctx, gloss, _gl):
+        ctx.hot.flat.prepare_grads()
+        dhf = ops.ft_intra_bwd(ctx.st, gloss.reshape(1).to(F32).contiguous())
+        ctx.st = None
+        return (None, dhf) + (None,) * (len(ctx.needs_input_grad) - 2)

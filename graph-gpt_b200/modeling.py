@@ -20,7 +20,7 @@ from transformers import LlamaConfig
 from transformers.utils import ModelOutput
 
 from . import precise
-from .engine import PRETRAIN_HEAD, BackboneFn, HotPath, PretrainHeadFn
+from .engine import PRETRAIN_HEAD, BackboneFn, FtHeadFn, FtIntraFn, HotPath, PretrainHeadFn
 
 # GraphGPT-specific config fields and their defaults (same names as the reference so YAML / checkpoints map 1:1).
 _GRAPHGPT_FIELDS = dict(
@@ -262,8 +262,9 @@ class _GraphGPTBase(nn.Module):
         for k in ("n_token_proj.weight", "lm_head.weight"):
             if k in named:
                 order.append(k)
-        if self.config.loss_type == "token_ce" and "score.weight" in named and "score.bias" not in named:
-            order.append("score.weight")     # token-level FT: the score head runs on the tensor cores over labelled rows
+        # fine-tuning score head (nn.Linear or the MLP of modules_utils.py:8-34): its few parameters live in the flat
+        # buffers too, so the fused AdamW / clipping / gradient exchange cover every parameter of the model
+        order += [k for k in named if k.startswith("score.") and k not in order]
         return [(k, named[k]) for k in order]
 
     @property
@@ -349,9 +350,14 @@ class _GraphGPTBase(nn.Module):
             return None
         if inputs_raw_embeds is None:
             raise ValueError("config.embed_dim > 0: inputs_raw_embeds [N, S, embed_dim] is required")
-        if inputs_raw_embeds.dim() != 3:
-            raise NotImplementedError("inputs_raw_embeds of shape [N,S,S,E] (edge-embedding sum, modeling_helpers.py:135-136) "
-                                      "is not built; pass [N,S,E]")
+        if inputs_raw_embeds.dim() == 4:
+            # [N,S,S,E] edge embeddings, summed over the third axis after norm / dropout / projection
+            # (modeling_helpers.py:135-136; fine-tuning models only — the pre-training mask-token swap is 3-D)
+            if labels is not None or tuple(inputs_raw_embeds.shape) != (N, S, S, cfg.embed_dim):
+                raise RuntimeError(f"inputs_raw_embeds shape {tuple(inputs_raw_embeds.shape)}: expected {(N, S, S, cfg.embed_dim)} "
+                                   "(fine-tuning) or [N,S,E]")
+            raw3 = inputs_raw_embeds.to(device=self.device, dtype=torch.float32).reshape(N * S, S, cfg.embed_dim).contiguous()
+            return raw3, None, 0
         if tuple(inputs_raw_embeds.shape) != (N, S, cfg.embed_dim):
             raise RuntimeError(f"inputs_raw_embeds shape {tuple(inputs_raw_embeds.shape)} != {(N, S, cfg.embed_dim)}")
         raw2d = inputs_raw_embeds.to(device=self.device, dtype=torch.float32).reshape(N * S, cfg.embed_dim).contiguous()
@@ -551,21 +557,100 @@ class GraphGPTTaskModel(_GraphGPTBase):
         if self.pooling_method != "last":
             raise AssertionError(f"{self.pooling_method}!='last'")
         if cfg.loss_type == "token_ce_intra":
-            raise NotImplementedError("token_ce_intra (intra-instance label embeddings, modeling_finetune.py:139-161) is not "
-                                      "built (SURVEY §8f N3)")
-        seq_len = (in_.to(dev) != cfg.pad_token_id).sum(-1) - 1                      # modeling_helpers.py:78-86
-        rows = torch.arange(N, device=dev)
-        pooled_hidden = hidden[rows, seq_len]                                        # [N, d] bf16
+            return self._token_ce_intra_outputs(hf, hidden, in_.to(dev), task_labels, cls_idx, N, S)
         self._last_backbone = (hf, N, S)
-        if cfg.loss_type == "token_ce":
-            return self._token_ce_outputs(hf, hidden, pooled_hidden, task_labels, N, S)
-        pooled_logits = self.score(pooled_hidden.float())
-        task_loss = None
-        if task_labels is not None:
-            task_loss = self._task_loss(task_labels.to(dev), pooled_logits, sample_wgt)
+        if precise.enabled() or cfg.loss_type == "token_ce":
+            # validation-only fp32 path / token-level task: pooling by torch indexing ([N]-sized)
+            seq_len = (in_.to(dev) != cfg.pad_token_id).sum(-1) - 1                  # modeling_helpers.py:78-86
+            pooled_hidden = hidden[torch.arange(N, device=dev), seq_len]             # [N, d]
+            if cfg.loss_type == "token_ce":
+                return self._token_ce_outputs(hf, hidden, pooled_hidden, task_labels, N, S)
+            pooled_logits = self.score(pooled_hidden.float())
+            task_loss = None
+            if task_labels is not None:
+                task_loss = self._task_loss(task_labels.to(dev), pooled_logits, sample_wgt)
+            return DoubleHeadsModelOutput(pretrain_loss=None, task_loss=task_loss, pretrain_logits=None,
+                                          task_logits=pooled_logits.float(), past_key_values=None, hidden_states=hidden,
+                                          task_hidden_states=pooled_hidden, attentions=None)
+        task_loss, pooled_logits, pooled_hidden = self._fused_task_head(hf, in_.to(dev), task_labels, sample_wgt)
         return DoubleHeadsModelOutput(pretrain_loss=None, task_loss=task_loss, pretrain_logits=None,
-                                      task_logits=pooled_logits.float(), past_key_values=None, hidden_states=hidden,
+                                      task_logits=pooled_logits, past_key_values=None, hidden_states=hidden,
                                       task_hidden_states=pooled_hidden, attentions=None)
+
+    def _token_ce_intra_outputs(self, hf, hidden, in_, task_labels, cls_idx, N, S):
+        """loss_type == "token_ce_intra" (modeling_finetune.py:137-165, 195-199): the normalised hidden states at positions
+        cls_idx[n] .. cls_idx[n] + num_labels - 1 act as the sample's label embeddings; logits = 20 * cosine similarity of
+        every position with them, CrossEntropyLoss over the labelled positions.  task_logits is [N,S,num_labels]."""
+        if precise.enabled():
+            raise NotImplementedError("token_ce_intra has no precise-mode variant")
+        if cls_idx is None:
+            raise ValueError("loss_type token_ce_intra needs cls_idx [N] (first class-token position of every sample)")
+        cfg = self.config
+        dev = hf.device
+        if task_labels is not None:
+            if cfg.problem_type is None:
+                cfg.problem_type = "single_label_classification"
+            if cfg.problem_type != "single_label_classification":
+                raise NotImplementedError(f"token_ce_intra with problem_type={cfg.problem_type!r}")
+        seq_len = (in_ != cfg.pad_token_id).sum(-1) - 1                              # modeling_helpers.py:78-86
+        pooled_hidden = hidden[torch.arange(N, device=dev), seq_len]
+        labels = None if task_labels is None else task_labels.to(dev).reshape(-1).to(torch.int64).contiguous()
+        params = [p for _, p in self._hot.flat.order]
+        loss, logits = FtIntraFn.apply(self._hot, hf, cls_idx.to(dev).reshape(-1).to(torch.int64).contiguous(), labels, N, S,
+                                       self.num_labels, *params)
+        return DoubleHeadsModelOutput(pretrain_loss=None, task_loss=loss if labels is not None else None,
+                                      pretrain_logits=None, task_logits=logits.reshape(N, S, self.num_labels),
+                                      past_key_values=None, hidden_states=hidden, task_hidden_states=pooled_hidden,
+                                      attentions=None)
+
+    def _score_layers(self):
+        """[(weight name, bias name | None)] of the score head in execution order, and whether it is the MLP variant."""
+        if isinstance(self.score, _ScoreMLP):
+            return [(f"score.mlp_modules.{j}.weight", f"score.mlp_modules.{j}.bias" if m.bias is not None else None)
+                    for j, m in enumerate(self.score.mlp_modules)], True
+        return [("score.weight", "score.bias" if self.score.bias is not None else None)], False
+
+    def _fused_task_head(self, hf, in_, task_labels, sample_wgt):
+        """Pooling + score head + task loss as ONE kernel (ggpt_ft_head_fwd / _bwd); the loss selection mirrors
+        calculate_task_loss (modeling_finetune.py:167-234)."""
+        cfg = self.config
+        hot = self._hot
+        dev = hf.device
+        layers, is_mlp = self._score_layers()
+        if is_mlp and cfg.hidden_act != "gelu":
+            raise NotImplementedError(f"score MLP with hidden_act={cfg.hidden_act!r} (GraphGPT uses gelu)")
+        if len(layers) > 4:
+            raise NotImplementedError("score MLP deeper than 4 Linear layers")
+        mode, labels_i, labels_f, wgt = -1, None, None, None
+        if task_labels is not None:
+            labels = task_labels.to(dev)
+            if cfg.problem_type is None:
+                if self.num_labels == 1:
+                    cfg.problem_type = "regression"
+                elif self.num_labels > 1 and labels.dtype in (torch.long, torch.int):
+                    cfg.problem_type = "single_label_classification"
+                else:
+                    cfg.problem_type = "multi_label_classification"
+            if cfg.problem_type == "regression":
+                mode = 3 if cfg.loss_type == "l1" else 2
+                labels_f = labels.to(torch.float32).reshape(-1, self.num_labels).contiguous()
+            elif cfg.problem_type == "single_label_classification":
+                if cfg.loss_type == "auc":
+                    raise NotImplementedError("auc loss is out of scope (SURVEY §2 row 16)")
+                labels_i = labels.reshape(-1).to(torch.int64).contiguous()
+                if sample_wgt is None:
+                    mode = 0
+                else:
+                    mode, wgt = 1, sample_wgt.to(dev).to(torch.float32).reshape(-1).contiguous()
+            else:
+                if self.pos_weight is not None:
+                    raise NotImplementedError("BCEWithLogitsLoss pos_weight")
+                mode = 4
+                labels_f = labels.to(torch.float32).reshape(-1, self.num_labels).contiguous()
+        drop_p = float(cfg.dropout) if (self.training and is_mlp) else 0.0
+        params = [p for _, p in hot.flat.order]
+        loss, logits, pooled = FtHeadFn.apply(hot, hf, in_, layers, int(is_mlp), drop_p, mode, labels_i, labels_f, wgt, *params)
+        return (loss if mode >= 0 else None), logits, pooled
 
     def _token_ce_outputs(self, hf, hidden, pooled_hidden, task_labels, N, S):
         """loss_type == "token_ce" (node-level tasks): `score` on every position, CrossEntropyLoss over the labelled

@@ -296,6 +296,25 @@ def raw_embed_norm_bwd(dh, raw, keep, mask_tok, rstd, w, dw, dmask_tok):
                                 w.data_ptr(), dw.data_ptr(), _ptr(dmask_tok), T, E, _stream())
 
 
+def raw_embed_norm_sum_fwd(raw3, w, eps, *, drop_p=0.0, drop_seed=0):
+    """raw3 f32 [T,S2,E] (edge embeddings of token t towards every position) -> bf16 [T,E] = w * sum_j rmsnorm-hat rows."""
+    _check(raw3, F32, "raw_embed_sum raw", 3)
+    if not raw3.is_contiguous():
+        raise RuntimeError("raw_embed_sum raw: expected a contiguous [T,S2,E] tensor")
+    T, S2, E = raw3.shape
+    h = torch.empty((T, E), device=raw3.device, dtype=BF16)
+    lib.ggpt_raw_embed_norm_sum(raw3.data_ptr(), w.data_ptr(), h.data_ptr(), E, 0, 0, 0, T, S2, E, float(eps), float(drop_p),
+                                int(drop_seed), _stream())
+    return h
+
+
+def raw_embed_norm_sum_bwd(dh, raw3, dw, eps, *, drop_p=0.0, drop_seed=0):
+    _check(dh, BF16, "raw_embed_sum dh", 2)
+    T, S2, E = raw3.shape
+    lib.ggpt_raw_embed_norm_sum(raw3.data_ptr(), 0, 0, 0, dh.data_ptr(), dh.stride(0), dw.data_ptr(), T, S2, E, float(eps),
+                                float(drop_p), int(drop_seed), _stream())
+
+
 def layerscale_bwd(dx, x_out, x_in, lam, rowscale, dlam):
     """dy bf16 [T,d] = dx * lam * rowscale; accumulates dlam [d] += sum_t dx * (x_out - x_in) / lam when dlam is given."""
     _check(dx, F32, "layerscale_bwd dx", 2)
@@ -462,6 +481,115 @@ def ce_bwd(logits, labels, V, row_lse, scale_ptr, gout, wgt=None, focal_gamma=0.
     lib.ggpt_ce_bwd(logits.data_ptr(), logits.stride(0), labels.data_ptr(), _ptr(wgt), row_lse.data_ptr(), scale_ptr,
                     _ptr(gout), dlogits.data_ptr(), ldd, L, V, float(focal_gamma), _stream())
     return dlogits
+
+
+# ------------------------------------------------------------------------------------------------
+# Fine-tuning head (pooling + score head + task loss)
+# ------------------------------------------------------------------------------------------------
+def _ptr_array(tensors):
+    import ctypes
+    arr = (ctypes.c_void_p * len(tensors))(*[(t.data_ptr() if t is not None else None) for t in tensors])
+    return arr, ctypes.cast(arr, ctypes.c_void_p)
+
+
+def _int_array(vals):
+    import ctypes
+    arr = (ctypes.c_int * len(vals))(*vals)
+    return arr, ctypes.cast(arr, ctypes.c_void_p)
+
+
+class FtHeadState:
+    """Buffers shared by ggpt_ft_head_fwd / ggpt_ft_head_bwd for one forward pass."""
+    pass
+
+
+def ft_head_fwd(hidden, in_ids, pad_id, weights, biases, *, act, drop_p=0.0, drop_seed=0, mode=-1, labels_i=None,
+                labels_f=None, sample_wgt=None, err_flag=None):
+    """hidden bf16 [N*S, d]; in_ids int64 [N,S] (any strides); weights / biases: lists of fp32 tensors (bias entries may
+    be None).  Returns FtHeadState with .seq_idx, .pooled bf16 [N,d], .logits f32 [N,C], .loss f32 [2] = [loss, 1/den]."""
+    _check(hidden, BF16, "ft_head hidden", 2)
+    if in_ids.dtype != torch.int64 or in_ids.dim() != 2 or not in_ids.is_cuda:
+        raise RuntimeError("ft_head: in_ids must be a CUDA int64 [N,S] tensor")
+    N, S = in_ids.shape
+    d = hidden.shape[1]
+    if hidden.shape[0] != N * S:
+        raise RuntimeError(f"ft_head: hidden has {hidden.shape[0]} rows, expected N*S = {N * S}")
+    dims = [d] + [int(w.shape[0]) for w in weights]
+    for l, w in enumerate(weights):
+        _check(w, F32, f"ft_head weight {l}", 2)
+        if w.shape[1] != dims[l] or not w.is_contiguous():
+            raise RuntimeError(f"ft_head: weight {l} has shape {tuple(w.shape)}, expected [*, {dims[l]}] contiguous")
+    dev = hidden.device
+    st = FtHeadState()
+    st.N, st.S, st.dims, st.max_dim, st.act, st.mode = N, S, dims, max(dims), int(act), int(mode)
+    st.drop_p, st.drop_seed = float(drop_p), int(drop_seed)
+    st.weights, st.biases = list(weights), list(biases)
+    st.labels_i, st.labels_f, st.sample_wgt = labels_i, labels_f, sample_wgt
+    st.seq_idx = torch.empty((N,), device=dev, dtype=torch.int32)
+    st.pooled = torch.empty((N, d), device=dev, dtype=BF16)
+    st.logits = torch.empty((N, dims[-1]), device=dev, dtype=F32)
+    st.pre = torch.empty((len(weights), N, st.max_dim), device=dev, dtype=F32)
+    st.row_loss = torch.empty((N,), device=dev, dtype=F32)
+    st.row_den = torch.empty((N,), device=dev, dtype=F32)
+    st.loss = torch.empty((2,), device=dev, dtype=F32)
+    keep_w, pw = _ptr_array(st.weights)
+    keep_b, pb = _ptr_array(st.biases)
+    keep_d, pd = _int_array(dims)
+    lib.ggpt_ft_head_fwd(hidden.data_ptr(), hidden.stride(0), in_ids.data_ptr(), in_ids.stride(0), in_ids.stride(1),
+                         int(pad_id), N, S, len(weights), pd, pw, pb, st.act, st.drop_p, st.drop_seed, st.mode,
+                         _ptr(labels_i), _ptr(labels_f), _ptr(sample_wgt), st.seq_idx.data_ptr(), st.pooled.data_ptr(),
+                         st.logits.data_ptr(), st.pre.data_ptr(), st.max_dim, st.row_loss.data_ptr(), st.row_den.data_ptr(),
+                         st.loss.data_ptr(), _ptr(err_flag), _stream())
+    return st
+
+
+def ft_head_bwd(st, gout, dweights, dbiases, dhidden):
+    """Adds into dweights / dbiases (lists, entries may be None) and writes the pooled rows' gradient into the pre-zeroed
+    dhidden bf16 [N*S, d]."""
+    _check(gout, F32, "ft_head gout")
+    _check(dhidden, BF16, "ft_head dhidden", 2)
+    keep_w, pw = _ptr_array(st.weights)
+    keep_dw, pdw = _ptr_array(dweights)
+    keep_db, pdb = _ptr_array(dbiases)
+    keep_d, pd = _int_array(st.dims)
+    lib.ggpt_ft_head_bwd(st.N, st.S, len(st.weights), pd, pw, pdw, pdb, st.act, st.drop_p, st.drop_seed, st.mode,
+                         _ptr(st.labels_i), _ptr(st.labels_f), _ptr(st.sample_wgt), st.seq_idx.data_ptr(),
+                         st.logits.data_ptr(), st.pre.data_ptr(), st.max_dim, st.loss.data_ptr(), gout.data_ptr(),
+                         dhidden.data_ptr(), dhidden.stride(0), _stream())
+
+
+def ft_intra_fwd(hidden, cls_idx, labels, N, S, C, err_flag=None):
+    """token_ce_intra: hidden bf16 [N*S,d], cls_idx int64 [N], labels int64 [N*S] | None.  Returns a state object with
+    .logits f32 [N*S,C], .loss f32 [2] = [loss, 1/#labelled], .rn (inverse norms)."""
+    _check(hidden, BF16, "ft_intra hidden", 2)
+    _check(cls_idx, torch.int64, "ft_intra cls_idx", 1)
+    if labels is not None:
+        _check(labels, torch.int64, "ft_intra labels", 1)
+    T, d = hidden.shape
+    dev = hidden.device
+    st = FtHeadState()
+    st.hidden, st.cls_idx, st.labels, st.N, st.S, st.C, st.d = hidden, cls_idx, labels, N, S, C, d
+    st.rn = torch.empty((T,), device=dev, dtype=F32)
+    st.logits = torch.empty((T, C), device=dev, dtype=F32)
+    st.row_loss = torch.empty((T,), device=dev, dtype=F32)
+    st.row_den = torch.empty((T,), device=dev, dtype=F32)
+    st.loss = torch.empty((2,), device=dev, dtype=F32)
+    lib.ggpt_ft_intra_fwd(hidden.data_ptr(), hidden.stride(0), cls_idx.data_ptr(), _ptr(labels), st.rn.data_ptr(),
+                          st.logits.data_ptr(), st.row_loss.data_ptr(), st.row_den.data_ptr(), st.loss.data_ptr(), N, S, C, d,
+                          _ptr(err_flag), _stream())
+    return st
+
+
+def ft_intra_bwd(st, gout):
+    T, d = st.hidden.shape
+    dev = st.hidden.device
+    dl = torch.empty((T, st.C), device=dev, dtype=F32)
+    g = torch.empty((T, d), device=dev, dtype=F32)
+    dh = torch.empty((T, d), device=dev, dtype=BF16)
+    lib.ggpt_ft_intra_bwd(st.hidden.data_ptr(), st.hidden.stride(0), st.cls_idx.data_ptr(), st.labels.data_ptr(),
+                          st.rn.data_ptr(), st.logits.data_ptr(), st.loss.data_ptr(), gout.data_ptr(), dl.data_ptr(),
+                          g.data_ptr(), dh.data_ptr(), d, st.N, st.S, st.C, d, _stream())
+    return dh
 
 
 # ------------------------------------------------------------------------------------------------

@@ -87,6 +87,8 @@ def backbone_forward(hot, ids2d, N, S, attention_mask, position_ids, raw=None):
     mask = ops.attn_mask_build(attention_mask, N, S, cfg.causal_attention, dev)
     if raw is not None:
         raw2d, rlabels, fchk = raw
+        if raw2d.dim() != 2:
+            raise NotImplementedError("precise mode: [N,S,S,E] edge embeddings have no validation-mode variant")
         E = raw2d.shape[1]
         hr = torch.empty((T, E), device=dev, dtype=F32)
         mask_tok = fp.w("emb_mask_token") if rlabels is not None else None

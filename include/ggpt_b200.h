@@ -296,6 +296,53 @@ int ggpt_vp_add_f32(const float* x_in, const float* y, long long ldy, const floa
                     float* x_out, long long T, int d, void* stream);
 int ggpt_vp_gather_rows_f32(const float* src, long long lds, const int* idx, float* out, long long n, int d, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Fine-tuning head: last-valid-row pooling + `score` head + task loss, one CTA per sample.
+ *   seq_idx[n] = (#ids of sample n != pad_id) - 1 (negative wraps)          ref: modeling_helpers.py:78-86
+ *   pooled[n]  = hidden[n, seq_idx[n]] (bf16 copy = task_hidden_states)     ref: modeling_finetune.py:293-296
+ *   logits[n]  = score(pooled[n]) in fp32: n_layers Linear layers (weights W[l] fp32 [dims[l+1], dims[l]], optional
+ *                biases), act = 1 puts gelu_erf (+ dropout drop_p) in front of EVERY Linear — the MLP head of
+ *                modules_utils.py:8-34 — act = 0 is the plain nn.Linear head     ref: modeling_finetune.py:281,289-292
+ *   loss_out   = [loss, 1 / denominator]   mode 0: CrossEntropy mean; 1: sum(l w) / sum(w) with sample_wgt; 2: MSE;
+ *                3: L1 (both: mean over all N x num_labels elements); 4: BCE-with-logits over the non-NaN labels;
+ *                -1: no labels, logits only                                   ref: modeling_finetune.py:167-234
+ * `ids` = first-feature token ids, element (n, s) at ids[n * ids_ld_n + s * ids_ld_s].  W / b / dW / db are HOST arrays
+ * of n_layers DEVICE pointers.  `pre` (fp32 [n_layers, N, max_dim]) keeps every layer's input for the backward pass.
+ * Backward adds the weight / bias gradients into dW / db (entries may be NULL) and writes the gradient of the pooled
+ * rows into the PRE-ZEROED dhidden [N*S, ldd] (bf16); gout = upstream gradient of the loss (1 float, device).
+ * ------------------------------------------------------------------------------------------- */
+int ggpt_ft_head_fwd(const void* hidden, long long ld, const long long* ids, long long ids_ld_n, long long ids_ld_s,
+                     long long pad_id, int N, int S, int n_layers, const int* dims, const float* const* W,
+                     const float* const* b, int act, float drop_p, unsigned long long drop_seed, int mode,
+                     const long long* labels_i, const float* labels_f, const float* sample_wgt, int* seq_idx, void* pooled,
+                     float* logits, float* pre, int max_dim, float* row_loss, float* row_den, float* loss_out, int* err_flag,
+                     void* stream);
+int ggpt_ft_head_bwd(int N, int S, int n_layers, const int* dims, const float* const* W, float* const* dW,
+                     float* const* db, int act, float drop_p, unsigned long long drop_seed, int mode,
+                     const long long* labels_i, const float* labels_f, const float* sample_wgt, const int* seq_idx,
+                     const float* logits, const float* pre, int max_dim, const float* loss_out, const float* gout,
+                     void* dhidden, long long ldd, void* stream);
+
+/* Raw EDGE embeddings [N,S,S,E] of the fine-tuning models (ref: modeling_helpers.py:127-139, 4-D input): raw is fp32
+ * [T, S2, E] (T = N*S tokens, S2 = S neighbours).  Forward (dh == NULL): h[t,:] = bf16(w * sum_j raw[t,j,:] rstd[t,j]
+ * drop(t,j,:)) — the layer-normed, dropped-out rows summed over j; embed_proj (bias-free) then runs ONCE on the T sums.
+ * Backward (dh != NULL, bf16 [T, lddh]): dw[E] += sum_t dh[t,:] * sum_j raw[t,j,:] rstd[t,j] drop(t,j,:). */
+int ggpt_raw_embed_norm_sum(const float* raw, const float* w, void* h, long long ldh, const void* dh, long long lddh,
+                            float* dw, long long T, int S2, int E, float eps, float drop_p, unsigned long long drop_seed,
+                            void* stream);
+
+/* loss_type "token_ce_intra" (ref: modeling_finetune.py:137-165): logits[n,s,c] = 20 * <a[n,s], a[n, cls_idx[n] + c]> with
+ * a = hidden / max(||hidden||, 1e-12) (the sample's own hidden states at its C class-token positions serve as label
+ * embeddings), CrossEntropy over the labelled positions (labels int64 [N*S], -100 ignored; NULL = logits only).
+ * rn = fp32 [N*S] scratch (inverse norms, reused by backward), logits fp32 [N*S, C], loss_out = [loss, 1/#labelled].
+ * Backward writes dhidden [N*S, ldd] (bf16, every row); dl_scratch fp32 [N*S, C], g_scratch fp32 [N*S, d]. */
+int ggpt_ft_intra_fwd(const void* hidden, long long ld, const long long* cls_idx, const long long* labels, float* rn,
+                      float* logits, float* row_loss, float* row_den, float* loss_out, int N, int S, int C, int d,
+                      int* err_flag, void* stream);
+int ggpt_ft_intra_bwd(const void* hidden, long long ld, const long long* cls_idx, const long long* labels, const float* rn,
+                      const float* logits, const float* loss_out, const float* gout, float* dl_scratch, float* g_scratch,
+                      void* dhidden, long long ldd, int N, int S, int C, int d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -245,7 +245,10 @@ def raw_embed_branch(inputs_raw_embeds, sd, cfg, labels=None, smtp_inside=False,
     x = rmsnorm(x, sd["embed_layernorm.weight"], cfg.rms_norm_eps)
     if raw_scale is not None:
         x = x * raw_scale
-    return F.linear(x, sd["embed_proj.weight"])
+    x = F.linear(x, sd["embed_proj.weight"])
+    if x.dim() == 4:                          # [N,S,S,d] edge embeddings: summed over the third axis, :135-136
+        x = x.sum(dim=-2)
+    return x
 
 
 def backbone(inputs_embeds, attention_mask, position_ids, sd, cfg, collect=None, drop=None, rnd=None):
@@ -389,7 +392,7 @@ def pretrain_forward(sd, cfg, input_ids, attention_mask=None, labels=None, sampl
 # ------------------------------------------------------------------------------------------------
 def task_forward(sd, cfg, input_ids, attention_mask=None, position_ids=None, task_labels=None, sample_wgt=None,
                  inputs_raw_embeds=None, pretrain_labels=None, drop=None, dtype=torch.float32, emulate_bf16=False,
-                 collect=None):
+                 collect=None, cls_idx=None):
     """GraphGPTTaskModel.forward (modeling_finetune.py:236-326): score on all positions, pool at the last non-pad
     index (modeling_helpers.py:78-86), CE / MSE / L1 / BCE loss (modeling_finetune.py:167-234)."""
     cfg = OracleConfig.from_any(cfg)
@@ -418,6 +421,18 @@ def task_forward(sd, cfg, input_ids, attention_mask=None, position_ids=None, tas
         pl = F.linear(hidden, sd["lm_head.weight"])
         aux = {"pretrain_logits": pl,
                "pretrain_loss": F.cross_entropy(pl.float().view(-1, pl.shape[-1]), pretrain_labels.view(-1))}
+    if cfg.loss_type == "token_ce_intra":
+        # intra-instance label embeddings (modeling_finetune.py:137-165): cosine logits against the sample's own hidden
+        # states at positions cls_idx .. cls_idx + num_labels - 1, temperature 1/20
+        hn = F.normalize(hidden, dim=-1)
+        N_ = hidden.shape[0]
+        idx1 = torch.arange(N_, device=hidden.device).reshape(-1, 1).expand(-1, cfg.num_labels)
+        idx2 = torch.arange(cfg.num_labels, device=hidden.device).reshape(1, -1).expand(N_, -1) + cls_idx.reshape(-1, 1)
+        logits = torch.matmul(hn, hn[idx1, idx2].transpose(-2, -1)) * 20
+        loss = None
+        if task_labels is not None:
+            loss = F.cross_entropy(logits.view(-1, cfg.num_labels).float(), task_labels.view(-1))
+        return {"loss": loss, "task_logits": logits.float(), "hidden": hidden, "task_hidden": pooled_hidden, **aux}
     if cfg.loss_type == "token_ce":
         # token-level task (modeling_finetune.py:161-165,195-199): every position is scored, CE ignores -100
         loss = None

@@ -193,6 +193,43 @@ def _ft_tok():
     return "finetune", cfg, dict(input_ids=t(b["input_ids"]), attention_mask=t(b["attention_mask"]), task_labels=t(lab))
 
 
+@case("c3_ft_token_ce_intra")
+def _ft_tok_intra():
+    """Node-level fine-tune with intra-instance label embeddings: loss_type token_ce_intra, cls_idx [N]
+    (modeling_finetune.py:137-165)."""
+    cfg = base_cfg(vocab_size=1200, hidden_size=64, intermediate_size=256, stacked_feat=4, next_n_token=4,
+                   num_labels=5, problem_type="single_label_classification", pooling_method="last",
+                   loss_type="token_ce_intra")
+    vocab = synth.VocabLayout(vocab_size=1200, scope=512, n_node_attr=2, n_edge_attr=1)
+    b = synth.make_batch(3, 48, layout="unpacked", task="ntp", vocab=vocab, seed=27)
+    g = np.random.default_rng(12)
+    lab = g.integers(0, 5, size=b["attention_mask"].shape).astype(np.int64)
+    lab[(b["attention_mask"] == 0) | (g.random(lab.shape) < 0.4)] = -100
+    lens = b["attention_mask"].sum(-1)
+    cls_idx = np.array([int(g.integers(0, max(1, l - 5))) for l in lens], dtype=np.int64)
+    return "finetune", cfg, dict(input_ids=t(b["input_ids"]), attention_mask=t(b["attention_mask"]), task_labels=t(lab),
+                                 cls_idx=t(cls_idx))
+
+
+@case("c3_raw_edge_embed_ft")
+def _raw_edge_ft():
+    """Fine-tune with raw EDGE embeddings [N,S,S,E]: embed_layernorm + embed_proj per (n,s,s') row, summed over s'
+    (modeling_helpers.py:127-139)."""
+    cfg = base_cfg(vocab_size=1200, hidden_size=64, intermediate_size=256, stacked_feat=4, next_n_token=4, embed_dim=16,
+                   num_labels=2, problem_type="single_label_classification", pooling_method="last")
+    vocab = synth.VocabLayout(vocab_size=1200, scope=512, n_node_attr=2, n_edge_attr=1)
+    b = synth.make_batch(3, 24, layout="unpacked", task="ntp", vocab=vocab, seed=28)
+    g = np.random.default_rng(13)
+    N, S = b["attention_mask"].shape
+    raw = g.standard_normal((N, S, S, 16)).astype(np.float32)
+    raw[g.random((N, S, S)) < 0.6] = 0.0                       # most (s, s') pairs carry no edge
+    am = b["attention_mask"].astype(bool)
+    raw[~am] = 0.0
+    raw[:, :, :, :][~(am[:, :, None] & am[:, None, :])] = 0.0
+    return "finetune", cfg, dict(input_ids=t(b["input_ids"]), attention_mask=t(b["attention_mask"]),
+                                 task_labels=torch.tensor([1, 0, 1]), inputs_raw_embeds=torch.from_numpy(raw))
+
+
 @case("c3_ft_double_heads")
 def _ft_double():
     """GraphGPTDoubleHeadsModel with use_aux: edge-level task loss + auxiliary LM loss over pretrain_labels [N,S]
