@@ -343,6 +343,29 @@ int ggpt_ft_intra_bwd(const void* hidden, long long ld, const long long* cls_idx
                       const float* logits, const float* loss_out, const float* gout, float* dl_scratch, float* g_scratch,
                       void* dhidden, long long ldd, int N, int S, int C, int d, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Eulerian-path serialisation of a batch of graphs.  ggpt_euler_paths is a HOST routine (all pointers are
+ * host pointers; multi-threaded C++, n_threads <= 0 = all cores): for graph g with node_count[g] nodes and the undirected
+ * edges edges[2*edge_off[g] .. 2*edge_off[g+1]) (local node ids) it walks every connected component along an Euler
+ * circuit of the eulerised component (odd-degree nodes joined along shortest paths), cut at the step that covers the
+ * last edge, visits components in random order joined by jump edges, and re-indexes the nodes cyclically in order of
+ * first appearance: node_map[node_off[g] + v] = (start_g + k_v) % scope.  steps = (src, tgt, original edge index within
+ * the graph's de-duplicated edge list | -1 for a jump edge) triples, graph g at steps[3*step_off[g] ..).  Returns the
+ * total number of steps; when steps == NULL or steps_cap is too small nothing is copied (sizing call).
+ * ref: src/utils/nx_utils.py:388-422 (graph2path_v2, connected_graph2path), :331-348 (shorten_path), :234-260 (cyclic map).
+ * The walk itself is a random object (networkx matching + Python's RNG in the reference): parity is property-level
+ * (oracle/euler_oracle.py), the re-index given the walk is exact.
+ * ggpt_stack_path_rows (DEVICE): one row of stacked tokens per path position — node-id token, the node's attribute tokens,
+ * the traversed edge's attribute tokens (default tokens for the first row and for jump edges).
+ * ref: src/data/tokenizer.py:1196-1266 (stack_node_edge_graph_attr_to_node).
+ * ------------------------------------------------------------------------------------------- */
+long long ggpt_euler_paths(int n_graphs, const int* node_count, const long long* edge_off, const int* edges,
+                           unsigned long long seed, int scope, int n_threads, long long* step_off, int* steps,
+                           long long steps_cap, long long* node_off, int* node_map);
+int ggpt_stack_path_rows(const int* row_node, const int* row_edge, const int* node_map, const long long* node_attr,
+                         int n_node_attr, const long long* edge_attr, int n_edge_attr, const long long* default_edge,
+                         long long node_base, long long* rows, long long R, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -294,3 +294,36 @@ def test_expand_rows_equals_memset_plus_scatter(n_out, d, density):
         want[idx.long()] = src[:n]
     got = ops.expand_rows(src, idx if n else torch.zeros(1, device="cuda", dtype=torch.int32), n, n_out)
     assert torch.equal(got, want)
+
+
+def test_stack_path_rows_matches_python_stacking():
+    """ggpt_stack_path_rows (device gather of the stacked token rows, tokenizer.py:1196-1266) against a plain numpy
+    restatement, on walks produced by the C++ Euler routine; the rows then feed the device-side packer."""
+    import numpy as np
+    from graphgpt_b200 import euler
+    rng = np.random.default_rng(4)
+    An, Ae, base = 3, 2, 22
+    graphs, node_attr, edge_attr = [], [], []
+    for _ in range(40):
+        n = int(rng.integers(1, 25))
+        edges = [(j, int(rng.integers(max(0, j - 3), j))) for j in range(1, n)]
+        e = euler.dedup_edges(np.asarray(edges, dtype=np.int64).reshape(-1, 2), n)
+        graphs.append((n, e))
+        node_attr.append(rng.integers(600, 700, size=(n, An)))
+        edge_attr.append(rng.integers(700, 750, size=(len(e), Ae)))
+    steps, maps = euler.euler_paths(graphs, seed=5, scope=512)
+    default_edge = np.asarray([598, 599], dtype=np.int64)
+    row_node, row_edge, expect = [], [], []
+    n_off = e_off = 0
+    for (n, e), st, mp, na, ea in zip(graphs, steps, maps, node_attr, edge_attr):
+        rn, re_ = euler.path_rows(st, n_off, e_off)
+        row_node.append(rn)
+        row_edge.append(re_)
+        for node, edge in zip(rn - n_off, np.where(re_ >= 0, re_ - e_off, -1)):
+            expect.append([base + int(mp[node])] + na[node].tolist() + (ea[edge].tolist() if edge >= 0 else default_edge.tolist()))
+        n_off += n
+        e_off += len(e)
+    cat = lambda xs, dt: torch.from_numpy(np.concatenate(xs).astype(dt)).cuda()
+    rows = euler.stack_rows(cat(row_node, np.int32), cat(row_edge, np.int32), cat(maps, np.int32), cat(node_attr, np.int64),
+                            cat([x.reshape(-1, Ae) for x in edge_attr], np.int64), torch.from_numpy(default_edge).cuda(), base)
+    assert torch.equal(rows.cpu(), torch.tensor(expect, dtype=torch.int64))
