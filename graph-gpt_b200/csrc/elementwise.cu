@@ -859,6 +859,18 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat1
     for (long long i = n4 * 4; i < n; ++i) dst[i] = __float2bfloat16_rn(src[i]);
 }
 
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, long long n) {
+  const long long n4 = n / 4;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint2 v = reinterpret_cast<const uint2*>(src)[i];
+    const float2 a = unpack_bf16(v.x), b = unpack_bf16(v.y);
+    reinterpret_cast<float4*>(dst)[i] = make_float4(a.x, a.y, b.x, b.y);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (long long i = n4 * 4; i < n; ++i) dst[i] = __bfloat162float(src[i]);
+}
+
 }  // namespace ggpt
 
 using namespace ggpt;
@@ -1084,6 +1096,15 @@ int ggpt_cast_f32_bf16(const float* src, void* dst, long long n, void* stream) {
   cast_f32_bf16_kernel<<<grid_for_rows(n / 4 + 1, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       src, static_cast<__nv_bfloat16*>(dst), n);
   return check_launch("cast_f32_bf16_kernel");
+}
+
+int ggpt_cast_bf16_f32(const void* src, float* dst, long long n, void* stream) {
+  GGPT_REQUIRE(src && dst && n > 0, "cast: bad arguments");
+  GGPT_REQUIRE((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (reinterpret_cast<uintptr_t>(src) & 7) == 0,
+               "cast: pointers must be 16/8-byte aligned");
+  cast_bf16_f32_kernel<<<grid_for_rows(n / 4 + 1, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(src), dst, n);
+  return check_launch("cast_bf16_f32_kernel");
 }
 
 }  // extern "C"

@@ -21,24 +21,46 @@ from . import ops
 
 class GradReducer:
     """Launches async all-reduces over [start,end) spans of one flat tensor and waits for them later.
-    Device-agnostic (NCCL on GPUs, gloo in the CPU tests)."""
+    Device-agnostic (NCCL on GPUs, gloo in the CPU tests).
 
-    def __init__(self, flat_grad, group=None):
+    wire_dtype = torch.bfloat16 exchanges the gradients in bf16 — what the reference's DeepSpeed bf16 configuration does
+    (ds_config2_pt_bf16.json: bf16 enabled => gradients are reduced in bf16): each span is cast into a bf16 staging buffer
+    (one streaming kernel), all-reduced at half the NVLink bytes, and cast back into the fp32 flat gradient after the
+    wait.  The fp32 accumulation of the wgrad GEMMs, the clipping norm and AdamW are unchanged."""
+
+    def __init__(self, flat_grad, group=None, wire_dtype=None, staging=None):
         self.flat = flat_grad
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.pending = []
         self.spans = []
+        self.wire_dtype = wire_dtype if wire_dtype not in (None, torch.float32) else None
+        self.staging = staging
+        if self.wire_dtype is not None and self.staging is None and self.world > 1:
+            self.staging = torch.empty(flat_grad.shape, device=flat_grad.device, dtype=self.wire_dtype)
 
     def reduce_span(self, start, end):
         self.spans.append((start, end))
         if self.world == 1:
             return
-        self.pending.append(dist.all_reduce(self.flat[start:end], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        if self.wire_dtype is None:
+            buf = self.flat[start:end]
+        else:
+            buf = self.staging[start:end]
+            if self.flat.is_cuda:
+                ops.cast_f32_bf16(self.flat[start:end], buf)
+            else:                               # CPU unit tests (gloo) only
+                buf.copy_(self.flat[start:end])
+        self.pending.append((dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True), start, end))
 
     def wait(self):
-        for w in self.pending:
+        for w, start, end in self.pending:
             w.wait()
+            if self.wire_dtype is not None:
+                if self.flat.is_cuda:
+                    ops.cast_bf16_f32(self.staging[start:end], self.flat[start:end])
+                else:
+                    self.flat[start:end].copy_(self.staging[start:end])
         self.pending = []
         spans, self.spans = self.spans, []
         return spans
@@ -83,7 +105,8 @@ def write_model_pt(module, ckp_dir):
 
 class GraphGPTEngine:
     def __init__(self, model, *, lr=3e-4, betas=(0.9, 0.95), eps=1e-6, weight_decay=0.1, max_grad_norm=1.0,
-                 lr_schedule=None, process_group=None, overlap_comm=True, gradient_accumulation_steps=1):
+                 lr_schedule=None, process_group=None, overlap_comm=True, gradient_accumulation_steps=1,
+                 grad_reduce_dtype=torch.bfloat16):
         self.module = model
         # DeepSpeed semantics (ds_config["gradient_accumulation_steps"], conf_utils.py:62-65): backward() scales the loss
         # by 1/gas and accumulates; the gradient exchange and the optimizer run on every gas-th step() only
@@ -107,7 +130,12 @@ class GraphGPTEngine:
         self.extra = [p for p in model.parameters() if id(p) not in flat_ids and p.requires_grad]
         self.extra_opt = (torch.optim.AdamW(self.extra, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
                           if self.extra else None)
-        self.reducer = GradReducer(self.flat.flat_grad, process_group)
+        # gradients cross NVLink in bf16 by default, as under the reference's DeepSpeed bf16 configuration
+        # (grad_reduce_dtype=torch.float32 keeps the exchange in fp32)
+        self.grad_reduce_dtype = grad_reduce_dtype
+        self._wire = (torch.empty((n,), device=dev, dtype=grad_reduce_dtype)
+                      if (self.world > 1 and grad_reduce_dtype not in (None, torch.float32)) else None)
+        self.reducer = GradReducer(self.flat.flat_grad, process_group, grad_reduce_dtype, self._wire)
         if self.world > 1:
             self._broadcast_params()
 
@@ -145,7 +173,7 @@ class GraphGPTEngine:
             hot.grad_ready_hook = None
             loss.backward()
             return
-        self.reducer = GradReducer(self.flat.flat_grad, self.group)
+        self.reducer = GradReducer(self.flat.flat_grad, self.group, self.grad_reduce_dtype, self._wire)
         if self.world > 1 and self.overlap_comm:
             hot.grad_ready_hook = lambda first, last: self.reducer.reduce_span(*self.flat.span(first, last))
         else:

@@ -651,3 +651,7 @@ def adamw(p, p_bf16, g, m, v, *, lr, betas, eps, weight_decay, step, gnorm_sq=No
 
 def cast_f32_bf16(src, dst):
     lib.ggpt_cast_f32_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), _stream())
+
+
+def cast_bf16_f32(src, dst):
+    lib.ggpt_cast_bf16_f32(src.data_ptr(), dst.data_ptr(), src.numel(), _stream())

@@ -272,6 +272,8 @@ int ggpt_adamw(float* p, void* p_bf16, const float* g, float* m, float* v, long 
                float beta2, float eps, float weight_decay, int step, const double* gnorm_sq, float max_norm,
                float grad_scale, void* stream);
 int ggpt_cast_f32_bf16(const float* src, void* dst, long long n, void* stream);
+/* bf16 -> fp32 (gradient segments come back from a bf16 all-reduce; ref: ds_config2_pt_bf16.json:24-27 reduces in bf16) */
+int ggpt_cast_bf16_f32(const void* src, float* dst, long long n, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Validation-only PRECISE mode (GGPT_PRECISE=1 in the Python host; never on the bench / training path).

@@ -200,6 +200,14 @@ spans = red.wait()
 expect = torch.arange(1000, dtype=torch.float32) * 3
 assert torch.equal(flat, expect), (flat[:4], expect[:4])
 assert sorted(spans) == [(0, 128), (128, 512), (512, 768), (768, 1000)]
+# bf16 on the wire (the DeepSpeed-bf16 behaviour, default of GraphGPTEngine): same protocol through a staging buffer
+flat2 = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+red2 = GradReducer(flat2, wire_dtype=torch.bfloat16)
+for a, b in ((512, 1000), (0, 512)):
+    red2.reduce_span(a, b)
+red2.wait()
+assert flat2.dtype == torch.float32 and torch.allclose(flat2, expect, rtol=2 ** -7, atol=0), (flat2[-4:], expect[-4:])
+assert torch.equal(flat2[:80], expect[:80])            # integers up to 256 are exact in bf16
 dist.barrier(); dist.destroy_process_group()
 print("ok", rank)
 """
