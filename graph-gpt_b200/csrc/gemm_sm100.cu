@@ -33,7 +33,7 @@
 
 namespace ggpt {
 
-enum : int { EPI_BF16 = 0, EPI_F32 = 1, EPI_RESID = 2, EPI_GEGLU = 3, EPI_QKV_ROPE = 4, EPI_DGEGLU = 5 };
+enum : int { EPI_BF16 = 0, EPI_F32 = 1, EPI_RESID = 2, EPI_GEGLU = 3, EPI_QKV_ROPE = 4, EPI_DGEGLU = 5, EPI_DGEGLU_TMA = 6 };
 
 struct GemmParams {
   int M, N, K;
@@ -63,22 +63,25 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kGemmThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant)
 
-template <int BN, bool PAIR>
+template <int BN, bool PAIR, int EPI>
 struct GemmSmem {
   static constexpr int kABytes = BM * BK * 2;  // 16 KB
   static constexpr int kBBytes = (PAIR ? BN / 2 : BN) * BK * 2;   // a CTA of a pair holds half of the B tile's rows
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256 && !PAIR) ? 4 : 6;
-  static constexpr int kStagingBytes = 8 * 4096;   // one 32 x 128 B transposition buffer per epilogue warp
+  // EPI_DGEGLU_TMA trades mainloop stages for a 3-deep ring of TMA-staged factor tiles (see its epilogue)
+  static constexpr int kStages = (EPI == EPI_DGEGLU_TMA) ? (PAIR ? 4 : 2) : ((BN == 256 && !PAIR) ? 4 : 6);
+  // one 32 x 128 B transposition buffer per epilogue warp;  DGEGLU_TMA: 3 x [gf1 chunk 16 KB | gf2 chunk 16 KB]
+  static constexpr int kStagingBytes = (EPI == EPI_DGEGLU_TMA) ? 3 * 32768 : 8 * 4096;
   static constexpr int kBarBytes = 256;
   static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kBarBytes + 1024;  // +1024 alignment slack
 };
 
 template <int BN, bool A_MN, bool B_MN, int EPI, int CL, bool PAIR>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmF, const GemmParams p) {
   static_assert(!PAIR || CL == 2, "a CTA pair is a cluster of two");
-  using S = GemmSmem<BN, PAIR>;
+  using S = GemmSmem<BN, PAIR, EPI>;
   constexpr int kStages = S::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -114,6 +117,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     mbar_init(&tfull_bar[1], 1);
     mbar_init(&tempty_bar[0], PAIR ? 16 : 8);   // pair mode: the epilogue warps of BOTH CTAs arrive on the leader's barrier
     mbar_init(&tempty_bar[1], PAIR ? 16 : 8);
+    if constexpr (EPI == EPI_DGEGLU_TMA) {
+      uint64_t* fbar = reinterpret_cast<uint64_t*>(bar_base + 192);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) mbar_init(&fbar[i], 1);
+      tma_prefetch_desc(&tmE);
+      tma_prefetch_desc(&tmF);
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -260,6 +270,98 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
     }
+  } else if constexpr (EPI == EPI_DGEGLU_TMA) {
+    // ===================== Epilogue warps (2..9), down_proj dgrad + GeGLU backward with TMA-staged factors =============
+    // acc = dact;  dgu = [ dact * gf[:, 0:N] | dact * gf[:, N:2N] ]  moves 8 bytes per accumulator element (4 in, 4 out):
+    // HBM-bound, 0.25 ms per layer at 65 536 tokens against a 0.22 ms mainloop.  Per-lane __ldg factor loads could not
+    // keep enough bytes in flight (0.55 ms).  Here the factor tiles travel by TMA: the accumulator tile is processed
+    // in 64-column chunks; for chunk g a [128 x 64] box of each factor half is loaded into one of THREE 32 KB smem buffers
+    // (SWIZZLE_128B, two chunks ahead of the compute), every thread multiplies its row's 32 columns IN PLACE (row-per-lane
+    // 16-byte accesses are conflict-free under the 128-byte swizzle), and the same buffer leaves through a TMA store
+    // (UTMASTG).  The ring spans tiles, so the loads of the next tile's first chunks overlap the current tile's tail.
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    uint8_t* fring = smem + kStages * S::kStageBytes;
+    uint64_t* fbar = reinterpret_cast<uint64_t*>(bar_base + 192);
+    const bool leader = (warp == 2 && lane == 0);
+    constexpr int kCh = BN / 64;
+    const int my_tiles = (num_tiles > item0) ? (num_tiles - item0 + item_stride - 1) / item_stride : 0;
+    const int n_chunks = my_tiles * kCh;
+    auto chunk_coords = [&](int g, int& m0, int& col) {
+      const int item = item0 + (g / kCh) * item_stride;
+      const int tile = item % mn_tiles;
+      m0 = ((tile / p.num_n_blocks) * CL + rank) * BM;
+      col = (tile % p.num_n_blocks) * BN + (g % kCh) * 64;
+    };
+    auto issue_load = [&](int g) {
+      int m0, col;
+      chunk_coords(g, m0, col);
+      uint8_t* buf = fring + (g % 3) * 32768;
+      mbar_expect_tx(&fbar[g % 3], 32768);
+      tma_load_2d(buf, &tmE, &fbar[g % 3], col, m0);
+      tma_load_2d(buf + 16384, &tmE, &fbar[g % 3], p.N + col, m0);
+    };
+    if (leader) {
+      if (n_chunks > 0) issue_load(0);
+      if (n_chunks > 1) issue_load(1);
+    }
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int rr = quad * 32 + lane;             // this thread's row of the tile
+    for (int g = 0; g < n_chunks; ++g) {
+      const int c = g % kCh;
+      if (c == 0) {
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+      }
+      mbar_wait(&fbar[g % 3], (g / 3) & 1);
+      uint8_t* buf = fring + (g % 3) * 32768;
+      uint32_t r[32];
+      tmem_ld32(tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16) + c * 64 + half * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t off = rr * 128u + (((half * 4 + q) ^ (rr & 7)) << 4);
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+          uint4* ptr = reinterpret_cast<uint4*>(buf + f * 16384 + off);
+          const uint4 v = *ptr;
+          const float2 f01 = unpack_bf16(v.x), f23 = unpack_bf16(v.y), f45 = unpack_bf16(v.z), f67 = unpack_bf16(v.w);
+          uint4 o;
+          o.x = pack_bf16(__uint_as_float(r[q * 8 + 0]) * f01.x, __uint_as_float(r[q * 8 + 1]) * f01.y);
+          o.y = pack_bf16(__uint_as_float(r[q * 8 + 2]) * f23.x, __uint_as_float(r[q * 8 + 3]) * f23.y);
+          o.z = pack_bf16(__uint_as_float(r[q * 8 + 4]) * f45.x, __uint_as_float(r[q * 8 + 5]) * f45.y);
+          o.w = pack_bf16(__uint_as_float(r[q * 8 + 6]) * f67.x, __uint_as_float(r[q * 8 + 7]) * f67.y);
+          *ptr = o;
+        }
+      }
+      fence_proxy_async_smem();                  // the in-place products must be visible to the TMA store
+      if (c == kCh - 1) {                        // accumulator fully drained: hand the TMEM buffer back to the MMA thread
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_cluster(&tempty_bar[acc], 0);
+          else mbar_arrive(&tempty_bar[acc]);
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+      asm volatile("bar.sync 2, 256;" ::: "memory");   // all eight epilogue warps have written this chunk
+      if (leader) {
+        int m0, col;
+        chunk_coords(g, m0, col);
+        tma_store_2d(&tmF, buf, col, m0);
+        tma_store_2d(&tmF, buf + 16384, p.N + col, m0);
+        tma_store_commit();
+        if (g + 2 < n_chunks) {
+          tma_store_wait_read<1>();              // the store of chunk g-1 has read buffer (g+2) % 3: refill it
+          issue_load(g + 2);
+        }
+      }
+    }
+    if (leader) tma_store_wait_all();
   } else {
     // ===================== Epilogue warps (2..9) =====================
     // TMEM rows are thread-private (lane = row), so writing them straight to HBM would touch 32 different
@@ -574,8 +676,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // ---------------------------------------------------------------------------------------------
 template <int BN, bool A_MN, bool B_MN, int EPI, int CL, bool PAIR>
 static int launch_gemm_cl(const void* A, long long lda, const void* B, long long ldb, GemmParams p, cudaStream_t stream) {
-  using S = GemmSmem<BN, PAIR>;
-  CUtensorMap tmA, tmB;
+  using S = GemmSmem<BN, PAIR, EPI>;
+  CUtensorMap tmA, tmB, tmE, tmF;
   int rc;
   // A: K-major -> global [M rows, K cols], box 128 x 64.  MN-major -> global [K rows, M cols], box 64 x 64.
   if (!A_MN) rc = make_tmap_2d_bf16(&tmA, A, p.M, p.K, lda, BM, 64);
@@ -588,6 +690,15 @@ static int launch_gemm_cl(const void* A, long long lda, const void* B, long long
   else rc = make_tmap_2d_bf16(&tmB, B, p.K, b_rows_total, ldb, 64, 64);
   if (rc) return rc;
 
+  if (EPI == EPI_DGEGLU_TMA) {   // factor tiles in, products out: [M, 2N] bf16, boxes of 128 rows x 64 columns
+    rc = make_tmap_2d_bf16(&tmE, p.gu, p.M, 2ull * p.N, p.ldgu, BM, 64);
+    if (rc) return rc;
+    rc = make_tmap_2d_bf16(&tmF, p.C, p.M, 2ull * p.N, p.ldc, BM, 64);
+    if (rc) return rc;
+  } else {
+    tmE = tmA;
+    tmF = tmA;
+  }
   const int items = ((p.num_m_blocks + CL - 1) / CL) * p.num_n_blocks * p.num_splits;
   int grid = num_sms() / CL * CL;
   if (grid > items * CL) grid = items * CL;
@@ -603,7 +714,7 @@ static int launch_gemm_cl(const void* A, long long lda, const void* B, long long
     attr_set = true;
   }
   if (CL == 1) {
-    kern<<<grid, kGemmThreads, S::kTotal, stream>>>(tmA, tmB, p);
+    kern<<<grid, kGemmThreads, S::kTotal, stream>>>(tmA, tmB, tmE, tmF, p);
   } else {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
@@ -617,7 +728,7 @@ static int launch_gemm_cl(const void* A, long long lda, const void* B, long long
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmE, tmF, p);
     if (e != cudaSuccess) {
       set_error("gemm: cluster launch failed: %s", cudaGetErrorString(e));
       return -2;
@@ -730,6 +841,12 @@ int ggpt_gemm_bf16_dgeglu(const void* dy, long long lda, const void* Wd, long lo
                "gemm_dgeglu: I and leading dimensions must be multiples of 8 and cover [gate | up]");
   GemmParams p{};
   p.M = M; p.N = I; p.K = K; p.C = dgu; p.ldc = lddgu; p.gu = gu; p.ldgu = ldgu;
+  // TMA-staged factor tiles need whole 256-column accumulator tiles inside each half (I = 4 d, d a multiple of 64, always
+  // satisfies this); GGPT_DGEGLU_TMA=0 selects the per-lane-load epilogue for A/B profiling
+  static const char* tma_env = getenv("GGPT_DGEGLU_TMA");
+  const bool use_tma = (I % 256 == 0) && !(tma_env != nullptr && tma_env[0] == '0') &&
+                       (reinterpret_cast<uintptr_t>(gu) & 15) == 0 && (reinterpret_cast<uintptr_t>(dgu) & 15) == 0;
+  if (use_tma) return launch_gemm<256, false, true, EPI_DGEGLU_TMA>(dy, lda, Wd, ldb, p, static_cast<cudaStream_t>(stream));
   return launch_gemm<256, false, true, EPI_DGEGLU>(dy, lda, Wd, ldb, p, static_cast<cudaStream_t>(stream));
 }
 

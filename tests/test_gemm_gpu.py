@@ -165,7 +165,7 @@ def test_gemm_wgrad_split_k(M, N, K):
     _report(f"wgrad split-k {M}x{N}x{K}", out, base + ref, 1e-4)
 
 
-@pytest.mark.parametrize("M,I,K", [(1000, 3072, 768), (130, 256, 64)])
+@pytest.mark.parametrize("M,I,K", [(1000, 3072, 768), (130, 256, 64), (300, 320, 128), (9000, 1024, 256), (77, 512, 768)])
 def test_gemm_dgeglu(M, I, K):
     """Fused down_proj dgrad + GeGLU backward against torch autograd of gelu(g)*u."""
     from graphgpt_b200 import ops
