@@ -441,16 +441,12 @@ attn_diag_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       const uint32_t d = tmem_base + st * 256 + lane_addr;
       const bool ok = r < it.len;
       const long long grow = static_cast<long long>(it.n) * p.S + it.r0 + r;
-      float cs[32], sn[32];
+      // cos / sin rows of this thread's token stay in the swizzled smem tables and are read 8 columns at a time inside
+      // store_pair: holding all 64 values in registers next to the accumulator rows pushed the kernel over the 168
+      // registers a 10-warp CTA can have (3 warps on one scheduler: 16384 / 96), and the spill stores of the PREFETCHED
+      // per-row inputs then waited for their global loads — a third of all warp stalls (ncu, profiles/r2n_*)
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       pair_barrier();
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 a = *reinterpret_cast<const float4*>(gb_cos + lane * 128 + ((j ^ (lane & 7)) << 4));
-        const float4 b = *reinterpret_cast<const float4*>(gb_sin + lane * 128 + ((j ^ (lane & 7)) << 4));
-        cs[j * 4 + 0] = a.x; cs[j * 4 + 1] = a.y; cs[j * 4 + 2] = a.z; cs[j * 4 + 3] = a.w;
-        sn[j * 4 + 0] = b.x; sn[j * 4 + 1] = b.y; sn[j * 4 + 2] = b.z; sn[j * 4 + 3] = b.w;
-      }
       mbar_wait(&acc_full[st], (i >> 1) & 1);
       tc_fence_after();
       // (staging these stores through smem for full-line writes, as the forward kernel does, was measured slower here:
@@ -461,16 +457,27 @@ attn_diag_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           float o1[8], o2[8];
+          if (rot) {
+            float cs[8], sn[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float d1 = __uint_as_float(x1[g * 8 + j]), d2 = __uint_as_float(x2[g * 8 + j]);
-            if (rot) {
-              const float c = cs[g * 8 + j], s = sn[g * 8 + j];
-              o1[j] = d1 * c + d2 * s;
-              o2[j] = d2 * c - d1 * s;
-            } else {
-              o1[j] = d1;
-              o2[j] = d2;
+            for (int q = 0; q < 2; ++q) {
+              const int ch = ((2 * g + q) ^ (lane & 7)) << 4;
+              const float4 a = *reinterpret_cast<const float4*>(gb_cos + lane * 128 + ch);
+              const float4 b = *reinterpret_cast<const float4*>(gb_sin + lane * 128 + ch);
+              cs[q * 4 + 0] = a.x; cs[q * 4 + 1] = a.y; cs[q * 4 + 2] = a.z; cs[q * 4 + 3] = a.w;
+              sn[q * 4 + 0] = b.x; sn[q * 4 + 1] = b.y; sn[q * 4 + 2] = b.z; sn[q * 4 + 3] = b.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float d1 = __uint_as_float(x1[g * 8 + j]), d2 = __uint_as_float(x2[g * 8 + j]);
+              o1[j] = d1 * cs[j] + d2 * sn[j];
+              o2[j] = d2 * cs[j] - d1 * sn[j];
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              o1[j] = __uint_as_float(x1[g * 8 + j]);
+              o2[j] = __uint_as_float(x2[g * 8 + j]);
             }
           }
           uint4 v1, v2;
