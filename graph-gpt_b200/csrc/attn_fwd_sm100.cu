@@ -18,20 +18,27 @@
 // per thread).  QK^T and PV run on tcgen05 with accumulators in TMEM; P goes through shared memory (bf16, 128B
 // swizzle) as the A operand of the PV MMA; V is consumed in place as an MN-major B operand.  Two CTAs fit per SM
 // (112 KB smem, 256 TMEM columns each) so one CTA's softmax overlaps the other's MMAs.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "attn_diag.cuh"
 #include "../../include/ggpt_b200.h"
 
 namespace ggpt {
 
-constexpr int kAttThreads = 192;
+constexpr int kAttSoftmaxWarps = 8;
+constexpr int kAttThreads = 64 + 32 * kAttSoftmaxWarps;
 constexpr int kTileQ = 128;
 constexpr int kTileK = 128;
 constexpr int kHeadDim = 64;
-constexpr int kAttSmem = 16384 /*Q*/ + 2 * 16384 /*K*/ + 2 * 16384 /*V*/ + 32768 /*P*/ + 256 /*barriers*/;
+// 2 CTAs per SM: 2 * (kAttSmem + 1 KB reserved) must stay within the SM's 228 KB — the 1 KB tail (barriers + tile plan)
+// is all that is left
+constexpr int kAttSmem = 16384 /*Q*/ + 2 * 16384 /*K*/ + 2 * 16384 /*V*/ + 32768 /*P*/ + 1024 /*barriers, tile plan*/;
+static_assert(2 * (kAttSmem + 1024) <= 233472, "two attention-forward CTAs must fit one SM");
 
 struct AttnFwdParams {
   int N, S, H;
+  int heads_per_cta;          // consecutive heads served by one CTA of the general kernel
   int max_tiles;              // allocation stride of the tile arrays (= ceil(S/64))
   int mask_words;             // uint32 words per mask row (multiple of 4, padded by 4)
   const uint32_t* mask_bits;  // [N, S, mask_words]
@@ -40,6 +47,7 @@ struct AttnFwdParams {
   const uint8_t* tile_cls;    // [N, max_tiles, max_tiles]  (query tile, key tile)
   const uint8_t* iso_flags;   // [N, max_tiles] tiles handled by the persistent diagonal kernel (may be NULL)
   __nv_bfloat16* out;         // [N*S, H*64]
+  __nv_bfloat16* out_lo;      // [N*S, H*64] bf16(O - bf16(O)), same ld (may be NULL): makes D = dO.(O + O_lo) exact in backward
   long long ldo;
   float* lse;                 // [N, H, S]  natural-log logsumexp of the scaled scores (for backward)
   int q_col0, k_col0, v_col0; // column offsets of q/k/v inside the fused qkv row
@@ -62,48 +70,39 @@ __device__ __forceinline__ void load_mask_words(const uint32_t* __restrict__ mro
   }
 }
 
-// Online-softmax update of one thread's query row for one 128-key tile: reads the scores twice from TMEM (row max, then
-// probabilities), writes bf16 P into the swizzled K-major A-operand buffer, returns the rescale factor of the running
-// output.  MASKED = the tile pair is "mixed" (class 2) and every element consults its mask bit; full tiles (class 1) skip
-// all mask work.  DROP = attention dropout is on (one 32-bit draw per key pair, see common.cuh).
-template <bool MASKED, bool DROP>
-__device__ __forceinline__ float fwd_softmax_tile(uint32_t tS, uint8_t* prow, int r, const uint32_t (&mw)[4],
-                                                  float scale_log2, float& m_run, float& l_run, uint32_t rk1,
-                                                  uint32_t rk2, int k0, uint32_t thresh) {
-  float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // independent chains instead of a 128-deep max
-#pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
-    uint32_t s[32];
-    tmem_ld32(tS + c * 32, s);
-    tmem_ld_wait();
-    const uint32_t w = (c == 0) ? mw[0] : (c == 1) ? mw[1] : (c == 2) ? mw[2] : mw[3];
+// Softmax work of one thread: HALF a query row (64 of the tile's 128 keys; two warps share a TMEM lane quadrant and split
+// the columns).  The 64 scores arrive in REGISTERS — the caller has already drained them from TMEM and handed the TMEM
+// buffer back to the MMA thread, so the score MMA of the next tile overlaps these functions.
+template <bool MASKED>
+__device__ __forceinline__ float fwd_half_max(const uint32_t (&s)[2][32], const uint32_t (&mw)[2]) {
+  float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // independent chains instead of a 64-deep max
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      float v = __uint_as_float(s[j]);
-      if (MASKED) v = ((w >> j) & 1u) ? v : -INFINITY;
+      float v = __uint_as_float(s[c][j]);
+      if (MASKED) v = ((mw[c] >> j) & 1u) ? v : -INFINITY;
       m4[j & 3] = fmaxf(m4[j & 3], v);
     }
   }
-  const float m_tile = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * scale_log2;   // scale > 0 commutes with max
-  const float m_new = fmaxf(m_run, m_tile);
-  const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-  const float alpha = (m_run == -INFINITY) ? 0.f : fast_exp2(m_run - m_use);
+  return fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+}
+
+// P = exp2(S * scale - m_used) (masked, then dropped) packed to bf16 IN PLACE: s[c][0..15] receive the 32 columns of
+// chunk c; returns the (undropped) sum of the half row.
+template <bool MASKED, bool DROP>
+__device__ __forceinline__ float fwd_half_exp(uint32_t (&s)[2][32], const uint32_t (&mw)[2], float scale_log2, float m_used,
+                                              uint32_t rk1, uint32_t rk2, int k0, uint32_t thresh) {
   float l4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
-    uint32_t s[32];
-    tmem_ld32(tS + c * 32, s);
-    tmem_ld_wait();
-    const uint32_t w = (c == 0) ? mw[0] : (c == 1) ? mw[1] : (c == 2) ? mw[2] : mw[3];
-    // columns c*32 .. c*32+31 of P: half = c/2 (64-col K block), 16-byte chunks (c&1)*4 .. +3
-    uint8_t* pbase = prow + (c >> 1) * 16384;
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       float pv[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float e = fast_exp2(fmaf(__uint_as_float(s[g * 8 + j]), scale_log2, -m_use));
-        if (MASKED) e = ((w >> (g * 8 + j)) & 1u) ? e : 0.f;
+        float e = fast_exp2(fmaf(__uint_as_float(s[c][g * 8 + j]), scale_log2, -m_used));
+        if (MASKED) e = ((mw[c] >> (g * 8 + j)) & 1u) ? e : 0.f;
         pv[j] = e;
         l4[j & 3] += e;
       }
@@ -115,19 +114,73 @@ __device__ __forceinline__ float fwd_softmax_tile(uint32_t tS, uint8_t* prow, in
           if (!drop_keep_odd(bits, thresh)) pv[j + 1] = 0.f;
         }
       }
-      uint4 o;
-      o.x = pack_bf16(pv[0], pv[1]);
-      o.y = pack_bf16(pv[2], pv[3]);
-      o.z = pack_bf16(pv[4], pv[5]);
-      o.w = pack_bf16(pv[6], pv[7]);
-      const int chunk = ((c & 1) * 4 + g) ^ (r & 7);
-      *reinterpret_cast<uint4*>(pbase + chunk * 16) = o;
+      s[c][g * 4 + 0] = pack_bf16(pv[0], pv[1]);
+      s[c][g * 4 + 1] = pack_bf16(pv[2], pv[3]);
+      s[c][g * 4 + 2] = pack_bf16(pv[4], pv[5]);
+      s[c][g * 4 + 3] = pack_bf16(pv[6], pv[7]);
     }
   }
-  l_run = l_run * alpha + ((l4[0] + l4[1]) + (l4[2] + l4[3]));
-  m_run = m_new;
-  return alpha;
+  return (l4[0] + l4[1]) + (l4[2] + l4[3]);
 }
+
+// One float per thread exchanged between the two warps that share a TMEM lane quadrant, through a spare TMEM column
+// (each thread's partner is the same lane of the other warp): st -> wait::st -> 64-thread named barrier -> ld.
+__device__ __forceinline__ float pair_exchange(uint32_t col_mine, uint32_t col_other, float v, int bar_id) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(col_mine), "r"(__float_as_uint(v)) : "memory");
+  tmem_st_wait();
+  tc_fence_before();
+  asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+  tc_fence_after();
+  uint32_t o;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(o) : "r"(col_other) : "memory");
+  tmem_ld_wait();
+  return __uint_as_float(o);
+}
+
+// OR of one predicate over the 64 threads of a quadrant's warp pair (named barrier with reduction).
+__device__ __forceinline__ bool pair_vote_or(bool v, int bar_id) {
+  uint32_t out;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %1, 0;\n\t"
+      "barrier.cta.red.or.pred q, %2, 64, p;\n\t"
+      "selp.b32 %0, 1, 0, q;\n\t}"
+      : "=r"(out)
+      : "r"(static_cast<uint32_t>(v)), "r"(bar_id)
+      : "memory");
+  return out != 0;
+}
+
+// Pipeline of one CTA (the two resident CTAs of an SM interleave two such pipelines):
+//   MMA thread     : S(0) | for it: [s_empty(it) & K(it+1)] -> S(it+1) ; [p_full(it) & V(it)] -> O (+)= P(it) V(it)
+//   softmax warps  : s_full(it) -> scores TMEM -> registers -> arrive s_empty   (the S buffer is free again: the score
+//                    MMA of tile it+1 runs while this tile's max / exp / pack are computed)
+//                    -> row max (halves combined through TMEM) -> lazy rescale of O in TMEM -> exp2 / mask / dropout /
+//                    pack -> pv_done(it-1) -> P to smem -> arrive p_full
+// EIGHT softmax warps, two threads per query row (64 keys each): the phases of a warp that do not use the MUFU pipe
+// (barrier waits, the TMEM drain, the row max, the P stores and their proxy fence, the output epilogue) are covered by the
+// exponentials of the other three warps of its scheduler — with four warps per CTA the MUFU pipe, the binding resource
+// at head_dim 64, was busy 36 % of the time (ncu, profiles/r2r_*).
+// O accumulates in TMEM over all key tiles.  The running maximum each row's sums are expressed against (m_used) is only
+// advanced — and O / l rescaled, by the row's own threads through tcgen05.ld / st — when the new maximum exceeds it by
+// more than 8 (log2 domain): stale maxima leave P <= 2^8, harmless in bf16 / fp32, and after the first tile or two of a
+// row the rescale almost never fires (the FlashAttention-4 "lazy rescale").
+constexpr float kRescaleThreshold = 8.0f;
+
+#ifdef GGPT_ATTN_TRACE      // profiling aid: per-phase clock64 stamps of one softmax warp of a few CTAs (tools/attn_trace.py)
+__device__ long long g_attn_trace[64 * 16 * 8];
+#define ATTN_TRACE(slot)                                                                                        \
+  do {                                                                                                          \
+    if (trace_on && lane == 0 && it < 16) g_attn_trace[(trace_cta * 16 + it) * 8 + (slot)] = clock64();          \
+  } while (0)
+#define ATTN_TRACE_H(slot)                                                                                      \
+  do {                                                                                                          \
+    if (trace_on && lane == 0) g_attn_trace[(trace_cta * 16 + 8 + (h - h_begin)) * 8 + (slot)] = clock64();      \
+  } while (0)
+#else
+#define ATTN_TRACE(slot) do { } while (0)
+#define ATTN_TRACE_H(slot) do { } while (0)
+#endif
 
 template <bool DROP>
 __global__ void __launch_bounds__(kAttThreads, 2)
@@ -139,22 +192,49 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
   uint8_t* sP = smem + 16384 + 65536;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 16384 + 65536 + 32768);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;    // [2]
-  uint64_t* kv_empty = bars + 3;   // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* o_full = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* k_full = bars + 1;     // [2]
+  uint64_t* k_empty = bars + 3;    // [2]  score MMA that read the stage has retired
+  uint64_t* v_full = bars + 5;     // [2]
+  uint64_t* v_empty = bars + 7;    // [2]  PV MMA that read the stage has retired
+  uint64_t* s_full = bars + 9;     // scores of tile g in TMEM
+  uint64_t* s_empty = bars + 10;   // ... and drained into registers (8 warps)
+  uint64_t* p_full = bars + 11;    // P(g) in smem, O rescaled if needed (8 warps)
+  uint64_t* pv_done = bars + 12;   // O += P(g) V(g) retired: P buffer reusable, O readable
+  uint64_t* q_empty = bars + 13;   // every score MMA of the current head has retired: Q buffer reusable
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
+  // One CTA serves ONE query tile for `heads_per_cta` consecutive heads: the tile plan, the TMEM allocation and the
+  // barrier set-up are paid once, and the output epilogue of head h overlaps the Q / K / V loads and the first score MMA
+  // of head h+1 (measured before: 44 % of a CTA's life was prologue + epilogue around an 8-tile loop).
+  const int qt = blockIdx.x, n = blockIdx.z;
+  const int h_begin = blockIdx.y * p.heads_per_cta;
+  const int h_end = min(p.H, h_begin + p.heads_per_cta);
   const int n_kt = p.n_tiles[n];
   if (qt >= n_kt) return;                       // uniform for the whole CTA, before any barrier / TMEM state
-  if (p.iso_flags != nullptr && p.iso_flags[n * p.max_tiles + qt]) return;   // done by attn_diag_fwd_kernel
-  const int* ts = p.tile_start + static_cast<size_t>(n) * (p.max_tiles + 1);
-  const int q0 = ts[qt], qlen = ts[qt + 1] - q0;
-  const uint8_t* cls_row = p.tile_cls + (static_cast<size_t>(n) * p.max_tiles + qt) * p.max_tiles;
+  const int* gts = p.tile_start + static_cast<size_t>(n) * (p.max_tiles + 1);
+  const int q0 = gts[qt], qlen = gts[qt + 1] - q0;
+  if (p.iso_flags != nullptr && p.iso_flags[n * p.max_tiles + qt]) {   // done by attn_diag_fwd_kernel
+    if (p.out_lo != nullptr) {                  // ... which stores no rounding residual: D of these rows uses bf16 O only
+      const int row_chunks = (h_end - h_begin) * 8;
+      for (int i = threadIdx.x; i < qlen * row_chunks; i += blockDim.x)
+        *reinterpret_cast<uint4*>(p.out_lo + (static_cast<long long>(n) * p.S + q0 + i / row_chunks) * p.ldo + h_begin * kHeadDim +
+                                  (i % row_chunks) * 8) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    return;
+  }
+  // this query tile's row of the tile plan (row offsets as uint16: S <= 16384; classes) is copied to shared memory once —
+  // every role reads it for every key tile, and a global load there is an L2 round trip on each tile's critical path
+  uint16_t* ts = reinterpret_cast<uint16_t*>(bars + 16);               // [<= 257]
+  uint8_t* cls_row = reinterpret_cast<uint8_t*>(bars + 16) + 520;      // [<= 256]
+  {
+    const uint8_t* g_cls = p.tile_cls + (static_cast<size_t>(n) * p.max_tiles + qt) * p.max_tiles;
+    for (int t = threadIdx.x; t <= n_kt; t += blockDim.x) {
+      ts[t] = static_cast<uint16_t>(gts[t]);
+      if (t < n_kt) cls_row[t] = g_cls[t];
+    }
+  }
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0) {
@@ -163,13 +243,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
     }
     tma_prefetch_desc(&tmQKV);
     mbar_init(q_full, 1);
-    mbar_init(&kv_full[0], 1);
-    mbar_init(&kv_full[1], 1);
-    mbar_init(&kv_empty[0], 1);
-    mbar_init(&kv_empty[1], 1);
+    mbar_init(q_empty, 1);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
     mbar_init(s_full, 1);
-    mbar_init(p_full, 4);
-    mbar_init(o_full, 1);
+    mbar_init(s_empty, kAttSoftmaxWarps);
+    mbar_init(p_full, kAttSoftmaxWarps);
+    mbar_init(pv_done, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -182,140 +267,251 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base;         // 128 columns
   const uint32_t tmem_O = tmem_base + 128;   // 64 columns
+  const uint32_t tmem_X = tmem_base + 192;   // 4 columns: row-max exchange [tile parity][column half]
+
+  int n_active = 0;                          // active key tiles of this query tile (the same for every head)
+  for (int kt = 0; kt < n_kt; ++kt) n_active += (cls_row[kt] != 0);
+  // g = running index of (head, active key tile) pairs: stage = g & 1 and phase = (g >> 1) & 1 of the K / V rings,
+  // parity g & 1 of the per-tile barriers — all barrier phases simply continue from one head to the next
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      mbar_expect_tx(q_full, 16384);
-      tma_load_3d(sQ, &tmQKV, q_full, p.q_col0 + h * kHeadDim, q0, n);
-      int it = 0;
-      for (int kt = 0; kt < n_kt; ++kt) {
-        if (cls_row[kt] == 0) continue;
-        const int st = it & 1;
-        mbar_wait(&kv_empty[st], ((it >> 1) & 1) ^ 1);
-        mbar_expect_tx(&kv_full[st], 32768);
-        tma_load_3d(sK + st * 16384, &tmQKV, &kv_full[st], p.k_col0 + h * kHeadDim, ts[kt], n);
-        tma_load_3d(sV + st * 16384, &tmQKV, &kv_full[st], p.v_col0 + h * kHeadDim, ts[kt], n);
-        ++it;
+    if (lane == 0 && n_active > 0) {
+      int g = 0;
+      for (int h = h_begin; h < h_end; ++h) {
+        if (h > h_begin) mbar_wait(q_empty, (h - h_begin - 1) & 1);
+        mbar_expect_tx(q_full, 16384);
+        tma_load_3d(sQ, &tmQKV, q_full, p.q_col0 + h * kHeadDim, q0, n);
+        for (int kt = 0; kt < n_kt; ++kt) {
+          if (cls_row[kt] == 0) continue;
+          const int st = g & 1;
+          const uint32_t ph = ((g >> 1) & 1) ^ 1;
+          mbar_wait(&k_empty[st], ph);
+          mbar_expect_tx(&k_full[st], 16384);
+          tma_load_3d(sK + st * 16384, &tmQKV, &k_full[st], p.k_col0 + h * kHeadDim, ts[kt], n);
+          mbar_wait(&v_empty[st], ph);
+          mbar_expect_tx(&v_full[st], 16384);
+          tma_load_3d(sV + st * 16384, &tmQKV, &v_full[st], p.v_col0 + h * kHeadDim, ts[kt], n);
+          ++g;
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (lane == 0 && n_active > 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, false, true);
       const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
-      auto issue_S = [&](int st) {
+      auto issue_S = [&](int g) {
+        const int st = g & 1;
+        mbar_wait(&k_full[st], (g >> 1) & 1);
+        tc_fence_after();
         const uint32_t aK = smem_u32(sK + st * 16384);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
           tc_mma_bf16(tmem_S, umma_desc_sw128(aQ + kk * 32, 16, 1024), umma_desc_sw128(aK + kk * 32, 16, 1024),
                       idesc_s, kk != 0);
         tc_commit(s_full);
+        tc_commit(&k_empty[st]);
       };
-      int n_active = 0;
-      for (int kt = 0; kt < n_kt; ++kt) n_active += (cls_row[kt] != 0);
-      if (n_active > 0) {
-        mbar_wait(q_full, 0);
-        mbar_wait(&kv_full[0], 0);
+      int g0 = 0;
+      for (int h = h_begin; h < h_end; ++h, g0 += n_active) {
+        mbar_wait(q_full, (h - h_begin) & 1);
+        if (g0 > 0) mbar_wait(s_empty, (g0 - 1) & 1);   // the last scores of the previous head are in registers
         tc_fence_after();
-        issue_S(0);
+        issue_S(g0);
         for (int it = 0; it < n_active; ++it) {
-          const int st = it & 1;
-          mbar_wait(p_full, it & 1);   // P(it) in smem, S(it) and O(it-1) drained from TMEM
+          const int g = g0 + it, st = g & 1;
+          if (it + 1 < n_active) {
+            mbar_wait(s_empty, g & 1);      // S(g) sits in the softmax warps' registers
+            tc_fence_after();
+            issue_S(g + 1);
+          } else {
+            tc_commit(q_empty);             // every score MMA of this head has been issued
+          }
+          mbar_wait(p_full, g & 1);         // P(g) in smem, O rescaled
+          mbar_wait(&v_full[st], (g >> 1) & 1);
           tc_fence_after();
           const uint32_t aV = smem_u32(sV + st * 16384);
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
             tc_mma_bf16(tmem_O, umma_desc_sw128(aP + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
-                        umma_desc_sw128(aV + kk * 2048, 8192, 1024), idesc_o, kk != 0);
-          tc_commit(o_full);
-          tc_commit(&kv_empty[st]);
-          if (it + 1 < n_active) {
-            const int st2 = (it + 1) & 1;
-            mbar_wait(&kv_full[st2], ((it + 1) >> 1) & 1);
-            tc_fence_after();
-            issue_S(st2);
-          }
+                        umma_desc_sw128(aV + kk * 2048, 8192, 1024), idesc_o, (it | kk) != 0);
+          tc_commit(pv_done);
+          tc_commit(&v_empty[st]);
         }
       }
     }
   } else {
-    // ===================== softmax / epilogue warps: one query row per thread =====================
+    // ===================== softmax / epilogue warps: two threads per query row =====================
     const int quad = warp & 3;
+    const int hc = (warp - 2) >> 2;              // column half of the score tile / of the output row
     const int r = quad * 32 + lane;              // row inside the tile
     const int q_row = q0 + r;
     const bool row_ok = r < qlen;
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t* mrow = p.mask_bits + (static_cast<size_t>(n) * p.S + (row_ok ? q_row : 0)) * p.mask_words;
+    uint8_t* prow = sP + hc * 16384 + r * 128;   // this thread's 64 columns are one 128-byte row of K block hc
+#ifdef GGPT_ATTN_TRACE
+    const int trace_cta = (blockIdx.z % 8) * 8 + blockIdx.x % 8;     // 64 traced CTAs: head group 1, sequences 8..15
+    const bool trace_on = (warp == 2) && blockIdx.y == 1 && blockIdx.z >= 8 && blockIdx.z < 16;
+#endif
 
-    float o_acc[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) o_acc[i] = 0.f;
-    const uint32_t rowkey = drop_rowkey(p.drop.seed_lo, p.drop.seed_hi, n, h, q_row);
-    const uint32_t rowkey2 = drop_rowkey2(rowkey);
-    float m_run = -INFINITY;   // running max of scaled (log2-domain) scores
-    float l_run = 0.f;
+    int g0 = 0;
+    for (int h = h_begin; h < h_end; ++h, g0 += n_active) {
+      const uint32_t rowkey = drop_rowkey(p.drop.seed_lo, p.drop.seed_hi, n, h, q_row);
+      const uint32_t rowkey2 = drop_rowkey2(rowkey);
+      float m_used = 0.f;     // log2-domain maximum the row's P / l / O are expressed against (same in both threads)
+      bool seen = false;      // some key of this row has been visible so far
+      float l_run = 0.f;      // this thread's half of the row sum
 
-    int it = 0;
-    for (int kt = 0; kt < n_kt; ++kt) {
-      const int cls = cls_row[kt];
-      if (cls == 0) continue;
-      uint32_t mw[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-      if (cls == 2) {
-        if (row_ok) {
-          load_mask_words(mrow, ts[kt], ts[kt + 1] - ts[kt], mw);
-        } else {
-          mw[0] = mw[1] = mw[2] = mw[3] = 0u;
+      int it = 0;
+      ATTN_TRACE_H(0);
+      for (int kt = 0; kt < n_kt; ++kt) {
+        const int cls = cls_row[kt];
+        if (cls == 0) continue;
+        const int g = g0 + it;
+        ATTN_TRACE(0);
+        uint32_t mw[2] = {0xffffffffu, 0xffffffffu};
+        if (cls == 2) {
+          if (row_ok) {
+            uint32_t w4[4];
+            load_mask_words(mrow, ts[kt], ts[kt + 1] - ts[kt], w4);
+            mw[0] = hc ? w4[2] : w4[0];
+            mw[1] = hc ? w4[3] : w4[1];
+          } else {
+            mw[0] = mw[1] = 0u;
+          }
         }
-      }
-      const int k0 = ts[kt];
-      mbar_wait(s_full, it & 1);
-      tc_fence_after();
-      const float alpha = (cls == 2)
-          ? fwd_softmax_tile<true, DROP>(tmem_S + lane_addr, sP + r * 128, r, mw, p.scale_log2, m_run, l_run, rowkey, rowkey2,
-                                         k0, p.drop.thresh)
-          : fwd_softmax_tile<false, DROP>(tmem_S + lane_addr, sP + r * 128, r, mw, p.scale_log2, m_run, l_run, rowkey,
-                                          rowkey2, k0, p.drop.thresh);
-      fence_proxy_async_smem();   // make P visible to the tensor-core (async) proxy
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
-      // accumulate O = O * alpha + P V
-      mbar_wait(o_full, it & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t o[32];
-        tmem_ld32(tmem_O + lane_addr + c * 32, o);
+        const int k0 = ts[kt] + hc * 64;
+        uint32_t s[2][32];
+        mbar_wait(s_full, g & 1);
+        ATTN_TRACE(6);
+        tc_fence_after();
+        tmem_ld32(tmem_S + lane_addr + hc * 64, s[0]);
+        tmem_ld32(tmem_S + lane_addr + hc * 64 + 32, s[1]);
         tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) o_acc[c * 32 + j] = fmaf(o_acc[c * 32 + j], alpha, __uint_as_float(o[j]));
-      }
-      ++it;
-    }
+        ATTN_TRACE(1);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_empty);
 
-    {
-      // every PV has retired (o_full of the last tile was waited for), so this warp's own 32 rows of the P buffer stage the
-      // output for full-line stores (stage_flush_rows) instead of 32 scattered 16-byte pieces per instruction
-      const float inv = (l_run > 0.f) ? p.drop.inv_keep / l_run : 0.f;   // dropout keeps are rescaled by 1/(1-p)
-      uint8_t* stg = sP + quad * 4096;
+        const float m_half = ((cls == 2) ? fwd_half_max<true>(s, mw) : fwd_half_max<false>(s, mw)) * p.scale_log2;
+        // The two threads of a row must agree on the reference maximum.  It only moves when one half's maximum is the
+        // row's first visible key or exceeds it by more than the threshold, so the halves first vote (one barrier with an
+        // OR reduction over the quadrant's two warps) and exchange their maxima — through TMEM, ~10x the cost of the vote
+        // — only when some row of the quadrant needs it: the first tile, and rarely afterwards.
+        const bool want = (m_half != -INFINITY) && (!seen || m_half > m_used + kRescaleThreshold);
+        bool need = false;
+        float alpha = 1.f;
+        if (pair_vote_or(want, 1 + quad)) {
+          const uint32_t xcol = tmem_X + lane_addr + (g & 1) * 2;
+          const float m_tile = fmaxf(m_half, pair_exchange(xcol + hc, xcol + (hc ^ 1), m_half, 1 + quad));
+          if (m_tile != -INFINITY) {
+            if (!seen) {                 // first visible keys of this row: O and l are still exactly zero
+              seen = true;
+              m_used = m_tile;
+            } else if (m_tile > m_used + kRescaleThreshold) {
+              need = true;
+              alpha = fast_exp2(m_used - m_tile);
+              m_used = m_tile;
+            }
+          }
+        }
+        ATTN_TRACE(2);
+        if (it > 0 && __any_sync(0xffffffffu, need)) {   // warp-uniform: tcgen05.ld / st are warp-collective
+          mbar_wait(pv_done, (g - 1) & 1);
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {                  // this thread's 32 output columns, 8 at a time
+            uint32_t o[8];
+            tmem_ld8(tmem_O + lane_addr + hc * 32 + c * 8, o);
+            tmem_ld_wait();
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        uint4 o;
-        o.x = pack_bf16(o_acc[g * 8 + 0] * inv, o_acc[g * 8 + 1] * inv);
-        o.y = pack_bf16(o_acc[g * 8 + 2] * inv, o_acc[g * 8 + 3] * inv);
-        o.z = pack_bf16(o_acc[g * 8 + 4] * inv, o_acc[g * 8 + 5] * inv);
-        o.w = pack_bf16(o_acc[g * 8 + 6] * inv, o_acc[g * 8 + 7] * inv);
-        stage_put16(stg, lane, g, o);
+            for (int j = 0; j < 8; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
+            tmem_st8(tmem_O + lane_addr + hc * 32 + c * 8, o);
+          }
+          tmem_st_wait();
+          l_run *= alpha;
+        }
+        const float l_tile = (cls == 2)
+            ? fwd_half_exp<true, DROP>(s, mw, p.scale_log2, m_used, rowkey, rowkey2, k0, p.drop.thresh)
+            : fwd_half_exp<false, DROP>(s, mw, p.scale_log2, m_used, rowkey, rowkey2, k0, p.drop.thresh);
+        l_run += l_tile;
+        ATTN_TRACE(3);
+        // the PV MMA of the previous tile has read the P buffer (tile 0 of a head: the epilogue of the previous head has
+        // waited for its last PV, and the pair's vote barrier above ordered this store behind the partner's flush of the
+        // staging rows that alias this buffer)
+        if (it > 0) mbar_wait(pv_done, (g - 1) & 1);
+        ATTN_TRACE(4);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq) {
+            const int chunk = (c * 4 + gq) ^ (r & 7);
+            *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(s[c][gq * 4 + 0], s[c][gq * 4 + 1], s[c][gq * 4 + 2], s[c][gq * 4 + 3]);
+          }
+        }
+        fence_proxy_async_smem();   // make P visible to the tensor-core (async) proxy
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+        ATTN_TRACE(5);
+        ++it;
       }
-      stage_flush_rows(stg, lane, p.out + (static_cast<long long>(n) * p.S + q0 + quad * 32) * p.ldo + h * kHeadDim, p.ldo,
-                       qlen - quad * 32);
-    }
-    if (row_ok) {
-      if (p.lse != nullptr) {
-        const float lse = (l_run > 0.f) ? (m_run * 0.6931471805599453f + logf(l_run)) : 0.f;
-        p.lse[(static_cast<size_t>(n) * p.H + h) * p.S + q_row] = lse;
+
+      {
+        // every PV of this head has retired, so the P buffer stages the output: the two warps of a quadrant fill one
+        // 32 x 128 B block (32 columns each) and flush 16 rows each as full 128-byte lines
+        ATTN_TRACE_H(1);
+        if (n_active > 0) {
+          mbar_wait(pv_done, (g0 + n_active - 1) & 1);
+          tc_fence_after();
+        }
+        ATTN_TRACE_H(2);
+        const uint32_t xcol = tmem_X + lane_addr;
+        const float l_row = l_run + pair_exchange(xcol + hc, xcol + (hc ^ 1), l_run, 1 + quad);
+        ATTN_TRACE_H(3);
+        const float inv = (l_row > 0.f) ? p.drop.inv_keep / l_row : 0.f;   // dropout keeps are rescaled by 1/(1-p)
+        uint8_t* stg = sP + quad * 4096;
+        uint8_t* stg_lo = sP + 16384 + quad * 4096;
+        uint32_t o[32];
+        if (n_active > 0) {
+          tmem_ld32(tmem_O + lane_addr + hc * 32, o);
+          tmem_ld_wait();
+          tc_fence_before();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[j] = 0u;
+        }
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) {
+          float f[8];
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(o[gq * 8 + j]) * inv;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            hi[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
+            const float2 back = unpack_bf16(hi[j]);
+            lo[j] = pack_bf16(f[2 * j] - back.x, f[2 * j + 1] - back.y);     // rounding residual of the bf16 output
+          }
+          stage_put16(stg, lane, hc * 4 + gq, make_uint4(hi[0], hi[1], hi[2], hi[3]));
+          if (p.out_lo != nullptr) stage_put16(stg_lo, lane, hc * 4 + gq, make_uint4(lo[0], lo[1], lo[2], lo[3]));
+        }
+        ATTN_TRACE_H(4);
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+        ATTN_TRACE_H(5);
+        const long long row0 = static_cast<long long>(n) * p.S + q0 + quad * 32 + hc * 16;
+        stage_flush_rows16(stg, lane, hc * 16, p.out + row0 * p.ldo + h * kHeadDim, p.ldo, qlen - quad * 32 - hc * 16);
+        if (p.out_lo != nullptr)
+          stage_flush_rows16(stg_lo, lane, hc * 16, p.out_lo + row0 * p.ldo + h * kHeadDim, p.ldo,
+                             qlen - quad * 32 - hc * 16);
+        if (row_ok && hc == 0 && p.lse != nullptr) {
+          const float lse = (l_row > 0.f) ? (m_used * 0.6931471805599453f + logf(l_row)) : 0.f;
+          p.lse[(static_cast<size_t>(n) * p.H + h) * p.S + q_row] = lse;
+        }
+        ATTN_TRACE_H(6);
       }
     }
   }
@@ -483,6 +679,12 @@ using namespace ggpt;
 
 extern "C" {
 
+#ifdef GGPT_ATTN_TRACE
+int ggpt_debug_attn_trace(long long* out, int n) {
+  return cudaMemcpyFromSymbol(out, ggpt::g_attn_trace, sizeof(long long) * n) == cudaSuccess ? 0 : -2;
+}
+#endif
+
 int ggpt_attn_mask_words(int S) { return ((S + 127) / 128) * 4 + 4; }
 
 int ggpt_attn_max_tiles(int S) { return (S + 63) / 64; }
@@ -529,7 +731,7 @@ int ggpt_attn_mask_build(const long long* attention_mask, int mask_dims, int N, 
 int ggpt_attn_fwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int v_col0, const uint32_t* mask_bits,
                   const int* tile_start, const int* n_tiles, const uint8_t* tile_cls, const uint8_t* iso_flags,
                   const int* iso_list, const int* iso_count, int run_general, float dropout_p, unsigned long long seed,
-                  void* out, long long ldo, float* lse, int N, int S, int H, void* stream) {
+                  void* out, void* out_lo, long long ldo, float* lse, int N, int S, int H, void* stream) {
   GGPT_REQUIRE(qkv && mask_bits && tile_start && n_tiles && tile_cls && out, "attn_fwd: null pointer");
   GGPT_REQUIRE(N > 0 && S > 0 && H > 0, "attn_fwd: empty problem");
   GGPT_REQUIRE(ld_qkv % 8 == 0 && ldo % 8 == 0 && q_col0 % 8 == 0 && k_col0 % 8 == 0 && v_col0 % 8 == 0,
@@ -542,7 +744,7 @@ int ggpt_attn_fwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int
   p.mask_words = ggpt_attn_mask_words(S);
   p.mask_bits = mask_bits; p.tile_start = tile_start; p.n_tiles = n_tiles; p.tile_cls = tile_cls;
   p.iso_flags = iso_flags;
-  p.out = static_cast<__nv_bfloat16*>(out); p.ldo = ldo; p.lse = lse;
+  p.out = static_cast<__nv_bfloat16*>(out); p.out_lo = static_cast<__nv_bfloat16*>(out_lo); p.ldo = ldo; p.lse = lse;
   p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
   GGPT_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "attn_fwd: dropout_p must be in [0,1)");
@@ -560,7 +762,11 @@ int ggpt_attn_fwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int
   }
   GGPT_REQUIRE(run_general || iso_flags, "attn_fwd: run_general == 0 needs the isolated-tile work list");
   if (run_general) {
-    dim3 grid(p.max_tiles, H, N);
+    // heads per CTA: 3 when that divides H (12 heads -> 4 groups), else 4 / 2 / 1
+    p.heads_per_cta = (H % 3 == 0) ? 3 : (H % 4 == 0) ? 4 : (H % 2 == 0) ? 2 : 1;
+    static const char* hpc_env = getenv("GGPT_ATTN_HEADS_PER_CTA");
+    if (hpc_env != nullptr && atoi(hpc_env) > 0) p.heads_per_cta = atoi(hpc_env);
+    dim3 grid(p.max_tiles, (H + p.heads_per_cta - 1) / p.heads_per_cta, N);
     if (p.drop.thresh != 0u) attn_fwd_kernel<true><<<grid, kAttThreads, kAttSmem, static_cast<cudaStream_t>(stream)>>>(tm, p);
     else attn_fwd_kernel<false><<<grid, kAttThreads, kAttSmem, static_cast<cudaStream_t>(stream)>>>(tm, p);
     if (int rc = check_launch("attn_fwd_kernel")) return rc;

@@ -82,6 +82,27 @@ int make_tmap_3d_bf16(CUtensorMap* map, const void* base, uint64_t d2, uint64_t 
   return 0;
 }
 
+int make_tmap_3d_f32(CUtensorMap* map, const void* base, uint64_t d2, uint64_t rows, uint64_t cols, uint64_t ld2,
+                     uint64_t ld, uint32_t box_rows, uint32_t box_cols) {
+  const CUtensorMapSwizzle sw = (box_cols * 4 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B
+                              : (box_cols * 4 == 64) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -3;
+  cuuint64_t gdim[3] = {cols, rows, d2};
+  cuuint64_t gstr[2] = {ld * 4, ld2 * 4};
+  cuuint32_t box[3] = {box_cols, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(3d f32 %llu x %llu x %llu) failed: CUresult %d", (unsigned long long)d2,
+              (unsigned long long)rows, (unsigned long long)cols, (int)r);
+    return -3;
+  }
+  return 0;
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {

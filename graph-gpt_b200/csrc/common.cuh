@@ -31,6 +31,11 @@ int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_
 int make_tmap_3d_bf16(CUtensorMap* map, const void* base, uint64_t d2, uint64_t rows, uint64_t cols,
                       uint64_t ld2, uint64_t ld, uint32_t box_rows, uint32_t box_cols);
 
+// fp32 [d2, rows, cols] view, box = 1 x box_rows x box_cols, swizzle = the box row size (128 B / 64 B, else none): TMA
+// reduce-add target.
+int make_tmap_3d_f32(CUtensorMap* map, const void* base, uint64_t d2, uint64_t rows, uint64_t cols,
+                     uint64_t ld2, uint64_t ld, uint32_t box_rows, uint32_t box_cols);
+
 int num_sms();
 
 #ifdef __CUDACC__
@@ -123,6 +128,14 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(m)),
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+// TMA reduction shared -> global (element-wise fp32 add into the tensor, performed at L2): same completion mechanism as
+// the TMA store.  Out-of-range rows / columns of the box are clipped.
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -269,6 +282,41 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 
+// registers -> TMEM, same 32 lanes x 32 columns shape (used to rescale an accumulator in place)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+// 8-column variants (32 lanes x 8 columns): for rarely taken paths that must not cost 32 live registers
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // ---- UMMA descriptors -------------------------------------------------------------------------
 // 64-bit shared-memory matrix descriptor, 128-byte swizzle (layout_type 2), descriptor version 1.
 //   [0,14)  start address >> 4        [16,30) leading byte offset >> 4
@@ -367,6 +415,21 @@ __device__ __forceinline__ void stage_flush_rows(uint8_t* stg, int lane, __nv_bf
           *reinterpret_cast<const uint4*>(stg + rr * 128 + ((rd_j ^ (rr & 7)) << 4));
   }
   __syncwarp();
+}
+
+// Same, for a 32-row block filled by TWO warps (each wrote half of every row's chunks): this warp flushes the 16 rows
+// [row_first, row_first + 16) of the block; dst_row0 is the global address of row `row_first`.
+__device__ __forceinline__ void stage_flush_rows16(uint8_t* stg_block, int lane, int row_first, __nv_bfloat16* dst_row0,
+                                                   long long ld, int rows_valid) {
+  const int rd_row = lane >> 3, rd_j = lane & 7;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int k = it * 4 + rd_row;
+    const int rr = row_first + k;
+    if (k < rows_valid)
+      *reinterpret_cast<uint4*>(dst_row0 + static_cast<long long>(k) * ld + rd_j * 8) =
+          *reinterpret_cast<const uint4*>(stg_block + rr * 128 + ((rd_j ^ (rr & 7)) << 4));
+  }
 }
 
 // Counter-based dropout mask for attention probabilities: keep(n,h,q,k) is a pure function of (seed, n, h, q, k) and of

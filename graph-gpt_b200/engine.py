@@ -327,7 +327,7 @@ class HotPath:
             # DropPath draws an independent per-sample mask for each of the two residual branches (utils_graphgpt.py:156,166)
             rs1, rs2 = (None, None) if droppath_scales is None else droppath_scales[i]
             qkv = ops.gemm_qkv_rope(h1, self._wqkv(i), pos, cos, sin, 2 * d)
-            a, lse = ops.attn_fwd(qkv, mask, H, want_lse=keep, dropout_p=attn_dropout, seed=drop_seed + i)
+            a, lse, a_lo = ops.attn_fwd(qkv, mask, H, want_lse=keep, want_lo=True, dropout_p=attn_dropout, seed=drop_seed + i)
             y1 = ops.gemm(a, fp.wb(p + "self_attn.o_proj.weight"))
             lam1 = fp.w(p + "lambda_1") if self.layer_scale else None
             x2, h2, rstd2 = ops.add_rmsnorm_fwd(x, y1, fp.w(p + "post_attention_layernorm.weight"), self.eps,
@@ -341,7 +341,7 @@ class HotPath:
             x3, h_next, rstd_next = ops.add_rmsnorm_fwd(x2, y2, next_w, self.eps, colscale=lam2, rowscale=rs2,
                                                         want_rstd=keep)
             if keep:
-                stash["layers"].append(dict(x=x, rstd1=rstd1, h1=h1, qkv=qkv, a=a, lse=lse, x2=x2, rstd2=rstd2, h2=h2,
+                stash["layers"].append(dict(x=x, rstd1=rstd1, h1=h1, qkv=qkv, a=a, a_lo=a_lo, lse=lse, x2=x2, rstd2=rstd2, h2=h2,
                                             gu=gu, act=act, x3=x3 if self.layer_scale else None, rs1=rs1, rs2=rs2))
             x, h1, rstd1 = x3, h_next, rstd_next
         hf, rstdf = h1, rstd1
@@ -437,7 +437,7 @@ class HotPath:
             da = ops.gemm(dyb, fp.wb(p + "self_attn.o_proj.weight"), b_mn_major=True)
             ops.gemm(dyb, st["a"], out=fp.g(p + "self_attn.o_proj.weight"), **wgrad)
             dqkv = ops.attn_bwd(da, st["qkv"], st["a"], st["lse"], stash["mask"], H, stash["pos"], stash["cos"],
-                                stash["sin"], dropout_p=stash["attn_dropout"], seed=stash["drop_seed"] + i)
+                                stash["sin"], out_lo=st["a_lo"], dropout_p=stash["attn_dropout"], seed=stash["drop_seed"] + i)
             ops.gemm(dqkv, st["h1"], out=self._gqkv(i), **wgrad)
             dh1 = ops.gemm(dqkv, self._wqkv(i), b_mn_major=True)
             dx, dxb = ops.rmsnorm_bwd(dh1, st["x"], st["rstd1"], fp.w(p + "input_layernorm.weight"), dx2,

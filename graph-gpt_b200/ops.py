@@ -178,8 +178,10 @@ def attn_mask_build(attention_mask, N, S, causal, device):
     return AttnMask(bits, tile_start, n_tiles, cls, iso_flags, iso_list, iso_count, N, S)
 
 
-def attn_fwd(qkv, mask: AttnMask, H, *, want_lse=True, dropout_p=0.0, seed=0):
-    """qkv bf16 [N*S, 3*H*64] (q | k | v).  Returns (out bf16 [N*S, H*64], lse f32 [N,H,S] or None)."""
+def attn_fwd(qkv, mask: AttnMask, H, *, want_lse=True, want_lo=False, dropout_p=0.0, seed=0):
+    """qkv bf16 [N*S, 3*H*64] (q | k | v).  Returns (out bf16 [N*S, H*64], lse f32 [N,H,S] or None) and, with want_lo, a
+    third element: the bf16 rounding residual of `out` that attn_bwd needs on the general (tile-loop) path — None when
+    every tile is isolated (packed batches) and the diagonal kernels do all the work, or when want_lse is off (inference)."""
     _check(qkv, BF16, "attn_fwd qkv", 2)
     N, S = mask.N, mask.S
     d = H * 64
@@ -187,27 +189,50 @@ def attn_fwd(qkv, mask: AttnMask, H, *, want_lse=True, dropout_p=0.0, seed=0):
         raise RuntimeError(f"attn_fwd: qkv shape {tuple(qkv.shape)} does not match N={N} S={S} H={H}")
     out = torch.empty((N * S, d), device=qkv.device, dtype=BF16)
     lse = torch.empty((N, H, S), device=qkv.device, dtype=F32) if want_lse else None
+    iso = mask._iso_args()
+    out_lo = torch.empty((N * S, d), device=qkv.device, dtype=BF16) if (want_lo and want_lse and iso[3]) else None
     lib.ggpt_attn_fwd(qkv.data_ptr(), qkv.stride(0), 0, d, 2 * d, mask.bits.data_ptr(), mask.tile_start.data_ptr(),
-                      mask.n_tiles.data_ptr(), mask.cls.data_ptr(), *mask._iso_args(), float(dropout_p), int(seed),
-                      out.data_ptr(), out.stride(0), _ptr(lse), N, S, H, _stream())
+                      mask.n_tiles.data_ptr(), mask.cls.data_ptr(), *iso, float(dropout_p), int(seed),
+                      out.data_ptr(), _ptr(out_lo), out.stride(0), _ptr(lse), N, S, H, _stream())
+    if want_lo:
+        return out, lse, out_lo
     return out, lse
 
 
-def attn_bwd(dout, qkv, out, lse, mask: AttnMask, H, pos, cos_tab, sin_tab, *, dropout_p=0.0, seed=0):
-    """Returns dqkv bf16 [N*S, 3*H*64] (gradient of the fused projection output, RoPE already undone)."""
+_DQ_ACC = {}
+
+
+def _dq_accumulator(device, numel):
+    """fp32 scratch of the general attention backward: zero on entry, zeroed again by the kernel that consumes it, so one
+    buffer per (device, size) is allocated and zero-filled exactly once."""
+    key = (device.index, numel)
+    buf = _DQ_ACC.get(key)
+    if buf is None:
+        buf = _DQ_ACC[key] = torch.zeros((numel,), device=device, dtype=F32)
+    return buf
+
+
+def attn_bwd(dout, qkv, out, lse, mask: AttnMask, H, pos, cos_tab, sin_tab, *, out_lo=None, dropout_p=0.0, seed=0):
+    """Returns dqkv bf16 [N*S, 3*H*64] (gradient of the fused projection output, RoPE already undone).  out_lo: third
+    result of attn_fwd(want_lo=True) (without it D = rowsum(dO * O) carries the bf16 rounding error of O)."""
     _check(dout, BF16, "attn_bwd dout", 2)
     _check(qkv, BF16, "attn_bwd qkv", 2)
     _check(out, BF16, "attn_bwd out", 2)
+    if out_lo is not None:
+        _check(out_lo, BF16, "attn_bwd out_lo", 2)
+        if out_lo.stride(0) != out.stride(0):
+            raise RuntimeError("attn_bwd: out_lo must have the layout of out")
     N, S = mask.N, mask.S
     d = H * 64
     dqkv = torch.empty_like(qkv)
     dsum = torch.empty((N, H, S), device=qkv.device, dtype=F32)
-    lib.ggpt_attn_bwd(qkv.data_ptr(), qkv.stride(0), 0, d, 2 * d, out.data_ptr(), out.stride(0), dout.data_ptr(),
+    iso = mask._iso_args()
+    dq_acc = _dq_accumulator(qkv.device, N * S * d) if iso[3] else None
+    lib.ggpt_attn_bwd(qkv.data_ptr(), qkv.stride(0), 0, d, 2 * d, out.data_ptr(), _ptr(out_lo), out.stride(0), dout.data_ptr(),
                       dout.stride(0), lse.data_ptr(), mask.bits.data_ptr(), mask.tile_start.data_ptr(),
-                      mask.n_tiles.data_ptr(), mask.cls.data_ptr(), *mask._iso_args(), float(dropout_p), int(seed),
-                      pos.data_ptr(),
-                      cos_tab.data_ptr(), sin_tab.data_ptr(), dsum.data_ptr(), dqkv.data_ptr(), dqkv.stride(0), N, S, H,
-                      _stream())
+                      mask.n_tiles.data_ptr(), mask.cls.data_ptr(), *iso, float(dropout_p), int(seed),
+                      pos.data_ptr(), cos_tab.data_ptr(), sin_tab.data_ptr(), dsum.data_ptr(), _ptr(dq_acc), dqkv.data_ptr(),
+                      dqkv.stride(0), N, S, H, _stream())
     return dqkv
 
 

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GGPT_ABI_VERSION 1
+#define GGPT_ABI_VERSION 2
 
 const char* ggpt_last_error(void);
 int ggpt_abi_version(void);
@@ -100,22 +100,27 @@ int ggpt_attn_mask_build(const long long* attention_mask, int mask_dims, int N, 
                          int* iso_count, void* stream);
 
 /* out[N*S, H*64] = dropout(softmax(q k^T / 8 + mask)) v per head; lse[N,H,S] (may be NULL) = log-sum-exp of the scaled
- * scores, kept for the backward pass.  dropout_p > 0 (training, config.attention_dropout) drops attention
+ * scores, kept for the backward pass.  out_lo (may be NULL; same shape / ld as out) receives the bf16 rounding residual
+ * bf16(O - bf16(O)) of the rows computed by the general tile-loop kernel (zeros for isolated tiles): ggpt_attn_bwd uses
+ * it to form D = dO.(O + O_lo) to fp32 accuracy.  dropout_p > 0 (training, config.attention_dropout) drops attention
  * probabilities with a counter-based mask that is a pure function of (seed, n, h, q, k); pass the same (dropout_p, seed)
  * to ggpt_attn_bwd.   ref: HF:199-221 (eager_attention_forward: fp32 softmax, dropout on the weights). */
 int ggpt_attn_fwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int v_col0, const uint32_t* mask_bits,
                   const int* tile_start, const int* n_tiles, const uint8_t* tile_cls, const uint8_t* iso_flags,
                   const int* iso_list, const int* iso_count, int run_general, float dropout_p, unsigned long long seed,
-                  void* out, long long ldo, float* lse, int N, int S, int H, void* stream);
+                  void* out, void* out_lo, long long ldo, float* lse, int N, int S, int H, void* stream);
 
 /* dqkv[N*S, ld_dqkv] (bf16) = gradient of the fused q|k|v projection output given dout = dL/d(attention output).
- * Recomputes P from lse; two deterministic tcgen05 passes (dK,dV then dQ); dQ/dK are un-rotated (inverse RoPE)
- * with the same pos / cos / sin tables as ggpt_gemm_bf16_qkv_rope.  dsum_scratch: fp32 [N,H,S].
- * ref: autograd of HF:199-221 and HF:146-168. */
-int ggpt_attn_bwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int v_col0, const void* out, long long ldo,
-                  const void* dout, long long lddo, const float* lse, const uint32_t* mask_bits, const int* tile_start,
-                  const int* n_tiles, const uint8_t* tile_cls, const uint8_t* iso_flags, const int* iso_list,
-                  const int* iso_count, int run_general, float dropout_p, unsigned long long seed, const int* pos, const float* cos_tab, const float* sin_tab, float* dsum_scratch, void* dqkv,
+ * Recomputes P from lse in ONE tcgen05 pass over the score tiles (per key tile: dK, dV in TMEM; the dQ contributions of
+ * the key tiles are summed with TMA reductions into dq_acc and converted by a finishing kernel); dQ/dK are un-rotated
+ * (inverse RoPE) with the same pos / cos / sin tables as ggpt_gemm_bf16_qkv_rope.  out_lo: see ggpt_attn_fwd (may be
+ * NULL).  Scratch: dsum_scratch fp32 [N,H,S]; dq_acc fp32 [N*S, H*64], ZERO on entry and zero again on return (needed
+ * only when run_general != 0).  ref: autograd of HF:199-221 and HF:146-168. */
+int ggpt_attn_bwd(const void* qkv, long long ld_qkv, int q_col0, int k_col0, int v_col0, const void* out, const void* out_lo,
+                  long long ldo, const void* dout, long long lddo, const float* lse, const uint32_t* mask_bits,
+                  const int* tile_start, const int* n_tiles, const uint8_t* tile_cls, const uint8_t* iso_flags,
+                  const int* iso_list, const int* iso_count, int run_general, float dropout_p, unsigned long long seed,
+                  const int* pos, const float* cos_tab, const float* sin_tab, float* dsum_scratch, float* dq_acc, void* dqkv,
                   long long ld_dqkv, int N, int S, int H, void* stream);
 
 /* ---------------------------------------------------------------------------------------------

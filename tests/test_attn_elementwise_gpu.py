@@ -335,8 +335,8 @@ def test_attn_bwd(N, S, H, kind, causal, rope):
     ref = torch.stack([unrot(gr[:, 0]), unrot(gr[:, 1]), gr[:, 2]], 1).reshape(N * S, 3 * d)
 
     mask = ops.attn_mask_build(am, N, S, causal, dev)
-    out, lse = ops.attn_fwd(qkv_b, mask, H)
-    dqkv = ops.attn_bwd(dout, qkv_b, out, lse, mask, H, pos, cos_tab, sin_tab)
+    out, lse, out_lo = ops.attn_fwd(qkv_b, mask, H, want_lo=True)
+    dqkv = ops.attn_bwd(dout, qkv_b, out, lse, mask, H, pos, cos_tab, sin_tab, out_lo=out_lo)
     torch.cuda.synchronize()
     for name, sl in (("dq", slice(0, d)), ("dk", slice(d, 2 * d)), ("dv", slice(2 * d, 3 * d))):
         a, b = dqkv[:, sl].float(), ref[:, sl]
@@ -406,8 +406,8 @@ def test_attn_diag_path_matches_general_path(S, H, monkeypatch):
         assert mask.use_diag == (mode == "diag")
         if mode == "diag":
             assert int(mask.iso_count[0]) == int(mask.n_tiles.sum()) == int(mask.iso_count[1])      # every tile of a packed batch is isolated
-        out, lse = ops.attn_fwd(qkv, mask, H)
-        dqkv = ops.attn_bwd(dout, qkv, out, lse, mask, H, pos, cos_tab, sin_tab)
+        out, lse, out_lo = ops.attn_fwd(qkv, mask, H, want_lo=True)
+        dqkv = ops.attn_bwd(dout, qkv, out, lse, mask, H, pos, cos_tab, sin_tab, out_lo=out_lo)
         torch.cuda.synchronize()
         res[mode] = (out.float(), lse, dqkv.float())
     for a, b_, name, tol in zip(res["diag"], res["general"], ("out", "lse", "dqkv"), (4e-3, 1e-5, 8e-3)):
@@ -456,11 +456,11 @@ def test_attn_dropout_consistent_forward_backward(kind, S):
     pr = torch.softmax(s_, -1) * keep / (1.0 - p_drop)
     ref_o = (pr @ v).transpose(1, 2).reshape(N * S, d)
     ref_o.backward(dout.float())
-    out, lse = ops.attn_fwd(qkv_b, mask, H, dropout_p=p_drop, seed=seed)
+    out, lse, out_lo = ops.attn_fwd(qkv_b, mask, H, want_lo=True, dropout_p=p_drop, seed=seed)
     pos = torch.zeros((N * S,), dtype=torch.int32, device=dev)
     cos_tab = torch.ones((1, 32), device=dev)
     sin_tab = torch.zeros((1, 32), device=dev)
-    dqkv = ops.attn_bwd(dout, qkv_b, out, lse, mask, H, pos, cos_tab, sin_tab, dropout_p=p_drop, seed=seed)
+    dqkv = ops.attn_bwd(dout, qkv_b, out, lse, mask, H, pos, cos_tab, sin_tab, out_lo=out_lo, dropout_p=p_drop, seed=seed)
     torch.cuda.synchronize()
     assert (out.float() - ref_o).abs().max().item() <= 1.5e-2 * ref_o.abs().max().item()
     for name, sl in (("dq", slice(0, d)), ("dk", slice(d, 2 * d)), ("dv", slice(2 * d, 3 * d))):

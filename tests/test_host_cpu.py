@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for name in protos:
         assert hasattr(dll, name), f"{name} declared in include/ggpt_b200.h but not exported"
     dll.ggpt_abi_version.restype = ctypes.c_int
-    assert dll.ggpt_abi_version() == 1
+    assert dll.ggpt_abi_version() == 2
     dll.ggpt_attn_mask_words.restype = ctypes.c_int
     assert dll.ggpt_attn_mask_words(1024) == 36 and dll.ggpt_attn_mask_words(40) == 8
     dll.ggpt_attn_max_tiles.restype = ctypes.c_int

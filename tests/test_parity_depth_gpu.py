@@ -54,29 +54,34 @@ def _cfg(L, d, V, F_, S, causal=False, **kw):
 
 def _tiled_attention(q, k, v, keep, tile_start, n_tiles, r):
     """The attention kernels' own schedule, in fp32 torch: online softmax over the key tiles of the mask plan with the
-    un-normalised numerators rounded to bf16 RELATIVE TO THE RUNNING MAXIMUM of that moment (that is what reaches the PV
-    tensor-core product), fp32 running sum of the unrounded numerators, fp32 rescaled accumulator.  q,k,v fp32 [N,H,S,64]
-    holding bf16 values, keep bool [N or 1,1,S,S]."""
+    un-normalised numerators rounded to bf16 RELATIVE TO THE REFERENCE MAXIMUM of that moment (that is what reaches the PV
+    tensor-core product), fp32 running sum of the unrounded numerators, fp32 accumulator.  The reference maximum is the
+    forward kernel's lazily advanced one (attn_fwd_sm100.cu): set by the first tile with a visible key, afterwards moved —
+    with a rescale of the accumulator and the sum — only when a tile's maximum exceeds it by more than 8 in the log2
+    domain.  q,k,v fp32 [N,H,S,64] holding bf16 values, keep bool [N or 1,1,S,S]."""
     N, H, S, _ = q.shape
     out = torch.zeros_like(q)
     ninf = float("-inf")
+    thr = 8.0 * 0.6931471805599453
     for n in range(N):
         ts, nt = tile_start[n].tolist(), int(n_tiles[n])
         kp = keep[n if keep.shape[0] > 1 else 0, 0]
-        m = torch.full((H, S), ninf, device=q.device)
+        mu = torch.full((H, S), ninf, device=q.device)
         l = torch.zeros((H, S), device=q.device)
         o = torch.zeros((H, S, 64), device=q.device)
         for kt in range(nt):
             k0, k1 = ts[kt], ts[kt + 1]
             s_ = (q[n] @ k[n, :, k0:k1].transpose(1, 2)) * 0.125
             s_ = s_.masked_fill(~kp[None, :, k0:k1], ninf)
-            m_new = torch.maximum(m, s_.max(-1).values)
-            m_use = torch.where(m_new == ninf, torch.zeros_like(m_new), m_new)
-            alpha = torch.where(m == ninf, torch.zeros_like(m), torch.exp(m - m_use))
+            m_tile = s_.max(-1).values
+            first = (mu == ninf) & (m_tile > ninf)
+            move = (mu > ninf) & (m_tile > mu + thr)
+            alpha = torch.where(move, torch.exp(mu - m_tile), torch.ones_like(mu))
+            mu = torch.where(first | move, m_tile, mu)
+            m_use = torch.where(mu == ninf, torch.zeros_like(mu), mu)
             e = torch.exp(s_ - m_use[..., None])
             l = l * alpha + e.sum(-1)
             o = o * alpha[..., None] + r(e) @ v[n, :, k0:k1]
-            m = m_new
         out[n] = torch.where(l[..., None] > 0, o / l.clamp_min(1e-30)[..., None], torch.zeros_like(o))
     return out.transpose(1, 2).contiguous()
 

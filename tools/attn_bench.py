@@ -47,12 +47,12 @@ def main():
         flops_f = 4.0 * ntok * vis * d
         for p_drop in (0.0, 0.1):
             def fwd():
-                return ops.attn_fwd(qkv, mask, H, dropout_p=p_drop, seed=7)
+                return ops.attn_fwd(qkv, mask, H, want_lo=True, dropout_p=p_drop, seed=7)
 
-            out, lse = fwd()
+            out, lse, out_lo = fwd()
 
             def bwd():
-                return ops.attn_bwd(dout, qkv, out, lse, mask, H, pos, cos, sin, dropout_p=p_drop, seed=7)
+                return ops.attn_bwd(dout, qkv, out, lse, mask, H, pos, cos, sin, out_lo=out_lo, dropout_p=p_drop, seed=7)
 
             bwd()
             torch.cuda.synchronize()

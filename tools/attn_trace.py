@@ -1,0 +1,49 @@
+#!/usr/bin/env python
+"""Per-phase timeline of the general attention forward kernel (one softmax warp of 64 CTAs), from clock64 stamps compiled
+in with -DGGPT_ATTN_TRACE:   python tools/attn_trace.py        (builds a scratch copy of the library under /tmp)
+slots: 0 loop top, 6 s_full seen, 1 scores in registers, 2 max + vote done, 3 exp done, 4 pv_done(it-1) seen, 5 P stored."""
+import ctypes
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+csrc = os.path.join(ROOT, "graph-gpt_b200", "csrc")
+so = "/tmp/libggpt_trace.so"
+srcs = [os.path.join(csrc, f) for f in sorted(os.listdir(csrc)) if f.endswith(".cu")]
+subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-DGGPT_ATTN_TRACE",
+                       "-I", os.path.join(ROOT, "include"), "-shared", "-o", so] + srcs + ["-lcudart"])
+import torch  # noqa: E402
+
+import graphgpt_b200.lib as L  # noqa: E402
+from graphgpt_b200 import ops  # noqa: E402
+
+L.LIB_PATH = so
+L.lib.load()
+N, S, H = 64, 1024, 12
+d = H * 64
+qkv = (torch.randn(N * S, 3 * d, device="cuda") * 0.7).to(torch.bfloat16)
+mask = ops.attn_mask_build(None, N, S, False, "cuda")
+for _ in range(3):
+    ops.attn_fwd(qkv, mask, H, want_lo=True)
+torch.cuda.synchronize()
+dll = ctypes.CDLL(so)
+buf = (ctypes.c_longlong * (64 * 16 * 8))()
+assert dll.ggpt_debug_attn_trace(buf, 64 * 16 * 8) == 0
+import numpy as np  # noqa: E402
+full = np.array(buf[:], dtype=np.int64).reshape(64, 16, 8)
+t = full[:, :8]
+hh = full[:, 8:11]          # per head (3 heads per CTA): 0 head start, 1 loop end, 2 last PV seen, 3 l exchanged, 4 staged, 5 pair barrier, 6 flushed
+print("per head (cycles): tile loop %.0f | wait last PV %.0f | l exchange %.0f | O ld + staging %.0f | pair barrier %.0f | flush %.0f | head period %.0f" % (
+    (hh[:, :, 1] - hh[:, :, 0]).mean(), (hh[:, :, 2] - hh[:, :, 1]).mean(), (hh[:, :, 3] - hh[:, :, 2]).mean(),
+    (hh[:, :, 4] - hh[:, :, 3]).mean(), (hh[:, :, 5] - hh[:, :, 4]).mean(), (hh[:, :, 6] - hh[:, :, 5]).mean(),
+    (hh[:, 1:, 0] - hh[:, :-1, 0]).mean()))
+names = {"wait s_full": (0, 6), "tmem ld": (6, 1), "max+vote": (1, 2), "exp": (2, 3), "wait pv_done": (3, 4), "store P+fence": (4, 5)}
+print("mean cycles per phase over 64 CTAs x tiles 1..7 (tile 0 separately)")
+for k, (a, b) in names.items():
+    dlt = t[:, :, b] - t[:, :, a]
+    print(f"  {k:16s} tile0 {dlt[:, 0].mean():8.0f}   tiles1-7 mean {dlt[:, 1:].mean():8.0f}  p90 {np.percentile(dlt[:, 1:], 90):8.0f}")
+per_tile = t[:, 1:, 0] - t[:, :-1, 0]
+print(f"  loop period      mean {per_tile.mean():8.0f}  p90 {np.percentile(per_tile, 90):8.0f}")
+print(f"  CTA span (tile loop only) mean {(t[:, 7, 5] - t[:, 0, 0]).mean():8.0f}")
