@@ -136,6 +136,9 @@ class GraphGPTEngine:
         self._wire = (torch.empty((n,), device=dev, dtype=grad_reduce_dtype)
                       if (self.world > 1 and grad_reduce_dtype not in (None, torch.float32)) else None)
         self.reducer = GradReducer(self.flat.flat_grad, process_group, grad_reduce_dtype, self._wire)
+        # 4-byte collective that aligns the ranks' compute streams at the start of backward (see backward())
+        self._align = torch.zeros((1,), device=dev, dtype=torch.float32) if self.world > 1 else None
+        self.align_ranks = True
         if self.world > 1:
             self._broadcast_params()
 
@@ -175,6 +178,14 @@ class GraphGPTEngine:
             return
         self.reducer = GradReducer(self.flat.flat_grad, self.group, self.grad_reduce_dtype, self._wire)
         if self.world > 1 and self.overlap_comm:
+            if self.align_ranks:
+                # The ranks reach backward up to ~1 ms apart (different batches => different head sizes, host jitter).  An
+                # all-reduce whose peer is late SPINS on its 16-24 SMs until the peer arrives, and the persistent GEMMs
+                # running beside it lose those SMs (kernel timeline, tools/dp_trace.py: the first two gradient all-reduces
+                # took 1.07 / 0.77 ms instead of 0.09 ms and the backward GEMMs 1.25 ms longer).  A 4-byte all-reduce —
+                # one NCCL channel, one SM — on which the compute stream waits absorbs the skew here instead; the step
+                # time is the slowest rank's either way, and every later collective finds its peers ready.
+                dist.all_reduce(self._align, group=self.group, async_op=True).wait()
             hot.grad_ready_hook = lambda first, last: self.reducer.reduce_span(*self.flat.span(first, last))
         else:
             hot.grad_ready_hook = None
