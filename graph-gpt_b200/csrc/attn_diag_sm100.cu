@@ -287,7 +287,23 @@ attn_diag_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const DiagParams
 // =====================================================================================================
 // backward: dQ, dK, dV of one isolated tile in a single pass
 // =====================================================================================================
-constexpr int kDBThreads = 320;                       // producer, MMA, 8 compute warps (two per TMEM lane quadrant)
+#ifdef GGPT_ATTN_TRACE      // profiling aid: clock64 stamps of compute warp 2 of 32 CTAs, 16 items each (tools/attn_trace.py diag)
+__device__ long long g_diag_trace[32 * 16 * 8];
+#define DIAG_TRACE(slot)                                                                                           \
+  do {                                                                                                             \
+    if (warp == 2 && lane == 0 && blockIdx.x < 32 && i >= 8 && i < 24)                                              \
+      g_diag_trace[(blockIdx.x * 16 + (i - 8)) * 8 + (slot)] = clock64();                                           \
+  } while (0)
+#define DIAG_TRACE_EPI(slot)                                                                                       \
+  do {                                                                                                             \
+    if (warp == 10 && lane == 0 && blockIdx.x < 32 && i >= 8 && i < 24)                                             \
+      g_diag_trace[(blockIdx.x * 16 + (i - 8)) * 8 + (slot)] = clock64();                                           \
+  } while (0)
+#else
+#define DIAG_TRACE(slot) do { } while (0)
+#define DIAG_TRACE_EPI(slot) do { } while (0)
+#endif
+constexpr int kDBThreads = 576;                       // producer, MMA, 8 softmax-gradient warps, 8 epilogue warps
 constexpr int kDBStageBytes = 65536;                  // Q | K | V | dO
 constexpr int kDBSmemP = 2 * kDBStageBytes;
 constexpr int kDBSmemDS = kDBSmemP + 32768;
@@ -361,10 +377,13 @@ attn_diag_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       constexpr uint32_t idesc_t = umma_idesc_bf16(128, 64, true, true);
       constexpr uint32_t idesc_q = umma_idesc_bf16(128, 64, false, true);
       const uint32_t aP = smem_u32(sP), aDS = smem_u32(sDS);
+      auto scores_ready = [&](int i) -> bool {
+        const int st = i & 1;
+        if (!mbar_try_wait(&full[st], (i >> 1) & 1)) return false;
+        return i < 2 || mbar_try_wait(&acc_empty[st], ((i >> 1) - 1) & 1);   // epilogue of item i-2 drained this slot
+      };
       auto issue_scores = [&](int i) {
         const int st = i & 1;
-        mbar_wait(&full[st], (i >> 1) & 1);
-        if (i >= 2) mbar_wait(&acc_empty[st], ((i >> 1) - 1) & 1);   // epilogue of item i-2 drained this slot
         tc_fence_after();
         const uint32_t aQ = smem_u32(smem + st * kDBStageBytes), aK = aQ + 16384, aV = aQ + 32768, aDO = aQ + 49152;
         const uint32_t d = tmem_base + st * 256;
@@ -377,9 +396,10 @@ attn_diag_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
                       kk != 0);
         tc_commit(&sdp_full[st]);
       };
-      issue_scores(0);
-      for (int i = 0; i < n_items; ++i) {
-        mbar_wait(pds_full, i & 1);
+      auto issue_grads = [&](int i) {
+#ifdef GGPT_ATTN_TRACE
+        if (blockIdx.x < 32 && i >= 8 && i < 24) g_diag_trace[(blockIdx.x * 16 + (i - 8)) * 8 + 5] = clock64();
+#endif
         tc_fence_after();
         const int st = i & 1;
         const uint32_t aQ = smem_u32(smem + st * kDBStageBytes), aK = aQ + 16384, aDO = aQ + 49152;
@@ -403,136 +423,45 @@ attn_diag_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         tc_commit(&acc_full[st]);
         tc_commit(pds_empty);
         tc_commit(&empty[st]);
-        // scores of the next item go behind the gradient MMAs: they need the TMEM slot that the epilogue of item
-        // i-1 (running on the compute warps right now, overlapped with the MMAs above) is draining
-        if (i + 1 < n_items) issue_scores(i + 1);
+      };
+      // Two independent streams of work for the tensor core: the scores of item a (need its stage loaded and the TMEM
+      // slot of item a-2 drained by the epilogue warps) and the gradient products of item b (need P / dS of item b).
+      // The thread polls both and issues whichever is ready: the gradient MMAs of item b must never sit behind a wait for
+      // the epilogue of item b-1 (they release the P / dS buffer the softmax-gradient warps are waiting for), nor the
+      // scores of item b+1 behind the softmax of item b.
+      int a = 0, b = 0;
+      uint32_t spins = 0;
+      while (b < n_items) {
+        bool progressed = false;
+        if (a < n_items && a <= b + 1 && scores_ready(a)) {
+          issue_scores(a);
+          ++a;
+          progressed = true;
+        }
+        if (b < a && mbar_try_wait(pds_full, b & 1)) {
+          issue_grads(b);
+          ++b;
+          progressed = true;
+        }
+        if (progressed) {
+          spins = 0;
+        } else if (++spins > (1u << 26)) {
+          printf("ggpt attn_diag_bwd: MMA issuer stuck block=%d a=%d b=%d\n", blockIdx.x, a, b);
+          __trap();
+        }
       }
     }
-  } else {
+  } else if (warp < 10) {
+    // ===================== softmax-gradient warps (2..9): two per TMEM lane quadrant, 64 key columns each ==============
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;          // which 64 key columns (softmax pass) / which outputs (epilogue)
+    const int half = (warp - 2) >> 2;
     const int r = quad * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
-    DiagItem prev{};
-    // RoPE table rows of the epilogue's tokens: the two warps of a lane quadrant need the same 32 cos rows and 32 sin rows,
-    // so warp `half` fetches table `half` for both with cp.async (no registers, issued BEFORE the softmax pass of the next
-    // item so the L2 latency is hidden) into a 4 KB swizzled buffer; a 64-thread named barrier publishes them.
-    uint8_t* gb_cos = smem + kDBSmemGather + (quad * 2) * 4096;
-    uint8_t* gb_sin = gb_cos + 4096;
-    auto pair_barrier = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory"); };
-    auto issue_gather = [&](int pos_row) {
-      pair_barrier();                                 // the partner has finished reading the previous tables
-      const float* tab = half ? p.sin_tab : p.cos_tab;
-      uint8_t* dst = half ? gb_sin : gb_cos;
-      const int rd_row = lane >> 3, rd_j = lane & 7;
-#pragma unroll
-      for (int it8 = 0; it8 < 8; ++it8) {
-        const int rr = it8 * 4 + rd_row;
-        const int src = __shfl_sync(0xffffffffu, pos_row, rr);
-        const float* g = tab + static_cast<long long>(src) * 32 + rd_j * 4;
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + rr * 128 + ((rd_j ^ (rr & 7)) << 4))),
-                     "l"(g)
-                     : "memory");
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    auto epilogue = [&](int i, const DiagItem& it) {
-      const int st = i & 1;
-      const uint32_t d = tmem_base + st * 256 + lane_addr;
-      const bool ok = r < it.len;
-      const long long grow = static_cast<long long>(it.n) * p.S + it.r0 + r;
-      // cos / sin rows of this thread's token stay in the swizzled smem tables and are read 8 columns at a time inside
-      // store_pair: holding all 64 values in registers next to the accumulator rows pushed the kernel over the 168
-      // registers a 10-warp CTA can have (3 warps on one scheduler: 16384 / 96), and the spill stores of the PREFETCHED
-      // per-row inputs then waited for their global loads — a third of all warp stalls (ncu, profiles/r2n_*)
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      pair_barrier();
-      mbar_wait(&acc_full[st], (i >> 1) & 1);
-      tc_fence_after();
-      // (staging these stores through smem for full-line writes, as the forward kernel does, was measured slower here:
-      //  the extra live state spills — 6.9 -> 8.0 ms per step)
-      auto store_pair = [&](uint32_t (&x1)[32], uint32_t (&x2)[32], bool rot, int col0) {
-        if (!ok) return;
-        __nv_bfloat16* orow = p.dqkv + grow * p.ld_dqkv + col0;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float o1[8], o2[8];
-          if (rot) {
-            float cs[8], sn[8];
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              const int ch = ((2 * g + q) ^ (lane & 7)) << 4;
-              const float4 a = *reinterpret_cast<const float4*>(gb_cos + lane * 128 + ch);
-              const float4 b = *reinterpret_cast<const float4*>(gb_sin + lane * 128 + ch);
-              cs[q * 4 + 0] = a.x; cs[q * 4 + 1] = a.y; cs[q * 4 + 2] = a.z; cs[q * 4 + 3] = a.w;
-              sn[q * 4 + 0] = b.x; sn[q * 4 + 1] = b.y; sn[q * 4 + 2] = b.z; sn[q * 4 + 3] = b.w;
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float d1 = __uint_as_float(x1[g * 8 + j]), d2 = __uint_as_float(x2[g * 8 + j]);
-              o1[j] = d1 * cs[j] + d2 * sn[j];
-              o2[j] = d2 * cs[j] - d1 * sn[j];
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              o1[j] = __uint_as_float(x1[g * 8 + j]);
-              o2[j] = __uint_as_float(x2[g * 8 + j]);
-            }
-          }
-          uint4 v1, v2;
-          v1.x = pack_bf16(o1[0], o1[1]); v1.y = pack_bf16(o1[2], o1[3]);
-          v1.z = pack_bf16(o1[4], o1[5]); v1.w = pack_bf16(o1[6], o1[7]);
-          v2.x = pack_bf16(o2[0], o2[1]); v2.y = pack_bf16(o2[2], o2[3]);
-          v2.z = pack_bf16(o2[4], o2[5]); v2.w = pack_bf16(o2[6], o2[7]);
-          *reinterpret_cast<uint4*>(orow + g * 8) = v1;
-          *reinterpret_cast<uint4*>(orow + 32 + g * 8) = v2;
-        }
-      };
-      uint32_t x1[32], x2[32];
-      if (half == 0) {
-        tmem_ld32(d, x1);            // dV
-        tmem_ld32(d + 32, x2);
-        tmem_ld_wait();
-        if (p.drop.thresh != 0u) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            x1[j] = __float_as_uint(__uint_as_float(x1[j]) * p.drop.inv_keep);
-            x2[j] = __float_as_uint(__uint_as_float(x2[j]) * p.drop.inv_keep);
-          }
-        }
-        store_pair(x1, x2, false, p.v_col0 + it.h * 64);
-        tmem_ld32(d + 64, x1);       // dK
-        tmem_ld32(d + 96, x2);
-        tmem_ld_wait();
-        store_pair(x1, x2, true, p.k_col0 + it.h * 64);
-      } else {
-        const float* e = epsx + (i & 1) * 256;
-        const float ce = (e[r] + e[128 + r]) * p.scale;
-        uint32_t y[32];
-        tmem_ld32(d + 128, x1);      // dQ
-        tmem_ld32(d + 160, x2);
-        tmem_ld32(d + 192, y);       // PK
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) x1[j] = __float_as_uint(__uint_as_float(x1[j]) - ce * __uint_as_float(y[j]));
-        tmem_ld32(d + 224, y);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) x2[j] = __float_as_uint(__uint_as_float(x2[j]) - ce * __uint_as_float(y[j]));
-        store_pair(x1, x2, true, p.q_col0 + it.h * 64);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[st]);
-    };
-
-    // Per-row inputs (the 3 mask words covering this warp's 64 key columns, lse, D, position) of item i+1 and the
-    // descriptor of item i+2 are requested while item i is processed: no global-load latency on the critical path.
+    // Per-row inputs (the 3 mask words covering this warp's 64 key columns, lse, D) of item i+1 and the descriptor of item
+    // i+1 are requested while item i is processed: no global-load latency on the critical path.
     struct RowPre {
-      uint32_t w[3];
+      uint32_t w[5];
       float lse, dsum;
-      int pos;
     };
     auto load_item = [&](int i) -> DiagItem {
       return (i < n_items) ? diag_item(p, blockIdx.x + i * gridDim.x) : DiagItem{0, 0, 0, 0, 0};
@@ -540,70 +469,84 @@ attn_diag_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     auto load_row = [&](const DiagItem& it, RowPre& o) {
       const int rr = min(r, max(it.len - 1, 0));
       const size_t row = static_cast<size_t>(it.n) * p.S + it.r0 + rr;
-      const uint32_t* mrow = p.mask_bits + row * p.mask_words + (it.r0 >> 5) + half * 2;
-      o.w[0] = __ldg(mrow);
-      o.w[1] = __ldg(mrow + 1);
-      o.w[2] = __ldg(mrow + 2);
+      const uint32_t* mrow = p.mask_bits + row * p.mask_words + (it.r0 >> 5);
+#pragma unroll
+      for (int k = 0; k < 5; ++k) o.w[k] = __ldg(mrow + k);
       const size_t li = (static_cast<size_t>(it.n) * p.H + it.h) * p.S + it.r0 + rr;
       o.lse = __ldg(p.lse_in + li);
       o.dsum = __ldg(p.dsum + li);
-      o.pos = __ldg(p.pos + row);
     };
     DiagItem it = load_item(0), it_next = load_item(1);
     RowPre rp;
     load_row(it, rp);
-    int pos_prev = 0;
     for (int i = 0; i < n_items; ++i) {
+      DIAG_TRACE(0);
       const DiagItem it_next2 = load_item(i + 2);
       RowPre rp_next;
       load_row(it_next, rp_next);
-      if (i > 0) issue_gather(pos_prev);     // tables for epilogue(i-1), hidden behind the softmax pass below
       const bool row_ok = r < it.len;
       const float lse2 = row_ok ? rp.lse * 1.4426950408889634f : 0.f;
       const float dsum = row_ok ? rp.dsum : 0.f;
-      // mw[cc] = 32 mask bits of this row for key columns (half*2 + cc)*32 ..
-      uint32_t mw[2] = {0xffffffffu, 0xffffffffu};
+      // The two warps of a quadrant take ALTERNATE 16-column pieces of the 128 keys (warp `half`: pieces half, half + 2,
+      // half + 4, half + 6).  Splitting the keys into a left and a right half left all the work of a block-diagonal mask
+      // with one of the two warps (clock64 trace: the busy warps needed 8k cycles per item, their partners 3.7k idling at
+      // the barrier).  mw16[q] = the 16 mask bits of this row for piece 2 q + half.
+      uint32_t mw16[4] = {0xffffu, 0xffffu, 0xffffu, 0xffffu};
       if (!row_ok) {
-        mw[0] = mw[1] = 0u;
+        mw16[0] = mw16[1] = mw16[2] = mw16[3] = 0u;
       } else if (it.cls == 2) {
         const int sh = it.r0 & 31;
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          const uint32_t v = __funnelshift_r(rp.w[cc], rp.w[cc + 1], sh);
-          const int nvalid = it.len - 32 * (half * 2 + cc);
-          mw[cc] = v & (nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u)));
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t v = __funnelshift_r(rp.w[q], rp.w[q + 1], sh);
+          const int nvalid = it.len - 32 * q;
+          const uint32_t m32 = v & (nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u)));
+          mw16[q] = (m32 >> (half * 16)) & 0xffffu;
+        }
+      } else if (it.len < 128) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int nvalid = it.len - 32 * q - 16 * half;
+          mw16[q] = nvalid >= 16 ? 0xffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u));
         }
       }
       const int st = i & 1;
       const uint32_t rowkey = drop_rowkey(p.drop.seed_lo, p.drop.seed_hi, it.n, it.h, it.r0 + r);
       const uint32_t rowkey2 = drop_rowkey2(rowkey);
+      DIAG_TRACE(1);
       mbar_wait(&sdp_full[st], (i >> 1) & 1);
       tc_fence_after();
-      if (i > 0) mbar_wait(pds_empty, (i - 1) & 1);
+      DIAG_TRACE(2);
       const uint32_t tS = tmem_base + st * 256 + lane_addr;
       float eps = 0.f;
-      // chunks / groups no row of this warp can see only get zeros stored (see the forward kernel)
+      if (i > 0) mbar_wait(pds_empty, (i - 1) & 1);   // P / dS smem is single-buffered: the gradient MMAs of item i-1 have read it
+      DIAG_TRACE(3);
+      // 16 key columns at a time (two tcgen05.ld x16 per piece): with 32-column pieces the warp needed more than the 96
+      // registers an 18-warp CTA allows, and the spill stores of the PREFETCHED per-row inputs then waited for their global
+      // loads (4.5k cycles per item, clock64 trace).  Pieces / 8-column groups no row of this warp can see only get zeros
+      // stored (see the forward kernel).
 #pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = half * 2 + cc;
-        const uint32_t w = cc ? mw[1] : mw[0];
-        uint8_t* pbase = sP + half * 16384 + r * 128;
-        uint8_t* dbase = sDS + half * 16384 + r * 128;
+      for (int q = 0; q < 4; ++q) {
+        const int c16 = 2 * q + half;                                 // 16-column piece of the 128-key tile
+        const uint32_t w = (q == 0) ? mw16[0] : (q == 1) ? mw16[1] : (q == 2) ? mw16[2] : mw16[3];
+        uint8_t* pbase = sP + (c16 >> 2) * 16384 + r * 128;           // 64-key K block, then the row
+        uint8_t* dbase = sDS + (c16 >> 2) * 16384 + r * 128;
+        const int ch0 = (c16 & 3) * 2;                                // first 16-byte chunk of the piece inside the row
         if (!__any_sync(0xffffffffu, w != 0u)) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int chunk = ((cc * 4 + g) ^ (r & 7)) << 4;
+          for (int g = 0; g < 2; ++g) {
+            const int chunk = ((ch0 + g) ^ (r & 7)) << 4;
             *reinterpret_cast<uint4*>(pbase + chunk) = make_uint4(0u, 0u, 0u, 0u);
             *reinterpret_cast<uint4*>(dbase + chunk) = make_uint4(0u, 0u, 0u, 0u);
           }
           continue;
         }
-        uint32_t s[32], dp[32];
-        tmem_ld32(tS + c * 32, s);
-        tmem_ld32(tS + 128 + c * 32, dp);
+        uint32_t s[16], dp[16];
+        tmem_ld16(tS + c16 * 16, s);
+        tmem_ld16(tS + 128 + c16 * 16, dp);
         tmem_ld_wait();
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < 2; ++g) {
           uint4 o = make_uint4(0u, 0u, 0u, 0u), o2 = make_uint4(0u, 0u, 0u, 0u);
           if (__any_sync(0xffffffffu, ((w >> (g * 8)) & 0xffu) != 0u)) {
             float pv[8], dv[8];
@@ -614,7 +557,7 @@ attn_diag_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
               pv[j] = ((w >> (g * 8 + j)) & 1u) ? e : 0.f;
               float dpe = __uint_as_float(dp[g * 8 + j]);
               if (p.drop.thresh != 0u) {
-                if ((j & 1) == 0) bits = drop_bits(rowkey, rowkey2, it.r0 + c * 32 + g * 8 + j);
+                if ((j & 1) == 0) bits = drop_bits(rowkey, rowkey2, it.r0 + c16 * 16 + g * 8 + j);
                 const bool keep = (j & 1) ? drop_keep_odd(bits, p.drop.thresh) : drop_keep_even(bits, p.drop.thresh);
                 dpe = keep ? dpe * p.drop.inv_keep : 0.f;
                 const float t0 = pv[j] * (dpe - dsum);
@@ -631,25 +574,155 @@ attn_diag_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
             o2.x = pack_bf16(dv[0], dv[1]); o2.y = pack_bf16(dv[2], dv[3]);
             o2.z = pack_bf16(dv[4], dv[5]); o2.w = pack_bf16(dv[6], dv[7]);
           }
-          const int chunk = ((cc * 4 + g) ^ (r & 7)) << 4;
+          const int chunk = ((ch0 + g) ^ (r & 7)) << 4;
           *reinterpret_cast<uint4*>(pbase + chunk) = o;
           *reinterpret_cast<uint4*>(dbase + chunk) = o2;
         }
       }
-      epsx[(i & 1) * 256 + half * 128 + r] = eps;
+      epsx[(i & 1) * 256 + half * 128 + r] = eps;   // read by the epilogue warps behind acc_full (barrier chain)
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full);
-      if (i > 0) epilogue(i - 1, prev);
-      prev = it;
-      pos_prev = rp.pos;
+      DIAG_TRACE(4);
       it = it_next;
       it_next = it_next2;
       rp = rp_next;
     }
-    issue_gather(pos_prev);
-    epilogue(n_items - 1, prev);
+  } else {
+    // ===================== epilogue warps (10..17): two per TMEM lane quadrant ==========================================
+    // They drain item i's gradient accumulators, un-rotate dQ / dK and store, WHILE the softmax-gradient warps are on
+    // item i+1 (before: the same eight warps did both, one after the other — the epilogue was 7.3k of the 12.5k cycles
+    // per item, clock64 trace tools/attn_trace.py).  half 0: dV and dK, half 1: dQ with the eps * (P K) correction.
+    // Accumulators are taken 16 columns at a time (two or four tcgen05.ld x16 per wait) so that the warp stays within the
+    // 96 registers an 18-warp CTA allows, and every thread stores 32 contiguous bytes (one full sector) per instruction.
+    const int quad = warp & 3;
+    const int half = (warp - 10) >> 2;
+    const int r = quad * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+    // RoPE table rows of this quadrant's tokens: the two warps of a quadrant need the same 32 cos rows and 32 sin rows, so
+    // warp `half` fetches table `half` for both with cp.async into a 4 KB swizzled buffer; 64-thread named barriers
+    // separate the partner's reads of the previous tables from the refill and publish the new ones.
+    uint8_t* gb_cos = smem + kDBSmemGather + (quad * 2) * 4096;
+    uint8_t* gb_sin = gb_cos + 4096;
+    auto pair_barrier = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory"); };
+    auto load_item = [&](int i) -> DiagItem {
+      return (i < n_items) ? diag_item(p, blockIdx.x + i * gridDim.x) : DiagItem{0, 0, 0, 0, 0};
+    };
+    auto load_pos = [&](const DiagItem& it) -> int {
+      return __ldg(p.pos + static_cast<size_t>(it.n) * p.S + it.r0 + min(r, max(it.len - 1, 0)));
+    };
+    auto st256 = [](__nv_bfloat16* dst, const float (&o)[16]) {
+      asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(pack_bf16(o[0], o[1])),
+                   "r"(pack_bf16(o[2], o[3])), "r"(pack_bf16(o[4], o[5])), "r"(pack_bf16(o[6], o[7])),
+                   "r"(pack_bf16(o[8], o[9])), "r"(pack_bf16(o[10], o[11])), "r"(pack_bf16(o[12], o[13])),
+                   "r"(pack_bf16(o[14], o[15]))
+                   : "memory");
+    };
+    DiagItem it = load_item(0), it_next = load_item(1);
+    int pos = load_pos(it);
+    for (int i = 0; i < n_items; ++i) {
+      const DiagItem it_next2 = load_item(i + 2);
+      const int pos_next = load_pos(it_next);
+      const int st = i & 1;
+      pair_barrier();                                 // the partner has finished reading the previous tables
+      {
+        const float* tab = half ? p.sin_tab : p.cos_tab;
+        uint8_t* dst = half ? gb_sin : gb_cos;
+        const int rd_row = lane >> 3, rd_j = lane & 7;
+#pragma unroll
+        for (int it8 = 0; it8 < 8; ++it8) {
+          const int rr = it8 * 4 + rd_row;
+          const int src = __shfl_sync(0xffffffffu, pos, rr);
+          const float* g = tab + static_cast<long long>(src) * 32 + rd_j * 4;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + rr * 128 + ((rd_j ^ (rr & 7)) << 4))),
+                       "l"(g)
+                       : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+      const uint32_t d = tmem_base + st * 256 + lane_addr;
+      const bool ok = r < it.len;
+      __nv_bfloat16* orow = p.dqkv + (static_cast<long long>(it.n) * p.S + it.r0 + r) * p.ld_dqkv + it.h * 64;
+      mbar_wait(&acc_full[st], (i >> 1) & 1);
+      tc_fence_after();
+      DIAG_TRACE_EPI(6);
+      if (half == 0) {
+        // ---- dV: no rotation (dropout: keeps were rescaled by 1 / (1 - p))
+        const float vs = (p.drop.thresh != 0u) ? p.drop.inv_keep : 1.0f;
+#pragma unroll 1
+        for (int cb = 0; cb < 2; ++cb) {
+          uint32_t x1[16], x2[16];
+          tmem_ld16(d + cb * 32, x1);
+          tmem_ld16(d + cb * 32 + 16, x2);
+          tmem_ld_wait();
+          float o1[16], o2[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            o1[j] = __uint_as_float(x1[j]) * vs;
+            o2[j] = __uint_as_float(x2[j]) * vs;
+          }
+          if (ok) {
+            st256(orow + p.v_col0 + cb * 32, o1);
+            st256(orow + p.v_col0 + cb * 32 + 16, o2);
+          }
+        }
+      }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      pair_barrier();                                 // both tables have landed
+      // ---- rotated outputs: half 0 -> dK (accumulator columns [64,128)), half 1 -> dQ ([128,192), PK at [192,256))
+      const uint32_t dacc = d + (half == 0 ? 64 : 128);
+      const int col0 = half == 0 ? p.k_col0 : p.q_col0;
+      float ce = 0.f;
+      if (half == 1) {
+        const float* e = epsx + (i & 1) * 256;
+        ce = (e[r] + e[128 + r]) * p.scale;
+      }
+#pragma unroll 1
+      for (int jb = 0; jb < 2; ++jb) {              // rotation pairs (j, j + 32), j in [16 jb, 16 jb + 16)
+        uint32_t x1[16], x2[16];
+        tmem_ld16(dacc + jb * 16, x1);
+        tmem_ld16(dacc + 32 + jb * 16, x2);
+        if (half == 1) {
+          uint32_t y1[16], y2[16];
+          tmem_ld16(d + 192 + jb * 16, y1);
+          tmem_ld16(d + 192 + 32 + jb * 16, y2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            x1[j] = __float_as_uint(__uint_as_float(x1[j]) - ce * __uint_as_float(y1[j]));
+            x2[j] = __float_as_uint(__uint_as_float(x2[j]) - ce * __uint_as_float(y2[j]));
+          }
+        } else {
+          tmem_ld_wait();
+        }
+        float o1[16], o2[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int ch = ((jb * 4 + q) ^ (lane & 7)) << 4;
+          const float4 a = *reinterpret_cast<const float4*>(gb_cos + lane * 128 + ch);
+          const float4 b4 = *reinterpret_cast<const float4*>(gb_sin + lane * 128 + ch);
+          const float cs[4] = {a.x, a.y, a.z, a.w}, sn[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float d1 = __uint_as_float(x1[q * 4 + j]), d2 = __uint_as_float(x2[q * 4 + j]);
+            o1[q * 4 + j] = d1 * cs[j] + d2 * sn[j];       // transpose of the forward rotation
+            o2[q * 4 + j] = d2 * cs[j] - d1 * sn[j];
+          }
+        }
+        if (ok) {
+          st256(orow + col0 + jb * 16, o1);
+          st256(orow + col0 + 32 + jb * 16, o2);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[st]);
+      DIAG_TRACE_EPI(7);
+      it = it_next;
+      it_next = it_next2;
+      pos = pos_next;
+    }
   }
 
   tc_fence_before();
@@ -696,6 +769,12 @@ static int set_smem_attr(const void* fn, int bytes, bool* done) {
   *done = true;
   return 0;
 }
+
+#ifdef GGPT_ATTN_TRACE
+int diag_trace_read(long long* out, int n) {
+  return cudaMemcpyFromSymbol(out, g_diag_trace, sizeof(long long) * n) == cudaSuccess ? 0 : -2;
+}
+#endif
 
 int attn_iso_build(const uint8_t* cls, const int* n_tiles, const int* tile_start, int N, int max_tiles, uint8_t* iso_flags,
                    int* iso_list, int* iso_count, cudaStream_t s) {

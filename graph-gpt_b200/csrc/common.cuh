@@ -500,9 +500,11 @@ __device__ __forceinline__ float edrop_scale1(const DropParams& dp, unsigned lon
 //   (Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7 — far below the bf16 rounding of the outputs), and with
 //   x = g / sqrt2 the same e^{-x^2} = e^{-g^2/2} is the Gaussian pdf needed by gelu'(g) = Phi(g) + g phi(g).
 __device__ __forceinline__ void gelu_cdf_pdf(float g, float& cdf, float& pdf) {
-  const float ax = fabsf(g) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
-  const float e = exp2f(g * g * -0.72134752044448170f);   // e^{-g^2/2}
+  // (t = 1 / (1 + 0.3275911 |g| / sqrt2): the constant is folded; rcp / ex2 are the bare MUFU forms — exp2f / __fdividef
+  // wrap them in range fix-ups (FSETP + 2 FMUL each) that an argument <= 0 / >= 1 never needs)
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.23164189f, fabsf(g), 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(g * g * -0.72134752044448170f));   // e^{-g^2/2}
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);

@@ -47,3 +47,34 @@ for k, (a, b) in names.items():
 per_tile = t[:, 1:, 0] - t[:, :-1, 0]
 print(f"  loop period      mean {per_tile.mean():8.0f}  p90 {np.percentile(per_tile, 90):8.0f}")
 print(f"  CTA span (tile loop only) mean {(t[:, 7, 5] - t[:, 0, 0]).mean():8.0f}")
+
+# ---- packed (isolated-tile) backward: compute warp 2 of 32 CTAs, items 8..23
+if "diag" in sys.argv:
+    from graphgpt_b200 import synth  # noqa: E402
+    b = synth.make_batch(N, S, layout="packed", seed=3)
+    am = torch.from_numpy(b["attention_mask"]).cuda()
+    pmask = ops.attn_mask_build(am, N, S, False, "cuda")
+    pos = torch.arange(S, device="cuda", dtype=torch.int32).repeat(N)
+    inv = 1.0 / (10000.0 ** (torch.arange(0, 64, 2).float() / 64))
+    fr = torch.arange(S).float()[:, None] * inv[None]
+    cos, sin = fr.cos().cuda().contiguous(), fr.sin().cuda().contiguous()
+    dout = (torch.randn(N * S, d, device="cuda") * 0.1).to(torch.bfloat16)
+    out, lse = ops.attn_fwd(qkv, pmask, H, dropout_p=0.1, seed=7)
+    for _ in range(3):
+        ops.attn_bwd(dout, qkv, out, lse, pmask, H, pos, cos, sin, dropout_p=0.1, seed=7)
+    torch.cuda.synchronize()
+    buf2 = (ctypes.c_longlong * (32 * 16 * 8))()
+    assert dll.ggpt_debug_diag_trace(buf2, 32 * 16 * 8) == 0
+    t2 = np.array(buf2[:], dtype=np.int64).reshape(32, 16, 8)[:, 1:15]
+    ph = {"prefetch": (0, 1), "wait S/dP": (1, 2), "wait P/dS buffer": (2, 3), "softmax-gradient pass": (3, 4),
+          "MMA thread: gradient MMAs issued -> accumulators ready": (5, 6), "warp 2 published P/dS -> MMA thread issues": (4, 5), "epilogue warp: drain + rotate + store": (6, 7)}
+    print("packed backward, cycles per item (compute warp 2, 32 CTAs x 14 items):")
+    for k, (a, b_) in ph.items():
+        dlt = t2[:, :, b_] - t2[:, :, a]
+        print(f"  {k:40s} mean {dlt.mean():8.0f}  p90 {np.percentile(dlt, 90):8.0f}")
+    lat = t2[:, :, 6] - t2[:, :, 4]
+    print(f"  P/dS published -> accumulators ready (gradient MMAs) mean {lat.mean():8.0f}  p90 {np.percentile(lat, 90):8.0f}")
+    lat2 = t2[:, 2:, 2] - t2[:, :-2, 7]
+    print(f"  epilogue(i-2) done -> scores(i) ready               mean {lat2.mean():8.0f}  p90 {np.percentile(lat2, 90):8.0f}")
+    per = t2[:, 1:, 0] - t2[:, :-1, 0]
+    print(f"  item period                              mean {per.mean():8.0f}  p90 {np.percentile(per, 90):8.0f}")
