@@ -123,48 +123,27 @@ __device__ __forceinline__ float fwd_half_exp(uint32_t (&s)[2][32], const uint32
   return (l4[0] + l4[1]) + (l4[2] + l4[3]);
 }
 
-// One float per thread exchanged between the two warps that share a TMEM lane quadrant, through a spare TMEM column
-// (each thread's partner is the same lane of the other warp): st -> wait::st -> 64-thread named barrier -> ld.
-__device__ __forceinline__ float pair_exchange(uint32_t col_mine, uint32_t col_other, float v, int bar_id) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(col_mine), "r"(__float_as_uint(v)) : "memory");
-  tmem_st_wait();
-  tc_fence_before();
-  asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-  tc_fence_after();
-  uint32_t o;
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(o) : "r"(col_other) : "memory");
-  tmem_ld_wait();
-  return __uint_as_float(o);
-}
-
-// OR of one predicate over the 64 threads of a quadrant's warp pair (named barrier with reduction).
-__device__ __forceinline__ bool pair_vote_or(bool v, int bar_id) {
-  uint32_t out;
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t"
-      "setp.ne.b32 p, %1, 0;\n\t"
-      "barrier.cta.red.or.pred q, %2, 64, p;\n\t"
-      "selp.b32 %0, 1, 0, q;\n\t}"
-      : "=r"(out)
-      : "r"(static_cast<uint32_t>(v)), "r"(bar_id)
-      : "memory");
-  return out != 0;
-}
-
 // Pipeline of one CTA (the two resident CTAs of an SM interleave two such pipelines):
-//   MMA thread     : S(0) | for it: [s_empty(it) & K(it+1)] -> S(it+1) ; [p_full(it) & V(it)] -> O (+)= P(it) V(it)
-//   softmax warps  : s_full(it) -> scores TMEM -> registers -> arrive s_empty   (the S buffer is free again: the score
-//                    MMA of tile it+1 runs while this tile's max / exp / pack are computed)
-//                    -> row max (halves combined through TMEM) -> lazy rescale of O in TMEM -> exp2 / mask / dropout /
-//                    pack -> pv_done(it-1) -> P to smem -> arrive p_full
-// EIGHT softmax warps, two threads per query row (64 keys each): the phases of a warp that do not use the MUFU pipe
-// (barrier waits, the TMEM drain, the row max, the P stores and their proxy fence, the output epilogue) are covered by the
-// exponentials of the other three warps of its scheduler — with four warps per CTA the MUFU pipe, the binding resource
-// at head_dim 64, was busy 36 % of the time (ncu, profiles/r2r_*).
-// O accumulates in TMEM over all key tiles.  The running maximum each row's sums are expressed against (m_used) is only
-// advanced — and O / l rescaled, by the row's own threads through tcgen05.ld / st — when the new maximum exceeds it by
-// more than 8 (log2 domain): stale maxima leave P <= 2^8, harmless in bf16 / fp32, and after the first tile or two of a
-// row the rescale almost never fires (the FlashAttention-4 "lazy rescale").
+//   MMA thread     : S(0) | for g: [s_empty(g) & K(g+1)] -> S(g+1) ; per key half hc: [p_full[hc](g) & V(g)] ->
+//                    O_hc (+)= P_hc(g) V_hc(g)
+//   softmax warps  : s_full(g) -> scores TMEM -> registers -> arrive s_empty   (the S buffer is free again: the score
+//                    MMA of tile g+1 runs while this tile's max / exp / pack are computed)
+//                    -> maximum -> lazy rescale of O_hc in TMEM -> exp2 / mask / dropout / pack -> pv_done[hc](g-1)
+//                    -> P_hc to smem -> arrive p_full[hc]
+// EIGHT softmax warps, two threads per query row.  The two threads of a row split the KEYS of every tile (64 each) and
+// run two INDEPENDENT online softmaxes: each has its own reference maximum, its own row sum and its own accumulator
+// O_hc = sum over its keys of P V in TMEM (the PV product of a tile is issued as two K = 64 halves into two 64-column
+// accumulators), and the halves are merged once per row in the epilogue,
+//     O = (w_0 O_0 + w_1 O_1) / (w_0 l_0 + w_1 l_1),   w_hc = 2^(m_hc - max(m_0, m_1)).
+// No value ever crosses a warp inside the key loop: a first version that kept one accumulator per row had the two
+// threads agree on the maximum every tile (named barrier + TMEM exchange) and spent 17 % of its time there (clock64
+// trace, tools/attn_trace.py).  With four warps per CTA the MUFU pipe, the binding resource at head_dim 64, was busy
+// 36 % of the time (ncu): the phases of a warp that do not use it (barrier waits, the TMEM drain, the maximum, the P
+// stores and their proxy fence, the output epilogue) are covered by the exponentials of the scheduler's other warps.
+// The maximum each half's sums are expressed against (m_used) is only advanced — and O_hc / l rescaled, by the row's own
+// thread through tcgen05.ld / st — when the new maximum exceeds it by more than 8 (log2 domain): stale maxima leave
+// P <= 2^8, harmless in bf16 / fp32, and after the first tile or two the rescale almost never fires (the
+// FlashAttention-4 "lazy rescale").
 constexpr float kRescaleThreshold = 8.0f;
 
 #ifdef GGPT_ATTN_TRACE      // profiling aid: per-phase clock64 stamps of one softmax warp of a few CTAs (tools/attn_trace.py)
@@ -195,19 +174,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
   uint64_t* k_full = bars + 1;     // [2]
   uint64_t* k_empty = bars + 3;    // [2]  score MMA that read the stage has retired
   uint64_t* v_full = bars + 5;     // [2]
-  uint64_t* v_empty = bars + 7;    // [2]  PV MMA that read the stage has retired
+  uint64_t* v_empty = bars + 7;    // [2]  both PV halves that read the stage have retired
   uint64_t* s_full = bars + 9;     // scores of tile g in TMEM
   uint64_t* s_empty = bars + 10;   // ... and drained into registers (8 warps)
-  uint64_t* p_full = bars + 11;    // P(g) in smem, O rescaled if needed (8 warps)
-  uint64_t* pv_done = bars + 12;   // O += P(g) V(g) retired: P buffer reusable, O readable
-  uint64_t* q_empty = bars + 13;   // every score MMA of the current head has retired: Q buffer reusable
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* p_full = bars + 11;    // [2] P_hc(g) in smem, O_hc rescaled if needed (4 warps each)
+  uint64_t* pv_done = bars + 13;   // [2] O_hc += P_hc(g) V_hc(g) retired: P_hc buffer reusable, O_hc readable
+  uint64_t* q_empty = bars + 15;   // every score MMA of the current head has retired: Q buffer reusable
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + 1016);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   // One CTA serves ONE query tile for `heads_per_cta` consecutive heads: the tile plan, the TMEM allocation and the
   // barrier set-up are paid once, and the output epilogue of head h overlaps the Q / K / V loads and the first score MMA
-  // of head h+1 (measured before: 44 % of a CTA's life was prologue + epilogue around an 8-tile loop).
+  // of head h+1.
   const int qt = blockIdx.x, n = blockIdx.z;
   const int h_begin = blockIdx.y * p.heads_per_cta;
   const int h_end = min(p.H, h_begin + p.heads_per_cta);
@@ -250,11 +229,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
       mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
+      mbar_init(&p_full[i], kAttSoftmaxWarps / 2);
+      mbar_init(&pv_done[i], 1);
     }
     mbar_init(s_full, 1);
     mbar_init(s_empty, kAttSoftmaxWarps);
-    mbar_init(p_full, kAttSoftmaxWarps);
-    mbar_init(pv_done, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -266,8 +245,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base;         // 128 columns
-  const uint32_t tmem_O = tmem_base + 128;   // 64 columns
-  const uint32_t tmem_X = tmem_base + 192;   // 4 columns: row-max exchange [tile parity][column half]
+  const uint32_t tmem_O = tmem_base + 128;   // 2 x 64 columns: O_0 (keys 0..63 of every tile) | O_1 (keys 64..127)
 
   int n_active = 0;                          // active key tiles of this query tile (the same for every head)
   for (int kt = 0; kt < n_kt; ++kt) n_active += (cls_row[kt] != 0);
@@ -329,29 +307,34 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
           } else {
             tc_commit(q_empty);             // every score MMA of this head has been issued
           }
-          mbar_wait(p_full, g & 1);         // P(g) in smem, O rescaled
           mbar_wait(&v_full[st], (g >> 1) & 1);
-          tc_fence_after();
           const uint32_t aV = smem_u32(sV + st * 16384);
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)
-            tc_mma_bf16(tmem_O, umma_desc_sw128(aP + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
-                        umma_desc_sw128(aV + kk * 2048, 8192, 1024), idesc_o, (it | kk) != 0);
-          tc_commit(pv_done);
+          for (int hc = 0; hc < 2; ++hc) {  // keys [64 hc, 64 hc + 64) of the tile -> accumulator O_hc
+            mbar_wait(&p_full[hc], g & 1);  // P_hc(g) in smem, O_hc rescaled
+            tc_fence_after();
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              tc_mma_bf16(tmem_O + hc * 64, umma_desc_sw128(aP + hc * 16384 + kk * 32, 16, 1024),
+                          umma_desc_sw128(aV + (hc * 4 + kk) * 2048, 8192, 1024), idesc_o, (it | kk) != 0);
+            tc_commit(&pv_done[hc]);
+          }
           tc_commit(&v_empty[st]);
         }
       }
     }
   } else {
-    // ===================== softmax / epilogue warps: two threads per query row =====================
+    // ===================== softmax / epilogue warps: two threads per query row, 64 keys of every tile each ==============
     const int quad = warp & 3;
-    const int hc = (warp - 2) >> 2;              // column half of the score tile / of the output row
+    const int hc = (warp - 2) >> 2;              // key half of every tile / column half of the output row
     const int r = quad * 32 + lane;              // row inside the tile
     const int q_row = q0 + r;
     const bool row_ok = r < qlen;
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t* mrow = p.mask_bits + (static_cast<size_t>(n) * p.S + (row_ok ? q_row : 0)) * p.mask_words;
     uint8_t* prow = sP + hc * 16384 + r * 128;   // this thread's 64 columns are one 128-byte row of K block hc
+    const uint32_t tmem_Omine = tmem_O + lane_addr + hc * 64;
+    const uint32_t tmem_Oother = tmem_O + lane_addr + (hc ^ 1) * 64;
 #ifdef GGPT_ATTN_TRACE
     const int trace_cta = (blockIdx.z % 8) * 8 + blockIdx.x % 8;     // 64 traced CTAs: head group 1, sequences 8..15
     const bool trace_on = (warp == 2) && blockIdx.y == 1 && blockIdx.z >= 8 && blockIdx.z < 16;
@@ -361,9 +344,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
     for (int h = h_begin; h < h_end; ++h, g0 += n_active) {
       const uint32_t rowkey = drop_rowkey(p.drop.seed_lo, p.drop.seed_hi, n, h, q_row);
       const uint32_t rowkey2 = drop_rowkey2(rowkey);
-      float m_used = 0.f;     // log2-domain maximum the row's P / l / O are expressed against (same in both threads)
-      bool seen = false;      // some key of this row has been visible so far
-      float l_run = 0.f;      // this thread's half of the row sum
+      float m_used = 0.f;     // log2-domain maximum this half's P / l / O_hc are expressed against
+      bool seen = false;      // some key of this half of the row has been visible so far
+      float l_run = 0.f;      // this half's sum
 
       int it = 0;
       ATTN_TRACE_H(0);
@@ -397,39 +380,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
         if (lane == 0) mbar_arrive(s_empty);
 
         const float m_half = ((cls == 2) ? fwd_half_max<true>(s, mw) : fwd_half_max<false>(s, mw)) * p.scale_log2;
-        // The two threads of a row must agree on the reference maximum.  It only moves when one half's maximum is the
-        // row's first visible key or exceeds it by more than the threshold, so the halves first vote (one barrier with an
-        // OR reduction over the quadrant's two warps) and exchange their maxima — through TMEM, ~10x the cost of the vote
-        // — only when some row of the quadrant needs it: the first tile, and rarely afterwards.
-        const bool want = (m_half != -INFINITY) && (!seen || m_half > m_used + kRescaleThreshold);
         bool need = false;
         float alpha = 1.f;
-        if (pair_vote_or(want, 1 + quad)) {
-          const uint32_t xcol = tmem_X + lane_addr + (g & 1) * 2;
-          const float m_tile = fmaxf(m_half, pair_exchange(xcol + hc, xcol + (hc ^ 1), m_half, 1 + quad));
-          if (m_tile != -INFINITY) {
-            if (!seen) {                 // first visible keys of this row: O and l are still exactly zero
-              seen = true;
-              m_used = m_tile;
-            } else if (m_tile > m_used + kRescaleThreshold) {
-              need = true;
-              alpha = fast_exp2(m_used - m_tile);
-              m_used = m_tile;
-            }
+        if (m_half != -INFINITY) {
+          if (!seen) {                 // first visible keys of this half: O_hc and l are still exactly zero
+            seen = true;
+            m_used = m_half;
+          } else if (m_half > m_used + kRescaleThreshold) {
+            need = true;
+            alpha = fast_exp2(m_used - m_half);
+            m_used = m_half;
           }
         }
         ATTN_TRACE(2);
         if (it > 0 && __any_sync(0xffffffffu, need)) {   // warp-uniform: tcgen05.ld / st are warp-collective
-          mbar_wait(pv_done, (g - 1) & 1);
+          mbar_wait(&pv_done[hc], (g - 1) & 1);
           tc_fence_after();
 #pragma unroll 1
-          for (int c = 0; c < 4; ++c) {                  // this thread's 32 output columns, 8 at a time
+          for (int c = 0; c < 8; ++c) {                  // this half's 64 accumulator columns, 8 at a time
             uint32_t o[8];
-            tmem_ld8(tmem_O + lane_addr + hc * 32 + c * 8, o);
+            tmem_ld8(tmem_Omine + c * 8, o);
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
-            tmem_st8(tmem_O + lane_addr + hc * 32 + c * 8, o);
+            tmem_st8(tmem_Omine + c * 8, o);
           }
           tmem_st_wait();
           l_run *= alpha;
@@ -439,10 +413,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
             : fwd_half_exp<false, DROP>(s, mw, p.scale_log2, m_used, rowkey, rowkey2, k0, p.drop.thresh);
         l_run += l_tile;
         ATTN_TRACE(3);
-        // the PV MMA of the previous tile has read the P buffer (tile 0 of a head: the epilogue of the previous head has
-        // waited for its last PV, and the pair's vote barrier above ordered this store behind the partner's flush of the
-        // staging rows that alias this buffer)
-        if (it > 0) mbar_wait(pv_done, (g - 1) & 1);
+        // the PV MMA of the previous tile has read this half's P buffer (tile 0 of a head: the epilogue of the previous
+        // head has waited for both last PVs, and its final pair barrier ordered this store behind the partner's flush of
+        // the staging rows that alias this buffer)
+        if (it > 0) mbar_wait(&pv_done[hc], (g - 1) & 1);
         ATTN_TRACE(4);
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
@@ -455,50 +429,67 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
         fence_proxy_async_smem();   // make P visible to the tensor-core (async) proxy
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(p_full);
+        if (lane == 0) mbar_arrive(&p_full[hc]);
         ATTN_TRACE(5);
         ++it;
       }
 
       {
-        // every PV of this head has retired, so the P buffer stages the output: the two warps of a quadrant fill one
-        // 32 x 128 B block (32 columns each) and flush 16 rows each as full 128-byte lines
+        // Merge of the two key halves and output.  Every PV of this head has retired, so the P buffer is free: first it
+        // carries each thread's (m, l) to its partner — written into the 16-byte chunk of the PARTNER's part of the
+        // staging row, which only the partner overwrites later, so one pair barrier suffices — then it stages the
+        // output: the two warps of a quadrant fill one 32 x 128 B block (32 output columns each) and flush 16 rows each
+        // as full 128-byte lines.
         ATTN_TRACE_H(1);
         if (n_active > 0) {
-          mbar_wait(pv_done, (g0 + n_active - 1) & 1);
+          const int gl = g0 + n_active - 1;
+          mbar_wait(&pv_done[hc], gl & 1);
+          mbar_wait(&pv_done[hc ^ 1], gl & 1);
           tc_fence_after();
         }
         ATTN_TRACE_H(2);
-        const uint32_t xcol = tmem_X + lane_addr;
-        const float l_row = l_run + pair_exchange(xcol + hc, xcol + (hc ^ 1), l_run, 1 + quad);
-        ATTN_TRACE_H(3);
-        const float inv = (l_row > 0.f) ? p.drop.inv_keep / l_row : 0.f;   // dropout keeps are rescaled by 1/(1-p)
         uint8_t* stg = sP + quad * 4096;
         uint8_t* stg_lo = sP + 16384 + quad * 4096;
-        uint32_t o[32];
-        if (n_active > 0) {
-          tmem_ld32(tmem_O + lane_addr + hc * 32, o);
-          tmem_ld_wait();
-          tc_fence_before();
-        } else {
+        const float m_mine = seen ? m_used : -INFINITY;
+        *reinterpret_cast<float2*>(stg + lane * 128 + ((((hc ^ 1) * 4) ^ (lane & 7)) << 4)) = make_float2(m_mine, l_run);
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+        const float2 other = *reinterpret_cast<const float2*>(stg + lane * 128 + (((hc * 4) ^ (lane & 7)) << 4));
+        const float m_row = fmaxf(m_mine, other.x);
+        const float w_mine = (m_mine == -INFINITY) ? 0.f : fast_exp2(m_mine - m_row);
+        const float w_other = (other.x == -INFINITY) ? 0.f : fast_exp2(other.x - m_row);
+        const float l_row = l_run * w_mine + other.y * w_other;
+        const float inv = (l_row > 0.f) ? p.drop.inv_keep / l_row : 0.f;   // dropout keeps are rescaled by 1/(1-p)
+        const float f_mine = w_mine * inv, f_other = w_other * inv;
+        ATTN_TRACE_H(3);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) o[j] = 0u;
-        }
+        for (int cb = 0; cb < 2; ++cb) {         // this thread's 32 output columns [32 hc, 32 hc + 32), 16 at a time
+          uint32_t oa[16], ob[16];
+          if (n_active > 0) {
+            tmem_ld16(tmem_Omine + hc * 32 + cb * 16, oa);
+            tmem_ld16(tmem_Oother + hc * 32 + cb * 16, ob);
+            tmem_ld_wait();
+          } else {
 #pragma unroll
-        for (int gq = 0; gq < 4; ++gq) {
-          float f[8];
-          uint32_t hi[4], lo[4];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(o[gq * 8 + j]) * inv;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            hi[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
-            const float2 back = unpack_bf16(hi[j]);
-            lo[j] = pack_bf16(f[2 * j] - back.x, f[2 * j + 1] - back.y);     // rounding residual of the bf16 output
+            for (int j = 0; j < 16; ++j) oa[j] = ob[j] = 0u;
           }
-          stage_put16(stg, lane, hc * 4 + gq, make_uint4(hi[0], hi[1], hi[2], hi[3]));
-          if (p.out_lo != nullptr) stage_put16(stg_lo, lane, hc * 4 + gq, make_uint4(lo[0], lo[1], lo[2], lo[3]));
+#pragma unroll
+          for (int gq = 0; gq < 2; ++gq) {
+            float f[8];
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              f[j] = __uint_as_float(oa[gq * 8 + j]) * f_mine + __uint_as_float(ob[gq * 8 + j]) * f_other;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              hi[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
+              const float2 back = unpack_bf16(hi[j]);
+              lo[j] = pack_bf16(f[2 * j] - back.x, f[2 * j + 1] - back.y);     // rounding residual of the bf16 output
+            }
+            stage_put16(stg, lane, hc * 4 + cb * 2 + gq, make_uint4(hi[0], hi[1], hi[2], hi[3]));
+            if (p.out_lo != nullptr) stage_put16(stg_lo, lane, hc * 4 + cb * 2 + gq, make_uint4(lo[0], lo[1], lo[2], lo[3]));
+          }
         }
+        tc_fence_before();
         ATTN_TRACE_H(4);
         asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
         ATTN_TRACE_H(5);
@@ -508,9 +499,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
           stage_flush_rows16(stg_lo, lane, hc * 16, p.out_lo + row0 * p.ldo + h * kHeadDim, p.ldo,
                              qlen - quad * 32 - hc * 16);
         if (row_ok && hc == 0 && p.lse != nullptr) {
-          const float lse = (l_row > 0.f) ? (m_used * 0.6931471805599453f + logf(l_row)) : 0.f;
+          const float lse = (l_row > 0.f) ? (m_row * 0.6931471805599453f + logf(l_row)) : 0.f;
           p.lse[(static_cast<size_t>(n) * p.H + h) * p.S + q_row] = lse;
         }
+        // the partner's flush reads staging rows that alias THIS thread's next P row: order the next head behind it
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
         ATTN_TRACE_H(6);
       }
     }

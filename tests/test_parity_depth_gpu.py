@@ -52,13 +52,15 @@ def _cfg(L, d, V, F_, S, causal=False, **kw):
     return c
 
 
-def _tiled_attention(q, k, v, keep, tile_start, n_tiles, r):
-    """The attention kernels' own schedule, in fp32 torch: online softmax over the key tiles of the mask plan with the
-    un-normalised numerators rounded to bf16 RELATIVE TO THE REFERENCE MAXIMUM of that moment (that is what reaches the PV
-    tensor-core product), fp32 running sum of the unrounded numerators, fp32 accumulator.  The reference maximum is the
-    forward kernel's lazily advanced one (attn_fwd_sm100.cu): set by the first tile with a visible key, afterwards moved —
-    with a rescale of the accumulator and the sum — only when a tile's maximum exceeds it by more than 8 in the log2
-    domain.  q,k,v fp32 [N,H,S,64] holding bf16 values, keep bool [N or 1,1,S,S]."""
+def _tiled_attention(q, k, v, keep, tile_start, n_tiles, r, split=True):
+    """The attention kernels' own schedule, in fp32 torch (attn_fwd_sm100.cu): every key tile of the mask plan is split
+    into two halves of 64 keys, and each half runs its own online softmax over the tiles — un-normalised numerators
+    rounded to bf16 RELATIVE TO THE HALF'S REFERENCE MAXIMUM of that moment (that is what reaches the PV tensor-core
+    product), fp32 sum of the unrounded numerators, fp32 accumulator.  The reference maximum is lazily advanced: set by the
+    first tile with a visible key, afterwards moved — with a rescale of the accumulator and the sum — only when a tile's
+    maximum exceeds it by more than 8 in the log2 domain.  The halves are merged at the end.  split=False: the
+    isolated-tile kernels of packed batches (attn_diag_sm100.cu) — one softmax over the whole tile, numerators rounded
+    relative to the exact row maximum.  q,k,v fp32 [N,H,S,64] holding bf16 values, keep bool [N or 1,1,S,S]."""
     N, H, S, _ = q.shape
     out = torch.zeros_like(q)
     ninf = float("-inf")
@@ -66,23 +68,34 @@ def _tiled_attention(q, k, v, keep, tile_start, n_tiles, r):
     for n in range(N):
         ts, nt = tile_start[n].tolist(), int(n_tiles[n])
         kp = keep[n if keep.shape[0] > 1 else 0, 0]
-        mu = torch.full((H, S), ninf, device=q.device)
-        l = torch.zeros((H, S), device=q.device)
-        o = torch.zeros((H, S, 64), device=q.device)
+        mu = [torch.full((H, S), ninf, device=q.device) for _ in range(2)]
+        l = [torch.zeros((H, S), device=q.device) for _ in range(2)]
+        o = [torch.zeros((H, S, 64), device=q.device) for _ in range(2)]
         for kt in range(nt):
-            k0, k1 = ts[kt], ts[kt + 1]
-            s_ = (q[n] @ k[n, :, k0:k1].transpose(1, 2)) * 0.125
-            s_ = s_.masked_fill(~kp[None, :, k0:k1], ninf)
-            m_tile = s_.max(-1).values
-            first = (mu == ninf) & (m_tile > ninf)
-            move = (mu > ninf) & (m_tile > mu + thr)
-            alpha = torch.where(move, torch.exp(mu - m_tile), torch.ones_like(mu))
-            mu = torch.where(first | move, m_tile, mu)
-            m_use = torch.where(mu == ninf, torch.zeros_like(mu), mu)
-            e = torch.exp(s_ - m_use[..., None])
-            l = l * alpha + e.sum(-1)
-            o = o * alpha[..., None] + r(e) @ v[n, :, k0:k1]
-        out[n] = torch.where(l[..., None] > 0, o / l.clamp_min(1e-30)[..., None], torch.zeros_like(o))
+            for hc in range(2 if split else 1):
+                if split:
+                    k0, k1 = min(ts[kt] + 64 * hc, ts[kt + 1]), min(ts[kt] + 64 * hc + 64, ts[kt + 1])
+                else:
+                    k0, k1 = ts[kt], ts[kt + 1]
+                if k1 <= k0:
+                    continue
+                s_ = (q[n] @ k[n, :, k0:k1].transpose(1, 2)) * 0.125
+                s_ = s_.masked_fill(~kp[None, :, k0:k1], ninf)
+                m_tile = s_.max(-1).values
+                first = (mu[hc] == ninf) & (m_tile > ninf)
+                move = (mu[hc] > ninf) & (m_tile > mu[hc] + thr)
+                alpha = torch.where(move, torch.exp(mu[hc] - m_tile), torch.ones_like(m_tile))
+                mu[hc] = torch.where(first | move, m_tile, mu[hc])
+                m_use = torch.where(mu[hc] == ninf, torch.zeros_like(m_tile), mu[hc])
+                e = torch.exp(s_ - m_use[..., None])
+                l[hc] = l[hc] * alpha + e.sum(-1)
+                o[hc] = o[hc] * alpha[..., None] + r(e) @ v[n, :, k0:k1]
+        m_row = torch.maximum(mu[0], mu[1])
+        w = [torch.where(mu[hc] == ninf, torch.zeros_like(m_row), torch.exp(mu[hc] - torch.where(m_row == ninf, torch.zeros_like(m_row), m_row)))
+             for hc in range(2)]
+        l_row = l[0] * w[0] + l[1] * w[1]
+        num = o[0] * w[0][..., None] + o[1] * w[1][..., None]
+        out[n] = torch.where(l_row[..., None] > 0, num / l_row.clamp_min(1e-30)[..., None], torch.zeros_like(num))
     return out.transpose(1, 2).contiguous()
 
 
@@ -125,7 +138,7 @@ def _stage_local(tag, model, stash, am, valid):
         lin = torch.cat((rope(lin[:, :2 * d]), lin[:, 2 * d:]), -1)
         e["qkv+rope"] = rel(st["qkv"], r(lin))
         q, k, vv = (st["qkv"][:, j * d:(j + 1) * d].float().view(N, S, H, 64).transpose(1, 2) for j in range(3))
-        att = _tiled_attention(q, k, vv, keep, plan.tile_start, plan.n_tiles, r).reshape(N * S, d)
+        att = _tiled_attention(q, k, vv, keep, plan.tile_start, plan.n_tiles, r, split=bool(plan._iso_args()[3])).reshape(N * S, d)
         e["attention"] = rel(st["a"], r(att))
         br = lam1 * r(st["a"].float() @ fp.wb(p + "self_attn.o_proj.weight").float().t())
         e["x+o_proj"] = rel(st["x2"], x + br, br)
