@@ -105,6 +105,19 @@ __device__ __forceinline__ void bwd_chunk(uint32_t (&s)[32], uint32_t (&dp)[32],
   }
 }
 
+#ifdef GGPT_ATTN_TRACE      // profiling aid: clock64 stamps of softmax-gradient warp 2 of 64 CTAs (tools/attn_trace.py bwd)
+__device__ long long g_bwd_trace[64 * 12 * 8];
+#define BWD_TRACE(row, slot)                                                                                     \
+  do {                                                                                                           \
+    if (trace_on && lane == 0 && (row) < 12) g_bwd_trace[(trace_cta * 12 + (row)) * 8 + (slot)] = clock64();      \
+  } while (0)
+int bwd_trace_read(long long* out, int n) {
+  return cudaMemcpyFromSymbol(out, g_bwd_trace, sizeof(long long) * n) == cudaSuccess ? 0 : -2;
+}
+#else
+#define BWD_TRACE(row, slot) do { } while (0)
+#endif
+
 template <bool DROP>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
@@ -131,6 +144,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int tile = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
+#ifdef GGPT_ATTN_TRACE
+  const int trace_cta = (blockIdx.z % 8) * 8 + blockIdx.x % 8;     // 64 traced CTAs: head 5, sequences 8..15
+  const bool trace_on = (warp == 2) && blockIdx.y == 5 && blockIdx.z >= 8 && blockIdx.z < 16;
+  BWD_TRACE(8, 0);
+#endif
   const int n_t = p.n_tiles[n];
   if (tile >= n_t) return;                      // uniform for the whole CTA, before any barrier / TMEM state
   if (p.iso_flags != nullptr && p.iso_flags[n * p.max_tiles + tile]) return;   // done by attn_diag_bwd_kernel
@@ -327,10 +345,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     int t = next_active(-1);
     if (t < n_t) fetch(t, cur);
     int prev_q0 = 0;
+    BWD_TRACE(8, 1);
     for (int it = 0; it < n_active; ++it) {
+      BWD_TRACE(it, 0);
       const int t_next = next_active(t);
       if (t_next < n_t) fetch(t_next, nxt);
       mbar_wait(sdp_full, it & 1);
+      BWD_TRACE(it, 1);
       tc_fence_after();
       uint32_t s0[32], d0[32];
       tmem_ld32(tmem_S + lane_addr + chunk_c * 32, s0);
@@ -339,6 +360,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       tc_fence_before();              // scores are in registers: hand S / dP back before the arithmetic, not after it
       __syncwarp();
       if (lane == 0) mbar_arrive(sdp_empty);
+      BWD_TRACE(it, 2);
       const float lse2 = cur.lse * 1.4426950408889634f;
       const int cur_q0 = s_ts[t];
       uint32_t rk1 = 0u, rk2 = 0u;
@@ -358,12 +380,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         bwd_chunk<false, DROP>(s0, d0, chunk_c, 0xffffffffu, p.scale_log2, p.scale, lse2, cur.dsum, rk1, rk2, row_base,
                                p.drop.thresh, p.drop.inv_keep);
       }
+      BWD_TRACE(it, 3);
       uint32_t dq[16];
       if (it > 0) {
         mbar_wait(pds_empty, (it - 1) & 1);   // gradient MMAs of tile it-1 retired: P / dS free, dQ_{it-1}(j) complete
         tc_fence_after();
         tmem_ld16(tmem_dQ + lane_addr + chunk_c * 16, dq);
         tmem_ld_wait();
+      }
+      BWD_TRACE(it, 4);
+      if (it > 0) {                              // this warp's previous dQ reduction has read the staging box
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
       }
       {
         uint8_t* pbase = sP + (chunk_c >> 1) * 16384 + r * 128;
@@ -374,18 +402,33 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           *reinterpret_cast<uint4*>(pbase + chunk * 16) = make_uint4(s0[g * 4 + 0], s0[g * 4 + 1], s0[g * 4 + 2], s0[g * 4 + 3]);
           *reinterpret_cast<uint4*>(dbase + chunk * 16) = make_uint4(d0[g * 4 + 0], d0[g * 4 + 1], d0[g * 4 + 2], d0[g * 4 + 3]);
         }
+        if (it > 0) {                            // dQ_{it-1}(j) rides on the same proxy fence as P / dS
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<uint4*>(dq_stage + ((i ^ dq_sw) << 4)) = make_uint4(dq[i * 4 + 0], dq[i * 4 + 1], dq[i * 4 + 2], dq[i * 4 + 3]);
+        }
       }
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(pds_full);
-      if (it > 0) dq_reduce(dq, prev_q0);
+      if (lane == 0) {
+        mbar_arrive(pds_full);
+        if (it > 0) {
+#ifndef GGPT_BWD_NO_REDUCE      // (timing experiment of tools/attn_trace.py: how much of the tile period is the TMA reduction?)
+          tma_reduce_add_3d(&tmDQ, dq_box, h * 64 + chunk_c * 16, prev_q0 + quad * 32, n);
+#endif
+          tma_store_commit();
+        }
+      }
+      BWD_TRACE(it, 5);
+      BWD_TRACE(it, 6);
       prev_q0 = cur_q0;
       cur = nxt;
       t = t_next;
     }
 
     // ---- last dQ tile, then the epilogue: this thread owns output row `row_base + r`
+    BWD_TRACE(8, 2);
     if (n_active > 0) {
       mbar_wait(acc_full, 0);
       tc_fence_after();
@@ -477,6 +520,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       }
     }
     if (lane == 0) tma_store_wait_all();        // the reductions have left shared memory and are globally performed
+    BWD_TRACE(8, 3);
   }
 
   tc_fence_before();

@@ -36,6 +36,7 @@ int attn_iso_build(const uint8_t* cls, const int* n_tiles, const int* tile_start
                    int* iso_list, int* iso_count, cudaStream_t s);
 #ifdef GGPT_ATTN_TRACE
 int diag_trace_read(long long* out, int n);
+int bwd_trace_read(long long* out, int n);
 #endif
 int attn_diag_fwd_launch(const CUtensorMap& tm, const DiagParams& p, cudaStream_t s);
 int attn_diag_bwd_launch(const CUtensorMap& tmQKV, const CUtensorMap& tmDO, const DiagParams& p, cudaStream_t s);

@@ -674,6 +674,7 @@ extern "C" {
 
 #ifdef GGPT_ATTN_TRACE
 int ggpt_debug_diag_trace(long long* out, int n) { return ggpt::diag_trace_read(out, n); }
+int ggpt_debug_bwd_trace(long long* out, int n) { return ggpt::bwd_trace_read(out, n); }
 int ggpt_debug_attn_trace(long long* out, int n) {
   return cudaMemcpyFromSymbol(out, ggpt::g_attn_trace, sizeof(long long) * n) == cudaSuccess ? 0 : -2;
 }

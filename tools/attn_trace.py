@@ -12,7 +12,7 @@ sys.path.insert(0, ROOT)
 csrc = os.path.join(ROOT, "graph-gpt_b200", "csrc")
 so = "/tmp/libggpt_trace.so"
 srcs = [os.path.join(csrc, f) for f in sorted(os.listdir(csrc)) if f.endswith(".cu")]
-subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-DGGPT_ATTN_TRACE",
+subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-DGGPT_ATTN_TRACE"] + os.environ.get("GGPT_TRACE_DEFS", "").split() + [
                        "-I", os.path.join(ROOT, "include"), "-shared", "-o", so] + srcs + ["-lcudart"])
 import torch  # noqa: E402
 
@@ -78,3 +78,29 @@ if "diag" in sys.argv:
     print(f"  epilogue(i-2) done -> scores(i) ready               mean {lat2.mean():8.0f}  p90 {np.percentile(lat2, 90):8.0f}")
     per = t2[:, 1:, 0] - t2[:, :-1, 0]
     print(f"  item period                              mean {per.mean():8.0f}  p90 {np.percentile(per, 90):8.0f}")
+
+# ---- general (tile-loop) backward, dense: softmax-gradient warp 2 of 64 CTAs
+if "bwd" in sys.argv:
+    pos = torch.arange(S, device="cuda", dtype=torch.int32).repeat(N)
+    inv = 1.0 / (10000.0 ** (torch.arange(0, 64, 2).float() / 64))
+    fr = torch.arange(S).float()[:, None] * inv[None]
+    cos, sin = fr.cos().cuda().contiguous(), fr.sin().cuda().contiguous()
+    dout = (torch.randn(N * S, d, device="cuda") * 0.1).to(torch.bfloat16)
+    out, lse, out_lo = ops.attn_fwd(qkv, mask, H, want_lo=True)
+    for _ in range(3):
+        ops.attn_bwd(dout, qkv, out, lse, mask, H, pos, cos, sin, out_lo=out_lo)
+    torch.cuda.synchronize()
+    buf3 = (ctypes.c_longlong * (64 * 12 * 8))()
+    assert dll.ggpt_debug_bwd_trace(buf3, 64 * 12 * 8) == 0
+    t3 = np.array(buf3[:], dtype=np.int64).reshape(64, 12, 8)
+    tl, cta = t3[:, :8], t3[:, 8]
+    ph = {"prefetch + wait S/dP": (0, 1), "TMEM drain": (1, 2), "P / dS arithmetic": (2, 3), "wait gradient MMAs(it-1) + dQ drain": (3, 4),
+          "P / dS store + fence": (4, 5), "dQ staging + TMA reduce issue": (5, 6)}
+    print("general backward (dense), cycles per query tile, tiles 1..7:")
+    for k, (a, b_) in ph.items():
+        dlt = tl[:, 1:, b_] - tl[:, 1:, a]
+        print(f"  {k:40s} mean {dlt.mean():8.0f}  p90 {np.percentile(dlt, 90):8.0f}")
+    per = tl[:, 1:, 0] - tl[:, :-1, 0]
+    print(f"  tile period                              mean {per.mean():8.0f}")
+    print(f"  CTA: kernel entry -> loop start {(cta[:, 1] - cta[:, 0]).mean():8.0f} | tile loop {(cta[:, 2] - cta[:, 1]).mean():8.0f} | "
+          f"last dQ + epilogue {(cta[:, 3] - cta[:, 2]).mean():8.0f}")
