@@ -750,6 +750,113 @@ __global__ void ce_fwd_kernel(const float* __restrict__ logits, long long ldl, c
   }
 }
 
+// Small vocabularies (V <= 1024, row pitch a multiple of 4 floats: the 756-entry vocabulary of the pre-training configs):
+// one warp per row, the whole row in registers from up to eight 16-byte loads per lane that are all issued before the
+// first use — one pass over the logits with 8 x 512 B in flight per warp, instead of two passes of scalar loads.
+__global__ void ce_fwd_small_kernel(const float* __restrict__ logits, long long ldl, const int* __restrict__ labels,
+                                    const float* __restrict__ wgt, float* __restrict__ row_lse, float* __restrict__ row_loss,
+                                    double* __restrict__ loss_sum, double* __restrict__ wgt_sum, int L, int V,
+                                    float focal_gamma, int* __restrict__ err) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  double local = 0.0, local_w = 0.0;
+  for (int e = blockIdx.x * warps_per_block + (threadIdx.x >> 5); e < L; e += gridDim.x * warps_per_block) {
+    const float* row = logits + static_cast<long long>(e) * ldl;
+    float4 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = (k * 32 + lane) * 4;
+      v[k] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      if (c + 3 < V) {
+        v[k] = *reinterpret_cast<const float4*>(row + c);
+      } else if (c < V) {
+        v[k].x = row[c];
+        if (c + 1 < V) v[k].y = row[c + 1];
+        if (c + 2 < V) v[k].z = row[c + 2];
+      }
+    }
+    float m = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m = fmaxf(m, fmaxf(fmaxf(v[k].x, v[k].y), fmaxf(v[k].z, v[k].w)));
+    m = warp_max(m);
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += (__expf(v[k].x - m) + __expf(v[k].y - m)) + (__expf(v[k].z - m) + __expf(v[k].w - m));
+    s = warp_sum(s);
+    const float lse = m + logf(s);
+    if (lane == 0) {
+      int lab = labels[e];
+      if (lab < 0 || lab >= V) {
+        if (err) atomicExch(err, 2);
+        lab = 0;
+      }
+      const float w = wgt ? wgt[e] : 1.0f;
+      float l = lse - row[lab];
+      if (focal_gamma > 0.f) l *= powf(fmaxf(1.0f - __expf(-l), 0.f), focal_gamma);
+      row_lse[e] = lse;
+      if (row_loss) row_loss[e] = l;
+      local += static_cast<double>(l) * w;
+      local_w += w;
+    }
+  }
+  __shared__ double s_l[32], s_w[32];
+  if (lane == 0) {
+    s_l[threadIdx.x >> 5] = local;
+    s_w[threadIdx.x >> 5] = local_w;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < warps_per_block; ++i) {
+      a += s_l[i];
+      b += s_w[i];
+    }
+    atomicAdd(loss_sum, a);
+    if (wgt_sum) atomicAdd(wgt_sum, b);
+  }
+}
+
+// Same idea for the gradient: all loads of the row first (16 bytes per lane each), then exp / subtract / pack, 8-byte stores.
+__global__ void ce_bwd_small_kernel(const float* __restrict__ logits, long long ldl, const int* __restrict__ labels,
+                                    const float* __restrict__ wgt, const float* __restrict__ row_lse,
+                                    const float* __restrict__ scale, const float* __restrict__ gout,
+                                    __nv_bfloat16* __restrict__ dlogits, long long ldd, int L, int V, int Vpad) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const float g = scale[0] * (gout ? gout[0] : 1.0f);
+  for (int e = blockIdx.x * warps_per_block + (threadIdx.x >> 5); e < L; e += gridDim.x * warps_per_block) {
+    const float* row = logits + static_cast<long long>(e) * ldl;
+    __nv_bfloat16* drow = dlogits + static_cast<long long>(e) * ldd;
+    float4 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = (k * 32 + lane) * 4;
+      v[k] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);      // exp(-inf - lse) = 0 for the pad columns
+      if (c + 3 < V) {
+        v[k] = *reinterpret_cast<const float4*>(row + c);
+      } else if (c < V) {
+        v[k].x = row[c];
+        if (c + 1 < V) v[k].y = row[c + 1];
+        if (c + 2 < V) v[k].z = row[c + 2];
+      }
+    }
+    const float lse = row_lse[e];
+    const int lab = labels[e];
+    const float w = (wgt ? wgt[e] : 1.0f) * g;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = (k * 32 + lane) * 4;
+      if (c < Vpad) {
+        const float o0 = (__expf(v[k].x - lse) - (c == lab ? 1.f : 0.f)) * w;
+        const float o1 = (__expf(v[k].y - lse) - (c + 1 == lab ? 1.f : 0.f)) * w;
+        const float o2 = (__expf(v[k].z - lse) - (c + 2 == lab ? 1.f : 0.f)) * w;
+        const float o3 = (__expf(v[k].w - lse) - (c + 3 == lab ? 1.f : 0.f)) * w;
+        *reinterpret_cast<uint2*>(drow + c) = make_uint2(pack_bf16(o0, o1), pack_bf16(o2, o3));
+      }
+    }
+  }
+}
+
 // dlogits[e,c] = (softmax(logits[e])[c] - [c == label[e]]) * wgt[e] * scale[0] * gout[0]   (bf16, pad columns = 0)
 // (FOCAL is a template flag so that powf's slow path costs the plain cross-entropy kernel no registers)
 template <bool FOCAL>
@@ -1038,6 +1145,11 @@ int ggpt_ce_fwd(const float* logits, long long ldl, const int* labels, const flo
                 double* loss_sum, double* wgt_sum, int L, int V, float focal_gamma, int* err_flag, void* stream) {
   GGPT_REQUIRE(logits && labels && row_lse && loss_sum, "ce_fwd: null pointer");
   if (L <= 0) return 0;
+  if (V <= 1024 && ldl % 4 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0) {
+    ce_fwd_small_kernel<<<grid_for_rows(L, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        logits, ldl, labels, wgt, row_lse, row_loss, loss_sum, wgt_sum, L, V, focal_gamma, err_flag);
+    return check_launch("ce_fwd_small_kernel");
+  }
   ce_fwd_kernel<<<grid_for_rows(L, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, ldl, labels, wgt, row_lse,
                                                                                     row_loss, loss_sum, wgt_sum, L, V,
                                                                                     focal_gamma, err_flag);
@@ -1059,6 +1171,13 @@ int ggpt_ce_bwd(const float* logits, long long ldl, const int* labels, const flo
   GGPT_REQUIRE(logits && labels && row_lse && scale && dlogits, "ce_bwd: null pointer");
   GGPT_REQUIRE(ldd % 8 == 0 && ldd >= ((V + 7) / 8) * 8, "ce_bwd: ldd must be a multiple of 8 covering V");
   if (L <= 0) return 0;
+  const int Vpad8 = ((V + 7) / 8) * 8;
+  if (focal_gamma <= 0.f && V <= 1024 && ldl % 4 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(dlogits) & 7) == 0) {
+    ce_bwd_small_kernel<<<grid_for_rows(L, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        logits, ldl, labels, wgt, row_lse, scale, gout, static_cast<__nv_bfloat16*>(dlogits), ldd, L, V, Vpad8);
+    return check_launch("ce_bwd_small_kernel");
+  }
   if (focal_gamma > 0.f)
     ce_bwd_kernel<true><<<grid_for_rows(L, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         logits, ldl, labels, wgt, row_lse, scale, gout, static_cast<__nv_bfloat16*>(dlogits), ldd, L, V,
