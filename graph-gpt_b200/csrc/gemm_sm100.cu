@@ -744,18 +744,67 @@ static int launch_gemm(const void* A, long long lda, const void* B, long long ld
   else p.num_n_blocks = (p.N + BN - 1) / BN;
   p.num_k_blocks = (p.K + BK - 1) / BK;
   p.b_half_rows = p.N / 2;
-  // split-K only where it is safe (fp32 output that accumulates into a pre-initialised buffer) and useful
-  // (fewer tiles than ~2 waves of SMs while K is long): each split keeps >= 16 k-blocks.
+  // split-K only where it is safe (fp32 output that accumulates into a pre-initialised buffer) and useful (wgrad: K =
+  // tokens is long while M x N has few tiles).  Work items are equal-sized, so what matters is WAVE QUANTISATION: with
+  // 74 CTA pairs, 153 items (the old "about two waves" rule on the o_proj wgrad) run as three waves at 69 % occupancy.
+  // The split factor is therefore the smallest one whose item count fills whole waves best (each split keeps >= 16
+  // k-blocks): o_proj 9 tiles x 8 = 72 items, qkv 27 x 8 = 216, down 36 x 2 = 72, gate|up 72 x 1 — all 97 %.
   p.num_splits = 1;
+  p.kb_per_split = p.num_k_blocks;
   if (EPI == EPI_F32 && p.accumulate) {
-    const int mn_tiles = p.num_m_blocks * p.num_n_blocks;
-    const int want = (2 * num_sms() + mn_tiles - 1) / mn_tiles;
+    static const char* mode_env0 = getenv("GGPT_GEMM_MODE");
+    const bool clustered = p.num_m_blocks >= 2 && !(mode_env0 != nullptr && mode_env0[0] == 's');
+    const int cl = clustered ? 2 : 1;
+    const int slots = num_sms() / cl;                                   // CTAs / CTA pairs resident at once
+    const int tiles = ((p.num_m_blocks + cl - 1) / cl) * p.num_n_blocks;
     const int max_by_k = p.num_k_blocks / 16;
-    int sp = want < max_by_k ? want : max_by_k;
-    if (sp > 1) p.num_splits = sp;
+    // first the best achievable occupancy, then the smallest split factor within 1 % of it that gives every CTA at least
+    // three items (measured: with one or two items per CTA the fp32 epilogue of a tile is poorly overlapped by the next
+    // mainloop — gate|up wgrad 1475 TF/s at three waves, 1290 at one or two), else two, else any
+    auto eval = [&](int sp, int& kb, int& real, long long& waves) -> double {
+      kb = (p.num_k_blocks + sp - 1) / sp;
+      real = (p.num_k_blocks + kb - 1) / kb;                            // no empty splits
+      const long long items = static_cast<long long>(tiles) * real;
+      waves = (items + slots - 1) / slots;
+      return static_cast<double>(items) / static_cast<double>(waves * slots);
+    };
+    const int sp_max = max_by_k < 64 ? max_by_k : 64;
+    double best_eff = 0.0;
+    int best_sp = 1, best_kb = p.num_k_blocks;
+    for (int sp = 1; sp <= sp_max; ++sp) {            // (at most four waves: more, shorter splits only add reduction traffic)
+      int kb, real;
+      long long waves;
+      const double eff = eval(sp, kb, real, waves);
+      if (eff > best_eff && (waves <= 4 || sp == 1)) best_eff = eff;
+    }
+    static const char* waves_env = getenv("GGPT_WGRAD_MIN_WAVES");
+    const int min_waves = waves_env != nullptr ? atoi(waves_env) : 3;
+    bool found = false;
+    for (int pass = 0; pass < 3 && !found; ++pass) {
+      for (int sp = 1; sp <= sp_max; ++sp) {
+        int kb, real;
+        long long waves;
+        const double eff = eval(sp, kb, real, waves);
+        if (eff >= best_eff - 0.01 && (waves <= 4 || sp == 1) && (pass == 2 || waves >= (pass == 0 ? min_waves : 2))) {
+          best_sp = real;
+          best_kb = kb;
+          found = true;
+          break;
+        }
+      }
+    }
+    p.num_splits = best_sp;
+    p.kb_per_split = best_kb;
+    static const char* split_env = getenv("GGPT_WGRAD_SPLIT");      // "twowaves": the previous rule, for A/B runs
+    if (split_env != nullptr && split_env[0] == 't') {
+      const int mn_tiles = p.num_m_blocks * p.num_n_blocks;
+      const int want = (2 * num_sms() + mn_tiles - 1) / mn_tiles;
+      int sp = want < max_by_k ? want : max_by_k;
+      if (sp < 1) sp = 1;
+      p.kb_per_split = (p.num_k_blocks + sp - 1) / sp;
+      p.num_splits = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;
+    }
   }
-  p.kb_per_split = (p.num_k_blocks + p.num_splits - 1) / p.num_splits;
-  p.num_splits = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;   // no empty splits
   // clusters of two CTAs along M share (multicast) the B tile; single m-block problems stay un-clustered
   // (GGPT_GEMM_MODE = single | multicast | pair overrides the choice — a profiling aid)
   static const char* mode_env = getenv("GGPT_GEMM_MODE");
