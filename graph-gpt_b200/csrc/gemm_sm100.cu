@@ -57,6 +57,8 @@ struct GemmParams {
   const float* cos_tab;   // QKV_ROPE: [max_pos, 32]
   const float* sin_tab;
   int rope_cols;          // QKV_ROPE: rotate columns [0, rope_cols) in heads of 64
+  int direct_store;       // bf16 epilogues: every thread stores its row's columns straight from registers, 32 bytes (one
+                          // full sector) per instruction, instead of transposing through the staging buffer
 };
 
 constexpr int BM = 128;
@@ -75,6 +77,17 @@ struct GemmSmem {
   static constexpr int kBarBytes = 256;
   static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kBarBytes + 1024;  // +1024 alignment slack
 };
+
+#ifdef GGPT_ATTN_TRACE      // profiling aid (tools/attn_trace.py gemm): clock64 stamps of epilogue warp 2 / the MMA thread, 32 CTAs x 24 tiles
+__device__ long long g_gemm_trace[32 * 24 * 8];
+#define GEMM_TRACE(slot)                                                                                         \
+  do {                                                                                                           \
+    if (lane == 0 && blockIdx.x < 64 && (blockIdx.x & 1) == 0 && tcount < 24)                                     \
+      g_gemm_trace[((blockIdx.x >> 1) * 24 + tcount) * 8 + (slot)] = clock64();                                   \
+  } while (0)
+#else
+#define GEMM_TRACE(slot) do { } while (0)
+#endif
 
 template <int BN, bool A_MN, bool B_MN, int EPI, int CL, bool PAIR>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -102,6 +115,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int rank = (CL > 1) ? static_cast<int>(cluster_ctarank()) : 0;
   const int item0 = blockIdx.x / CL;
   const int item_stride = gridDim.x / CL;
+  // Item order.  Default: round-robin (item0, item0 + stride, ...).  QKV + RoPE: each cluster takes a CONTIGUOUS range of
+  // tiles with the n-block fastest, i.e. it sweeps the 9 n-blocks of one m-block back to back — the cos / sin rows of the
+  // tile's tokens are then gathered once per m-block instead of once per tile (clock64 trace: the gather was 4.3k of the
+  // epilogue's 10.2k cycles per tile against a 7.5k-cycle mainloop), and the A tile is re-read from L2 while it is hot.
+  constexpr bool kContiguous = (EPI == EPI_QKV_ROPE);
+  const int items_per = (num_tiles + item_stride - 1) / item_stride;
+  const int it_begin = kContiguous ? item0 * items_per : item0;
+  const int it_end = kContiguous ? min(num_tiles, it_begin + items_per) : num_tiles;
+  const int it_step = kContiguous ? 1 : item_stride;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -146,7 +168,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = item0; item < num_tiles; item += item_stride) {
+      for (int item = it_begin; item < it_end; item += it_step) {
         const int tile = item % mn_tiles, split = item / mn_tiles;
         const int m0 = ((tile / p.num_n_blocks) * CL + rank) * BM;
         const int nb = tile % p.num_n_blocks;
@@ -233,11 +255,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int item = item0; item < num_tiles; item += item_stride) {
+      int tcount = 0;
+      for (int item = it_begin; item < it_end; item += it_step, ++tcount) {
         const int split = item / mn_tiles;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
+        GEMM_TRACE(5);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        GEMM_TRACE(6);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -262,6 +287,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             phase ^= 1;
           }
         }
+        GEMM_TRACE(7);
         if (PAIR) tc_commit_pair_mc(&tfull_bar[acc], 3);   // each CTA's epilogue drains its own 128 rows
         else tc_commit(&tfull_bar[acc]);                   // accumulator complete
         if (++acc == 2) {
@@ -390,23 +416,46 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         stage_put(jbase + g, o);
       }
     };
+    // 16 consecutive bf16 columns of this thread's row, packed, as ONE 32-byte store (a full sector)
+    auto st256 = [](__nv_bfloat16* dst, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4, uint32_t a5,
+                    uint32_t a6, uint32_t a7) {
+      asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(a4),
+                   "r"(a5), "r"(a6), "r"(a7)
+                   : "memory");
+    };
+    auto st_bf16_32 = [&](__nv_bfloat16* dst, const uint32_t (&r)[32]) {   // 32 fp32 accumulators -> 32 bf16 columns
+#pragma unroll
+      for (int g = 0; g < 2; ++g)
+        st256(dst + g * 16, pack_bf16(__uint_as_float(r[g * 16 + 0]), __uint_as_float(r[g * 16 + 1])),
+              pack_bf16(__uint_as_float(r[g * 16 + 2]), __uint_as_float(r[g * 16 + 3])),
+              pack_bf16(__uint_as_float(r[g * 16 + 4]), __uint_as_float(r[g * 16 + 5])),
+              pack_bf16(__uint_as_float(r[g * 16 + 6]), __uint_as_float(r[g * 16 + 7])),
+              pack_bf16(__uint_as_float(r[g * 16 + 8]), __uint_as_float(r[g * 16 + 9])),
+              pack_bf16(__uint_as_float(r[g * 16 + 10]), __uint_as_float(r[g * 16 + 11])),
+              pack_bf16(__uint_as_float(r[g * 16 + 12]), __uint_as_float(r[g * 16 + 13])),
+              pack_bf16(__uint_as_float(r[g * 16 + 14]), __uint_as_float(r[g * 16 + 15])));
+    };
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int item = item0; item < num_tiles; item += item_stride) {
+    int tcount = 0;
+    // QKV_ROPE: cos/sin rows of this thread's token — the same for every head and every n-block of the m-block — gathered
+    // (coalesced, through the staging buffer) once per m-block, BEFORE waiting for the accumulator
+    float cc[(EPI == EPI_QKV_ROPE) ? 32 : 1], ss[(EPI == EPI_QKV_ROPE) ? 32 : 1];
+    int rope_m0 = -1;
+    for (int item = it_begin; item < it_end; item += it_step, ++tcount) {
+      if (warp == 2) GEMM_TRACE(0);
       const int tile = item % mn_tiles;
       const int m0 = ((tile / p.num_n_blocks) * CL + rank) * BM;
       const int nb = tile % p.num_n_blocks;
       const int row0 = m0 + quad * 32;                 // first global row of this warp's quadrant
       const int row = row0 + lane;                     // write-phase row of this thread
       const bool row_ok = row < p.M;
-      // QKV_ROPE: cos/sin rows of this thread's token — the same for every head — are gathered (coalesced, through the
-      // staging buffer) BEFORE waiting for the accumulator, so the dependent pos -> table-row loads overlap the mainloop
-      float cc[(EPI == EPI_QKV_ROPE) ? 32 : 1], ss[(EPI == EPI_QKV_ROPE) ? 32 : 1];
       if constexpr (EPI == EPI_QKV_ROPE) {
-        if (nb * BN + half * (BN / 2) < p.rope_cols) {   // warp-uniform
+        if (nb * BN + half * (BN / 2) < p.rope_cols && m0 != rope_m0) {   // warp-uniform
           const int pos = row_ok ? p.pos[row] : 0;
           warp_gather_rows32(p.cos_tab, pos, stg, lane, cc);
           warp_gather_rows32(p.sin_tab, pos, stg, lane, ss);
+          rope_m0 = m0;
         }
       }
       // DGEGLU: saved GeGLU factors of this thread's (row, 4-column) pieces of one 32-column chunk (read-phase layout)
@@ -427,7 +476,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       };
       if constexpr (EPI == EPI_DGEGLU)   // chunk 0's factors are fetched while the mainloop of this tile still runs
         dgeglu_load(reinterpret_cast<const __nv_bfloat16*>(p.gu), half * (BN / 2), f1, f2);
+      if (warp == 2) GEMM_TRACE(1);
       mbar_wait(&tfull_bar[acc], acc_phase);
+      if (warp == 2) GEMM_TRACE(2);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
 
@@ -452,6 +503,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           tmem_ld32(taddr + c, r0);
           tmem_ld32(taddr + c + 32, r1);
           tmem_ld_wait();
+          if (p.direct_store) {
+            if (row_ok && n0 + c < p.N) {
+              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<long long>(row) * p.ldc + n0 + c;
+              st_bf16_32(dst, r0);
+              st_bf16_32(dst + 32, r1);
+            }
+            continue;
+          }
           put_bf16_32(0, r0);
           put_bf16_32(4, r1);
           copy_out_bf16(reinterpret_cast<__nv_bfloat16*>(p.C), p.ldc, n0 + c, p.N);
@@ -536,6 +595,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               ru[j >> 1] = pack_bf16(a2[0], a2[1]);
               actp[hh][j >> 1] = pack_bf16(ac[0], ac[1]);
             }
+            if (p.direct_store) {      // this row's 32 columns of each factor: two 32-byte stores per factor
+              if (row_ok && nh + c + hh * 32 < half_n) {
+                __nv_bfloat16* d1 = gf + static_cast<long long>(row) * p.ldc + nh + c + hh * 32;
+                st256(d1, rg[0], rg[1], rg[2], rg[3], rg[4], rg[5], rg[6], rg[7]);
+                st256(d1 + 16, rg[8], rg[9], rg[10], rg[11], rg[12], rg[13], rg[14], rg[15]);
+                st256(d1 + half_n, ru[0], ru[1], ru[2], ru[3], ru[4], ru[5], ru[6], ru[7]);
+                st256(d1 + half_n + 16, ru[8], ru[9], ru[10], ru[11], ru[12], ru[13], ru[14], ru[15]);
+              }
+              continue;
+            }
             // staging row = [ 32 cols of u*gelu' (64 B) | 32 cols of gelu (64 B) ]; lanes 0-3 of a row group write the first
             // factor, lanes 4-7 the second — 64-byte contiguous pieces, two full sectors each
 #pragma unroll
@@ -556,11 +625,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
             __syncwarp();
           }
+          if (p.direct_store) {
+            if (row_ok && nh + c < half_n) {
+              __nv_bfloat16* da = reinterpret_cast<__nv_bfloat16*>(p.C2) + static_cast<long long>(row) * p.ldc2 + nh + c;
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh)
+              for (int hh = 0; hh < 2; ++hh) {
+                st256(da + hh * 32, actp[hh][0], actp[hh][1], actp[hh][2], actp[hh][3], actp[hh][4], actp[hh][5], actp[hh][6],
+                      actp[hh][7]);
+                st256(da + hh * 32 + 16, actp[hh][8], actp[hh][9], actp[hh][10], actp[hh][11], actp[hh][12], actp[hh][13],
+                      actp[hh][14], actp[hh][15]);
+              }
+            }
+          } else {
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              stage_put(hh * 4 + q, make_uint4(actp[hh][q * 4 + 0], actp[hh][q * 4 + 1], actp[hh][q * 4 + 2], actp[hh][q * 4 + 3]));
+            for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                stage_put(hh * 4 + q, make_uint4(actp[hh][q * 4 + 0], actp[hh][q * 4 + 1], actp[hh][q * 4 + 2], actp[hh][q * 4 + 3]));
+          }
         } else {
 #pragma unroll 1
           for (int hh = 0; hh < 2; ++hh) {                  // inference: act only, 1-MUFU GELU
@@ -574,7 +656,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             put_bf16_32(hh * 4, rg);
           }
         }
-        copy_out_bf16(reinterpret_cast<__nv_bfloat16*>(p.C2), p.ldc2, nh + c, half_n);
+        if (!(p.direct_store && gf != nullptr)) copy_out_bf16(reinterpret_cast<__nv_bfloat16*>(p.C2), p.ldc2, nh + c, half_n);
       } else if constexpr (EPI == EPI_DGEGLU) {
         // acc = dact = d(act); fused GeGLU backward with the factors saved by the forward epilogue:
         //   dgate = dact * gf[:, 0:N] (= u gelu'(g)),  dup = dact * gf[:, N:2N] (= gelu(g))  — two multiplies per element.
@@ -626,25 +708,36 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
       } else if constexpr (EPI == EPI_QKV_ROPE) {
+        // one head (64 columns) per iteration, the rotation pairs (j, j + 32) 16 at a time: two tcgen05.ld x16 per wait keep
+        // the live accumulator values at 32 registers next to the 64 cos / sin values that persist across the m-block;
+        // every thread stores its row's 16 columns as one 32-byte sector
         const int n0 = nb * BN;
 #pragma unroll 1
-        for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 64) {   // one head (64 columns) per iteration
-          uint32_t r1[32], r2[32];
-          tmem_ld32(taddr + c, r1);
-          tmem_ld32(taddr + c + 32, r2);
-          tmem_ld_wait();
-          if ((n0 + c) < p.rope_cols) {
+        for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 64) {
+          const bool rot = (n0 + c) < p.rope_cols;
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<long long>(row) * p.ldc + n0 + c;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float x1 = __uint_as_float(r1[j]);
-              const float x2 = __uint_as_float(r2[j]);
-              r1[j] = __float_as_uint(x1 * cc[j] - x2 * ss[j]);   // q*cos + rotate_half(q)*sin, first half
-              r2[j] = __float_as_uint(x2 * cc[j] + x1 * ss[j]);   // second half
+          for (int jb = 0; jb < 2; ++jb) {
+            uint32_t x1[16], x2[16];
+            tmem_ld16(taddr + c + jb * 16, x1);
+            tmem_ld16(taddr + c + 32 + jb * 16, x2);
+            tmem_ld_wait();
+            if (rot) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float a = __uint_as_float(x1[j]), b = __uint_as_float(x2[j]);
+                x1[j] = __float_as_uint(a * cc[jb * 16 + j] - b * ss[jb * 16 + j]);   // q*cos + rotate_half(q)*sin, first half
+                x2[j] = __float_as_uint(b * cc[jb * 16 + j] + a * ss[jb * 16 + j]);   // second half
+              }
+            }
+            if (row_ok && n0 + c < p.N) {
+              auto pk = [](uint32_t lo, uint32_t hi) { return pack_bf16(__uint_as_float(lo), __uint_as_float(hi)); };
+              st256(dst + jb * 16, pk(x1[0], x1[1]), pk(x1[2], x1[3]), pk(x1[4], x1[5]), pk(x1[6], x1[7]), pk(x1[8], x1[9]),
+                    pk(x1[10], x1[11]), pk(x1[12], x1[13]), pk(x1[14], x1[15]));
+              st256(dst + 32 + jb * 16, pk(x2[0], x2[1]), pk(x2[2], x2[3]), pk(x2[4], x2[5]), pk(x2[6], x2[7]), pk(x2[8], x2[9]),
+                    pk(x2[10], x2[11]), pk(x2[12], x2[13]), pk(x2[14], x2[15]));
             }
           }
-          put_bf16_32(0, r1);
-          put_bf16_32(4, r2);
-          copy_out_bf16(reinterpret_cast<__nv_bfloat16*>(p.C), p.ldc, n0 + c, p.N);
         }
       }
 
@@ -654,6 +747,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (PAIR) mbar_arrive_cluster(&tempty_bar[acc], 0);
         else mbar_arrive(&tempty_bar[acc]);
       }
+      if (warp == 2) GEMM_TRACE(3);
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
@@ -824,6 +918,13 @@ static int dispatch_major(int a_mn, int b_mn, const void* A, long long lda, cons
   return -1;
 }
 
+// direct 32-byte stores need 32-byte aligned rows and whole 64-column chunks (GGPT_GEMM_DIRECT_STORE=0/1 overrides: A/B runs)
+static int want_direct_store(const void* C, long long ldc, int n_cols, int dflt) {
+  static const char* env = getenv("GGPT_GEMM_DIRECT_STORE");
+  const int on = env != nullptr ? (env[0] != '0') : dflt;   // default on: +1..4 % per GEMM, same-box A/B (profiles/r2aq_*)
+  return on && C != nullptr && (reinterpret_cast<uintptr_t>(C) & 31) == 0 && (ldc % 16) == 0 && (n_cols % 64) == 0;
+}
+
 static int check_common(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K) {
   GGPT_REQUIRE(A && B, "gemm: null operand");
   GGPT_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
@@ -839,6 +940,12 @@ using namespace ggpt;
 
 extern "C" {
 
+#ifdef GGPT_ATTN_TRACE
+int ggpt_debug_gemm_trace(long long* out, int n) {
+  return cudaMemcpyFromSymbol(out, ggpt::g_gemm_trace, sizeof(long long) * n) == cudaSuccess ? 0 : -2;
+}
+#endif
+
 int ggpt_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major,
                    void* C, long long ldc, int out_f32, int accumulate, int M, int N, int K, void* stream) {
   if (int rc = check_common(A, lda, B, ldb, M, N, K)) return rc;
@@ -853,6 +960,7 @@ int ggpt_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, 
                 : dispatch_major<128, EPI_F32>(a_mn_major, b_mn_major, A, lda, B, ldb, p, s);
   }
   GGPT_REQUIRE(!accumulate, "gemm: accumulate needs an fp32 output");
+  p.direct_store = want_direct_store(C, ldc, N, 1);
   return wide ? dispatch_major<256, EPI_BF16>(a_mn_major, b_mn_major, A, lda, B, ldb, p, s)
               : dispatch_major<128, EPI_BF16>(a_mn_major, b_mn_major, A, lda, B, ldb, p, s);
 }
@@ -879,6 +987,7 @@ int ggpt_gemm_bf16_geglu(const void* A, long long lda, const void* Wgu, long lon
   GGPT_REQUIRE(ldact % 8 == 0 && (gu == nullptr || ldgu % 8 == 0), "gemm_geglu: ld must be a multiple of 8");
   GemmParams p{};
   p.M = M; p.N = N2; p.K = K; p.C = gu; p.ldc = ldgu; p.C2 = act; p.ldc2 = ldact;
+  p.direct_store = gu != nullptr && want_direct_store(gu, ldgu, N2 / 2, 1) && want_direct_store(act, ldact, N2 / 2, 1);
   return launch_gemm<256, false, false, EPI_GEGLU>(A, lda, Wgu, ldb, p, static_cast<cudaStream_t>(stream));
 }
 
@@ -908,6 +1017,9 @@ int ggpt_gemm_bf16_qkv_rope(const void* A, long long lda, const void* Wqkv, long
   GemmParams p{};
   p.M = M; p.N = N; p.K = K; p.C = qkv; p.ldc = ldc; p.pos = pos; p.cos_tab = cos_tab; p.sin_tab = sin_tab;
   p.rope_cols = rope_cols;
+  GGPT_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 31) == 0 && ldc % 16 == 0,
+               "gemm_qkv_rope: the output must be 32-byte aligned with a row pitch that is a multiple of 16 elements");
+  p.direct_store = 1;
   return launch_gemm<256, false, false, EPI_QKV_ROPE>(A, lda, Wqkv, ldb, p, static_cast<cudaStream_t>(stream));
 }
 

@@ -104,3 +104,30 @@ if "bwd" in sys.argv:
     print(f"  tile period                              mean {per.mean():8.0f}")
     print(f"  CTA: kernel entry -> loop start {(cta[:, 1] - cta[:, 0]).mean():8.0f} | tile loop {(cta[:, 2] - cta[:, 1]).mean():8.0f} | "
           f"last dQ + epilogue {(cta[:, 3] - cta[:, 2]).mean():8.0f}")
+
+# ---- tcgen05 GEMM epilogues: epilogue warp 2 and the MMA thread of 32 leader CTAs, first 24 tiles
+if "gemm" in sys.argv:
+    T, dm, I = 65536, 768, 3072
+    x = (torch.randn(T, dm, device="cuda") * 0.5).to(torch.bfloat16)
+    w_qkv = (torch.randn(3 * dm, dm, device="cuda") * 0.05).to(torch.bfloat16)
+    w_gu = (torch.randn(2 * I, dm, device="cuda") * 0.05).to(torch.bfloat16)
+    w_o = (torch.randn(dm, dm, device="cuda") * 0.05).to(torch.bfloat16)
+    posg = torch.arange(T, device="cuda", dtype=torch.int32) % 1024
+    inv = 1.0 / (10000.0 ** (torch.arange(0, 64, 2).float() / 64))
+    fr = torch.arange(1024).float()[:, None] * inv[None]
+    cosg, sing = fr.cos().cuda().contiguous(), fr.sin().cuda().contiguous()
+    cases = {"plain fwd [T,768]x[768,768]": lambda: ops.gemm(x, w_o),
+             "qkv+rope [T,768]x[2304,768]": lambda: ops.gemm_qkv_rope(x, w_qkv, posg, cosg, sing, 2 * dm),
+             "geglu (training) [T,768]x[6144,768]": lambda: ops.gemm_geglu(x, w_gu, want_gu=True)}
+    for name, fn in cases.items():
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        bufg = (ctypes.c_longlong * (32 * 24 * 8))()
+        assert dll.ggpt_debug_gemm_trace(bufg, 32 * 24 * 8) == 0
+        tg = np.array(bufg[:], dtype=np.int64).reshape(32, 24, 8)[:, 2:8]
+        print(f"{name}: cycles per tile (leader CTAs, tiles 2..7)")
+        print(f"   epilogue warp: prologue (gathers) {np.mean(tg[:, :, 1] - tg[:, :, 0]):7.0f} | wait accumulator {np.mean(tg[:, :, 2] - tg[:, :, 1]):7.0f} | "
+              f"drain + math + stores {np.mean(tg[:, :, 3] - tg[:, :, 2]):7.0f} | tile period {np.mean(tg[:, 1:, 0] - tg[:, :-1, 0]):7.0f}")
+        print(f"   MMA thread   : wait TMEM buffer {np.mean(tg[:, :, 6] - tg[:, :, 5]):7.0f} | mainloop issue {np.mean(tg[:, :, 7] - tg[:, :, 6]):7.0f} | "
+              f"tile period {np.mean(tg[:, 1:, 5] - tg[:, :-1, 5]):7.0f}")
