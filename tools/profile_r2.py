@@ -111,7 +111,7 @@ def main():
         for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"{n:60s} launches {c:4d}  {t / 1e6:9.3f} ms  share {t / total:6.3f}\n")
         f.write(f"total {total / 1e6:.3f} ms over {len(step)} launches\n")
-    ce = next(i for i in range(s2, e2) if names[i].startswith("ce_fwd_kernel"))
+    ce = next(i for i in range(s2, e2) if names[i].startswith("ce_fwd"))
     windows = {"fwd": (s2, 18), "boundary": (ce - 13, 46), "tail": (e2 - 8, 8)}
     rows = []
     for w, (skip, count) in windows.items():
