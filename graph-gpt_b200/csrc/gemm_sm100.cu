@@ -105,7 +105,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* tempty_bar = tfull_bar + 2;        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
   // work items = (m-block group of CL, n-block, k-split); the CTAs of a cluster take consecutive m-blocks
   // k-split is the SLOW index: the CTAs running concurrently work on the same K range of different output tiles, so the
@@ -249,7 +249,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && (!PAIR || rank == 0)) {   // pair mode: the leader issues every MMA for both CTAs
+    // The whole warp runs this loop (warp-uniform control flow and values) and ONE elected lane executes the tcgen05
+    // instructions: descriptors and barrier addresses then live in uniform registers.  Run by lane 0 alone, every MMA
+    // cost ~20 instructions (per-lane descriptor arithmetic + an R2UR / ELECT / branch waterfall into the uniform operands
+    // of UTCHMMA), ~100 per k-block from one thread that shares its scheduler with the epilogue warps.
+#ifdef GGPT_MMA_LANE0      // the previous form, for same-box A/B runs (tools/gemm_ab.sh)
+#define GGPT_MMA_ELECT() true
+#define GGPT_MMA_SYNCWARP() do { } while (0)
+    if (lane == 0 && (!PAIR || rank == 0)) {
+#else
+#define GGPT_MMA_ELECT() elect_one()
+#define GGPT_MMA_SYNCWARP() __syncwarp()
+    if (!PAIR || rank == 0) {                  // pair mode: the leader issues every MMA for both CTAs
+#endif
       constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * BM : BM, BN, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
@@ -276,20 +288,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                         : umma_desc_sw128(sa + kk * 32, 16, 1024);
             const uint64_t bdesc = B_MN ? umma_desc_sw128(sb + kk * 2048, 8192, 1024)
                                         : umma_desc_sw128(sb + kk * 32, 16, 1024);
-            if (PAIR) tc_mma_bf16_pair(d_tmem, adesc, bdesc, idesc, (kb != kb0 || kk != 0) ? 1u : 0u);
-            else tc_mma_bf16(d_tmem, adesc, bdesc, idesc, (kb != kb0 || kk != 0) ? 1u : 0u);
+            if (GGPT_MMA_ELECT()) {
+              if (PAIR) tc_mma_bf16_pair(d_tmem, adesc, bdesc, idesc, (kb != kb0 || kk != 0) ? 1u : 0u);
+              else tc_mma_bf16(d_tmem, adesc, bdesc, idesc, (kb != kb0 || kk != 0) ? 1u : 0u);
+            }
           }
-          if (PAIR) tc_commit_pair_mc(&empty_bar[stage], 3);     // frees the slot in both CTAs of the pair
-          else if (CL > 1) tc_commit_mc(&empty_bar[stage], 3);   // frees the slot in BOTH CTAs (multicast B lands in both)
-          else tc_commit(&empty_bar[stage]);                     // frees the smem slot when these MMAs retire
+          if (GGPT_MMA_ELECT()) {
+            if (PAIR) tc_commit_pair_mc(&empty_bar[stage], 3);     // frees the slot in both CTAs of the pair
+            else if (CL > 1) tc_commit_mc(&empty_bar[stage], 3);   // frees the slot in BOTH CTAs (multicast B lands in both)
+            else tc_commit(&empty_bar[stage]);                     // frees the smem slot when these MMAs retire
+          }
+          GGPT_MMA_SYNCWARP();
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
         GEMM_TRACE(7);
-        if (PAIR) tc_commit_pair_mc(&tfull_bar[acc], 3);   // each CTA's epilogue drains its own 128 rows
-        else tc_commit(&tfull_bar[acc]);                   // accumulator complete
+        if (GGPT_MMA_ELECT()) {
+          if (PAIR) tc_commit_pair_mc(&tfull_bar[acc], 3);   // each CTA's epilogue drains its own 128 rows
+          else tc_commit(&tfull_bar[acc]);                   // accumulator complete
+        }
+        GGPT_MMA_SYNCWARP();
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;

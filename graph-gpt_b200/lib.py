@@ -9,6 +9,7 @@ import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libggpt_b200.so")
+LIB_PATH = os.environ.get("GGPT_LIB_PATH", LIB_PATH)   # profiling aid: an alternative build of the same library
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "ggpt_b200.h")
 
 _CTYPES = {
