@@ -141,7 +141,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   uint64_t* acc_full = bars + 11;   // final accumulators ready
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
   const int tile = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
 #ifdef GGPT_ATTN_TRACE
@@ -224,7 +224,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && n_active > 0) {
+    if (n_active > 0) {                      // whole warp, one elected lane issues (see tc_mma_bf16_e)
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);     // S, dP : K-major x K-major
       constexpr uint32_t idesc_t = umma_idesc_bf16(128, 64, true, true);        // P^T dO, dS^T Q : MN x MN
       constexpr uint32_t idesc_q = umma_idesc_bf16(128, 64, false, true);       // dS K : K-major x MN-major
@@ -238,13 +238,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         const uint32_t aQ = smem_u32(sStr + st_s * 32768), aDO = aQ + 16384;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          tc_mma_bf16(tmem_S, umma_desc_sw128(aQ + kk * 32, 16, 1024), umma_desc_sw128(aK + kk * 32, 16, 1024),
+          tc_mma_bf16_e(tmem_S, umma_desc_sw128(aQ + kk * 32, 16, 1024), umma_desc_sw128(aK + kk * 32, 16, 1024),
                       idesc_s, kk != 0);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          tc_mma_bf16(tmem_dP, umma_desc_sw128(aDO + kk * 32, 16, 1024), umma_desc_sw128(aV + kk * 32, 16, 1024),
+          tc_mma_bf16_e(tmem_dP, umma_desc_sw128(aDO + kk * 32, 16, 1024), umma_desc_sw128(aV + kk * 32, 16, 1024),
                       idesc_s, kk != 0);
-        tc_commit(sdp_full);
+        tc_commit_e(sdp_full);
         if (++st_s == kBwdStages) {
           st_s = 0;
           ph_s ^= 1;
@@ -267,20 +267,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         // dV += P^T dO_i ; dK += dS^T Q_i      (A = P / dS read MN-major: M = keys, K = query rows)
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
-          tc_mma_bf16(tmem_dV, umma_desc_sw128(aP + kk * 2048, 16384, 1024), umma_desc_sw128(aDO + kk * 2048, 8192, 1024),
+          tc_mma_bf16_e(tmem_dV, umma_desc_sw128(aP + kk * 2048, 16384, 1024), umma_desc_sw128(aDO + kk * 2048, 8192, 1024),
                       idesc_t, (it | kk) != 0);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
-          tc_mma_bf16(tmem_dK, umma_desc_sw128(aDS + kk * 2048, 16384, 1024), umma_desc_sw128(aQ + kk * 2048, 8192, 1024),
+          tc_mma_bf16_e(tmem_dK, umma_desc_sw128(aDS + kk * 2048, 16384, 1024), umma_desc_sw128(aQ + kk * 2048, 8192, 1024),
                       idesc_t, (it | kk) != 0);
         // dQ_i(j) = dS K_j                       (A = dS K-major: M = query rows, K = keys; B = K_j MN-major)
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
-          tc_mma_bf16(tmem_dQ, umma_desc_sw128(aDS + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+          tc_mma_bf16_e(tmem_dQ, umma_desc_sw128(aDS + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
                       umma_desc_sw128(aK + kk * 2048, 8192, 1024), idesc_q, kk != 0);
-        tc_commit(pds_empty);
-        tc_commit(&str_empty[st]);
-        if (it + 1 == n_active) tc_commit(acc_full);
+        tc_commit_e(pds_empty);
+        tc_commit_e(&str_empty[st]);
+        if (it + 1 == n_active) tc_commit_e(acc_full);
         if (++st == kBwdStages) st = 0;
       }
     }

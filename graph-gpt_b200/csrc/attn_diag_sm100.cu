@@ -71,7 +71,7 @@ attn_diag_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const DiagParams
   uint64_t* o_full = bars + 10;     // [2]
   uint64_t* slot_free = bars + 12;  // [2] count 4: group finished reading S / O of its slot
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp: provably uniform
   const int total = p.iso_count[0] * p.H;
   if (static_cast<int>(blockIdx.x) >= total) return;   // uniform; nothing allocated yet
   const int n_items = (total - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
@@ -113,7 +113,7 @@ attn_diag_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const DiagParams
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {                                        // whole warp, one elected lane issues (see tc_mma_bf16_e)
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, false, true);
       auto issue_S = [&](int i) {
@@ -124,9 +124,9 @@ attn_diag_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const DiagParams
         const uint32_t aQ = smem_u32(smem + st * kDFStageBytes), aK = aQ + 16384;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          tc_mma_bf16(tmem_base + b * 256, umma_desc_sw128(aQ + kk * 32, 16, 1024), umma_desc_sw128(aK + kk * 32, 16, 1024),
+          tc_mma_bf16_e(tmem_base + b * 256, umma_desc_sw128(aQ + kk * 32, 16, 1024), umma_desc_sw128(aK + kk * 32, 16, 1024),
                       idesc_s, kk != 0);
-        tc_commit(&s_full[b]);
+        tc_commit_e(&s_full[b]);
       };
       auto issue_PV = [&](int i) {
         const int st = i % kDFStages, b = i & 1;
@@ -136,10 +136,10 @@ attn_diag_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const DiagParams
         const uint32_t aP = smem_u32(smem + kDFSmemP + b * 32768);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
-          tc_mma_bf16(tmem_base + b * 256 + 128, umma_desc_sw128(aP + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+          tc_mma_bf16_e(tmem_base + b * 256 + 128, umma_desc_sw128(aP + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
                       umma_desc_sw128(aV + kk * 2048, 8192, 1024), idesc_o, kk != 0);
-        tc_commit(&o_full[b]);
-        tc_commit(&empty[st]);
+        tc_commit_e(&o_full[b]);
+        tc_commit_e(&empty[st]);
       };
       for (int i = 0; i < n_items; ++i) {
         issue_S(i);
@@ -327,7 +327,7 @@ attn_diag_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   uint64_t* acc_full = bars + 8;     // [2]
   uint64_t* acc_empty = bars + 10;   // [2] count 8
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp: provably uniform
   const int total = p.iso_count[0] * p.H;
   if (static_cast<int>(blockIdx.x) >= total) return;
   const int n_items = (total - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
@@ -372,15 +372,15 @@ attn_diag_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {                                        // whole warp, one elected lane issues (see tc_mma_bf16_e)
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
       constexpr uint32_t idesc_t = umma_idesc_bf16(128, 64, true, true);
       constexpr uint32_t idesc_q = umma_idesc_bf16(128, 64, false, true);
       const uint32_t aP = smem_u32(sP), aDS = smem_u32(sDS);
       auto scores_ready = [&](int i) -> bool {
         const int st = i & 1;
-        if (!mbar_try_wait(&full[st], (i >> 1) & 1)) return false;
-        return i < 2 || mbar_try_wait(&acc_empty[st], ((i >> 1) - 1) & 1);   // epilogue of item i-2 drained this slot
+        if (!mbar_try_wait_warp(&full[st], (i >> 1) & 1)) return false;
+        return i < 2 || mbar_try_wait_warp(&acc_empty[st], ((i >> 1) - 1) & 1);   // epilogue of item i-2 drained this slot
       };
       auto issue_scores = [&](int i) {
         const int st = i & 1;
@@ -389,16 +389,16 @@ attn_diag_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         const uint32_t d = tmem_base + st * 256;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          tc_mma_bf16(d, umma_desc_sw128(aQ + kk * 32, 16, 1024), umma_desc_sw128(aK + kk * 32, 16, 1024), idesc_s, kk != 0);
+          tc_mma_bf16_e(d, umma_desc_sw128(aQ + kk * 32, 16, 1024), umma_desc_sw128(aK + kk * 32, 16, 1024), idesc_s, kk != 0);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          tc_mma_bf16(d + 128, umma_desc_sw128(aDO + kk * 32, 16, 1024), umma_desc_sw128(aV + kk * 32, 16, 1024), idesc_s,
+          tc_mma_bf16_e(d + 128, umma_desc_sw128(aDO + kk * 32, 16, 1024), umma_desc_sw128(aV + kk * 32, 16, 1024), idesc_s,
                       kk != 0);
-        tc_commit(&sdp_full[st]);
+        tc_commit_e(&sdp_full[st]);
       };
       auto issue_grads = [&](int i) {
 #ifdef GGPT_ATTN_TRACE
-        if (blockIdx.x < 32 && i >= 8 && i < 24) g_diag_trace[(blockIdx.x * 16 + (i - 8)) * 8 + 5] = clock64();
+        if (lane == 0 && blockIdx.x < 32 && i >= 8 && i < 24) g_diag_trace[(blockIdx.x * 16 + (i - 8)) * 8 + 5] = clock64();
 #endif
         tc_fence_after();
         const int st = i & 1;
@@ -406,23 +406,23 @@ attn_diag_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         const uint32_t d = tmem_base + st * 256;
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)   // dV = P^T dO
-          tc_mma_bf16(d, umma_desc_sw128(aP + kk * 2048, 16384, 1024), umma_desc_sw128(aDO + kk * 2048, 8192, 1024),
+          tc_mma_bf16_e(d, umma_desc_sw128(aP + kk * 2048, 16384, 1024), umma_desc_sw128(aDO + kk * 2048, 8192, 1024),
                       idesc_t, kk != 0);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)   // dK = dS^T Q
-          tc_mma_bf16(d + 64, umma_desc_sw128(aDS + kk * 2048, 16384, 1024), umma_desc_sw128(aQ + kk * 2048, 8192, 1024),
+          tc_mma_bf16_e(d + 64, umma_desc_sw128(aDS + kk * 2048, 16384, 1024), umma_desc_sw128(aQ + kk * 2048, 8192, 1024),
                       idesc_t, kk != 0);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)   // dQ = dS K
-          tc_mma_bf16(d + 128, umma_desc_sw128(aDS + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+          tc_mma_bf16_e(d + 128, umma_desc_sw128(aDS + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
                       umma_desc_sw128(aK + kk * 2048, 8192, 1024), idesc_q, kk != 0);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)   // PK = P K  (row-sum correction, see attn_bwd_sm100.cu)
-          tc_mma_bf16(d + 192, umma_desc_sw128(aP + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+          tc_mma_bf16_e(d + 192, umma_desc_sw128(aP + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
                       umma_desc_sw128(aK + kk * 2048, 8192, 1024), idesc_q, kk != 0);
-        tc_commit(&acc_full[st]);
-        tc_commit(pds_empty);
-        tc_commit(&empty[st]);
+        tc_commit_e(&acc_full[st]);
+        tc_commit_e(pds_empty);
+        tc_commit_e(&empty[st]);
       };
       // Two independent streams of work for the tensor core: the scores of item a (need its stage loaded and the TMEM
       // slot of item a-2 drained by the epilogue warps) and the gradient products of item b (need P / dS of item b).
@@ -438,7 +438,7 @@ attn_diag_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
           ++a;
           progressed = true;
         }
-        if (b < a && mbar_try_wait(pds_full, b & 1)) {
+        if (b < a && mbar_try_wait_warp(pds_full, b & 1)) {
           issue_grads(b);
           ++b;
           progressed = true;

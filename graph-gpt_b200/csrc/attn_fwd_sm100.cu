@@ -182,7 +182,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
   uint64_t* q_empty = bars + 15;   // every score MMA of the current head has retired: Q buffer reusable
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + 1016);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
   // One CTA serves ONE query tile for `heads_per_cta` consecutive heads: the tile plan, the TMEM allocation and the
   // barrier set-up are paid once, and the output epilogue of head h overlaps the Q / K / V loads and the first score MMA
@@ -276,7 +276,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && n_active > 0) {
+    if (n_active > 0) {                      // whole warp, one elected lane issues (see tc_mma_bf16_e)
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, false, true);
       const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
@@ -287,10 +287,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
         const uint32_t aK = smem_u32(sK + st * 16384);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          tc_mma_bf16(tmem_S, umma_desc_sw128(aQ + kk * 32, 16, 1024), umma_desc_sw128(aK + kk * 32, 16, 1024),
+          tc_mma_bf16_e(tmem_S, umma_desc_sw128(aQ + kk * 32, 16, 1024), umma_desc_sw128(aK + kk * 32, 16, 1024),
                       idesc_s, kk != 0);
-        tc_commit(s_full);
-        tc_commit(&k_empty[st]);
+        tc_commit_e(s_full);
+        tc_commit_e(&k_empty[st]);
       };
       int g0 = 0;
       for (int h = h_begin; h < h_end; ++h, g0 += n_active) {
@@ -305,7 +305,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
             tc_fence_after();
             issue_S(g + 1);
           } else {
-            tc_commit(q_empty);             // every score MMA of this head has been issued
+            tc_commit_e(q_empty);             // every score MMA of this head has been issued
           }
           mbar_wait(&v_full[st], (g >> 1) & 1);
           const uint32_t aV = smem_u32(sV + st * 16384);
@@ -315,11 +315,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
             tc_fence_after();
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
-              tc_mma_bf16(tmem_O + hc * 64, umma_desc_sw128(aP + hc * 16384 + kk * 32, 16, 1024),
+              tc_mma_bf16_e(tmem_O + hc * 64, umma_desc_sw128(aP + hc * 16384 + kk * 32, 16, 1024),
                           umma_desc_sw128(aV + (hc * 4 + kk) * 2048, 8192, 1024), idesc_o, (it | kk) != 0);
-            tc_commit(&pv_done[hc]);
+            tc_commit_e(&pv_done[hc]);
           }
-          tc_commit(&v_empty[st]);
+          tc_commit_e(&v_empty[st]);
         }
       }
     }

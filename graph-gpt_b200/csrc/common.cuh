@@ -265,6 +265,22 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uin
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Warp-uniform issue: the whole warp executes the surrounding (uniform) control flow and address arithmetic — which then
+// lives in uniform registers — and ONE elected lane executes the tcgen05 instruction.  Issued from divergent single-lane
+// code every MMA costs ~20 instructions (per-lane descriptor arithmetic + an R2UR / ELECT / branch waterfall).
+__device__ __forceinline__ void tc_mma_bf16_e(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (elect_one()) tc_mma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
+}
+__device__ __forceinline__ void tc_commit_e(uint64_t* bar) {
+  if (elect_one()) tc_commit(bar);
+  __syncwarp();
+}
+// non-blocking barrier test by lane 0, result broadcast: keeps a polling loop warp-uniform
+__device__ __forceinline__ bool mbar_try_wait_warp(uint64_t* bar, uint32_t parity) {
+  int ok = 0;
+  if ((threadIdx.x & 31) == 0) ok = mbar_try_wait(bar, parity) ? 1 : 0;
+  return __shfl_sync(0xffffffffu, ok, 0) != 0;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // 32 lanes x 32 consecutive fp32 columns: thread t of the warp receives lane (base_lane + t).
