@@ -113,6 +113,9 @@ def main():
         f.write(f"total {total / 1e6:.3f} ms over {len(step)} launches\n")
     ce = next(i for i in range(s2, e2) if names[i].startswith("ce_fwd"))
     windows = {"fwd": (s2, 18), "boundary": (ce - 13, 46), "tail": (e2 - 8, 8)}
+    only = [a for a in sys.argv[2:] if a in windows]          # e.g. `profile_r2.py <tag> boundary`: that window only
+    if only:
+        windows = {k: v for k, v in windows.items() if k in only}
     rows = []
     for w, (skip, count) in windows.items():
         rows += capture(tag, w, skip, count)
