@@ -371,9 +371,13 @@ rmsnorm_bwd_bulk_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, co
       if (t0 + s * tstep < T) issue(t0 + s * tstep, s);
   }
   const float inv_d = 1.0f / static_cast<float>(d);
-  float4 dwacc[NV];
+  float4 dwacc[NV], wreg[NV];               // this lane's slice of the norm weight stays in registers for all rows
 #pragma unroll
-  for (int k = 0; k < NV; ++k) dwacc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < NV; ++k) {
+    dwacc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int c = lane * 4 + k * 128;
+    wreg[k] = (c < d) ? __ldg(reinterpret_cast<const float4*>(w + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   int stage = 0;
   uint32_t phase = 0;
   float rstd_next = (t0 < T) ? rstd_in[t0] : 0.f;
@@ -395,7 +399,11 @@ rmsnorm_bwd_bulk_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, co
         gv[k] = make_float4(d01.x, d01.y, d23.x, d23.y);
         dwacc[k].x += gv[k].x * xs[k].x; dwacc[k].y += gv[k].y * xs[k].y;
         dwacc[k].z += gv[k].z * xs[k].z; dwacc[k].w += gv[k].w * xs[k].w;
+#ifdef GGPT_RMSBWD_LDG_W      // the previous form, for same-box A/B runs
         const float4 wv = __ldg(reinterpret_cast<const float4*>(w + c));
+#else
+        const float4 wv = wreg[k];
+#endif
         gv[k].x *= wv.x; gv[k].y *= wv.y; gv[k].z *= wv.z; gv[k].w *= wv.w;
         dot += gv[k].x * xs[k].x + gv[k].y * xs[k].y + gv[k].z * xs[k].z + gv[k].w * xs[k].w;
       }
