@@ -248,6 +248,64 @@ __global__ void add_rmsnorm_fwd_kernel(const float* __restrict__ x_in, const __n
   }
 }
 
+// Same, for d = NV * 128: the row stays in registers between the two phases (the generic kernel re-reads the x' it has just
+// written, through L1) and so do this lane's slices of the norm weight and of colscale for all rows of the warp.
+template <int NV>
+__global__ void add_rmsnorm_fwd_reg_kernel(const float* __restrict__ x_in, const __nv_bfloat16* __restrict__ y, long long ldy,
+                                           const float* __restrict__ colscale, const float* __restrict__ rowscale,
+                                           const float* __restrict__ w, float* __restrict__ x_out,
+                                           __nv_bfloat16* __restrict__ h, float* __restrict__ rstd_out, long long T,
+                                           float eps) {
+  constexpr int d = NV * 128;
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  float4 wreg[NV], cs[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = lane * 4 + k * 128;
+    wreg[k] = __ldg(reinterpret_cast<const float4*>(w + c));
+    cs[k] = colscale != nullptr ? __ldg(reinterpret_cast<const float4*>(colscale + c)) : make_float4(1.f, 1.f, 1.f, 1.f);
+  }
+  for (long long t = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); t < T;
+       t += static_cast<long long>(gridDim.x) * warps_per_block) {
+    const float* xr = x_in + t * d;
+    const __nv_bfloat16* yr = y + t * ldy;
+    float4 xv[NV];
+    uint2 yv[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {          // all loads of the row first
+      const int c = lane * 4 + k * 128;
+      xv[k] = *reinterpret_cast<const float4*>(xr + c);
+      yv[k] = *reinterpret_cast<const uint2*>(yr + c);
+    }
+    const float rs = rowscale != nullptr ? rowscale[t] : 1.0f;
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = lane * 4 + k * 128;
+      const float2 y01 = unpack_bf16(yv[k].x), y23 = unpack_bf16(yv[k].y);
+      float4 o;
+      o.x = fmaf(y01.x, rs * cs[k].x, xv[k].x); o.y = fmaf(y01.y, rs * cs[k].y, xv[k].y);
+      o.z = fmaf(y23.x, rs * cs[k].z, xv[k].z); o.w = fmaf(y23.y, rs * cs[k].w, xv[k].w);
+      *reinterpret_cast<float4*>(x_out + t * d + c) = o;
+      xv[k] = o;
+      ss += o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
+    }
+    ss = warp_sum(ss);
+    const float rstd = rsqrtf(ss / static_cast<float>(d) + eps);
+    if (lane == 0 && rstd_out != nullptr) rstd_out[t] = rstd;
+    if (h == nullptr) continue;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = lane * 4 + k * 128;
+      uint2 o;
+      o.x = pack_bf16(wreg[k].x * (xv[k].x * rstd), wreg[k].y * (xv[k].y * rstd));
+      o.y = pack_bf16(wreg[k].z * (xv[k].z * rstd), wreg[k].w * (xv[k].w * rstd));
+      *reinterpret_cast<uint2*>(h + t * d + c) = o;
+    }
+  }
+}
+
 // dx_out = dresid + rstd * (g - xhat * mean(g * xhat)),  g = dy * w,  xhat = x * rstd;  dw += sum_t dy * xhat
 // Also emits a bf16 copy of dx_out (the A operand of the next dgrad GEMMs).
 // Each lane owns the same columns (lane*4 + k*128) for every row its warp visits, so the row is held in registers
@@ -1047,6 +1105,18 @@ int ggpt_add_rmsnorm_fwd(const float* x_in, const void* y, long long ldy, const 
                          const float* w, float* x_out, void* h, float* rstd, long long T, int d, float eps, void* stream) {
   GGPT_REQUIRE(x_in && y && w && x_out, "add_rmsnorm_fwd: null pointer");
   GGPT_REQUIRE(T > 0 && d % 4 == 0 && ldy % 4 == 0, "add_rmsnorm_fwd: bad sizes");
+  static const bool generic_only = getenv("GGPT_ADD_RMSNORM_GENERIC") != nullptr;     // A/B aid
+  if (!generic_only && (d == 768 || d == 1024 || d == 512 || d == 256)) {
+    const dim3 g(grid_for_rows(T, 8));
+    const __nv_bfloat16* yb = static_cast<const __nv_bfloat16*>(y);
+    __nv_bfloat16* hb = static_cast<__nv_bfloat16*>(h);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (d == 768) add_rmsnorm_fwd_reg_kernel<6><<<g, 256, 0, s>>>(x_in, yb, ldy, colscale, rowscale, w, x_out, hb, rstd, T, eps);
+    else if (d == 1024) add_rmsnorm_fwd_reg_kernel<8><<<g, 256, 0, s>>>(x_in, yb, ldy, colscale, rowscale, w, x_out, hb, rstd, T, eps);
+    else if (d == 512) add_rmsnorm_fwd_reg_kernel<4><<<g, 256, 0, s>>>(x_in, yb, ldy, colscale, rowscale, w, x_out, hb, rstd, T, eps);
+    else add_rmsnorm_fwd_reg_kernel<2><<<g, 256, 0, s>>>(x_in, yb, ldy, colscale, rowscale, w, x_out, hb, rstd, T, eps);
+    return check_launch("add_rmsnorm_fwd_reg_kernel");
+  }
   add_rmsnorm_fwd_kernel<<<grid_for_rows(T, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       x_in, static_cast<const __nv_bfloat16*>(y), ldy, colscale, rowscale, w, x_out, static_cast<__nv_bfloat16*>(h), rstd, T,
       d, eps);
