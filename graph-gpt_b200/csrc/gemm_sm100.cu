@@ -851,6 +851,52 @@ static int launch_gemm_cl(const void* A, long long lda, const void* B, long long
   return check_launch("gemm_kernel");
 }
 
+// Split-K plan of an accumulating fp32 GEMM (wgrad): equal-sized work items, so what matters is wave quantisation over
+// the CTAs (or CTA pairs) resident at once.  First the best achievable occupancy with at most four waves (more, shorter
+// splits only add reduction traffic; every split keeps >= 16 k-blocks), then the smallest split factor within 1 % of it
+// that gives every CTA at least `min_waves` items (measured: with one or two items per CTA the fp32 epilogue of a tile is
+// poorly overlapped by the next mainloop — gate|up wgrad 1475 TF/s at three waves, 1290 at one or two), else two, else any.
+// Pure host arithmetic: ggpt_gemm_split_plan exposes it to the CPU tests.
+static void plan_split_k(int num_m_blocks, int num_n_blocks, int num_k_blocks, int sms, bool clustered, int min_waves,
+                         int* num_splits, int* kb_per_split) {
+  const int cl = clustered ? 2 : 1;
+  const int slots = sms / cl > 0 ? sms / cl : 1;                       // CTAs / CTA pairs resident at once
+  const int tiles = ((num_m_blocks + cl - 1) / cl) * num_n_blocks;
+  const int max_by_k = num_k_blocks / 16;
+  auto eval = [&](int sp, int& kb, int& real, long long& waves) -> double {
+    kb = (num_k_blocks + sp - 1) / sp;
+    real = (num_k_blocks + kb - 1) / kb;                               // no empty splits
+    const long long items = static_cast<long long>(tiles) * real;
+    waves = (items + slots - 1) / slots;
+    return static_cast<double>(items) / static_cast<double>(waves * slots);
+  };
+  const int sp_max = max_by_k < 64 ? max_by_k : 64;
+  double best_eff = 0.0;
+  int best_sp = 1, best_kb = num_k_blocks;
+  for (int sp = 1; sp <= sp_max; ++sp) {
+    int kb, real;
+    long long waves;
+    const double eff = eval(sp, kb, real, waves);
+    if (eff > best_eff && (waves <= 4 || sp == 1)) best_eff = eff;
+  }
+  bool found = false;
+  for (int pass = 0; pass < 3 && !found; ++pass) {
+    for (int sp = 1; sp <= sp_max; ++sp) {
+      int kb, real;
+      long long waves;
+      const double eff = eval(sp, kb, real, waves);
+      if (eff >= best_eff - 0.01 && (waves <= 4 || sp == 1) && (pass == 2 || waves >= (pass == 0 ? min_waves : 2))) {
+        best_sp = real;
+        best_kb = kb;
+        found = true;
+        break;
+      }
+    }
+  }
+  *num_splits = best_sp;
+  *kb_per_split = best_kb;
+}
+
 template <int BN, bool A_MN, bool B_MN, int EPI>
 static int launch_gemm(const void* A, long long lda, const void* B, long long ldb, GemmParams p, cudaStream_t stream) {
   p.num_m_blocks = (p.M + BM - 1) / BM;
@@ -868,47 +914,10 @@ static int launch_gemm(const void* A, long long lda, const void* B, long long ld
   if (EPI == EPI_F32 && p.accumulate) {
     static const char* mode_env0 = getenv("GGPT_GEMM_MODE");
     const bool clustered = p.num_m_blocks >= 2 && !(mode_env0 != nullptr && mode_env0[0] == 's');
-    const int cl = clustered ? 2 : 1;
-    const int slots = num_sms() / cl;                                   // CTAs / CTA pairs resident at once
-    const int tiles = ((p.num_m_blocks + cl - 1) / cl) * p.num_n_blocks;
-    const int max_by_k = p.num_k_blocks / 16;
-    // first the best achievable occupancy, then the smallest split factor within 1 % of it that gives every CTA at least
-    // three items (measured: with one or two items per CTA the fp32 epilogue of a tile is poorly overlapped by the next
-    // mainloop — gate|up wgrad 1475 TF/s at three waves, 1290 at one or two), else two, else any
-    auto eval = [&](int sp, int& kb, int& real, long long& waves) -> double {
-      kb = (p.num_k_blocks + sp - 1) / sp;
-      real = (p.num_k_blocks + kb - 1) / kb;                            // no empty splits
-      const long long items = static_cast<long long>(tiles) * real;
-      waves = (items + slots - 1) / slots;
-      return static_cast<double>(items) / static_cast<double>(waves * slots);
-    };
-    const int sp_max = max_by_k < 64 ? max_by_k : 64;
-    double best_eff = 0.0;
-    int best_sp = 1, best_kb = p.num_k_blocks;
-    for (int sp = 1; sp <= sp_max; ++sp) {            // (at most four waves: more, shorter splits only add reduction traffic)
-      int kb, real;
-      long long waves;
-      const double eff = eval(sp, kb, real, waves);
-      if (eff > best_eff && (waves <= 4 || sp == 1)) best_eff = eff;
-    }
     static const char* waves_env = getenv("GGPT_WGRAD_MIN_WAVES");
-    const int min_waves = waves_env != nullptr ? atoi(waves_env) : 3;
-    bool found = false;
-    for (int pass = 0; pass < 3 && !found; ++pass) {
-      for (int sp = 1; sp <= sp_max; ++sp) {
-        int kb, real;
-        long long waves;
-        const double eff = eval(sp, kb, real, waves);
-        if (eff >= best_eff - 0.01 && (waves <= 4 || sp == 1) && (pass == 2 || waves >= (pass == 0 ? min_waves : 2))) {
-          best_sp = real;
-          best_kb = kb;
-          found = true;
-          break;
-        }
-      }
-    }
-    p.num_splits = best_sp;
-    p.kb_per_split = best_kb;
+    const int max_by_k = p.num_k_blocks / 16;
+    plan_split_k(p.num_m_blocks, p.num_n_blocks, p.num_k_blocks, num_sms(), clustered,
+                 waves_env != nullptr ? atoi(waves_env) : 3, &p.num_splits, &p.kb_per_split);
     static const char* split_env = getenv("GGPT_WGRAD_SPLIT");      // "twowaves": the previous rule, for A/B runs
     if (split_env != nullptr && split_env[0] == 't') {
       const int mn_tiles = p.num_m_blocks * p.num_n_blocks;
@@ -983,6 +992,15 @@ int ggpt_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, 
   p.direct_store = want_direct_store(C, ldc, N, 1);
   return wide ? dispatch_major<256, EPI_BF16>(a_mn_major, b_mn_major, A, lda, B, ldb, p, s)
               : dispatch_major<128, EPI_BF16>(a_mn_major, b_mn_major, A, lda, B, ldb, p, s);
+}
+
+int ggpt_gemm_split_plan(int M, int N, int K, int sm_count, int* num_splits, int* kb_per_split) {
+  GGPT_REQUIRE(M > 0 && N > 0 && K > 0 && sm_count > 0, "gemm_split_plan: bad arguments M=%d N=%d K=%d sm_count=%d", M, N, K, sm_count);
+  GGPT_REQUIRE(num_splits != nullptr && kb_per_split != nullptr, "gemm_split_plan: null output");
+  const int bn = N > 128 ? 256 : 128;
+  const int mb = (M + BM - 1) / BM;
+  plan_split_k(mb, (N + bn - 1) / bn, (K + BK - 1) / BK, sm_count, mb >= 2, 3, num_splits, kb_per_split);
+  return 0;
 }
 
 int ggpt_gemm_bf16_resid(const void* A, long long lda, const void* B, long long ldb, const float* resid,

@@ -52,7 +52,7 @@ def parse_header(path=HEADER_PATH):
 _VALUE_FUNCS = {"ggpt_abi_version", "ggpt_attn_mask_words", "ggpt_attn_max_tiles", "ggpt_euler_paths"}
 # kernels launched per entry point (default 1; 0 = host-only helper) — feeds bench.py's `gpu_launches`
 _LAUNCHES = {"ggpt_last_error": 0, "ggpt_abi_version": 0, "ggpt_device_info": 0, "ggpt_attn_mask_words": 0,
-             "ggpt_head_scratch_ints": 0, "ggpt_euler_paths": 0, "ggpt_attn_max_tiles": 0, "ggpt_attn_mask_build": 4, "ggpt_head_compact": 3, "ggpt_attn_fwd": 2, "ggpt_attn_bwd": 4, "ggpt_ft_head_fwd": 2, "ggpt_ft_intra_fwd": 3, "ggpt_ft_intra_bwd": 3}
+             "ggpt_head_scratch_ints": 0, "ggpt_gemm_split_plan": 0, "ggpt_euler_paths": 0, "ggpt_attn_max_tiles": 0, "ggpt_attn_mask_build": 4, "ggpt_head_compact": 3, "ggpt_attn_fwd": 2, "ggpt_attn_bwd": 4, "ggpt_ft_head_fwd": 2, "ggpt_ft_intra_fwd": 3, "ggpt_ft_intra_bwd": 3}
 _GEMM_FUNCS = {"ggpt_gemm_bf16", "ggpt_gemm_bf16_resid", "ggpt_gemm_bf16_geglu", "ggpt_gemm_bf16_qkv_rope",
                "ggpt_gemm_bf16_dgeglu"}
 

@@ -42,6 +42,12 @@ int ggpt_device_info(int* sm_count, int* cc_major, int* cc_minor);
 int ggpt_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major,
                    void* C, long long ldc, int out_f32, int accumulate, int M, int N, int K, void* stream);
 
+/* Host-only query (no GPU needed): the split-K plan ggpt_gemm_bf16 uses for an accumulating fp32 output of this shape
+ * (weight gradients, K = tokens) on a device with `sm_count` SMs.  The k range is cut into `num_splits` work items of
+ * `kb_per_split` 64-wide k-blocks each (the last one may be shorter); every split keeps >= 16 k-blocks.  Chosen so that
+ * tiles x splits fills whole waves of resident CTAs (CTA pairs when M spans >= 2 row tiles). */
+int ggpt_gemm_split_plan(int M, int N, int K, int sm_count, int* num_splits, int* kb_per_split);
+
 /* out[M,N] (fp32) = resid[M,N] (fp32) + rowscale[m] * colscale[n] * (A[M,K] * B[N,K]^T)
  * colscale (LayerScale lambda_1/lambda_2) and rowscale (DropPath keep-mask / keep-prob) may be NULL.
  * ref: HF:325,331 (residual adds after o_proj / down_proj); utils_graphgpt.py:153-166 (lambda, drop_path). */

@@ -319,3 +319,44 @@ def test_plan_greedy_properties():
         for n in range(len(cu_seq) - 1):
             run = np.cumsum(lengths[seq_graphs[cu_seq[n]:cu_seq[n + 1]]] + 1)
             assert (run[:-1] < mpe).all() and (run[-1] >= mpe or n == len(cu_seq) - 2)
+
+
+def test_wgrad_split_k_plan_fills_whole_waves():
+    """The split-K plan of the weight-gradient GEMMs (host arithmetic in gemm_sm100.cu, queried through the C ABI):
+    covers K exactly, keeps >= 16 k-blocks per split, and on BASELINE configs[1]'s shapes (T = 32768 tokens, 148 SMs,
+    74 CTA pairs) every wgrad runs at >= 97 % wave occupancy — the property the planner exists for."""
+    from graphgpt_b200.lib import lib
+
+    def plan(M, N, K, sms=148):
+        sp, kb = ctypes.c_int(0), ctypes.c_int(0)
+        lib.ggpt_gemm_split_plan(M, N, K, sms, ctypes.addressof(sp), ctypes.addressof(kb))
+        return sp.value, kb.value
+
+    def occupancy(M, N, sp, sms=148):
+        mb, nb = -(-M // 128), -(-N // (256 if N > 128 else 128))
+        cl = 2 if mb >= 2 else 1
+        items, slots = -(-mb // cl) * nb * sp, sms // cl
+        return items / (-(-items // slots) * slots), -(-items // slots)
+
+    T = 32768
+    for name, (M, N) in {"o_proj": (768, 768), "qkv": (2304, 768), "down": (768, 3072), "gate|up": (6144, 768)}.items():
+        sp, kb = plan(M, N, T)
+        nk = T // 64
+        assert kb >= 16 and (sp - 1) * kb < nk <= sp * kb, (name, sp, kb)
+        occ, waves = occupancy(M, N, sp)
+        assert occ >= 0.97 and waves <= 4, (name, sp, kb, occ, waves)
+    # short K: no split possible below 32 k-blocks; tiny problems stay un-split and un-clustered
+    assert plan(768, 768, 1024) == (1, 16)
+    assert plan(128, 128, 64) == (1, 1)
+    # generic properties over random shapes and SM counts
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        M, N = int(rng.integers(1, 9000)), int(rng.integers(1, 9000))
+        K, sms = int(rng.integers(1, 70000)), int(rng.choice([1, 2, 108, 132, 148, 160]))
+        sp, kb = plan(M, N, K, sms)
+        nk = -(-K // 64)
+        assert sp >= 1 and (sp - 1) * kb < nk <= sp * kb, (M, N, K, sms, sp, kb)
+        assert sp == 1 or kb >= 16, (M, N, K, sms, sp, kb)
+        assert sp == 1 or occupancy(M, N, sp, sms)[1] <= 4, (M, N, K, sms, sp, kb)
+    with pytest.raises(RuntimeError, match="bad arguments"):
+        lib.ggpt_gemm_split_plan(0, 1, 1, 148, 0, 0)
