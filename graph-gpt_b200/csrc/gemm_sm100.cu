@@ -905,10 +905,8 @@ static int launch_gemm(const void* A, long long lda, const void* B, long long ld
   p.num_k_blocks = (p.K + BK - 1) / BK;
   p.b_half_rows = p.N / 2;
   // split-K only where it is safe (fp32 output that accumulates into a pre-initialised buffer) and useful (wgrad: K =
-  // tokens is long while M x N has few tiles).  Work items are equal-sized, so what matters is WAVE QUANTISATION: with
-  // 74 CTA pairs, 153 items (the old "about two waves" rule on the o_proj wgrad) run as three waves at 69 % occupancy.
-  // The split factor is therefore the smallest one whose item count fills whole waves best (each split keeps >= 16
-  // k-blocks): o_proj 9 tiles x 8 = 72 items, qkv 27 x 8 = 216, down 36 x 2 = 72, gate|up 72 x 1 — all 97 %.
+  // tokens is long while M x N has few tiles); plan_split_k picks the factor (configs[1]: o_proj 9 tiles x 24, qkv 27 x 8,
+  // down 36 x 6, gate|up 72 x 3 — all 216 items = three waves of the 74 CTA pairs at 97 %).
   p.num_splits = 1;
   p.kb_per_split = p.num_k_blocks;
   if (EPI == EPI_F32 && p.accumulate) {

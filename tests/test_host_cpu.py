@@ -323,7 +323,7 @@ def test_plan_greedy_properties():
 
 def test_wgrad_split_k_plan_fills_whole_waves():
     """The split-K plan of the weight-gradient GEMMs (host arithmetic in gemm_sm100.cu, queried through the C ABI):
-    covers K exactly, keeps >= 16 k-blocks per split, and on BASELINE configs[1]'s shapes (T = 32768 tokens, 148 SMs,
+    covers K exactly, keeps >= 16 k-blocks per split, and on BASELINE configs[1]'s shapes (T = 65536 tokens, 148 SMs,
     74 CTA pairs) every wgrad runs at >= 97 % wave occupancy — the property the planner exists for."""
     from graphgpt_b200.lib import lib
 
@@ -338,13 +338,13 @@ def test_wgrad_split_k_plan_fills_whole_waves():
         items, slots = -(-mb // cl) * nb * sp, sms // cl
         return items / (-(-items // slots) * slots), -(-items // slots)
 
-    T = 32768
+    T = 65536
     for name, (M, N) in {"o_proj": (768, 768), "qkv": (2304, 768), "down": (768, 3072), "gate|up": (6144, 768)}.items():
         sp, kb = plan(M, N, T)
         nk = T // 64
         assert kb >= 16 and (sp - 1) * kb < nk <= sp * kb, (name, sp, kb)
         occ, waves = occupancy(M, N, sp)
-        assert occ >= 0.97 and waves <= 4, (name, sp, kb, occ, waves)
+        assert occ >= 0.97 and waves == 3, (name, sp, kb, occ, waves)
     # short K: no split possible below 32 k-blocks; tiny problems stay un-split and un-clustered
     assert plan(768, 768, 1024) == (1, 16)
     assert plan(128, 128, 64) == (1, 1)
