@@ -14,10 +14,11 @@
 // exactly one key tile, instead of the ~3 an aligned 128-grid gives.  Dense / padded / causal masks have no interior
 // boundaries and fall back to the uniform grid.
 //
-// One CTA per (128-query tile, head, sequence); 6 warps: TMA producer, MMA issuer, 4 softmax warps (one query row
-// per thread).  QK^T and PV run on tcgen05 with accumulators in TMEM; P goes through shared memory (bf16, 128B
-// swizzle) as the A operand of the PV MMA; V is consumed in place as an MN-major B operand.  Two CTAs fit per SM
-// (112 KB smem, 256 TMEM columns each) so one CTA's softmax overlaps the other's MMAs.
+// One CTA per (128-query tile, group of heads, sequence); 10 warps: TMA producer, MMA issuer, 8 softmax warps (two
+// threads per query row, 64 keys each — see the pipeline comment above attn_fwd_kernel).  QK^T and PV run on tcgen05
+// with accumulators in TMEM; P goes through shared memory (bf16, 128B swizzle) as the A operand of the PV MMA; V is
+// consumed in place as an MN-major B operand.  Two CTAs fit per SM (113 KB smem, 256 TMEM columns each) so one CTA's
+// softmax overlaps the other's MMAs.
 #include <stdlib.h>
 
 #include "common.cuh"
