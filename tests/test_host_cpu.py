@@ -360,3 +360,35 @@ def test_wgrad_split_k_plan_fills_whole_waves():
         assert sp == 1 or occupancy(M, N, sp, sms)[1] <= 4, (M, N, K, sms, sp, kb)
     with pytest.raises(RuntimeError, match="bad arguments"):
         lib.ggpt_gemm_split_plan(0, 1, 1, 148, 0, 0)
+
+
+def test_built_library_is_tcgen05_tma_native():
+    """SASS of the built library (cuobjdump, no GPU needed): the GEMM and attention kernels issue tcgen05.mma (UTCHMMA),
+    read accumulators from TMEM (LDTM) and move tiles with TMA (UTMALDG); the fused dgrad+GeGLU epilogue stores by TMA
+    (UTMASTG), the single-pass attention backward reduces dQ by TMA (UTMAREDG), rmsnorm_bwd streams rows with 1-D bulk
+    copies (UBLKCP); there is no legacy mma.sync (HMMA) anywhere."""
+    import re
+    import shutil
+    from graphgpt_b200.lib import LIB_PATH
+    if shutil.which("cuobjdump") is None or shutil.which("cu++filt") is None:
+        pytest.skip("CUDA binary utilities not installed")
+    sass = subprocess.run(["cuobjdump", "-sass", LIB_PATH], capture_output=True, text=True, check=True).stdout
+    per, kern = {}, None
+    for line in sass.splitlines():
+        m = re.match(r"\s*Function : (\S+)", line)
+        if m:
+            kern = m.group(1)
+            per[kern] = set()
+            continue
+        m = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d\s+)?([A-Z][A-Z0-9_]*)", line)
+        if m and kern is not None:
+            per[kern].add(m.group(1))
+    names = subprocess.run(["cu++filt"] + list(per), capture_output=True, text=True, check=True).stdout.splitlines()
+    ops = {}
+    for mangled, name in zip(per, names):
+        ops.setdefault(re.sub(r"^(void )?ggpt::|[<(].*", "", name), set()).update(per[mangled])
+    assert not any(o.startswith(("HMMA", "HGMMA", "IMMA")) for s in ops.values() for o in s)
+    for k in ("gemm_kernel", "attn_fwd_kernel", "attn_bwd_kernel", "attn_diag_fwd_kernel", "attn_diag_bwd_kernel"):
+        assert {"UTCHMMA", "LDTM", "UTMALDG"} <= ops[k], (k, sorted(ops[k] & {"UTCHMMA", "LDTM", "UTMALDG"}))
+    assert "UTMASTG" in ops["gemm_kernel"] and "UTMAREDG" in ops["attn_bwd_kernel"] and "STTM" in ops["attn_fwd_kernel"]
+    assert "UBLKCP" in ops["rmsnorm_bwd_bulk_kernel"]
